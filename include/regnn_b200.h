@@ -1,0 +1,204 @@
+/*
+ * regnn_b200.h -- C ABI of libregnn_b200.so: hand-written sm_100a CUDA kernels for RE-GNN's
+ * relation-embedded message passing (REGraphConv / REGATConv / REGATv2Conv / REMixHopConv).
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its layers call DGL 0.7.1
+ * (`update_all`, `apply_edges`, `edge_softmax`) which dispatches to DGL's C++/CUDA `gspmm` /
+ * `gsddmm` kernels.  Every entry point below cites the reference call site(s) it replaces, as
+ * file:line under /root/reference.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (the PyTorch allocator in our host
+ *     code); nothing is allocated inside the library; scratch space is passed in explicitly and
+ *     sized by the matching *_workspace_bytes() query;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, except
+ *     regnn_csr_build / regnn_etype_permute which synchronise `stream` once to report invalid
+ *     node ids / edge types (one-time graph construction);
+ *   - return value: 0 = REGNN_OK, negative = error; regnn_last_error_string() is thread-local;
+ *   - fp32 values, int32 graph indices, uint8 0-based edge types inside the library; the int64 /
+ *     1-based conventions of the reference (run_regnn.py:94-99, `e_feat - 1`) stop at
+ *     regnn_csr_build / regnn_etype_permute;
+ *   - every reduction has a fixed summation order (no floating-point atomics): results are
+ *     bit-identical run to run.
+ *
+ * Graph layout (built once per graph by regnn_csr_build, kept resident in HBM)
+ *   indptr[N+1], indices[E], eid[E], row[E]   destination-sorted CSR: slot s of row v holds the
+ *                                             in-edge (indices[s] -> v) with edge id eid[s];
+ *                                             slots of a row are ordered by edge id (stable sort)
+ *   indptr_t[N+1], indices_t[E], slot_t[E]    source-sorted view: entry j of row u is the out-edge
+ *                                             (u -> indices_t[j]) stored at CSR slot slot_t[j];
+ *                                             entries of a row are ordered by CSR slot
+ *   etype_csr[E], etype_t[E]                  uint8 0-based edge type per CSR slot / per entry
+ */
+#ifndef REGNN_B200_H_
+#define REGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REGNN_OK 0
+#define REGNN_ERR_INVALID_ARG (-1)
+#define REGNN_ERR_UNSUPPORTED_SHAPE (-2)
+#define REGNN_ERR_CUDA (-3)
+#define REGNN_ERR_WORKSPACE_TOO_SMALL (-4)
+
+#define REGNN_MAX_RELATIONS 255 /* uint8 edge types */
+#define REGNN_MAX_HEADS 32
+
+int regnn_version(void);
+const char* regnn_status_string(int status);
+const char* regnn_last_error_string(void);
+/* Number of thread blocks regnn_* reduction kernels emit partial sums for (sizing helper). */
+int regnn_partial_blocks(int64_t num_rows);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph construction.  Replaces DGL's lazy in-CSR / out-CSR build behind
+ * `dgl.DGLGraph(adjM)` ... `g.to(device)` (run_regnn.py:84-87) and the first `update_all`
+ * (layer/REGraphConv.py:69).  src/dst: int64 [E] in edge-id order (what `g.edges()` returns,
+ * run_regnn.py:95).  Hand-written stable LSD radix sort (8-bit digits) + prefix scans.
+ * Returns REGNN_ERR_INVALID_ARG if any node id is outside [0, N).
+ */
+size_t regnn_csr_build_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int regnn_csr_build(const int64_t* src, const int64_t* dst, int64_t num_nodes, int64_t num_edges,
+                    int32_t* indptr, int32_t* indices, int32_t* eid, int32_t* row,
+                    int32_t* indptr_t, int32_t* indices_t, int32_t* slot_t,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* `edge_weight[e_feat - 1]` indexing (layer/REGraphConv.py:61, REGATConv.py:75, REGATv2Conv.py:143,
+ * REMixHopConv.py:53): converts the reference's 1-based int64 edge types (edge-id order) to uint8
+ * 0-based types in CSR-slot order and in transposed-entry order.
+ * Returns REGNN_ERR_INVALID_ARG if any type is outside [1, num_relations]. */
+int regnn_etype_permute(const int64_t* etype_1based, const int32_t* eid, const int32_t* slot_t,
+                        int64_t num_edges, int num_relations, uint8_t* etype_csr, uint8_t* etype_t,
+                        int32_t* status_scratch /* device int32[1] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Relation-weighted in-degree normalisation:
+ *   w = LeakyReLU_0.01(alpha * theta);  deg[v] = sum_{e in In(v)} w[etype e];
+ *   norm[v] = max(deg[v], 1) ^ exponent
+ * Replaces `update_all(u_mul_e('nones','ew'), sum)` + clamp + pow
+ * (layer/REGraphConv.py:58-75, layer/REMixHopConv.py:50-64; exponent -1: RESAGEConv.py:75-78).
+ * theta: [R] (the [R,1] `edge_weight` parameter).  Row range [row_begin, row_end) lets a rank of a
+ * destination-row partition compute only the rows it owns; deg/norm are indexed by global row id.
+ */
+int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr, const float* theta,
+                        float alpha, int num_relations, float exponent, int64_t row_begin,
+                        int64_t row_end, float* deg, float* norm, void* stream);
+/* Backward of the above: d_theta[r] += alpha * LeakyReLU'(alpha*theta[r]) *
+ *   sum_{e: etype e = r} d_deg[dst e],   d_deg[v] = [deg[v] >= 1] * q * max(deg,1)^(q-1) * d_norm[v].
+ * partials: double [regnn_partial_blocks(row_end-row_begin) * R] scratch.  d_theta is OVERWRITTEN. */
+int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const float* theta,
+                        float alpha, int num_relations, float exponent, int64_t row_begin,
+                        int64_t row_end, const float* deg, const float* d_norm, double* partials,
+                        float* d_theta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Relation-weighted, degree-normalised SpMM (the REGCN / REMixHop aggregation):
+ *   Y[v,:] = norm_dst[v] * sum_{s in row v} w[etype[s]] * norm_src[indices[s]] * X[indices[s],:]
+ * Replaces `feat * norm` -> `update_all(u_mul_e('h','ew'), sum)` -> `rst * norm`
+ * (layer/REGraphConv.py:76,84-98) and, with etype == NULL (w == 1), the un-weighted
+ * `update_all(copy_u, sum)` of layer/REMixHopConv.py:78-82.  norm_src / norm_dst may be NULL (== 1).
+ * The same entry point run on the transposed view (indptr_t, indices_t, etype_t) is the
+ * backward pass w.r.t. X (DGL: gspmm on the reverse graph).
+ * X: [*, F] with leading dimension ldx (floats); Y: rows [row_begin,row_end) written at Y[v*ldy].
+ */
+int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
+                   const float* theta, float alpha, int num_relations, const float* norm_src,
+                   const float* norm_dst, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                   int64_t row_begin, int64_t row_end, int feat, void* stream);
+
+/* Backward of regnn_spmm_fwd w.r.t. the relation weights and the norm vector (norm_src == norm_dst
+ * == norm, the reference's case).  Given G = dL/dY, X, Y and dX (= the transposed regnn_spmm_fwd of G):
+ *   d_norm[v]  = ( <Y[v],G[v]> + <X[v],dX[v]> ) / norm[v]
+ *   d_theta[r] = alpha*LeakyReLU'(alpha*theta[r]) * sum_{e: etype=r} norm[src]norm[dst] <X[src],G[dst]>
+ * (DGL: gsddmm(dot) for the edge-weight gradient + atomic index_put_ of `w[e_feat-1]`; here a
+ * deterministic two-level reduction).  etype == NULL: only d_norm is produced (REMixHop).
+ * norm_sides: bit 0 = the forward scaled the source side by norm, bit 1 = the destination side
+ * (3 for REGraphConv / REMixHopConv; 1 for RESAGEConv, layer/RESAGEConv.py:82; 2 for REGINConv,
+ * layer/REGINConv.py:61); the unscaled side drops out of both formulas.
+ * partials: double [regnn_partial_blocks(rows) * R].  d_theta is OVERWRITTEN; d_norm rows written. */
+int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
+                     const float* theta, float alpha, int num_relations, const float* norm,
+                     int norm_sides, const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* G,
+                     int64_t ldg, const float* dX, int64_t lddx, int64_t row_begin, int64_t row_end,
+                     int feat, double* partials, float* d_theta, float* d_norm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused REGAT layer core (layer/REGATConv.py:71-92): per destination v and head h
+ *   l[e,h] = LeakyReLU_slope( el[src,h] + er[v,h] + w[etype,h] ),  w = LeakyReLU_0.01(alpha*theta)
+ *   a      = softmax over In(v) of l  (per-destination max subtracted, no epsilon)
+ *   out[v,h,:] = sum_e a[e,h] * keep[eid e, h] * feat[src,h,:]
+ * Replaces apply_edges(u_add_v) + index/add/LeakyReLU + edge_softmax (4 kernels) +
+ * update_all(u_mul_e, sum).  etype == NULL drops the relation term (`edge_feats=None`).
+ * keep: optional [E,H] attention-dropout scale (0 or 1/(1-p)) in EDGE-ID order, NULL = none.
+ * attn_out: optional [E,H] output of a*keep in EDGE-ID order (`get_attention`), NULL = skip.
+ * Saves rowmax/rowsum [N,H] for the backward pass.  theta: [R,H].
+ */
+int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
+                  const uint8_t* etype_csr, const float* theta, float alpha, int num_relations,
+                  const float* feat, const float* el, const float* er, float negative_slope,
+                  const float* keep, int num_heads, int head_dim, int64_t row_begin, int64_t row_end,
+                  float* out, float* rowmax, float* rowsum, float* attn_out, void* stream);
+
+/* Backward, destination-major pass.  G = dL/d out.  Produces, per CSR slot, a_csr = a*keep and
+ * dpre_csr = dL/d(el[src]+er[dst]+w) (both [E,H], slot order), d_er [N,H] and d_theta [R,H].
+ * partials: double [regnn_partial_blocks(rows) * R * H]. */
+int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
+                      const uint8_t* etype_csr, const float* theta, float alpha, int num_relations,
+                      const float* feat, const float* el, const float* er, float negative_slope,
+                      const float* keep, const float* out, const float* rowmax, const float* rowsum,
+                      const float* G, int num_heads, int head_dim, int64_t row_begin,
+                      int64_t row_end, float* a_csr, float* dpre_csr, float* d_er, double* partials,
+                      float* d_theta, void* stream);
+
+/* Backward, source-major pass over the transposed view:
+ *   d_feat[u,h,:] = sum_{j in Out(u)} a_csr[slot_t[j],h] * G[indices_t[j],h,:]
+ *   d_el[u,h]     = sum_{j in Out(u)} dpre_csr[slot_t[j],h]          (dpre_csr may be NULL)
+ * (DGL: gspmm on the reverse graph + u_add_v backward reduce). */
+int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
+                      const float* a_csr, const float* dpre_csr, const float* G, int num_heads,
+                      int head_dim, int64_t row_begin, int64_t row_end, float* d_feat, float* d_el,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused REGATv2 layer core (layer/REGATv2Conv.py:133-152):
+ *   l[e,h] = sum_d attn[h,d] * LeakyReLU_slope( fs[src,h,d] + fd[v,h,d] ) + w[etype,h]
+ *   a = edge_softmax(l);  out[v,h,:] = sum_e a*keep * fs[src,h,:]
+ * The [E,H,D] intermediates of the reference are never materialised.
+ */
+int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
+                    const uint8_t* etype_csr, const float* theta, float alpha, int num_relations,
+                    const float* fs, const float* fd, const float* attn, float negative_slope,
+                    const float* keep, int num_heads, int head_dim, int64_t row_begin,
+                    int64_t row_end, float* out, float* rowmax, float* rowsum, float* attn_out,
+                    void* stream);
+
+/* Backward, destination-major pass: a_csr = a*keep, dl_csr = dL/dl (both [E,H] slot order),
+ * d_fd [N,H,D], d_attn [H,D], d_theta [R,H].
+ * partials: double [regnn_partial_blocks(rows) * (R*H + H*D)]. */
+int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
+                        const uint8_t* etype_csr, const float* theta, float alpha,
+                        int num_relations, const float* fs, const float* fd, const float* attn,
+                        float negative_slope, const float* keep, const float* out,
+                        const float* rowmax, const float* rowsum, const float* G, int num_heads,
+                        int head_dim, int64_t row_begin, int64_t row_end, float* a_csr,
+                        float* dl_csr, float* d_fd, float* d_attn, double* partials, float* d_theta,
+                        void* stream);
+
+/* Backward, source-major pass:
+ *   d_fs[u,h,d] = sum_{j in Out(u)} ( a_csr[s,h]*G[v,h,d]
+ *                                   + dl_csr[s,h]*attn[h,d]*LeakyReLU'(fs[u,h,d]+fd[v,h,d]) ),
+ *   s = slot_t[j], v = indices_t[j]. */
+int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
+                        const float* a_csr, const float* dl_csr, const float* fs, const float* fd,
+                        const float* attn, float negative_slope, const float* G, int num_heads,
+                        int head_dim, int64_t row_begin, int64_t row_end, float* d_fs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGNN_B200_H_ */

@@ -1,0 +1,204 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A plain-PyTorch (CPU, fp32 or fp64) restatement of the arithmetic of RE-GNN's relation-embedded
+message-passing layers, written against explicit ``(src, dst, etype, num_nodes)`` arrays in
+edge-id order instead of a DGLGraph.  Gradients come from autograd.
+
+Who may import this: ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` -- as the checker or the timed CPU baseline, never as a
+fallback for ``re_gnn_b200`` (the product path raises when its CUDA library is missing).
+
+Parity status: the reference ships no tests, golden vectors or fixtures, and its arithmetic lives in
+``dgl==0.7.1`` which cannot be installed here.  What pins this oracle instead:
+  * ``tests/golden/*.npz`` were produced by running the reference's own, unmodified
+    ``layer/*.py`` / ``model/*.py`` over ``oracle/dgl_stub`` (a restatement of the DGL *primitives*
+    only: SURVEY.md Appendix B) with ``tests/golden/make_golden.py``;
+    ``tests/test_oracle_golden.py`` checks every function below against them;
+  * ``tests/test_oracle_dense.py`` checks it against an independent dense-adjacency formulation
+    in float64 and against analytic known answers.
+The DGL primitive semantics themselves (u_mul_e/copy_u/u_add_v + sum, edge_softmax) remain
+"parity unpinned": no DGL binary is available to confirm them.
+
+Each function cites the reference lines it follows (paths relative to /root/reference).
+"""
+import torch
+import torch.nn.functional as F
+
+RELATION_SLOPE = 0.01  # nn.LeakyReLU() default used for the relation table in every layer
+
+
+def relation_weight(edge_weight, alpha):
+    """``w = LeakyReLU_0.01(edge_weight * alpha)``  -- layer/REGraphConv.py:58-60,
+    layer/REGATConv.py:72-74, layer/REGATv2Conv.py:140-142, layer/REMixHopConv.py:50-52."""
+    return F.leaky_relu(edge_weight * alpha, RELATION_SLOPE)
+
+
+def edge_relation(edge_weight, alpha, etype):
+    """``ew = w[e_feat - 1]`` (1-based edge types) -- layer/REGraphConv.py:61."""
+    return relation_weight(edge_weight, alpha)[etype - 1]
+
+
+def segment_sum(values, dst, num_nodes):
+    """``update_all(..., fn.sum)``: sum of per-edge messages over the in-edges of each node."""
+    out = torch.zeros((num_nodes,) + tuple(values.shape[1:]), dtype=values.dtype)
+    return out.index_add(0, dst, values)
+
+
+def weighted_degree_norm(ew, dst, num_nodes, exponent=-0.5):
+    """``norm = clamp(sum_in ew, min=1) ** exponent`` -- layer/REGraphConv.py:66-73,
+    layer/REMixHopConv.py:58-62 (exponent -0.5); layer/RESAGEConv.py:78 uses -1."""
+    deg = segment_sum(ew.reshape(-1, 1), dst, num_nodes).squeeze(1)
+    return torch.pow(deg.clamp(min=1), exponent)
+
+
+def edge_softmax(logits, dst, num_nodes):
+    """dgl edge_softmax (norm_by='dst'): per destination, per trailing index; the per-destination
+    maximum is subtracted; no epsilon -- call sites layer/REGATConv.py:88, layer/REGATv2Conv.py:148."""
+    shape = (num_nodes,) + tuple(logits.shape[1:])
+    idx = dst.view((-1,) + (1,) * (logits.dim() - 1)).expand_as(logits)
+    mx = torch.full(shape, float('-inf'), dtype=logits.dtype).scatter_reduce(
+        0, idx, logits.detach(), 'amax', include_self=True)
+    ex = torch.exp(logits - mx[dst])
+    return ex / segment_sum(ex, dst, num_nodes)[dst]
+
+
+# ------------------------------------------------------------------------------------------------
+def regraphconv_forward(src, dst, etype, num_nodes, feat, edge_weight, alpha, weight=None, bias=None,
+                        activation=None, norm=True, in_feats=None, out_feats=None):
+    """layer/REGraphConv.py:52-106 with dropout 0.  ``weight`` is ``[in, out]`` or None."""
+    ew = edge_relation(edge_weight, alpha, etype)                       # :58-62, [E,1]
+    if norm:
+        nrm = weighted_degree_norm(ew, dst, num_nodes).unsqueeze(1)     # :66-75
+        feat = feat * nrm                                               # :76
+    in_feats = feat.shape[1] if in_feats is None else in_feats
+    out_feats = (weight.shape[1] if weight is not None else in_feats) if out_feats is None else out_feats
+    if in_feats > out_feats:                                            # :78-87
+        if weight is not None:
+            feat = feat @ weight
+        rst = segment_sum(feat[src] * ew, dst, num_nodes)
+    else:                                                               # :88-95
+        rst = segment_sum(feat[src] * ew, dst, num_nodes)
+        if weight is not None:
+            rst = rst @ weight
+    if norm:
+        rst = rst * nrm                                                 # :97-98
+    if bias is not None:
+        rst = rst + bias                                                # :100-101
+    if activation is not None:
+        rst = activation(rst)                                           # :103-104
+    return rst
+
+
+def regat_forward(src, dst, etype, num_nodes, feat, attn_l, attn_r, edge_weight, alpha,
+                  negative_slope=0.2, fc_weight=None, res_weight=None, residual_identity=False,
+                  activation=None, return_attention=False):
+    """layer/REGATConv.py:64-100 with dropout 0.  ``fc_weight`` is nn.Linear's ``[H*D, in]`` or None
+    (``use_weight=False`` -> Identity).  ``etype=None`` drops the relation term (:71,:83)."""
+    H, D = attn_l.shape[1], attn_l.shape[2]
+    h = feat
+    f = (h @ fc_weight.t() if fc_weight is not None else h).view(-1, H, D)   # :67
+    el = (f * attn_l).sum(-1, keepdim=True)                                  # :68
+    er = (f * attn_r).sum(-1, keepdim=True)                                  # :69
+    e = el[src] + er[dst]                                                    # :80
+    if etype is not None:
+        e = e + edge_relation(edge_weight, alpha, etype).reshape(-1, H, 1)   # :72-75,:84
+    e = F.leaky_relu(e, negative_slope)                                      # :86
+    a = edge_softmax(e, dst, num_nodes)                                      # :88
+    rst = segment_sum(f[src] * a, dst, num_nodes)                            # :90-92
+    if res_weight is not None:                                               # :94-96
+        rst = rst + (h @ res_weight.t()).view(h.shape[0], -1, D)
+    elif residual_identity:
+        rst = rst + h.view(h.shape[0], -1, D)
+    if activation is not None:
+        rst = activation(rst)
+    return (rst, a) if return_attention else rst
+
+
+def regatv2_forward(src, dst, etype, num_nodes, feat, attn, edge_weight, alpha, negative_slope=0.2,
+                    fc_src=None, fc_dst=None, res_fc=None, residual_identity=False,
+                    activation=None, return_attention=False):
+    """layer/REGATv2Conv.py:103-164 with dropout 0.  ``fc_src`` / ``fc_dst`` / ``res_fc`` are
+    ``(weight[H*D, in], bias[H*D] | None)`` tuples or None (Identity); pass ``fc_dst=fc_src`` for
+    ``share_weights``."""
+    H, D = attn.shape[1], attn.shape[2]
+
+    def lin(p, x):
+        if p is None:
+            return x
+        y = x @ p[0].t()
+        return y + p[1] if p[1] is not None else y
+
+    h = feat
+    fs = lin(fc_src, h).view(-1, H, D)                                       # :123-124
+    fd = lin(fc_dst, h).view(-1, H, D)                                       # :125-130
+    e = F.leaky_relu(fs[src] + fd[dst], negative_slope)                      # :135-136
+    e = (e * attn).sum(-1).unsqueeze(2)                                      # :137
+    if etype is not None:
+        e = e + edge_relation(edge_weight, alpha, etype).reshape(-1, H, 1)   # :139-145
+    a = edge_softmax(e, dst, num_nodes)                                      # :148
+    rst = segment_sum(fs[src] * a, dst, num_nodes)                           # :150-152
+    if res_fc is not None:                                                   # :154-156
+        rst = rst + lin(res_fc, h).view(h.shape[0], -1, D)
+    elif residual_identity:
+        rst = rst + h.view(h.shape[0], -1, D)
+    if activation is not None:
+        rst = activation(rst)
+    return (rst, a) if return_attention else rst
+
+
+def remixhop_forward(src, dst, etype, num_nodes, feats, edge_weight, alpha, weights, p=(0, 1, 2),
+                     activation=None, bn=None):
+    """layer/REMixHopConv.py:48-94 with dropout 0.  ``weights`` maps power j -> nn.Linear weight
+    ``[out, in]``.  The propagation after the highest power is dead code in the reference
+    (:70-82) and is skipped here; ``bn`` is an optional callable (BatchNorm1d)."""
+    ew = edge_relation(edge_weight, alpha, etype)                            # :50-55
+    nrm = weighted_degree_norm(ew, dst, num_nodes).unsqueeze(1)              # :58-64
+    outputs = []
+    for j in range(max(p) + 1):                                              # :70
+        if j in p:
+            outputs.append(feats @ weights[j].t())                          # :74-76
+        if j < max(p):
+            feats = feats * nrm                                              # :78
+            feats = segment_sum(feats[src], dst, num_nodes)                  # :79-81 (copy_u: unweighted)
+            feats = feats * nrm                                              # :82
+    final = torch.cat(outputs, dim=1)                                        # :84
+    if bn is not None:
+        final = bn(final)
+    if activation is not None:
+        final = activation(final)
+    return final
+
+
+def resage_forward(src, dst, etype, num_nodes, feat, edge_weight, alpha, weight=None, bias=None,
+                   activation=None, norm=True):
+    """layer/RESAGEConv.py:55-114 (dropout 0; ``in_feats <= out_feats`` branch order is irrelevant
+    to the maths): source-side norm with exponent -1, no destination-side norm, ``+ feat_root``."""
+    feat_root = feat @ weight if weight is not None else feat               # :60-63 (weight_root unused, Q9)
+    ew = edge_relation(edge_weight, alpha, etype)
+    if norm:
+        feat = feat * weighted_degree_norm(ew, dst, num_nodes, -1.0).unsqueeze(1)   # :72-82
+    rst = segment_sum(feat[src] * ew, dst, num_nodes)
+    if weight is not None:
+        rst = rst @ weight
+    rst = rst + feat_root                                                    # :106
+    if bias is not None:
+        rst = rst + bias
+    if activation is not None:
+        rst = activation(rst)
+    return rst
+
+
+# ------------------------------------------------------------------------------------------------
+# Callers (model/*.py) restated on top of the layer functions: used for the epoch-time CPU baseline.
+def regcn_model_forward(src, dst, etype, num_nodes, features_list, params, alpha, n_layers,
+                        activation=F.elu):
+    """model/REGCN.py:35-46 with dropout 0.  ``params``: dict with ``fc`` (list of (W,b)),
+    ``layers`` (list of dicts edge_weight/weight/bias), ``out`` (W,b)."""
+    h = torch.cat([x @ w.t() + b for (w, b), x in zip(params['fc'], features_list)], 0)
+    for l in range(n_layers):
+        lp = params['layers'][l]
+        act = activation if 0 < l < n_layers - 1 else None
+        h = regraphconv_forward(src, dst, etype, num_nodes, h, lp['edge_weight'], alpha,
+                                lp.get('weight'), lp.get('bias'), act)
+    w, b = params['out']
+    return h @ w.t() + b, h

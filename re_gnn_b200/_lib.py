@@ -1,0 +1,75 @@
+"""ctypes binding of ``libregnn_b200.so`` (C ABI declared in ``include/regnn_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a
+``RuntimeError`` is raised.  Nothing here touches ``oracle/``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libregnn_b200.so')
+
+_p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int
+_f32 = ctypes.c_float
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/regnn_b200.h one to one
+SIGNATURES = {
+    'regnn_version': (_i32, []),
+    'regnn_status_string': (ctypes.c_char_p, [_i32]),
+    'regnn_last_error_string': (ctypes.c_char_p, []),
+    'regnn_partial_blocks': (_i32, [_i64]),
+    'regnn_csr_build_workspace_bytes': (_sz, [_i64, _i64]),
+    'regnn_csr_build': (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    'regnn_etype_permute': (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
+    'regnn_wdeg_norm_fwd': (_i32, [_p, _p, _p, _f32, _i32, _f32, _i64, _i64, _p, _p, _p]),
+    'regnn_wdeg_norm_bwd': (_i32, [_p, _p, _p, _f32, _i32, _f32, _i64, _i64, _p, _p, _p, _p, _p]),
+    'regnn_spmm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i32, _p]),
+    'regnn_spmm_bwd_w': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
+                                _i64, _i64, _i32, _p, _p, _p, _p]),
+    'regnn_gat_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
+                             _p, _p, _p, _p, _p]),
+    'regnn_gat_bwd_dst': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p,
+                                 _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    'regnn_gat_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i64, _p, _p, _p]),
+    'regnn_gatv2_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
+                               _p, _p, _p, _p, _p]),
+    'regnn_gatv2_bwd_dst': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p,
+                                   _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    'regnn_gatv2_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once) and returns the ctypes handle; raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'libregnn_b200.so is missing (%s). Build it with `python -m re_gnn_b200.build` or '
+            '`__graft_entry__.build()`; re_gnn_b200 has no CPU or eager fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Calls a status-returning entry point; raises RuntimeError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.regnn_last_error_string().decode() or lib.regnn_status_string(rc).decode()
+        raise RuntimeError('%s failed (%d: %s): %s' % (name, rc, lib.regnn_status_string(rc).decode(), msg))
+
+
+def partial_blocks(rows):
+    return load().regnn_partial_blocks(int(rows))

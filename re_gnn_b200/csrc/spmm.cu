@@ -1,0 +1,476 @@
+// REGCN / REMixHop aggregation kernels: relation-weighted in-degree norm, the fused
+// norm * (relation-weighted SpMM) * norm, and the deterministic backward reductions.
+// Reference call sites: layer/REGraphConv.py:58-98, layer/REMixHopConv.py:50-82.
+//
+// All of these are gather-bound (HBM / L2 bandwidth): one source row of 4F bytes per edge.
+// Mapping: a group of G lanes (G*4 floats >= one 128-bit column slice of the row) owns one
+// destination row; 32/G rows per warp, 8 warps per block.  The G lanes read the row's column
+// indices / edge types coalesced, broadcast them with shuffles, and issue U*C independent 128-bit
+// row loads per lane before the FMAs (memory-level parallelism).  Per-row sums run in slot order:
+// no atomics, bit-identical run to run.
+#include "common.cuh"
+
+namespace regnn {
+
+struct SpmmArgs {
+  const int32_t* indptr;
+  const int32_t* indices;
+  const uint8_t* etype;
+  const float* theta;
+  float alpha;
+  int R;
+  const float* norm_src;
+  const float* norm_dst;
+  const float* X;
+  int64_t ldx;
+  float* Y;
+  int64_t ldy;
+  int64_t row_begin, row_end;
+  int F;
+};
+
+template <int VW> struct Vec;
+template <> struct Vec<4> {
+  using T = float4;
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ T load(const float* p) { return ldg4(p); }
+  static __device__ __forceinline__ void store(float* p, T v) { st4(p, v); }
+  static __device__ __forceinline__ void fma(T& a, float s, T v) { fma4(a, s, v); }
+  static __device__ __forceinline__ float dot(T a, T b) { return dot4(a, b); }
+  static __device__ __forceinline__ T scaled(T a, float s) { scale4(a, s); return a; }
+};
+template <> struct Vec<1> {
+  using T = float;
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, T v) { *p = v; }
+  static __device__ __forceinline__ void fma(T& a, float s, T v) { a = fmaf(s, v, a); }
+  static __device__ __forceinline__ float dot(T a, T b) { return a * b; }
+  static __device__ __forceinline__ T scaled(T a, float s) { return a * s; }
+};
+
+template <int C> struct Unroll { static constexpr int U = C <= 2 ? 4 : (C <= 4 ? 2 : 1); };
+
+// ---- forward / backward-w.r.t.-X -------------------------------------------------------------
+template <int G, int C, int VW>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_kernel(SpmmArgs a) {
+  using V = Vec<VW>;
+  using T = typename V::T;
+  constexpr int U = Unroll<C>::U;
+  constexpr int GPW = 32 / G;
+  __shared__ float w_s[256];
+  if (a.etype != nullptr) {
+    for (int i = threadIdx.x; i < a.R; i += blockDim.x) w_s[i] = leaky(a.theta[i] * a.alpha, kRelationSlope);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % G, grp = lane / G;
+  const int64_t v = a.row_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * GPW + grp;
+  const bool row_ok = v < a.row_end;
+  int s0 = 0, len = 0;
+  if (row_ok) {
+    s0 = a.indptr[v];
+    len = a.indptr[v + 1] - s0;
+  }
+  const int maxlen = (G == 32) ? len : warp_max_int(len);
+
+  T acc[C];
+  bool col_ok[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    acc[k] = V::zero();
+    col_ok[k] = (lg + k * G) * VW < a.F;
+  }
+  const float* xcol = a.X + (size_t)lg * VW;
+
+  for (int base = 0; base < maxlen; base += G) {
+    int idx = 0;
+    float coef = 0.f;
+    if (base + lg < len) {
+      const int s = s0 + base + lg;
+      idx = a.indices[s];
+      coef = a.etype != nullptr ? w_s[a.etype[s]] : 1.f;
+      if (a.norm_src != nullptr) coef *= __ldg(a.norm_src + idx);
+    }
+    const int cnt = min(G, maxlen - base);
+    for (int j = 0; j < cnt; j += U) {
+      int sidx[U];
+      float sc[U];
+      T x[U][C];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = min(j + u, G - 1);
+        sidx[u] = __shfl_sync(0xffffffffu, idx, jj, G);
+        sc[u] = __shfl_sync(0xffffffffu, coef, jj, G);
+        const bool valid = base + j + u < len && j + u < G;
+        if (!valid) sc[u] = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+          x[u][k] = (valid && col_ok[k]) ? V::load(xcol + (size_t)sidx[u] * a.ldx + (size_t)k * G * VW)
+                                         : V::zero();
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < C; ++k) V::fma(acc[k], sc[u], x[u][k]);
+    }
+  }
+  if (row_ok) {
+    const float nd = a.norm_dst != nullptr ? a.norm_dst[v] : 1.f;
+    float* y = a.Y + (size_t)v * a.ldy + (size_t)lg * VW;
+#pragma unroll
+    for (int k = 0; k < C; ++k)
+      if (col_ok[k]) V::store(y + (size_t)k * G * VW, V::scaled(acc[k], nd));
+  }
+}
+
+// ---- per-block reduction of lane-local relation bins ------------------------------------------
+// bins: [warps][R][32] floats (lane-local running sums), scratch: [warps][R] doubles.
+__device__ __forceinline__ void reduce_bins(const float* bins, double* scratch, int R,
+                                            double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncwarp();
+  for (int r = 0; r < R; ++r) {
+    double t = (double)bins[((size_t)warp * R + r) * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) scratch[warp * R + r] = t;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) s += scratch[w * R + r];
+    out[r] = s;
+  }
+}
+
+struct SpmmBwdArgs {
+  const int32_t* indptr;
+  const int32_t* indices;
+  const uint8_t* etype;
+  int R;
+  const float* norm;
+  int sides;  // bit 0: source side scaled by norm, bit 1: destination side
+  const float* X;  int64_t ldx;
+  const float* Y;  int64_t ldy;
+  const float* G;  int64_t ldg;
+  const float* dX; int64_t lddx;
+  int64_t row_begin, row_end;
+  int F;
+  double* partials;
+  float* d_norm;
+};
+
+// Destination-major pass: d_norm rows and (WEIGHTED) the per-relation sums of
+// norm[src]*norm[dst]*<X[src], G[dst]>.  Persistent grid; each warp walks row groups in a fixed order.
+template <int G, int C, int VW, bool WEIGHTED>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_bwd_w_kernel(SpmmBwdArgs a) {
+  using V = Vec<VW>;
+  using T = typename V::T;
+  constexpr int U = Unroll<C>::U;
+  constexpr int GPW = 32 / G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* scratch = reinterpret_cast<double*>(smem_raw);                      // [warps][R]
+  float* bins = reinterpret_cast<float*>(scratch + kWarpsPerBlock * a.R);     // [warps][R][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % G, grp = lane / G;
+  float* mybins = bins + (size_t)warp * a.R * 32 + lane;
+  if (WEIGHTED)
+    for (int r = 0; r < a.R; ++r) mybins[r * 32] = 0.f;
+
+  bool col_ok[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) col_ok[k] = (lg + k * G) * VW < a.F;
+  const int64_t rows = a.row_end - a.row_begin;
+  const int64_t ngroups = (rows + GPW - 1) / GPW;
+
+  for (int64_t rg = (int64_t)blockIdx.x * kWarpsPerBlock + warp; rg < ngroups;
+       rg += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t v = a.row_begin + rg * GPW + grp;
+    const bool row_ok = v < a.row_end;
+    int s0 = 0, len = 0;
+    float nv = 1.f;
+    T g[C];
+    float p = 0.f;
+    if (row_ok) {
+      s0 = a.indptr[v];
+      len = a.indptr[v + 1] - s0;
+      nv = a.norm != nullptr ? a.norm[v] : 1.f;
+    }
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      g[k] = V::zero();
+      if (row_ok && col_ok[k]) {
+        const size_t c = (size_t)(lg + k * G) * VW;
+        g[k] = V::load(a.G + (size_t)v * a.ldg + c);
+        if (a.sides & 2) p += V::dot(V::load(a.Y + (size_t)v * a.ldy + c), g[k]);
+        if (a.sides & 1) p += V::dot(V::load(a.X + (size_t)v * a.ldx + c), V::load(a.dX + (size_t)v * a.lddx + c));
+      }
+    }
+    p = group_sum<G>(p);
+    if (row_ok && lg == 0 && a.d_norm != nullptr) a.d_norm[v] = p / nv;
+
+    if (WEIGHTED) {
+#pragma unroll
+      for (int k = 0; k < C; ++k) g[k] = V::scaled(g[k], (a.sides & 2) ? nv : 1.f);
+      const int maxlen = (G == 32) ? len : warp_max_int(len);
+      const float* xcol = a.X + (size_t)lg * VW;
+      for (int base = 0; base < maxlen; base += G) {
+        int idx = 0, et = 0;
+        float ns = 0.f;
+        if (base + lg < len) {
+          const int s = s0 + base + lg;
+          idx = a.indices[s];
+          et = a.etype[s];
+          ns = (a.norm != nullptr && (a.sides & 1)) ? __ldg(a.norm + idx) : 1.f;
+        }
+        const int cnt = min(G, maxlen - base);
+        for (int j = 0; j < cnt; j += U) {
+          int sidx[U], set[U];
+          float sn[U];
+          T x[U][C];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int jj = min(j + u, G - 1);
+            sidx[u] = __shfl_sync(0xffffffffu, idx, jj, G);
+            set[u] = __shfl_sync(0xffffffffu, et, jj, G);
+            sn[u] = __shfl_sync(0xffffffffu, ns, jj, G);
+            const bool valid = base + j + u < len && j + u < G;
+            if (!valid) sn[u] = 0.f;
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+              x[u][k] = (valid && col_ok[k]) ? V::load(xcol + (size_t)sidx[u] * a.ldx + (size_t)k * G * VW)
+                                             : V::zero();
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float d = 0.f;
+#pragma unroll
+            for (int k = 0; k < C; ++k) d += V::dot(x[u][k], g[k]);
+            mybins[set[u] * 32] += sn[u] * d;  // lane-local bin: fixed order, conflict-free
+          }
+        }
+      }
+    }
+  }
+  if (WEIGHTED) reduce_bins(bins, scratch, a.R, a.partials + (size_t)blockIdx.x * a.R);
+}
+
+// ---- relation-weighted in-degree norm ------------------------------------------------------------
+__device__ __forceinline__ float norm_from_deg(float deg, float exponent) {
+  const float c = fmaxf(deg, 1.f);
+  if (exponent == -0.5f) return 1.f / sqrtf(c);
+  if (exponent == -1.f) return 1.f / c;
+  return powf(c, exponent);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+wdeg_norm_fwd_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restrict__ etype,
+                     const float* __restrict__ theta, float alpha, int R, float exponent,
+                     int64_t row_begin, int64_t row_end, float* __restrict__ deg,
+                     float* __restrict__ norm) {
+  constexpr int G = 8;
+  __shared__ float w_s[256];
+  for (int i = threadIdx.x; i < R; i += blockDim.x) w_s[i] = leaky(theta[i] * alpha, kRelationSlope);
+  __syncthreads();
+  const int lg = threadIdx.x % G;
+  const int64_t v = row_begin + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  float acc = 0.f;
+  if (v < row_end) {
+    const int s1 = indptr[v + 1];
+    for (int s = indptr[v] + lg; s < s1; s += G) acc += w_s[etype[s]];
+  }
+  acc = group_sum<G>(acc);
+  if (v < row_end && lg == 0) {
+    if (deg != nullptr) deg[v] = acc;
+    norm[v] = norm_from_deg(acc, exponent);
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+wdeg_norm_bwd_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restrict__ etype, int R,
+                     float exponent, int64_t row_begin, int64_t row_end,
+                     const float* __restrict__ deg, const float* __restrict__ d_norm,
+                     double* __restrict__ partials) {
+  constexpr int G = 8, GPW = 32 / G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* scratch = reinterpret_cast<double*>(smem_raw);
+  float* bins = reinterpret_cast<float*>(scratch + kWarpsPerBlock * R);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % G, grp = lane / G;
+  float* mybins = bins + (size_t)warp * R * 32 + lane;
+  for (int r = 0; r < R; ++r) mybins[r * 32] = 0.f;
+  const int64_t rows = row_end - row_begin;
+  const int64_t ngroups = (rows + GPW - 1) / GPW;
+  for (int64_t rg = (int64_t)blockIdx.x * kWarpsPerBlock + warp; rg < ngroups;
+       rg += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t v = row_begin + rg * GPW + grp;
+    if (v < row_end) {
+      const float d = deg[v];
+      // clamp(min=1) passes the gradient at deg == 1 (PyTorch semantics)
+      const float dd = d >= 1.f ? exponent * powf(fmaxf(d, 1.f), exponent - 1.f) * d_norm[v] : 0.f;
+      const int s1 = indptr[v + 1];
+      for (int s = indptr[v] + lg; s < s1; s += G) mybins[etype[s] * 32] += dd;
+    }
+  }
+  reduce_bins(bins, scratch, R, partials + (size_t)blockIdx.x * R);
+}
+
+// ---- dispatch ---------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+struct Shape { int G, C, VW; };
+
+// Picks lanes-per-row G, 128-bit (or scalar) chunks per lane C.  Returns false if F is too wide.
+static bool pick_shape(int F, bool vec_ok, Shape* s) {
+  if (vec_ok && F % 4 == 0) {
+    const int f4 = F / 4;
+    int G = 32;
+    if (f4 <= 4) G = 4;
+    else if (f4 <= 8) G = 8;
+    else if (f4 <= 16) G = 16;
+    else if (f4 % 32 != 0 && f4 % 16 == 0 && f4 / 16 <= 3) G = 16;  // e.g. F=192: 16 lanes x 3
+    int C = (f4 + G - 1) / G;
+    if (C > 8) return false;
+    if (C > 4) C = 8;
+    *s = {G, C, 4};
+    return true;
+  }
+  int G = 32;
+  if (F <= 4) G = 4;
+  else if (F <= 8) G = 8;
+  else if (F <= 16) G = 16;
+  int C = (F + G - 1) / G;
+  if (C > 8) return false;
+  if (C > 4) C = 8;
+  *s = {G, C, 1};
+  return true;
+}
+
+#define REGNN_DISPATCH_GC(G_, C_, VW_, CALL)                    \
+  if (sh.G == G_ && sh.C == C_ && sh.VW == VW_) {               \
+    constexpr int G = G_, C = C_, VW = VW_;                     \
+    CALL;                                                       \
+    launched = true;                                            \
+  }
+#define REGNN_DISPATCH_SHAPES(CALL)                                                            \
+  REGNN_DISPATCH_GC(4, 1, 4, CALL) REGNN_DISPATCH_GC(8, 1, 4, CALL) REGNN_DISPATCH_GC(16, 1, 4, CALL) \
+  REGNN_DISPATCH_GC(16, 2, 4, CALL) REGNN_DISPATCH_GC(16, 3, 4, CALL)                          \
+  REGNN_DISPATCH_GC(32, 1, 4, CALL) REGNN_DISPATCH_GC(32, 2, 4, CALL) REGNN_DISPATCH_GC(32, 3, 4, CALL) \
+  REGNN_DISPATCH_GC(32, 4, 4, CALL) REGNN_DISPATCH_GC(32, 8, 4, CALL)                          \
+  REGNN_DISPATCH_GC(4, 1, 1, CALL) REGNN_DISPATCH_GC(8, 1, 1, CALL) REGNN_DISPATCH_GC(16, 1, 1, CALL) \
+  REGNN_DISPATCH_GC(32, 1, 1, CALL) REGNN_DISPATCH_GC(32, 2, 1, CALL) REGNN_DISPATCH_GC(32, 3, 1, CALL) \
+  REGNN_DISPATCH_GC(32, 4, 1, CALL) REGNN_DISPATCH_GC(32, 8, 1, CALL)
+
+}  // namespace regnn
+
+using namespace regnn;
+
+extern "C" int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr,
+                                   const float* theta, float alpha, int num_relations,
+                                   float exponent, int64_t row_begin, int64_t row_end, float* deg,
+                                   float* norm, void* stream) {
+  REGNN_REQUIRE(indptr && etype_csr && theta && norm, REGNN_ERR_INVALID_ARG, "wdeg_norm_fwd: null pointer");
+  REGNN_REQUIRE(num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS, REGNN_ERR_UNSUPPORTED_SHAPE,
+                "num_relations=%d outside [1,%d]", num_relations, REGNN_MAX_RELATIONS);
+  const int64_t rows = row_end - row_begin;
+  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "wdeg_norm_fwd: empty/negative row range");
+  if (rows == 0) return REGNN_OK;
+  const int threads = kWarpsPerBlock * 32;
+  const int64_t blocks = (rows * 8 + threads - 1) / threads;
+  wdeg_norm_fwd_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      indptr, etype_csr, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
+  return check_launch("regnn_wdeg_norm_fwd");
+}
+
+static size_t bins_smem_bytes(int R) { return (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float)); }
+
+extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr,
+                                   const float* theta, float alpha, int num_relations,
+                                   float exponent, int64_t row_begin, int64_t row_end,
+                                   const float* deg, const float* d_norm, double* partials,
+                                   float* d_theta, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  REGNN_REQUIRE(indptr && etype_csr && theta && deg && d_norm && partials && d_theta,
+                REGNN_ERR_INVALID_ARG, "wdeg_norm_bwd: null pointer");
+  const int R = num_relations;
+  REGNN_REQUIRE(R >= 1 && R <= 200, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,200]", R);
+  const int64_t rows = row_end - row_begin;
+  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "wdeg_norm_bwd: negative row range");
+  const int nb = partial_blocks(rows);
+  const size_t smem = bins_smem_bytes(R);
+  int rc = set_smem(wdeg_norm_bwd_kernel, smem);
+  if (rc != REGNN_OK) return rc;
+  wdeg_norm_bwd_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent,
+                                                                   row_begin, row_end, deg, d_norm, partials);
+  launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
+  return check_launch("regnn_wdeg_norm_bwd");
+}
+
+extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
+                              const float* theta, float alpha, int num_relations,
+                              const float* norm_src, const float* norm_dst, const float* X,
+                              int64_t ldx, float* Y, int64_t ldy, int64_t row_begin,
+                              int64_t row_end, int feat, void* stream) {
+  REGNN_REQUIRE(indptr && indices && X && Y, REGNN_ERR_INVALID_ARG, "spmm_fwd: null pointer");
+  REGNN_REQUIRE(etype == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd: etype without theta");
+  REGNN_REQUIRE(etype == nullptr || (num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS),
+                REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,%d]", num_relations, REGNN_MAX_RELATIONS);
+  REGNN_REQUIRE(feat >= 1 && ldx >= feat && ldy >= feat, REGNN_ERR_INVALID_ARG, "spmm_fwd: bad feature width / leading dimension");
+  const int64_t rows = row_end - row_begin;
+  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "spmm_fwd: negative row range");
+  if (rows == 0) return REGNN_OK;
+  const bool vec_ok = aligned16(X) && aligned16(Y) && ldx % 4 == 0 && ldy % 4 == 0;
+  Shape sh;
+  REGNN_REQUIRE(pick_shape(feat, vec_ok, &sh), REGNN_ERR_UNSUPPORTED_SHAPE,
+                "spmm_fwd: feature width %d too wide (max 1024 aligned / 256 unaligned)", feat);
+  SpmmArgs a{indptr, indices, etype, theta, alpha, num_relations, norm_src, norm_dst, X, ldx, Y, ldy,
+             row_begin, row_end, feat};
+  const int rows_per_block = kWarpsPerBlock * (32 / sh.G);
+  const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+  bool launched = false;
+  REGNN_DISPATCH_SHAPES((spmm_kernel<G, C, VW><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(a)))
+  REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: no kernel for G=%d C=%d VW=%d", sh.G, sh.C, sh.VW);
+  return check_launch("regnn_spmm_fwd");
+}
+
+extern "C" int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
+                                const float* theta, float alpha, int num_relations,
+                                const float* norm, int norm_sides, const float* X, int64_t ldx, const float* Y,
+                                int64_t ldy, const float* Gd, int64_t ldg, const float* dX,
+                                int64_t lddx, int64_t row_begin, int64_t row_end, int feat,
+                                double* partials, float* d_theta, float* d_norm, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  REGNN_REQUIRE(indptr && indices && X && Y && Gd && dX, REGNN_ERR_INVALID_ARG, "spmm_bwd_w: null pointer");
+  const bool weighted = etype != nullptr;
+  const int R = weighted ? num_relations : 1;
+  REGNN_REQUIRE(!weighted || (theta && partials && d_theta), REGNN_ERR_INVALID_ARG, "spmm_bwd_w: null relation buffers");
+  REGNN_REQUIRE(R >= 1 && R <= 200, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,200]", R);
+  REGNN_REQUIRE(feat >= 1 && ldx >= feat && ldy >= feat && ldg >= feat && lddx >= feat, REGNN_ERR_INVALID_ARG,
+                "spmm_bwd_w: bad feature width / leading dimension");
+  const int64_t rows = row_end - row_begin;
+  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "spmm_bwd_w: negative row range");
+  const bool vec_ok = aligned16(X) && aligned16(Y) && aligned16(Gd) && aligned16(dX) && ldx % 4 == 0 &&
+                      ldy % 4 == 0 && ldg % 4 == 0 && lddx % 4 == 0;
+  Shape sh;
+  REGNN_REQUIRE(pick_shape(feat, vec_ok, &sh), REGNN_ERR_UNSUPPORTED_SHAPE,
+                "spmm_bwd_w: feature width %d too wide", feat);
+  SpmmBwdArgs a{indptr, indices, etype, R, norm, norm != nullptr ? (norm_sides & 3) : 0, X, ldx, Y, ldy, Gd, ldg, dX, lddx, row_begin, row_end,
+                feat, partials, d_norm};
+  const int nb = partial_blocks(rows);
+  const size_t smem = weighted ? bins_smem_bytes(R) : 16;
+  bool launched = false;
+  int rc = REGNN_OK;
+  if (weighted) {
+    REGNN_DISPATCH_SHAPES((rc = set_smem(spmm_bwd_w_kernel<G, C, VW, true>, smem),
+                           spmm_bwd_w_kernel<G, C, VW, true><<<nb, kWarpsPerBlock * 32, smem, stream>>>(a)))
+  } else {
+    REGNN_DISPATCH_SHAPES((spmm_bwd_w_kernel<G, C, VW, false><<<nb, kWarpsPerBlock * 32, smem, stream>>>(a)))
+  }
+  if (rc != REGNN_OK) return rc;
+  REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_w: no kernel for G=%d C=%d VW=%d", sh.G, sh.C, sh.VW);
+  if (weighted) launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
+  return check_launch("regnn_spmm_bwd_w");
+}

@@ -1,0 +1,138 @@
+"""``torch.autograd.Function`` wrappers that stitch the CUDA operators into autograd.
+
+The backward formulas are those of SURVEY.md Appendix A (derived from the reference's layer code:
+layer/REGraphConv.py:52-106, REGATConv.py:64-100, REGATv2Conv.py:103-164, REMixHopConv.py:48-94);
+all reductions are executed by the deterministic kernels in ``re_gnn_b200/csrc``.
+"""
+import torch
+
+from . import ops
+
+
+class _WDegNorm(torch.autograd.Function):
+    """norm = max(sum_in LeakyReLU_0.01(alpha*theta)[etype], 1) ** exponent."""
+
+    @staticmethod
+    def forward(ctx, graph, etv, theta, alpha, exponent):
+        csr = graph.csr()
+        deg, norm = ops.wdeg_norm_fwd(csr, etv[0], theta, alpha, exponent)
+        ctx.graph, ctx.etv, ctx.alpha, ctx.exponent = graph, etv, alpha, exponent
+        ctx.save_for_backward(theta, deg)
+        return norm
+
+    @staticmethod
+    def backward(ctx, d_norm):
+        theta, deg = ctx.saved_tensors
+        d_theta = ops.wdeg_norm_bwd(ctx.graph.csr(), ctx.etv[0], theta, ctx.alpha, ctx.exponent, deg,
+                                    d_norm.contiguous())
+        return None, None, d_theta.view_as(theta), None, None
+
+
+def weighted_degree_norm(graph, etv, theta, alpha, exponent=-0.5):
+    return _WDegNorm.apply(graph, etv, theta, alpha, exponent)
+
+
+class _Propagate(torch.autograd.Function):
+    """Y = norm (.) A_w (norm (.) X);  theta=None -> un-weighted (A_w = A);  norm=None -> no scaling.
+    ``sides``: bit 0 scales the source side, bit 1 the destination side (3 = both, the REGCN case)."""
+
+    @staticmethod
+    def forward(ctx, graph, etv, x, theta, alpha, norm, sides):
+        csr = graph.csr()
+        weighted = theta is not None
+        ns = norm if sides & 1 else None
+        nd = norm if sides & 2 else None
+        y = ops.spmm(csr['indptr'], csr['indices'], etv[0] if weighted else None, theta, alpha, ns, nd, x)
+        ctx.graph, ctx.etv, ctx.alpha, ctx.weighted, ctx.has_norm = graph, etv, alpha, weighted, norm is not None
+        ctx.sides = sides
+        ctx.save_for_backward(x, y, theta if weighted else None, norm)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, theta, norm = ctx.saved_tensors
+        csr = ctx.graph.csr()
+        g = g.contiguous()
+        need_x = ctx.needs_input_grad[2]
+        need_theta = ctx.weighted and ctx.needs_input_grad[3]
+        need_norm = ctx.has_norm and ctx.needs_input_grad[5]
+        dx = d_theta = d_norm = None
+        if need_x or need_norm:
+            # transposed SpMM: dX[u] = norm[u] * sum_{e in Out(u)} w_e * norm[dst] * G[dst]
+            # (on the transposed view the roles of the two sides swap)
+            ns = norm if ctx.sides & 2 else None
+            nd = norm if ctx.sides & 1 else None
+            dx = ops.spmm(csr['indptr_t'], csr['indices_t'], ctx.etv[1] if ctx.weighted else None, theta,
+                          ctx.alpha, ns, nd, g)
+        if need_theta or need_norm:
+            if dx is None:
+                dx = torch.zeros_like(x)
+            d_theta, d_norm = ops.spmm_bwd_w(csr, ctx.etv[0] if need_theta else None, theta if need_theta else None,
+                                             ctx.alpha, norm, x, y, g, dx, sides=ctx.sides)
+            if d_theta is not None:
+                d_theta = d_theta.view_as(theta)
+        return None, None, (dx if need_x else None), d_theta, None, (d_norm if need_norm else None), None
+
+
+def propagate(graph, etv, x, theta, alpha, norm, sides=3):
+    return _Propagate.apply(graph, etv, x, theta, alpha, norm, sides if norm is not None else 0)
+
+
+class _GatAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, graph, etv, feat, el, er, theta, alpha, slope, keep, want_attn):
+        csr = graph.csr()
+        et = etv[0] if etv is not None else None
+        out, rowmax, rowsum, attn = ops.gat_fwd(csr, et, theta if et is not None else None, alpha, feat, el, er,
+                                                slope, keep, want_attn)
+        ctx.graph, ctx.et, ctx.alpha, ctx.slope = graph, et, alpha, slope
+        ctx.save_for_backward(feat, el, er, theta if et is not None else None, keep, out, rowmax, rowsum)
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+            return out, attn
+        return out, None
+
+    @staticmethod
+    def backward(ctx, g, _g_attn=None):
+        feat, el, er, theta, keep, out, rowmax, rowsum = ctx.saved_tensors
+        csr = ctx.graph.csr()
+        g = g.contiguous()
+        a_csr, dpre_csr, d_er, d_theta = ops.gat_bwd_dst(csr, ctx.et, theta, ctx.alpha, feat, el, er, ctx.slope,
+                                                         keep, out, rowmax, rowsum, g)
+        d_feat, d_el = ops.gat_bwd_src(csr, a_csr, dpre_csr, g)
+        return (None, None, d_feat, d_el, d_er, d_theta.view_as(theta) if d_theta is not None else None,
+                None, None, None, None)
+
+
+def gat_aggregate(graph, etv, feat, el, er, theta, alpha, slope, keep=None, want_attn=False):
+    return _GatAggregate.apply(graph, etv, feat, el, er, theta, alpha, slope, keep, want_attn)
+
+
+class _GatV2Aggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn):
+        csr = graph.csr()
+        et = etv[0] if etv is not None else None
+        out, rowmax, rowsum, a = ops.gatv2_fwd(csr, et, theta if et is not None else None, alpha, fs, fd, attn,
+                                               slope, keep, want_attn)
+        ctx.graph, ctx.et, ctx.alpha, ctx.slope = graph, et, alpha, slope
+        ctx.save_for_backward(fs, fd, attn, theta if et is not None else None, keep, out, rowmax, rowsum)
+        if want_attn:
+            ctx.mark_non_differentiable(a)
+            return out, a
+        return out, None
+
+    @staticmethod
+    def backward(ctx, g, _g_attn=None):
+        fs, fd, attn, theta, keep, out, rowmax, rowsum = ctx.saved_tensors
+        csr = ctx.graph.csr()
+        g = g.contiguous()
+        a_csr, dl_csr, d_fd, d_attn, d_theta = ops.gatv2_bwd_dst(csr, ctx.et, theta, ctx.alpha, fs, fd, attn,
+                                                                 ctx.slope, keep, out, rowmax, rowsum, g)
+        d_fs = ops.gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, ctx.slope, g)
+        return (None, None, d_fs, d_fd, d_attn.view_as(attn),
+                d_theta.view_as(theta) if d_theta is not None else None, None, None, None, None)
+
+
+def gatv2_aggregate(graph, etv, fs, fd, attn, theta, alpha, slope, keep=None, want_attn=False):
+    return _GatV2Aggregate.apply(graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn)

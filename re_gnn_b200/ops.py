@@ -1,0 +1,207 @@
+"""Raw operator wrappers: one Python function per C-ABI entry point of ``libregnn_b200.so``.
+
+Each wrapper allocates its outputs with the PyTorch caching allocator, passes raw device pointers
+and the current CUDA stream, and raises on any error.  No arithmetic happens here and there is no
+CPU branch: tensors must live on a CUDA device.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('re_gnn_b200 operators need CUDA tensors (got %s); there is no CPU path' % t.device)
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _rows(rows, n):
+    return (0, n) if rows is None else (int(rows[0]), int(rows[1]))
+
+
+def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None):
+    """deg[v] = sum_in w[etype], norm = max(deg,1)^exponent -> (deg[N], norm[N])."""
+    theta = _f32(theta).view(-1)
+    n = csr['indptr'].numel() - 1
+    rb, re = _rows(rows, n)
+    deg = torch.empty(n, dtype=torch.float32, device=theta.device)
+    norm = torch.empty(n, dtype=torch.float32, device=theta.device)
+    with torch.cuda.device(theta.device):
+        _lib.call('regnn_wdeg_norm_fwd', _ptr(csr['indptr']), _ptr(et_csr), _ptr(theta), float(alpha),
+                  theta.numel(), float(exponent), rb, re, _ptr(deg), _ptr(norm), _stream())
+    return deg, norm
+
+
+def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None):
+    theta = _f32(theta).view(-1)
+    d_norm = _f32(d_norm)
+    n = csr['indptr'].numel() - 1
+    rb, re = _rows(rows, n)
+    r = theta.numel()
+    partials = torch.empty(_lib.partial_blocks(re - rb) * r, dtype=torch.float64, device=theta.device)
+    d_theta = torch.empty(r, dtype=torch.float32, device=theta.device)
+    with torch.cuda.device(theta.device):
+        _lib.call('regnn_wdeg_norm_bwd', _ptr(csr['indptr']), _ptr(et_csr), _ptr(theta), float(alpha), r,
+                  float(exponent), rb, re, _ptr(deg), _ptr(d_norm), _ptr(partials), _ptr(d_theta), _stream())
+    return d_theta
+
+
+def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None):
+    """Y[v] = norm_dst[v] * sum_s w[etype[s]] * norm_src[indices[s]] * X[indices[s]] over rows."""
+    x = _f32(x)
+    n = indptr.numel() - 1
+    rb, re = _rows(rows, n)
+    f = x.shape[1]
+    theta = _f32(theta).view(-1) if theta is not None else None
+    if out is None:
+        out = torch.empty((n, f), dtype=torch.float32, device=x.device)
+        if (rb, re) != (0, n):
+            out.zero_()
+    with torch.cuda.device(x.device):
+        _lib.call('regnn_spmm_fwd', _ptr(indptr), _ptr(indices), _ptr(etype) if theta is not None else None,
+                  _ptr(theta), float(alpha), theta.numel() if theta is not None else 0, _ptr(norm_src),
+                  _ptr(norm_dst), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rb, re, f, _stream())
+    return out
+
+
+def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3):
+    """-> (d_theta[R] or None, d_norm[N] or None).  sides: bit0 source side scaled, bit1 destination."""
+    x, y, g, dx = _f32(x), _f32(y), _f32(g), _f32(dx)
+    n = csr['indptr'].numel() - 1
+    rb, re = _rows(rows, n)
+    weighted = theta is not None
+    theta = _f32(theta).view(-1) if weighted else None
+    r = theta.numel() if weighted else 0
+    partials = torch.empty(max(_lib.partial_blocks(re - rb) * r, 1), dtype=torch.float64, device=x.device)
+    d_theta = torch.empty(r, dtype=torch.float32, device=x.device) if weighted else None
+    d_norm = torch.zeros(n, dtype=torch.float32, device=x.device) if norm is not None else None
+    with torch.cuda.device(x.device):
+        _lib.call('regnn_spmm_bwd_w', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(et_csr) if weighted else None,
+                  _ptr(theta), float(alpha), r, _ptr(norm), int(sides), _ptr(x), x.stride(0), _ptr(y), y.stride(0),
+                  _ptr(g), g.stride(0), _ptr(dx), dx.stride(0), rb, re, x.shape[1], _ptr(partials),
+                  _ptr(d_theta), _ptr(d_norm), _stream())
+    return d_theta, d_norm
+
+
+def _rel(theta, et_csr):
+    if theta is None or et_csr is None:
+        return None, None, 0
+    theta = _f32(theta)
+    return theta, et_csr, theta.shape[0]
+
+
+def gat_fwd(csr, et_csr, theta, alpha, feat, el, er, slope, keep=None, want_attn=False, rows=None):
+    feat, el, er, keep = _f32(feat), _f32(el), _f32(er), _f32(keep)
+    n, h, d = feat.shape
+    rb, re = _rows(rows, n)
+    theta, et_csr, r = _rel(theta, et_csr)
+    dev = feat.device
+    out = torch.empty_like(feat) if (rb, re) == (0, n) else torch.zeros_like(feat)
+    rowmax = torch.zeros((n, h), dtype=torch.float32, device=dev)
+    rowsum = torch.zeros((n, h), dtype=torch.float32, device=dev)
+    e = csr['indices'].numel()
+    attn = torch.zeros((e, h), dtype=torch.float32, device=dev) if want_attn else None
+    with torch.cuda.device(dev):
+        _lib.call('regnn_gat_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
+                  _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep), h, d,
+                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(attn), _stream())
+    return out, rowmax, rowsum, attn
+
+
+def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowmax, rowsum, g, rows=None):
+    feat, el, er, keep, g = _f32(feat), _f32(el), _f32(er), _f32(keep), _f32(g)
+    n, h, d = feat.shape
+    rb, re = _rows(rows, n)
+    theta, et_csr, r = _rel(theta, et_csr)
+    dev = feat.device
+    e = csr['indices'].numel()
+    a_csr = torch.empty((e, h), dtype=torch.float32, device=dev)
+    dpre_csr = torch.empty((e, h), dtype=torch.float32, device=dev)
+    d_er = torch.zeros((n, h), dtype=torch.float32, device=dev)
+    partials = torch.empty(max(_lib.partial_blocks(re - rb) * r * h, 1), dtype=torch.float64, device=dev)
+    d_theta = torch.empty((r, h), dtype=torch.float32, device=dev) if r else None
+    with torch.cuda.device(dev):
+        _lib.call('regnn_gat_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
+                  _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep),
+                  _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dpre_csr),
+                  _ptr(d_er), _ptr(partials), _ptr(d_theta), _stream())
+    return a_csr, dpre_csr, d_er, d_theta
+
+
+def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None):
+    g = _f32(g)
+    n, h, d = g.shape
+    rb, re = _rows(rows, n)
+    dev = g.device
+    d_feat = torch.empty_like(g) if (rb, re) == (0, n) else torch.zeros_like(g)
+    d_el = torch.zeros((n, h), dtype=torch.float32, device=dev) if dpre_csr is not None else None
+    with torch.cuda.device(dev):
+        _lib.call('regnn_gat_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
+                  _ptr(a_csr), _ptr(dpre_csr), _ptr(g), h, d, rb, re, _ptr(d_feat), _ptr(d_el), _stream())
+    return d_feat, d_el
+
+
+def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_attn=False, rows=None):
+    fs, fd, keep = _f32(fs), _f32(fd), _f32(keep)
+    attn = _f32(attn).view(-1)
+    n, h, d = fd.shape
+    rb, re = _rows(rows, n)
+    theta, et_csr, r = _rel(theta, et_csr)
+    dev = fs.device
+    out = torch.empty_like(fd) if (rb, re) == (0, n) else torch.zeros_like(fd)
+    rowmax = torch.zeros((n, h), dtype=torch.float32, device=dev)
+    rowsum = torch.zeros((n, h), dtype=torch.float32, device=dev)
+    e = csr['indices'].numel()
+    att = torch.zeros((e, h), dtype=torch.float32, device=dev) if want_attn else None
+    with torch.cuda.device(dev):
+        _lib.call('regnn_gatv2_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
+                  _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep), h, d,
+                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(att), _stream())
+    return out, rowmax, rowsum, att
+
+
+def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, rowmax, rowsum, g, rows=None):
+    fs, fd, keep, g = _f32(fs), _f32(fd), _f32(keep), _f32(g)
+    attn = _f32(attn).view(-1)
+    n, h, d = fd.shape
+    rb, re = _rows(rows, n)
+    theta, et_csr, r = _rel(theta, et_csr)
+    dev = fs.device
+    e = csr['indices'].numel()
+    a_csr = torch.empty((e, h), dtype=torch.float32, device=dev)
+    dl_csr = torch.empty((e, h), dtype=torch.float32, device=dev)
+    d_fd = torch.empty_like(fd) if (rb, re) == (0, n) else torch.zeros_like(fd)
+    d_attn = torch.empty(h * d, dtype=torch.float32, device=dev)
+    partials = torch.empty(_lib.partial_blocks(re - rb) * (r * h + h * d), dtype=torch.float64, device=dev)
+    d_theta = torch.empty((r, h), dtype=torch.float32, device=dev) if r else None
+    with torch.cuda.device(dev):
+        _lib.call('regnn_gatv2_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
+                  _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep),
+                  _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dl_csr),
+                  _ptr(d_fd), _ptr(d_attn), _ptr(partials), _ptr(d_theta), _stream())
+    return a_csr, dl_csr, d_fd, d_attn, d_theta
+
+
+def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
+    fs, fd, g = _f32(fs), _f32(fd), _f32(g)
+    attn = _f32(attn).view(-1)
+    n, h, d = fs.shape
+    rb, re = _rows(rows, n)
+    d_fs = torch.empty_like(fs) if (rb, re) == (0, n) else torch.zeros_like(fs)
+    with torch.cuda.device(fs.device):
+        _lib.call('regnn_gatv2_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
+                  _ptr(a_csr), _ptr(dl_csr), _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(g), h, d,
+                  rb, re, _ptr(d_fs), _stream())
+    return d_fs

@@ -1,0 +1,225 @@
+"""TEST-ONLY emulation of ``re_gnn_b200.ops`` (one function per CUDA operator, same signatures and
+the same slot-order conventions) in plain PyTorch on the CPU, plus CPU versions of
+``Graph.csr`` / ``Graph.etype_views`` built on oracle/csr_oracle.py.
+
+Purpose: run the package's host logic -- autograd Functions, layer modules, the reference's model
+files on top of them -- in the GPU-less build container.  Installed by the ``cpu_ops`` fixture via
+monkeypatch; never imported by the package.
+"""
+import numpy as np
+import torch
+
+from oracle import csr_oracle
+
+SLOPE = 0.01
+
+
+def _leaky(x, s):
+    return torch.where(x > 0, x, x * s)
+
+
+def _lgrad(x, s):
+    return torch.where(x > 0, torch.ones_like(x), torch.full_like(x, s))
+
+
+def _rows_of(indptr):
+    n = indptr.numel() - 1
+    return torch.repeat_interleave(torch.arange(n), (indptr[1:] - indptr[:-1]).long())
+
+
+def _w(theta, alpha):
+    return _leaky(theta * alpha, SLOPE)
+
+
+def graph_csr(self):
+    if self._csr is None:
+        c = csr_oracle.csr_build(self._src.numpy(), self._dst.numpy(), self._n)
+        self._csr = {k: torch.as_tensor(v) for k, v in c.items()}
+    return self._csr
+
+
+def graph_etype_views(self, e_feat, num_relations):
+    c = self.csr()
+    et = e_feat.numpy()
+    if et.size and (et.min() < 1 or et.max() > num_relations):
+        raise RuntimeError('edge type outside [1, %d]' % num_relations)
+    a, b = csr_oracle.etype_permute(et, c['eid'].numpy(), c['slot_t'].numpy())
+    return torch.as_tensor(a), torch.as_tensor(b)
+
+
+def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None):
+    w = _w(theta.detach().view(-1), alpha)
+    n = csr['indptr'].numel() - 1
+    deg = torch.zeros(n, dtype=w.dtype).index_add(0, csr['row'].long(), w[et_csr.long()])
+    return deg, deg.clamp(min=1) ** exponent
+
+
+def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None):
+    th = theta.detach().view(-1)
+    dd = torch.where(deg >= 1, exponent * deg.clamp(min=1) ** (exponent - 1) * d_norm, torch.zeros_like(deg))
+    dw = torch.zeros_like(th).index_add(0, et_csr.long(), dd[csr['row'].long()])
+    return dw * alpha * _lgrad(th * alpha, SLOPE)
+
+
+def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None):
+    x = x.detach()
+    row, col = _rows_of(indptr), indices.long()
+    coef = torch.ones(col.numel(), dtype=x.dtype)
+    if theta is not None:
+        coef = _w(theta.detach().view(-1), alpha)[etype.long()]
+    if norm_src is not None:
+        coef = coef * norm_src.detach()[col]
+    y = torch.zeros((indptr.numel() - 1, x.shape[1]), dtype=x.dtype).index_add(0, row, coef[:, None] * x[col])
+    if norm_dst is not None:
+        y = y * norm_dst.detach()[:, None]
+    return y
+
+
+def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3):
+    x, y, g, dx = x.detach(), y.detach(), g.detach(), dx.detach()
+    d_norm = None
+    if norm is None:
+        sides = 0
+    if norm is not None:
+        d_norm = ((y * g).sum(1) * bool(sides & 2) + (x * dx).sum(1) * bool(sides & 1)) / norm.detach()
+    d_theta = None
+    if theta is not None:
+        th = theta.detach().view(-1)
+        row, col = csr['row'].long(), csr['indices'].long()
+        dwe = (x[col] * g[row]).sum(1)
+        if sides & 1:
+            dwe = dwe * norm.detach()[col]
+        if sides & 2:
+            dwe = dwe * norm.detach()[row]
+        dw = torch.zeros_like(th).index_add(0, et_csr.long(), dwe)
+        d_theta = dw * alpha * _lgrad(th * alpha, SLOPE)
+    return d_theta, d_norm
+
+
+def _softmax_rows(l, row, n):
+    mx = torch.full((n, l.shape[1]), float('-inf'), dtype=l.dtype).scatter_reduce(
+        0, row[:, None].expand_as(l), l, 'amax', include_self=True)
+    ex = torch.exp(l - mx[row])
+    sm = torch.zeros((n, l.shape[1]), dtype=l.dtype).index_add(0, row, ex)
+    mx = torch.where(torch.isinf(mx), torch.zeros_like(mx), mx)
+    return ex / sm[row], mx, sm
+
+
+def _keep_csr(keep, csr):
+    return None if keep is None else keep.detach()[csr['eid'].long()]
+
+
+def _to_edge_order(v_csr, csr):
+    out = torch.empty_like(v_csr)
+    out[csr['eid'].long()] = v_csr
+    return out
+
+
+def _gat_logits(csr, et_csr, theta, alpha, el, er, slope):
+    row, col = csr['row'].long(), csr['indices'].long()
+    pre = el.detach()[col] + er.detach()[row]
+    if theta is not None and et_csr is not None:
+        pre = pre + _w(theta.detach(), alpha)[et_csr.long()]
+    return pre, _leaky(pre, slope)
+
+
+def gat_fwd(csr, et_csr, theta, alpha, feat, el, er, slope, keep=None, want_attn=False, rows=None):
+    feat = feat.detach()
+    n = feat.shape[0]
+    row, col = csr['row'].long(), csr['indices'].long()
+    _, l = _gat_logits(csr, et_csr, theta, alpha, el, er, slope)
+    a, mx, sm = _softmax_rows(l, row, n)
+    kc = _keep_csr(keep, csr)
+    at = a if kc is None else a * kc
+    out = torch.zeros_like(feat).index_add(0, row, at[:, :, None] * feat[col])
+    return out, mx, sm, (_to_edge_order(at, csr) if want_attn else None)
+
+
+def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowmax, rowsum, g, rows=None):
+    feat, g, out = feat.detach(), g.detach(), out.detach()
+    row, col = csr['row'].long(), csr['indices'].long()
+    pre, l = _gat_logits(csr, et_csr, theta, alpha, el, er, slope)
+    a = torch.exp(l - rowmax[row]) / rowsum[row]
+    kc = _keep_csr(keep, csr)
+    at = a if kc is None else a * kc
+    da = (feat[col] * g[row]).sum(-1)
+    S = (out * g).sum(-1)
+    dpre = (at * da - a * S[row]) * _lgrad(pre, slope)
+    d_er = torch.zeros_like(rowmax).index_add(0, row, dpre)
+    d_theta = None
+    if theta is not None and et_csr is not None:
+        th = theta.detach()
+        dw = torch.zeros_like(th).index_add(0, et_csr.long(), dpre)
+        d_theta = dw * alpha * _lgrad(th * alpha, SLOPE)
+    return at, dpre, d_er, d_theta
+
+
+def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None):
+    g = g.detach()
+    src = _rows_of(csr['indptr_t'])
+    dstn, slot = csr['indices_t'].long(), csr['slot_t'].long()
+    d_feat = torch.zeros_like(g).index_add(0, src, a_csr[slot][:, :, None] * g[dstn])
+    d_el = None
+    if dpre_csr is not None:
+        d_el = torch.zeros((g.shape[0], g.shape[1]), dtype=g.dtype).index_add(0, src, dpre_csr[slot])
+    return d_feat, d_el
+
+
+def _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope):
+    row, col = csr['row'].long(), csr['indices'].long()
+    q = fs.detach()[col] + fd.detach()[row]
+    lr = _leaky(q, slope)
+    l = (lr * attn.detach().view(1, fs.shape[1], fs.shape[2])).sum(-1)
+    if theta is not None and et_csr is not None:
+        l = l + _w(theta.detach(), alpha)[et_csr.long()]
+    return q, lr, l
+
+
+def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_attn=False, rows=None):
+    n = fd.shape[0]
+    row, col = csr['row'].long(), csr['indices'].long()
+    _, _, l = _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope)
+    a, mx, sm = _softmax_rows(l, row, n)
+    kc = _keep_csr(keep, csr)
+    at = a if kc is None else a * kc
+    out = torch.zeros_like(fd.detach()).index_add(0, row, at[:, :, None] * fs.detach()[col])
+    return out, mx, sm, (_to_edge_order(at, csr) if want_attn else None)
+
+
+def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, rowmax, rowsum, g, rows=None):
+    g, out = g.detach(), out.detach()
+    row, col = csr['row'].long(), csr['indices'].long()
+    q, lr, l = _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope)
+    a = torch.exp(l - rowmax[row]) / rowsum[row]
+    kc = _keep_csr(keep, csr)
+    at = a if kc is None else a * kc
+    da = (fs.detach()[col] * g[row]).sum(-1)
+    S = (out * g).sum(-1)
+    dl = at * da - a * S[row]
+    av = attn.detach().view(1, fs.shape[1], fs.shape[2])
+    dq = dl[:, :, None] * av * _lgrad(q, slope)
+    d_fd = torch.zeros_like(fd.detach()).index_add(0, row, dq)
+    d_attn = (dl[:, :, None] * lr).sum(0).reshape(-1)
+    d_theta = None
+    if theta is not None and et_csr is not None:
+        th = theta.detach()
+        d_theta = torch.zeros_like(th).index_add(0, et_csr.long(), dl) * alpha * _lgrad(th * alpha, SLOPE)
+    return at, dl, d_fd, d_attn, d_theta
+
+
+def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
+    fs, fd, g = fs.detach(), fd.detach(), g.detach()
+    src = _rows_of(csr['indptr_t'])
+    dstn, slot = csr['indices_t'].long(), csr['slot_t'].long()
+    av = attn.detach().view(1, fs.shape[1], fs.shape[2])
+    msg = a_csr[slot][:, :, None] * g[dstn] + dl_csr[slot][:, :, None] * av * _lgrad(fs[src] + fd[dstn], slope)
+    return torch.zeros_like(fs).index_add(0, src, msg)
+
+
+def install(monkeypatch):
+    from re_gnn_b200 import graph as G, ops
+    monkeypatch.setattr(G.Graph, 'csr', graph_csr)
+    monkeypatch.setattr(G.Graph, 'etype_views', graph_etype_views)
+    for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'gat_fwd', 'gat_bwd_dst',
+                 'gat_bwd_src', 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src'):
+        monkeypatch.setattr(ops, name, globals()[name])
