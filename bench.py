@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the RE-GNN hot path on B200.
+
+Metric (BASELINE.json): GTEPS forward+backward per RE-layer (+ % of the HBM roofline).  A "step" is
+one forward + backward of one RE-layer (REGraphConv aggregation core: relation-weighted degree norm
++ fused norm*SpMM*norm, gradients w.r.t. the features and the relation embedding) over the whole
+synthetic ogbn-mag-shaped graph (BASELINE config 4; 1.94 M nodes, 23.05 M edges incl. self loops,
+F = 128 fp32).  With --gpus N the same graph is partitioned by destination-row blocks (strong scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mag_regcn]
+
+One JSON line on stdout from rank 0.  `--impl reference` times the CPU restatement of the reference
+(oracle/regnn_oracle.py; DGL itself cannot be installed) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALPHA = 100.0
+FEAT = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='mag_regcn', choices=['mag_regcn'])
+    ap.add_argument('--feat', type=int, default=FEAT)
+    ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
+    ap.add_argument('--no-others', action='store_true', help='skip the secondary HGB-shaped workloads')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # NVML missing: report nulls rather than fail the bench
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def theta_init(r, w, seed=0):
+    rng = np.random.RandomState(seed)
+    return torch.as_tensor(rng.uniform(0.5, 1.5, size=(r, w)) / ALPHA, dtype=torch.float32)
+
+
+def algorithmic_bytes_spmm(n, e, f):
+    """SURVEY.md 8(d) gather model, forward SpMM: per edge source row + col idx + etype + norm[src];
+    per row output row + indptr + norm[dst]."""
+    return e * (4 * f + 4 + 1 + 4) + n * (4 * f + 4 + 4)
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(d, feat, steps, warmup, max_edges=1_500_000):
+    """Times the CPU restatement of the reference layer (oracle) forward+backward on a bounded sample:
+    the destination-row block [0, k) of the same graph holding ~max_edges in-edges."""
+    from oracle import regnn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dst = d['dst']
+    order = np.argsort(dst, kind='stable')
+    k_edges = min(max_edges, dst.size)
+    sel = np.sort(order[:k_edges])
+    src, dsts, et = (torch.as_tensor(d[k][sel]) for k in ('src', 'dst', 'etype'))
+    n = d['num_nodes']
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, feat, generator=g).requires_grad_(True)
+    th = theta_init(d['num_relations'], 1).requires_grad_(True)
+    gout = torch.randn(n, feat, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        x.grad = th.grad = None
+        t0 = time.perf_counter()
+        out = O.regraphconv_forward(src, dsts, et, n, x, th, ALPHA)
+        out.backward(gout)
+        times.append(time.perf_counter() - t0)
+    t = float(np.median(times[warmup:]))
+    return {'value': k_edges / t / 1e9, 'unit': 'GTEPS', 'cores': cores, 'kind': 'port',
+            'sample': 'oracle/regnn_oracle.py REGraphConv fwd+bwd (PyTorch CPU, fp32) on the destination-row block '
+                      'holding the first %d in-edges of the same graph, median of %d runs after %d warm-ups, '
+                      '%.3f s per run' % (k_edges, steps, warmup, t)}, t
+
+
+def run_reference(args, d):
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cb, t = cpu_reference_sample(d, args.feat, steps, warmup)
+    line = {
+        'impl': 'reference', 'metric': 'GTEPS fwd+bwd per RE-layer', 'value': cb['value'], 'unit': 'GTEPS',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, d), 'cpu_baseline': cb,
+        'e2e': {'value': cb['value'], 'unit': 'GTEPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, d):
+    return {'workload': 'REGraphConv RE-layer fwd+bwd, full-batch, synthetic ogbn-mag-shaped graph '
+                        '(BASELINE config 4), dst-row-partitioned over --gpus',
+            'num_nodes': int(d['num_nodes']), 'num_edges': int(d['src'].size), 'num_relations': int(d['num_relations']),
+            'feat': args.feat, 'graph_scale': args.scale,
+            'l2': 'inputs larger than L2 (source matrix %.0f MB vs 126 MB L2); no flush needed'
+                  % (d['num_nodes'] * args.feat * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def timed(fn, steps, warmup, sync, barrier=None):
+    """W untimed warm-ups, then exactly K steps between CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    sync()
+    if barrier:
+        barrier()
+    sync()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        fn()
+    t1.record()
+    sync()
+    if barrier:
+        barrier()
+    return t0.elapsed_time(t1) / 1e3  # seconds for K steps
+
+
+def others(dev, steps, warmup):
+    """Secondary workloads (BASELINE configs 1-3; L2-resident, so each timed iteration is preceded by an
+    L2 flush and timed on its own): GTEPS fwd+bwd of one layer call."""
+    import torch.nn.functional as F
+    import re_gnn_b200
+    from re_gnn_b200 import Graph, synth
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    res = {}
+    cases = [
+        ('dblp_regcn_f64', 'dblp', lambda r: re_gnn_b200.REGraphConv(r, ALPHA, 64, 64, bias=False, weight=False), 64),
+        ('acm_regat_h8d64', 'acm', lambda r: re_gnn_b200.REGATConv(r, ALPHA, 512, 64, 8, negative_slope=0.01,
+                                                                   use_weight=False), 512),
+        ('imdb_remixhop_p012_f64', 'imdb', lambda r: re_gnn_b200.REMixHopConv(r, ALPHA, 64, 64, p=[0, 1, 2]), 64),
+        ('imdb_regatv2_h8d64', 'imdb', lambda r: re_gnn_b200.REGATv2Conv(r, ALPHA, 512, 64, 8, negative_slope=0.01,
+                                                                         use_weight=False), 512),
+    ]
+    for name, shape, ctor, fin in cases:
+        d = synth.hetero_graph(shape)
+        g = Graph(d['src'], d['dst'], d['num_nodes']).to(dev)
+        et = torch.as_tensor(d['etype']).to(dev)
+        mod = ctor(d['num_relations']).to(dev)
+        mod.edge_weight.data.copy_(theta_init(d['num_relations'], mod.edge_weight.shape[1]))
+        x = torch.randn(d['num_nodes'], fin, device=dev, requires_grad=True)
+        out = mod(g, x, et)
+        gout = torch.randn_like(out)
+        ts = []
+        for i in range(warmup + steps):
+            x.grad = None
+            mod.zero_grad(set_to_none=True)
+            flush.zero_()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            mod(g, x, et).backward(gout)
+            t1.record()
+            torch.cuda.synchronize()
+            ts.append(t0.elapsed_time(t1) / 1e3)
+        t = float(np.median(ts[warmup:]))
+        res[name] = {'gteps_fwd_bwd': d['src'].size / t / 1e9, 'ms': t * 1e3, 'num_edges': int(d['src'].size),
+                     'l2': 'flushed between iterations'}
+    return res
+
+
+def run_ours(args, d):
+    import torch.distributed as dist
+    import re_gnn_b200  # noqa: F401  (fails loudly if the CUDA library is missing)
+    from re_gnn_b200 import Graph, _lib, functional as RF, ops, partition
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sync = torch.cuda.synchronize
+    barrier = (lambda: dist.barrier()) if world > 1 else None
+
+    n, e, r, f = d['num_nodes'], d['src'].size, d['num_relations'], args.feat
+    g = Graph(d['src'], d['dst'], n).to(dev)
+    et = torch.as_tensor(d['etype']).to(dev)
+    t_build0 = time.perf_counter()
+    csr = g.csr()
+    etv = g.etype_views(et, r)
+    sync()
+    build_s = time.perf_counter() - t_build0
+    theta = theta_init(r, 1).to(dev).requires_grad_(True)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    x_full = torch.randn(n, f, device=dev, generator=gen)
+    g_full = torch.randn(n, f, device=dev, generator=gen)
+
+    if world == 1:
+        x = x_full.clone().requires_grad_(True)
+        gout = g_full
+
+        def step():
+            x.grad = theta.grad = None
+            nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5)
+            RF.propagate(g, etv, x, theta, ALPHA, nrm).backward(gout)
+    else:
+        bounds = partition.row_blocks(csr['indptr'], world)
+        rb, re = bounds[rank], bounds[rank + 1]
+        x = x_full[rb:re].clone().requires_grad_(True)
+        gout = g_full[rb:re].clone()
+        del x_full, g_full
+
+        def step():
+            x.grad = theta.grad = None
+            nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5)
+            partition.partitioned_propagate(g, etv, x, theta, ALPHA, nrm, bounds, rank).backward(gout)
+            partition.allreduce_relation_grads([theta])
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count
+    total = timed(step, args.steps, args.warmup, sync, barrier)
+    launches = (_lib.launch_count - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+    ms = total / args.steps * 1e3
+    value = e / (total / args.steps) / 1e9
+
+    # ---- end-to-end arm: host buffers, H2D of the step's inputs and D2H of its result inside the timed region
+    x_h = torch.randn(x.shape, dtype=torch.float32).pin_memory()
+    g_h = torch.randn(gout.shape, dtype=torch.float32).pin_memory()
+    res_h = torch.empty(r + 1, dtype=torch.float32).pin_memory()
+    x_e = torch.empty_like(x, requires_grad=True)
+    g_e = torch.empty_like(gout)
+
+    def step_e2e():
+        x_e.grad = theta.grad = None
+        with torch.no_grad():
+            x_e.copy_(x_h, non_blocking=True)
+            g_e.copy_(g_h, non_blocking=True)
+        nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5)
+        if world == 1:
+            out = RF.propagate(g, etv, x_e, theta, ALPHA, nrm)
+        else:
+            out = partition.partitioned_propagate(g, etv, x_e, theta, ALPHA, nrm, bounds, rank)
+        out.backward(g_e)
+        if world > 1:
+            partition.allreduce_relation_grads([theta])
+        res_h.copy_(torch.cat([theta.grad.view(-1), out.detach().sum().view(1)]), non_blocking=True)
+
+    e2e_total = timed(step_e2e, max(3, args.steps // 2), 3, sync, barrier)
+    if world > 1:
+        t = torch.tensor([e2e_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_steps = max(3, args.steps // 2)
+    e2e = {'value': e / (e2e_total / e2e_steps) / 1e9, 'unit': 'GTEPS',
+           'h2d_bytes_per_step': int(x_h.numel() * 4 + g_h.numel() * 4), 'd2h_bytes_per_step': int(res_h.numel() * 4),
+           'ms_per_step': e2e_total / e2e_steps * 1e3,
+           'note': 'per rank: pinned-host X and dL/dY rows copied in, relation gradient + output checksum copied out'}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (forward SpMM launch, timed alone on the launching stream)
+    hbm, how = peaks()
+    with torch.no_grad():
+        nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5).detach()
+        xs = x_e.detach() if world == 1 else torch.randn(n, f, device=dev)
+        y = torch.empty(n, f, device=dev)
+        rows = None if world == 1 else (bounds[rank], bounds[rank + 1])
+
+        def k():
+            ops.spmm(csr['indptr'], csr['indices'], etv[0], theta.detach(), ALPHA, nrm, nrm, xs, rows=rows, out=y)
+        tk = timed(k, 20, 5, sync) / 20
+        rows_n = n if rows is None else rows[1] - rows[0]
+        edges_n = e if rows is None else int(csr['indptr'][rows[1]].item() - csr['indptr'][rows[0]].item())
+    alg = algorithmic_bytes_spmm(rows_n, edges_n, f)
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tp) and world == 1 and args.scale == 1.0 and f == FEAT:
+        with open(tp) as fh:
+            traffic = json.load(fh).get('spmm_kernel_fwd_mag_f128_bytes')
+    roofline = {'bound': 'hbm', 'kernel': 'regnn::spmm_kernel<32,1,4> (forward launch)', 'achieved': alg / tk / 1e9,
+                'peak': hbm, 'peak_source': how, 'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm, 'traffic': traffic,
+                'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3}
+
+    line = {
+        'metric': 'GTEPS fwd+bwd per RE-layer', 'value': value, 'unit': 'GTEPS', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, d), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+        'roofline': roofline, 'graph_build_s': build_s,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'], _ = cpu_reference_sample(d, f, 3, 1)
+    if world == 1 and not args.no_others:
+        line['others'] = others(dev, 10, 3)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    if args.impl == 'reference' and rank != 0:
+        return
+    from re_gnn_b200 import synth
+    d = synth.hetero_graph('mag', scale=args.scale)
+    if args.impl == 'reference':
+        run_reference(args, d)
+    else:
+        run_ours(args, d)
+
+
+if __name__ == '__main__':
+    main()

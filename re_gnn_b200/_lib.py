@@ -62,6 +62,16 @@ def load():
     return lib
 
 
+# Kernel launches issued through the C ABI since import (bench.py reports the count of a timed region).
+# Each wrapper in ops.py adds the number of kernels its entry point launches.
+launch_count = 0
+
+
+def count_launches(n):
+    global launch_count
+    launch_count += n
+
+
 def call(name, *args):
     """Calls a status-returning entry point; raises RuntimeError with the library's message on failure."""
     lib = load()

@@ -41,6 +41,7 @@ def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None):
     with torch.cuda.device(theta.device):
         _lib.call('regnn_wdeg_norm_fwd', _ptr(csr['indptr']), _ptr(et_csr), _ptr(theta), float(alpha),
                   theta.numel(), float(exponent), rb, re, _ptr(deg), _ptr(norm), _stream())
+        _lib.count_launches(1)
     return deg, norm
 
 
@@ -55,6 +56,7 @@ def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None):
     with torch.cuda.device(theta.device):
         _lib.call('regnn_wdeg_norm_bwd', _ptr(csr['indptr']), _ptr(et_csr), _ptr(theta), float(alpha), r,
                   float(exponent), rb, re, _ptr(deg), _ptr(d_norm), _ptr(partials), _ptr(d_theta), _stream())
+        _lib.count_launches(2)
     return d_theta
 
 
@@ -73,6 +75,7 @@ def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None,
         _lib.call('regnn_spmm_fwd', _ptr(indptr), _ptr(indices), _ptr(etype) if theta is not None else None,
                   _ptr(theta), float(alpha), theta.numel() if theta is not None else 0, _ptr(norm_src),
                   _ptr(norm_dst), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rb, re, f, _stream())
+        _lib.count_launches(1)
     return out
 
 
@@ -92,6 +95,7 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3)
                   _ptr(theta), float(alpha), r, _ptr(norm), int(sides), _ptr(x), x.stride(0), _ptr(y), y.stride(0),
                   _ptr(g), g.stride(0), _ptr(dx), dx.stride(0), rb, re, x.shape[1], _ptr(partials),
                   _ptr(d_theta), _ptr(d_norm), _stream())
+        _lib.count_launches(2 if weighted else 1)
     return d_theta, d_norm
 
 
@@ -117,6 +121,7 @@ def gat_fwd(csr, et_csr, theta, alpha, feat, el, er, slope, keep=None, want_attn
         _lib.call('regnn_gat_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep), h, d,
                   rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(attn), _stream())
+        _lib.count_launches(1)
     return out, rowmax, rowsum, attn
 
 
@@ -137,6 +142,7 @@ def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowma
                   _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep),
                   _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dpre_csr),
                   _ptr(d_er), _ptr(partials), _ptr(d_theta), _stream())
+        _lib.count_launches(2 if r else 1)
     return a_csr, dpre_csr, d_er, d_theta
 
 
@@ -150,6 +156,7 @@ def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None):
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
                   _ptr(a_csr), _ptr(dpre_csr), _ptr(g), h, d, rb, re, _ptr(d_feat), _ptr(d_el), _stream())
+        _lib.count_launches(1)
     return d_feat, d_el
 
 
@@ -169,6 +176,7 @@ def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_at
         _lib.call('regnn_gatv2_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep), h, d,
                   rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(att), _stream())
+        _lib.count_launches(1)
     return out, rowmax, rowsum, att
 
 
@@ -191,6 +199,7 @@ def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, row
                   _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep),
                   _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dl_csr),
                   _ptr(d_fd), _ptr(d_attn), _ptr(partials), _ptr(d_theta), _stream())
+        _lib.count_launches(3 if r else 2)
     return a_csr, dl_csr, d_fd, d_attn, d_theta
 
 
@@ -204,4 +213,5 @@ def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
         _lib.call('regnn_gatv2_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
                   _ptr(a_csr), _ptr(dl_csr), _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(g), h, d,
                   rb, re, _ptr(d_fs), _stream())
+        _lib.count_launches(1)
     return d_fs

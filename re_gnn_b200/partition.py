@@ -1,0 +1,89 @@
+"""Destination-row-block partitioning of the full-batch REGCN aggregation across ranks
+(BASELINE config 4: ogbn-mag-shaped graph over 2/4/8 B200).  The reference has no multi-GPU code
+(SURVEY.md 2.4); numerics must equal the single-device result.
+
+Scheme (owner computes, no floating-point reduction across ranks except the tiny relation-gradient
+table):
+  * rank p owns the contiguous destination rows [r_p, r_{p+1}), balanced by in-edge count;
+  * every rank holds the whole CSR / transposed view (int32 structures: ~0.4 GB at MAG scale) and
+    computes the (cheap, E-byte) relation-weighted degree norm for all rows;
+  * forward:  NCCL all-gather of the owned source-feature rows -> full X; fused SpMM on owned rows;
+  * backward: NCCL all-gather of the owned dL/dY rows -> full G; transposed SpMM on owned SOURCE rows
+    gives the owned dX rows (no reduce-scatter, no atomics); the relation-gradient partials of the
+    owned rows are summed with one all-reduce of R floats.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def row_blocks(indptr, parts):
+    """Row boundaries [r_0=0, ..., r_P=N] with ~equal in-edge counts per block (prefix sums of indptr)."""
+    n = indptr.numel() - 1
+    e = int(indptr[-1].item())
+    targets = torch.arange(1, parts, device=indptr.device, dtype=torch.int64) * e // parts
+    cuts = torch.searchsorted(indptr.to(torch.int64), targets)
+    bounds = [0] + [int(c) for c in cuts.clamp(max=n).tolist()] + [n]
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+def _all_gather_rows(full, own, bounds, group):
+    """Gathers every rank's row block into ``full`` ([N, F], global row ids).  Blocks are uneven
+    (balanced by edges, not rows); ProcessGroupNCCL handles that with grouped broadcasts."""
+    views = [full[bounds[p]:bounds[p + 1]] for p in range(len(bounds) - 1)]
+    dist.all_gather(views, own.contiguous(), group=group)
+    return full
+
+
+class _PartitionedPropagate(torch.autograd.Function):
+    """Rows [rb, re) of  Y = norm (.) A_w (norm (.) X)  with X row-partitioned across ranks."""
+
+    @staticmethod
+    def forward(ctx, graph, etv, x_own, theta, alpha, norm, bounds, rank, group):
+        csr = graph.csr()
+        n = graph.number_of_nodes()
+        rb, re = bounds[rank], bounds[rank + 1]
+        x_full = torch.empty((n, x_own.shape[1]), dtype=x_own.dtype, device=x_own.device)
+        _all_gather_rows(x_full, x_own, bounds, group)
+        y_full = torch.empty_like(x_full)
+        ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, alpha, norm, norm, x_full, rows=(rb, re), out=y_full)
+        ctx.graph, ctx.etv, ctx.alpha, ctx.bounds, ctx.rank, ctx.group = graph, etv, alpha, bounds, rank, group
+        ctx.save_for_backward(x_full, y_full, theta, norm)
+        return y_full[rb:re]
+
+    @staticmethod
+    def backward(ctx, g_own):
+        x_full, y_full, theta, norm = ctx.saved_tensors
+        csr = ctx.graph.csr()
+        bounds, rank = ctx.bounds, ctx.rank
+        rb, re = bounds[rank], bounds[rank + 1]
+        g_full = torch.empty_like(x_full)
+        _all_gather_rows(g_full, g_own, bounds, ctx.group)
+        dx_full = torch.empty_like(x_full)
+        ops.spmm(csr['indptr_t'], csr['indices_t'], ctx.etv[1], theta, ctx.alpha, norm, norm, g_full,
+                 rows=(rb, re), out=dx_full)
+        d_theta, d_norm = ops.spmm_bwd_w(csr, ctx.etv[0], theta, ctx.alpha, norm, x_full, y_full, g_full, dx_full,
+                                         rows=(rb, re))
+        # d_theta / d_norm hold this rank's rows only; the caller all-reduces the parameter gradient once.
+        return None, None, dx_full[rb:re], d_theta.view_as(theta), None, d_norm, None, None, None
+
+
+def partitioned_propagate(graph, etv, x_own, theta, alpha, norm, bounds, rank, group=None):
+    return _PartitionedPropagate.apply(graph, etv, x_own, theta, alpha, norm, bounds, rank, group)
+
+
+def allreduce_relation_grads(params, group=None):
+    """Sums the per-rank relation-embedding gradients (R x H floats each) -- the only cross-rank
+    floating-point reduction of the partitioned layer."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()

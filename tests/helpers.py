@@ -41,9 +41,19 @@ def load_params(module, case, dtype=torch.float64, device='cpu'):
     return module
 
 
-def assert_close(actual, expected, rtol, name=''):
+def f32_exact(a):
+    """float64 tensor whose values are exactly representable in float32, so the float64 oracle and
+    the fp32 kernels start from identical inputs (and LeakyReLU kinks are hit on the same side)."""
+    return torch.as_tensor(np.asarray(a, dtype=np.float32).astype(np.float64))
+
+
+def assert_close(actual, expected, rtol, name='', max_outlier_frac=0.0):
     """Norm-wise relative check used for fp32 results: |a-e| <= rtol * (|e| + max|e|) elementwise.
-    (Sums with cancellation make a purely elementwise relative bound meaningless near zero.)"""
+    (Sums with cancellation make a purely elementwise relative bound meaningless near zero.)
+    ``max_outlier_frac``: fraction of elements allowed outside the bound -- only used downstream of a
+    LeakyReLU kink fed by an fp32 GEMM, where a pre-activation within 1 ulp of zero can land on the
+    other side of the kink than in float64 and flips one gradient term (a property of fp32, also of
+    the reference's own fp32 run)."""
     a = torch.as_tensor(np.asarray(actual), dtype=torch.float64)
     e = torch.as_tensor(np.asarray(expected), dtype=torch.float64)
     assert a.shape == e.shape, '%s: shape %s vs %s' % (name, tuple(a.shape), tuple(e.shape))
@@ -51,6 +61,40 @@ def assert_close(actual, expected, rtol, name=''):
     scale = e.abs().max().item() if e.numel() else 0.0
     err = (a - e).abs()
     bound = rtol * (e.abs() + scale) + 1e-30
-    worst = (err / bound).max().item() if e.numel() else 0.0
+    ratio = err / bound
+    if max_outlier_frac > 0 and e.numel():
+        k = int(max_outlier_frac * e.numel())
+        if k > 0:
+            ratio = torch.topk(ratio.reshape(-1), k + 1, largest=True).values[-1:]
+    worst = ratio.max().item() if e.numel() else 0.0
     assert worst <= 1.0, '%s: max err %.3e (scale %.3e), %.2fx over rtol=%g' % (
         name, err.max().item(), scale, worst, rtol)
+
+
+def build_model(model_pkg, meta, g):
+    """Instantiates REGCN / REGAT / REMixHop (ours or the reference's) from fixture metadata."""
+    args = [ACT.get(a, a) if isinstance(a, str) else a for a in meta['args']]
+    if meta['kind'] == 'REGCN':
+        return model_pkg.REGCN(g, *args)
+    if meta['kind'] == 'REGAT':
+        return model_pkg.REGAT(g, *args, use_gatv2=meta.get('use_gatv2', False))
+    return model_pkg.REMixHop(g, *args, activation=ACT[meta.get('activation')])
+
+
+def run_model_case(model_pkg, graph_cls, case, device='cpu', dtype=torch.float64):
+    g = graph_cls(case['src'], case['dst'], int(case['num_nodes'])).to(device)
+    net = load_params(build_model(model_pkg, case['meta'], g), case, dtype, device)
+    feats = [torch.as_tensor(case['in::f%d' % i]).to(device=device, dtype=dtype).requires_grad_(True) for i in range(3)]
+    out, _ = net(feats, torch.as_tensor(case['etype']).to(device))
+    out.backward(torch.as_tensor(case['gout']).to(device=device, dtype=dtype))
+    return net, feats, out
+
+
+def check_model_case(case, net, feats, out, rtol, grad_rtol=None):
+    grad_rtol = grad_rtol or rtol
+    assert_close(out.detach().cpu(), case['out0'], rtol, 'logits')
+    for i, f in enumerate(feats):
+        assert_close(f.grad.cpu(), case['gin::f%d' % i], grad_rtol, 'd_f%d' % i)
+    for k, p in net.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert_close(got.cpu(), case['grad::' + k], grad_rtol, 'd_' + k)
