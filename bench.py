@@ -337,7 +337,8 @@ def run_ours(args, d):
         rows = None if world == 1 else (bounds[rank], bounds[rank + 1])
 
         def k():
-            ops.spmm(csr['indptr'], csr['indices'], etv[0], theta.detach(), ALPHA, nrm, nrm, xs, rows=rows, out=y)
+            ops.spmm(csr['indptr'], csr['indices'], etv[0], theta.detach(), ALPHA, nrm, nrm, xs, rows=rows, out=y,
+                     split=csr.get('split'))
         tk = timed(k, 20, 5, sync) / 20
         rows_n = n if rows is None else rows[1] - rows[0]
         edges_n = e if rows is None else int(csr['indptr'][rows[1]].item() - csr['indptr'][rows[0]].item())

@@ -49,6 +49,19 @@ extern "C" {
 #define REGNN_MAX_RELATIONS 255 /* uint8 edge types */
 #define REGNN_MAX_HEADS 32
 
+/* Long-row decomposition of one CSR view (built once per graph by the host, see re_gnn_b200/graph.py):
+ * rows with more than `threshold` slots are cut into fragments of `threshold` consecutive slots so that
+ * no single warp has to walk a hub row (ogbn-mag-scale graphs have rows with 1e4-1e5 in-edges).
+ * Fragment partial results are combined in fragment order => still deterministic.
+ * All pointers are device pointers; pass NULL instead of the struct for "no splitting". */
+typedef struct regnn_rowsplit {
+  const int32_t* long_rows;  /* [num_long]    ids of the rows longer than threshold, ascending */
+  const int32_t* frag_ptr;   /* [num_long+1]  first fragment of each long row                  */
+  const int32_t* frag_row;   /* [num_frags]   row id of each fragment                          */
+  const int32_t* frag_begin; /* [num_frags]   first CSR slot of each fragment                  */
+  int32_t num_long, num_frags, threshold;
+} regnn_rowsplit_t;
+
 int regnn_version(void);
 const char* regnn_status_string(int status);
 const char* regnn_last_error_string(void);
@@ -109,7 +122,8 @@ int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const f
 int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
                    const float* theta, float alpha, int num_relations, const float* norm_src,
                    const float* norm_dst, const float* X, int64_t ldx, float* Y, int64_t ldy,
-                   int64_t row_begin, int64_t row_end, int feat, void* stream);
+                   int64_t row_begin, int64_t row_end, int feat, const regnn_rowsplit_t* split,
+                   float* split_workspace /* [split->num_frags * feat] floats, or NULL */, void* stream);
 
 /* Backward of regnn_spmm_fwd w.r.t. the relation weights and the norm vector (norm_src == norm_dst
  * == norm, the reference's case).  Given G = dL/dY, X, Y and dX (= the transposed regnn_spmm_fwd of G):
@@ -125,7 +139,8 @@ int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_
                      const float* theta, float alpha, int num_relations, const float* norm,
                      int norm_sides, const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* G,
                      int64_t ldg, const float* dX, int64_t lddx, int64_t row_begin, int64_t row_end,
-                     int feat, double* partials, float* d_theta, float* d_norm, void* stream);
+                     int feat, double* partials, float* d_theta, float* d_norm,
+                     const regnn_rowsplit_t* split, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused REGAT layer core (layer/REGATConv.py:71-92): per destination v and head h

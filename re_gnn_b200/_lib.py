@@ -26,9 +26,9 @@ SIGNATURES = {
     'regnn_etype_permute': (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
     'regnn_wdeg_norm_fwd': (_i32, [_p, _p, _p, _f32, _i32, _f32, _i64, _i64, _p, _p, _p]),
     'regnn_wdeg_norm_bwd': (_i32, [_p, _p, _p, _f32, _i32, _f32, _i64, _i64, _p, _p, _p, _p, _p]),
-    'regnn_spmm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i32, _p]),
+    'regnn_spmm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i32, _p, _p, _p]),
     'regnn_spmm_bwd_w': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
-                                _i64, _i64, _i32, _p, _p, _p, _p]),
+                                _i64, _i64, _i32, _p, _p, _p, _p, _p]),
     'regnn_gat_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
                              _p, _p, _p, _p, _p]),
     'regnn_gat_bwd_dst': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p,
@@ -40,6 +40,14 @@ SIGNATURES = {
                                    _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
     'regnn_gatv2_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64, _p, _p]),
 }
+
+
+
+class RowSplit(ctypes.Structure):
+    """Mirror of ``regnn_rowsplit_t`` (include/regnn_b200.h)."""
+    _fields_ = [('long_rows', _p), ('frag_ptr', _p), ('frag_row', _p), ('frag_begin', _p),
+                ('num_long', ctypes.c_int32), ('num_frags', ctypes.c_int32), ('threshold', ctypes.c_int32)]
+
 
 _lib = None
 

@@ -27,6 +27,11 @@ struct SpmmArgs {
   int64_t ldy;
   int64_t row_begin, row_end;
   int F;
+  // long-row fragments (see regnn_rowsplit_t): work items [0, nfrag) are fragments, padded to nfrag_pad
+  const int32_t* frag_row;
+  const int32_t* frag_begin;
+  int nfrag, nfrag_pad, threshold;
+  float* partial;  // [nfrag][F] un-normalised fragment sums
 };
 
 template <int VW> struct Vec;
@@ -49,9 +54,12 @@ template <> struct Vec<1> {
   static __device__ __forceinline__ T scaled(T a, float s) { return a * s; }
 };
 
-template <int C> struct Unroll { static constexpr int U = C <= 2 ? 4 : (C <= 4 ? 2 : 1); };
+template <int C> struct Unroll { static constexpr int U = C <= 1 ? 8 : (C <= 2 ? 4 : (C <= 4 ? 2 : 1)); };
 
 // ---- forward / backward-w.r.t.-X -------------------------------------------------------------
+// Work items: fragments of long rows first (lowest block ids start first, so the heaviest rows never
+// form the tail), then one item per ordinary row.  A fragment writes its un-normalised partial sum to
+// `partial`; spmm_frag_finalize_kernel adds the fragments of a row in fragment order.
 template <int G, int C, int VW>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_kernel(SpmmArgs a) {
@@ -66,12 +74,28 @@ spmm_kernel(SpmmArgs a) {
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lg = lane % G, grp = lane / G;
-  const int64_t v = a.row_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * GPW + grp;
-  const bool row_ok = v < a.row_end;
+  const int64_t wi = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * GPW + grp;
+  const bool is_frag = wi < a.nfrag_pad;
+  bool row_ok = false;
+  int64_t v = 0;
   int s0 = 0, len = 0;
-  if (row_ok) {
-    s0 = a.indptr[v];
-    len = a.indptr[v + 1] - s0;
+  if (is_frag) {
+    if (wi < a.nfrag) {
+      v = a.frag_row[wi];
+      if (v >= a.row_begin && v < a.row_end) {
+        s0 = a.frag_begin[wi];
+        len = min(a.threshold, a.indptr[v + 1] - s0);
+        row_ok = true;
+      }
+    }
+  } else {
+    v = a.row_begin + (wi - a.nfrag_pad);
+    if (v < a.row_end) {
+      s0 = a.indptr[v];
+      len = a.indptr[v + 1] - s0;
+      row_ok = len <= a.threshold;  // longer rows are covered by fragments
+      if (!row_ok) len = 0;
+    }
   }
   const int maxlen = (G == 32) ? len : warp_max_int(len);
 
@@ -84,14 +108,26 @@ spmm_kernel(SpmmArgs a) {
   }
   const float* xcol = a.X + (size_t)lg * VW;
 
+  // software prefetch: the column index / coefficient of the next batch is in flight while the
+  // current batch's rows are gathered
+  int nidx = 0;
+  float ncoef = 0.f;
+  if (lg < len) {
+    const int s = s0 + lg;
+    nidx = a.indices[s];
+    ncoef = a.etype != nullptr ? w_s[a.etype[s]] : 1.f;
+    if (a.norm_src != nullptr) ncoef *= __ldg(a.norm_src + nidx);
+  }
   for (int base = 0; base < maxlen; base += G) {
-    int idx = 0;
-    float coef = 0.f;
-    if (base + lg < len) {
-      const int s = s0 + base + lg;
-      idx = a.indices[s];
-      coef = a.etype != nullptr ? w_s[a.etype[s]] : 1.f;
-      if (a.norm_src != nullptr) coef *= __ldg(a.norm_src + idx);
+    const int idx = nidx;
+    const float coef = ncoef;
+    nidx = 0;
+    ncoef = 0.f;
+    if (base + G + lg < len) {
+      const int s = s0 + base + G + lg;
+      nidx = a.indices[s];
+      ncoef = a.etype != nullptr ? w_s[a.etype[s]] : 1.f;
+      if (a.norm_src != nullptr) ncoef *= __ldg(a.norm_src + nidx);
     }
     const int cnt = min(G, maxlen - base);
     for (int j = 0; j < cnt; j += U) {
@@ -117,11 +153,37 @@ spmm_kernel(SpmmArgs a) {
     }
   }
   if (row_ok) {
-    const float nd = a.norm_dst != nullptr ? a.norm_dst[v] : 1.f;
-    float* y = a.Y + (size_t)v * a.ldy + (size_t)lg * VW;
+    if (is_frag) {
+      float* y = a.partial + (size_t)wi * a.F + (size_t)lg * VW;
 #pragma unroll
-    for (int k = 0; k < C; ++k)
-      if (col_ok[k]) V::store(y + (size_t)k * G * VW, V::scaled(acc[k], nd));
+      for (int k = 0; k < C; ++k)
+        if (col_ok[k]) V::store(y + (size_t)k * G * VW, acc[k]);
+    } else {
+      const float nd = a.norm_dst != nullptr ? a.norm_dst[v] : 1.f;
+      float* y = a.Y + (size_t)v * a.ldy + (size_t)lg * VW;
+#pragma unroll
+      for (int k = 0; k < C; ++k)
+        if (col_ok[k]) V::store(y + (size_t)k * G * VW, V::scaled(acc[k], nd));
+    }
+  }
+}
+
+// Y[v] = norm_dst[v] * sum over the fragments of long row v (fragment order => deterministic).
+__global__ void spmm_frag_finalize_kernel(const int32_t* __restrict__ long_rows,
+                                          const int32_t* __restrict__ frag_ptr, int num_long,
+                                          const float* __restrict__ partial, const float* __restrict__ norm_dst,
+                                          float* __restrict__ Y, int64_t ldy, int F, int64_t row_begin,
+                                          int64_t row_end) {
+  const int l = blockIdx.x;
+  if (l >= num_long) return;
+  const int64_t v = long_rows[l];
+  if (v < row_begin || v >= row_end) return;
+  const int f0 = frag_ptr[l], f1 = frag_ptr[l + 1];
+  const float nd = norm_dst != nullptr ? norm_dst[v] : 1.f;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float s = 0.f;
+    for (int f = f0; f < f1; ++f) s += partial[(size_t)f * F + c];
+    Y[(size_t)v * ldy + c] = s * nd;
   }
 }
 
@@ -160,10 +222,15 @@ struct SpmmBwdArgs {
   int F;
   double* partials;
   float* d_norm;
+  const int32_t* frag_row;
+  const int32_t* frag_begin;
+  int nfrag, threshold;
 };
 
 // Destination-major pass: d_norm rows and (WEIGHTED) the per-relation sums of
-// norm[src]*norm[dst]*<X[src], G[dst]>.  Persistent grid; each warp walks row groups in a fixed order.
+// norm[src]*norm[dst]*<X[src], G[dst]>.  Persistent grid; each warp walks work items (fragments of
+// long rows first, then ordinary rows) in a fixed order.  The row-local d_norm is produced by the
+// item that starts the row.
 template <int G, int C, int VW, bool WEIGHTED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_bwd_w_kernel(SpmmBwdArgs a) {
@@ -184,47 +251,77 @@ spmm_bwd_w_kernel(SpmmBwdArgs a) {
 #pragma unroll
   for (int k = 0; k < C; ++k) col_ok[k] = (lg + k * G) * VW < a.F;
   const int64_t rows = a.row_end - a.row_begin;
-  const int64_t ngroups = (rows + GPW - 1) / GPW;
+  const int64_t nfrag_groups = (a.nfrag + GPW - 1) / GPW;
+  const int64_t ngroups = nfrag_groups + (rows + GPW - 1) / GPW;
 
   for (int64_t rg = (int64_t)blockIdx.x * kWarpsPerBlock + warp; rg < ngroups;
        rg += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const int64_t v = a.row_begin + rg * GPW + grp;
-    const bool row_ok = v < a.row_end;
+    bool row_ok = false, first = true;
+    int64_t v = 0;
     int s0 = 0, len = 0;
+    if (rg < nfrag_groups) {
+      const int64_t fi = rg * GPW + grp;
+      if (fi < a.nfrag) {
+        v = a.frag_row[fi];
+        if (v >= a.row_begin && v < a.row_end) {
+          s0 = a.frag_begin[fi];
+          len = min(a.threshold, a.indptr[v + 1] - s0);
+          first = s0 == a.indptr[v];
+          row_ok = true;
+        }
+      }
+    } else {
+      v = a.row_begin + (rg - nfrag_groups) * GPW + grp;
+      if (v < a.row_end) {
+        s0 = a.indptr[v];
+        len = a.indptr[v + 1] - s0;
+        row_ok = len <= a.threshold;
+        if (!row_ok) len = 0;
+      }
+    }
     float nv = 1.f;
     T g[C];
     float p = 0.f;
-    if (row_ok) {
-      s0 = a.indptr[v];
-      len = a.indptr[v + 1] - s0;
-      nv = a.norm != nullptr ? a.norm[v] : 1.f;
-    }
+    if (row_ok) nv = a.norm != nullptr ? a.norm[v] : 1.f;
 #pragma unroll
     for (int k = 0; k < C; ++k) {
       g[k] = V::zero();
       if (row_ok && col_ok[k]) {
         const size_t c = (size_t)(lg + k * G) * VW;
         g[k] = V::load(a.G + (size_t)v * a.ldg + c);
-        if (a.sides & 2) p += V::dot(V::load(a.Y + (size_t)v * a.ldy + c), g[k]);
-        if (a.sides & 1) p += V::dot(V::load(a.X + (size_t)v * a.ldx + c), V::load(a.dX + (size_t)v * a.lddx + c));
+        if (first && a.d_norm != nullptr) {
+          if (a.sides & 2) p += V::dot(V::load(a.Y + (size_t)v * a.ldy + c), g[k]);
+          if (a.sides & 1) p += V::dot(V::load(a.X + (size_t)v * a.ldx + c), V::load(a.dX + (size_t)v * a.lddx + c));
+        }
       }
     }
     p = group_sum<G>(p);
-    if (row_ok && lg == 0 && a.d_norm != nullptr) a.d_norm[v] = p / nv;
+    if (row_ok && first && lg == 0 && a.d_norm != nullptr) a.d_norm[v] = p / nv;
 
     if (WEIGHTED) {
 #pragma unroll
       for (int k = 0; k < C; ++k) g[k] = V::scaled(g[k], (a.sides & 2) ? nv : 1.f);
       const int maxlen = (G == 32) ? len : warp_max_int(len);
       const float* xcol = a.X + (size_t)lg * VW;
+      const bool src_scaled = a.norm != nullptr && (a.sides & 1);
+      int nidx = 0, net = 0;
+      float nns = 0.f;
+      if (lg < len) {
+        const int s = s0 + lg;
+        nidx = a.indices[s];
+        net = a.etype[s];
+        nns = src_scaled ? __ldg(a.norm + nidx) : 1.f;
+      }
       for (int base = 0; base < maxlen; base += G) {
-        int idx = 0, et = 0;
-        float ns = 0.f;
-        if (base + lg < len) {
-          const int s = s0 + base + lg;
-          idx = a.indices[s];
-          et = a.etype[s];
-          ns = (a.norm != nullptr && (a.sides & 1)) ? __ldg(a.norm + idx) : 1.f;
+        const int idx = nidx, et = net;
+        const float ns = nns;
+        nidx = net = 0;
+        nns = 0.f;
+        if (base + G + lg < len) {
+          const int s = s0 + base + G + lg;
+          nidx = a.indices[s];
+          net = a.etype[s];
+          nns = src_scaled ? __ldg(a.norm + nidx) : 1.f;
         }
         const int cnt = min(G, maxlen - base);
         for (int j = 0; j < cnt; j += U) {
@@ -413,7 +510,8 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
                               const float* theta, float alpha, int num_relations,
                               const float* norm_src, const float* norm_dst, const float* X,
                               int64_t ldx, float* Y, int64_t ldy, int64_t row_begin,
-                              int64_t row_end, int feat, void* stream) {
+                              int64_t row_end, int feat, const regnn_rowsplit_t* split,
+                              float* split_workspace, void* stream) {
   REGNN_REQUIRE(indptr && indices && X && Y, REGNN_ERR_INVALID_ARG, "spmm_fwd: null pointer");
   REGNN_REQUIRE(etype == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd: etype without theta");
   REGNN_REQUIRE(etype == nullptr || (num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS),
@@ -426,13 +524,24 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
   Shape sh;
   REGNN_REQUIRE(pick_shape(feat, vec_ok, &sh), REGNN_ERR_UNSUPPORTED_SHAPE,
                 "spmm_fwd: feature width %d too wide (max 1024 aligned / 256 unaligned)", feat);
+  const bool use_split = split != nullptr && split->num_frags > 0;
+  REGNN_REQUIRE(!use_split || (split_workspace && split->long_rows && split->frag_ptr && split->frag_row &&
+                               split->frag_begin && split->threshold > 0),
+                REGNN_ERR_INVALID_ARG, "spmm_fwd: incomplete row split");
+  const int items_per_block = kWarpsPerBlock * (32 / sh.G);
+  const int nfrag = use_split ? split->num_frags : 0;
+  const int nfrag_pad = (nfrag + items_per_block - 1) / items_per_block * items_per_block;
   SpmmArgs a{indptr, indices, etype, theta, alpha, num_relations, norm_src, norm_dst, X, ldx, Y, ldy,
-             row_begin, row_end, feat};
-  const int rows_per_block = kWarpsPerBlock * (32 / sh.G);
-  const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+             row_begin, row_end, feat,
+             use_split ? split->frag_row : nullptr, use_split ? split->frag_begin : nullptr, nfrag, nfrag_pad,
+             use_split ? split->threshold : 0x7fffffff, split_workspace};
+  const int64_t blocks = (rows + nfrag_pad + items_per_block - 1) / items_per_block;
   bool launched = false;
   REGNN_DISPATCH_SHAPES((spmm_kernel<G, C, VW><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(a)))
   REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: no kernel for G=%d C=%d VW=%d", sh.G, sh.C, sh.VW);
+  if (use_split)
+    spmm_frag_finalize_kernel<<<split->num_long, 128, 0, (cudaStream_t)stream>>>(
+        split->long_rows, split->frag_ptr, split->num_long, split_workspace, norm_dst, Y, ldy, feat, row_begin, row_end);
   return check_launch("regnn_spmm_fwd");
 }
 
@@ -441,7 +550,8 @@ extern "C" int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, c
                                 const float* norm, int norm_sides, const float* X, int64_t ldx, const float* Y,
                                 int64_t ldy, const float* Gd, int64_t ldg, const float* dX,
                                 int64_t lddx, int64_t row_begin, int64_t row_end, int feat,
-                                double* partials, float* d_theta, float* d_norm, void* stream_) {
+                                double* partials, float* d_theta, float* d_norm,
+                                const regnn_rowsplit_t* split, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && indices && X && Y && Gd && dX, REGNN_ERR_INVALID_ARG, "spmm_bwd_w: null pointer");
   const bool weighted = etype != nullptr;
@@ -457,8 +567,12 @@ extern "C" int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, c
   Shape sh;
   REGNN_REQUIRE(pick_shape(feat, vec_ok, &sh), REGNN_ERR_UNSUPPORTED_SHAPE,
                 "spmm_bwd_w: feature width %d too wide", feat);
+  const bool use_split = split != nullptr && split->num_frags > 0;
+  REGNN_REQUIRE(!use_split || (split->frag_row && split->frag_begin && split->threshold > 0), REGNN_ERR_INVALID_ARG,
+                "spmm_bwd_w: incomplete row split");
   SpmmBwdArgs a{indptr, indices, etype, R, norm, norm != nullptr ? (norm_sides & 3) : 0, X, ldx, Y, ldy, Gd, ldg, dX, lddx, row_begin, row_end,
-                feat, partials, d_norm};
+                feat, partials, d_norm, use_split ? split->frag_row : nullptr, use_split ? split->frag_begin : nullptr,
+                use_split ? split->num_frags : 0, use_split ? split->threshold : 0x7fffffff};
   const int nb = partial_blocks(rows);
   const size_t smem = weighted ? bins_smem_bytes(R) : 16;
   bool launched = false;

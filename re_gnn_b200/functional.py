@@ -42,7 +42,8 @@ class _Propagate(torch.autograd.Function):
         weighted = theta is not None
         ns = norm if sides & 1 else None
         nd = norm if sides & 2 else None
-        y = ops.spmm(csr['indptr'], csr['indices'], etv[0] if weighted else None, theta, alpha, ns, nd, x)
+        y = ops.spmm(csr['indptr'], csr['indices'], etv[0] if weighted else None, theta, alpha, ns, nd, x,
+                     split=csr.get('split'))
         ctx.graph, ctx.etv, ctx.alpha, ctx.weighted, ctx.has_norm = graph, etv, alpha, weighted, norm is not None
         ctx.sides = sides
         ctx.save_for_backward(x, y, theta if weighted else None, norm)
@@ -63,12 +64,12 @@ class _Propagate(torch.autograd.Function):
             ns = norm if ctx.sides & 2 else None
             nd = norm if ctx.sides & 1 else None
             dx = ops.spmm(csr['indptr_t'], csr['indices_t'], ctx.etv[1] if ctx.weighted else None, theta,
-                          ctx.alpha, ns, nd, g)
+                          ctx.alpha, ns, nd, g, split=csr.get('split_t'))
         if need_theta or need_norm:
             if dx is None:
                 dx = torch.zeros_like(x)
             d_theta, d_norm = ops.spmm_bwd_w(csr, ctx.etv[0] if need_theta else None, theta if need_theta else None,
-                                             ctx.alpha, norm, x, y, g, dx, sides=ctx.sides)
+                                             ctx.alpha, norm, x, y, g, dx, sides=ctx.sides, split=csr.get('split'))
             if d_theta is not None:
                 d_theta = d_theta.view_as(theta)
         return None, None, (dx if need_x else None), d_theta, None, (d_norm if need_norm else None), None

@@ -34,6 +34,30 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+SPLIT_THRESHOLD = 256   # rows with more slots are cut into fragments of this many slots
+
+
+def _row_split(indptr, threshold):
+    """Long-row decomposition of one CSR view (``regnn_rowsplit_t``): index bookkeeping with torch ops on the
+    device, once per graph.  Returns None when no row exceeds the threshold."""
+    deg = (indptr[1:] - indptr[:-1]).to(torch.int64)
+    long_rows = torch.nonzero(deg > threshold).view(-1)
+    if long_rows.numel() == 0:
+        return None
+    nfr = (deg[long_rows] + threshold - 1) // threshold
+    frag_ptr = torch.zeros(long_rows.numel() + 1, dtype=torch.int64, device=indptr.device)
+    frag_ptr[1:] = torch.cumsum(nfr, 0)
+    total = int(frag_ptr[-1].item())
+    frag_row = torch.repeat_interleave(long_rows, nfr)
+    within = torch.arange(total, device=indptr.device) - torch.repeat_interleave(frag_ptr[:-1], nfr)
+    frag_begin = indptr.to(torch.int64)[frag_row] + within * threshold
+    t = dict(long_rows=long_rows.to(torch.int32), frag_ptr=frag_ptr.to(torch.int32),
+             frag_row=frag_row.to(torch.int32), frag_begin=frag_begin.to(torch.int32))
+    t['struct'] = _lib.RowSplit(t['long_rows'].data_ptr(), t['frag_ptr'].data_ptr(), t['frag_row'].data_ptr(),
+                                t['frag_begin'].data_ptr(), long_rows.numel(), total, threshold)
+    return t
+
+
 class Graph:
     is_block = False
 
@@ -132,6 +156,8 @@ class Graph:
             _lib.call('regnn_csr_build', _ptr(self._src), _ptr(self._dst), n, e, _ptr(out['indptr']),
                       _ptr(out['indices']), _ptr(out['eid']), _ptr(out['row']), _ptr(out['indptr_t']),
                       _ptr(out['indices_t']), _ptr(out['slot_t']), _ptr(ws), ws_bytes, _stream())
+            out['split'] = _row_split(out['indptr'], SPLIT_THRESHOLD)
+            out['split_t'] = _row_split(out['indptr_t'], SPLIT_THRESHOLD)
         self._csr = out
         return out
 

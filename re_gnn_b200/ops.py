@@ -60,8 +60,16 @@ def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None):
     return d_theta
 
 
-def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None):
-    """Y[v] = norm_dst[v] * sum_s w[etype[s]] * norm_src[indices[s]] * X[indices[s]] over rows."""
+def _split_args(split, feat, device):
+    if split is None:
+        return None, None, 0
+    ws = torch.empty(split['struct'].num_frags * feat, dtype=torch.float32, device=device)
+    return ctypes.byref(split['struct']), ws, 1
+
+
+def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None, split=None):
+    """Y[v] = norm_dst[v] * sum_s w[etype[s]] * norm_src[indices[s]] * X[indices[s]] over rows.
+    ``split``: the long-row decomposition of this CSR view (Graph.csr()['split' | 'split_t'])."""
     x = _f32(x)
     n = indptr.numel() - 1
     rb, re = _rows(rows, n)
@@ -71,15 +79,16 @@ def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None,
         out = torch.empty((n, f), dtype=torch.float32, device=x.device)
         if (rb, re) != (0, n):
             out.zero_()
+    sp, ws, extra = _split_args(split, f, x.device)
     with torch.cuda.device(x.device):
         _lib.call('regnn_spmm_fwd', _ptr(indptr), _ptr(indices), _ptr(etype) if theta is not None else None,
                   _ptr(theta), float(alpha), theta.numel() if theta is not None else 0, _ptr(norm_src),
-                  _ptr(norm_dst), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rb, re, f, _stream())
-        _lib.count_launches(1)
+                  _ptr(norm_dst), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rb, re, f, sp, _ptr(ws), _stream())
+        _lib.count_launches(1 + extra)
     return out
 
 
-def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3):
+def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3, split=None):
     """-> (d_theta[R] or None, d_norm[N] or None).  sides: bit0 source side scaled, bit1 destination."""
     x, y, g, dx = _f32(x), _f32(y), _f32(g), _f32(dx)
     n = csr['indptr'].numel() - 1
@@ -94,7 +103,7 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3)
         _lib.call('regnn_spmm_bwd_w', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(et_csr) if weighted else None,
                   _ptr(theta), float(alpha), r, _ptr(norm), int(sides), _ptr(x), x.stride(0), _ptr(y), y.stride(0),
                   _ptr(g), g.stride(0), _ptr(dx), dx.stride(0), rb, re, x.shape[1], _ptr(partials),
-                  _ptr(d_theta), _ptr(d_norm), _stream())
+                  _ptr(d_theta), _ptr(d_norm), ctypes.byref(split['struct']) if split is not None else None, _stream())
         _lib.count_launches(2 if weighted else 1)
     return d_theta, d_norm
 

@@ -34,7 +34,14 @@ def _all_gather_rows(full, own, bounds, group):
     """Gathers every rank's row block into ``full`` ([N, F], global row ids).  Blocks are uneven
     (balanced by edges, not rows); ProcessGroupNCCL handles that with grouped broadcasts."""
     views = [full[bounds[p]:bounds[p + 1]] for p in range(len(bounds) - 1)]
-    dist.all_gather(views, own.contiguous(), group=group)
+    if dist.get_backend(group) == 'nccl':
+        dist.all_gather(views, own.contiguous(), group=group)
+    else:  # gloo (CPU tests) has no uneven all-gather: one broadcast per owner
+        rank = dist.get_rank(group)
+        views[rank].copy_(own)
+        for p, v in enumerate(views):
+            if v.numel():
+                dist.broadcast(v, src=dist.get_global_rank(group, p) if group is not None else p, group=group)
     return full
 
 
@@ -49,7 +56,8 @@ class _PartitionedPropagate(torch.autograd.Function):
         x_full = torch.empty((n, x_own.shape[1]), dtype=x_own.dtype, device=x_own.device)
         _all_gather_rows(x_full, x_own, bounds, group)
         y_full = torch.empty_like(x_full)
-        ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, alpha, norm, norm, x_full, rows=(rb, re), out=y_full)
+        ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, alpha, norm, norm, x_full, rows=(rb, re), out=y_full,
+                 split=csr.get('split'))
         ctx.graph, ctx.etv, ctx.alpha, ctx.bounds, ctx.rank, ctx.group = graph, etv, alpha, bounds, rank, group
         ctx.save_for_backward(x_full, y_full, theta, norm)
         return y_full[rb:re]
@@ -64,9 +72,9 @@ class _PartitionedPropagate(torch.autograd.Function):
         _all_gather_rows(g_full, g_own, bounds, ctx.group)
         dx_full = torch.empty_like(x_full)
         ops.spmm(csr['indptr_t'], csr['indices_t'], ctx.etv[1], theta, ctx.alpha, norm, norm, g_full,
-                 rows=(rb, re), out=dx_full)
+                 rows=(rb, re), out=dx_full, split=csr.get('split_t'))
         d_theta, d_norm = ops.spmm_bwd_w(csr, ctx.etv[0], theta, ctx.alpha, norm, x_full, y_full, g_full, dx_full,
-                                         rows=(rb, re))
+                                         rows=(rb, re), split=csr.get('split'))
         # d_theta / d_norm hold this rank's rows only; the caller all-reduces the parameter gradient once.
         return None, None, dx_full[rb:re], d_theta.view_as(theta), None, d_norm, None, None, None
 

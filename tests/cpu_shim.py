@@ -61,7 +61,7 @@ def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None):
     return dw * alpha * _lgrad(th * alpha, SLOPE)
 
 
-def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None):
+def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None, split=None):
     x = x.detach()
     row, col = _rows_of(indptr), indices.long()
     coef = torch.ones(col.numel(), dtype=x.dtype)
@@ -72,16 +72,30 @@ def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None,
     y = torch.zeros((indptr.numel() - 1, x.shape[1]), dtype=x.dtype).index_add(0, row, coef[:, None] * x[col])
     if norm_dst is not None:
         y = y * norm_dst.detach()[:, None]
+    if rows is not None:          # only the owned row block is written (partitioned runs)
+        keep = torch.zeros(y.shape[0], 1, dtype=y.dtype)
+        keep[rows[0]:rows[1]] = 1
+        y = y * keep
+    if out is not None:
+        if rows is None:
+            out.copy_(y)
+        else:
+            out[rows[0]:rows[1]] = y[rows[0]:rows[1]]
+        return out
     return y
 
 
-def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3):
+def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3, split=None):
     x, y, g, dx = x.detach(), y.detach(), g.detach(), dx.detach()
     d_norm = None
     if norm is None:
         sides = 0
+    n = csr['indptr'].numel() - 1
+    own = torch.zeros(n, dtype=x.dtype)
+    own[slice(*rows) if rows is not None else slice(0, n)] = 1
     if norm is not None:
         d_norm = ((y * g).sum(1) * bool(sides & 2) + (x * dx).sum(1) * bool(sides & 1)) / norm.detach()
+        d_norm = torch.where(own > 0, d_norm, torch.zeros_like(d_norm))   # foreign rows hold garbage
     d_theta = None
     if theta is not None:
         th = theta.detach().view(-1)
@@ -91,7 +105,7 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3)
             dwe = dwe * norm.detach()[col]
         if sides & 2:
             dwe = dwe * norm.detach()[row]
-        dw = torch.zeros_like(th).index_add(0, et_csr.long(), dwe)
+        dw = torch.zeros_like(th).index_add(0, et_csr.long(), torch.where(own[row] > 0, dwe, torch.zeros_like(dwe)))
         d_theta = dw * alpha * _lgrad(th * alpha, SLOPE)
     return d_theta, d_norm
 

@@ -55,8 +55,8 @@ def test_csr_build_bit_exact(n, e, seed):
     if e > 10:
         dst[: e // 3] = rng.randint(0, min(n, 3), size=e // 3)   # hub rows
     g = Graph(src, dst, n).to(DEV)
-    got = {k: v.cpu().numpy() for k, v in g.csr().items()}
     want = csr_oracle.csr_build(src, dst, n)
+    got = {k: g.csr()[k].cpu().numpy() for k in want}
     for k in want:
         assert got[k].dtype == np.int32 and np.array_equal(got[k], want[k]), k
     assert np.array_equal(g.in_degrees().cpu().numpy(), csr_oracle.in_degrees(dst, n))
@@ -72,8 +72,8 @@ def test_csr_build_named_shapes_bit_exact():
     for name in ('dblp', 'acm', 'imdb'):
         d = synth.hetero_graph(name)
         g = _graph(d)
-        got = {k: v.cpu().numpy() for k, v in g.csr().items()}
         want = csr_oracle.csr_build(d['src'], d['dst'], d['num_nodes'])
+        got = {k: g.csr()[k].cpu().numpy() for k in want}
         for k in want:
             assert np.array_equal(got[k], want[k]), (name, k)
         a, b = g.etype_views(torch.as_tensor(d['etype']), d['num_relations'])

@@ -1,0 +1,89 @@
+"""Multi-rank path on CPU: world_size-2 ``gloo`` processes run the destination-row-partitioned RE-layer
+(re_gnn_b200/partition.py) with the CUDA operators replaced by tests/cpu_shim.py and must reproduce the
+single-process result (outputs, feature gradients, relation-embedding gradient)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _single(d, x, gout, theta0):
+    from re_gnn_b200 import Graph, functional as RF
+    g = Graph(d['src'], d['dst'], d['num_nodes'])
+    et = torch.as_tensor(d['etype'])
+    etv = g.etype_views(et, d['num_relations'])
+    xs = x.clone().requires_grad_(True)
+    th = theta0.clone().requires_grad_(True)
+    out = RF.propagate(g, etv, xs, th, 100.0, RF.weighted_degree_norm(g, etv, th, 100.0, -0.5))
+    out.backward(gout)
+    return out.detach(), xs.grad, th.grad
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import cpu_shim
+    from re_gnn_b200 import Graph, functional as RF, graph as G, ops, partition, synth
+
+    class MP:  # minimal monkeypatch stand-in
+        @staticmethod
+        def setattr(obj, name, val):
+            setattr(obj, name, val)
+    cpu_shim.install(MP)
+    d = synth.hetero_graph('dblp', seed=5, scale=0.03)
+    n, r = d['num_nodes'], d['num_relations']
+    rng = np.random.RandomState(0)
+    x = torch.as_tensor(rng.randn(n, 8))
+    gout = torch.as_tensor(rng.randn(n, 8))
+    theta0 = torch.as_tensor(rng.uniform(0.5, 1.5, (r, 1)) / 100.0)
+    g = Graph(d['src'], d['dst'], n)
+    etv = g.etype_views(torch.as_tensor(d['etype']), r)
+    bounds = partition.row_blocks(g.csr()['indptr'], world)
+    rb, re = bounds[rank], bounds[rank + 1]
+    xo = x[rb:re].clone().requires_grad_(True)
+    th = theta0.clone().requires_grad_(True)
+    nrm = RF.weighted_degree_norm(g, etv, th, 100.0, -0.5)
+    out = partition.partitioned_propagate(g, etv, xo, th, 100.0, nrm, bounds, rank)
+    out.backward(gout[rb:re])
+    partition.allreduce_relation_grads([th])
+    ref_out, ref_dx, ref_dth = _single(d, x, gout, theta0)
+    ok = (torch.allclose(out.detach(), ref_out[rb:re], rtol=1e-12, atol=1e-12)
+          and torch.allclose(xo.grad, ref_dx[rb:re], rtol=1e-12, atol=1e-12)
+          and torch.allclose(th.grad, ref_dth, rtol=1e-10, atol=1e-12)
+          and re > rb and bounds[-1] == n)
+    if not ok:
+        print('rank', rank, 'bounds', bounds, 'out', (out.detach() - ref_out[rb:re]).abs().max().item(),
+              'dx', (xo.grad - ref_dx[rb:re]).abs().max().item(), 'dth', (th.grad - ref_dth).abs().max().item(),
+              file=sys.stderr)
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_blocks_balance_edges():
+    sys.path.insert(0, ROOT)
+    from re_gnn_b200 import partition
+    indptr = torch.tensor([0, 10, 10, 11, 30, 31, 40])
+    assert partition.row_blocks(indptr, 1) == [0, 6]
+    b = partition.row_blocks(indptr, 2)
+    assert b[0] == 0 and b[-1] == 6 and all(x <= y for x, y in zip(b, b[1:]))
+    b4 = partition.row_blocks(indptr, 4)
+    assert len(b4) == 5 and b4[-1] == 6
+
+
+@pytest.mark.timeout(300)
+def test_partitioned_layer_matches_single_process_world2():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.get_context('spawn').Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
