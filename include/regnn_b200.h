@@ -157,7 +157,8 @@ int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, const int32_t* 
                   const uint8_t* etype_csr, const float* theta, float alpha, int num_relations,
                   const float* feat, const float* el, const float* er, float negative_slope,
                   const float* keep, int num_heads, int head_dim, int64_t row_begin, int64_t row_end,
-                  float* out, float* rowmax, float* rowsum, float* attn_out, void* stream);
+                  float* out, float* rowmax, float* rowsum, float* attn_out, const regnn_rowsplit_t* split,
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
 
 /* Backward, destination-major pass.  G = dL/d out.  Produces, per CSR slot, a_csr = a*keep and
  * dpre_csr = dL/d(el[src]+er[dst]+w) (both [E,H], slot order), d_er [N,H] and d_theta [R,H].
@@ -168,7 +169,8 @@ int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32
                       const float* keep, const float* out, const float* rowmax, const float* rowsum,
                       const float* G, int num_heads, int head_dim, int64_t row_begin,
                       int64_t row_end, float* a_csr, float* dpre_csr, float* d_er, double* partials,
-                      float* d_theta, void* stream);
+                      float* d_theta, const regnn_rowsplit_t* split,
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
 
 /* Backward, source-major pass over the transposed view:
  *   d_feat[u,h,:] = sum_{j in Out(u)} a_csr[slot_t[j],h] * G[indices_t[j],h,:]
@@ -177,7 +179,8 @@ int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32
 int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
                       const float* a_csr, const float* dpre_csr, const float* G, int num_heads,
                       int head_dim, int64_t row_begin, int64_t row_end, float* d_feat, float* d_el,
-                      void* stream);
+                      const regnn_rowsplit_t* split_t /* of the transposed view */,
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused REGATv2 layer core (layer/REGATv2Conv.py:133-152):
@@ -190,7 +193,8 @@ int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t
                     const float* fs, const float* fd, const float* attn, float negative_slope,
                     const float* keep, int num_heads, int head_dim, int64_t row_begin,
                     int64_t row_end, float* out, float* rowmax, float* rowsum, float* attn_out,
-                    void* stream);
+                    const regnn_rowsplit_t* split,
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
 
 /* Backward, destination-major pass: a_csr = a*keep, dl_csr = dL/dl (both [E,H] slot order),
  * d_fd [N,H,D], d_attn [H,D], d_theta [R,H].
@@ -202,7 +206,8 @@ int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices, const int
                         const float* rowmax, const float* rowsum, const float* G, int num_heads,
                         int head_dim, int64_t row_begin, int64_t row_end, float* a_csr,
                         float* dl_csr, float* d_fd, float* d_attn, double* partials, float* d_theta,
-                        void* stream);
+                        const regnn_rowsplit_t* split,
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
 
 /* Backward, source-major pass:
  *   d_fs[u,h,d] = sum_{j in Out(u)} ( a_csr[s,h]*G[v,h,d]
@@ -211,7 +216,8 @@ int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices, const int
 int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
                         const float* a_csr, const float* dl_csr, const float* fs, const float* fd,
                         const float* attn, float negative_slope, const float* G, int num_heads,
-                        int head_dim, int64_t row_begin, int64_t row_end, float* d_fs, void* stream);
+                        int head_dim, int64_t row_begin, int64_t row_end, float* d_fs, const regnn_rowsplit_t* split_t /* of the transposed view */,
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,46 @@ struct AttnArgs {
   int partial_stride;
   const float* a_csr;      // bwd_src inputs
   const float* d_csr;
+  // long-row fragments (regnn_rowsplit_t): items [0, nfrag) are fragments (padded to nfrag_pad in the
+  // grid-mapped kernels); their partial results go to p0/p1/p2 and are merged by the finalize kernels
+  const int32_t* frag_row;
+  const int32_t* frag_begin;
+  int nfrag, nfrag_pad, threshold;
+  float* p0;               // [nfrag][H*D]  partial rows (fwd: un-normalised acc; bwd: d_feat / d_fd / d_fs)
+  float* p1;               // [nfrag][H]    fwd: fragment max      bwd: d_er / d_el partial
+  float* p2;               // [nfrag][H]    fwd: fragment sum
 };
+
+struct WorkItem {
+  int64_t v, fi;
+  int s0, len;
+  bool ok, frag, first;
+};
+
+// Item wi of a kernel whose first `nfrag_items` items are long-row fragments and the rest ordinary rows.
+__device__ __forceinline__ WorkItem decode_item(const AttnArgs& a, int64_t wi, int64_t nfrag_items) {
+  WorkItem w{0, wi, 0, 0, false, false, true};
+  if (wi < nfrag_items) {
+    w.frag = true;
+    if (wi < a.nfrag) {
+      w.v = a.frag_row[wi];
+      if (w.v >= a.row_begin && w.v < a.row_end) {
+        w.s0 = a.frag_begin[wi];
+        w.len = min(a.threshold, a.indptr[w.v + 1] - w.s0);
+        w.first = w.s0 == a.indptr[w.v];
+        w.ok = true;
+      }
+    }
+  } else {
+    w.v = a.row_begin + (wi - nfrag_items);
+    if (w.v < a.row_end) {
+      w.s0 = a.indptr[w.v];
+      w.len = a.indptr[w.v + 1] - w.s0;
+      w.ok = w.len <= a.threshold;  // longer rows are covered by fragments
+    }
+  }
+  return w;
+}
 
 template <int C> struct UnrollA { static constexpr int U = C <= 1 ? 4 : (C <= 4 ? 2 : 1); };
 
@@ -96,10 +135,10 @@ gat_fwd_kernel(AttnArgs a) {
   float* sc_s = p_s + 32 * HP;
   float* m_s = sc_s + H;
   load_rel_table(w_s, a);
-  const int64_t v = a.row_begin + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (v >= a.row_end) return;
-
-  const int s0 = a.indptr[v], len = a.indptr[v + 1] - s0;
+  const WorkItem it = decode_item(a, (int64_t)blockIdx.x * kWarpsPerBlock + warp, a.nfrag_pad);
+  if (!it.ok) return;
+  const int64_t v = it.v;
+  const int s0 = it.s0, len = it.len;
   const Slices<C> sl(lane, H, D);
   float4 acc[C];
 #pragma unroll
@@ -166,6 +205,17 @@ gat_fwd_kernel(AttnArgs a) {
     __syncwarp();
   }
 
+  if (it.frag) {  // un-normalised partial + fragment statistics; attn_frag_finalize_kernel merges them
+    if (lane < H) {
+      a.p1[(size_t)it.fi * H + lane] = m_run;
+      a.p2[(size_t)it.fi * H + lane] = s_run;
+    }
+    float* pcol = a.p0 + (size_t)it.fi * HD + (size_t)lane * 4;
+#pragma unroll
+    for (int k = 0; k < C; ++k)
+      if (sl.ok[k]) st4(pcol + (size_t)k * 128, acc[k]);
+    return;
+  }
   if (lane < H) {
     const float m = len > 0 ? m_run : 0.f;
     a.o1[(size_t)v * H + lane] = m;
@@ -209,12 +259,14 @@ gat_bwd_dst_kernel(AttnArgs a) {
   load_rel_table(w_s, a);
   const Slices<C> sl(lane, H, D);
   const float* fcol = a.feat + (size_t)lane * 4;
-  const int64_t rows = a.row_end - a.row_begin;
+  const int64_t items = a.nfrag + (a.row_end - a.row_begin);
 
-  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp; r < rows;
+  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp; r < items;
        r += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const int64_t v = a.row_begin + r;
-    const int s0 = a.indptr[v], len = a.indptr[v + 1] - s0;
+    const WorkItem it = decode_item(a, r, a.nfrag);
+    if (!it.ok) continue;
+    const int64_t v = it.v;
+    const int s0 = it.s0, len = it.len;
     float4 g[C];
     float S[C], m[C], inv[C], erv[C], der[C];
 #pragma unroll
@@ -285,7 +337,10 @@ gat_bwd_dst_kernel(AttnArgs a) {
     }
 #pragma unroll
     for (int k = 0; k < C; ++k)
-      if (sl.leader[k]) a.o2[(size_t)v * H + sl.head[k]] = der[k];
+      if (sl.leader[k]) {
+        if (it.frag) a.p1[(size_t)it.fi * H + sl.head[k]] = der[k];
+        else a.o2[(size_t)v * H + sl.head[k]] = der[k];
+      }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < RH; i += blockDim.x) {
@@ -307,9 +362,10 @@ gat_bwd_src_kernel(AttnArgs a) {
   const int H = a.H, D = a.D, HD = H * D, HP = H | 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* p_s = smem + warp * (32 * HP);
-  const int64_t u_row = a.row_begin + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (u_row >= a.row_end) return;
-  const int t0 = a.indptr[u_row], len = a.indptr[u_row + 1] - t0;
+  const WorkItem it = decode_item(a, (int64_t)blockIdx.x * kWarpsPerBlock + warp, a.nfrag_pad);
+  if (!it.ok) return;
+  const int64_t u_row = it.v;
+  const int t0 = it.s0, len = it.len;
   const Slices<C> sl(lane, H, D);
   float4 acc[C];
 #pragma unroll
@@ -355,11 +411,14 @@ gat_bwd_src_kernel(AttnArgs a) {
     }
     __syncwarp();
   }
-  float* ocol = a.o0 + (size_t)u_row * HD + (size_t)lane * 4;
+  float* ocol = it.frag ? a.p0 + (size_t)it.fi * HD + (size_t)lane * 4 : a.o0 + (size_t)u_row * HD + (size_t)lane * 4;
 #pragma unroll
   for (int k = 0; k < C; ++k)
     if (sl.ok[k]) st4(ocol + (size_t)k * 128, acc[k]);
-  if (a.d_csr != nullptr && lane < H) a.o1[(size_t)u_row * H + lane] = del_run;
+  if (a.d_csr != nullptr && lane < H) {
+    if (it.frag) a.p1[(size_t)it.fi * H + lane] = del_run;
+    else a.o1[(size_t)u_row * H + lane] = del_run;
+  }
 }
 
 // =================================================================================================
@@ -377,9 +436,10 @@ gatv2_fwd_kernel(AttnArgs a) {
   float* m_s = smem + RH + warp * 2 * H;
   float* inv_s = m_s + H;
   load_rel_table(w_s, a);
-  const int64_t v = a.row_begin + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (v >= a.row_end) return;
-  const int s0 = a.indptr[v], len = a.indptr[v + 1] - s0;
+  const WorkItem it = decode_item(a, (int64_t)blockIdx.x * kWarpsPerBlock + warp, a.nfrag_pad);
+  if (!it.ok) return;
+  const int64_t v = it.v;
+  const int s0 = it.s0, len = it.len;
   const Slices<C> sl(lane, H, D);
   float4 acc[C], fdv[C], at[C];
   float m[C], s[C];
@@ -443,6 +503,18 @@ gatv2_fwd_kernel(AttnArgs a) {
       }
     }
   }
+  if (it.frag) {
+#pragma unroll
+    for (int k = 0; k < C; ++k)
+      if (sl.ok[k]) {
+        st4(a.p0 + (size_t)it.fi * HD + (size_t)(lane + 32 * k) * 4, acc[k]);
+        if (sl.leader[k]) {
+          a.p1[(size_t)it.fi * H + sl.head[k]] = m[k];
+          a.p2[(size_t)it.fi * H + sl.head[k]] = s[k];
+        }
+      }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < C; ++k) {
     if (sl.ok[k]) {
@@ -490,7 +562,7 @@ gatv2_bwd_dst_kernel(AttnArgs a) {
   load_rel_table(w_s, a);
   const Slices<C> sl(lane, H, D);
   const float* fcol = a.feat + (size_t)lane * 4;
-  const int64_t rows = a.row_end - a.row_begin;
+  const int64_t items = a.nfrag + (a.row_end - a.row_begin);
   float4 at[C], dat[C];
 #pragma unroll
   for (int k = 0; k < C; ++k) {
@@ -498,10 +570,12 @@ gatv2_bwd_dst_kernel(AttnArgs a) {
     at[k] = sl.ok[k] ? ldg4(a.el + (size_t)(lane + 32 * k) * 4) : zero4();
   }
 
-  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp; r < rows;
+  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp; r < items;
        r += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const int64_t v = a.row_begin + r;
-    const int s0 = a.indptr[v], len = a.indptr[v + 1] - s0;
+    const WorkItem it = decode_item(a, r, a.nfrag);
+    if (!it.ok) continue;
+    const int64_t v = it.v;
+    const int s0 = it.s0, len = it.len;
     float4 g[C], fdv[C], dfd[C];
     float S[C], m[C], inv[C];
 #pragma unroll
@@ -575,9 +649,10 @@ gatv2_bwd_dst_kernel(AttnArgs a) {
         }
       }
     }
+    float* drow = it.frag ? a.p0 + (size_t)it.fi * HD : a.o2 + (size_t)v * HD;
 #pragma unroll
     for (int k = 0; k < C; ++k)
-      if (sl.ok[k]) st4(a.o2 + (size_t)v * HD + (size_t)(lane + 32 * k) * 4, dfd[k]);
+      if (sl.ok[k]) st4(drow + (size_t)(lane + 32 * k) * 4, dfd[k]);
   }
 #pragma unroll
   for (int k = 0; k < C; ++k)
@@ -608,9 +683,10 @@ gatv2_bwd_src_kernel(AttnArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* p_s = smem + warp * (64 * HP);
   float* q_s = p_s + 32 * HP;
-  const int64_t u_row = a.row_begin + (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (u_row >= a.row_end) return;
-  const int t0 = a.indptr[u_row], len = a.indptr[u_row + 1] - t0;
+  const WorkItem it = decode_item(a, (int64_t)blockIdx.x * kWarpsPerBlock + warp, a.nfrag_pad);
+  if (!it.ok) return;
+  const int64_t u_row = it.v;
+  const int t0 = it.s0, len = it.len;
   const Slices<C> sl(lane, H, D);
   float4 acc[C], fsu[C], at[C];
 #pragma unroll
@@ -668,9 +744,88 @@ gatv2_bwd_src_kernel(AttnArgs a) {
     }
     __syncwarp();
   }
+  float* orow = it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)u_row * HD;
 #pragma unroll
   for (int k = 0; k < C; ++k)
-    if (sl.ok[k]) st4(a.o0 + (size_t)u_row * HD + (size_t)(lane + 32 * k) * 4, acc[k]);
+    if (sl.ok[k]) st4(orow + (size_t)(lane + 32 * k) * 4, acc[k]);
+}
+
+// =================================================================================================
+// Merges the fragments of every long row of a forward pass (online-softmax combine in fragment order):
+//   M = max_f m_f;  S = sum_f s_f*exp(m_f-M);  out = sum_f acc_f*exp(m_f-M) / S
+// and, for get_attention, normalises the row's stored logits.  One warp per long row.
+template <int C>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+attn_frag_finalize_kernel(AttnArgs a, const int32_t* __restrict__ long_rows,
+                          const int32_t* __restrict__ frag_ptr, int num_long) {
+  const int H = a.H, D = a.D, HD = H * D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = blockIdx.x * kWarpsPerBlock + warp;
+  if (l >= num_long) return;
+  const int64_t v = long_rows[l];
+  if (v < a.row_begin || v >= a.row_end) return;
+  const int f0 = frag_ptr[l], f1 = frag_ptr[l + 1];
+  const Slices<C> sl(lane, H, D);
+  float M = -INFINITY;  // lane h (< H) owns head h
+  if (lane < H)
+    for (int f = f0; f < f1; ++f) M = fmaxf(M, a.p1[(size_t)f * H + lane]);
+  float S = 0.f;
+  float4 acc[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) acc[k] = zero4();
+  for (int f = f0; f < f1; ++f) {
+    float sc = 0.f;
+    if (lane < H) {
+      sc = expf(a.p1[(size_t)f * H + lane] - M);
+      S += a.p2[(size_t)f * H + lane] * sc;
+    }
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      const float sk = __shfl_sync(0xffffffffu, sc, sl.head[k]);
+      if (sl.ok[k]) fma4(acc[k], sk, ldg4(a.p0 + (size_t)f * HD + (size_t)(lane + 32 * k) * 4));
+    }
+  }
+  const float inv = S > 0.f ? 1.f / S : 0.f;
+  if (lane < H) {
+    a.o1[(size_t)v * H + lane] = M;
+    a.o2[(size_t)v * H + lane] = S;
+  }
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    const float ik = __shfl_sync(0xffffffffu, inv, sl.head[k]);
+    if (sl.ok[k]) {
+      scale4(acc[k], ik);
+      st4(a.o0 + (size_t)v * HD + (size_t)(lane + 32 * k) * 4, acc[k]);
+    }
+  }
+  if (a.o3 != nullptr) {
+    __syncwarp();
+    const int s0 = a.indptr[v], len = a.indptr[v + 1] - s0;
+    for (int i = lane; i < len * H; i += 32) {
+      const int h = i % H;
+      const size_t o = (size_t)a.eid[s0 + i / H] * H + h;
+      const float s = a.o2[(size_t)v * H + h];
+      float av = expf(a.o3[o] - a.o1[(size_t)v * H + h]) * (s > 0.f ? 1.f / s : 0.f);
+      if (a.keep != nullptr) av *= a.keep[o];
+      a.o3[o] = av;
+    }
+  }
+}
+
+// out[v][c] = sum over the fragments of long row v of partial[f][c]  (fragment order; block per row)
+__global__ void frag_rowsum_kernel(const int32_t* __restrict__ long_rows, const int32_t* __restrict__ frag_ptr,
+                                   int num_long, const float* __restrict__ partial, int W,
+                                   float* __restrict__ out, int64_t row_begin, int64_t row_end) {
+  const int l = blockIdx.x;
+  if (l >= num_long) return;
+  const int64_t v = long_rows[l];
+  if (v < row_begin || v >= row_end) return;
+  const int f0 = frag_ptr[l], f1 = frag_ptr[l + 1];
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    float s = 0.f;
+    for (int f = f0; f < f1; ++f) s += partial[(size_t)f * W + c];
+    out[(size_t)v * W + c] = s;
+  }
 }
 
 // ---- dispatch ---------------------------------------------------------------------------------------
@@ -683,6 +838,31 @@ static int pick_c(int HD) {
   if (c <= 4) return 4;
   if (c <= 8) return 8;
   return 0;
+}
+
+// Fills the fragment fields of `a` from the caller's row split; returns false if it is incomplete.
+static bool apply_split(AttnArgs& a, const regnn_rowsplit_t* split, float* ws) {
+  a.nfrag = a.nfrag_pad = 0;
+  a.threshold = 0x7fffffff;
+  if (split == nullptr || split->num_frags <= 0) return true;
+  if (!ws || !split->long_rows || !split->frag_ptr || !split->frag_row || !split->frag_begin || split->threshold <= 0)
+    return false;
+  a.frag_row = split->frag_row;
+  a.frag_begin = split->frag_begin;
+  a.nfrag = split->num_frags;
+  a.nfrag_pad = (a.nfrag + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock;
+  a.threshold = split->threshold;
+  const size_t HD = (size_t)a.H * a.D;
+  a.p0 = ws;
+  a.p1 = ws + (size_t)a.nfrag * HD;
+  a.p2 = a.p1 + (size_t)a.nfrag * a.H;
+  return true;
+}
+
+static void launch_rowsum(const regnn_rowsplit_t* split, const float* partial, int W, float* out, int64_t rb,
+                          int64_t re, cudaStream_t stream) {
+  frag_rowsum_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->frag_ptr, split->num_long, partial,
+                                                          W, out, rb, re);
 }
 
 static int check_shape(const char* who, int H, int D, int R, bool has_rel, bool needs_dot) {
@@ -710,6 +890,16 @@ static int check_shape(const char* who, int H, int D, int R, bool has_rel, bool 
     if (rc_ != REGNN_OK) return rc_;                                                   \
   } while (0)
 
+#define REGNN_DISPATCH_FINALIZE(GRID)                                                                                  \
+  do {                                                                                                                 \
+    switch (pick_c(a.H * a.D)) {                                                                                       \
+      case 1: attn_frag_finalize_kernel<1><<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long); break; \
+      case 2: attn_frag_finalize_kernel<2><<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long); break; \
+      case 4: attn_frag_finalize_kernel<4><<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long); break; \
+      default: attn_frag_finalize_kernel<8><<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long); break; \
+    }                                                                                                                  \
+  } while (0)
+
 }  // namespace regnn
 
 using namespace regnn;
@@ -719,7 +909,8 @@ extern "C" int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, cons
                              int num_relations, const float* feat, const float* el, const float* er,
                              float negative_slope, const float* keep, int num_heads, int head_dim,
                              int64_t row_begin, int64_t row_end, float* out, float* rowmax,
-                             float* rowsum, float* attn_out, void* stream_) {
+                             float* rowsum, float* attn_out, const regnn_rowsplit_t* split, float* split_workspace,
+    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && indices && feat && el && er && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gat_fwd: null pointer");
   REGNN_REQUIRE((keep == nullptr && attn_out == nullptr) || eid != nullptr, REGNN_ERR_INVALID_ARG, "gat_fwd: keep/attn_out need eid");
@@ -735,10 +926,15 @@ extern "C" int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, cons
   a.R = etype_csr ? num_relations : 0; a.feat = feat; a.el = el; a.er = er; a.slope = negative_slope; a.keep = keep;
   a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end;
   a.o0 = out; a.o1 = rowmax; a.o2 = rowsum; a.o3 = attn_out;
+  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_fwd: incomplete row split");
   const int H = num_heads, HP = H | 1;
   const size_t smem = sizeof(float) * ((size_t)a.R * H + (size_t)kWarpsPerBlock * (32 * HP + 2 * H));
-  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned grid = (unsigned)((rows + a.nfrag_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
   REGNN_DISPATCH_C(gat_fwd_kernel, grid, smem);
+  if (a.nfrag > 0) {
+    const unsigned fgrid = (unsigned)((split->num_long + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    REGNN_DISPATCH_FINALIZE(fgrid);
+  }
   return check_launch("regnn_gat_fwd");
 }
 
@@ -749,7 +945,8 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
                                  const float* out, const float* rowmax, const float* rowsum,
                                  const float* Gd, int num_heads, int head_dim, int64_t row_begin,
                                  int64_t row_end, float* a_csr, float* dpre_csr, float* d_er,
-                                 double* partials, float* d_theta, void* stream_) {
+                                 double* partials, float* d_theta, const regnn_rowsplit_t* split, float* split_workspace,
+    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && indices && feat && el && er && out && rowmax && rowsum && Gd && a_csr && dpre_csr && d_er,
                 REGNN_ERR_INVALID_ARG, "gat_bwd_dst: null pointer");
@@ -766,10 +963,12 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
   a.out = out; a.rowmax = rowmax; a.rowsum = rowsum; a.G = Gd; a.H = num_heads; a.D = head_dim;
   a.row_begin = row_begin; a.row_end = row_end; a.o0 = a_csr; a.o1 = dpre_csr; a.o2 = d_er;
   a.partials = partials; a.partial_stride = a.R * num_heads;
+  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_dst: incomplete row split");
   const int RH = a.R * num_heads;
   const size_t smem = sizeof(float) * ((size_t)RH * (1 + kWarpsPerBlock)) + 16;
-  const int nb = partial_blocks(rows);
+  const int nb = partial_blocks(rows + a.nfrag);
   REGNN_DISPATCH_C(gat_bwd_dst_kernel, nb, smem);
+  if (a.nfrag > 0) launch_rowsum(split, a.p1, num_heads, d_er, row_begin, row_end, stream);
   if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH, RH, theta, alpha, d_theta, stream);
   return check_launch("regnn_gat_bwd_dst");
 }
@@ -777,7 +976,8 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
 extern "C" int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices_t,
                                  const int32_t* slot_t, const float* a_csr, const float* dpre_csr,
                                  const float* Gd, int num_heads, int head_dim, int64_t row_begin,
-                                 int64_t row_end, float* d_feat, float* d_el, void* stream_) {
+                                 int64_t row_end, float* d_feat, float* d_el, const regnn_rowsplit_t* split, float* split_workspace,
+    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr_t && indices_t && slot_t && a_csr && Gd && d_feat, REGNN_ERR_INVALID_ARG, "gat_bwd_src: null pointer");
   REGNN_REQUIRE(dpre_csr == nullptr || d_el != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_src: dpre_csr without d_el");
@@ -790,10 +990,15 @@ extern "C" int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices
   AttnArgs a{};
   a.indptr = indptr_t; a.indices = indices_t; a.eid = slot_t; a.a_csr = a_csr; a.d_csr = dpre_csr; a.G = Gd;
   a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end; a.o0 = d_feat; a.o1 = d_el;
+  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_src: incomplete row split");
   const int HP = num_heads | 1;
   const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * 32 * HP;
-  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned grid = (unsigned)((rows + a.nfrag_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
   REGNN_DISPATCH_C(gat_bwd_src_kernel, grid, smem);
+  if (a.nfrag > 0) {
+    launch_rowsum(split, a.p0, num_heads * head_dim, d_feat, row_begin, row_end, stream);
+    if (dpre_csr != nullptr) launch_rowsum(split, a.p1, num_heads, d_el, row_begin, row_end, stream);
+  }
   return check_launch("regnn_gat_bwd_src");
 }
 
@@ -803,7 +1008,8 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
                                const float* attn, float negative_slope, const float* keep,
                                int num_heads, int head_dim, int64_t row_begin, int64_t row_end,
                                float* out, float* rowmax, float* rowsum, float* attn_out,
-                               void* stream_) {
+                               const regnn_rowsplit_t* split, float* split_workspace,
+    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && indices && fs && fd && attn && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gatv2_fwd: null pointer");
   REGNN_REQUIRE((keep == nullptr && attn_out == nullptr) || eid != nullptr, REGNN_ERR_INVALID_ARG, "gatv2_fwd: keep/attn_out need eid");
@@ -819,9 +1025,14 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
   a.R = etype_csr ? num_relations : 0; a.feat = fs; a.fd = fd; a.el = attn; a.slope = negative_slope; a.keep = keep;
   a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end;
   a.o0 = out; a.o1 = rowmax; a.o2 = rowsum; a.o3 = attn_out;
+  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_fwd: incomplete row split");
   const size_t smem = sizeof(float) * ((size_t)a.R * num_heads + (size_t)kWarpsPerBlock * 2 * num_heads) + 16;
-  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned grid = (unsigned)((rows + a.nfrag_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
   REGNN_DISPATCH_C(gatv2_fwd_kernel, grid, smem);
+  if (a.nfrag > 0) {
+    const unsigned fgrid = (unsigned)((split->num_long + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    REGNN_DISPATCH_FINALIZE(fgrid);
+  }
   return check_launch("regnn_gatv2_fwd");
 }
 
@@ -832,7 +1043,8 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
                                    const float* out, const float* rowmax, const float* rowsum,
                                    const float* Gd, int num_heads, int head_dim, int64_t row_begin,
                                    int64_t row_end, float* a_csr, float* dl_csr, float* d_fd,
-                                   float* d_attn, double* partials, float* d_theta, void* stream_) {
+                                   float* d_attn, double* partials, float* d_theta, const regnn_rowsplit_t* split, float* split_workspace,
+    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && indices && fs && fd && attn && out && rowmax && rowsum && Gd && a_csr && dl_csr && d_fd && d_attn && partials,
                 REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: null pointer");
@@ -852,8 +1064,10 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
   const int RH = a.R * num_heads, HD = num_heads * head_dim;
   a.partials = partials; a.partial_stride = RH + HD;
   const size_t smem = sizeof(float) * ((size_t)((RH + 3) & ~3) * (1 + kWarpsPerBlock) + (size_t)kWarpsPerBlock * HD) + 16;
-  const int nb = partial_blocks(rows);
+  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: incomplete row split");
+  const int nb = partial_blocks(rows + a.nfrag);
   REGNN_DISPATCH_C(gatv2_bwd_dst_kernel, nb, smem);
+  if (a.nfrag > 0) launch_rowsum(split, a.p0, HD, d_fd, row_begin, row_end, stream);
   if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH + HD, RH, theta, alpha, d_theta, stream);
   launch_colsum_finalize(partials, nb, RH + HD, RH, HD, d_attn, stream);
   return check_launch("regnn_gatv2_bwd_dst");
@@ -864,7 +1078,8 @@ extern "C" int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indic
                                    const float* fs, const float* fd, const float* attn,
                                    float negative_slope, const float* Gd, int num_heads,
                                    int head_dim, int64_t row_begin, int64_t row_end, float* d_fs,
-                                   void* stream_) {
+                                   const regnn_rowsplit_t* split, float* split_workspace,
+    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr_t && indices_t && slot_t && a_csr && dl_csr && fs && fd && attn && Gd && d_fs,
                 REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: null pointer");
@@ -880,8 +1095,10 @@ extern "C" int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indic
   a.feat = fs; a.fd = fd; a.el = attn; a.slope = negative_slope; a.G = Gd;
   a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end; a.o0 = d_fs;
   const int HP = num_heads | 1;
+  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: incomplete row split");
   const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * 64 * HP;
-  const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned grid = (unsigned)((rows + a.nfrag_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
   REGNN_DISPATCH_C(gatv2_bwd_src_kernel, grid, smem);
+  if (a.nfrag > 0) launch_rowsum(split, a.p0, num_heads * head_dim, d_fs, row_begin, row_end, stream);
   return check_launch("regnn_gatv2_bwd_src");
 }

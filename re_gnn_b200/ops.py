@@ -108,6 +108,14 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3,
     return d_theta, d_norm
 
 
+def _attn_split(split, h, d, device):
+    """(byref(struct) | None, workspace | None, extra finalize launches flag) for the attention kernels."""
+    if split is None:
+        return None, None
+    ws = torch.empty(split['struct'].num_frags * (h * d + 2 * h), dtype=torch.float32, device=device)
+    return ctypes.byref(split['struct']), ws
+
+
 def _rel(theta, et_csr):
     if theta is None or et_csr is None:
         return None, None, 0
@@ -126,11 +134,12 @@ def gat_fwd(csr, et_csr, theta, alpha, feat, el, er, slope, keep=None, want_attn
     rowsum = torch.zeros((n, h), dtype=torch.float32, device=dev)
     e = csr['indices'].numel()
     attn = torch.zeros((e, h), dtype=torch.float32, device=dev) if want_attn else None
+    sp, ws = _attn_split(csr.get('split'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep), h, d,
-                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(attn), _stream())
-        _lib.count_launches(1)
+                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(attn), sp, _ptr(ws), _stream())
+        _lib.count_launches(1 + (sp is not None))
     return out, rowmax, rowsum, attn
 
 
@@ -146,12 +155,13 @@ def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowma
     d_er = torch.zeros((n, h), dtype=torch.float32, device=dev)
     partials = torch.empty(max(_lib.partial_blocks(re - rb) * r * h, 1), dtype=torch.float64, device=dev)
     d_theta = torch.empty((r, h), dtype=torch.float32, device=dev) if r else None
+    sp, ws = _attn_split(csr.get('split'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep),
                   _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dpre_csr),
-                  _ptr(d_er), _ptr(partials), _ptr(d_theta), _stream())
-        _lib.count_launches(2 if r else 1)
+                  _ptr(d_er), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _stream())
+        _lib.count_launches((2 if r else 1) + (sp is not None))
     return a_csr, dpre_csr, d_er, d_theta
 
 
@@ -162,10 +172,11 @@ def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None):
     dev = g.device
     d_feat = torch.empty_like(g) if (rb, re) == (0, n) else torch.zeros_like(g)
     d_el = torch.zeros((n, h), dtype=torch.float32, device=dev) if dpre_csr is not None else None
+    sp, ws = _attn_split(csr.get('split_t'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
-                  _ptr(a_csr), _ptr(dpre_csr), _ptr(g), h, d, rb, re, _ptr(d_feat), _ptr(d_el), _stream())
-        _lib.count_launches(1)
+                  _ptr(a_csr), _ptr(dpre_csr), _ptr(g), h, d, rb, re, _ptr(d_feat), _ptr(d_el), sp, _ptr(ws), _stream())
+        _lib.count_launches(1 + (2 if sp is not None else 0))
     return d_feat, d_el
 
 
@@ -181,11 +192,12 @@ def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_at
     rowsum = torch.zeros((n, h), dtype=torch.float32, device=dev)
     e = csr['indices'].numel()
     att = torch.zeros((e, h), dtype=torch.float32, device=dev) if want_attn else None
+    sp, ws = _attn_split(csr.get('split'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gatv2_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep), h, d,
-                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(att), _stream())
-        _lib.count_launches(1)
+                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(att), sp, _ptr(ws), _stream())
+        _lib.count_launches(1 + (sp is not None))
     return out, rowmax, rowsum, att
 
 
@@ -203,12 +215,13 @@ def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, row
     d_attn = torch.empty(h * d, dtype=torch.float32, device=dev)
     partials = torch.empty(_lib.partial_blocks(re - rb) * (r * h + h * d), dtype=torch.float64, device=dev)
     d_theta = torch.empty((r, h), dtype=torch.float32, device=dev) if r else None
+    sp, ws = _attn_split(csr.get('split'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gatv2_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep),
                   _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dl_csr),
-                  _ptr(d_fd), _ptr(d_attn), _ptr(partials), _ptr(d_theta), _stream())
-        _lib.count_launches(3 if r else 2)
+                  _ptr(d_fd), _ptr(d_attn), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _stream())
+        _lib.count_launches((3 if r else 2) + (sp is not None))
     return a_csr, dl_csr, d_fd, d_attn, d_theta
 
 
@@ -218,9 +231,10 @@ def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
     n, h, d = fs.shape
     rb, re = _rows(rows, n)
     d_fs = torch.empty_like(fs) if (rb, re) == (0, n) else torch.zeros_like(fs)
+    sp, ws = _attn_split(csr.get('split_t'), h, d, fs.device)
     with torch.cuda.device(fs.device):
         _lib.call('regnn_gatv2_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
                   _ptr(a_csr), _ptr(dl_csr), _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(g), h, d,
-                  rb, re, _ptr(d_fs), _stream())
-        _lib.count_launches(1)
+                  rb, re, _ptr(d_fs), sp, _ptr(ws), _stream())
+        _lib.count_launches(1 + (sp is not None))
     return d_fs
