@@ -348,7 +348,7 @@ def run_ours(args, d):
     if os.path.exists(tp) and world == 1 and args.scale == 1.0 and f == FEAT:
         with open(tp) as fh:
             traffic = json.load(fh).get('spmm_kernel_fwd_mag_f128_bytes')
-    roofline = {'bound': 'hbm', 'kernel': 'regnn::spmm_kernel<32,1,4> (forward launch)', 'achieved': alg / tk / 1e9,
+    roofline = {'bound': 'hbm', 'kernel': 'regnn::spmm_stream_kernel<1,4,false> (forward launch)', 'achieved': alg / tk / 1e9,
                 'peak': hbm, 'peak_source': how, 'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm, 'traffic': traffic,
                 'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3}
 

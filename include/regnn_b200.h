@@ -142,6 +142,27 @@ int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_
                      int feat, double* partials, float* d_theta, float* d_norm,
                      const regnn_rowsplit_t* split, void* stream);
 
+/* Fused backward of regnn_spmm_fwd: ONE gather pass over the transposed view produces both
+ *   dX[u]      = ns(u) * sum_{e in Out(u)} w[etype e] * nd(dst e) * G[dst e]       (DGL: gspmm on the reverse graph)
+ *   d_theta[r] = alpha*LeakyReLU'(alpha*theta[r]) * sum_{e: etype=r} ns(src)*nd(dst)*<X[src], G[dst]>
+ * (ns/nd = norm on the sides selected by norm_sides, else 1): the per-edge dot <X[u], G[dst]> reuses the
+ * G[dst] row that the dX gather already holds in registers; X rows of the block are staged in shared
+ * memory by TMA bulk copies.  d_norm is NOT produced here: see regnn_rowdot_norm_bwd.
+ * partials: double [regnn_partial_blocks(rows) * R]; d_theta is OVERWRITTEN;
+ * split_workspace: split_t->num_frags * feat floats. */
+int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t, const uint8_t* etype_t,
+                         const float* theta, float alpha, int num_relations, const float* norm,
+                         int norm_sides, const float* X, int64_t ldx, const float* G, int64_t ldg,
+                         float* dX, int64_t lddx, int64_t row_begin, int64_t row_end, int feat,
+                         double* partials, float* d_theta, const regnn_rowsplit_t* split_t,
+                         float* split_workspace, void* stream);
+
+/* d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v] for rows [row_begin,row_end):
+ * the gradient of regnn_spmm_fwd w.r.t. the norm vector (row-local, pure streaming). */
+int regnn_rowdot_norm_bwd(const float* norm, int norm_sides, const float* X, int64_t ldx, const float* Y,
+                          int64_t ldy, const float* G, int64_t ldg, const float* dX, int64_t lddx,
+                          int64_t row_begin, int64_t row_end, int feat, float* d_norm, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused REGAT layer core (layer/REGATConv.py:71-92): per destination v and head h
  *   l[e,h] = LeakyReLU_slope( el[src,h] + er[v,h] + w[etype,h] ),  w = LeakyReLU_0.01(alpha*theta)

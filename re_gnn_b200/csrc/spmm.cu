@@ -8,6 +8,8 @@
 // indices / edge types coalesced, broadcast them with shuffles, and issue U*C independent 128-bit
 // row loads per lane before the FMAs (memory-level parallelism).  Per-row sums run in slot order:
 // no atomics, bit-identical run to run.
+#include <initializer_list>
+
 #include "common.cuh"
 
 namespace regnn {
@@ -205,6 +207,284 @@ __device__ __forceinline__ void reduce_bins(const float* bins, double* scratch, 
     for (int w = 0; w < kWarpsPerBlock; ++w) s += scratch[w * R + r];
     out[r] = s;
   }
+}
+
+// ---- streaming SpMM (the production forward / backward kernel) ---------------------------------------
+// One warp streams the CONCATENATED slot range of a block of RB consecutive rows: column indices, edge
+// types and norm[src] are read coalesced 32 slots at a time (and prefetched one batch ahead), U source
+// rows are gathered with fully coalesced 128-bit loads before any FMA, and the accumulator is flushed
+// whenever the slot stream crosses a row boundary.  Short rows therefore cost no dependent-latency
+// bubble of their own: the gather pipeline never drains inside a block.  Rows longer than the split
+// threshold are skipped here and covered by fragment items (first in the grid).
+//
+// BINS variant (backward, run on the transposed view): per slot the gathered row G[dst] is also dotted
+// with the row-level tile Xrow[u] (staged in shared memory by TMA bulk copies, cp.async.bulk +
+// mbarrier) and added to a lane-local per-relation bin: d w[r] = sum_e norm*norm*<X[src], G[dst]> falls
+// out of the same gather that produces dX -- no second pass over the edges.
+template <> struct Vec<2> {
+  using T = float2;
+  static __device__ __forceinline__ T zero() { return make_float2(0.f, 0.f); }
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ void store(float* p, T v) { *reinterpret_cast<float2*>(p) = v; }
+  static __device__ __forceinline__ void fma(T& a, float s, T v) { a.x = fmaf(s, v.x, a.x); a.y = fmaf(s, v.y, a.y); }
+  static __device__ __forceinline__ float dot(T a, T b) { return fmaf(a.x, b.x, a.y * b.y); }
+  static __device__ __forceinline__ T scaled(T a, float s) { return make_float2(a.x * s, a.y * s); }
+};
+template <int VW> __device__ __forceinline__ typename Vec<VW>::T lds_vec(const float* p);
+template <> __device__ __forceinline__ float4 lds_vec<4>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float2 lds_vec<2>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float lds_vec<1>(const float* p) { return *p; }
+
+struct StreamArgs {
+  SpmmArgs s;
+  // BINS only
+  const float* Xrow;     // row-level operand of the per-edge dot (forward input X), leading dim ldr
+  int64_t ldr;
+  double* partials;      // [gridDim.x][R]
+  int use_tma;           // rows are 16-byte aligned multiples of 16 bytes: stage the tile with cp.async.bulk
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+  for (int spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    if (spin > (1 << 24)) __trap();  // never hang the GPU on a lost copy
+  }
+}
+
+constexpr int kRowsPerItem = 32;      // rows per warp item, plain variant
+constexpr int kRowsPerItemBins = 8;   // rows per warp item, BINS variant (bounds the shared-memory tile)
+
+template <int C, int VW, bool BINS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_stream_kernel(StreamArgs sa) {
+  using V = Vec<VW>;
+  using T = typename V::T;
+  constexpr int U = Unroll<C>::U;
+  constexpr int RB = BINS ? kRowsPerItemBins : kRowsPerItem;
+  const SpmmArgs& a = sa.s;
+  __shared__ float w_s[256];
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Fp = (a.F + 3) & ~3;  // tile row pitch (floats), keeps rows 16-byte aligned
+  // dynamic smem (BINS): [warps] mbarrier | [warps][R] double scratch | [warps][R][32] bins | [warps][RB][Fp] tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
+  double* scratch = reinterpret_cast<double*>(dsm + 64);
+  float* bins = reinterpret_cast<float*>(scratch + kWarpsPerBlock * a.R);
+  float* tiles = bins + (size_t)kWarpsPerBlock * a.R * 32;
+  float* mytile = tiles + (size_t)warp * RB * Fp;
+  float* mybins = bins + (size_t)warp * a.R * 32 + lane;
+  uint64_t* mybar = bars + warp;
+  if (a.etype != nullptr)
+    for (int i = threadIdx.x; i < a.R; i += blockDim.x) w_s[i] = leaky(a.theta[i] * a.alpha, kRelationSlope);
+  if (BINS) {
+    for (int r = 0; r < a.R; ++r) mybins[r * 32] = 0.f;
+    if (lane == 0) mbar_init(mybar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  bool col_ok[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) col_ok[k] = (lane + k * 32) * VW < a.F;
+  const float* xcol = a.X + (size_t)lane * VW;
+  const int64_t rows = a.row_end - a.row_begin;
+  const int64_t nitems = a.nfrag_pad + (rows + RB - 1) / RB;
+  const int64_t stride = BINS ? (int64_t)gridDim.x * kWarpsPerBlock : nitems;  // plain: one item per warp
+  uint32_t phase = 0;
+
+  for (int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; wi < nitems; wi += stride) {
+    // ---- decode the item: a fragment of a long row, or a block of RB rows
+    const bool is_frag = wi < a.nfrag_pad;
+    int64_t r0 = 0;
+    int nrows = 0, my_begin = 0, my_end = 0;
+    if (is_frag) {
+      if (wi < a.nfrag) {
+        const int64_t v = a.frag_row[wi];
+        if (v >= a.row_begin && v < a.row_end) {
+          r0 = v;
+          nrows = 1;
+          my_begin = a.frag_begin[wi];
+          my_end = my_begin + min(a.threshold, a.indptr[v + 1] - my_begin);
+        }
+      }
+    } else {
+      r0 = a.row_begin + (wi - a.nfrag_pad) * RB;
+      nrows = (int)min((int64_t)RB, a.row_end - r0);
+      if (lane < nrows) {
+        my_begin = a.indptr[r0 + lane];
+        my_end = a.indptr[r0 + lane + 1];
+      }
+    }
+    if (nrows <= 0) continue;  // warp-uniform
+    const float my_nd = (lane < nrows && a.norm_dst != nullptr) ? a.norm_dst[r0 + lane] : 1.f;
+    const unsigned longmask = is_frag ? 0u : __ballot_sync(0xffffffffu, lane < nrows && my_end - my_begin > a.threshold);
+    if (BINS) {  // stage the row-level tile (rows r0 .. r0+nrows-1 of Xrow) with TMA bulk copies
+      __syncwarp();  // every lane is done reading the previous tile
+      if (sa.use_tma) {
+        if (lane == 0) {
+          const uint32_t row_bytes = (uint32_t)a.F * 4u;
+          mbar_expect_tx(mybar, row_bytes * (uint32_t)nrows);
+          for (int r = 0; r < nrows; ++r)
+            bulk_g2s(mytile + (size_t)r * Fp, sa.Xrow + (size_t)(r0 + r) * sa.ldr, row_bytes, mybar);
+        }
+      } else {  // odd widths / unaligned rows: plain coalesced copy
+        for (int r = 0; r < nrows; ++r)
+          for (int c = lane; c < a.F; c += 32) mytile[(size_t)r * Fp + c] = sa.Xrow[(size_t)(r0 + r) * sa.ldr + c];
+        __syncwarp();
+      }
+    }
+    bool tile_ready = !BINS || !sa.use_tma;
+
+    int cur = 0;
+    while (cur < nrows) {
+      if ((longmask >> cur) & 1u) {  // long row: covered by fragments
+        ++cur;
+        continue;
+      }
+      const unsigned rest = longmask >> cur;
+      const int seg_end = min(nrows, rest ? cur + __ffs(rest) - 1 : nrows);
+      const int s_begin = __shfl_sync(0xffffffffu, my_begin, cur);
+      const int s_end = __shfl_sync(0xffffffffu, my_end, seg_end - 1);
+      int row = cur;
+      int row_end_slot = __shfl_sync(0xffffffffu, my_end, row);
+      float nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
+      T acc[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k) acc[k] = V::zero();
+
+      auto flush = [&]() {
+        if (is_frag) {
+          float* y = a.partial + (size_t)wi * a.F + (size_t)lane * VW;
+#pragma unroll
+          for (int k = 0; k < C; ++k)
+            if (col_ok[k]) V::store(y + (size_t)k * 32 * VW, acc[k]);
+        } else {
+          float* y = a.Y + (size_t)(r0 + row) * a.ldy + (size_t)lane * VW;
+#pragma unroll
+          for (int k = 0; k < C; ++k)
+            if (col_ok[k]) V::store(y + (size_t)k * 32 * VW, V::scaled(acc[k], nd_cur));
+        }
+#pragma unroll
+        for (int k = 0; k < C; ++k) acc[k] = V::zero();
+      };
+
+      // prefetch of the first batch
+      int nidx = 0, net = 0;
+      float ncoef = 0.f, nns = 0.f;
+      if (s_begin + lane < s_end) {
+        const int s = s_begin + lane;
+        nidx = a.indices[s];
+        if (a.etype != nullptr) net = a.etype[s];
+        nns = a.norm_src != nullptr ? __ldg(a.norm_src + nidx) : 1.f;
+        ncoef = (a.etype != nullptr ? w_s[net] : 1.f) * nns;
+      }
+      for (int s = s_begin; s < s_end; s += 32) {
+        const int idx = nidx, et = net;
+        const float coef = ncoef, ns = nns;
+        nidx = net = 0;
+        ncoef = nns = 0.f;
+        if (s + 32 + lane < s_end) {
+          const int sn = s + 32 + lane;
+          nidx = a.indices[sn];
+          if (a.etype != nullptr) net = a.etype[sn];
+          nns = a.norm_src != nullptr ? __ldg(a.norm_src + nidx) : 1.f;
+          ncoef = (a.etype != nullptr ? w_s[net] : 1.f) * nns;
+        }
+        const int cnt = min(32, s_end - s);
+        for (int j = 0; j < cnt; j += U) {
+          int sidx[U];
+          T x[U][C];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int jj = min(j + u, cnt - 1);
+            sidx[u] = __shfl_sync(0xffffffffu, idx, jj);
+#pragma unroll
+            for (int k = 0; k < C; ++k)
+              x[u][k] = (j + u < cnt && col_ok[k]) ? V::load(xcol + (size_t)sidx[u] * a.ldx + (size_t)k * 32 * VW)
+                                                   : V::zero();
+          }
+          if (BINS && !tile_ready) {  // first use of the tile: the bulk copies had the index loads to hide behind
+            mbar_wait(mybar, phase);
+            phase ^= 1u;
+            tile_ready = true;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (j + u < cnt) {  // warp-uniform
+              const int slot = s + j + u;
+              while (slot >= row_end_slot) {  // crossed a row boundary (also walks over empty rows)
+                flush();
+                ++row;
+                row_end_slot = __shfl_sync(0xffffffffu, my_end, row);
+                nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
+              }
+              const float sc = __shfl_sync(0xffffffffu, coef, j + u);
+#pragma unroll
+              for (int k = 0; k < C; ++k) V::fma(acc[k], sc, x[u][k]);
+              if (BINS) {
+                const float sb = __shfl_sync(0xffffffffu, ns, j + u) * nd_cur;
+                const int se = __shfl_sync(0xffffffffu, et, j + u);
+                const float* trow = mytile + (size_t)row * Fp + (size_t)lane * VW;
+                float d = 0.f;
+#pragma unroll
+                for (int k = 0; k < C; ++k)
+                  if (col_ok[k]) d += V::dot(x[u][k], lds_vec<VW>(trow + (size_t)k * 32 * VW));
+                mybins[se * 32] += sb * d;  // lane-local bin: fixed order, bank-conflict free
+              }
+            }
+          }
+        }
+      }
+      while (row < seg_end) {  // last row of the segment + trailing empty rows
+        flush();
+        ++row;
+        if (row < seg_end) nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
+      }
+      cur = seg_end;
+    }
+    if (BINS && !tile_ready) {  // item without a single short-row slot: still consume the barrier phase
+      mbar_wait(mybar, phase);
+      phase ^= 1u;
+    }
+  }
+  if (BINS) reduce_bins(bins, scratch, a.R, sa.partials + (size_t)blockIdx.x * a.R);
+}
+
+// d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v]   (pure streaming, row per warp)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rowdot_norm_kernel(const float* __restrict__ norm, int sides, const float* __restrict__ X, int64_t ldx,
+                   const float* __restrict__ Y, int64_t ldy, const float* __restrict__ G, int64_t ldg,
+                   const float* __restrict__ dX, int64_t lddx, int F, int64_t row_begin, int64_t row_end,
+                   float* __restrict__ d_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t v = row_begin + (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (v >= row_end) return;
+  float p = 0.f;
+  for (int c = lane; c < F; c += 32) {
+    if (sides & 2) p = fmaf(__ldg(Y + (size_t)v * ldy + c), __ldg(G + (size_t)v * ldg + c), p);
+    if (sides & 1) p = fmaf(__ldg(X + (size_t)v * ldx + c), __ldg(dX + (size_t)v * lddx + c), p);
+  }
+  p = group_sum<32>(p);
+  if (lane == 0) d_norm[v] = p / norm[v];
 }
 
 struct SpmmBwdArgs {
@@ -506,12 +786,74 @@ extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_c
   return check_launch("regnn_wdeg_norm_bwd");
 }
 
+struct StreamShape { int C, VW; };
+
+static bool aligned_to(const void* p, int bytes) { return ((uintptr_t)p & (bytes - 1)) == 0; }
+
+// Vector width and 32-lane chunks per row for the streaming kernels.  `align` = largest power of two
+// (<= 16 bytes) dividing every base pointer and leading dimension (in bytes).
+static bool pick_stream_shape(int F, int align, StreamShape* sh) {
+  int VW = 1;
+  if (align >= 16 && F % 4 == 0 && F >= 96) VW = 4;
+  else if (align >= 8 && F % 2 == 0 && F >= 34) VW = 2;
+  int C = (F + 32 * VW - 1) / (32 * VW);
+  if (C > 8) {
+    if (VW == 1 && align >= 8 && F % 2 == 0) { VW = 2; C = (F + 63) / 64; }
+    if (C > 8 && align >= 16 && F % 4 == 0) { VW = 4; C = (F + 127) / 128; }
+    if (C > 8) return false;
+  }
+  if (C > 4) C = 8;
+  *sh = {C, VW};
+  return true;
+}
+
+static int common_align(std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> lds) {
+  int al = 16;
+  for (const void* p : ptrs)
+    while (p != nullptr && al > 4 && !aligned_to(p, al)) al >>= 1;
+  for (int64_t ld : lds)
+    while (al > 4 && (ld * 4) % al != 0) al >>= 1;
+  return al;
+}
+
+#define REGNN_STREAM_CASE(C_, VW_, BINS_, CALL)     \
+  if (sh.C == C_ && sh.VW == VW_) {                 \
+    constexpr int C = C_, VW = VW_;                 \
+    constexpr bool BINS = BINS_;                    \
+    CALL;                                           \
+    launched = true;                                \
+  }
+#define REGNN_STREAM_DISPATCH(BINS_, CALL)                                                          \
+  REGNN_STREAM_CASE(1, 4, BINS_, CALL) REGNN_STREAM_CASE(2, 4, BINS_, CALL) REGNN_STREAM_CASE(3, 4, BINS_, CALL) \
+  REGNN_STREAM_CASE(4, 4, BINS_, CALL) REGNN_STREAM_CASE(8, 4, BINS_, CALL)                          \
+  REGNN_STREAM_CASE(1, 2, BINS_, CALL) REGNN_STREAM_CASE(2, 2, BINS_, CALL) REGNN_STREAM_CASE(3, 2, BINS_, CALL) \
+  REGNN_STREAM_CASE(4, 2, BINS_, CALL) REGNN_STREAM_CASE(8, 2, BINS_, CALL)                          \
+  REGNN_STREAM_CASE(1, 1, BINS_, CALL) REGNN_STREAM_CASE(2, 1, BINS_, CALL) REGNN_STREAM_CASE(3, 1, BINS_, CALL) \
+  REGNN_STREAM_CASE(4, 1, BINS_, CALL) REGNN_STREAM_CASE(8, 1, BINS_, CALL)
+
+static int fill_split(SpmmArgs& a, const regnn_rowsplit_t* split, float* ws, const char* who) {
+  a.frag_row = a.frag_begin = nullptr;
+  a.nfrag = a.nfrag_pad = 0;
+  a.threshold = 0x7fffffff;
+  a.partial = ws;
+  if (split == nullptr || split->num_frags <= 0) return REGNN_OK;
+  REGNN_REQUIRE(ws && split->long_rows && split->frag_ptr && split->frag_row && split->frag_begin && split->threshold > 0,
+                REGNN_ERR_INVALID_ARG, "%s: incomplete row split", who);
+  a.frag_row = split->frag_row;
+  a.frag_begin = split->frag_begin;
+  a.nfrag = split->num_frags;
+  a.nfrag_pad = (a.nfrag + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock;
+  a.threshold = split->threshold;
+  return REGNN_OK;
+}
+
 extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
                               const float* theta, float alpha, int num_relations,
                               const float* norm_src, const float* norm_dst, const float* X,
                               int64_t ldx, float* Y, int64_t ldy, int64_t row_begin,
                               int64_t row_end, int feat, const regnn_rowsplit_t* split,
-                              float* split_workspace, void* stream) {
+                              float* split_workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && indices && X && Y, REGNN_ERR_INVALID_ARG, "spmm_fwd: null pointer");
   REGNN_REQUIRE(etype == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd: etype without theta");
   REGNN_REQUIRE(etype == nullptr || (num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS),
@@ -520,29 +862,84 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "spmm_fwd: negative row range");
   if (rows == 0) return REGNN_OK;
-  const bool vec_ok = aligned16(X) && aligned16(Y) && ldx % 4 == 0 && ldy % 4 == 0;
-  Shape sh;
-  REGNN_REQUIRE(pick_shape(feat, vec_ok, &sh), REGNN_ERR_UNSUPPORTED_SHAPE,
-                "spmm_fwd: feature width %d too wide (max 1024 aligned / 256 unaligned)", feat);
-  const bool use_split = split != nullptr && split->num_frags > 0;
-  REGNN_REQUIRE(!use_split || (split_workspace && split->long_rows && split->frag_ptr && split->frag_row &&
-                               split->frag_begin && split->threshold > 0),
-                REGNN_ERR_INVALID_ARG, "spmm_fwd: incomplete row split");
-  const int items_per_block = kWarpsPerBlock * (32 / sh.G);
-  const int nfrag = use_split ? split->num_frags : 0;
-  const int nfrag_pad = (nfrag + items_per_block - 1) / items_per_block * items_per_block;
-  SpmmArgs a{indptr, indices, etype, theta, alpha, num_relations, norm_src, norm_dst, X, ldx, Y, ldy,
-             row_begin, row_end, feat,
-             use_split ? split->frag_row : nullptr, use_split ? split->frag_begin : nullptr, nfrag, nfrag_pad,
-             use_split ? split->threshold : 0x7fffffff, split_workspace};
-  const int64_t blocks = (rows + nfrag_pad + items_per_block - 1) / items_per_block;
+  StreamShape sh;
+  REGNN_REQUIRE(pick_stream_shape(feat, common_align({X, Y, split_workspace}, {ldx, ldy, (int64_t)feat}), &sh),
+                REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: feature width %d too wide (max 1024 aligned / 256 unaligned)", feat);
+  StreamArgs sa{};
+  sa.s = SpmmArgs{indptr, indices, etype, theta, alpha, num_relations, norm_src, norm_dst, X, ldx, Y, ldy,
+                  row_begin, row_end, feat, nullptr, nullptr, 0, 0, 0x7fffffff, nullptr};
+  int rc = fill_split(sa.s, split, split_workspace, "spmm_fwd");
+  if (rc != REGNN_OK) return rc;
+  const int64_t nitems = sa.s.nfrag_pad + (rows + kRowsPerItem - 1) / kRowsPerItem;
+  const unsigned blocks = (unsigned)((nitems + kWarpsPerBlock - 1) / kWarpsPerBlock);
   bool launched = false;
-  REGNN_DISPATCH_SHAPES((spmm_kernel<G, C, VW><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(a)))
-  REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: no kernel for G=%d C=%d VW=%d", sh.G, sh.C, sh.VW);
-  if (use_split)
-    spmm_frag_finalize_kernel<<<split->num_long, 128, 0, (cudaStream_t)stream>>>(
-        split->long_rows, split->frag_ptr, split->num_long, split_workspace, norm_dst, Y, ldy, feat, row_begin, row_end);
+  REGNN_STREAM_DISPATCH(false, (spmm_stream_kernel<C, VW, BINS><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(sa)))
+  REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: no kernel for C=%d VW=%d", sh.C, sh.VW);
+  if (sa.s.nfrag > 0)
+    spmm_frag_finalize_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->frag_ptr, split->num_long,
+                                                                   split_workspace, norm_dst, Y, ldy, feat, row_begin, row_end);
   return check_launch("regnn_spmm_fwd");
+}
+
+extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t,
+                                    const uint8_t* etype_t, const float* theta, float alpha,
+                                    int num_relations, const float* norm, int norm_sides, const float* X,
+                                    int64_t ldx, const float* Gd, int64_t ldg, float* dX, int64_t lddx,
+                                    int64_t row_begin, int64_t row_end, int feat, double* partials,
+                                    float* d_theta, const regnn_rowsplit_t* split_t,
+                                    float* split_workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  REGNN_REQUIRE(indptr_t && indices_t && etype_t && theta && X && Gd && dX && partials && d_theta,
+                REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: null pointer");
+  const int R = num_relations;
+  REGNN_REQUIRE(R >= 1 && R <= 160, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,160]", R);
+  REGNN_REQUIRE(feat >= 1 && ldx >= feat && ldg >= feat && lddx >= feat, REGNN_ERR_INVALID_ARG,
+                "spmm_bwd_fused: bad feature width / leading dimension");
+  const int64_t rows = row_end - row_begin;
+  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: negative row range");
+  StreamShape sh;
+  REGNN_REQUIRE(pick_stream_shape(feat, common_align({X, Gd, dX, split_workspace}, {ldx, ldg, lddx, (int64_t)feat}), &sh),
+                REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_fused: feature width %d too wide", feat);
+  const int sides = norm != nullptr ? (norm_sides & 3) : 0;
+  StreamArgs sa{};
+  // transposed view: gathered rows are destinations (scaled when the forward scaled its destination side)
+  sa.s = SpmmArgs{indptr_t, indices_t, etype_t, theta, alpha, R, (sides & 2) ? norm : nullptr, (sides & 1) ? norm : nullptr,
+                  Gd, ldg, dX, lddx, row_begin, row_end, feat, nullptr, nullptr, 0, 0, 0x7fffffff, nullptr};
+  int rc = fill_split(sa.s, split_t, split_workspace, "spmm_bwd_fused");
+  if (rc != REGNN_OK) return rc;
+  sa.Xrow = X;
+  sa.ldr = ldx;
+  sa.partials = partials;
+  sa.use_tma = (feat % 4 == 0 && aligned_to(X, 16) && ldx % 4 == 0) ? 1 : 0;
+  const int Fp = (feat + 3) & ~3;
+  const size_t smem = 64 + (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float)) +
+                      (size_t)kWarpsPerBlock * kRowsPerItemBins * Fp * sizeof(float);
+  const int nb = partial_blocks(rows / kRowsPerItemBins + sa.s.nfrag + 1);
+  bool launched = false;
+  REGNN_STREAM_DISPATCH(true, (rc = set_smem(spmm_stream_kernel<C, VW, BINS>, smem),
+                               spmm_stream_kernel<C, VW, BINS><<<nb, kWarpsPerBlock * 32, smem, stream>>>(sa)))
+  if (rc != REGNN_OK) return rc;
+  REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_fused: no kernel for C=%d VW=%d", sh.C, sh.VW);
+  if (sa.s.nfrag > 0)
+    spmm_frag_finalize_kernel<<<split_t->num_long, 128, 0, stream>>>(split_t->long_rows, split_t->frag_ptr,
+                                                                     split_t->num_long, split_workspace, sa.s.norm_dst, dX,
+                                                                     lddx, feat, row_begin, row_end);
+  launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
+  return check_launch("regnn_spmm_bwd_fused");
+}
+
+extern "C" int regnn_rowdot_norm_bwd(const float* norm, int norm_sides, const float* X, int64_t ldx,
+                                     const float* Y, int64_t ldy, const float* Gd, int64_t ldg,
+                                     const float* dX, int64_t lddx, int64_t row_begin, int64_t row_end,
+                                     int feat, float* d_norm, void* stream) {
+  REGNN_REQUIRE(norm && X && Y && Gd && dX && d_norm, REGNN_ERR_INVALID_ARG, "rowdot_norm_bwd: null pointer");
+  const int64_t rows = row_end - row_begin;
+  REGNN_REQUIRE(rows >= 0 && feat >= 1, REGNN_ERR_INVALID_ARG, "rowdot_norm_bwd: bad range / width");
+  if (rows == 0) return REGNN_OK;
+  rowdot_norm_kernel<<<(unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, 0,
+                       (cudaStream_t)stream>>>(norm, norm_sides & 3, X, ldx, Y, ldy, Gd, ldg, dX, lddx, feat, row_begin,
+                                               row_end, d_norm);
+  return check_launch("regnn_rowdot_norm_bwd");
 }
 
 extern "C" int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,

@@ -58,20 +58,24 @@ class _Propagate(torch.autograd.Function):
         need_theta = ctx.weighted and ctx.needs_input_grad[3]
         need_norm = ctx.has_norm and ctx.needs_input_grad[5]
         dx = d_theta = d_norm = None
-        if need_x or need_norm:
-            # transposed SpMM: dX[u] = norm[u] * sum_{e in Out(u)} w_e * norm[dst] * G[dst]
-            # (on the transposed view the roles of the two sides swap)
-            ns = norm if ctx.sides & 2 else None
-            nd = norm if ctx.sides & 1 else None
-            dx = ops.spmm(csr['indptr_t'], csr['indices_t'], ctx.etv[1] if ctx.weighted else None, theta,
-                          ctx.alpha, ns, nd, g, split=csr.get('split_t'))
-        if need_theta or need_norm:
-            if dx is None:
-                dx = torch.zeros_like(x)
-            d_theta, d_norm = ops.spmm_bwd_w(csr, ctx.etv[0] if need_theta else None, theta if need_theta else None,
-                                             ctx.alpha, norm, x, y, g, dx, sides=ctx.sides, split=csr.get('split'))
-            if d_theta is not None:
+        if need_theta and x.shape[1] <= ops.FUSED_BWD_MAX_FEAT:
+            # one gather pass over the transposed view: dX and the relation gradient together
+            dx, d_theta = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x, g, sides=ctx.sides)
+            d_theta = d_theta.view_as(theta)
+        else:
+            if need_x or need_norm or need_theta:
+                # transposed SpMM: dX[u] = ns(u) * sum_{e in Out(u)} w_e * nd(dst) * G[dst]
+                # (on the transposed view the roles of the two sides swap)
+                ns = norm if ctx.sides & 2 else None
+                nd = norm if ctx.sides & 1 else None
+                dx = ops.spmm(csr['indptr_t'], csr['indices_t'], ctx.etv[1] if ctx.weighted else None, theta,
+                              ctx.alpha, ns, nd, g, split=csr.get('split_t'))
+            if need_theta:
+                d_theta, _ = ops.spmm_bwd_w(csr, ctx.etv[0], theta, ctx.alpha, norm, x, y, g, dx, sides=ctx.sides,
+                                            split=csr.get('split'))
                 d_theta = d_theta.view_as(theta)
+        if need_norm:
+            d_norm = ops.rowdot_norm_bwd(norm, x, y, g, dx, sides=ctx.sides)
         return None, None, (dx if need_x else None), d_theta, None, (d_norm if need_norm else None), None
 
 

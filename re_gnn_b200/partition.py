@@ -71,10 +71,11 @@ class _PartitionedPropagate(torch.autograd.Function):
         g_full = torch.empty_like(x_full)
         _all_gather_rows(g_full, g_own, bounds, ctx.group)
         dx_full = torch.empty_like(x_full)
-        ops.spmm(csr['indptr_t'], csr['indices_t'], ctx.etv[1], theta, ctx.alpha, norm, norm, g_full,
-                 rows=(rb, re), out=dx_full, split=csr.get('split_t'))
-        d_theta, d_norm = ops.spmm_bwd_w(csr, ctx.etv[0], theta, ctx.alpha, norm, x_full, y_full, g_full, dx_full,
-                                         rows=(rb, re), split=csr.get('split'))
+        # owner computes: the transposed rows [rb, re) are this rank's SOURCE rows; one fused gather pass gives
+        # their dX and this rank's share of the relation gradient (each edge belongs to exactly one source row)
+        _, d_theta = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x_full, g_full, rows=(rb, re),
+                                        out=dx_full)
+        d_norm = ops.rowdot_norm_bwd(norm, x_full, y_full, g_full, dx_full, rows=(rb, re))
         # d_theta / d_norm hold this rank's rows only; the caller all-reduces the parameter gradient once.
         return None, None, dx_full[rb:re], d_theta.view_as(theta), None, d_norm, None, None, None
 

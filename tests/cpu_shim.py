@@ -110,6 +110,36 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3,
     return d_theta, d_norm
 
 
+def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None):
+    ns = norm if (norm is not None and sides & 2) else None
+    nd = norm if (norm is not None and sides & 1) else None
+    dx = spmm(csr['indptr_t'], csr['indices_t'], et_t, theta, alpha, ns, nd, g, rows=rows, out=out)
+    x, g = x.detach(), g.detach()
+    th = theta.detach().view(-1)
+    src = _rows_of(csr['indptr_t'])
+    dstn = csr['indices_t'].long()
+    dwe = (x[src] * g[dstn]).sum(1)
+    if norm is not None and sides & 1:
+        dwe = dwe * norm.detach()[src]
+    if norm is not None and sides & 2:
+        dwe = dwe * norm.detach()[dstn]
+    if rows is not None:          # a rank owns the edges whose SOURCE row it owns
+        dwe = torch.where((src >= rows[0]) & (src < rows[1]), dwe, torch.zeros_like(dwe))
+    dw = torch.zeros_like(th).index_add(0, et_t.long(), dwe)
+    return dx, dw * alpha * _lgrad(th * alpha, SLOPE)
+
+
+def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3):
+    x, y, g, dx = x.detach(), y.detach(), g.detach(), dx.detach()
+    n = norm.numel()
+    d = ((y * g).sum(1) * bool(sides & 2) + (x * dx).sum(1) * bool(sides & 1)) / norm.detach()
+    if rows is not None:
+        own = torch.zeros(n, dtype=torch.bool)
+        own[rows[0]:rows[1]] = True
+        d = torch.where(own, d, torch.zeros_like(d))
+    return d
+
+
 def _softmax_rows(l, row, n):
     mx = torch.full((n, l.shape[1]), float('-inf'), dtype=l.dtype).scatter_reduce(
         0, row[:, None].expand_as(l), l, 'amax', include_self=True)
@@ -234,6 +264,6 @@ def install(monkeypatch):
     from re_gnn_b200 import graph as G, ops
     monkeypatch.setattr(G.Graph, 'csr', graph_csr)
     monkeypatch.setattr(G.Graph, 'etype_views', graph_etype_views)
-    for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'gat_fwd', 'gat_bwd_dst',
+    for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'spmm_bwd_fused', 'rowdot_norm_bwd', 'gat_fwd', 'gat_bwd_dst',
                  'gat_bwd_src', 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src'):
         monkeypatch.setattr(ops, name, globals()[name])
