@@ -25,39 +25,48 @@ int check_launch(const char* what) {
   return REGNN_OK;
 }
 
-// One thread per table entry; the loop over blocks runs in block order => fixed summation order.
+// One warp per table entry: lane l sums blocks l, l+32, ... in order, then a fixed xor-tree combines the
+// 32 lane sums => the summation order is a pure function of num_blocks (deterministic).
 __global__ void relation_grad_finalize_kernel(const double* __restrict__ partials, int num_blocks,
                                               int stride, int count, const float* __restrict__ theta,
                                               float alpha, float* __restrict__ d_theta) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= count) return;
   double s = 0.0;
-  for (int b = 0; b < num_blocks; ++b) s += partials[(size_t)b * stride + i];
-  float z = theta[i] * alpha;
-  d_theta[i] = (float)(s * (double)(alpha * leaky_grad(z, kRelationSlope)));
+  for (int b = lane; b < num_blocks; b += 32) s += partials[(size_t)b * stride + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const float z = theta[i] * alpha;
+    d_theta[i] = (float)(s * (double)(alpha * leaky_grad(z, kRelationSlope)));
+  }
 }
 
 __global__ void colsum_finalize_kernel(const double* __restrict__ partials, int num_blocks,
                                        int stride, int offset, int count, float* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= count) return;
   double s = 0.0;
-  for (int b = 0; b < num_blocks; ++b) s += partials[(size_t)b * stride + offset + i];
-  out[i] = (float)s;
+  for (int b = lane; b < num_blocks; b += 32) s += partials[(size_t)b * stride + offset + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[i] = (float)s;
 }
 
 void launch_relation_grad_finalize(const double* partials, int num_blocks, int stride, int count,
                                    const float* theta, float alpha, float* d_theta,
                                    cudaStream_t stream) {
-  int threads = 128;
-  relation_grad_finalize_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(
+  const int warps = 4;
+  relation_grad_finalize_kernel<<<(count + warps - 1) / warps, warps * 32, 0, stream>>>(
       partials, num_blocks, stride, count, theta, alpha, d_theta);
 }
 
 void launch_colsum_finalize(const double* partials, int num_blocks, int stride, int offset,
                             int count, float* out, cudaStream_t stream) {
-  int threads = 128;
-  colsum_finalize_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(
+  const int warps = 4;
+  colsum_finalize_kernel<<<(count + warps - 1) / warps, warps * 32, 0, stream>>>(
       partials, num_blocks, stride, offset, count, out);
 }
 

@@ -274,7 +274,7 @@ constexpr int kRowsPerItem = 32;      // rows per warp item, plain variant
 constexpr int kRowsPerItemBins = 8;   // rows per warp item, BINS variant (bounds the shared-memory tile)
 
 template <int C, int VW, bool BINS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (C <= 1 ? 3 : 1))
 spmm_stream_kernel(StreamArgs sa) {
   using V = Vec<VW>;
   using T = typename V::T;
@@ -695,6 +695,98 @@ wdeg_norm_bwd_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restri
   reduce_bins(bins, scratch, R, partials + (size_t)blockIdx.x * R);
 }
 
+// ---- slot-parallel variants of the two norm kernels (R <= 32) ----------------------------------------
+// A warp owns a block of 32 consecutive rows and strides its 32 lanes over the block's concatenated
+// slot range, so a hub row with 1e4-1e5 in-edges costs the same per slot as any other row.  The row of
+// a slot is found by a 5-step binary search over the block's row ends (shared memory).
+// Forward: integer per-(row, relation) counts (shared-memory integer atomics: order-free and exact),
+// then deg[v] = sum_r count[v][r] * w[r] in relation order.  Backward: lane-local relation bins.
+constexpr int kWdegRows = 32;
+
+__device__ __forceinline__ int row_of_slot(const int* ends, int nrows, int s) {
+  int lo = 0, hi = nrows - 1;  // first row whose end is > s
+#pragma unroll
+  for (int it = 0; it < 5; ++it) {
+    const int mid = (lo + hi) >> 1;
+    if (lo < hi) {
+      if (ends[mid] > s) hi = mid; else lo = mid + 1;
+    }
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+wdeg_norm_fwd_slot_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restrict__ etype,
+                          const float* __restrict__ theta, float alpha, int R, float exponent,
+                          int64_t row_begin, int64_t row_end, float* __restrict__ deg,
+                          float* __restrict__ norm) {
+  __shared__ float w_s[32];
+  __shared__ int ends_s[kWarpsPerBlock][kWdegRows];
+  __shared__ int cnt_s[kWarpsPerBlock][kWdegRows * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < R) w_s[threadIdx.x] = leaky(theta[threadIdx.x] * alpha, kRelationSlope);
+  __syncthreads();
+  const int64_t r0 = row_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * kWdegRows;
+  if (r0 >= row_end) return;
+  const int nrows = (int)min((int64_t)kWdegRows, row_end - r0);
+  int my_begin = 0, my_end = 0;
+  if (lane < nrows) {
+    my_begin = indptr[r0 + lane];
+    my_end = indptr[r0 + lane + 1];
+    ends_s[warp][lane] = my_end;
+  }
+  int* cnt = cnt_s[warp];
+  for (int i = lane; i < nrows * R; i += 32) cnt[i] = 0;
+  const int s_begin = __shfl_sync(0xffffffffu, my_begin, 0);
+  const int s_end = __shfl_sync(0xffffffffu, my_end, nrows - 1);
+  __syncwarp();
+  for (int s = s_begin + lane; s < s_end; s += 32)
+    atomicAdd(&cnt[row_of_slot(ends_s[warp], nrows, s) * R + etype[s]], 1);
+  __syncwarp();
+  if (lane < nrows) {
+    float d = 0.f;
+    for (int r = 0; r < R; ++r) d = fmaf((float)cnt[lane * R + r], w_s[r], d);
+    if (deg != nullptr) deg[r0 + lane] = d;
+    norm[r0 + lane] = norm_from_deg(d, exponent);
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+wdeg_norm_bwd_slot_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restrict__ etype, int R,
+                          float exponent, int64_t row_begin, int64_t row_end,
+                          const float* __restrict__ deg, const float* __restrict__ d_norm,
+                          double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* scratch = reinterpret_cast<double*>(smem_raw);
+  float* bins = reinterpret_cast<float*>(scratch + kWarpsPerBlock * R);
+  __shared__ int ends_s[kWarpsPerBlock][kWdegRows];
+  __shared__ float dd_s[kWarpsPerBlock][kWdegRows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* mybins = bins + (size_t)warp * R * 32 + lane;
+  for (int r = 0; r < R; ++r) mybins[r * 32] = 0.f;
+  const int64_t nblocks = (row_end - row_begin + kWdegRows - 1) / kWdegRows;
+  for (int64_t b = (int64_t)blockIdx.x * kWarpsPerBlock + warp; b < nblocks; b += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t r0 = row_begin + b * kWdegRows;
+    const int nrows = (int)min((int64_t)kWdegRows, row_end - r0);
+    int my_begin = 0, my_end = 0;
+    __syncwarp();
+    if (lane < nrows) {
+      my_begin = indptr[r0 + lane];
+      my_end = indptr[r0 + lane + 1];
+      ends_s[warp][lane] = my_end;
+      const float d = deg[r0 + lane];
+      // clamp(min=1) passes the gradient at deg == 1 (PyTorch semantics)
+      dd_s[warp][lane] = d >= 1.f ? exponent * powf(fmaxf(d, 1.f), exponent - 1.f) * d_norm[r0 + lane] : 0.f;
+    }
+    const int s_begin = __shfl_sync(0xffffffffu, my_begin, 0);
+    const int s_end = __shfl_sync(0xffffffffu, my_end, nrows - 1);
+    __syncwarp();
+    for (int s = s_begin + lane; s < s_end; s += 32)
+      mybins[etype[s] * 32] += dd_s[warp][row_of_slot(ends_s[warp], nrows, s)];
+  }
+  reduce_bins(bins, scratch, R, partials + (size_t)blockIdx.x * R);
+}
+
 // ---- dispatch ---------------------------------------------------------------------------------------
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
@@ -756,9 +848,15 @@ extern "C" int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_c
   REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "wdeg_norm_fwd: empty/negative row range");
   if (rows == 0) return REGNN_OK;
   const int threads = kWarpsPerBlock * 32;
-  const int64_t blocks = (rows * 8 + threads - 1) / threads;
-  wdeg_norm_fwd_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-      indptr, etype_csr, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
+  if (num_relations <= 32) {
+    const int64_t blocks = (rows + kWarpsPerBlock * kWdegRows - 1) / (kWarpsPerBlock * kWdegRows);
+    wdeg_norm_fwd_slot_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        indptr, etype_csr, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
+  } else {
+    const int64_t blocks = (rows * 8 + threads - 1) / threads;
+    wdeg_norm_fwd_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        indptr, etype_csr, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
+  }
   return check_launch("regnn_wdeg_norm_fwd");
 }
 
@@ -780,8 +878,12 @@ extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_c
   const size_t smem = bins_smem_bytes(R);
   int rc = set_smem(wdeg_norm_bwd_kernel, smem);
   if (rc != REGNN_OK) return rc;
-  wdeg_norm_bwd_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent,
-                                                                   row_begin, row_end, deg, d_norm, partials);
+  if (R <= 32)
+    wdeg_norm_bwd_slot_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent, row_begin,
+                                                                          row_end, deg, d_norm, partials);
+  else
+    wdeg_norm_bwd_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent,
+                                                                     row_begin, row_end, deg, d_norm, partials);
   launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
   return check_launch("regnn_wdeg_norm_bwd");
 }
