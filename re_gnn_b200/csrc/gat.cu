@@ -82,7 +82,7 @@ __device__ __forceinline__ WorkItem decode_item(const AttnArgs& a, int64_t wi, i
   return w;
 }
 
-template <int C> struct UnrollA { static constexpr int U = C <= 1 ? 4 : (C <= 4 ? 2 : 1); };
+constexpr int kUA = 8;  // source rows gathered per lane before any math (memory-level parallelism)
 
 __device__ __forceinline__ void load_rel_table(float* w_s, const AttnArgs& a) {
   if (a.etype != nullptr) {
@@ -100,52 +100,59 @@ __device__ __forceinline__ float4 leaky4(float4 q, float s) {
 }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// Slice bookkeeping shared by all kernels.
-template <int C>
-struct Slices {
-  int head[C];
-  bool ok[C];
-  bool leader[C];  // first lane of the head's lane group: writes per-(row|edge, head) scalars
-  __device__ __forceinline__ Slices(int lane, int H, int D) {
-    const int lph = D >> 2;
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-      const int c4 = lane + 32 * k;
-      ok[k] = c4 * 4 < H * D;
-      head[k] = ok[k] ? (c4 * 4) / D : 0;
-      leader[k] = ok[k] && (c4 % lph == 0);
-    }
-  }
+// Head-group mapping: a row of H*D floats is cut into 128-float slices ("head groups"); ONE WARP owns
+// one (row | fragment, head group) item, lane l holding the 128-bit slice [128*hg + 4*l, +4).  Heads are
+// independent in both layers, so the HG = ceil(H*D/128) warps of a row never have to talk to each other,
+// every gathered source slice is one fully coalesced 512-byte request, and each lane needs a single
+// float4 per edge -- which leaves registers for kUA rows in flight per lane.
+struct Group {
+  int hg, col, hl, h_lo, nh, lph;
+  bool ok, leader;
 };
+__device__ __forceinline__ Group make_group(const AttnArgs& a, int hg, int lane) {
+  Group g;
+  const int HD = a.H * a.D;
+  g.hg = hg;
+  g.col = hg * 128 + lane * 4;
+  g.ok = g.col < HD;
+  g.h_lo = (hg * 128) / a.D;
+  const int h_hi = min(a.H - 1, (hg * 128 + 127) / a.D);
+  g.nh = h_hi - g.h_lo + 1;
+  g.hl = g.ok ? g.col / a.D : g.h_lo;
+  const int lanes_per_head = a.D >> 2;
+  g.lph = min(32, lanes_per_head);
+  g.leader = g.ok && ((g.col >> 2) % lanes_per_head == 0);
+  return g;
+}
+__device__ __forceinline__ int num_groups(const AttnArgs& a) { return (a.H * a.D + 127) / 128; }
 
 // =================================================================================================
-// REGAT forward.  Logits of a batch of 32 edges are computed one edge per lane (all heads); the
-// batch max / sum go through warp shuffles; probabilities are staged in shared memory; then the
-// whole warp aggregates the batch edge by edge with C coalesced 128-bit loads per lane per edge.
+// REGAT forward.  Logits of a batch of 32 edges are computed one edge per lane (heads of this group);
+// batch max / sum through warp shuffles; probabilities staged in shared memory; then the warp
+// aggregates the batch with kUA coalesced 128-bit loads in flight per lane.
 // Dynamic smem: w_s[R*H] | per warp: p_s[32][HP], sc_s[H], m_s[H]     (HP = H|1: conflict-free)
-template <int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gat_fwd_kernel(AttnArgs a) {
-  constexpr int U = UnrollA<C>::U;
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, D = a.D, HD = H * D, HP = H | 1;
+  const int H = a.H, HD = H * a.D, HP = H | 1;
   float* w_s = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* p_s = smem + a.R * H + warp * (32 * HP + 2 * H);
   float* sc_s = p_s + 32 * HP;
   float* m_s = sc_s + H;
   load_rel_table(w_s, a);
-  const WorkItem it = decode_item(a, (int64_t)blockIdx.x * kWarpsPerBlock + warp, a.nfrag_pad);
+  const int HG = num_groups(a);
+  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const WorkItem it = decode_item(a, wi / HG, a.nfrag);
   if (!it.ok) return;
+  const Group g = make_group(a, (int)(wi % HG), lane);
   const int64_t v = it.v;
   const int s0 = it.s0, len = it.len;
-  const Slices<C> sl(lane, H, D);
-  float4 acc[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) acc[k] = zero4();
-  float m_run = -INFINITY, s_run = 0.f;  // lane h (< H) owns the running max / sum of head h
-  const float* fcol = a.feat + (size_t)lane * 4;
+  float4 acc = zero4();
+  float m_run = -INFINITY, s_run = 0.f;  // lane t (< nh) owns the running max / sum of head h_lo + t
+  const float* fcol = a.feat + g.col;
   const bool need_eid = a.keep != nullptr || a.o3 != nullptr;
+  const int tl = g.hl - g.h_lo;
 
   for (int base = 0; base < len; base += 32) {
     const int cnt = min(32, len - base);
@@ -157,7 +164,8 @@ gat_fwd_kernel(AttnArgs a) {
       if (a.etype != nullptr) et = a.etype[slot];
       if (need_eid) e = a.eid[slot];
     }
-    for (int h = 0; h < H; ++h) {
+    for (int t = 0; t < g.nh; ++t) {
+      const int h = g.h_lo + t;
       float x = -INFINITY;
       if (valid) {
         float pre = __ldg(a.el + (size_t)idx * H + h) + __ldg(a.er + (size_t)v * H + h);
@@ -166,76 +174,64 @@ gat_fwd_kernel(AttnArgs a) {
         if (a.o3 != nullptr) a.o3[(size_t)e * H + h] = x;  // raw logit; normalised after the row
       }
       const float bm = warp_max(x);
-      const float m_old = __shfl_sync(0xffffffffu, m_run, h);
+      const float m_old = __shfl_sync(0xffffffffu, m_run, t);
       const float m_new = fmaxf(m_old, bm);
       float p = valid ? expf(x - m_new) : 0.f;
       const float bs = group_sum<32>(p);
       const float sc = expf(m_old - m_new);  // first batch: exp(-inf) = 0
-      if (lane == h) {
+      if (lane == t) {
         m_run = m_new;
         s_run = s_run * sc + bs;
-        sc_s[h] = sc;
+        sc_s[t] = sc;
       }
       if (valid && a.keep != nullptr) p *= __ldg(a.keep + (size_t)e * H + h);
-      p_s[lane * HP + h] = p;
+      p_s[lane * HP + t] = p;
     }
     __syncwarp();
+    scale4(acc, sc_s[tl]);
+    for (int j = 0; j < cnt; j += kUA) {
+      float4 x[kUA];
+      float p[kUA];
 #pragma unroll
-    for (int k = 0; k < C; ++k) scale4(acc[k], sc_s[sl.head[k]]);
-    for (int j = 0; j < cnt; j += U) {
-      float4 x[U][C];
-      float p[U][C];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < kUA; ++u) {
         const bool ok = j + u < cnt;
         const int jj = ok ? j + u : j;
         const int sidx = __shfl_sync(0xffffffffu, idx, jj);
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-          const bool ld = ok && sl.ok[k];
-          x[u][k] = ld ? ldg4(fcol + (size_t)sidx * HD + (size_t)k * 128) : zero4();
-          p[u][k] = ld ? p_s[jj * HP + sl.head[k]] : 0.f;
-        }
+        const bool ld = ok && g.ok;
+        x[u] = ld ? ldg4(fcol + (size_t)sidx * HD) : zero4();
+        p[u] = ld ? p_s[jj * HP + tl] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int k = 0; k < C; ++k) fma4(acc[k], p[u][k], x[u][k]);
+      for (int u = 0; u < kUA; ++u) fma4(acc, p[u], x[u]);
     }
     __syncwarp();
   }
 
   if (it.frag) {  // un-normalised partial + fragment statistics; attn_frag_finalize_kernel merges them
-    if (lane < H) {
-      a.p1[(size_t)it.fi * H + lane] = m_run;
-      a.p2[(size_t)it.fi * H + lane] = s_run;
+    if (lane < g.nh) {
+      a.p1[(size_t)it.fi * H + g.h_lo + lane] = m_run;
+      a.p2[(size_t)it.fi * H + g.h_lo + lane] = s_run;
     }
-    float* pcol = a.p0 + (size_t)it.fi * HD + (size_t)lane * 4;
-#pragma unroll
-    for (int k = 0; k < C; ++k)
-      if (sl.ok[k]) st4(pcol + (size_t)k * 128, acc[k]);
+    if (g.ok) st4(a.p0 + (size_t)it.fi * HD + g.col, acc);
     return;
   }
-  if (lane < H) {
+  if (lane < g.nh) {
     const float m = len > 0 ? m_run : 0.f;
-    a.o1[(size_t)v * H + lane] = m;
-    a.o2[(size_t)v * H + lane] = s_run;
+    a.o1[(size_t)v * H + g.h_lo + lane] = m;
+    a.o2[(size_t)v * H + g.h_lo + lane] = s_run;
     sc_s[lane] = s_run > 0.f ? 1.f / s_run : 0.f;
     m_s[lane] = m;
   }
   __syncwarp();
-  float* ocol = a.o0 + (size_t)v * HD + (size_t)lane * 4;
-#pragma unroll
-  for (int k = 0; k < C; ++k)
-    if (sl.ok[k]) {
-      scale4(acc[k], sc_s[sl.head[k]]);
-      st4(ocol + (size_t)k * 128, acc[k]);
-    }
-  if (a.o3 != nullptr) {  // get_attention: stored logits -> a*keep, edge-id order
-    for (int i = lane; i < len * H; i += 32) {
-      const int h = i % H;
-      const size_t o = (size_t)a.eid[s0 + i / H] * H + h;
-      float av = expf(a.o3[o] - m_s[h]) * sc_s[h];
+  if (g.ok) {
+    scale4(acc, sc_s[tl]);
+    st4(a.o0 + (size_t)v * HD + g.col, acc);
+  }
+  if (a.o3 != nullptr) {  // get_attention: stored logits -> a*keep, edge-id order (heads of this group)
+    for (int i = lane; i < len * g.nh; i += 32) {
+      const int t = i % g.nh;
+      const size_t o = (size_t)a.eid[s0 + i / g.nh] * H + g.h_lo + t;
+      float av = expf(a.o3[o] - m_s[t]) * sc_s[t];
       if (a.keep != nullptr) av *= a.keep[o];
       a.o3[o] = av;
     }
@@ -243,50 +239,41 @@ gat_fwd_kernel(AttnArgs a) {
 }
 
 // =================================================================================================
-// REGAT backward, destination-major.  Per edge: da = <feat[src,h,:], G[v,h,:]>, recomputed a from
-// the saved row max / sum, dl = a*keep*da - a*S with S = <out[v,h,:], G[v,h,:]>.
+// REGAT backward, destination-major.  Per edge: da = <feat[src,h,:], G[v,h,:]>, a recomputed from the
+// saved row max / sum, dl = a*keep*da - a*S with S = <out[v,h,:], G[v,h,:]>.
 // Dynamic smem: w_s[R*H] | per warp: binsw[R*H]
-template <int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gat_bwd_dst_kernel(AttnArgs a) {
-  constexpr int U = UnrollA<C>::U;
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, D = a.D, HD = H * D, RH = a.etype != nullptr ? a.R * H : 0, lph = D >> 2;
+  const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
   float* w_s = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* binsw = smem + RH + warp * RH;
   for (int i = lane; i < RH; i += 32) binsw[i] = 0.f;
   load_rel_table(w_s, a);
-  const Slices<C> sl(lane, H, D);
-  const float* fcol = a.feat + (size_t)lane * 4;
-  const int64_t items = a.nfrag + (a.row_end - a.row_begin);
+  const int HG = num_groups(a);
+  const int64_t items = (a.nfrag + (a.row_end - a.row_begin)) * HG;
 
-  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp; r < items;
-       r += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const WorkItem it = decode_item(a, r, a.nfrag);
+  for (int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; wi < items;
+       wi += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const WorkItem it = decode_item(a, wi / HG, a.nfrag);
     if (!it.ok) continue;
+    const Group g = make_group(a, (int)(wi % HG), lane);
     const int64_t v = it.v;
     const int s0 = it.s0, len = it.len;
-    float4 g[C];
-    float S[C], m[C], inv[C], erv[C], der[C];
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-      float part = 0.f;
-      g[k] = zero4();
-      m[k] = inv[k] = erv[k] = 0.f;
-      der[k] = 0.f;
-      if (sl.ok[k]) {
-        const size_t c = (size_t)v * HD + (size_t)(lane + 32 * k) * 4;
-        g[k] = ldg4(a.G + c);
-        part = dot4(ldg4(a.out + c), g[k]);
-        const size_t vh = (size_t)v * H + sl.head[k];
-        m[k] = a.rowmax[vh];
-        const float s = a.rowsum[vh];
-        inv[k] = s > 0.f ? 1.f / s : 0.f;
-        erv[k] = a.er[vh];
-      }
-      S[k] = group_sum_rt(part, lph);
+    const float* fcol = a.feat + g.col;
+    float4 gv = zero4();
+    float part = 0.f, m = 0.f, inv = 0.f, erv = 0.f, der = 0.f;
+    if (g.ok) {
+      gv = ldg4(a.G + (size_t)v * HD + g.col);
+      part = dot4(ldg4(a.out + (size_t)v * HD + g.col), gv);
+      const size_t vh = (size_t)v * H + g.hl;
+      m = a.rowmax[vh];
+      const float sm = a.rowsum[vh];
+      inv = sm > 0.f ? 1.f / sm : 0.f;
+      erv = a.er[vh];
     }
+    const float S = group_sum_rt(part, g.lph);
     for (int base = 0; base < len; base += 32) {
       const int cnt = min(32, len - base);
       const int slot = s0 + base + lane;
@@ -296,51 +283,43 @@ gat_bwd_dst_kernel(AttnArgs a) {
         if (a.etype != nullptr) et = a.etype[slot];
         if (a.keep != nullptr) e = a.eid[slot];
       }
-      for (int j = 0; j < cnt; j += U) {
-        float4 x[U][C];
-        int sidx[U], set[U], se[U];
+      for (int j = 0; j < cnt; j += kUA) {
+        float4 x[kUA];
+        float da[kUA];
+        int sidx[kUA];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int jj = min(j + u, cnt - 1);
-          sidx[u] = __shfl_sync(0xffffffffu, idx, jj);
-          set[u] = __shfl_sync(0xffffffffu, et, jj);
-          se[u] = __shfl_sync(0xffffffffu, e, jj);
-#pragma unroll
-          for (int k = 0; k < C; ++k)
-            x[u][k] = (j + u < cnt && sl.ok[k]) ? ldg4(fcol + (size_t)sidx[u] * HD + (size_t)k * 128) : zero4();
+        for (int u = 0; u < kUA; ++u) {
+          sidx[u] = __shfl_sync(0xffffffffu, idx, min(j + u, cnt - 1));
+          x[u] = (j + u < cnt && g.ok) ? ldg4(fcol + (size_t)sidx[u] * HD) : zero4();
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j + u < cnt) {  // warp-uniform
-            const size_t sh = (size_t)(s0 + base + j + u) * H;
+        for (int u = 0; u < kUA; ++u) da[u] = group_sum_rt(dot4(x[u], gv), g.lph);  // independent reductions: ILP
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-              const float da = group_sum_rt(dot4(x[u][k], g[k]), lph);
-              if (sl.ok[k]) {
-                const int h = sl.head[k];
-                float pre = __ldg(a.el + (size_t)sidx[u] * H + h) + erv[k];
-                if (a.etype != nullptr) pre += w_s[set[u] * H + h];
-                const float aa = expf(leaky(pre, a.slope) - m[k]) * inv[k];
-                const float at = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)se[u] * H + h) : aa;
-                const float dp = (at * da - aa * S[k]) * leaky_grad(pre, a.slope);
-                if (sl.leader[k]) {
-                  a.o0[sh + h] = at;
-                  a.o1[sh + h] = dp;
-                  der[k] += dp;
-                  if (a.etype != nullptr) binsw[set[u] * H + h] += dp;
-                }
-              }
+        for (int u = 0; u < kUA; ++u) {
+          if (j + u < cnt) {  // warp-uniform
+            const int set = __shfl_sync(0xffffffffu, et, j + u);
+            const int se = __shfl_sync(0xffffffffu, e, j + u);
+            if (g.leader) {
+              const int h = g.hl;
+              const size_t sh = (size_t)(s0 + base + j + u) * H + h;
+              float pre = __ldg(a.el + (size_t)sidx[u] * H + h) + erv;
+              if (a.etype != nullptr) pre += w_s[set * H + h];
+              const float aa = expf(leaky(pre, a.slope) - m) * inv;
+              const float at = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)se * H + h) : aa;
+              const float dp = (at * da[u] - aa * S) * leaky_grad(pre, a.slope);
+              a.o0[sh] = at;
+              a.o1[sh] = dp;
+              der += dp;
+              if (a.etype != nullptr) binsw[set * H + h] += dp;
             }
           }
         }
       }
     }
-#pragma unroll
-    for (int k = 0; k < C; ++k)
-      if (sl.leader[k]) {
-        if (it.frag) a.p1[(size_t)it.fi * H + sl.head[k]] = der[k];
-        else a.o2[(size_t)v * H + sl.head[k]] = der[k];
-      }
+    if (g.leader) {
+      if (it.frag) a.p1[(size_t)it.fi * H + g.hl] = der;
+      else a.o2[(size_t)v * H + g.hl] = der;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < RH; i += blockDim.x) {
@@ -354,24 +333,23 @@ gat_bwd_dst_kernel(AttnArgs a) {
 // Source-major aggregation with precomputed per-slot, per-head weights (REGAT backward w.r.t. feat,
 // and the el-gradient reduction):  d_feat[u] = sum_j a_csr[slot_t[j]] * G[indices_t[j]].
 // Dynamic smem per warp: p_s[32][HP]
-template <int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gat_bwd_src_kernel(AttnArgs a) {
-  constexpr int U = UnrollA<C>::U;
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, D = a.D, HD = H * D, HP = H | 1;
+  const int H = a.H, HD = H * a.D, HP = H | 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* p_s = smem + warp * (32 * HP);
-  const WorkItem it = decode_item(a, (int64_t)blockIdx.x * kWarpsPerBlock + warp, a.nfrag_pad);
+  const int HG = num_groups(a);
+  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const WorkItem it = decode_item(a, wi / HG, a.nfrag);
   if (!it.ok) return;
+  const Group g = make_group(a, (int)(wi % HG), lane);
   const int64_t u_row = it.v;
   const int t0 = it.s0, len = it.len;
-  const Slices<C> sl(lane, H, D);
-  float4 acc[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) acc[k] = zero4();
+  const int tl = g.hl - g.h_lo;
+  float4 acc = zero4();
   float del_run = 0.f;
-  const float* gcol = a.G + (size_t)lane * 4;
+  const float* gcol = a.G + g.col;
 
   for (int base = 0; base < len; base += 32) {
     const int cnt = min(32, len - base);
@@ -381,79 +359,67 @@ gat_bwd_src_kernel(AttnArgs a) {
       d = a.indices[t0 + base + lane];
       slot = a.eid[t0 + base + lane];
     }
-    for (int h = 0; h < H; ++h) {
-      p_s[lane * HP + h] = valid ? __ldg(a.a_csr + (size_t)slot * H + h) : 0.f;
+    for (int t = 0; t < g.nh; ++t) {
+      const int h = g.h_lo + t;
+      p_s[lane * HP + t] = valid ? __ldg(a.a_csr + (size_t)slot * H + h) : 0.f;
       if (a.d_csr != nullptr) {
         const float tot = group_sum<32>(valid ? __ldg(a.d_csr + (size_t)slot * H + h) : 0.f);
-        if (lane == h) del_run += tot;
+        if (lane == t) del_run += tot;
       }
     }
     __syncwarp();
-    for (int j = 0; j < cnt; j += U) {
-      float4 x[U][C];
-      float p[U][C];
+    for (int j = 0; j < cnt; j += kUA) {
+      float4 x[kUA];
+      float p[kUA];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < kUA; ++u) {
         const bool ok = j + u < cnt;
         const int jj = ok ? j + u : j;
         const int sd = __shfl_sync(0xffffffffu, d, jj);
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-          const bool ld = ok && sl.ok[k];
-          x[u][k] = ld ? ldg4(gcol + (size_t)sd * HD + (size_t)k * 128) : zero4();
-          p[u][k] = ld ? p_s[jj * HP + sl.head[k]] : 0.f;
-        }
+        const bool ld = ok && g.ok;
+        x[u] = ld ? ldg4(gcol + (size_t)sd * HD) : zero4();
+        p[u] = ld ? p_s[jj * HP + tl] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int k = 0; k < C; ++k) fma4(acc[k], p[u][k], x[u][k]);
+      for (int u = 0; u < kUA; ++u) fma4(acc, p[u], x[u]);
     }
     __syncwarp();
   }
-  float* ocol = it.frag ? a.p0 + (size_t)it.fi * HD + (size_t)lane * 4 : a.o0 + (size_t)u_row * HD + (size_t)lane * 4;
-#pragma unroll
-  for (int k = 0; k < C; ++k)
-    if (sl.ok[k]) st4(ocol + (size_t)k * 128, acc[k]);
-  if (a.d_csr != nullptr && lane < H) {
-    if (it.frag) a.p1[(size_t)it.fi * H + lane] = del_run;
-    else a.o1[(size_t)u_row * H + lane] = del_run;
+  if (g.ok) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)u_row * HD) + g.col, acc);
+  if (a.d_csr != nullptr && lane < g.nh) {
+    if (it.frag) a.p1[(size_t)it.fi * H + g.h_lo + lane] = del_run;
+    else a.o1[(size_t)u_row * H + g.h_lo + lane] = del_run;
   }
 }
 
 // =================================================================================================
-// REGATv2 forward: per edge the gathered fs[src] row feeds both the logit
-// (sum_d attn*LeakyReLU(fs+fd)) and the aggregation; online softmax per edge.
+// REGATv2 forward: the gathered fs[src] slice feeds both the logit (sum_d attn*LeakyReLU(fs+fd),
+// reduced by xor-shuffles over the D/4 lanes of a head) and the aggregation; online softmax per
+// group of kUA edges.  Nothing [E,H,D]-sized is ever written.
 // Dynamic smem: w_s[R*H] | per warp: m_s[H], inv_s[H]
-template <int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gatv2_fwd_kernel(AttnArgs a) {
-  constexpr int U = UnrollA<C>::U;
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, D = a.D, HD = H * D, RH = a.etype != nullptr ? a.R * H : 0, lph = D >> 2;
+  const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
   float* w_s = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* m_s = smem + RH + warp * 2 * H;
   float* inv_s = m_s + H;
   load_rel_table(w_s, a);
-  const WorkItem it = decode_item(a, (int64_t)blockIdx.x * kWarpsPerBlock + warp, a.nfrag_pad);
+  const int HG = num_groups(a);
+  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const WorkItem it = decode_item(a, wi / HG, a.nfrag);
   if (!it.ok) return;
+  const Group g = make_group(a, (int)(wi % HG), lane);
   const int64_t v = it.v;
   const int s0 = it.s0, len = it.len;
-  const Slices<C> sl(lane, H, D);
-  float4 acc[C], fdv[C], at[C];
-  float m[C], s[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) {
-    acc[k] = fdv[k] = at[k] = zero4();
-    m[k] = -INFINITY;
-    s[k] = 0.f;
-    if (sl.ok[k]) {
-      fdv[k] = ldg4(a.fd + (size_t)v * HD + (size_t)(lane + 32 * k) * 4);
-      at[k] = ldg4(a.el + (size_t)(lane + 32 * k) * 4);
-    }
+  float4 acc = zero4(), fdv = zero4(), at = zero4();
+  float m = -INFINITY, s = 0.f;
+  if (g.ok) {
+    fdv = ldg4(a.fd + (size_t)v * HD + g.col);
+    at = ldg4(a.el + g.col);
   }
-  const float* fcol = a.feat + (size_t)lane * 4;
+  const float* fcol = a.feat + g.col;
   const bool need_eid = a.keep != nullptr || a.o3 != nullptr;
 
   for (int base = 0; base < len; base += 32) {
@@ -465,77 +431,70 @@ gatv2_fwd_kernel(AttnArgs a) {
       if (a.etype != nullptr) et = a.etype[slot];
       if (need_eid) e = a.eid[slot];
     }
-    for (int j = 0; j < cnt; j += U) {
-      float4 x[U][C];
-      int set[U], se[U];
+    for (int j = 0; j < cnt; j += kUA) {
+      float4 x[kUA];
+      float l[kUA];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int jj = min(j + u, cnt - 1);
-        const int sidx = __shfl_sync(0xffffffffu, idx, jj);
-        set[u] = __shfl_sync(0xffffffffu, et, jj);
-        se[u] = __shfl_sync(0xffffffffu, e, jj);
-#pragma unroll
-        for (int k = 0; k < C; ++k)
-          x[u][k] = (j + u < cnt && sl.ok[k]) ? ldg4(fcol + (size_t)sidx * HD + (size_t)k * 128) : zero4();
+      for (int u = 0; u < kUA; ++u) {
+        const int sidx = __shfl_sync(0xffffffffu, idx, min(j + u, cnt - 1));
+        x[u] = (j + u < cnt && g.ok) ? ldg4(fcol + (size_t)sidx * HD) : zero4();
       }
+      float bm = -INFINITY;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < kUA; ++u) {  // kUA independent head reductions
+        l[u] = group_sum_rt(dot4(at, leaky4(add4(x[u], fdv), a.slope)), g.lph);
+        const int set = __shfl_sync(0xffffffffu, et, min(j + u, cnt - 1));
+        if (a.etype != nullptr) l[u] += w_s[set * H + g.hl];
+        if (j + u >= cnt) l[u] = -INFINITY;
+        bm = fmaxf(bm, l[u]);
+      }
+      const float m_new = fmaxf(m, bm);
+      const float sc = expf(m - m_new);
+      m = m_new;
+      s *= sc;
+      scale4(acc, sc);
+#pragma unroll
+      for (int u = 0; u < kUA; ++u) {
         if (j + u < cnt) {  // warp-uniform
-#pragma unroll
-          for (int k = 0; k < C; ++k) {
-            const float part = dot4(at[k], leaky4(add4(x[u][k], fdv[k]), a.slope));
-            float l = group_sum_rt(part, lph);
-            if (sl.ok[k]) {
-              const int h = sl.head[k];
-              if (a.etype != nullptr) l += w_s[set[u] * H + h];
-              if (a.o3 != nullptr && sl.leader[k]) a.o3[(size_t)se[u] * H + h] = l;
-              const float m_new = fmaxf(m[k], l);
-              const float sc = expf(m[k] - m_new);
-              float p = expf(l - m_new);
-              s[k] = s[k] * sc + p;
-              m[k] = m_new;
-              if (a.keep != nullptr) p *= __ldg(a.keep + (size_t)se[u] * H + h);
-              scale4(acc[k], sc);
-              fma4(acc[k], p, x[u][k]);
-            }
+          const int se = __shfl_sync(0xffffffffu, e, j + u);
+          if (g.ok) {
+            if (a.o3 != nullptr && g.leader) a.o3[(size_t)se * H + g.hl] = l[u];
+            float p = expf(l[u] - m_new);
+            s += p;
+            if (a.keep != nullptr) p *= __ldg(a.keep + (size_t)se * H + g.hl);
+            fma4(acc, p, x[u]);
           }
         }
       }
     }
   }
   if (it.frag) {
-#pragma unroll
-    for (int k = 0; k < C; ++k)
-      if (sl.ok[k]) {
-        st4(a.p0 + (size_t)it.fi * HD + (size_t)(lane + 32 * k) * 4, acc[k]);
-        if (sl.leader[k]) {
-          a.p1[(size_t)it.fi * H + sl.head[k]] = m[k];
-          a.p2[(size_t)it.fi * H + sl.head[k]] = s[k];
-        }
+    if (g.ok) {
+      st4(a.p0 + (size_t)it.fi * HD + g.col, acc);
+      if (g.leader) {
+        a.p1[(size_t)it.fi * H + g.hl] = m;
+        a.p2[(size_t)it.fi * H + g.hl] = s;
       }
+    }
     return;
   }
-#pragma unroll
-  for (int k = 0; k < C; ++k) {
-    if (sl.ok[k]) {
-      const float inv = s[k] > 0.f ? 1.f / s[k] : 0.f;
-      const float mm = len > 0 ? m[k] : 0.f;
-      scale4(acc[k], inv);
-      st4(a.o0 + (size_t)v * HD + (size_t)(lane + 32 * k) * 4, acc[k]);
-      if (sl.leader[k]) {
-        const int h = sl.head[k];
-        a.o1[(size_t)v * H + h] = mm;
-        a.o2[(size_t)v * H + h] = s[k];
-        m_s[h] = mm;
-        inv_s[h] = inv;
-      }
+  if (g.ok) {
+    const float inv = s > 0.f ? 1.f / s : 0.f;
+    const float mm = len > 0 ? m : 0.f;
+    scale4(acc, inv);
+    st4(a.o0 + (size_t)v * HD + g.col, acc);
+    if (g.leader) {
+      a.o1[(size_t)v * H + g.hl] = mm;
+      a.o2[(size_t)v * H + g.hl] = s;
+      m_s[g.hl] = mm;
+      inv_s[g.hl] = inv;
     }
   }
   if (a.o3 != nullptr) {
     __syncwarp();
-    for (int i = lane; i < len * H; i += 32) {
-      const int h = i % H;
-      const size_t o = (size_t)a.eid[s0 + i / H] * H + h;
+    for (int i = lane; i < len * g.nh; i += 32) {
+      const int h = g.h_lo + i % g.nh;
+      const size_t o = (size_t)a.eid[s0 + i / g.nh] * H + h;
       float av = expf(a.o3[o] - m_s[h]) * inv_s[h];
       if (a.keep != nullptr) av *= a.keep[o];
       a.o3[o] = av;
@@ -546,55 +505,46 @@ gatv2_fwd_kernel(AttnArgs a) {
 // =================================================================================================
 // REGATv2 backward, destination-major: a_csr, dl_csr, d_fd rows, per-block partials of d_attn and
 // of the relation-gradient table.
-// Dynamic smem: w_s[R*H] | per warp: binsw[R*H] | per warp: dat_s[H*D]
-template <int C>
+// Dynamic smem: w_s[R*H] | per warp: binsw[R*H] | per warp: dat_s[128]
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gatv2_bwd_dst_kernel(AttnArgs a) {
-  constexpr int U = UnrollA<C>::U;
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, D = a.D, HD = H * D, RH = a.etype != nullptr ? a.R * H : 0, lph = D >> 2;
+  const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
+  const int RHp = (RH + 3) & ~3;  // keeps dat_all 16-byte aligned
   float* w_s = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int RHp = (RH + 3) & ~3;  // keeps dat_all 16-byte aligned
   float* binsw = smem + RHp + warp * RHp;
   float* dat_all = smem + RHp * (1 + kWarpsPerBlock);
   for (int i = lane; i < RH; i += 32) binsw[i] = 0.f;
   load_rel_table(w_s, a);
-  const Slices<C> sl(lane, H, D);
-  const float* fcol = a.feat + (size_t)lane * 4;
-  const int64_t items = a.nfrag + (a.row_end - a.row_begin);
-  float4 at[C], dat[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) {
-    dat[k] = zero4();
-    at[k] = sl.ok[k] ? ldg4(a.el + (size_t)(lane + 32 * k) * 4) : zero4();
-  }
+  const int HG = num_groups(a);
+  // every warp keeps ONE head group for all its items (its d_attn slice accumulates in registers): warp wg owns
+  // group wg % HG and walks the row items wg / HG, + usable / HG, ...; the last (nW % HG) warps stay idle
+  const int64_t nW = (int64_t)gridDim.x * kWarpsPerBlock, usable = nW - nW % HG;
+  const int64_t wg = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const Group g = make_group(a, (int)(wg % HG), lane);
+  const int64_t row_items = a.nfrag + (a.row_end - a.row_begin);
+  const float* fcol = a.feat + g.col;
+  const float4 at = g.ok ? ldg4(a.el + g.col) : zero4();
+  float4 dat = zero4();
 
-  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp; r < items;
-       r += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const WorkItem it = decode_item(a, r, a.nfrag);
+  for (int64_t ri = wg / HG; wg < usable && ri < row_items; ri += usable / HG) {
+    const WorkItem it = decode_item(a, ri, a.nfrag);
     if (!it.ok) continue;
     const int64_t v = it.v;
     const int s0 = it.s0, len = it.len;
-    float4 g[C], fdv[C], dfd[C];
-    float S[C], m[C], inv[C];
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-      float part = 0.f;
-      g[k] = fdv[k] = dfd[k] = zero4();
-      m[k] = inv[k] = 0.f;
-      if (sl.ok[k]) {
-        const size_t c = (size_t)v * HD + (size_t)(lane + 32 * k) * 4;
-        g[k] = ldg4(a.G + c);
-        fdv[k] = ldg4(a.fd + c);
-        part = dot4(ldg4(a.out + c), g[k]);
-        const size_t vh = (size_t)v * H + sl.head[k];
-        m[k] = a.rowmax[vh];
-        const float s = a.rowsum[vh];
-        inv[k] = s > 0.f ? 1.f / s : 0.f;
-      }
-      S[k] = group_sum_rt(part, lph);
+    float4 gv = zero4(), fdv = zero4(), dfd = zero4();
+    float part = 0.f, m = 0.f, inv = 0.f;
+    if (g.ok) {
+      gv = ldg4(a.G + (size_t)v * HD + g.col);
+      fdv = ldg4(a.fd + (size_t)v * HD + g.col);
+      part = dot4(ldg4(a.out + (size_t)v * HD + g.col), gv);
+      const size_t vh = (size_t)v * H + g.hl;
+      m = a.rowmax[vh];
+      const float sm = a.rowsum[vh];
+      inv = sm > 0.f ? 1.f / sm : 0.f;
     }
+    const float S = group_sum_rt(part, g.lph);
     for (int base = 0; base < len; base += 32) {
       const int cnt = min(32, len - base);
       const int slot = s0 + base + lane;
@@ -604,101 +554,92 @@ gatv2_bwd_dst_kernel(AttnArgs a) {
         if (a.etype != nullptr) et = a.etype[slot];
         if (a.keep != nullptr) e = a.eid[slot];
       }
-      for (int j = 0; j < cnt; j += U) {
-        float4 x[U][C];
-        int set[U], se[U];
+      for (int j = 0; j < cnt; j += kUA) {
+        float4 x[kUA];
+        float l[kUA], da[kUA];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int jj = min(j + u, cnt - 1);
-          const int sidx = __shfl_sync(0xffffffffu, idx, jj);
-          set[u] = __shfl_sync(0xffffffffu, et, jj);
-          se[u] = __shfl_sync(0xffffffffu, e, jj);
-#pragma unroll
-          for (int k = 0; k < C; ++k)
-            x[u][k] = (j + u < cnt && sl.ok[k]) ? ldg4(fcol + (size_t)sidx * HD + (size_t)k * 128) : zero4();
+        for (int u = 0; u < kUA; ++u) {
+          const int sidx = __shfl_sync(0xffffffffu, idx, min(j + u, cnt - 1));
+          x[u] = (j + u < cnt && g.ok) ? ldg4(fcol + (size_t)sidx * HD) : zero4();
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j + u < cnt) {  // warp-uniform
-            const size_t sh = (size_t)(s0 + base + j + u) * H;
+        for (int u = 0; u < kUA; ++u) {
+          l[u] = group_sum_rt(dot4(at, leaky4(add4(x[u], fdv), a.slope)), g.lph);
+          da[u] = group_sum_rt(dot4(x[u], gv), g.lph);
+        }
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-              const float4 q = add4(x[u][k], fdv[k]);
-              const float4 lr = leaky4(q, a.slope);
-              float l = group_sum_rt(dot4(at[k], lr), lph);
-              const float da = group_sum_rt(dot4(x[u][k], g[k]), lph);
-              if (sl.ok[k]) {
-                const int h = sl.head[k];
-                if (a.etype != nullptr) l += w_s[set[u] * H + h];
-                const float aa = expf(l - m[k]) * inv[k];
-                const float att = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)se[u] * H + h) : aa;
-                const float dl = att * da - aa * S[k];
-                if (sl.leader[k]) {
-                  a.o0[sh + h] = att;
-                  a.o1[sh + h] = dl;
-                  if (a.etype != nullptr) binsw[set[u] * H + h] += dl;
-                }
-                dfd[k].x = fmaf(dl * at[k].x, leaky_grad(q.x, a.slope), dfd[k].x);
-                dfd[k].y = fmaf(dl * at[k].y, leaky_grad(q.y, a.slope), dfd[k].y);
-                dfd[k].z = fmaf(dl * at[k].z, leaky_grad(q.z, a.slope), dfd[k].z);
-                dfd[k].w = fmaf(dl * at[k].w, leaky_grad(q.w, a.slope), dfd[k].w);
-                fma4(dat[k], dl, lr);
+        for (int u = 0; u < kUA; ++u) {
+          if (j + u < cnt) {  // warp-uniform
+            const int set = __shfl_sync(0xffffffffu, et, j + u);
+            const int se = __shfl_sync(0xffffffffu, e, j + u);
+            if (g.ok) {
+              const int h = g.hl;
+              float lu = l[u];
+              if (a.etype != nullptr) lu += w_s[set * H + h];
+              const float aa = expf(lu - m) * inv;
+              const float att = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)se * H + h) : aa;
+              const float dl = att * da[u] - aa * S;
+              if (g.leader) {
+                const size_t sh = (size_t)(s0 + base + j + u) * H + h;
+                a.o0[sh] = att;
+                a.o1[sh] = dl;
+                if (a.etype != nullptr) binsw[set * H + h] += dl;
               }
+              const float4 q = add4(x[u], fdv);
+              dfd.x = fmaf(dl * at.x, leaky_grad(q.x, a.slope), dfd.x);
+              dfd.y = fmaf(dl * at.y, leaky_grad(q.y, a.slope), dfd.y);
+              dfd.z = fmaf(dl * at.z, leaky_grad(q.z, a.slope), dfd.z);
+              dfd.w = fmaf(dl * at.w, leaky_grad(q.w, a.slope), dfd.w);
+              fma4(dat, dl, leaky4(q, a.slope));
             }
           }
         }
       }
     }
-    float* drow = it.frag ? a.p0 + (size_t)it.fi * HD : a.o2 + (size_t)v * HD;
-#pragma unroll
-    for (int k = 0; k < C; ++k)
-      if (sl.ok[k]) st4(drow + (size_t)(lane + 32 * k) * 4, dfd[k]);
+    if (g.ok) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o2 + (size_t)v * HD) + g.col, dfd);
   }
-#pragma unroll
-  for (int k = 0; k < C; ++k)
-    if (sl.ok[k]) st4(dat_all + (size_t)warp * HD + (size_t)(lane + 32 * k) * 4, dat[k]);
+  st4(dat_all + (size_t)warp * 128 + lane * 4, dat);
   __syncthreads();
   double* outp = a.partials + (size_t)blockIdx.x * a.partial_stride;
   for (int i = threadIdx.x; i < RH; i += blockDim.x) {
-    double s = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w) s += (double)smem[RHp + w * RHp + i];
-    outp[i] = s;
+    double sum = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) sum += (double)smem[RHp + w * RHp + i];
+    outp[i] = sum;
   }
   for (int i = threadIdx.x; i < HD; i += blockDim.x) {
-    double s = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w) s += (double)dat_all[w * HD + i];
-    outp[RH + i] = s;
+    double sum = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w)  // warps of this block that own head group i/128, in warp order
+      if (((int64_t)blockIdx.x * kWarpsPerBlock + w) % HG == i / 128) sum += (double)dat_all[w * 128 + (i & 127)];
+    outp[RH + i] = sum;
   }
 }
 
 // =================================================================================================
 // REGATv2 backward, source-major: d_fs[u] = sum_j a_csr*G[dst] + dl_csr*attn*LeakyReLU'(fs[u]+fd[dst]).
 // Dynamic smem per warp: p_s[32][HP], q_s[32][HP]
-template <int C>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gatv2_bwd_src_kernel(AttnArgs a) {
-  constexpr int U = C <= 2 ? 2 : 1;
+  constexpr int U = kUA / 2;  // two gathered rows per edge
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, D = a.D, HD = H * D, HP = H | 1;
+  const int H = a.H, HD = H * a.D, HP = H | 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* p_s = smem + warp * (64 * HP);
   float* q_s = p_s + 32 * HP;
-  const WorkItem it = decode_item(a, (int64_t)blockIdx.x * kWarpsPerBlock + warp, a.nfrag_pad);
+  const int HG = num_groups(a);
+  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const WorkItem it = decode_item(a, wi / HG, a.nfrag);
   if (!it.ok) return;
+  const Group g = make_group(a, (int)(wi % HG), lane);
   const int64_t u_row = it.v;
   const int t0 = it.s0, len = it.len;
-  const Slices<C> sl(lane, H, D);
-  float4 acc[C], fsu[C], at[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) {
-    acc[k] = fsu[k] = at[k] = zero4();
-    if (sl.ok[k]) {
-      fsu[k] = ldg4(a.feat + (size_t)u_row * HD + (size_t)(lane + 32 * k) * 4);
-      at[k] = ldg4(a.el + (size_t)(lane + 32 * k) * 4);
-    }
+  const int tl = g.hl - g.h_lo;
+  float4 acc = zero4(), fsu = zero4(), at = zero4();
+  if (g.ok) {
+    fsu = ldg4(a.feat + (size_t)u_row * HD + g.col);
+    at = ldg4(a.el + g.col);
   }
-  const float* gcol = a.G + (size_t)lane * 4;
-  const float* dcol = a.fd + (size_t)lane * 4;
+  const float* gcol = a.G + g.col;
+  const float* dcol = a.fd + g.col;
 
   for (int base = 0; base < len; base += 32) {
     const int cnt = min(32, len - base);
@@ -708,102 +649,83 @@ gatv2_bwd_src_kernel(AttnArgs a) {
       d = a.indices[t0 + base + lane];
       slot = a.eid[t0 + base + lane];
     }
-    for (int h = 0; h < H; ++h) {
-      p_s[lane * HP + h] = valid ? __ldg(a.a_csr + (size_t)slot * H + h) : 0.f;
-      q_s[lane * HP + h] = valid ? __ldg(a.d_csr + (size_t)slot * H + h) : 0.f;
+    for (int t = 0; t < g.nh; ++t) {
+      const int h = g.h_lo + t;
+      p_s[lane * HP + t] = valid ? __ldg(a.a_csr + (size_t)slot * H + h) : 0.f;
+      q_s[lane * HP + t] = valid ? __ldg(a.d_csr + (size_t)slot * H + h) : 0.f;
     }
     __syncwarp();
     for (int j = 0; j < cnt; j += U) {
-      float4 xg[U][C], xd[U][C];
-      float p[U][C], q[U][C];
+      float4 xg[U], xd[U];
+      float p[U], q[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const bool ok = j + u < cnt;
         const int jj = ok ? j + u : j;
         const int sd = __shfl_sync(0xffffffffu, d, jj);
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-          const bool ld = ok && sl.ok[k];
-          xg[u][k] = ld ? ldg4(gcol + (size_t)sd * HD + (size_t)k * 128) : zero4();
-          xd[u][k] = ld ? ldg4(dcol + (size_t)sd * HD + (size_t)k * 128) : zero4();
-          p[u][k] = ld ? p_s[jj * HP + sl.head[k]] : 0.f;
-          q[u][k] = ld ? q_s[jj * HP + sl.head[k]] : 0.f;
-        }
+        const bool ld = ok && g.ok;
+        xg[u] = ld ? ldg4(gcol + (size_t)sd * HD) : zero4();
+        xd[u] = ld ? ldg4(dcol + (size_t)sd * HD) : zero4();
+        p[u] = ld ? p_s[jj * HP + tl] : 0.f;
+        q[u] = ld ? q_s[jj * HP + tl] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int k = 0; k < C; ++k) {
-          fma4(acc[k], p[u][k], xg[u][k]);
-          const float4 z = add4(fsu[k], xd[u][k]);
-          acc[k].x = fmaf(q[u][k] * at[k].x, leaky_grad(z.x, a.slope), acc[k].x);
-          acc[k].y = fmaf(q[u][k] * at[k].y, leaky_grad(z.y, a.slope), acc[k].y);
-          acc[k].z = fmaf(q[u][k] * at[k].z, leaky_grad(z.z, a.slope), acc[k].z);
-          acc[k].w = fmaf(q[u][k] * at[k].w, leaky_grad(z.w, a.slope), acc[k].w);
-        }
+      for (int u = 0; u < U; ++u) {
+        fma4(acc, p[u], xg[u]);
+        const float4 z = add4(fsu, xd[u]);
+        acc.x = fmaf(q[u] * at.x, leaky_grad(z.x, a.slope), acc.x);
+        acc.y = fmaf(q[u] * at.y, leaky_grad(z.y, a.slope), acc.y);
+        acc.z = fmaf(q[u] * at.z, leaky_grad(z.z, a.slope), acc.z);
+        acc.w = fmaf(q[u] * at.w, leaky_grad(z.w, a.slope), acc.w);
+      }
     }
     __syncwarp();
   }
-  float* orow = it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)u_row * HD;
-#pragma unroll
-  for (int k = 0; k < C; ++k)
-    if (sl.ok[k]) st4(orow + (size_t)(lane + 32 * k) * 4, acc[k]);
+  if (g.ok) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)u_row * HD) + g.col, acc);
 }
 
 // =================================================================================================
 // Merges the fragments of every long row of a forward pass (online-softmax combine in fragment order):
 //   M = max_f m_f;  S = sum_f s_f*exp(m_f-M);  out = sum_f acc_f*exp(m_f-M) / S
-// and, for get_attention, normalises the row's stored logits.  One warp per long row.
-template <int C>
+// and, for get_attention, normalises the row's stored logits.  One warp per (long row, head group).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 attn_frag_finalize_kernel(AttnArgs a, const int32_t* __restrict__ long_rows,
                           const int32_t* __restrict__ frag_ptr, int num_long) {
-  const int H = a.H, D = a.D, HD = H * D;
+  const int H = a.H, HD = H * a.D;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int l = blockIdx.x * kWarpsPerBlock + warp;
+  const int HG = num_groups(a);
+  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int l = (int)(wi / HG);
   if (l >= num_long) return;
   const int64_t v = long_rows[l];
   if (v < a.row_begin || v >= a.row_end) return;
+  const Group g = make_group(a, (int)(wi % HG), lane);
   const int f0 = frag_ptr[l], f1 = frag_ptr[l + 1];
-  const Slices<C> sl(lane, H, D);
-  float M = -INFINITY;  // lane h (< H) owns head h
-  if (lane < H)
-    for (int f = f0; f < f1; ++f) M = fmaxf(M, a.p1[(size_t)f * H + lane]);
+  const size_t hh = g.hl;  // every lane tracks the statistics of its own head (redundant within a head)
+  float M = -INFINITY;
+  for (int f = f0; f < f1; ++f) M = fmaxf(M, a.p1[(size_t)f * H + hh]);
   float S = 0.f;
-  float4 acc[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) acc[k] = zero4();
+  float4 acc = zero4();
   for (int f = f0; f < f1; ++f) {
-    float sc = 0.f;
-    if (lane < H) {
-      sc = expf(a.p1[(size_t)f * H + lane] - M);
-      S += a.p2[(size_t)f * H + lane] * sc;
-    }
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-      const float sk = __shfl_sync(0xffffffffu, sc, sl.head[k]);
-      if (sl.ok[k]) fma4(acc[k], sk, ldg4(a.p0 + (size_t)f * HD + (size_t)(lane + 32 * k) * 4));
-    }
+    const float sc = expf(a.p1[(size_t)f * H + hh] - M);
+    S += a.p2[(size_t)f * H + hh] * sc;
+    if (g.ok) fma4(acc, sc, ldg4(a.p0 + (size_t)f * HD + g.col));
   }
   const float inv = S > 0.f ? 1.f / S : 0.f;
-  if (lane < H) {
-    a.o1[(size_t)v * H + lane] = M;
-    a.o2[(size_t)v * H + lane] = S;
-  }
-#pragma unroll
-  for (int k = 0; k < C; ++k) {
-    const float ik = __shfl_sync(0xffffffffu, inv, sl.head[k]);
-    if (sl.ok[k]) {
-      scale4(acc[k], ik);
-      st4(a.o0 + (size_t)v * HD + (size_t)(lane + 32 * k) * 4, acc[k]);
+  if (g.ok) {
+    scale4(acc, inv);
+    st4(a.o0 + (size_t)v * HD + g.col, acc);
+    if (g.leader) {
+      a.o1[(size_t)v * H + hh] = M;
+      a.o2[(size_t)v * H + hh] = S;
     }
   }
   if (a.o3 != nullptr) {
     __syncwarp();
     const int s0 = a.indptr[v], len = a.indptr[v + 1] - s0;
-    for (int i = lane; i < len * H; i += 32) {
-      const int h = i % H;
-      const size_t o = (size_t)a.eid[s0 + i / H] * H + h;
+    for (int i = lane; i < len * g.nh; i += 32) {
+      const int h = g.h_lo + i % g.nh;
+      const size_t o = (size_t)a.eid[s0 + i / g.nh] * H + h;
       const float s = a.o2[(size_t)v * H + h];
       float av = expf(a.o3[o] - a.o1[(size_t)v * H + h]) * (s > 0.f ? 1.f / s : 0.f);
       if (a.keep != nullptr) av *= a.keep[o];
@@ -850,7 +772,7 @@ static bool apply_split(AttnArgs& a, const regnn_rowsplit_t* split, float* ws) {
   a.frag_row = split->frag_row;
   a.frag_begin = split->frag_begin;
   a.nfrag = split->num_frags;
-  a.nfrag_pad = (a.nfrag + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock;
+  a.nfrag_pad = a.nfrag;
   a.threshold = split->threshold;
   const size_t HD = (size_t)a.H * a.D;
   a.p0 = ws;
@@ -878,27 +800,17 @@ static int check_shape(const char* who, int H, int D, int R, bool has_rel, bool 
   return REGNN_OK;
 }
 
-#define REGNN_DISPATCH_C(KERNEL, GRID, SMEM)                                           \
-  do {                                                                                 \
-    int rc_ = REGNN_OK;                                                                \
-    switch (pick_c(a.H * a.D)) {                                                       \
-      case 1: rc_ = set_smem(KERNEL<1>, SMEM); if (rc_ == REGNN_OK) KERNEL<1><<<GRID, kWarpsPerBlock * 32, SMEM, stream>>>(a); break; \
-      case 2: rc_ = set_smem(KERNEL<2>, SMEM); if (rc_ == REGNN_OK) KERNEL<2><<<GRID, kWarpsPerBlock * 32, SMEM, stream>>>(a); break; \
-      case 4: rc_ = set_smem(KERNEL<4>, SMEM); if (rc_ == REGNN_OK) KERNEL<4><<<GRID, kWarpsPerBlock * 32, SMEM, stream>>>(a); break; \
-      default: rc_ = set_smem(KERNEL<8>, SMEM); if (rc_ == REGNN_OK) KERNEL<8><<<GRID, kWarpsPerBlock * 32, SMEM, stream>>>(a); break; \
-    }                                                                                  \
-    if (rc_ != REGNN_OK) return rc_;                                                   \
+#define REGNN_DISPATCH_C(KERNEL, GRID, SMEM)                                  \
+  do {                                                                        \
+    int rc_ = set_smem(KERNEL, SMEM);                                         \
+    if (rc_ != REGNN_OK) return rc_;                                          \
+    KERNEL<<<GRID, kWarpsPerBlock * 32, SMEM, stream>>>(a);                   \
   } while (0)
 
-#define REGNN_DISPATCH_FINALIZE(GRID)                                                                                  \
-  do {                                                                                                                 \
-    switch (pick_c(a.H * a.D)) {                                                                                       \
-      case 1: attn_frag_finalize_kernel<1><<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long); break; \
-      case 2: attn_frag_finalize_kernel<2><<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long); break; \
-      case 4: attn_frag_finalize_kernel<4><<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long); break; \
-      default: attn_frag_finalize_kernel<8><<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long); break; \
-    }                                                                                                                  \
-  } while (0)
+#define REGNN_DISPATCH_FINALIZE(GRID) \
+  attn_frag_finalize_kernel<<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long)
+
+static int head_groups(int H, int D) { return (H * D + 127) / 128; }
 
 }  // namespace regnn
 
@@ -929,10 +841,10 @@ extern "C" int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, cons
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_fwd: incomplete row split");
   const int H = num_heads, HP = H | 1;
   const size_t smem = sizeof(float) * ((size_t)a.R * H + (size_t)kWarpsPerBlock * (32 * HP + 2 * H));
-  const unsigned grid = (unsigned)((rows + a.nfrag_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
   REGNN_DISPATCH_C(gat_fwd_kernel, grid, smem);
   if (a.nfrag > 0) {
-    const unsigned fgrid = (unsigned)((split->num_long + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const unsigned fgrid = (unsigned)(((int64_t)split->num_long * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
     REGNN_DISPATCH_FINALIZE(fgrid);
   }
   return check_launch("regnn_gat_fwd");
@@ -966,7 +878,7 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_dst: incomplete row split");
   const int RH = a.R * num_heads;
   const size_t smem = sizeof(float) * ((size_t)RH * (1 + kWarpsPerBlock)) + 16;
-  const int nb = partial_blocks(rows + a.nfrag);
+  const int nb = partial_blocks((rows + a.nfrag) * head_groups(a.H, a.D));
   REGNN_DISPATCH_C(gat_bwd_dst_kernel, nb, smem);
   if (a.nfrag > 0) launch_rowsum(split, a.p1, num_heads, d_er, row_begin, row_end, stream);
   if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH, RH, theta, alpha, d_theta, stream);
@@ -993,7 +905,7 @@ extern "C" int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_src: incomplete row split");
   const int HP = num_heads | 1;
   const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * 32 * HP;
-  const unsigned grid = (unsigned)((rows + a.nfrag_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
   REGNN_DISPATCH_C(gat_bwd_src_kernel, grid, smem);
   if (a.nfrag > 0) {
     launch_rowsum(split, a.p0, num_heads * head_dim, d_feat, row_begin, row_end, stream);
@@ -1027,10 +939,10 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
   a.o0 = out; a.o1 = rowmax; a.o2 = rowsum; a.o3 = attn_out;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_fwd: incomplete row split");
   const size_t smem = sizeof(float) * ((size_t)a.R * num_heads + (size_t)kWarpsPerBlock * 2 * num_heads) + 16;
-  const unsigned grid = (unsigned)((rows + a.nfrag_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
   REGNN_DISPATCH_C(gatv2_fwd_kernel, grid, smem);
   if (a.nfrag > 0) {
-    const unsigned fgrid = (unsigned)((split->num_long + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const unsigned fgrid = (unsigned)(((int64_t)split->num_long * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
     REGNN_DISPATCH_FINALIZE(fgrid);
   }
   return check_launch("regnn_gatv2_fwd");
@@ -1065,7 +977,7 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
   a.partials = partials; a.partial_stride = RH + HD;
   const size_t smem = sizeof(float) * ((size_t)((RH + 3) & ~3) * (1 + kWarpsPerBlock) + (size_t)kWarpsPerBlock * HD) + 16;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: incomplete row split");
-  const int nb = partial_blocks(rows + a.nfrag);
+  const int nb = partial_blocks((rows + a.nfrag) * head_groups(a.H, a.D));
   REGNN_DISPATCH_C(gatv2_bwd_dst_kernel, nb, smem);
   if (a.nfrag > 0) launch_rowsum(split, a.p0, HD, d_fd, row_begin, row_end, stream);
   if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH + HD, RH, theta, alpha, d_theta, stream);
@@ -1097,7 +1009,7 @@ extern "C" int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indic
   const int HP = num_heads | 1;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: incomplete row split");
   const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * 64 * HP;
-  const unsigned grid = (unsigned)((rows + a.nfrag_pad + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
   REGNN_DISPATCH_C(gatv2_bwd_src_kernel, grid, smem);
   if (a.nfrag > 0) launch_rowsum(split, a.p0, num_heads * head_dim, d_fs, row_begin, row_end, stream);
   return check_launch("regnn_gatv2_bwd_src");
