@@ -65,8 +65,9 @@ typedef struct regnn_rowsplit {
 int regnn_version(void);
 const char* regnn_status_string(int status);
 const char* regnn_last_error_string(void);
-/* Number of thread blocks regnn_* reduction kernels emit partial sums for (sizing helper). */
-int regnn_partial_blocks(int64_t num_rows);
+/* Upper bound on the number of thread blocks any regnn_* reduction kernel emits partial sums for: size every
+ * `partials` scratch argument as regnn_max_partial_blocks() * <per-block entries> doubles. */
+int regnn_max_partial_blocks(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph construction.  Replaces DGL's lazy in-CSR / out-CSR build behind
@@ -103,7 +104,7 @@ int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr, const f
                         int64_t row_end, float* deg, float* norm, void* stream);
 /* Backward of the above: d_theta[r] += alpha * LeakyReLU'(alpha*theta[r]) *
  *   sum_{e: etype e = r} d_deg[dst e],   d_deg[v] = [deg[v] >= 1] * q * max(deg,1)^(q-1) * d_norm[v].
- * partials: double [regnn_partial_blocks(row_end-row_begin) * R] scratch.  d_theta is OVERWRITTEN. */
+ * partials: double [regnn_max_partial_blocks() * R] scratch.  d_theta is OVERWRITTEN. */
 int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const float* theta,
                         float alpha, int num_relations, float exponent, int64_t row_begin,
                         int64_t row_end, const float* deg, const float* d_norm, double* partials,
@@ -134,7 +135,7 @@ int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t*
  * norm_sides: bit 0 = the forward scaled the source side by norm, bit 1 = the destination side
  * (3 for REGraphConv / REMixHopConv; 1 for RESAGEConv, layer/RESAGEConv.py:82; 2 for REGINConv,
  * layer/REGINConv.py:61); the unscaled side drops out of both formulas.
- * partials: double [regnn_partial_blocks(rows) * R].  d_theta is OVERWRITTEN; d_norm rows written. */
+ * partials: double [regnn_max_partial_blocks() * R].  d_theta is OVERWRITTEN; d_norm rows written. */
 int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
                      const float* theta, float alpha, int num_relations, const float* norm,
                      int norm_sides, const float* X, int64_t ldx, const float* Y, int64_t ldy, const float* G,
@@ -148,7 +149,7 @@ int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_
  * (ns/nd = norm on the sides selected by norm_sides, else 1): the per-edge dot <X[u], G[dst]> reuses the
  * G[dst] row that the dX gather already holds in registers; X rows of the block are staged in shared
  * memory by TMA bulk copies.  d_norm is NOT produced here: see regnn_rowdot_norm_bwd.
- * partials: double [regnn_partial_blocks(rows) * R]; d_theta is OVERWRITTEN;
+ * partials: double [regnn_max_partial_blocks() * R]; d_theta is OVERWRITTEN;
  * split_workspace: split_t->num_frags * feat floats. */
 int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t, const uint8_t* etype_t,
                          const float* theta, float alpha, int num_relations, const float* norm,
@@ -183,7 +184,7 @@ int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, const int32_t* 
 
 /* Backward, destination-major pass.  G = dL/d out.  Produces, per CSR slot, a_csr = a*keep and
  * dpre_csr = dL/d(el[src]+er[dst]+w) (both [E,H], slot order), d_er [N,H] and d_theta [R,H].
- * partials: double [regnn_partial_blocks(rows) * R * H]. */
+ * partials: double [regnn_max_partial_blocks() * R * H]. */
 int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
                       const uint8_t* etype_csr, const float* theta, float alpha, int num_relations,
                       const float* feat, const float* el, const float* er, float negative_slope,
@@ -219,7 +220,7 @@ int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t
 
 /* Backward, destination-major pass: a_csr = a*keep, dl_csr = dL/dl (both [E,H] slot order),
  * d_fd [N,H,D], d_attn [H,D], d_theta [R,H].
- * partials: double [regnn_partial_blocks(rows) * (R*H + H*D)]. */
+ * partials: double [regnn_max_partial_blocks() * (R*H + H*D)]. */
 int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
                         const uint8_t* etype_csr, const float* theta, float alpha,
                         int num_relations, const float* fs, const float* fd, const float* attn,

@@ -20,7 +20,7 @@ SIGNATURES = {
     'regnn_version': (_i32, []),
     'regnn_status_string': (ctypes.c_char_p, [_i32]),
     'regnn_last_error_string': (ctypes.c_char_p, []),
-    'regnn_partial_blocks': (_i32, [_i64]),
+    'regnn_max_partial_blocks': (_i32, []),
     'regnn_csr_build_workspace_bytes': (_sz, [_i64, _i64]),
     'regnn_csr_build': (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     'regnn_etype_permute': (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
@@ -92,5 +92,6 @@ def call(name, *args):
         raise RuntimeError('%s failed (%d: %s): %s' % (name, rc, lib.regnn_status_string(rc).decode(), msg))
 
 
-def partial_blocks(rows):
-    return load().regnn_partial_blocks(int(rows))
+def partial_blocks(rows=None):
+    """Number of per-block partial slots to allocate for any reduction entry point (an upper bound)."""
+    return load().regnn_max_partial_blocks()

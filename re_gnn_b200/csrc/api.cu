@@ -89,6 +89,6 @@ const char* regnn_status_string(int status) {
 
 const char* regnn_last_error_string(void) { return regnn::g_err; }
 
-int regnn_partial_blocks(int64_t num_rows) { return regnn::partial_blocks(num_rows); }
+int regnn_max_partial_blocks(void) { return regnn::kMaxPartialBlocks; }
 
 }  // extern "C"
