@@ -975,7 +975,7 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
   a.row_begin = row_begin; a.row_end = row_end; a.o0 = a_csr; a.o1 = dl_csr; a.o2 = d_fd;
   const int RH = a.R * num_heads, HD = num_heads * head_dim;
   a.partials = partials; a.partial_stride = RH + HD;
-  const size_t smem = sizeof(float) * ((size_t)((RH + 3) & ~3) * (1 + kWarpsPerBlock) + (size_t)kWarpsPerBlock * HD) + 16;
+  const size_t smem = sizeof(float) * ((size_t)((RH + 3) & ~3) * (1 + kWarpsPerBlock) + (size_t)kWarpsPerBlock * 128) + 16;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: incomplete row split");
   const int nb = partial_blocks((rows + a.nfrag) * head_groups(a.H, a.D));
   REGNN_DISPATCH_C(gatv2_bwd_dst_kernel, nb, smem);
