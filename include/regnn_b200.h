@@ -155,14 +155,16 @@ int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t, cons
                          const float* theta, float alpha, int num_relations, const float* norm,
                          int norm_sides, const float* X, int64_t ldx, const float* G, int64_t ldg,
                          float* dX, int64_t lddx, int64_t row_begin, int64_t row_end, int feat,
-                         double* partials, float* d_theta, const regnn_rowsplit_t* split_t,
-                         float* split_workspace, void* stream);
+                         double* partials, float* d_theta, float* xdx /* optional [N]: <X[u],dX[u]> per row */,
+                         const regnn_rowsplit_t* split_t, float* split_workspace, void* stream);
 
 /* d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v] for rows [row_begin,row_end):
- * the gradient of regnn_spmm_fwd w.r.t. the norm vector (row-local, pure streaming). */
+ * the gradient of regnn_spmm_fwd w.r.t. the norm vector (row-local, pure streaming).  If xdx (from
+ * regnn_spmm_bwd_fused) is given, X and dX are not read. */
 int regnn_rowdot_norm_bwd(const float* norm, int norm_sides, const float* X, int64_t ldx, const float* Y,
                           int64_t ldy, const float* G, int64_t ldg, const float* dX, int64_t lddx,
-                          int64_t row_begin, int64_t row_end, int feat, float* d_norm, void* stream);
+                          const float* xdx, int64_t row_begin, int64_t row_end, int feat, float* d_norm,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused REGAT layer core (layer/REGATConv.py:71-92): per destination v and head h

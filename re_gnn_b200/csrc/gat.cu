@@ -82,7 +82,8 @@ __device__ __forceinline__ WorkItem decode_item(const AttnArgs& a, int64_t wi, i
   return w;
 }
 
-constexpr int kUA = 8;  // source rows gathered per lane before any math (memory-level parallelism)
+constexpr int kUA = 4;  // source rows gathered per lane before any math; kept small so that 5 blocks (40 warps) fit
+                         // per SM: with short rows it is resident warps, not loads per warp, that hide the latency chain
 
 __device__ __forceinline__ void load_rel_table(float* w_s, const AttnArgs& a) {
   if (a.etype != nullptr) {
@@ -131,7 +132,7 @@ __device__ __forceinline__ int num_groups(const AttnArgs& a) { return (a.H * a.D
 // batch max / sum through warp shuffles; probabilities staged in shared memory; then the warp
 // aggregates the batch with kUA coalesced 128-bit loads in flight per lane.
 // Dynamic smem: w_s[R*H] | per warp: p_s[32][HP], sc_s[H], m_s[H]     (HP = H|1: conflict-free)
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 gat_fwd_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int H = a.H, HD = H * a.D, HP = H | 1;
@@ -242,7 +243,7 @@ gat_fwd_kernel(AttnArgs a) {
 // REGAT backward, destination-major.  Per edge: da = <feat[src,h,:], G[v,h,:]>, a recomputed from the
 // saved row max / sum, dl = a*keep*da - a*S with S = <out[v,h,:], G[v,h,:]>.
 // Dynamic smem: w_s[R*H] | per warp: binsw[R*H]
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 gat_bwd_dst_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
@@ -333,7 +334,7 @@ gat_bwd_dst_kernel(AttnArgs a) {
 // Source-major aggregation with precomputed per-slot, per-head weights (REGAT backward w.r.t. feat,
 // and the el-gradient reduction):  d_feat[u] = sum_j a_csr[slot_t[j]] * G[indices_t[j]].
 // Dynamic smem per warp: p_s[32][HP]
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 gat_bwd_src_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int H = a.H, HD = H * a.D, HP = H | 1;
@@ -397,7 +398,7 @@ gat_bwd_src_kernel(AttnArgs a) {
 // reduced by xor-shuffles over the D/4 lanes of a head) and the aggregation; online softmax per
 // group of kUA edges.  Nothing [E,H,D]-sized is ever written.
 // Dynamic smem: w_s[R*H] | per warp: m_s[H], inv_s[H]
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 gatv2_fwd_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
@@ -506,7 +507,7 @@ gatv2_fwd_kernel(AttnArgs a) {
 // REGATv2 backward, destination-major: a_csr, dl_csr, d_fd rows, per-block partials of d_attn and
 // of the relation-gradient table.
 // Dynamic smem: w_s[R*H] | per warp: binsw[R*H] | per warp: dat_s[128]
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 gatv2_bwd_dst_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
@@ -617,7 +618,7 @@ gatv2_bwd_dst_kernel(AttnArgs a) {
 // =================================================================================================
 // REGATv2 backward, source-major: d_fs[u] = sum_j a_csr*G[dst] + dl_csr*attn*LeakyReLU'(fs[u]+fd[dst]).
 // Dynamic smem per warp: p_s[32][HP], q_s[32][HP]
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 gatv2_bwd_src_kernel(AttnArgs a) {
   constexpr int U = kUA / 2;  // two gathered rows per edge
   extern __shared__ __align__(16) float smem[];

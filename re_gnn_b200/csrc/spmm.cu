@@ -242,6 +242,7 @@ struct StreamArgs {
   int64_t ldr;
   double* partials;      // [gridDim.x][R]
   int use_tma;           // rows are 16-byte aligned multiples of 16 bytes: stage the tile with cp.async.bulk
+  float* xdx;            // optional [N]: <Xrow[u], dX[u]> per row (the source-side half of d_norm), or null
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -367,11 +368,29 @@ spmm_stream_kernel(StreamArgs sa) {
       int row = cur;
       int row_end_slot = __shfl_sync(0xffffffffu, my_end, row);
       float nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
-      T acc[C];
+      T acc[C], trow[C];   // trow: the row-level tile slice of the current row (BINS), kept in registers
 #pragma unroll
-      for (int k = 0; k < C; ++k) acc[k] = V::zero();
+      for (int k = 0; k < C; ++k) acc[k] = trow[k] = V::zero();
+      bool trow_valid = false;
+      int cur_rel = 0;      // run-length accumulation of the relation bins: one shared-memory update per run
+      float racc = 0.f;
 
+      auto load_trow = [&]() {
+        const float* tp = mytile + (size_t)row * Fp + (size_t)lane * VW;
+#pragma unroll
+        for (int k = 0; k < C; ++k) trow[k] = col_ok[k] ? lds_vec<VW>(tp + (size_t)k * 32 * VW) : V::zero();
+        trow_valid = true;
+      };
       auto flush = [&]() {
+        if (BINS && sa.xdx != nullptr && !is_frag) {  // <X[u], dX[u]> while dX[u] is still in registers
+          if (!trow_valid) load_trow();
+          float d = 0.f;
+#pragma unroll
+          for (int k = 0; k < C; ++k) d += V::dot(acc[k], trow[k]);
+          d = group_sum<32>(d) * nd_cur;
+          if (lane == 0) sa.xdx[r0 + row] = d;
+        }
+        trow_valid = false;
         if (is_frag) {
           float* y = a.partial + (size_t)wi * a.F + (size_t)lane * VW;
 #pragma unroll
@@ -443,22 +462,32 @@ spmm_stream_kernel(StreamArgs sa) {
               if (BINS) {
                 const float sb = __shfl_sync(0xffffffffu, ns, j + u) * nd_cur;
                 const int se = __shfl_sync(0xffffffffu, et, j + u);
-                const float* trow = mytile + (size_t)row * Fp + (size_t)lane * VW;
+                if (!trow_valid) load_trow();
                 float d = 0.f;
 #pragma unroll
-                for (int k = 0; k < C; ++k)
-                  if (col_ok[k]) d += V::dot(x[u][k], lds_vec<VW>(trow + (size_t)k * 32 * VW));
-                mybins[se * 32] += sb * d;  // lane-local bin: fixed order, bank-conflict free
+                for (int k = 0; k < C; ++k) d += V::dot(x[u][k], trow[k]);
+                if (se != cur_rel) {  // warp-uniform: lane-local bin, fixed order, bank-conflict free
+                  mybins[cur_rel * 32] += racc;
+                  racc = 0.f;
+                  cur_rel = se;
+                }
+                racc = fmaf(sb, d, racc);
               }
             }
           }
         }
+      }
+      if (BINS && !tile_ready) {  // segment without slots: the flush below still needs the tile
+        mbar_wait(mybar, phase);
+        phase ^= 1u;
+        tile_ready = true;
       }
       while (row < seg_end) {  // last row of the segment + trailing empty rows
         flush();
         ++row;
         if (row < seg_end) nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
       }
+      if (BINS) mybins[cur_rel * 32] += racc;
       cur = seg_end;
     }
     if (BINS && !tile_ready) {  // item without a single short-row slot: still consume the barrier phase
@@ -469,22 +498,39 @@ spmm_stream_kernel(StreamArgs sa) {
   if (BINS) reduce_bins(bins, scratch, a.R, sa.partials + (size_t)blockIdx.x * a.R);
 }
 
-// d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v]   (pure streaming, row per warp)
+// d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v]   (pure streaming, row per warp).
+// xdx != null supplies <X[v],dX[v]> (produced by the fused backward), so X and dX are not read again.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 rowdot_norm_kernel(const float* __restrict__ norm, int sides, const float* __restrict__ X, int64_t ldx,
                    const float* __restrict__ Y, int64_t ldy, const float* __restrict__ G, int64_t ldg,
-                   const float* __restrict__ dX, int64_t lddx, int F, int64_t row_begin, int64_t row_end,
-                   float* __restrict__ d_norm) {
+                   const float* __restrict__ dX, int64_t lddx, const float* __restrict__ xdx, int F,
+                   int64_t row_begin, int64_t row_end, float* __restrict__ d_norm) {
   const int lane = threadIdx.x & 31;
   const int64_t v = row_begin + (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (v >= row_end) return;
   float p = 0.f;
   for (int c = lane; c < F; c += 32) {
     if (sides & 2) p = fmaf(__ldg(Y + (size_t)v * ldy + c), __ldg(G + (size_t)v * ldg + c), p);
-    if (sides & 1) p = fmaf(__ldg(X + (size_t)v * ldx + c), __ldg(dX + (size_t)v * lddx + c), p);
+    if ((sides & 1) && xdx == nullptr) p = fmaf(__ldg(X + (size_t)v * ldx + c), __ldg(dX + (size_t)v * lddx + c), p);
   }
   p = group_sum<32>(p);
+  if ((sides & 1) && xdx != nullptr) p += xdx[v];
   if (lane == 0) d_norm[v] = p / norm[v];
+}
+
+// xdx[v] = <X[v], dX[v]> for the long rows (their dX is only complete after the fragment finalize)
+__global__ void long_row_xdx_kernel(const int32_t* __restrict__ long_rows, int num_long, const float* __restrict__ X,
+                                    int64_t ldx, const float* __restrict__ dX, int64_t lddx, int F, int64_t row_begin,
+                                    int64_t row_end, float* __restrict__ xdx) {
+  const int lane = threadIdx.x & 31;
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (l >= num_long) return;
+  const int64_t v = long_rows[l];
+  if (v < row_begin || v >= row_end) return;
+  float p = 0.f;
+  for (int c = lane; c < F; c += 32) p = fmaf(__ldg(X + (size_t)v * ldx + c), dX[(size_t)v * lddx + c], p);
+  p = group_sum<32>(p);
+  if (lane == 0) xdx[v] = p;
 }
 
 struct SpmmBwdArgs {
@@ -988,7 +1034,7 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
                                     int num_relations, const float* norm, int norm_sides, const float* X,
                                     int64_t ldx, const float* Gd, int64_t ldg, float* dX, int64_t lddx,
                                     int64_t row_begin, int64_t row_end, int feat, double* partials,
-                                    float* d_theta, const regnn_rowsplit_t* split_t,
+                                    float* d_theta, float* xdx, const regnn_rowsplit_t* split_t,
                                     float* split_workspace, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr_t && indices_t && etype_t && theta && X && Gd && dX && partials && d_theta,
@@ -1013,6 +1059,7 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
   sa.ldr = ldx;
   sa.partials = partials;
   sa.use_tma = (feat % 4 == 0 && aligned_to(X, 16) && ldx % 4 == 0) ? 1 : 0;
+  sa.xdx = xdx;
   const int Fp = (feat + 3) & ~3;
   const size_t smem = 64 + (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float)) +
                       (size_t)kWarpsPerBlock * kRowsPerItemBins * Fp * sizeof(float);
@@ -1026,21 +1073,24 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
     spmm_frag_finalize_kernel<<<split_t->num_long, 128, 0, stream>>>(split_t->long_rows, split_t->frag_ptr,
                                                                      split_t->num_long, split_workspace, sa.s.norm_dst, dX,
                                                                      lddx, feat, row_begin, row_end);
+  if (sa.s.nfrag > 0 && xdx != nullptr)
+    long_row_xdx_kernel<<<(split_t->num_long + 3) / 4, 128, 0, stream>>>(split_t->long_rows, split_t->num_long, X, ldx, dX,
+                                                                         lddx, feat, row_begin, row_end, xdx);
   launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
   return check_launch("regnn_spmm_bwd_fused");
 }
 
 extern "C" int regnn_rowdot_norm_bwd(const float* norm, int norm_sides, const float* X, int64_t ldx,
                                      const float* Y, int64_t ldy, const float* Gd, int64_t ldg,
-                                     const float* dX, int64_t lddx, int64_t row_begin, int64_t row_end,
-                                     int feat, float* d_norm, void* stream) {
-  REGNN_REQUIRE(norm && X && Y && Gd && dX && d_norm, REGNN_ERR_INVALID_ARG, "rowdot_norm_bwd: null pointer");
+                                     const float* dX, int64_t lddx, const float* xdx, int64_t row_begin,
+                                     int64_t row_end, int feat, float* d_norm, void* stream) {
+  REGNN_REQUIRE(norm && Y && Gd && d_norm && (xdx || (X && dX)), REGNN_ERR_INVALID_ARG, "rowdot_norm_bwd: null pointer");
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0 && feat >= 1, REGNN_ERR_INVALID_ARG, "rowdot_norm_bwd: bad range / width");
   if (rows == 0) return REGNN_OK;
   rowdot_norm_kernel<<<(unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, 0,
-                       (cudaStream_t)stream>>>(norm, norm_sides & 3, X, ldx, Y, ldy, Gd, ldg, dX, lddx, feat, row_begin,
-                                               row_end, d_norm);
+                       (cudaStream_t)stream>>>(norm, norm_sides & 3, X, ldx, Y, ldy, Gd, ldg, dX, lddx, xdx, feat,
+                                               row_begin, row_end, d_norm);
   return check_launch("regnn_rowdot_norm_bwd");
 }
 

@@ -57,10 +57,11 @@ class _Propagate(torch.autograd.Function):
         need_x = ctx.needs_input_grad[2]
         need_theta = ctx.weighted and ctx.needs_input_grad[3]
         need_norm = ctx.has_norm and ctx.needs_input_grad[5]
-        dx = d_theta = d_norm = None
+        dx = d_theta = d_norm = xdx = None
         if need_theta and x.shape[1] <= ops.FUSED_BWD_MAX_FEAT:
-            # one gather pass over the transposed view: dX and the relation gradient together
-            dx, d_theta = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x, g, sides=ctx.sides)
+            # one gather pass over the transposed view: dX, the relation gradient and <X,dX> together
+            dx, d_theta, xdx = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x, g, sides=ctx.sides,
+                                                  want_xdx=need_norm and bool(ctx.sides & 1))
             d_theta = d_theta.view_as(theta)
         else:
             if need_x or need_norm or need_theta:
@@ -75,7 +76,7 @@ class _Propagate(torch.autograd.Function):
                                             split=csr.get('split'))
                 d_theta = d_theta.view_as(theta)
         if need_norm:
-            d_norm = ops.rowdot_norm_bwd(norm, x, y, g, dx, sides=ctx.sides)
+            d_norm = ops.rowdot_norm_bwd(norm, x, y, g, dx, sides=ctx.sides, xdx=xdx)
         return None, None, (dx if need_x else None), d_theta, None, (d_norm if need_norm else None), None
 
 

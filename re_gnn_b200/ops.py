@@ -108,8 +108,8 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3,
     return d_theta, d_norm
 
 
-def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None):
-    """One gather pass over the transposed view -> (dX[N,F], d_theta[R]).  See regnn_spmm_bwd_fused."""
+def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None, want_xdx=False):
+    """One gather pass over the transposed view -> (dX[N,F], d_theta[R], xdx[N] | None).  See regnn_spmm_bwd_fused."""
     x, g = _f32(x), _f32(g)
     theta = _f32(theta).view(-1)
     n = csr['indptr_t'].numel() - 1
@@ -122,18 +122,19 @@ def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=
     partials = torch.empty(_lib.partial_blocks(re - rb) * r, dtype=torch.float64, device=x.device)
     d_theta = torch.empty(r, dtype=torch.float32, device=x.device)
     sp, ws, extra = _split_args(csr.get('split_t'), f, x.device)
+    xdx = torch.zeros(n, dtype=torch.float32, device=x.device) if want_xdx else None
     with torch.cuda.device(x.device):
         _lib.call('regnn_spmm_bwd_fused', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(et_t), _ptr(theta),
                   float(alpha), r, _ptr(norm), int(sides), _ptr(x), x.stride(0), _ptr(g), g.stride(0), _ptr(out),
-                  out.stride(0), rb, re, f, _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _stream())
-        _lib.count_launches(2 + extra)
-    return out, d_theta
+                  out.stride(0), rb, re, f, _ptr(partials), _ptr(d_theta), _ptr(xdx), sp, _ptr(ws), _stream())
+        _lib.count_launches(2 + extra * (2 if want_xdx else 1))
+    return out, d_theta, xdx
 
 
 FUSED_BWD_MAX_FEAT = 512   # wider rows do not fit the shared-memory tile: two-pass backward instead
 
 
-def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3):
+def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3, xdx=None):
     """d_norm[v] = ([sides&2]<Y,G> + [sides&1]<X,dX>) / norm, rows outside the range are zero."""
     x, y, g, dx = _f32(x), _f32(y), _f32(g), _f32(dx)
     n = norm.numel()
@@ -142,7 +143,7 @@ def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3):
         torch.zeros(n, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.call('regnn_rowdot_norm_bwd', _ptr(norm), int(sides), _ptr(x), x.stride(0), _ptr(y), y.stride(0),
-                  _ptr(g), g.stride(0), _ptr(dx), dx.stride(0), rb, re, x.shape[1], _ptr(d_norm), _stream())
+                  _ptr(g), g.stride(0), _ptr(dx), dx.stride(0), _ptr(xdx), rb, re, x.shape[1], _ptr(d_norm), _stream())
         _lib.count_launches(1)
     return d_norm
 

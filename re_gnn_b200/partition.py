@@ -73,9 +73,9 @@ class _PartitionedPropagate(torch.autograd.Function):
         dx_full = torch.empty_like(x_full)
         # owner computes: the transposed rows [rb, re) are this rank's SOURCE rows; one fused gather pass gives
         # their dX and this rank's share of the relation gradient (each edge belongs to exactly one source row)
-        _, d_theta = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x_full, g_full, rows=(rb, re),
-                                        out=dx_full)
-        d_norm = ops.rowdot_norm_bwd(norm, x_full, y_full, g_full, dx_full, rows=(rb, re))
+        _, d_theta, xdx = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x_full, g_full, rows=(rb, re),
+                                             out=dx_full, want_xdx=True)
+        d_norm = ops.rowdot_norm_bwd(norm, x_full, y_full, g_full, dx_full, rows=(rb, re), xdx=xdx)
         # d_theta / d_norm hold this rank's rows only; the caller all-reduces the parameter gradient once.
         return None, None, dx_full[rb:re], d_theta.view_as(theta), None, d_norm, None, None, None
 

@@ -110,7 +110,7 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3,
     return d_theta, d_norm
 
 
-def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None):
+def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None, want_xdx=False):
     ns = norm if (norm is not None and sides & 2) else None
     nd = norm if (norm is not None and sides & 1) else None
     dx = spmm(csr['indptr_t'], csr['indices_t'], et_t, theta, alpha, ns, nd, g, rows=rows, out=out)
@@ -126,13 +126,21 @@ def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=
     if rows is not None:          # a rank owns the edges whose SOURCE row it owns
         dwe = torch.where((src >= rows[0]) & (src < rows[1]), dwe, torch.zeros_like(dwe))
     dw = torch.zeros_like(th).index_add(0, et_t.long(), dwe)
-    return dx, dw * alpha * _lgrad(th * alpha, SLOPE)
+    xdx = None
+    if want_xdx:
+        xdx = (x * dx.detach()).sum(1)
+        if rows is not None:
+            own = torch.zeros(xdx.numel(), dtype=torch.bool)
+            own[rows[0]:rows[1]] = True
+            xdx = torch.where(own, xdx, torch.zeros_like(xdx))
+    return dx, dw * alpha * _lgrad(th * alpha, SLOPE), xdx
 
 
-def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3):
+def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3, xdx=None):
     x, y, g, dx = x.detach(), y.detach(), g.detach(), dx.detach()
     n = norm.numel()
-    d = ((y * g).sum(1) * bool(sides & 2) + (x * dx).sum(1) * bool(sides & 1)) / norm.detach()
+    xd = xdx if xdx is not None else (x * dx).sum(1)
+    d = ((y * g).sum(1) * bool(sides & 2) + xd * bool(sides & 1)) / norm.detach()
     if rows is not None:
         own = torch.zeros(n, dtype=torch.bool)
         own[rows[0]:rows[1]] = True
