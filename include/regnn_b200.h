@@ -99,13 +99,20 @@ int regnn_etype_permute(const int64_t* etype_1based, const int32_t* eid, const i
  * theta: [R] (the [R,1] `edge_weight` parameter).  Row range [row_begin, row_end) lets a rank of a
  * destination-row partition compute only the rows it owns; deg/norm are indexed by global row id.
  */
-int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr, const float* theta,
+/* counts[v*R + r] = number of in-edges of v with (0-based) relation r: a parameter-independent [N,R] int32
+ * table built once per (graph, e_feat).  When passed to the two entry points below, the degree norm and its
+ * gradient become dense streaming passes over it (no per-edge work per training step). */
+int regnn_relation_counts(const int32_t* row, const uint8_t* etype_csr, int64_t num_edges, int64_t num_nodes,
+                          int num_relations, int32_t* counts, void* stream);
+
+int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr,
+                        const int32_t* counts /* optional: then indptr/etype_csr may be NULL */, const float* theta,
                         float alpha, int num_relations, float exponent, int64_t row_begin,
                         int64_t row_end, float* deg, float* norm, void* stream);
 /* Backward of the above: d_theta[r] += alpha * LeakyReLU'(alpha*theta[r]) *
  *   sum_{e: etype e = r} d_deg[dst e],   d_deg[v] = [deg[v] >= 1] * q * max(deg,1)^(q-1) * d_norm[v].
  * partials: double [regnn_max_partial_blocks() * R] scratch.  d_theta is OVERWRITTEN. */
-int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const float* theta,
+int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const int32_t* counts, const float* theta,
                         float alpha, int num_relations, float exponent, int64_t row_begin,
                         int64_t row_end, const float* deg, const float* d_norm, double* partials,
                         float* d_theta, void* stream);

@@ -368,12 +368,14 @@ spmm_stream_kernel(StreamArgs sa) {
       int row = cur;
       int row_end_slot = __shfl_sync(0xffffffffu, my_end, row);
       float nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
-      T acc[C], trow[C];   // trow: the row-level tile slice of the current row (BINS), kept in registers
+      // BINS: slots of a row come in runs of equal relation (edge ids are grouped by relation).  accr collects
+      // sum ns*G[dst] over the current run; at the end of a run  acc += w[r]*accr  and the lane-local bin of r gets
+      // nd*<X[u], accr>: one dot per RUN instead of one per edge, and the per-edge work equals the plain kernel's.
+      T acc[C], accr[C], trow[C];   // trow: the row-level tile slice of the current row, kept in registers
 #pragma unroll
-      for (int k = 0; k < C; ++k) acc[k] = trow[k] = V::zero();
+      for (int k = 0; k < C; ++k) acc[k] = accr[k] = trow[k] = V::zero();
       bool trow_valid = false;
-      int cur_rel = 0;      // run-length accumulation of the relation bins: one shared-memory update per run
-      float racc = 0.f;
+      int cur_rel = -1;
 
       auto load_trow = [&]() {
         const float* tp = mytile + (size_t)row * Fp + (size_t)lane * VW;
@@ -381,7 +383,23 @@ spmm_stream_kernel(StreamArgs sa) {
         for (int k = 0; k < C; ++k) trow[k] = col_ok[k] ? lds_vec<VW>(tp + (size_t)k * 32 * VW) : V::zero();
         trow_valid = true;
       };
+      auto end_run = [&]() {
+        if (cur_rel >= 0) {
+          if (!trow_valid) load_trow();
+          const float wr = a.etype != nullptr ? w_s[cur_rel] : 1.f;
+          float d = 0.f;
+#pragma unroll
+          for (int k = 0; k < C; ++k) {
+            d += V::dot(accr[k], trow[k]);
+            V::fma(acc[k], wr, accr[k]);
+            accr[k] = V::zero();
+          }
+          mybins[cur_rel * 32] += nd_cur * d;  // lane-local bin: fixed order, bank-conflict free
+          cur_rel = -1;
+        }
+      };
       auto flush = [&]() {
+        if (BINS) end_run();
         if (BINS && sa.xdx != nullptr && !is_frag) {  // <X[u], dX[u]> while dX[u] is still in registers
           if (!trow_valid) load_trow();
           float d = 0.f;
@@ -456,22 +474,19 @@ spmm_stream_kernel(StreamArgs sa) {
                 row_end_slot = __shfl_sync(0xffffffffu, my_end, row);
                 nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
               }
-              const float sc = __shfl_sync(0xffffffffu, coef, j + u);
-#pragma unroll
-              for (int k = 0; k < C; ++k) V::fma(acc[k], sc, x[u][k]);
               if (BINS) {
-                const float sb = __shfl_sync(0xffffffffu, ns, j + u) * nd_cur;
+                const float sb = __shfl_sync(0xffffffffu, ns, j + u);
                 const int se = __shfl_sync(0xffffffffu, et, j + u);
-                if (!trow_valid) load_trow();
-                float d = 0.f;
-#pragma unroll
-                for (int k = 0; k < C; ++k) d += V::dot(x[u][k], trow[k]);
-                if (se != cur_rel) {  // warp-uniform: lane-local bin, fixed order, bank-conflict free
-                  mybins[cur_rel * 32] += racc;
-                  racc = 0.f;
+                if (se != cur_rel) {  // warp-uniform
+                  end_run();
                   cur_rel = se;
                 }
-                racc = fmaf(sb, d, racc);
+#pragma unroll
+                for (int k = 0; k < C; ++k) V::fma(accr[k], sb, x[u][k]);
+              } else {
+                const float sc = __shfl_sync(0xffffffffu, coef, j + u);
+#pragma unroll
+                for (int k = 0; k < C; ++k) V::fma(acc[k], sc, x[u][k]);
               }
             }
           }
@@ -487,7 +502,6 @@ spmm_stream_kernel(StreamArgs sa) {
         ++row;
         if (row < seg_end) nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
       }
-      if (BINS) mybins[cur_rel * 32] += racc;
       cur = seg_end;
     }
     if (BINS && !tile_ready) {  // item without a single short-row slot: still consume the barrier phase
@@ -509,9 +523,19 @@ rowdot_norm_kernel(const float* __restrict__ norm, int sides, const float* __res
   const int64_t v = row_begin + (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (v >= row_end) return;
   float p = 0.f;
-  for (int c = lane; c < F; c += 32) {
-    if (sides & 2) p = fmaf(__ldg(Y + (size_t)v * ldy + c), __ldg(G + (size_t)v * ldg + c), p);
-    if ((sides & 1) && xdx == nullptr) p = fmaf(__ldg(X + (size_t)v * ldx + c), __ldg(dX + (size_t)v * lddx + c), p);
+  const bool use_x = (sides & 1) && xdx == nullptr;
+  const bool vec = (F & 3) == 0 && ((ldy | ldg) & 3) == 0 && ((((uintptr_t)Y) | ((uintptr_t)G)) & 15) == 0 &&
+                   (!use_x || (((ldx | lddx) & 3) == 0 && ((((uintptr_t)X) | ((uintptr_t)dX)) & 15) == 0));
+  if (vec) {
+    for (int c = lane * 4; c < F; c += 128) {
+      if (sides & 2) p += dot4(ldg4(Y + (size_t)v * ldy + c), ldg4(G + (size_t)v * ldg + c));
+      if (use_x) p += dot4(ldg4(X + (size_t)v * ldx + c), ldg4(dX + (size_t)v * lddx + c));
+    }
+  } else {
+    for (int c = lane; c < F; c += 32) {
+      if (sides & 2) p = fmaf(__ldg(Y + (size_t)v * ldy + c), __ldg(G + (size_t)v * ldg + c), p);
+      if (use_x) p = fmaf(__ldg(X + (size_t)v * ldx + c), __ldg(dX + (size_t)v * lddx + c), p);
+    }
   }
   p = group_sum<32>(p);
   if ((sides & 1) && xdx != nullptr) p += xdx[v];
@@ -833,6 +857,54 @@ wdeg_norm_bwd_slot_kernel(const int32_t* __restrict__ indptr, const uint8_t* __r
   reduce_bins(bins, scratch, R, partials + (size_t)blockIdx.x * R);
 }
 
+// ---- count-based variants of the two norm kernels ----------------------------------------------------
+// cnt[v][r] = number of in-edges of v with relation r is a property of the graph, not of the parameters:
+// it is built once per (graph, e_feat) by relation_count_kernel (integer atomics: exact, order-free).
+// Then deg[v] = sum_r cnt[v][r]*w[r] and d w[r] = sum_v d_deg[v]*cnt[v][r] are dense streaming passes over
+// an [N,R] int32 matrix -- no per-edge work and no sensitivity to hub rows on the per-step path.
+__global__ void relation_count_kernel(const int32_t* __restrict__ row, const uint8_t* __restrict__ etype,
+                                      int64_t num_edges, int R, int32_t* __restrict__ cnt) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < num_edges) atomicAdd(&cnt[(size_t)row[s] * R + etype[s]], 1);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+wdeg_norm_fwd_cnt_kernel(const int32_t* __restrict__ cnt, const float* __restrict__ theta, float alpha, int R,
+                         float exponent, int64_t row_begin, int64_t row_end, float* __restrict__ deg,
+                         float* __restrict__ norm) {
+  __shared__ float w_s[256];
+  for (int i = threadIdx.x; i < R; i += blockDim.x) w_s[i] = leaky(theta[i] * alpha, kRelationSlope);
+  __syncthreads();
+  const int64_t v = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= row_end) return;
+  const int32_t* c = cnt + (size_t)v * R;
+  float d = 0.f;
+  for (int r = 0; r < R; ++r) d = fmaf((float)__ldg(c + r), w_s[r], d);
+  if (deg != nullptr) deg[v] = d;
+  norm[v] = norm_from_deg(d, exponent);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+wdeg_norm_bwd_cnt_kernel(const int32_t* __restrict__ cnt, int R, float exponent, int64_t row_begin,
+                         int64_t row_end, const float* __restrict__ deg, const float* __restrict__ d_norm,
+                         double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* scratch = reinterpret_cast<double*>(smem_raw);
+  float* bins = reinterpret_cast<float*>(scratch + kWarpsPerBlock * R);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* mybins = bins + (size_t)warp * R * 32 + lane;
+  for (int r = 0; r < R; ++r) mybins[r * 32] = 0.f;
+  for (int64_t v = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < row_end;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const float d = deg[v];
+    // clamp(min=1) passes the gradient at deg == 1 (PyTorch semantics)
+    const float dd = d >= 1.f ? exponent * powf(fmaxf(d, 1.f), exponent - 1.f) * d_norm[v] : 0.f;
+    const int32_t* c = cnt + (size_t)v * R;
+    for (int r = 0; r < R; ++r) mybins[r * 32] = fmaf(dd, (float)__ldg(c + r), mybins[r * 32]);
+  }
+  reduce_bins(bins, scratch, R, partials + (size_t)blockIdx.x * R);
+}
+
 // ---- dispatch ---------------------------------------------------------------------------------------
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
@@ -883,18 +955,33 @@ static bool pick_shape(int F, bool vec_ok, Shape* s) {
 
 using namespace regnn;
 
-extern "C" int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr,
+extern "C" int regnn_relation_counts(const int32_t* row, const uint8_t* etype_csr, int64_t num_edges,
+                                     int64_t num_nodes, int num_relations, int32_t* counts, void* stream) {
+  REGNN_REQUIRE(counts && (num_edges == 0 || (row && etype_csr)), REGNN_ERR_INVALID_ARG, "relation_counts: null pointer");
+  REGNN_REQUIRE(num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS, REGNN_ERR_UNSUPPORTED_SHAPE,
+                "num_relations=%d outside [1,%d]", num_relations, REGNN_MAX_RELATIONS);
+  cudaMemsetAsync(counts, 0, (size_t)num_nodes * num_relations * sizeof(int32_t), (cudaStream_t)stream);
+  if (num_edges > 0)
+    relation_count_kernel<<<(unsigned)((num_edges + 255) / 256), 256, 0, (cudaStream_t)stream>>>(row, etype_csr, num_edges,
+                                                                                               num_relations, counts);
+  return check_launch("regnn_relation_counts");
+}
+
+extern "C" int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr, const int32_t* counts,
                                    const float* theta, float alpha, int num_relations,
                                    float exponent, int64_t row_begin, int64_t row_end, float* deg,
                                    float* norm, void* stream) {
-  REGNN_REQUIRE(indptr && etype_csr && theta && norm, REGNN_ERR_INVALID_ARG, "wdeg_norm_fwd: null pointer");
+  REGNN_REQUIRE(theta && norm && (counts || (indptr && etype_csr)), REGNN_ERR_INVALID_ARG, "wdeg_norm_fwd: null pointer");
   REGNN_REQUIRE(num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS, REGNN_ERR_UNSUPPORTED_SHAPE,
                 "num_relations=%d outside [1,%d]", num_relations, REGNN_MAX_RELATIONS);
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "wdeg_norm_fwd: empty/negative row range");
   if (rows == 0) return REGNN_OK;
   const int threads = kWarpsPerBlock * 32;
-  if (num_relations <= 32) {
+  if (counts != nullptr) {
+    wdeg_norm_fwd_cnt_kernel<<<(unsigned)((rows + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        counts, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
+  } else if (num_relations <= 32) {
     const int64_t blocks = (rows + kWarpsPerBlock * kWdegRows - 1) / (kWarpsPerBlock * kWdegRows);
     wdeg_norm_fwd_slot_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
         indptr, etype_csr, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
@@ -908,13 +995,13 @@ extern "C" int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_c
 
 static size_t bins_smem_bytes(int R) { return (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float)); }
 
-extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr,
+extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const int32_t* counts,
                                    const float* theta, float alpha, int num_relations,
                                    float exponent, int64_t row_begin, int64_t row_end,
                                    const float* deg, const float* d_norm, double* partials,
                                    float* d_theta, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && etype_csr && theta && deg && d_norm && partials && d_theta,
+  REGNN_REQUIRE((counts || (indptr && etype_csr)) && theta && deg && d_norm && partials && d_theta,
                 REGNN_ERR_INVALID_ARG, "wdeg_norm_bwd: null pointer");
   const int R = num_relations;
   REGNN_REQUIRE(R >= 1 && R <= 200, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,200]", R);
@@ -924,7 +1011,10 @@ extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_c
   const size_t smem = bins_smem_bytes(R);
   int rc = set_smem(wdeg_norm_bwd_kernel, smem);
   if (rc != REGNN_OK) return rc;
-  if (R <= 32)
+  if (counts != nullptr)
+    wdeg_norm_bwd_cnt_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(counts, R, exponent, row_begin, row_end, deg,
+                                                                         d_norm, partials);
+  else if (R <= 32)
     wdeg_norm_bwd_slot_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent, row_begin,
                                                                           row_end, deg, d_norm, partials);
   else
@@ -978,6 +1068,16 @@ static int common_align(std::initializer_list<const void*> ptrs, std::initialize
   REGNN_STREAM_CASE(4, 2, BINS_, CALL) REGNN_STREAM_CASE(8, 2, BINS_, CALL)                          \
   REGNN_STREAM_CASE(1, 1, BINS_, CALL) REGNN_STREAM_CASE(2, 1, BINS_, CALL) REGNN_STREAM_CASE(3, 1, BINS_, CALL) \
   REGNN_STREAM_CASE(4, 1, BINS_, CALL) REGNN_STREAM_CASE(8, 1, BINS_, CALL)
+
+template <typename K>
+static int resident_blocks(K kernel, size_t smem) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  return min(sms * per_sm, kMaxPartialBlocks);
+}
 
 static int fill_split(SpmmArgs& a, const regnn_rowsplit_t* split, float* ws, const char* who) {
   a.frag_row = a.frag_begin = nullptr;
@@ -1063,9 +1163,11 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
   const int Fp = (feat + 3) & ~3;
   const size_t smem = 64 + (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float)) +
                       (size_t)kWarpsPerBlock * kRowsPerItemBins * Fp * sizeof(float);
-  const int nb = partial_blocks(rows / kRowsPerItemBins + sa.s.nfrag + 1);
+  int nb = partial_blocks(rows / kRowsPerItemBins + sa.s.nfrag + 1);
   bool launched = false;
+  // persistent kernel: exactly one resident wave (148 SMs x blocks per SM), never more than the partial slots
   REGNN_STREAM_DISPATCH(true, (rc = set_smem(spmm_stream_kernel<C, VW, BINS>, smem),
+                               nb = min(nb, resident_blocks(spmm_stream_kernel<C, VW, BINS>, smem)),
                                spmm_stream_kernel<C, VW, BINS><<<nb, kWarpsPerBlock * 32, smem, stream>>>(sa)))
   if (rc != REGNN_OK) return rc;
   REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_fused: no kernel for C=%d VW=%d", sh.C, sh.VW);

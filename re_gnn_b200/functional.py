@@ -15,7 +15,7 @@ class _WDegNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, graph, etv, theta, alpha, exponent):
         csr = graph.csr()
-        deg, norm = ops.wdeg_norm_fwd(csr, etv[0], theta, alpha, exponent)
+        deg, norm = ops.wdeg_norm_fwd(csr, etv[0], theta, alpha, exponent, counts=etv[2] if len(etv) > 2 else None)
         ctx.graph, ctx.etv, ctx.alpha, ctx.exponent = graph, etv, alpha, exponent
         ctx.save_for_backward(theta, deg)
         return norm
@@ -24,7 +24,7 @@ class _WDegNorm(torch.autograd.Function):
     def backward(ctx, d_norm):
         theta, deg = ctx.saved_tensors
         d_theta = ops.wdeg_norm_bwd(ctx.graph.csr(), ctx.etv[0], theta, ctx.alpha, ctx.exponent, deg,
-                                    d_norm.contiguous())
+                                    d_norm.contiguous(), counts=ctx.etv[2] if len(ctx.etv) > 2 else None)
         return None, None, d_theta.view_as(theta), None, None
 
 

@@ -35,6 +35,7 @@ def _stream():
 
 
 SPLIT_THRESHOLD = 256   # rows with more slots are cut into fragments of this many slots
+COUNTS_MAX_BYTES = 4 << 30   # build the [N,R] relation-count table only while it stays below this size
 
 
 def _row_split(indptr, threshold):
@@ -180,7 +181,13 @@ class Graph:
             scratch = torch.zeros(1, dtype=torch.int32, device=dev)
             _lib.call('regnn_etype_permute', _ptr(et), _ptr(csr['eid']), _ptr(csr['slot_t']), e,
                       int(num_relations), _ptr(et_csr), _ptr(et_t), _ptr(scratch), _stream())
+            # per-(row, relation) in-edge counts: turns the degree norm into a dense [N,R] pass (when it fits)
+            counts = None
+            if self._n * int(num_relations) * 4 <= COUNTS_MAX_BYTES:
+                counts = torch.empty(max(self._n * int(num_relations), 1), dtype=torch.int32, device=dev)
+                _lib.call('regnn_relation_counts', _ptr(csr['row']), _ptr(et_csr), e, self._n, int(num_relations),
+                          _ptr(counts), _stream())
         if len(self._etype_cache) > 8:
             self._etype_cache.clear()
-        self._etype_cache[key] = (et_csr, et_t)
-        return et_csr, et_t
+        self._etype_cache[key] = (et_csr, et_t, counts)
+        return self._etype_cache[key]

@@ -44,17 +44,17 @@ def graph_etype_views(self, e_feat, num_relations):
     if et.size and (et.min() < 1 or et.max() > num_relations):
         raise RuntimeError('edge type outside [1, %d]' % num_relations)
     a, b = csr_oracle.etype_permute(et, c['eid'].numpy(), c['slot_t'].numpy())
-    return torch.as_tensor(a), torch.as_tensor(b)
+    return torch.as_tensor(a), torch.as_tensor(b), None
 
 
-def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None):
+def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None, counts=None):
     w = _w(theta.detach().view(-1), alpha)
     n = csr['indptr'].numel() - 1
     deg = torch.zeros(n, dtype=w.dtype).index_add(0, csr['row'].long(), w[et_csr.long()])
     return deg, deg.clamp(min=1) ** exponent
 
 
-def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None):
+def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None, counts=None):
     th = theta.detach().view(-1)
     dd = torch.where(deg >= 1, exponent * deg.clamp(min=1) ** (exponent - 1) * d_norm, torch.zeros_like(deg))
     dw = torch.zeros_like(th).index_add(0, et_csr.long(), dd[csr['row'].long()])

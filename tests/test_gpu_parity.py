@@ -63,7 +63,10 @@ def test_csr_build_bit_exact(n, e, seed):
     if e:
         r = 9
         et = rng.randint(1, r + 1, size=e).astype(np.int64)
-        a, b = g.etype_views(torch.as_tensor(et), r)
+        a, b, cnt = g.etype_views(torch.as_tensor(et), r)
+        want_cnt = np.zeros((n, r), dtype=np.int32)
+        np.add.at(want_cnt, (dst, et - 1), 1)
+        assert np.array_equal(cnt.cpu().numpy().reshape(n, r), want_cnt)
         wa, wb = csr_oracle.etype_permute(et, want['eid'], want['slot_t'])
         assert np.array_equal(a.cpu().numpy(), wa) and np.array_equal(b.cpu().numpy(), wb)
 
@@ -76,7 +79,7 @@ def test_csr_build_named_shapes_bit_exact():
         got = {k: g.csr()[k].cpu().numpy() for k in want}
         for k in want:
             assert np.array_equal(got[k], want[k]), (name, k)
-        a, b = g.etype_views(torch.as_tensor(d['etype']), d['num_relations'])
+        a, b, _ = g.etype_views(torch.as_tensor(d['etype']), d['num_relations'])
         wa, wb = csr_oracle.etype_permute(d['etype'], want['eid'], want['slot_t'])
         assert np.array_equal(a.cpu().numpy(), wa) and np.array_equal(b.cpu().numpy(), wb)
 
