@@ -368,14 +368,12 @@ spmm_stream_kernel(StreamArgs sa) {
       int row = cur;
       int row_end_slot = __shfl_sync(0xffffffffu, my_end, row);
       float nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
-      // BINS: slots of a row come in runs of equal relation (edge ids are grouped by relation).  accr collects
-      // sum ns*G[dst] over the current run; at the end of a run  acc += w[r]*accr  and the lane-local bin of r gets
-      // nd*<X[u], accr>: one dot per RUN instead of one per edge, and the per-edge work equals the plain kernel's.
-      T acc[C], accr[C], trow[C];   // trow: the row-level tile slice of the current row, kept in registers
+      T acc[C], trow[C];   // trow: the row-level tile slice of the current row (BINS), kept in registers
 #pragma unroll
-      for (int k = 0; k < C; ++k) acc[k] = accr[k] = trow[k] = V::zero();
+      for (int k = 0; k < C; ++k) acc[k] = trow[k] = V::zero();
       bool trow_valid = false;
-      int cur_rel = -1;
+      int cur_rel = 0;      // run-length accumulation of the relation bins: one shared-memory update per run
+      float racc = 0.f;
 
       auto load_trow = [&]() {
         const float* tp = mytile + (size_t)row * Fp + (size_t)lane * VW;
@@ -383,23 +381,7 @@ spmm_stream_kernel(StreamArgs sa) {
         for (int k = 0; k < C; ++k) trow[k] = col_ok[k] ? lds_vec<VW>(tp + (size_t)k * 32 * VW) : V::zero();
         trow_valid = true;
       };
-      auto end_run = [&]() {
-        if (cur_rel >= 0) {
-          if (!trow_valid) load_trow();
-          const float wr = a.etype != nullptr ? w_s[cur_rel] : 1.f;
-          float d = 0.f;
-#pragma unroll
-          for (int k = 0; k < C; ++k) {
-            d += V::dot(accr[k], trow[k]);
-            V::fma(acc[k], wr, accr[k]);
-            accr[k] = V::zero();
-          }
-          mybins[cur_rel * 32] += nd_cur * d;  // lane-local bin: fixed order, bank-conflict free
-          cur_rel = -1;
-        }
-      };
       auto flush = [&]() {
-        if (BINS) end_run();
         if (BINS && sa.xdx != nullptr && !is_frag) {  // <X[u], dX[u]> while dX[u] is still in registers
           if (!trow_valid) load_trow();
           float d = 0.f;
@@ -474,19 +456,22 @@ spmm_stream_kernel(StreamArgs sa) {
                 row_end_slot = __shfl_sync(0xffffffffu, my_end, row);
                 nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
               }
+              const float sc = __shfl_sync(0xffffffffu, coef, j + u);
+#pragma unroll
+              for (int k = 0; k < C; ++k) V::fma(acc[k], sc, x[u][k]);
               if (BINS) {
-                const float sb = __shfl_sync(0xffffffffu, ns, j + u);
+                const float sb = __shfl_sync(0xffffffffu, ns, j + u) * nd_cur;
                 const int se = __shfl_sync(0xffffffffu, et, j + u);
-                if (se != cur_rel) {  // warp-uniform
-                  end_run();
+                if (!trow_valid) load_trow();
+                float d = 0.f;
+#pragma unroll
+                for (int k = 0; k < C; ++k) d += V::dot(x[u][k], trow[k]);
+                if (se != cur_rel) {  // warp-uniform: lane-local bin, fixed order, bank-conflict free
+                  mybins[cur_rel * 32] += racc;
+                  racc = 0.f;
                   cur_rel = se;
                 }
-#pragma unroll
-                for (int k = 0; k < C; ++k) V::fma(accr[k], sb, x[u][k]);
-              } else {
-                const float sc = __shfl_sync(0xffffffffu, coef, j + u);
-#pragma unroll
-                for (int k = 0; k < C; ++k) V::fma(acc[k], sc, x[u][k]);
+                racc = fmaf(sb, d, racc);
               }
             }
           }
@@ -502,6 +487,7 @@ spmm_stream_kernel(StreamArgs sa) {
         ++row;
         if (row < seg_end) nd_cur = __shfl_sync(0xffffffffu, my_nd, row);
       }
+      if (BINS) mybins[cur_rel * 32] += racc;
       cur = seg_end;
     }
     if (BINS && !tile_ready) {  // item without a single short-row slot: still consume the barrier phase
