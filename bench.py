@@ -35,7 +35,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='mag_regcn', choices=['mag_regcn'])
+    ap.add_argument('--workload', default='mag_regcn', choices=['mag_regcn', 'mag_ns'])
     ap.add_argument('--feat', type=int, default=FEAT)
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
     ap.add_argument('--no-others', action='store_true', help='skip the secondary HGB-shaped workloads')
@@ -369,6 +369,90 @@ def run_ours(args, d):
         dist.destroy_process_group()
 
 
+def run_ns(args, d):
+    """BASELINE config 5: neighbour-sampled minibatch training of the MAG-stack RE-GCN (batch 512 seeds per rank,
+    fan-out [25, 20], 2 layers, hidden 512, 349 classes; mag/regnn_ns.py:41-51,200-208), data-parallel with one
+    gradient all-reduce per step.  Weak scaling: every rank draws its own batches.  value = sampled edges / s."""
+    import torch.distributed as dist
+    from re_gnn_b200 import Graph, _lib, mag
+    from re_gnn_b200.sampling import NeighborSampler
+    world, rank, local = (int(os.environ.get(k, '0' if k != 'WORLD_SIZE' else '1')) for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    sync = torch.cuda.synchronize
+    barrier = (lambda: dist.barrier()) if world > 1 else None
+    n, net, sizes = d['num_nodes'], d['num_etype'], d['type_sizes']
+    nnt = len(sizes)
+    g = Graph(d['src'][:-n], d['dst'][:-n], n).to(dev)        # MAG stack: no stored self loops (self_loop_type 2 adds them)
+    g.csr()
+    edge_type0 = (torch.as_tensor(d['etype'][:-n]) - 1).to(dev)
+    node_type = torch.as_tensor(d['ntype']).to(dev)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    local_idx = torch.as_tensor(np.arange(n) - offs[d['ntype']]).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    x_dict = {k: torch.randn(sizes[k], 128, device=dev, generator=gen) for k in range(nnt)}
+    labels = torch.randint(0, 349, (n,), device=dev, generator=gen)
+    torch.manual_seed(123)
+    model = mag.REGNN(128, 512, 349, 1, 2, ALPHA, 0.5, {k: 128 for k in range(nnt)}, net, residual=True, no_re=False,
+                      self_loop_type=2).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sampler = NeighborSampler(g, [25, 20], seed=123, rank=rank)
+    batch_size, n_train = 512, int(sizes[0] * 0.855)          # 629,571 of 736,389 papers are training nodes in ogbn-mag
+    perm = torch.randperm(n_train, generator=torch.Generator().manual_seed(1000 + rank))
+    seeds_h = perm[:batch_size * 64].view(64, batch_size).pin_memory()
+    loss_h = torch.empty(1).pin_memory()
+    state = {'i': 0, 'edges': 0}
+
+    def step():
+        i = state['i']
+        seeds = seeds_h[i % 64].to(dev, non_blocking=True)     # the step's input comes from pinned host memory
+        loss, ne = mag.train_step(model, opt, sampler, seeds, labels[seeds], x_dict, edge_type0, node_type, local_idx,
+                                  epoch=0, batch=i, world_size=world)
+        loss_h.copy_(loss.view(1), non_blocking=True)          # the step's result goes back to the host
+        state['i'] += 1
+        state['edges'] += ne
+
+    sampler_clk = ClockSampler(local)
+    sampler_clk.start()
+    l0 = _lib.launch_count
+    for _ in range(args.warmup):
+        step()
+    state['edges'] = 0
+    total = timed(step, args.steps, 0, sync, barrier)
+    clocks = sampler_clk.stop()
+    launches = (_lib.launch_count - l0) * args.steps // (args.steps + args.warmup)
+    edges = torch.tensor([float(state['edges']), total], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = edges[1:].clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        esum = edges[:1].clone()
+        dist.all_reduce(esum, op=dist.ReduceOp.SUM)
+        total, all_edges = float(tmax.item()), float(esum.item())
+    else:
+        all_edges = float(state['edges'])
+    if rank == 0:
+        val = all_edges / total / 1e9
+        n_params = sum(p.numel() for p in model.parameters())
+        line = {'metric': 'GTEPS (sampled edges) per neighbour-sampled train step, data-parallel', 'value': val,
+                'unit': 'GTEPS', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': total / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'RE-GCN (MAG stack) neighbour-sampled minibatch training, BASELINE config 5',
+                           'batch_size_per_rank': batch_size, 'fanout': [25, 20], 'hidden': 512, 'classes': 349,
+                           'params': n_params, 'sampled_edges_per_step': all_edges / args.steps,
+                           'l2': 'every step touches a new random batch; feature tables (993 MB) exceed L2'},
+                'clocks': clocks,
+                'e2e': {'value': val, 'unit': 'GTEPS', 'h2d_bytes_per_step': batch_size * 8, 'd2h_bytes_per_step': 4,
+                        'note': 'the timed step already starts from pinned-host seed ids and ends with the loss on the host'},
+                'gpu_launches': int(launches), 'steps_per_s': args.steps / total * world}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', '0'))
@@ -378,6 +462,8 @@ def main():
     d = synth.hetero_graph('mag', scale=args.scale)
     if args.impl == 'reference':
         run_reference(args, d)
+    elif args.workload == 'mag_ns':
+        run_ns(args, d)
     else:
         run_ours(args, d)
 

@@ -250,6 +250,16 @@ int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const
                         int head_dim, int64_t row_begin, int64_t row_end, float* d_fs, const regnn_rowsplit_t* split_t /* of the transposed view */,
     float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Neighbour sampling for the sampled-minibatch path (replaces torch_sparse's CPU `sample_adj` behind
+ * `NeighborSampler(edge_index, sizes=[25, 20], ...)`, mag/regnn_ns.py:206-214).  For target i the kernel
+ * writes up to `fanout` distinct CSR slots of its in-edges to out_slot[i*fanout + j] (-1 = none): all
+ * in-edges if the in-degree is <= fanout, else a keyed pseudo-random subset without replacement
+ * (4-round Feistel permutation with cycle walking; oracle/sampler_oracle.py is the bit-exact spec).
+ * Counter-based: `key` = f(seed, epoch, rank, batch, layer); no RNG state. */
+int regnn_sample_neighbors(const int32_t* indptr, const int64_t* targets, int64_t num_targets, int fanout,
+                           uint64_t key, int32_t* out_slot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

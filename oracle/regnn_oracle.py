@@ -202,3 +202,26 @@ def regcn_model_forward(src, dst, etype, num_nodes, features_list, params, alpha
                                 lp.get('weight'), lp.get('bias'), act)
     w, b = params['out']
     return h @ w.t() + b, h
+
+
+# ------------------------------------------------------------------------------------------------
+# MAG stack (PyG API).  PyG / torch_scatter cannot be installed here, so this restatement of
+# mag/regnn_layers.py is "parity unpinned" (no reference run to compare with).
+def mag_regcn_forward(x_src, x_target, edge_index, edge_type, target_node_type, weight, bias, relation_weight,
+                      scaling_factor, num_edge_types, self_loop_type=2, residual=False):
+    """mag/regnn_layers.py:80-150 (``REGCNConv.forward``; ``aggr='mean'``, bias added in ``update``)."""
+    src, dst = edge_index[0], edge_index[1]
+    n_dst = x_target.shape[0]
+    if self_loop_type == 2:                                                       # :90-96
+        loop = torch.arange(n_dst, dtype=src.dtype)
+        src, dst = torch.cat([src, loop]), torch.cat([dst, loop])
+        edge_type = torch.cat([edge_type, target_node_type + num_edge_types])
+    xs = x_src @ weight                                                           # :102
+    w = F.leaky_relu(relation_weight * scaling_factor, RELATION_SLOPE)[edge_type]  # :110-113
+    msg = w.view(-1, 1) * xs[src]                                                 # message(): ew * x_j, ew = edge_weight (:129)
+    out = torch.zeros((n_dst, xs.shape[1]), dtype=xs.dtype).index_add(0, dst, msg)
+    cnt = torch.zeros(n_dst, dtype=xs.dtype).index_add(0, dst, torch.ones(dst.numel(), dtype=xs.dtype))
+    out = out / cnt.clamp(min=1).view(-1, 1) + bias                               # aggr='mean', update(): + bias
+    if residual:
+        out = out + x_target @ weight                                             # weight_root aliases weight (:50)
+    return out

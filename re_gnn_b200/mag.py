@@ -1,0 +1,137 @@
+"""MAG-stack (PyG-API) RE-GCN layer and model on the fused CUDA operators -- the sampled-minibatch path of
+BASELINE config 5 ("next" row f-1 of SURVEY.md section 8).
+
+Mirrors, for ``--model regcn``, the constructor arguments, parameter names and forward conventions of
+``REGCNConv`` (mag/regnn_layers.py:24-150) and ``REGNN`` (mag/regnn_ns.py:216-346): bipartite
+``(x_src, x_target)`` inputs with the targets first, ``edge_index`` [2,E] of local ids, 0-based ``edge_type``,
+``self_loop_type == 2`` appending one typed self loop per target, ``aggr='mean'`` over the UN-normalised
+relation weights (the ``ew`` the reference computes is returned but never used for aggregation, :119-129).
+PyG / torch_scatter are not involved: the aggregation is ``regnn_spmm_fwd`` on a per-block CSR.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import functional as RF
+from .graph import Graph
+
+
+class REGCNConv(nn.Module):
+    def __init__(self, in_channels, out_channels, num_node_types, num_edge_types, scaling_factor=100., dropout=0.,
+                 use_softmax=False, residual=False, use_norm=None, self_loop_type=1, no_re=False):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_node_types, self.num_edge_types = num_node_types, num_edge_types
+        self.use_softmax, self.dropout, self.residual = use_softmax, dropout, residual
+        self.use_norm, self.self_loop_type, self.scaling_factor = use_norm, self_loop_type, scaling_factor
+        self.weight = nn.Parameter(torch.empty(in_channels, out_channels))
+        if residual:
+            self.weight_root = self.weight   # the reference aliases the two (:50)
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        rw_dim = num_edge_types if self_loop_type in (1, 3) else num_edge_types + num_node_types
+        self.relation_weight = nn.Parameter(torch.empty(rw_dim), requires_grad=not no_re)
+        if use_norm == 'bn':
+            self.norm = nn.BatchNorm1d(out_channels)
+        elif use_norm == 'ln':
+            self.norm = nn.LayerNorm(out_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.weight)
+        nn.init.zeros_(self.bias)
+        nn.init.constant_(self.relation_weight, 1.0 / self.scaling_factor)
+        if self.use_norm in ('bn', 'ln'):
+            self.norm.reset_parameters()
+
+    def forward(self, x, edge_index, edge_type, target_node_type, return_weights=False):
+        x_src, x_target = x
+        n_src, n_dst = x_src.shape[0], x_target.shape[0]
+        src, dst = edge_index[0], edge_index[1]
+        if self.self_loop_type == 2:   # one typed self loop per target node (:90-96)
+            loop = torch.arange(n_dst, dtype=src.dtype, device=src.device)
+            src, dst = torch.cat([src, loop]), torch.cat([dst, loop])
+            edge_type = torch.cat([edge_type, target_node_type + self.num_edge_types])
+        graph = Graph(src, dst, n_src)
+        etv = graph.etype_views(edge_type + 1, self.relation_weight.numel())
+        xs = x_src @ self.weight
+        # aggr='mean': divide by the NUMBER of in-edges (incl. the appended loops); rows without edges give 0
+        inv_cnt = 1.0 / graph.in_degrees().clamp(min=1).to(xs.dtype)
+        out = RF.propagate(graph, etv, xs, self.relation_weight.view(-1, 1), self.scaling_factor, inv_cnt, sides=2)
+        out = out[:n_dst] + self.bias
+        if self.residual:
+            out = out + x_target @ self.weight_root
+        if self.use_norm in ('bn', 'ln'):
+            out = self.norm(out)
+        if return_weights:
+            w = F.leaky_relu(self.relation_weight * self.scaling_factor)
+            return out, None, w
+        return out
+
+
+class REGNN(nn.Module):
+    """mag/regnn_ns.py:216-346 with ``args.model == 'regcn'`` and per-type feature projections
+    (``args.feats_type != 2``); the module-level ``args`` the reference reads become constructor keywords."""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, heads, num_layers, scaling_factor, dropout,
+                 num_feature_dict, num_edge_types, residual, no_re, use_norm=None, self_loop_type=2):
+        super().__init__()
+        self.in_channels, self.hidden_channels, self.out_channels = in_channels, hidden_channels, out_channels
+        self.heads, self.num_layers, self.dropout = heads, num_layers, dropout
+        self.residual, self.use_norm = residual, use_norm
+        self.num_node_types, self.num_edge_types = len(num_feature_dict), num_edge_types
+        self.hidden_dim = hidden_channels
+        self.lins = nn.ModuleDict({str(k): nn.Linear(d, self.hidden_dim) for k, d in num_feature_dict.items()})
+        self.convs = nn.ModuleList([
+            REGCNConv(hidden_channels, hidden_channels, self.num_node_types, num_edge_types, scaling_factor,
+                      dropout=dropout, residual=residual, use_norm=use_norm, self_loop_type=self_loop_type, no_re=no_re)
+            for _ in range(num_layers)])
+        self.out_lin = nn.Linear(self.hidden_dim, out_channels)
+
+    def group_input(self, x_dict, node_type, local_node_idx, n_id=None):
+        if n_id is not None:
+            node_type, local_node_idx = node_type[n_id], local_node_idx[n_id]
+        h = torch.zeros((node_type.size(0), self.hidden_dim), device=node_type.device)
+        for key, x in x_dict.items():
+            mask = node_type == key
+            h[mask] = self.lins[str(key)](x[local_node_idx[mask]])
+        return h
+
+    def forward(self, n_id, x_dict, adjs, edge_type, node_type, local_node_idx):
+        x = self.group_input(x_dict, node_type, local_node_idx, n_id)
+        node_type = node_type[n_id]
+        for i, (edge_index, e_id, size) in enumerate(adjs):
+            x_target, node_type = x[:size[1]], node_type[:size[1]]
+            x = self.convs[i]((x, x_target), edge_index, edge_type[e_id], node_type)
+            x = F.dropout(F.relu(x), p=self.dropout, training=self.training)
+        return self.out_lin(x).log_softmax(dim=-1)
+
+
+def allreduce_gradients(params, world_size, group=None):
+    """Data-parallel gradient averaging: ONE all-reduce of the flattened gradients per step."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or world_size == 1:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= world_size
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return flat.numel()
+
+
+def train_step(model, optimizer, sampler, seeds, labels, x_dict, edge_type, node_type, local_node_idx, epoch, batch,
+               world_size=1):
+    """One sampled-minibatch training step (mag/regnn_ns.py:399-407 + gradient all-reduce).
+    Returns (loss tensor, number of sampled edges)."""
+    n_id, blocks = sampler.sample(seeds, epoch=epoch, batch=batch)
+    adjs = [(b.edge_index, b.eid, b.size) for b in blocks]
+    optimizer.zero_grad(set_to_none=True)
+    out = model(n_id, x_dict, adjs, edge_type, node_type, local_node_idx)
+    loss = F.nll_loss(out, labels)
+    loss.backward()
+    allreduce_gradients(list(model.parameters()), world_size)
+    optimizer.step()
+    return loss.detach(), sum(int(b.src.numel()) for b in blocks)

@@ -268,8 +268,14 @@ def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
     return torch.zeros_like(fs).index_add(0, src, msg)
 
 
+def sampler_sample_slots(self, targets, fanout, key):
+    from oracle import sampler_oracle
+    return torch.as_tensor(sampler_oracle.sample_slots(self.graph.csr()['indptr'].numpy(), targets.numpy(), fanout, key))
+
+
 def install(monkeypatch):
-    from re_gnn_b200 import graph as G, ops
+    from re_gnn_b200 import graph as G, ops, sampling
+    monkeypatch.setattr(sampling.NeighborSampler, 'sample_slots', sampler_sample_slots)
     monkeypatch.setattr(G.Graph, 'csr', graph_csr)
     monkeypatch.setattr(G.Graph, 'etype_views', graph_etype_views)
     for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'spmm_bwd_fused', 'rowdot_norm_bwd', 'gat_fwd', 'gat_bwd_dst',

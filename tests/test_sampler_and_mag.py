@@ -1,0 +1,61 @@
+"""Sampled-minibatch path: oracle self-checks and the MAG-stack layer through the CPU shim (no GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import csr_oracle, regnn_oracle as O, sampler_oracle as S
+from re_gnn_b200 import synth
+
+
+def test_feistel_is_a_permutation_and_deterministic():
+    for deg in (2, 3, 5, 64, 65, 1000, 4097):
+        p = [S.feistel_perm(j, deg, 0xC0FFEE) for j in range(deg)]
+        assert sorted(p) == list(range(deg))
+        assert p == [S.feistel_perm(j, deg, 0xC0FFEE) for j in range(deg)]
+    assert [S.feistel_perm(j, 1000, 1) for j in range(8)] != [S.feistel_perm(j, 1000, 2) for j in range(8)]
+
+
+def test_sample_blocks_contract():
+    d = synth.random_multigraph(400, 9000, 5, seed=2)
+    c = csr_oracle.csr_build(d['src'], d['dst'], 400)
+    seeds = np.arange(20, 52)
+    n_id, blocks = S.sample_blocks(c, seeds, [5, 3], seed=11, epoch=1, rank=0, batch=4)
+    assert len(blocks) == 2 and np.array_equal(n_id[:32], seeds)          # targets first
+    inner = blocks[-1]
+    assert inner[4] == 32 and inner[3] == blocks[0][4]                     # frontier sizes chain up
+    deg = np.diff(c['indptr'])
+    src_l, dst_l, eid, n_src, n_dst = inner
+    for i, t in enumerate(seeds):                                          # min(deg, fanout) distinct in-edges of t
+        e = eid[dst_l == i]
+        assert len(e) == min(deg[t], 5) and len(set(e.tolist())) == len(e)
+        assert np.all(d['dst'][e] == t)
+    outer_nid = n_id[:blocks[0][3]]
+    assert np.array_equal(outer_nid[blocks[0][0]], d['src'][blocks[0][2]])  # local -> global ids are consistent
+    n2, b2 = S.sample_blocks(c, seeds, [5, 3], seed=11, epoch=1, rank=1, batch=4)
+    assert not np.array_equal(b2[-1][2], inner[2])                         # another rank draws another sample
+
+
+def test_mag_regcn_layer_matches_oracle(cpu_ops):
+    from re_gnn_b200 import mag
+    torch.manual_seed(0)
+    rng = np.random.RandomState(0)
+    n_src, n_dst, e, net, nnt = 40, 12, 150, 5, 3
+    ei = torch.as_tensor(np.stack([rng.randint(0, n_src, e), rng.randint(0, n_dst - 2, e)]))   # 2 targets w/o edges
+    et = torch.as_tensor(rng.randint(0, net, e))
+    tnt = torch.as_tensor(rng.randint(0, nnt, n_dst))
+    for slt, residual in [(2, False), (2, True), (1, False)]:
+        conv = mag.REGCNConv(8, 6 if not residual else 8, nnt, net, 100.0, residual=residual, self_loop_type=slt).double()
+        conv.relation_weight.data.copy_(torch.as_tensor(rng.uniform(-0.5, 1.5, conv.relation_weight.shape) / 100.0))
+        x = torch.as_tensor(rng.randn(n_src, 8)).requires_grad_(True)
+        out = conv((x, x[:n_dst]), ei, et, tnt)
+        p = {k: v.detach().clone().requires_grad_(True) for k, v in conv.named_parameters()}
+        xr = x.detach().clone().requires_grad_(True)
+        ref = O.mag_regcn_forward(xr, xr[:n_dst], ei, et, tnt, p['weight'], p['bias'], p['relation_weight'], 100.0,
+                                  net, slt, residual)
+        assert torch.allclose(out, ref, rtol=1e-10, atol=1e-12)
+        g = torch.as_tensor(rng.randn(*ref.shape))
+        out.backward(g)
+        ref.backward(g)
+        assert torch.allclose(x.grad, xr.grad, rtol=1e-9, atol=1e-12)
+        for k, v in conv.named_parameters():
+            assert torch.allclose(v.grad, p[k].grad, rtol=1e-9, atol=1e-11), k
