@@ -222,13 +222,18 @@ static void radix_sort_pairs(SortBuffers& sb, int64_t n, int bits, uint32_t** ke
 }
 
 // indptr[v] = first sorted position whose key is >= v (keys sorted ascending); indptr[N] = n.
+// One thread per row, binary search: no serial walk over runs of empty rows (sampled blocks have
+// tens of thousands of trailing rows without in-edges).
 __global__ void boundary_fill_kernel(const uint32_t* __restrict__ keys, int64_t n, int64_t n_nodes,
                                      int32_t* __restrict__ indptr) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > n) return;
-  int64_t prev = i == 0 ? -1 : (int64_t)keys[i - 1];
-  int64_t cur = i == n ? n_nodes : (int64_t)keys[i];
-  for (int64_t v = prev + 1; v <= cur; ++v) indptr[v] = (int32_t)i;
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > n_nodes) return;
+  int64_t lo = 0, hi = n;  // first index with keys[idx] >= v
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)keys[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  indptr[v] = (int32_t)lo;
 }
 
 __global__ void finish_csr_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
@@ -314,7 +319,7 @@ extern "C" int regnn_csr_build(const int64_t* src, const int64_t* dst, int64_t n
   SortBuffers sb = carve(workspace, num_edges);
   const int bits = key_bits(num_nodes);
   const int T = 256;
-  const unsigned eb = (unsigned)((num_edges + T - 1) / T), ebp = (unsigned)((num_edges + 1 + T - 1) / T);
+  const unsigned eb = (unsigned)((num_edges + T - 1) / T), ebp = (unsigned)((num_nodes + 1 + T - 1) / T);
   cudaMemsetAsync(sb.err, 0, sizeof(int), stream);
   uint32_t *keys, *vals;
 
