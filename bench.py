@@ -225,6 +225,49 @@ def others(dev, steps, warmup):
     return res
 
 
+def epoch_times(dev, steps, warmup):
+    """Epoch time in the reference's own definition (run_regnn.py:144-159): one training step (forward, cross-entropy
+    on the training nodes, backward, Adam) plus one no-grad evaluation forward, full batch, for the three callers
+    of the hot path on their HGB-shaped graphs with the reference's default hyper-parameters
+    (hidden 64, 4 heads x 4 layers for REGAT, 2 layers for REGCN / REMixHop, dropout as in scripts/*.sh)."""
+    import torch.nn.functional as F
+    from re_gnn_b200 import Graph, model as M, synth
+    in_dims = {'dblp': [334, 4231, 50, 20], 'acm': [1902, 1902, 1902, 1902], 'imdb': [3066, 3066, 3066, 3066]}
+    classes = {'dblp': 4, 'acm': 3, 'imdb': 5}
+    res = {}
+    for name, shape, build in [
+        ('dblp_regcn_2layer', 'dblp', lambda g, r, dims, c: M.REGCN(g, r, ALPHA, 64, 64, c, 2, F.elu, 0.5, dims)),
+        ('acm_regat_4layer_8head', 'acm', lambda g, r, dims, c: M.REGAT(g, r, ALPHA, 4, 64, 64, c, [8] * 4 + [1], F.elu,
+                                                                       0.6, 0.6, 0.01, False, dims)),
+        ('imdb_remixhop_2layer', 'imdb', lambda g, r, dims, c: M.REMixHop(g, r, ALPHA, 64, 64, c, 2, dims,
+                                                                           input_dropout=0.6, activation=F.elu)),
+    ]:
+        d = synth.hetero_graph(shape)
+        g = Graph(d['src'], d['dst'], d['num_nodes']).to(dev)
+        et = torch.as_tensor(d['etype']).to(dev)
+        net = build(g, d['num_relations'], in_dims[shape], classes[shape]).to(dev)
+        feats = [torch.randn(sz, dim, device=dev) for sz, dim in zip(d['type_sizes'], in_dims[shape])]
+        labels = torch.randint(0, classes[shape], (d['type_sizes'][0],), device=dev)
+        train_idx = torch.arange(0, d['type_sizes'][0], 2, device=dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-3)
+
+        def epoch():
+            net.train()
+            logits, _ = net(feats, et)
+            loss = F.cross_entropy(logits[train_idx], labels[train_idx])
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            net.eval()
+            with torch.no_grad():
+                net(feats, et)
+
+        t = timed(epoch, steps, warmup, torch.cuda.synchronize) / steps
+        res[name] = {'epoch_ms': t * 1e3, 'num_edges': int(d['src'].size), 'num_nodes': int(d['num_nodes']),
+                     'definition': 'train step + no-grad eval forward (run_regnn.py:144-159)'}
+    return res
+
+
 def run_ours(args, d):
     import torch.distributed as dist
     import re_gnn_b200  # noqa: F401  (fails loudly if the CUDA library is missing)
@@ -363,6 +406,7 @@ def run_ours(args, d):
         line['cpu_baseline'], _ = cpu_reference_sample(d, f, 3, 1)
     if world == 1 and not args.no_others:
         line['others'] = others(dev, 10, 3)
+        line['epoch_time'] = epoch_times(dev, 10, 3)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

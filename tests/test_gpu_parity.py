@@ -403,3 +403,52 @@ def test_mag_regcn_layer_and_train_step():
         losses.append(float(loss))
         assert n_edges > 0
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+# ---- row-range (partitioned) kernel paths on one GPU: P virtual ranks, all-gather emulated by sharing buffers ----
+@pytest.mark.parametrize('parts', [2, 5])
+def test_row_partitioned_kernels_equal_full_run(parts):
+    from re_gnn_b200 import ops, partition
+    d = synth.hetero_graph('dblp', seed=9, scale=0.3)
+    g, et = _graph(d), torch.as_tensor(d['etype']).to(DEV)
+    n, r, f = d['num_nodes'], d['num_relations'], 64
+    csr = g.csr()
+    etv = g.etype_views(et, r)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(n, f, device=DEV, generator=gen)
+    gout = torch.randn(n, f, device=DEV, generator=gen)
+    th = _theta(r, 1, 5).to(DEV, torch.float32)
+    deg, nrm = ops.wdeg_norm_fwd(csr, etv[0], th, 100.0, -0.5, counts=etv[2])
+    y = ops.spmm(csr['indptr'], csr['indices'], etv[0], th, 100.0, nrm, nrm, x, split=csr.get('split'))
+    dx, dth, xdx = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, x, gout, want_xdx=True)
+    dn = ops.rowdot_norm_bwd(nrm, x, y, gout, dx, xdx=xdx)
+    dth_n = ops.wdeg_norm_bwd(csr, etv[0], th, 100.0, -0.5, deg, dn, counts=etv[2])
+    bounds = partition.row_blocks(csr['indptr'], parts)
+    assert bounds[0] == 0 and bounds[-1] == n and len(bounds) == parts + 1
+    y_p, dx_p, dn_p = torch.empty_like(y), torch.empty_like(dx), torch.zeros_like(dn)
+    dth_p = torch.zeros_like(dth, dtype=torch.float64)
+    dth_np = torch.zeros_like(dth_n, dtype=torch.float64)
+    for p in range(parts):
+        rows = (bounds[p], bounds[p + 1])
+        ops.spmm(csr['indptr'], csr['indices'], etv[0], th, 100.0, nrm, nrm, x, rows=rows, out=y_p, split=csr.get('split'))
+        _, t, xd = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, x, gout, rows=rows, out=dx_p, want_xdx=True)
+        dth_p += t.double()
+        dnr = ops.rowdot_norm_bwd(nrm, x, y_p, gout, dx_p, rows=rows, xdx=xd)
+        dn_p[rows[0]:rows[1]] = dnr[rows[0]:rows[1]]
+        assert float(dnr[:rows[0]].abs().sum() + dnr[rows[1]:].abs().sum()) == 0.0
+        dth_np += ops.wdeg_norm_bwd(csr, etv[0], th, 100.0, -0.5, deg, dnr, rows=rows, counts=etv[2]).double()
+    assert torch.equal(y_p, y) and torch.equal(dx_p, dx) and torch.equal(dn_p, dn)      # row-local: bit-identical
+    helpers.assert_close(dth_p.cpu(), dth.double().cpu(), RTOL, 'd_theta (sum of rank shares)')
+    helpers.assert_close(dth_np.cpu(), dth_n.double().cpu(), 5 * RTOL, 'd_theta via norm (sum of rank shares)')
+    # attention kernels with a row range
+    h, dim = 4, 16
+    feat = torch.randn(n, h, dim, device=DEV, generator=gen)
+    el, er = torch.randn(n, h, device=DEV, generator=gen), torch.randn(n, h, device=DEV, generator=gen)
+    th2 = _theta(r, h, 6).to(DEV, torch.float32)
+    full = ops.gat_fwd(csr, etv[0], th2, 100.0, feat, el, er, 0.2)
+    part_out = torch.zeros_like(full[0])
+    for p in range(parts):
+        rows = (bounds[p], bounds[p + 1])
+        o = ops.gat_fwd(csr, etv[0], th2, 100.0, feat, el, er, 0.2, rows=rows)[0]
+        part_out[rows[0]:rows[1]] = o[rows[0]:rows[1]]
+    assert torch.equal(part_out, full[0])
