@@ -249,13 +249,13 @@ def epoch_times(dev, steps, warmup):
         feats = [torch.randn(sz, dim, device=dev) for sz, dim in zip(d['type_sizes'], in_dims[shape])]
         labels = torch.randint(0, classes[shape], (d['type_sizes'][0],), device=dev)
         train_idx = torch.arange(0, d['type_sizes'][0], 2, device=dev)
-        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-3)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-3, capturable=True)
 
         def epoch():
             net.train()
             logits, _ = net(feats, et)
             loss = F.cross_entropy(logits[train_idx], labels[train_idx])
-            opt.zero_grad()
+            opt.zero_grad(set_to_none=True)
             loss.backward()
             opt.step()
             net.eval()
@@ -265,6 +265,23 @@ def epoch_times(dev, steps, warmup):
         t = timed(epoch, steps, warmup, torch.cuda.synchronize) / steps
         res[name] = {'epoch_ms': t * 1e3, 'num_edges': int(d['src'].size), 'num_nodes': int(d['num_nodes']),
                      'definition': 'train step + no-grad eval forward (run_regnn.py:144-159)'}
+        # the same epoch captured once into a CUDA graph and replayed: these graphs are launch-bound
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    epoch()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                epoch()
+            tg = timed(graph.replay, steps, warmup, torch.cuda.synchronize) / steps
+            res[name]['epoch_ms_cuda_graph'] = tg * 1e3
+        except Exception as exc:  # report, do not hide
+            res[name]['epoch_ms_cuda_graph'] = None
+            res[name]['cuda_graph_error'] = str(exc)[:200]
+            torch.cuda.synchronize()
     return res
 
 

@@ -10,7 +10,7 @@ namespace regnn {
 
 constexpr float kRelationSlope = 0.01f;  // nn.LeakyReLU() default: layer/REGraphConv.py:60
 constexpr int kWarpsPerBlock = 8;        // row-parallel kernels: 256 threads, one row per (sub)warp
-constexpr int kMaxPartialBlocks = 1184;  // 148 SMs x 8: grid of the kernels that emit partial sums
+constexpr int kMaxPartialBlocks = 4736;  // 148 SMs x 32: cap on the grid of the kernels that emit per-block partial sums
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

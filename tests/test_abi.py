@@ -52,7 +52,7 @@ def test_status_strings_and_version(lib):
     assert lib.regnn_version() >= 100
     assert lib.regnn_status_string(0) == b'ok'
     assert lib.regnn_status_string(-2) == b'unsupported shape'
-    assert lib.regnn_max_partial_blocks() == 1184
+    assert lib.regnn_max_partial_blocks() == 4736
     assert lib.regnn_csr_build_workspace_bytes(10, 0) > 0
 
 
