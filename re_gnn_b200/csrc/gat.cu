@@ -9,6 +9,8 @@
 // LDG.128.  Slice k of lane l belongs to head (4*(l+32k))/D.  Per-head dot products are reduced
 // with xor-shuffles inside the aligned group of D/4 lanes that covers a head.  Gather-bound: one
 // H*D*4-byte source row per edge (two in the GATv2 source-major backward pass).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace regnn {
@@ -32,6 +34,8 @@ struct AttnArgs {
   const float* rowsum;
   const float* G;
   int H, D;
+  int d_shift;             // log2(D) when D is a power of two (the common case), else -1: avoids integer divisions
+  int hg_count;            // ceil(H*D / 128)
   int64_t row_begin, row_end;
   float* o0;               // fwd: out      bwd_dst: a_csr     bwd_src: d_feat / d_fs
   float* o1;               // fwd: rowmax   bwd_dst: dpre/dl   bwd_src: d_el
@@ -110,22 +114,34 @@ struct Group {
   int hg, col, hl, h_lo, nh, lph;
   bool ok, leader;
 };
+__device__ __forceinline__ int div_d(const AttnArgs& a, int x) { return a.d_shift >= 0 ? (x >> a.d_shift) : x / a.D; }
 __device__ __forceinline__ Group make_group(const AttnArgs& a, int hg, int lane) {
   Group g;
   const int HD = a.H * a.D;
   g.hg = hg;
   g.col = hg * 128 + lane * 4;
   g.ok = g.col < HD;
-  g.h_lo = (hg * 128) / a.D;
-  const int h_hi = min(a.H - 1, (hg * 128 + 127) / a.D);
+  g.h_lo = div_d(a, hg * 128);
+  const int h_hi = min(a.H - 1, div_d(a, hg * 128 + 127));
   g.nh = h_hi - g.h_lo + 1;
-  g.hl = g.ok ? g.col / a.D : g.h_lo;
+  g.hl = g.ok ? div_d(a, g.col) : g.h_lo;
   const int lanes_per_head = a.D >> 2;
   g.lph = min(32, lanes_per_head);
-  g.leader = g.ok && ((g.col >> 2) % lanes_per_head == 0);
+  g.leader = g.ok && (g.col - g.hl * a.D == 0);   // first lane of its head
   return g;
 }
-__device__ __forceinline__ int num_groups(const AttnArgs& a) { return (a.H * a.D + 127) / 128; }
+__device__ __forceinline__ int num_groups(const AttnArgs& a) { return a.hg_count; }
+// (item index, head group) of warp item wi; 32-bit arithmetic whenever the item count allows it
+__device__ __forceinline__ void split_item(int64_t wi, int HG, int64_t* ri, int* hg) {
+  if (wi < 0x7fffffffLL) {
+    const unsigned w = (unsigned)wi;
+    *ri = w / (unsigned)HG;
+    *hg = (int)(w % (unsigned)HG);
+  } else {
+    *ri = wi / HG;
+    *hg = (int)(wi % HG);
+  }
+}
 
 // =================================================================================================
 // REGAT forward.  Logits of a batch of 32 edges are computed one edge per lane (heads of this group);
@@ -144,9 +160,12 @@ gat_fwd_kernel(AttnArgs a) {
   load_rel_table(w_s, a);
   const int HG = num_groups(a);
   const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  const WorkItem it = decode_item(a, wi / HG, a.nfrag);
+  int64_t ri;
+  int hg;
+  split_item(wi, HG, &ri, &hg);
+  const WorkItem it = decode_item(a, ri, a.nfrag);
   if (!it.ok) return;
-  const Group g = make_group(a, (int)(wi % HG), lane);
+  const Group g = make_group(a, hg, lane);
   const int64_t v = it.v;
   const int s0 = it.s0, len = it.len;
   float4 acc = zero4();
@@ -190,12 +209,14 @@ gat_fwd_kernel(AttnArgs a) {
     }
     __syncwarp();
     scale4(acc, sc_s[tl]);
-    for (int j = 0; j < cnt; j += kUA) {
+    // full groups of kUA edges run without per-edge predicates; the tail group is predicated
+    auto body = [&](int j, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
       float4 x[kUA];
       float p[kUA];
 #pragma unroll
       for (int u = 0; u < kUA; ++u) {
-        const bool ok = j + u < cnt;
+        const bool ok = FULL || j + u < cnt;
         const int jj = ok ? j + u : j;
         const int sidx = __shfl_sync(0xffffffffu, idx, jj);
         const bool ld = ok && g.ok;
@@ -204,7 +225,10 @@ gat_fwd_kernel(AttnArgs a) {
       }
 #pragma unroll
       for (int u = 0; u < kUA; ++u) fma4(acc, p[u], x[u]);
-    }
+    };
+    int j = 0;
+    for (; j + kUA <= cnt; j += kUA) body(j, std::true_type{});
+    if (j < cnt) body(j, std::false_type{});
     __syncwarp();
   }
 
@@ -242,14 +266,23 @@ gat_fwd_kernel(AttnArgs a) {
 // =================================================================================================
 // REGAT backward, destination-major.  Per edge: da = <feat[src,h,:], G[v,h,:]>, a recomputed from the
 // saved row max / sum, dl = a*keep*da - a*S with S = <out[v,h,:], G[v,h,:]>.
-// Dynamic smem: w_s[R*H] | per warp: binsw[R*H]
+// Two phases per batch of 32 slots, like the forward: (1) one edge per lane recomputes a, a*keep and the
+// LeakyReLU slope for the heads of this group (the el[src] gathers and exps are spread over 32 lanes instead
+// of serialising on the head-leader lanes); (2) the warp gathers the feat[src] slices, reduces the dots in the
+// D/4-lane head groups and the leader lanes finish dpre; (3) each lane writes the values of its edge.
+// Dynamic smem: w_s[R*H] | per warp: binsw[R*H] | per warp: pa_s, pt_s, pg_s, dp_s [32][HP]
+template <int LPH>   // lanes per head = min(32, D/4), a power of two
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 gat_bwd_dst_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
+  const int H = a.H, HD = H * a.D, HP = H | 1, RH = a.etype != nullptr ? a.R * H : 0;
   float* w_s = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* binsw = smem + RH + warp * RH;
+  float* pa_s = smem + RH * (1 + kWarpsPerBlock) + warp * (4 * 32 * HP);
+  float* pt_s = pa_s + 32 * HP;
+  float* pg_s = pt_s + 32 * HP;
+  float* dp_s = pg_s + 32 * HP;
   for (int i = lane; i < RH; i += 32) binsw[i] = 0.f;
   load_rel_table(w_s, a);
   const int HG = num_groups(a);
@@ -257,65 +290,91 @@ gat_bwd_dst_kernel(AttnArgs a) {
 
   for (int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; wi < items;
        wi += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const WorkItem it = decode_item(a, wi / HG, a.nfrag);
+    int64_t ri;
+    int hg;
+    split_item(wi, HG, &ri, &hg);
+    const WorkItem it = decode_item(a, ri, a.nfrag);
     if (!it.ok) continue;
-    const Group g = make_group(a, (int)(wi % HG), lane);
+    const Group g = make_group(a, hg, lane);
     const int64_t v = it.v;
     const int s0 = it.s0, len = it.len;
+    const int tl = g.hl - g.h_lo;
     const float* fcol = a.feat + g.col;
     float4 gv = zero4();
-    float part = 0.f, m = 0.f, inv = 0.f, erv = 0.f, der = 0.f;
+    float part = 0.f, der = 0.f;
     if (g.ok) {
       gv = ldg4(a.G + (size_t)v * HD + g.col);
       part = dot4(ldg4(a.out + (size_t)v * HD + g.col), gv);
-      const size_t vh = (size_t)v * H + g.hl;
-      m = a.rowmax[vh];
-      const float sm = a.rowsum[vh];
-      inv = sm > 0.f ? 1.f / sm : 0.f;
-      erv = a.er[vh];
     }
-    const float S = group_sum_rt(part, g.lph);
+    const float S = group_sum<LPH>(part);
     for (int base = 0; base < len; base += 32) {
       const int cnt = min(32, len - base);
+      const bool valid = lane < cnt;
       const int slot = s0 + base + lane;
       int idx = 0, et = 0, e = 0;
-      if (lane < cnt) {
+      if (valid) {
         idx = a.indices[slot];
         if (a.etype != nullptr) et = a.etype[slot];
         if (a.keep != nullptr) e = a.eid[slot];
       }
-      for (int j = 0; j < cnt; j += kUA) {
+      for (int t = 0; t < g.nh; ++t) {  // phase 1: one edge per lane
+        const int h = g.h_lo + t;
+        float aa = 0.f, at = 0.f, gr = 0.f;
+        if (valid) {
+          const size_t vh = (size_t)v * H + h;
+          float pre = __ldg(a.el + (size_t)idx * H + h) + __ldg(a.er + vh);
+          if (a.etype != nullptr) pre += w_s[et * H + h];
+          const float sm = __ldg(a.rowsum + vh);
+          aa = expf(leaky(pre, a.slope) - __ldg(a.rowmax + vh)) * (sm > 0.f ? 1.f / sm : 0.f);
+          at = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)e * H + h) : aa;
+          gr = leaky_grad(pre, a.slope);
+        }
+        pa_s[lane * HP + t] = aa;
+        pt_s[lane * HP + t] = at;
+        pg_s[lane * HP + t] = gr;
+      }
+      __syncwarp();
+      auto body = [&](int j, auto full_tag) {  // phase 2: gather + per-head dots
+        constexpr bool FULL = decltype(full_tag)::value;
         float4 x[kUA];
         float da[kUA];
-        int sidx[kUA];
 #pragma unroll
         for (int u = 0; u < kUA; ++u) {
-          sidx[u] = __shfl_sync(0xffffffffu, idx, min(j + u, cnt - 1));
-          x[u] = (j + u < cnt && g.ok) ? ldg4(fcol + (size_t)sidx[u] * HD) : zero4();
+          const bool ok = FULL || j + u < cnt;
+          const int sidx = __shfl_sync(0xffffffffu, idx, ok ? j + u : j);
+          x[u] = (ok && g.ok) ? ldg4(fcol + (size_t)sidx * HD) : zero4();
         }
 #pragma unroll
-        for (int u = 0; u < kUA; ++u) da[u] = group_sum_rt(dot4(x[u], gv), g.lph);  // independent reductions: ILP
+        for (int u = 0; u < kUA; ++u) da[u] = group_sum<LPH>(dot4(x[u], gv));  // independent reductions: ILP
 #pragma unroll
         for (int u = 0; u < kUA; ++u) {
-          if (j + u < cnt) {  // warp-uniform
+          if (FULL || j + u < cnt) {  // warp-uniform
             const int set = __shfl_sync(0xffffffffu, et, j + u);
-            const int se = __shfl_sync(0xffffffffu, e, j + u);
             if (g.leader) {
-              const int h = g.hl;
-              const size_t sh = (size_t)(s0 + base + j + u) * H + h;
-              float pre = __ldg(a.el + (size_t)sidx[u] * H + h) + erv;
-              if (a.etype != nullptr) pre += w_s[set * H + h];
-              const float aa = expf(leaky(pre, a.slope) - m) * inv;
-              const float at = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)se * H + h) : aa;
-              const float dp = (at * da[u] - aa * S) * leaky_grad(pre, a.slope);
-              a.o0[sh] = at;
-              a.o1[sh] = dp;
+              const int o = (j + u) * HP + tl;
+              const float dp = (pt_s[o] * da[u] - pa_s[o] * S) * pg_s[o];
+              dp_s[o] = dp;
               der += dp;
-              if (a.etype != nullptr) binsw[set * H + h] += dp;
+              if (a.etype != nullptr) binsw[set * H + g.hl] += dp;
             }
           }
         }
+      };
+      {
+        int j = 0;
+        for (; j + kUA <= cnt; j += kUA) body(j, std::true_type{});
+        if (j < cnt) body(j, std::false_type{});
       }
+      __syncwarp();
+      if (valid) {  // phase 3: each lane writes the heads of its own edge
+        float* ao = a.o0 + (size_t)slot * H + g.h_lo;
+        float* po = a.o1 + (size_t)slot * H + g.h_lo;
+        for (int t = 0; t < g.nh; ++t) {
+          ao[t] = pt_s[lane * HP + t];
+          po[t] = dp_s[lane * HP + t];
+        }
+      }
+      __syncwarp();
     }
     if (g.leader) {
       if (it.frag) a.p1[(size_t)it.fi * H + g.hl] = der;
@@ -342,9 +401,12 @@ gat_bwd_src_kernel(AttnArgs a) {
   float* p_s = smem + warp * (32 * HP);
   const int HG = num_groups(a);
   const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  const WorkItem it = decode_item(a, wi / HG, a.nfrag);
+  int64_t ri;
+  int hg;
+  split_item(wi, HG, &ri, &hg);
+  const WorkItem it = decode_item(a, ri, a.nfrag);
   if (!it.ok) return;
-  const Group g = make_group(a, (int)(wi % HG), lane);
+  const Group g = make_group(a, hg, lane);
   const int64_t u_row = it.v;
   const int t0 = it.s0, len = it.len;
   const int tl = g.hl - g.h_lo;
@@ -369,12 +431,13 @@ gat_bwd_src_kernel(AttnArgs a) {
       }
     }
     __syncwarp();
-    for (int j = 0; j < cnt; j += kUA) {
+    auto body = [&](int j, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
       float4 x[kUA];
       float p[kUA];
 #pragma unroll
       for (int u = 0; u < kUA; ++u) {
-        const bool ok = j + u < cnt;
+        const bool ok = FULL || j + u < cnt;
         const int jj = ok ? j + u : j;
         const int sd = __shfl_sync(0xffffffffu, d, jj);
         const bool ld = ok && g.ok;
@@ -383,7 +446,10 @@ gat_bwd_src_kernel(AttnArgs a) {
       }
 #pragma unroll
       for (int u = 0; u < kUA; ++u) fma4(acc, p[u], x[u]);
-    }
+    };
+    int j = 0;
+    for (; j + kUA <= cnt; j += kUA) body(j, std::true_type{});
+    if (j < cnt) body(j, std::false_type{});
     __syncwarp();
   }
   if (g.ok) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)u_row * HD) + g.col, acc);
@@ -398,6 +464,7 @@ gat_bwd_src_kernel(AttnArgs a) {
 // reduced by xor-shuffles over the D/4 lanes of a head) and the aggregation; online softmax per
 // group of kUA edges.  Nothing [E,H,D]-sized is ever written.
 // Dynamic smem: w_s[R*H] | per warp: m_s[H], inv_s[H]
+template <int LPH>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 gatv2_fwd_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -409,9 +476,12 @@ gatv2_fwd_kernel(AttnArgs a) {
   load_rel_table(w_s, a);
   const int HG = num_groups(a);
   const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  const WorkItem it = decode_item(a, wi / HG, a.nfrag);
+  int64_t ri;
+  int hg;
+  split_item(wi, HG, &ri, &hg);
+  const WorkItem it = decode_item(a, ri, a.nfrag);
   if (!it.ok) return;
-  const Group g = make_group(a, (int)(wi % HG), lane);
+  const Group g = make_group(a, hg, lane);
   const int64_t v = it.v;
   const int s0 = it.s0, len = it.len;
   float4 acc = zero4(), fdv = zero4(), at = zero4();
@@ -432,21 +502,23 @@ gatv2_fwd_kernel(AttnArgs a) {
       if (a.etype != nullptr) et = a.etype[slot];
       if (need_eid) e = a.eid[slot];
     }
-    for (int j = 0; j < cnt; j += kUA) {
+    auto body = [&](int j, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
       float4 x[kUA];
       float l[kUA];
 #pragma unroll
       for (int u = 0; u < kUA; ++u) {
-        const int sidx = __shfl_sync(0xffffffffu, idx, min(j + u, cnt - 1));
-        x[u] = (j + u < cnt && g.ok) ? ldg4(fcol + (size_t)sidx * HD) : zero4();
+        const bool ok = FULL || j + u < cnt;
+        const int sidx = __shfl_sync(0xffffffffu, idx, ok ? j + u : j);
+        x[u] = (ok && g.ok) ? ldg4(fcol + (size_t)sidx * HD) : zero4();
       }
       float bm = -INFINITY;
 #pragma unroll
       for (int u = 0; u < kUA; ++u) {  // kUA independent head reductions
-        l[u] = group_sum_rt(dot4(at, leaky4(add4(x[u], fdv), a.slope)), g.lph);
-        const int set = __shfl_sync(0xffffffffu, et, min(j + u, cnt - 1));
-        if (a.etype != nullptr) l[u] += w_s[set * H + g.hl];
-        if (j + u >= cnt) l[u] = -INFINITY;
+        const bool ok = FULL || j + u < cnt;
+        l[u] = group_sum<LPH>(dot4(at, leaky4(add4(x[u], fdv), a.slope)));
+        if (a.etype != nullptr) l[u] += w_s[__shfl_sync(0xffffffffu, et, ok ? j + u : j) * H + g.hl];
+        if (!ok) l[u] = -INFINITY;
         bm = fmaxf(bm, l[u]);
       }
       const float m_new = fmaxf(m, bm);
@@ -456,8 +528,9 @@ gatv2_fwd_kernel(AttnArgs a) {
       scale4(acc, sc);
 #pragma unroll
       for (int u = 0; u < kUA; ++u) {
-        if (j + u < cnt) {  // warp-uniform
-          const int se = __shfl_sync(0xffffffffu, e, j + u);
+        if (FULL || j + u < cnt) {  // warp-uniform
+          int se = 0;
+          if (need_eid) se = __shfl_sync(0xffffffffu, e, j + u);
           if (g.ok) {
             if (a.o3 != nullptr && g.leader) a.o3[(size_t)se * H + g.hl] = l[u];
             float p = expf(l[u] - m_new);
@@ -467,7 +540,10 @@ gatv2_fwd_kernel(AttnArgs a) {
           }
         }
       }
-    }
+    };
+    int j = 0;
+    for (; j + kUA <= cnt; j += kUA) body(j, std::true_type{});
+    if (j < cnt) body(j, std::false_type{});
   }
   if (it.frag) {
     if (g.ok) {
@@ -507,6 +583,7 @@ gatv2_fwd_kernel(AttnArgs a) {
 // REGATv2 backward, destination-major: a_csr, dl_csr, d_fd rows, per-block partials of d_attn and
 // of the relation-gradient table.
 // Dynamic smem: w_s[R*H] | per warp: binsw[R*H] | per warp: dat_s[128]
+template <int LPH>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 gatv2_bwd_dst_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -545,7 +622,7 @@ gatv2_bwd_dst_kernel(AttnArgs a) {
       const float sm = a.rowsum[vh];
       inv = sm > 0.f ? 1.f / sm : 0.f;
     }
-    const float S = group_sum_rt(part, g.lph);
+    const float S = group_sum<LPH>(part);
     for (int base = 0; base < len; base += 32) {
       const int cnt = min(32, len - base);
       const int slot = s0 + base + lane;
@@ -565,8 +642,8 @@ gatv2_bwd_dst_kernel(AttnArgs a) {
         }
 #pragma unroll
         for (int u = 0; u < kUA; ++u) {
-          l[u] = group_sum_rt(dot4(at, leaky4(add4(x[u], fdv), a.slope)), g.lph);
-          da[u] = group_sum_rt(dot4(x[u], gv), g.lph);
+          l[u] = group_sum<LPH>(dot4(at, leaky4(add4(x[u], fdv), a.slope)));
+          da[u] = group_sum<LPH>(dot4(x[u], gv));
         }
 #pragma unroll
         for (int u = 0; u < kUA; ++u) {
@@ -628,9 +705,12 @@ gatv2_bwd_src_kernel(AttnArgs a) {
   float* q_s = p_s + 32 * HP;
   const int HG = num_groups(a);
   const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  const WorkItem it = decode_item(a, wi / HG, a.nfrag);
+  int64_t ri;
+  int hg;
+  split_item(wi, HG, &ri, &hg);
+  const WorkItem it = decode_item(a, ri, a.nfrag);
   if (!it.ok) return;
-  const Group g = make_group(a, (int)(wi % HG), lane);
+  const Group g = make_group(a, hg, lane);
   const int64_t u_row = it.v;
   const int t0 = it.s0, len = it.len;
   const int tl = g.hl - g.h_lo;
@@ -765,6 +845,10 @@ static int pick_c(int HD) {
 
 // Fills the fragment fields of `a` from the caller's row split; returns false if it is incomplete.
 static bool apply_split(AttnArgs& a, const regnn_rowsplit_t* split, float* ws) {
+  a.hg_count = (a.H * a.D + 127) / 128;
+  a.d_shift = -1;
+  for (int b = 2; b <= 10; ++b)
+    if ((1 << b) == a.D) a.d_shift = b;
   a.nfrag = a.nfrag_pad = 0;
   a.threshold = 0x7fffffff;
   if (split == nullptr || split->num_frags <= 0) return true;
@@ -812,6 +896,20 @@ static int check_shape(const char* who, int H, int D, int R, bool has_rel, bool 
   attn_frag_finalize_kernel<<<GRID, kWarpsPerBlock * 32, 0, stream>>>(a, split->long_rows, split->frag_ptr, split->num_long)
 
 static int head_groups(int H, int D) { return (H * D + 127) / 128; }
+
+// kernels that reduce over the D/4 lanes of a head are compiled per lane count (fully unrolled butterflies)
+#define REGNN_DISPATCH_LPH(KERNEL, GRID, SMEM)                                          \
+  do {                                                                                  \
+    const int lph_ = a.D / 4 >= 32 ? 32 : a.D / 4;                                      \
+    switch (lph_) {                                                                     \
+      case 1: REGNN_DISPATCH_C(KERNEL<1>, GRID, SMEM); break;                           \
+      case 2: REGNN_DISPATCH_C(KERNEL<2>, GRID, SMEM); break;                           \
+      case 4: REGNN_DISPATCH_C(KERNEL<4>, GRID, SMEM); break;                           \
+      case 8: REGNN_DISPATCH_C(KERNEL<8>, GRID, SMEM); break;                           \
+      case 16: REGNN_DISPATCH_C(KERNEL<16>, GRID, SMEM); break;                         \
+      default: REGNN_DISPATCH_C(KERNEL<32>, GRID, SMEM); break;                         \
+    }                                                                                   \
+  } while (0)
 
 }  // namespace regnn
 
@@ -878,9 +976,9 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
   a.partials = partials; a.partial_stride = a.R * num_heads;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_dst: incomplete row split");
   const int RH = a.R * num_heads;
-  const size_t smem = sizeof(float) * ((size_t)RH * (1 + kWarpsPerBlock)) + 16;
+  const size_t smem = sizeof(float) * ((size_t)RH * (1 + kWarpsPerBlock) + (size_t)kWarpsPerBlock * 4 * 32 * (num_heads | 1)) + 16;
   const int nb = partial_blocks((rows + a.nfrag) * head_groups(a.H, a.D));
-  REGNN_DISPATCH_C(gat_bwd_dst_kernel, nb, smem);
+  REGNN_DISPATCH_LPH(gat_bwd_dst_kernel, nb, smem);
   if (a.nfrag > 0) launch_rowsum(split, a.p1, num_heads, d_er, row_begin, row_end, stream);
   if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH, RH, theta, alpha, d_theta, stream);
   return check_launch("regnn_gat_bwd_dst");
@@ -941,7 +1039,7 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_fwd: incomplete row split");
   const size_t smem = sizeof(float) * ((size_t)a.R * num_heads + (size_t)kWarpsPerBlock * 2 * num_heads) + 16;
   const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  REGNN_DISPATCH_C(gatv2_fwd_kernel, grid, smem);
+  REGNN_DISPATCH_LPH(gatv2_fwd_kernel, grid, smem);
   if (a.nfrag > 0) {
     const unsigned fgrid = (unsigned)(((int64_t)split->num_long * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
     REGNN_DISPATCH_FINALIZE(fgrid);
@@ -979,7 +1077,7 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
   const size_t smem = sizeof(float) * ((size_t)((RH + 3) & ~3) * (1 + kWarpsPerBlock) + (size_t)kWarpsPerBlock * 128) + 16;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: incomplete row split");
   const int nb = partial_blocks((rows + a.nfrag) * head_groups(a.H, a.D));
-  REGNN_DISPATCH_C(gatv2_bwd_dst_kernel, nb, smem);
+  REGNN_DISPATCH_LPH(gatv2_bwd_dst_kernel, nb, smem);
   if (a.nfrag > 0) launch_rowsum(split, a.p0, HD, d_fd, row_begin, row_end, stream);
   if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH + HD, RH, theta, alpha, d_theta, stream);
   launch_colsum_finalize(partials, nb, RH + HD, RH, HD, d_attn, stream);
