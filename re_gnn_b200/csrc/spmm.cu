@@ -275,11 +275,11 @@ constexpr int kRowsPerItem = 32;      // rows per warp item, plain variant
 constexpr int kRowsPerItemBins = 8;   // rows per warp item, BINS variant (bounds the shared-memory tile)
 
 template <int C, int VW, bool BINS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (C <= 1 ? 3 : 1))
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (C <= 1 ? (BINS ? 3 : 4) : 1))
 spmm_stream_kernel(StreamArgs sa) {
   using V = Vec<VW>;
   using T = typename V::T;
-  constexpr int U = Unroll<C>::U;
+  constexpr int U = (!BINS && C == 1) ? 6 : Unroll<C>::U;  // 6 gathers x 32 warps/SM beat 8 x 24 (measured)
   constexpr int RB = BINS ? kRowsPerItemBins : kRowsPerItem;
   const SpmmArgs& a = sa.s;
   __shared__ float w_s[256];
