@@ -275,11 +275,11 @@ constexpr int kRowsPerItem = 32;      // rows per warp item, plain variant
 constexpr int kRowsPerItemBins = 8;   // rows per warp item, BINS variant (bounds the shared-memory tile)
 
 template <int C, int VW, bool BINS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (C <= 1 ? (BINS ? 3 : 4) : 1))
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (C <= 1 ? 4 : 1))
 spmm_stream_kernel(StreamArgs sa) {
   using V = Vec<VW>;
   using T = typename V::T;
-  constexpr int U = (!BINS && C == 1) ? 6 : Unroll<C>::U;  // 6 gathers x 32 warps/SM beat 8 x 24 (measured)
+  constexpr int U = C == 1 ? (BINS ? 4 : 6) : Unroll<C>::U;  // 6 gathers x 32 warps/SM beat 8 x 24 (measured)
   constexpr int RB = BINS ? kRowsPerItemBins : kRowsPerItem;
   const SpmmArgs& a = sa.s;
   __shared__ float w_s[256];
@@ -500,32 +500,53 @@ spmm_stream_kernel(StreamArgs sa) {
 
 // d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v]   (pure streaming, row per warp).
 // xdx != null supplies <X[v],dX[v]> (produced by the fused backward), so X and dX are not read again.
+constexpr int kRowdotRows = 4;  // rows per warp: 2-4 x 4 independent 128-bit loads in flight per lane
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 rowdot_norm_kernel(const float* __restrict__ norm, int sides, const float* __restrict__ X, int64_t ldx,
                    const float* __restrict__ Y, int64_t ldy, const float* __restrict__ G, int64_t ldg,
                    const float* __restrict__ dX, int64_t lddx, const float* __restrict__ xdx, int F,
                    int64_t row_begin, int64_t row_end, float* __restrict__ d_norm) {
   const int lane = threadIdx.x & 31;
-  const int64_t v = row_begin + (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (v >= row_end) return;
-  float p = 0.f;
+  const int64_t v0 = row_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * kRowdotRows;
+  if (v0 >= row_end) return;
   const bool use_x = (sides & 1) && xdx == nullptr;
   const bool vec = (F & 3) == 0 && ((ldy | ldg) & 3) == 0 && ((((uintptr_t)Y) | ((uintptr_t)G)) & 15) == 0 &&
                    (!use_x || (((ldx | lddx) & 3) == 0 && ((((uintptr_t)X) | ((uintptr_t)dX)) & 15) == 0));
+  float p[kRowdotRows];
+#pragma unroll
+  for (int r = 0; r < kRowdotRows; ++r) p[r] = 0.f;
   if (vec) {
     for (int c = lane * 4; c < F; c += 128) {
-      if (sides & 2) p += dot4(ldg4(Y + (size_t)v * ldy + c), ldg4(G + (size_t)v * ldg + c));
-      if (use_x) p += dot4(ldg4(X + (size_t)v * ldx + c), ldg4(dX + (size_t)v * lddx + c));
+#pragma unroll
+      for (int r = 0; r < kRowdotRows; ++r) {
+        const int64_t v = v0 + r;
+        if (v < row_end) {
+          if (sides & 2) p[r] += dot4(ldg4(Y + (size_t)v * ldy + c), ldg4(G + (size_t)v * ldg + c));
+          if (use_x) p[r] += dot4(ldg4(X + (size_t)v * ldx + c), ldg4(dX + (size_t)v * lddx + c));
+        }
+      }
     }
   } else {
     for (int c = lane; c < F; c += 32) {
-      if (sides & 2) p = fmaf(__ldg(Y + (size_t)v * ldy + c), __ldg(G + (size_t)v * ldg + c), p);
-      if (use_x) p = fmaf(__ldg(X + (size_t)v * ldx + c), __ldg(dX + (size_t)v * lddx + c), p);
+#pragma unroll
+      for (int r = 0; r < kRowdotRows; ++r) {
+        const int64_t v = v0 + r;
+        if (v < row_end) {
+          if (sides & 2) p[r] = fmaf(__ldg(Y + (size_t)v * ldy + c), __ldg(G + (size_t)v * ldg + c), p[r]);
+          if (use_x) p[r] = fmaf(__ldg(X + (size_t)v * ldx + c), __ldg(dX + (size_t)v * lddx + c), p[r]);
+        }
+      }
     }
   }
-  p = group_sum<32>(p);
-  if ((sides & 1) && xdx != nullptr) p += xdx[v];
-  if (lane == 0) d_norm[v] = p / norm[v];
+#pragma unroll
+  for (int r = 0; r < kRowdotRows; ++r) {
+    const int64_t v = v0 + r;
+    float t = group_sum<32>(p[r]);
+    if (v < row_end && lane == 0) {
+      if ((sides & 1) && xdx != nullptr) t += xdx[v];
+      d_norm[v] = t / norm[v];
+    }
+  }
 }
 
 // xdx[v] = <X[v], dX[v]> for the long rows (their dX is only complete after the fragment finalize)
@@ -1176,7 +1197,8 @@ extern "C" int regnn_rowdot_norm_bwd(const float* norm, int norm_sides, const fl
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0 && feat >= 1, REGNN_ERR_INVALID_ARG, "rowdot_norm_bwd: bad range / width");
   if (rows == 0) return REGNN_OK;
-  rowdot_norm_kernel<<<(unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, 0,
+  const int64_t rows_per_block = (int64_t)kWarpsPerBlock * kRowdotRows;
+  rowdot_norm_kernel<<<(unsigned)((rows + rows_per_block - 1) / rows_per_block), kWarpsPerBlock * 32, 0,
                        (cudaStream_t)stream>>>(norm, norm_sides & 3, X, ldx, Y, ldy, Gd, ldg, dX, lddx, xdx, feat,
                                                row_begin, row_end, d_norm);
   return check_launch("regnn_rowdot_norm_bwd");
