@@ -93,7 +93,9 @@ int regnn_etype_permute(const int64_t* etype_1based, const int32_t* eid, const i
 /* ------------------------------------------------------------------------------------------------
  * Relation-weighted in-degree normalisation:
  *   w = LeakyReLU_0.01(alpha * theta);  deg[v] = sum_{e in In(v)} w[etype e];
- *   norm[v] = max(deg[v], 1) ^ exponent
+ *   norm[v] = max(deg[v], clamp_min) ^ exponent        (clamp_min = 1 in every HGB layer;
+ *             clamp_min <= 0: no clamp, deg ^ exponent, and 0 for rows without in-edges -- the
+ *             `deg.pow(-1)` of the MAG-stack layers, mag/regnn_saint.py:254-258)
  * Replaces `update_all(u_mul_e('nones','ew'), sum)` + clamp + pow
  * (layer/REGraphConv.py:58-75, layer/REMixHopConv.py:50-64; exponent -1: RESAGEConv.py:75-78).
  * theta: [R] (the [R,1] `edge_weight` parameter).  Row range [row_begin, row_end) lets a rank of a
@@ -107,13 +109,13 @@ int regnn_relation_counts(const int32_t* row, const uint8_t* etype_csr, int64_t 
 
 int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr,
                         const int32_t* counts /* optional: then indptr/etype_csr may be NULL */, const float* theta,
-                        float alpha, int num_relations, float exponent, int64_t row_begin,
+                        float alpha, int num_relations, float exponent, float clamp_min, int64_t row_begin,
                         int64_t row_end, float* deg, float* norm, void* stream);
 /* Backward of the above: d_theta[r] += alpha * LeakyReLU'(alpha*theta[r]) *
  *   sum_{e: etype e = r} d_deg[dst e],   d_deg[v] = [deg[v] >= 1] * q * max(deg,1)^(q-1) * d_norm[v].
  * partials: double [regnn_max_partial_blocks() * R] scratch.  d_theta is OVERWRITTEN. */
 int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const int32_t* counts, const float* theta,
-                        float alpha, int num_relations, float exponent, int64_t row_begin,
+                        float alpha, int num_relations, float exponent, float clamp_min, int64_t row_begin,
                         int64_t row_end, const float* deg, const float* d_norm, double* partials,
                         float* d_theta, void* stream);
 

@@ -25,8 +25,8 @@ SIGNATURES = {
     'regnn_csr_build': (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     'regnn_etype_permute': (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p]),
     'regnn_relation_counts': (_i32, [_p, _p, _i64, _i64, _i32, _p, _p]),
-    'regnn_wdeg_norm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _f32, _i64, _i64, _p, _p, _p]),
-    'regnn_wdeg_norm_bwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _f32, _i64, _i64, _p, _p, _p, _p, _p]),
+    'regnn_wdeg_norm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _f32, _f32, _i64, _i64, _p, _p, _p]),
+    'regnn_wdeg_norm_bwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _f32, _f32, _i64, _i64, _p, _p, _p, _p, _p]),
     'regnn_spmm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i32, _p, _p, _p]),
     'regnn_spmm_bwd_w': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
                                 _i64, _i64, _i32, _p, _p, _p, _p, _p]),

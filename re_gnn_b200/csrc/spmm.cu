@@ -713,8 +713,17 @@ spmm_bwd_w_kernel(SpmmBwdArgs a) {
 }
 
 // ---- relation-weighted in-degree norm ------------------------------------------------------------
-__device__ __forceinline__ float norm_from_deg(float deg, float exponent) {
-  const float c = fmaxf(deg, 1.f);
+// clamp_min > 0: max(deg, clamp_min)^q (REGraphConv & co. use 1).  clamp_min <= 0: deg^q with no clamp and 0 for
+// deg == 0 (rows without in-edges; the mean/add aggregators of the MAG stack, mag/regnn_saint.py:254-258).
+// d deg = [deg >= clamp_min] * q * max(deg, clamp_min)^(q-1) * d_norm  (clamp passes the gradient at equality:
+// PyTorch semantics); without a clamp every non-empty row passes.
+__device__ __forceinline__ float ddeg_from(float d, float exponent, float clamp_min, float dn) {
+  if (clamp_min > 0.f) return d >= clamp_min ? exponent * powf(fmaxf(d, clamp_min), exponent - 1.f) * dn : 0.f;
+  return d != 0.f ? exponent * powf(d, exponent - 1.f) * dn : 0.f;
+}
+__device__ __forceinline__ float norm_from_deg(float deg, float exponent, float clamp_min) {
+  if (clamp_min <= 0.f && deg == 0.f) return 0.f;
+  const float c = clamp_min > 0.f ? fmaxf(deg, clamp_min) : deg;
   if (exponent == -0.5f) return 1.f / sqrtf(c);
   if (exponent == -1.f) return 1.f / c;
   return powf(c, exponent);
@@ -722,7 +731,7 @@ __device__ __forceinline__ float norm_from_deg(float deg, float exponent) {
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 wdeg_norm_fwd_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restrict__ etype,
-                     const float* __restrict__ theta, float alpha, int R, float exponent,
+                     const float* __restrict__ theta, float alpha, int R, float exponent, float clamp_min,
                      int64_t row_begin, int64_t row_end, float* __restrict__ deg,
                      float* __restrict__ norm) {
   constexpr int G = 8;
@@ -739,13 +748,13 @@ wdeg_norm_fwd_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restri
   acc = group_sum<G>(acc);
   if (v < row_end && lg == 0) {
     if (deg != nullptr) deg[v] = acc;
-    norm[v] = norm_from_deg(acc, exponent);
+    norm[v] = norm_from_deg(acc, exponent, clamp_min);
   }
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 wdeg_norm_bwd_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restrict__ etype, int R,
-                     float exponent, int64_t row_begin, int64_t row_end,
+                     float exponent, float clamp_min, int64_t row_begin, int64_t row_end,
                      const float* __restrict__ deg, const float* __restrict__ d_norm,
                      double* __restrict__ partials) {
   constexpr int G = 8, GPW = 32 / G;
@@ -764,7 +773,7 @@ wdeg_norm_bwd_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restri
     if (v < row_end) {
       const float d = deg[v];
       // clamp(min=1) passes the gradient at deg == 1 (PyTorch semantics)
-      const float dd = d >= 1.f ? exponent * powf(fmaxf(d, 1.f), exponent - 1.f) * d_norm[v] : 0.f;
+      const float dd = ddeg_from(d, exponent, clamp_min, d_norm[v]);
       const int s1 = indptr[v + 1];
       for (int s = indptr[v] + lg; s < s1; s += G) mybins[etype[s] * 32] += dd;
     }
@@ -794,7 +803,7 @@ __device__ __forceinline__ int row_of_slot(const int* ends, int nrows, int s) {
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 wdeg_norm_fwd_slot_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restrict__ etype,
-                          const float* __restrict__ theta, float alpha, int R, float exponent,
+                          const float* __restrict__ theta, float alpha, int R, float exponent, float clamp_min,
                           int64_t row_begin, int64_t row_end, float* __restrict__ deg,
                           float* __restrict__ norm) {
   __shared__ float w_s[32];
@@ -824,13 +833,13 @@ wdeg_norm_fwd_slot_kernel(const int32_t* __restrict__ indptr, const uint8_t* __r
     float d = 0.f;
     for (int r = 0; r < R; ++r) d = fmaf((float)cnt[lane * R + r], w_s[r], d);
     if (deg != nullptr) deg[r0 + lane] = d;
-    norm[r0 + lane] = norm_from_deg(d, exponent);
+    norm[r0 + lane] = norm_from_deg(d, exponent, clamp_min);
   }
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 wdeg_norm_bwd_slot_kernel(const int32_t* __restrict__ indptr, const uint8_t* __restrict__ etype, int R,
-                          float exponent, int64_t row_begin, int64_t row_end,
+                          float exponent, float clamp_min, int64_t row_begin, int64_t row_end,
                           const float* __restrict__ deg, const float* __restrict__ d_norm,
                           double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -853,7 +862,7 @@ wdeg_norm_bwd_slot_kernel(const int32_t* __restrict__ indptr, const uint8_t* __r
       ends_s[warp][lane] = my_end;
       const float d = deg[r0 + lane];
       // clamp(min=1) passes the gradient at deg == 1 (PyTorch semantics)
-      dd_s[warp][lane] = d >= 1.f ? exponent * powf(fmaxf(d, 1.f), exponent - 1.f) * d_norm[r0 + lane] : 0.f;
+      dd_s[warp][lane] = ddeg_from(d, exponent, clamp_min, d_norm[r0 + lane]);
     }
     const int s_begin = __shfl_sync(0xffffffffu, my_begin, 0);
     const int s_end = __shfl_sync(0xffffffffu, my_end, nrows - 1);
@@ -877,7 +886,7 @@ __global__ void relation_count_kernel(const int32_t* __restrict__ row, const uin
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 wdeg_norm_fwd_cnt_kernel(const int32_t* __restrict__ cnt, const float* __restrict__ theta, float alpha, int R,
-                         float exponent, int64_t row_begin, int64_t row_end, float* __restrict__ deg,
+                         float exponent, float clamp_min, int64_t row_begin, int64_t row_end, float* __restrict__ deg,
                          float* __restrict__ norm) {
   __shared__ float w_s[256];
   for (int i = threadIdx.x; i < R; i += blockDim.x) w_s[i] = leaky(theta[i] * alpha, kRelationSlope);
@@ -888,11 +897,11 @@ wdeg_norm_fwd_cnt_kernel(const int32_t* __restrict__ cnt, const float* __restric
   float d = 0.f;
   for (int r = 0; r < R; ++r) d = fmaf((float)__ldg(c + r), w_s[r], d);
   if (deg != nullptr) deg[v] = d;
-  norm[v] = norm_from_deg(d, exponent);
+  norm[v] = norm_from_deg(d, exponent, clamp_min);
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-wdeg_norm_bwd_cnt_kernel(const int32_t* __restrict__ cnt, int R, float exponent, int64_t row_begin,
+wdeg_norm_bwd_cnt_kernel(const int32_t* __restrict__ cnt, int R, float exponent, float clamp_min, int64_t row_begin,
                          int64_t row_end, const float* __restrict__ deg, const float* __restrict__ d_norm,
                          double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -905,7 +914,7 @@ wdeg_norm_bwd_cnt_kernel(const int32_t* __restrict__ cnt, int R, float exponent,
        v += (int64_t)gridDim.x * blockDim.x) {
     const float d = deg[v];
     // clamp(min=1) passes the gradient at deg == 1 (PyTorch semantics)
-    const float dd = d >= 1.f ? exponent * powf(fmaxf(d, 1.f), exponent - 1.f) * d_norm[v] : 0.f;
+    const float dd = ddeg_from(d, exponent, clamp_min, d_norm[v]);
     const int32_t* c = cnt + (size_t)v * R;
     for (int r = 0; r < R; ++r) mybins[r * 32] = fmaf(dd, (float)__ldg(c + r), mybins[r * 32]);
   }
@@ -976,7 +985,7 @@ extern "C" int regnn_relation_counts(const int32_t* row, const uint8_t* etype_cs
 
 extern "C" int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_csr, const int32_t* counts,
                                    const float* theta, float alpha, int num_relations,
-                                   float exponent, int64_t row_begin, int64_t row_end, float* deg,
+                                   float exponent, float clamp_min, int64_t row_begin, int64_t row_end, float* deg,
                                    float* norm, void* stream) {
   REGNN_REQUIRE(theta && norm && (counts || (indptr && etype_csr)), REGNN_ERR_INVALID_ARG, "wdeg_norm_fwd: null pointer");
   REGNN_REQUIRE(num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS, REGNN_ERR_UNSUPPORTED_SHAPE,
@@ -987,15 +996,15 @@ extern "C" int regnn_wdeg_norm_fwd(const int32_t* indptr, const uint8_t* etype_c
   const int threads = kWarpsPerBlock * 32;
   if (counts != nullptr) {
     wdeg_norm_fwd_cnt_kernel<<<(unsigned)((rows + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        counts, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
+        counts, theta, alpha, num_relations, exponent, clamp_min, row_begin, row_end, deg, norm);
   } else if (num_relations <= 32) {
     const int64_t blocks = (rows + kWarpsPerBlock * kWdegRows - 1) / (kWarpsPerBlock * kWdegRows);
     wdeg_norm_fwd_slot_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        indptr, etype_csr, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
+        indptr, etype_csr, theta, alpha, num_relations, exponent, clamp_min, row_begin, row_end, deg, norm);
   } else {
     const int64_t blocks = (rows * 8 + threads - 1) / threads;
     wdeg_norm_fwd_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        indptr, etype_csr, theta, alpha, num_relations, exponent, row_begin, row_end, deg, norm);
+        indptr, etype_csr, theta, alpha, num_relations, exponent, clamp_min, row_begin, row_end, deg, norm);
   }
   return check_launch("regnn_wdeg_norm_fwd");
 }
@@ -1004,7 +1013,7 @@ static size_t bins_smem_bytes(int R) { return (size_t)kWarpsPerBlock * R * (size
 
 extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const int32_t* counts,
                                    const float* theta, float alpha, int num_relations,
-                                   float exponent, int64_t row_begin, int64_t row_end,
+                                   float exponent, float clamp_min, int64_t row_begin, int64_t row_end,
                                    const float* deg, const float* d_norm, double* partials,
                                    float* d_theta, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1019,13 +1028,13 @@ extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_c
   int rc = set_smem(wdeg_norm_bwd_kernel, smem);
   if (rc != REGNN_OK) return rc;
   if (counts != nullptr)
-    wdeg_norm_bwd_cnt_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(counts, R, exponent, row_begin, row_end, deg,
+    wdeg_norm_bwd_cnt_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(counts, R, exponent, clamp_min, row_begin, row_end, deg,
                                                                          d_norm, partials);
   else if (R <= 32)
-    wdeg_norm_bwd_slot_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent, row_begin,
+    wdeg_norm_bwd_slot_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent, clamp_min, row_begin,
                                                                           row_end, deg, d_norm, partials);
   else
-    wdeg_norm_bwd_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent,
+    wdeg_norm_bwd_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent, clamp_min,
                                                                      row_begin, row_end, deg, d_norm, partials);
   launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
   return check_launch("regnn_wdeg_norm_bwd");

@@ -13,10 +13,11 @@ class _WDegNorm(torch.autograd.Function):
     """norm = max(sum_in LeakyReLU_0.01(alpha*theta)[etype], 1) ** exponent."""
 
     @staticmethod
-    def forward(ctx, graph, etv, theta, alpha, exponent):
+    def forward(ctx, graph, etv, theta, alpha, exponent, clamp_min):
         csr = graph.csr()
-        deg, norm = ops.wdeg_norm_fwd(csr, etv[0], theta, alpha, exponent, counts=etv[2] if len(etv) > 2 else None)
-        ctx.graph, ctx.etv, ctx.alpha, ctx.exponent = graph, etv, alpha, exponent
+        deg, norm = ops.wdeg_norm_fwd(csr, etv[0], theta, alpha, exponent, counts=etv[2] if len(etv) > 2 else None,
+                                      clamp_min=clamp_min)
+        ctx.graph, ctx.etv, ctx.alpha, ctx.exponent, ctx.clamp_min = graph, etv, alpha, exponent, clamp_min
         ctx.save_for_backward(theta, deg)
         return norm
 
@@ -24,12 +25,14 @@ class _WDegNorm(torch.autograd.Function):
     def backward(ctx, d_norm):
         theta, deg = ctx.saved_tensors
         d_theta = ops.wdeg_norm_bwd(ctx.graph.csr(), ctx.etv[0], theta, ctx.alpha, ctx.exponent, deg,
-                                    d_norm.contiguous(), counts=ctx.etv[2] if len(ctx.etv) > 2 else None)
-        return None, None, d_theta.view_as(theta), None, None
+                                    d_norm.contiguous(), counts=ctx.etv[2] if len(ctx.etv) > 2 else None,
+                                    clamp_min=ctx.clamp_min)
+        return None, None, d_theta.view_as(theta), None, None, None
 
 
-def weighted_degree_norm(graph, etv, theta, alpha, exponent=-0.5):
-    return _WDegNorm.apply(graph, etv, theta, alpha, exponent)
+def weighted_degree_norm(graph, etv, theta, alpha, exponent=-0.5, clamp_min=1.0):
+    """norm = max(deg, clamp_min) ** exponent; ``clamp_min <= 0`` = no clamp (0 for rows without in-edges)."""
+    return _WDegNorm.apply(graph, etv, theta, alpha, exponent, clamp_min)
 
 
 class _Propagate(torch.autograd.Function):

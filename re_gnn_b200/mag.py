@@ -43,16 +43,22 @@ class REGCNConv(nn.Module):
         if self.use_norm in ('bn', 'ln'):
             self.norm.reset_parameters()
 
-    def forward(self, x, edge_index, edge_type, target_node_type, return_weights=False):
-        x_src, x_target = x
-        n_src, n_dst = x_src.shape[0], x_target.shape[0]
+    def build_block(self, edge_index, edge_type, target_node_type, n_src, n_dst):
+        """Graph + 1-based edge types of one message-passing block, with the typed self loops of
+        ``self_loop_type == 2`` appended (:90-96).  Reusable across calls on the same block (inference)."""
         src, dst = edge_index[0], edge_index[1]
-        if self.self_loop_type == 2:   # one typed self loop per target node (:90-96)
+        if self.self_loop_type == 2:
             loop = torch.arange(n_dst, dtype=src.dtype, device=src.device)
             src, dst = torch.cat([src, loop]), torch.cat([dst, loop])
             edge_type = torch.cat([edge_type, target_node_type + self.num_edge_types])
-        graph = Graph(src, dst, n_src)
-        etv = graph.etype_views(edge_type + 1, self.relation_weight.numel())
+        return Graph(src, dst, n_src), (edge_type + 1).contiguous()
+
+    def forward(self, x, edge_index, edge_type, target_node_type, return_weights=False, block=None):
+        x_src, x_target = x
+        n_src, n_dst = x_src.shape[0], x_target.shape[0]
+        graph, etype1 = block if block is not None else self.build_block(edge_index, edge_type, target_node_type,
+                                                                         n_src, n_dst)
+        etv = graph.etype_views(etype1, self.relation_weight.numel())
         xs = x_src @ self.weight
         # aggr='mean': divide by the NUMBER of in-edges (incl. the appended loops); rows without edges give 0
         inv_cnt = 1.0 / graph.in_degrees().clamp(min=1).to(xs.dtype)
@@ -104,6 +110,20 @@ class REGNN(nn.Module):
             x = self.convs[i]((x, x_target), edge_index, edge_type[e_id], node_type)
             x = F.dropout(F.relu(x), p=self.dropout, training=self.training)
         return self.out_lin(x).log_softmax(dim=-1)
+
+
+@torch.no_grad()
+def full_graph_inference(model, x_dict, edge_index, edge_type, node_type, local_node_idx):
+    """Layer-wise full-neighbour inference (mag/regnn_ns.py:348-369) without leaving the device: the reference
+    walks ``NeighborSampler(sizes=[-1])`` batches and bounces activations through host memory per layer; with
+    every node as a target and all its in-edges, that is one full-graph convolution per layer.  The CSR (with
+    the typed self loops) is built once and shared by all layers."""
+    n = node_type.numel()
+    x = model.group_input(x_dict, node_type, local_node_idx)
+    block = model.convs[0].build_block(edge_index, edge_type, node_type, n, n)
+    for conv in model.convs:
+        x = F.relu(conv((x, x), edge_index, edge_type, node_type, block=block))
+    return model.out_lin(x)
 
 
 def allreduce_gradients(params, world_size, group=None):

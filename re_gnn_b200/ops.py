@@ -31,7 +31,7 @@ def _rows(rows, n):
     return (0, n) if rows is None else (int(rows[0]), int(rows[1]))
 
 
-def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None, counts=None):
+def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None, counts=None, clamp_min=1.0):
     """deg[v] = sum_in w[etype], norm = max(deg,1)^exponent -> (deg[N], norm[N]).
     ``counts``: the per-(row, relation) in-edge counts of this e_feat (Graph.etype_views()[2])."""
     theta = _f32(theta).view(-1)
@@ -41,12 +41,12 @@ def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None, counts=None):
     norm = torch.empty(n, dtype=torch.float32, device=theta.device)
     with torch.cuda.device(theta.device):
         _lib.call('regnn_wdeg_norm_fwd', _ptr(csr['indptr']), _ptr(et_csr), _ptr(counts), _ptr(theta), float(alpha),
-                  theta.numel(), float(exponent), rb, re, _ptr(deg), _ptr(norm), _stream())
+                  theta.numel(), float(exponent), float(clamp_min), rb, re, _ptr(deg), _ptr(norm), _stream())
         _lib.count_launches(1)
     return deg, norm
 
 
-def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None, counts=None):
+def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None, counts=None, clamp_min=1.0):
     theta = _f32(theta).view(-1)
     d_norm = _f32(d_norm)
     n = csr['indptr'].numel() - 1
@@ -56,7 +56,8 @@ def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None, c
     d_theta = torch.empty(r, dtype=torch.float32, device=theta.device)
     with torch.cuda.device(theta.device):
         _lib.call('regnn_wdeg_norm_bwd', _ptr(csr['indptr']), _ptr(et_csr), _ptr(counts), _ptr(theta), float(alpha), r,
-                  float(exponent), rb, re, _ptr(deg), _ptr(d_norm), _ptr(partials), _ptr(d_theta), _stream())
+                  float(exponent), float(clamp_min), rb, re, _ptr(deg), _ptr(d_norm), _ptr(partials), _ptr(d_theta),
+                  _stream())
         _lib.count_launches(2)
     return d_theta
 

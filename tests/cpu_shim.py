@@ -47,16 +47,24 @@ def graph_etype_views(self, e_feat, num_relations):
     return torch.as_tensor(a), torch.as_tensor(b), None
 
 
-def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None, counts=None):
+def wdeg_norm_fwd(csr, et_csr, theta, alpha, exponent, rows=None, counts=None, clamp_min=1.0):
     w = _w(theta.detach().view(-1), alpha)
     n = csr['indptr'].numel() - 1
     deg = torch.zeros(n, dtype=w.dtype).index_add(0, csr['row'].long(), w[et_csr.long()])
-    return deg, deg.clamp(min=1) ** exponent
+    if clamp_min > 0:
+        return deg, deg.clamp(min=clamp_min) ** exponent
+    safe = torch.where(deg == 0, torch.ones_like(deg), deg)
+    return deg, torch.where(deg == 0, torch.zeros_like(deg), safe ** exponent)
 
 
-def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None, counts=None):
+def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None, counts=None, clamp_min=1.0):
     th = theta.detach().view(-1)
-    dd = torch.where(deg >= 1, exponent * deg.clamp(min=1) ** (exponent - 1) * d_norm, torch.zeros_like(deg))
+    if clamp_min > 0:
+        dd = torch.where(deg >= clamp_min, exponent * deg.clamp(min=clamp_min) ** (exponent - 1) * d_norm,
+                         torch.zeros_like(deg))
+    else:
+        safe = torch.where(deg == 0, torch.ones_like(deg), deg)
+        dd = torch.where(deg != 0, exponent * safe ** (exponent - 1) * d_norm, torch.zeros_like(deg))
     dw = torch.zeros_like(th).index_add(0, et_csr.long(), dd[csr['row'].long()])
     return dw * alpha * _lgrad(th * alpha, SLOPE)
 

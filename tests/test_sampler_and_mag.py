@@ -59,3 +59,45 @@ def test_mag_regcn_layer_matches_oracle(cpu_ops):
         assert torch.allclose(x.grad, xr.grad, rtol=1e-9, atol=1e-12)
         for k, v in conv.named_parameters():
             assert torch.allclose(v.grad, p[k].grad, rtol=1e-9, atol=1e-11), k
+
+
+def test_edge_types_from_matrix_matches_reference_loop():
+    import scipy.sparse as sp
+    from re_gnn_b200 import Graph
+    from re_gnn_b200.utils import edge_types_from_matrix
+    rng = np.random.RandomState(3)
+    n = 30
+    u, v = rng.randint(0, n, 120), rng.randint(0, n, 120)
+    keep = u != v
+    pairs = np.unique(np.stack([u[keep], v[keep]], 1), axis=0)
+    types = rng.randint(1, 6, len(pairs))
+    adj = sp.coo_matrix((np.ones(len(pairs)), (pairs[:, 0], pairs[:, 1])), shape=(n, n))
+    g = Graph(adj).remove_self_loop().add_self_loop()
+    tm = sp.lil_matrix((n, n), dtype=np.int64)
+    for (a, b), t in zip(pairs, types):
+        tm[a, b] = t
+    for i in range(n):
+        tm[i, i] = 6 + i % 3                      # self loops typed by node type (run_regnn.py: adjMM_wsl_2)
+    got = edge_types_from_matrix(g, tm)
+    s, d = g.edges()
+    want = [tm[(int(a), int(b))] for a, b in zip(s.tolist(), d.tolist())]   # the reference's loop, verbatim semantics
+    assert got.tolist() == want
+
+
+def test_full_graph_inference_equals_layerwise_forward(cpu_ops):
+    from re_gnn_b200 import mag
+    torch.manual_seed(1)
+    d = synth.random_multigraph(60, 400, 4, seed=5, self_loops=False)
+    n, net, nnt = 60, 4, 3
+    ei = torch.as_tensor(np.stack([d['src'], d['dst']]))
+    et0 = torch.as_tensor(d['etype'] - 1)
+    node_type = torch.as_tensor(np.arange(n) % nnt)
+    local_idx = torch.as_tensor(np.arange(n) // nnt)
+    x_dict = {k: torch.randn(n // nnt, 6) for k in range(nnt)}
+    model = mag.REGNN(6, 8, 5, 1, 2, 100.0, 0.0, {k: 6 for k in range(nnt)}, net, residual=True, no_re=False).eval()
+    out = mag.full_graph_inference(model, x_dict, ei, et0, node_type, local_idx)
+    # the same through the training-style forward with "sample everything" blocks
+    n_id = torch.arange(n)
+    adjs = [(ei, torch.arange(ei.shape[1]), (n, n))] * 2
+    ref = model(n_id, x_dict, adjs, et0, node_type, local_idx)
+    assert torch.allclose(out.log_softmax(-1), ref, rtol=1e-5, atol=1e-6)
