@@ -35,7 +35,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='mag_regcn', choices=['mag_regcn', 'mag_ns'])
+    ap.add_argument('--workload', default='mag_regcn', choices=['mag_regcn', 'mag_ns', 'mag_saint'])
     ap.add_argument('--feat', type=int, default=FEAT)
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
     ap.add_argument('--no-others', action='store_true', help='skip the secondary HGB-shaped workloads')
@@ -514,6 +514,82 @@ def run_ns(args, d):
         dist.destroy_process_group()
 
 
+def run_saint(args, d):
+    """BASELINE config 5, GraphSAINT variant: 20 000 random-walk roots x walk length 2 per step, RE-GCN (SAINT flavour)
+    with hidden 128, 2 layers, batch norm + residual (mag/regnn_saint.py:37-46,185-190), data-parallel, one gradient
+    all-reduce per step.  Weak scaling.  value = subgraph edges processed / s."""
+    import torch.distributed as dist
+    from re_gnn_b200 import Graph, _lib, mag
+    from re_gnn_b200.sampling import SaintRandomWalkSampler
+    world, rank, local = (int(os.environ.get(k, '0' if k != 'WORLD_SIZE' else '1')) for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    sync = torch.cuda.synchronize
+    barrier = (lambda: dist.barrier()) if world > 1 else None
+    n, net, sizes = d['num_nodes'], d['num_etype'], d['type_sizes']
+    nnt = len(sizes)
+    g = Graph(d['src'][:-n], d['dst'][:-n], n).to(dev)
+    g.csr()
+    edge_type0 = (torch.as_tensor(d['etype'][:-n]) - 1).to(dev)
+    node_type = torch.as_tensor(d['ntype']).to(dev)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    local_idx = torch.as_tensor(np.arange(n) - offs[d['ntype']]).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    x_dict = {k: torch.randn(sizes[k], 128, device=dev, generator=gen) for k in range(nnt)}
+    labels = torch.randint(0, 349, (n,), device=dev, generator=gen)
+    train_mask = (node_type == 0) & (local_idx < int(sizes[0] * 0.855))
+    torch.manual_seed(123)
+    model = mag.SaintREGCN(128, 128, 349, 2, ALPHA, 0.5, {k: 128 for k in range(nnt)}, net, use_bn=True, residual=True,
+                           gcn=False).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3)
+    sampler = SaintRandomWalkSampler(g, roots=20000, walk_length=2, seed=123, rank=rank)
+    loss_h = torch.empty(1).pin_memory()
+    state = {'i': 0, 'edges': 0}
+
+    def step():
+        loss, ne = mag.saint_train_step(model, opt, sampler, labels, train_mask, x_dict, edge_type0, node_type, local_idx,
+                                        epoch=0, batch=state['i'], world_size=world)
+        loss_h.copy_(loss.view(1), non_blocking=True)
+        state['i'] += 1
+        state['edges'] += ne
+
+    clk = ClockSampler(local)
+    clk.start()
+    l0 = _lib.launch_count
+    for _ in range(args.warmup):
+        step()
+    state['edges'] = 0
+    total = timed(step, args.steps, 0, sync, barrier)
+    clocks = clk.stop()
+    launches = (_lib.launch_count - l0) * args.steps // (args.steps + args.warmup)
+    all_edges = float(state['edges'])
+    if world > 1:
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        es = torch.tensor([all_edges], device=dev, dtype=torch.float64)
+        dist.all_reduce(es, op=dist.ReduceOp.SUM)
+        total, all_edges = float(t.item()), float(es.item())
+    if rank == 0:
+        val = all_edges / total / 1e9
+        print(json.dumps({
+            'metric': 'GTEPS (subgraph edges) per GraphSAINT train step, data-parallel', 'value': val, 'unit': 'GTEPS',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'RE-GCN GraphSAINT random-walk minibatch training, BASELINE config 5',
+                       'roots_per_rank': 20000, 'walk_length': 2, 'hidden': 128, 'classes': 349,
+                       'subgraph_edges_per_step': all_edges / args.steps,
+                       'l2': 'every step touches a new random subgraph; feature tables (993 MB) exceed L2'},
+            'clocks': clocks,
+            'e2e': {'value': val, 'unit': 'GTEPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 4,
+                    'note': 'sampling starts from counter-based keys on the device; the loss is copied to the host every step'},
+            'gpu_launches': int(launches), 'steps_per_s': args.steps / total * world}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', '0'))
@@ -525,6 +601,8 @@ def main():
         run_reference(args, d)
     elif args.workload == 'mag_ns':
         run_ns(args, d)
+    elif args.workload == 'mag_saint':
+        run_saint(args, d)
     else:
         run_ours(args, d)
 

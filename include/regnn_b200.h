@@ -262,6 +262,13 @@ int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const
 int regnn_sample_neighbors(const int32_t* indptr, const int64_t* targets, int64_t num_targets, int fanout,
                            uint64_t key, int32_t* out_slot, void* stream);
 
+/* GraphSAINT random-walk roots (replaces torch_sparse `random_walk` behind
+ * `GraphSAINTRandomWalkSampler(data, batch_size=20000, walk_length=2, ...)`, mag/regnn_saint.py:185-190):
+ * root i starts at node hash(key, i) % N and takes `walk_length` steps along out-edges of the transposed view;
+ * walks[i*(walk_length+1) + s] is the node after s steps.  Counter-based, bit-exact with the oracle. */
+int regnn_random_walk(const int32_t* indptr_t, const int32_t* indices_t, int64_t num_nodes, int64_t num_roots,
+                      int walk_length, uint64_t key, int64_t* walks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

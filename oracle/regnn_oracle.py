@@ -225,3 +225,14 @@ def mag_regcn_forward(x_src, x_target, edge_index, edge_type, target_node_type, 
     if residual:
         out = out + x_target @ weight                                             # weight_root aliases weight (:50)
     return out
+
+
+def saint_regcn_forward(x, edge_index, edge_type, weight, bias, relation_weight, scaling_factor):
+    """mag/regnn_saint.py:224-275 (``REGCNConv.forward``, ``aggr='add'``, dropout 0, use_softmax False)."""
+    src, dst = edge_index[0], edge_index[1]
+    n = x.shape[0]
+    xs = x @ weight                                                               # :234-236
+    w = F.leaky_relu(relation_weight * scaling_factor, RELATION_SLOPE)[edge_type]  # :239-242
+    deg = torch.zeros(n, dtype=x.dtype).index_add(0, dst, w)                      # :253 weighted_degree
+    ew = w * deg.pow(-1.0)[dst]                                                   # :254-256
+    return torch.zeros((n, xs.shape[1]), dtype=x.dtype).index_add(0, dst, ew.view(-1, 1) * xs[src]) + bias

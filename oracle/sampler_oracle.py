@@ -87,3 +87,40 @@ def sample_blocks(csr, seeds, fanouts, seed=0, epoch=0, rank=0, batch=0):
         blocks.append((src_local, dst_local, e, len(new_n_id), t))
         n_id = new_n_id
     return n_id, blocks[::-1]
+
+
+# ---- GraphSAINT random-walk sampler (mag/regnn_saint.py:185-190) ---------------------------------------------
+def random_walks(csr, num_nodes, num_roots, walk_length, key):
+    """int64 [num_roots, walk_length+1]; bit-exact spec of regnn_random_walk."""
+    key_lo, key_hi = key & M32, (key >> 32) & M32
+    indptr_t, indices_t = np.asarray(csr['indptr_t']), np.asarray(csr['indices_t'])
+    out = np.zeros((num_roots, walk_length + 1), dtype=np.int64)
+    for i in range(num_roots):
+        cur = mix32(key_lo ^ mix32((i * 0x9E3779B1 + key_hi) & M32)) % num_nodes
+        out[i, 0] = cur
+        for step in range(1, walk_length + 1):
+            t0, deg = int(indptr_t[cur]), int(indptr_t[cur + 1] - indptr_t[cur])
+            if deg > 0:
+                r = mix32(key_hi ^ mix32((i * 0x85EBCA6B + step * 0xC2B2AE35 + key_lo) & M32))
+                cur = int(indices_t[t0 + r % deg])
+            out[i, step] = cur
+    return out
+
+
+def saint_subgraph(csr, num_nodes, num_roots, walk_length, seed=0, epoch=0, rank=0, batch=0):
+    """Node-induced subgraph of the nodes visited by the walks: (n_id sorted ascending, src_local, dst_local, eid),
+    edges ordered by (destination position in n_id, CSR slot)."""
+    walks = random_walks(csr, num_nodes, num_roots, walk_length, layer_key(seed, epoch, rank, batch, 0x5A1))
+    n_id = np.unique(walks.reshape(-1))
+    indptr, indices, eid = (np.asarray(csr[k]) for k in ('indptr', 'indices', 'eid'))
+    relabel = np.full(num_nodes, -1, dtype=np.int64)
+    relabel[n_id] = np.arange(len(n_id))
+    src_l, dst_l, es = [], [], []
+    for j, v in enumerate(n_id.tolist()):
+        sl = np.arange(indptr[v], indptr[v + 1])
+        keep = relabel[indices[sl]] >= 0
+        src_l.append(relabel[indices[sl][keep]])
+        dst_l.append(np.full(int(keep.sum()), j, dtype=np.int64))
+        es.append(eid[sl][keep].astype(np.int64))
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, dtype=np.int64)  # noqa: E731
+    return n_id, cat(src_l), cat(dst_l), cat(es)

@@ -33,6 +33,7 @@ SIGNATURES = {
     'regnn_spmm_bwd_fused': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i64,
                                     _i32, _p, _p, _p, _p, _p, _p]),
     'regnn_rowdot_norm_bwd': (_i32, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p]),
+    'regnn_random_walk': (_i32, [_p, _p, _i64, _i64, _i32, ctypes.c_uint64, _p, _p]),
     'regnn_sample_neighbors': (_i32, [_p, _p, _i64, _i32, ctypes.c_uint64, _p, _p]),
     'regnn_gat_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
                              _p, _p, _p, _p, _p, _p, _p]),

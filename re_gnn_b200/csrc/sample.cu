@@ -69,3 +69,37 @@ extern "C" int regnn_sample_neighbors(const int32_t* indptr, const int64_t* targ
       indptr, targets, num_targets, fanout, (uint32_t)(key & 0xffffffffu), (uint32_t)(key >> 32), out_slot);
   return check_launch("regnn_sample_neighbors");
 }
+
+// ---- GraphSAINT random-walk roots (mag/regnn_saint.py:185-190: GraphSAINTRandomWalkSampler) ---------------
+// One thread per root: `walk_length` steps along OUT-edges (transposed view), the next hop chosen by a
+// counter-based hash -- no RNG state, bit-exact with oracle/sampler_oracle.py::random_walks.  A node without
+// out-edges keeps the walker in place (torch_sparse's behaviour for dangling nodes).
+namespace regnn {
+__global__ void random_walk_kernel(const int32_t* __restrict__ indptr_t, const int32_t* __restrict__ indices_t,
+                                   int64_t num_nodes, int64_t num_roots, int walk_length, uint32_t key_lo,
+                                   uint32_t key_hi, int64_t* __restrict__ walks) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_roots) return;
+  int64_t cur = (int64_t)(mix32(key_lo ^ mix32((uint32_t)i * 0x9E3779B1u + key_hi)) % (uint32_t)num_nodes);
+  walks[i * (walk_length + 1)] = cur;
+  for (int step = 1; step <= walk_length; ++step) {
+    const int32_t t0 = indptr_t[cur];
+    const uint32_t deg = (uint32_t)(indptr_t[cur + 1] - t0);
+    if (deg > 0) {
+      const uint32_t r = mix32(key_hi ^ mix32((uint32_t)i * 0x85EBCA6Bu + (uint32_t)step * 0xC2B2AE35u + key_lo));
+      cur = indices_t[t0 + (int32_t)(r % deg)];
+    }
+    walks[i * (walk_length + 1) + step] = cur;
+  }
+}
+}  // namespace regnn
+
+extern "C" int regnn_random_walk(const int32_t* indptr_t, const int32_t* indices_t, int64_t num_nodes,
+                                 int64_t num_roots, int walk_length, uint64_t key, int64_t* walks, void* stream) {
+  REGNN_REQUIRE(indptr_t && walks && num_nodes > 0 && num_nodes < 0xffffffffLL, REGNN_ERR_INVALID_ARG, "random_walk: bad arguments");
+  REGNN_REQUIRE(walk_length >= 0 && num_roots >= 0, REGNN_ERR_INVALID_ARG, "random_walk: negative size");
+  if (num_roots == 0) return REGNN_OK;
+  regnn::random_walk_kernel<<<(unsigned)((num_roots + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      indptr_t, indices_t, num_nodes, num_roots, walk_length, (uint32_t)(key & 0xffffffffu), (uint32_t)(key >> 32), walks);
+  return regnn::check_launch("regnn_random_walk");
+}

@@ -155,3 +155,98 @@ def train_step(model, optimizer, sampler, seeds, labels, x_dict, edge_type, node
     allreduce_gradients(list(model.parameters()), world_size)
     optimizer.step()
     return loss.detach(), sum(int(b.src.numel()) for b in blocks)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GraphSAINT variant (mag/regnn_saint.py)
+class SaintREGCNConv(nn.Module):
+    """``REGCNConv`` of mag/regnn_saint.py:195-275: ``aggr='add'`` with the relation weights normalised by the
+    relation-WEIGHTED in-degree, ``ew = w[etype] / deg[dst]`` (no clamp), bias added after aggregation.  The
+    model never passes ``dropout`` to the layer (:303-307), so the edge-weight dropout is inactive; a non-zero
+    value in training mode is rejected rather than silently ignored."""
+
+    def __init__(self, in_channels, out_channels, num_node_types, num_edge_types, scaling_factor=100., gcn=False,
+                 dropout=0., use_softmax=False):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_node_types, self.num_edge_types = num_node_types, num_edge_types
+        self.use_softmax, self.dropout, self.scaling_factor = use_softmax, dropout, scaling_factor
+        self.weight = nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        self.relation_weight = nn.Parameter(torch.empty(num_edge_types), requires_grad=not gcn)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.weight)
+        nn.init.zeros_(self.bias)
+        nn.init.constant_(self.relation_weight, 1.0 / self.scaling_factor)
+
+    def forward(self, x, edge_index, edge_type, return_weights=False, graph=None):
+        if self.use_softmax:
+            raise NotImplementedError('use_softmax=True (global-max softmax of mag/utils.py:28-57) is not built')
+        if self.training and self.dropout > 0:
+            raise NotImplementedError('edge-weight dropout is not built (the reference model leaves it at 0)')
+        x_src, x_target = x if isinstance(x, tuple) else (x, x)
+        n_src, n_dst = x_src.shape[0], x_target.shape[0]
+        if graph is None:
+            graph = Graph(edge_index[0], edge_index[1], n_src)
+        etv = graph.etype_views(edge_type + 1, self.num_edge_types)
+        theta = self.relation_weight.view(-1, 1)
+        inv_deg = RF.weighted_degree_norm(graph, etv, theta, self.scaling_factor, -1.0, clamp_min=0.0)
+        out = RF.propagate(graph, etv, x_src @ self.weight, theta, self.scaling_factor, inv_deg, sides=2)
+        return out[:n_dst] + self.bias
+
+
+class SaintREGCN(nn.Module):
+    """``REGCN`` of mag/regnn_saint.py:278-361 (full-subgraph forward)."""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, scaling_factor, dropout,
+                 num_feature_dict, num_edge_types, use_bn, residual, gcn):
+        super().__init__()
+        self.in_channels, self.hidden_channels, self.out_channels = in_channels, hidden_channels, out_channels
+        self.num_layers, self.dropout, self.use_bn, self.residual = num_layers, dropout, use_bn, residual
+        self.num_node_types, self.num_edge_types = len(num_feature_dict), num_edge_types
+        self.lins = nn.ModuleDict({str(k): nn.Linear(d, hidden_channels) for k, d in num_feature_dict.items()})
+        dims = [hidden_channels] * num_layers + [out_channels]
+        self.convs = nn.ModuleList([
+            SaintREGCNConv(dims[i], dims[i + 1] if i == num_layers - 1 else hidden_channels, self.num_node_types,
+                           num_edge_types, scaling_factor, gcn) for i in range(num_layers)])
+        self.bns = nn.ModuleList([nn.BatchNorm1d(hidden_channels) for _ in range(num_layers)])
+
+    def group_input(self, x_dict, node_type, local_node_idx, n_id=None):
+        if n_id is not None:
+            node_type, local_node_idx = node_type[n_id], local_node_idx[n_id]
+        h = torch.zeros((node_type.size(0), self.hidden_channels), device=node_type.device)
+        for key, x in x_dict.items():
+            mask = node_type == key
+            h[mask] = self.lins[str(key)](x[local_node_idx[mask]])
+        return h
+
+    def forward(self, x_dict, edge_index, edge_type, node_type, local_node_idx):
+        x = self.group_input(x_dict, node_type, local_node_idx)
+        graph = Graph(edge_index[0], edge_index[1], x.shape[0])     # one CSR for all layers of this subgraph
+        for layer, conv in enumerate(self.convs):
+            x_pre = x
+            x = conv(x, edge_index, edge_type, graph=graph)
+            if layer != self.num_layers - 1:
+                if self.residual:
+                    x = x + x_pre
+                if self.use_bn:
+                    x = self.bns[layer](x)
+                x = F.dropout(F.relu(x), p=self.dropout, training=self.training)
+        return x.log_softmax(dim=-1)
+
+
+def saint_train_step(model, optimizer, sampler, labels, train_mask, x_dict, edge_type, node_type, local_node_idx,
+                     epoch, batch, world_size=1):
+    """One GraphSAINT training step (mag/regnn_saint.py:427-443 + gradient all-reduce): loss on the training nodes
+    of the sampled subgraph.  Returns (loss, number of subgraph edges)."""
+    n_id, edge_index, eid = sampler.sample(epoch=epoch, batch=batch)
+    optimizer.zero_grad(set_to_none=True)
+    out = model(x_dict, edge_index, edge_type[eid], node_type[n_id], local_node_idx[n_id])
+    mask = train_mask[n_id]
+    loss = F.nll_loss(out[mask], labels[n_id][mask])
+    loss.backward()
+    allreduce_gradients(list(model.parameters()), world_size)
+    optimizer.step()
+    return loss.detach(), int(edge_index.shape[1])

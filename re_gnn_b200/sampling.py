@@ -89,3 +89,43 @@ class NeighborSampler:
             blocks.append(Block(pos[inv[t:]], dst_local, eid, new_n_id.numel(), t))
             n_id = new_n_id
         return n_id, blocks[::-1]
+
+
+class SaintRandomWalkSampler:
+    """GraphSAINT random-walk sampler (``GraphSAINTRandomWalkSampler(data, batch_size=roots, walk_length=...)``,
+    mag/regnn_saint.py:185-190; ``sample_coverage=0`` so no normalisation statistics): ``roots`` random start
+    nodes, ``walk_length`` steps along out-edges (``regnn_random_walk``), then the subgraph INDUCED by the visited
+    nodes.  Returns ``(n_id, edge_index_local [2,E'], eid)`` with ``n_id`` sorted ascending."""
+
+    def __init__(self, graph: Graph, roots, walk_length, seed=0, rank=0):
+        self.graph, self.roots, self.walk_length = graph, int(roots), int(walk_length)
+        self.seed, self.rank = int(seed), int(rank)
+
+    def walks(self, key):
+        csr = self.graph.csr()
+        dev = csr['indptr'].device
+        out = torch.empty((self.roots, self.walk_length + 1), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call('regnn_random_walk', ctypes.c_void_p(csr['indptr_t'].data_ptr()),
+                      ctypes.c_void_p(csr['indices_t'].data_ptr()), self.graph.number_of_nodes(), self.roots,
+                      self.walk_length, ctypes.c_uint64(key), ctypes.c_void_p(out.data_ptr()),
+                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _lib.count_launches(1)
+        return out
+
+    def sample(self, epoch=0, batch=0):
+        csr = self.graph.csr()
+        n = self.graph.number_of_nodes()
+        dev = csr['indptr'].device
+        n_id = torch.unique(self.walks(layer_key(self.seed, epoch, self.rank, batch, 0x5A1)).view(-1))
+        relabel = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        relabel[n_id] = torch.arange(n_id.numel(), device=dev)
+        indptr = csr['indptr'].to(torch.int64)
+        starts, degs = indptr[n_id], indptr[n_id + 1] - indptr[n_id]
+        total = int(degs.sum().item())
+        first = torch.cumsum(degs, 0) - degs
+        slot = torch.repeat_interleave(starts - first, degs) + torch.arange(total, device=dev)
+        dst_local = torch.repeat_interleave(torch.arange(n_id.numel(), device=dev), degs)
+        src_local = relabel[csr['indices'][slot].to(torch.int64)]
+        keep = src_local >= 0
+        return n_id, torch.stack([src_local[keep], dst_local[keep]]), csr['eid'][slot[keep]].to(torch.int64)

@@ -281,9 +281,16 @@ def sampler_sample_slots(self, targets, fanout, key):
     return torch.as_tensor(sampler_oracle.sample_slots(self.graph.csr()['indptr'].numpy(), targets.numpy(), fanout, key))
 
 
+def saint_walks(self, key):
+    from oracle import sampler_oracle
+    csr = {k: v.numpy() for k, v in self.graph.csr().items() if torch.is_tensor(v)}
+    return torch.as_tensor(sampler_oracle.random_walks(csr, self.graph.number_of_nodes(), self.roots, self.walk_length, key))
+
+
 def install(monkeypatch):
     from re_gnn_b200 import graph as G, ops, sampling
     monkeypatch.setattr(sampling.NeighborSampler, 'sample_slots', sampler_sample_slots)
+    monkeypatch.setattr(sampling.SaintRandomWalkSampler, 'walks', saint_walks)
     monkeypatch.setattr(G.Graph, 'csr', graph_csr)
     monkeypatch.setattr(G.Graph, 'etype_views', graph_etype_views)
     for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'spmm_bwd_fused', 'rowdot_norm_bwd', 'gat_fwd', 'gat_bwd_dst',

@@ -452,3 +452,53 @@ def test_row_partitioned_kernels_equal_full_run(parts):
         o = ops.gat_fwd(csr, etv[0], th2, 100.0, feat, el, er, 0.2, rows=rows)[0]
         part_out[rows[0]:rows[1]] = o[rows[0]:rows[1]]
     assert torch.equal(part_out, full[0])
+
+
+def test_saint_sampler_bit_exact_and_train_step():
+    from oracle import sampler_oracle as S
+    from re_gnn_b200 import mag
+    from re_gnn_b200.sampling import SaintRandomWalkSampler
+    d = synth.hetero_graph('mag', seed=6, scale=0.01)
+    g = _graph(d)
+    n, net, nnt = d['num_nodes'], d['num_etype'], len(d['type_sizes'])
+    c = csr_oracle.csr_build(d['src'], d['dst'], n)
+    sampler = SaintRandomWalkSampler(g, roots=300, walk_length=2, seed=9, rank=1)
+    for epoch, batch in [(0, 0), (2, 11)]:
+        n_id, ei, eid = sampler.sample(epoch=epoch, batch=batch)
+        w_nid, w_s, w_t, w_e = S.saint_subgraph(c, n, 300, 2, seed=9, epoch=epoch, rank=1, batch=batch)
+        assert np.array_equal(n_id.cpu().numpy(), w_nid)
+        assert np.array_equal(ei[0].cpu().numpy(), w_s) and np.array_equal(ei[1].cpu().numpy(), w_t)
+        assert np.array_equal(eid.cpu().numpy(), w_e)
+    # layer parity on a sampled subgraph (fp32 CUDA vs float64 oracle)
+    rng = np.random.RandomState(3)
+    edge_type0 = (torch.as_tensor(d['etype']) - 1).to(DEV)
+    r_all = d['num_relations']                                   # the synthetic graph stores typed self loops too
+    conv = mag.SaintREGCNConv(32, 16, nnt, r_all, 100.0)
+    conv.relation_weight.data.copy_(helpers.f32_exact(rng.uniform(0.5, 1.5, r_all) / 100.0))
+    p64 = {k: v.detach().double().requires_grad_(True) for k, v in conv.named_parameters()}
+    x64 = helpers.f32_exact(rng.randn(n_id.numel(), 32)).requires_grad_(True)
+    ref = O.saint_regcn_forward(x64, ei.cpu(), edge_type0[eid].cpu(), p64['weight'], p64['bias'], p64['relation_weight'], 100.0)
+    conv = conv.to(DEV)
+    x = x64.detach().to(DEV, torch.float32).requires_grad_(True)
+    out = conv(x, ei, edge_type0[eid])
+    gout = helpers.f32_exact(rng.randn(*ref.shape))
+    out.backward(gout.to(DEV, torch.float32))
+    ref.backward(gout)
+    helpers.assert_close(out.detach().cpu(), ref.detach(), RTOL, 'saint out')
+    helpers.assert_close(x.grad.cpu(), x64.grad, 2 * RTOL, 'saint d_x')
+    for k, v in conv.named_parameters():
+        helpers.assert_close(v.grad.cpu(), p64[k].grad, 5 * RTOL, 'saint d_' + k)
+    # whole pipeline: a few SAINT steps reduce the loss
+    torch.manual_seed(0)
+    offs = np.concatenate([[0], np.cumsum(d['type_sizes'])])
+    node_type = torch.as_tensor(d['ntype']).to(DEV)
+    local_idx = torch.as_tensor(np.arange(n) - offs[d['ntype']]).to(DEV)
+    x_dict = {k: torch.randn(d['type_sizes'][k], 16, device=DEV) for k in range(nnt)}
+    labels = torch.randint(0, 5, (n,), device=DEV)
+    train_mask = node_type == 0
+    model = mag.SaintREGCN(16, 32, 5, 2, 100.0, 0.0, {k: 16 for k in range(nnt)}, r_all, use_bn=True, residual=True,
+                           gcn=False).to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    losses = [float(mag.saint_train_step(model, opt, sampler, labels, train_mask, x_dict, edge_type0, node_type,
+                                         local_idx, epoch=0, batch=0)[0]) for _ in range(15)]
+    assert losses[-1] < 0.8 * losses[0], losses

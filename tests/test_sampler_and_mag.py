@@ -101,3 +101,44 @@ def test_full_graph_inference_equals_layerwise_forward(cpu_ops):
     adjs = [(ei, torch.arange(ei.shape[1]), (n, n))] * 2
     ref = model(n_id, x_dict, adjs, et0, node_type, local_idx)
     assert torch.allclose(out.log_softmax(-1), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_saint_subgraph_oracle_contract():
+    d = synth.random_multigraph(500, 6000, 5, seed=7)
+    c = csr_oracle.csr_build(d['src'], d['dst'], 500)
+    walks = S.random_walks(c, 500, 40, 3, key=0xABCDEF0123)
+    assert walks.shape == (40, 4)
+    for w in walks:                                   # every hop follows an existing out-edge (or stays on a dangling node)
+        for a, b in zip(w[:-1], w[1:]):
+            outs = d['dst'][d['src'] == a]
+            assert (b in outs) or (len(outs) == 0 and a == b)
+    n_id, s, t, e = S.saint_subgraph(c, 500, 40, 3, seed=1, epoch=2, rank=0, batch=5)
+    assert np.all(np.diff(n_id) > 0) and set(np.unique(walks)) != set()      # sorted node ids
+    inset = np.zeros(500, bool)
+    inset[n_id] = True
+    want = np.nonzero(inset[d['src']] & inset[d['dst']])[0]                   # the induced edge set, as edge ids
+    assert np.array_equal(np.sort(e), want)
+    assert np.array_equal(n_id[s], d['src'][e]) and np.array_equal(n_id[t], d['dst'][e])
+
+
+def test_saint_regcn_layer_matches_oracle(cpu_ops):
+    from re_gnn_b200 import mag
+    rng = np.random.RandomState(2)
+    n, e, net = 50, 300, 6
+    dst = rng.randint(0, n - 5, e)                                            # 5 nodes without in-edges
+    ei = torch.as_tensor(np.stack([rng.randint(0, n, e), dst]))
+    et = torch.as_tensor(rng.randint(0, net, e))
+    conv = mag.SaintREGCNConv(8, 5, 3, net, 100.0).double()
+    conv.relation_weight.data.copy_(torch.as_tensor(rng.uniform(0.2, 1.5, net) / 100.0))
+    x = torch.as_tensor(rng.randn(n, 8)).requires_grad_(True)
+    out = conv(x, ei, et)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in conv.named_parameters()}
+    xr = x.detach().clone().requires_grad_(True)
+    ref = O.saint_regcn_forward(xr, ei, et, p['weight'], p['bias'], p['relation_weight'], 100.0)
+    assert torch.allclose(out, ref, rtol=1e-10, atol=1e-12)
+    g = torch.as_tensor(rng.randn(*ref.shape))
+    out.backward(g)
+    ref.backward(g)
+    assert torch.allclose(x.grad, xr.grad, rtol=1e-9, atol=1e-12)
+    for k, v in conv.named_parameters():
+        assert torch.allclose(v.grad, p[k].grad, rtol=1e-8, atol=1e-10), k
