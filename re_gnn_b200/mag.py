@@ -193,8 +193,12 @@ class SaintREGCNConv(nn.Module):
         etv = graph.etype_views(edge_type + 1, self.num_edge_types)
         theta = self.relation_weight.view(-1, 1)
         inv_deg = RF.weighted_degree_norm(graph, etv, theta, self.scaling_factor, -1.0, clamp_min=0.0)
-        out = RF.propagate(graph, etv, x_src @ self.weight, theta, self.scaling_factor, inv_deg, sides=2)
-        return out[:n_dst] + self.bias
+        if self.in_channels < self.out_channels:
+            # aggregation is linear, so A(xW) = (Ax)W: gather the narrower rows (e.g. 128 instead of 349 classes)
+            out = RF.propagate(graph, etv, x_src, theta, self.scaling_factor, inv_deg, sides=2)[:n_dst] @ self.weight
+        else:
+            out = RF.propagate(graph, etv, x_src @ self.weight, theta, self.scaling_factor, inv_deg, sides=2)[:n_dst]
+        return out + self.bias
 
 
 class SaintREGCN(nn.Module):
