@@ -61,7 +61,7 @@ class _Propagate(torch.autograd.Function):
         need_theta = ctx.weighted and ctx.needs_input_grad[3]
         need_norm = ctx.has_norm and ctx.needs_input_grad[5]
         dx = d_theta = d_norm = xdx = None
-        if need_theta and x.shape[1] <= ops.FUSED_BWD_MAX_FEAT:
+        if need_theta and x.shape[1] <= ops.FUSED_BWD_MAX_FEAT and theta.numel() <= ops.FUSED_BWD_MAX_REL:
             # one gather pass over the transposed view: dX, the relation gradient and <X,dX> together
             dx, d_theta, xdx = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x, g, sides=ctx.sides,
                                                   want_xdx=need_norm and bool(ctx.sides & 1))

@@ -134,6 +134,7 @@ def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=
 
 
 FUSED_BWD_MAX_FEAT = 512   # wider rows do not fit the shared-memory tile: two-pass backward instead
+FUSED_BWD_MAX_REL = 160    # relation bins of the fused kernel live in shared memory
 
 
 def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3, xdx=None):
@@ -175,7 +176,7 @@ def gat_fwd(csr, et_csr, theta, alpha, feat, el, er, slope, keep=None, want_attn
     rowmax = torch.zeros((n, h), dtype=torch.float32, device=dev)
     rowsum = torch.zeros((n, h), dtype=torch.float32, device=dev)
     e = csr['indices'].numel()
-    attn = torch.zeros((e, h), dtype=torch.float32, device=dev) if want_attn else None
+    attn = torch.zeros((max(e, 1), h), dtype=torch.float32, device=dev)[:e] if want_attn else None
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
@@ -192,8 +193,8 @@ def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowma
     theta, et_csr, r = _rel(theta, et_csr)
     dev = feat.device
     e = csr['indices'].numel()
-    a_csr = torch.empty((e, h), dtype=torch.float32, device=dev)
-    dpre_csr = torch.empty((e, h), dtype=torch.float32, device=dev)
+    a_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]      # never a null pointer, even for E = 0
+    dpre_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
     d_er = torch.zeros((n, h), dtype=torch.float32, device=dev)
     partials = torch.empty(max(_lib.partial_blocks(re - rb) * r * h, 1), dtype=torch.float64, device=dev)
     d_theta = torch.empty((r, h), dtype=torch.float32, device=dev) if r else None
@@ -233,7 +234,7 @@ def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_at
     rowmax = torch.zeros((n, h), dtype=torch.float32, device=dev)
     rowsum = torch.zeros((n, h), dtype=torch.float32, device=dev)
     e = csr['indices'].numel()
-    att = torch.zeros((e, h), dtype=torch.float32, device=dev) if want_attn else None
+    att = torch.zeros((max(e, 1), h), dtype=torch.float32, device=dev)[:e] if want_attn else None
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gatv2_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
@@ -251,8 +252,8 @@ def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, row
     theta, et_csr, r = _rel(theta, et_csr)
     dev = fs.device
     e = csr['indices'].numel()
-    a_csr = torch.empty((e, h), dtype=torch.float32, device=dev)
-    dl_csr = torch.empty((e, h), dtype=torch.float32, device=dev)
+    a_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
+    dl_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
     d_fd = torch.empty_like(fd) if (rb, re) == (0, n) else torch.zeros_like(fd)
     d_attn = torch.empty(h * d, dtype=torch.float32, device=dev)
     partials = torch.empty(_lib.partial_blocks(re - rb) * (r * h + h * d), dtype=torch.float64, device=dev)

@@ -502,3 +502,54 @@ def test_saint_sampler_bit_exact_and_train_step():
     losses = [float(mag.saint_train_step(model, opt, sampler, labels, train_mask, x_dict, edge_type0, node_type,
                                          local_idx, epoch=0, batch=0)[0]) for _ in range(15)]
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+# ---- degenerate inputs through the whole stack ------------------------------------------------------------
+@pytest.mark.parametrize('n,edges', [(6, 0), (1, 1), (3, 2)])
+def test_empty_and_tiny_graphs_all_layers(n, edges):
+    """E = 0 (no edges at all), a single self loop, rows without in-edges: forward and backward must run and
+    equal the oracle."""
+    rng = np.random.RandomState(n * 10 + edges)
+    src = rng.randint(0, n, edges).astype(np.int64)
+    dst = np.zeros(edges, dtype=np.int64)
+    et = rng.randint(1, 4, edges).astype(np.int64)
+    g = Graph(src, dst, n).to(DEV)
+    s64, d64, e64 = torch.as_tensor(src), torch.as_tensor(dst), torch.as_tensor(et)
+    x64 = helpers.f32_exact(rng.randn(n, 8)).requires_grad_(True)
+    gout = None
+    for kind in ('REGraphConv', 'REMixHopConv', 'REGATConv', 'REGATv2Conv'):
+        if kind == 'REGraphConv':
+            mod = re_gnn_b200.REGraphConv(3, 100.0, 8, 8)
+        elif kind == 'REMixHopConv':
+            mod = re_gnn_b200.REMixHopConv(3, 100.0, 8, 4, p=[0, 1, 2])
+        elif kind == 'REGATConv':
+            mod = re_gnn_b200.REGATConv(3, 100.0, 8, 4, 2)
+        else:
+            mod = re_gnn_b200.REGATv2Conv(3, 100.0, 8, 4, 2, allow_zero_in_degree=True)
+        # move the relation embeddings off their init value: w == 1 puts single-edge rows exactly on the clamp(min=1) kink
+        mod.edge_weight.data.copy_(_theta(3, mod.edge_weight.shape[1], 11))
+        p64 = {k: v.detach().double().requires_grad_(True) for k, v in mod.named_parameters()}
+        xr = x64.detach().clone().requires_grad_(True)
+        if kind == 'REGraphConv':
+            ref = O.regraphconv_forward(s64, d64, e64, n, xr, p64['edge_weight'], 100.0, p64['weight'], p64['bias'])
+        elif kind == 'REMixHopConv':
+            ref = O.remixhop_forward(s64, d64, e64, n, xr, p64['edge_weight'], 100.0,
+                                     {j: p64['weights.%d.weight' % j] for j in (0, 1, 2)}, (0, 1, 2))
+        elif kind == 'REGATConv':
+            ref = O.regat_forward(s64, d64, e64, n, xr, p64['attn_l'], p64['attn_r'], p64['edge_weight'], 100.0, 0.2,
+                                  p64['fc.weight'])
+        else:
+            ref = O.regatv2_forward(s64, d64, e64, n, xr, p64['attn'], p64['edge_weight'], 100.0, 0.2,
+                                    (p64['fc_src.weight'], p64['fc_src.bias']), (p64['fc_dst.weight'], p64['fc_dst.bias']))
+        gout = helpers.f32_exact(rng.randn(*ref.shape))
+        ref.backward(gout)
+        mod = mod.to(DEV)
+        x = x64.detach().to(DEV, torch.float32).requires_grad_(True)
+        out = mod(g, x, e64.to(DEV))
+        out.backward(gout.to(DEV, torch.float32))
+        helpers.assert_close(out.detach().cpu(), ref.detach(), RTOL, kind + ' out')
+        helpers.assert_close(x.grad.cpu(), xr.grad, 2 * RTOL, kind + ' d_x')
+        for k, v in mod.named_parameters():
+            want = p64[k].grad if p64[k].grad is not None else torch.zeros_like(p64[k])
+            got = v.grad if v.grad is not None else torch.zeros_like(v)
+            helpers.assert_close(got.cpu(), want, 2 * RTOL, kind + ' d_' + k)
