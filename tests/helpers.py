@@ -47,7 +47,7 @@ def f32_exact(a):
     return torch.as_tensor(np.asarray(a, dtype=np.float32).astype(np.float64))
 
 
-def assert_close(actual, expected, rtol, name='', max_outlier_frac=0.0):
+def assert_close(actual, expected, rtol, name='', max_outlier_frac=0.0, atol=0.0):
     """Norm-wise relative check used for fp32 results: |a-e| <= rtol * (|e| + max|e|) elementwise.
     (Sums with cancellation make a purely elementwise relative bound meaningless near zero.)
     ``max_outlier_frac``: fraction of elements allowed outside the bound -- only used downstream of a
@@ -60,7 +60,7 @@ def assert_close(actual, expected, rtol, name='', max_outlier_frac=0.0):
     assert torch.isfinite(a).all(), '%s: non-finite values' % name
     scale = e.abs().max().item() if e.numel() else 0.0
     err = (a - e).abs()
-    bound = rtol * (e.abs() + scale) + 1e-30
+    bound = rtol * (e.abs() + scale) + 1e-30 + atol   # atol: for quantities whose exact value is 0 (pure rounding noise)
     ratio = err / bound
     if max_outlier_frac > 0 and e.numel():
         k = int(max_outlier_frac * e.numel())

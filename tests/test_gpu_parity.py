@@ -547,9 +547,10 @@ def test_empty_and_tiny_graphs_all_layers(n, edges):
         x = x64.detach().to(DEV, torch.float32).requires_grad_(True)
         out = mod(g, x, e64.to(DEV))
         out.backward(gout.to(DEV, torch.float32))
-        helpers.assert_close(out.detach().cpu(), ref.detach(), RTOL, kind + ' out')
-        helpers.assert_close(x.grad.cpu(), xr.grad, 2 * RTOL, kind + ' d_x')
+        # several gradients are exactly 0 here (no edges / identical edges): allow fp32 rounding noise around 0
+        helpers.assert_close(out.detach().cpu(), ref.detach(), RTOL, kind + ' out', atol=1e-6)
+        helpers.assert_close(x.grad.cpu(), xr.grad, 2 * RTOL, kind + ' d_x', atol=1e-5)
         for k, v in mod.named_parameters():
             want = p64[k].grad if p64[k].grad is not None else torch.zeros_like(p64[k])
             got = v.grad if v.grad is not None else torch.zeros_like(v)
-            helpers.assert_close(got.cpu(), want, 2 * RTOL, kind + ' d_' + k)
+            helpers.assert_close(got.cpu(), want, 2 * RTOL, kind + ' d_' + k, atol=1e-4 if k == 'edge_weight' else 1e-5)
