@@ -923,7 +923,7 @@ extern "C" int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, cons
                              float* rowsum, float* attn_out, const regnn_rowsplit_t* split, float* split_workspace,
     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && indices && feat && el && er && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gat_fwd: null pointer");
+  REGNN_REQUIRE(indptr && feat && el && er && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gat_fwd: null pointer");
   REGNN_REQUIRE((keep == nullptr && attn_out == nullptr) || eid != nullptr, REGNN_ERR_INVALID_ARG, "gat_fwd: keep/attn_out need eid");
   REGNN_REQUIRE(etype_csr == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "gat_fwd: etype without theta");
   int rc = check_shape("gat_fwd", num_heads, head_dim, num_relations, etype_csr != nullptr, false);
@@ -959,7 +959,7 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
                                  double* partials, float* d_theta, const regnn_rowsplit_t* split, float* split_workspace,
     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && indices && feat && el && er && out && rowmax && rowsum && Gd && a_csr && dpre_csr && d_er,
+  REGNN_REQUIRE(indptr && feat && el && er && out && rowmax && rowsum && Gd && d_er,
                 REGNN_ERR_INVALID_ARG, "gat_bwd_dst: null pointer");
   REGNN_REQUIRE(keep == nullptr || eid != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_dst: keep needs eid");
   REGNN_REQUIRE(etype_csr == nullptr || (theta && partials && d_theta), REGNN_ERR_INVALID_ARG, "gat_bwd_dst: null relation buffers");
@@ -990,7 +990,7 @@ extern "C" int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices
                                  int64_t row_end, float* d_feat, float* d_el, const regnn_rowsplit_t* split, float* split_workspace,
     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr_t && indices_t && slot_t && a_csr && Gd && d_feat, REGNN_ERR_INVALID_ARG, "gat_bwd_src: null pointer");
+  REGNN_REQUIRE(indptr_t && Gd && d_feat, REGNN_ERR_INVALID_ARG, "gat_bwd_src: null pointer");
   REGNN_REQUIRE(dpre_csr == nullptr || d_el != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_src: dpre_csr without d_el");
   int rc = check_shape("gat_bwd_src", num_heads, head_dim, 0, false, false);
   if (rc != REGNN_OK) return rc;
@@ -1022,7 +1022,7 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
                                const regnn_rowsplit_t* split, float* split_workspace,
     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && indices && fs && fd && attn && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gatv2_fwd: null pointer");
+  REGNN_REQUIRE(indptr && fs && fd && attn && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gatv2_fwd: null pointer");
   REGNN_REQUIRE((keep == nullptr && attn_out == nullptr) || eid != nullptr, REGNN_ERR_INVALID_ARG, "gatv2_fwd: keep/attn_out need eid");
   REGNN_REQUIRE(etype_csr == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "gatv2_fwd: etype without theta");
   int rc = check_shape("gatv2_fwd", num_heads, head_dim, num_relations, etype_csr != nullptr, true);
@@ -1057,7 +1057,7 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
                                    float* d_attn, double* partials, float* d_theta, const regnn_rowsplit_t* split, float* split_workspace,
     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && indices && fs && fd && attn && out && rowmax && rowsum && Gd && a_csr && dl_csr && d_fd && d_attn && partials,
+  REGNN_REQUIRE(indptr && fs && fd && attn && out && rowmax && rowsum && Gd && d_fd && d_attn && partials,
                 REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: null pointer");
   REGNN_REQUIRE(keep == nullptr || eid != nullptr, REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: keep needs eid");
   REGNN_REQUIRE(etype_csr == nullptr || (theta && d_theta), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: null relation buffers");
@@ -1092,7 +1092,7 @@ extern "C" int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indic
                                    const regnn_rowsplit_t* split, float* split_workspace,
     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr_t && indices_t && slot_t && a_csr && dl_csr && fs && fd && attn && Gd && d_fs,
+  REGNN_REQUIRE(indptr_t && fs && fd && attn && Gd && d_fs,
                 REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: null pointer");
   int rc = check_shape("gatv2_bwd_src", num_heads, head_dim, 0, false, false);
   if (rc != REGNN_OK) return rc;

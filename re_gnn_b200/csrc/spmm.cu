@@ -1118,7 +1118,7 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
                               int64_t row_end, int feat, const regnn_rowsplit_t* split,
                               float* split_workspace, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && indices && X && Y, REGNN_ERR_INVALID_ARG, "spmm_fwd: null pointer");
+  REGNN_REQUIRE(indptr && X && Y,  /* per-edge arrays may be NULL when E == 0 */ REGNN_ERR_INVALID_ARG, "spmm_fwd: null pointer");
   REGNN_REQUIRE(etype == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd: etype without theta");
   REGNN_REQUIRE(etype == nullptr || (num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS),
                 REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,%d]", num_relations, REGNN_MAX_RELATIONS);
@@ -1153,7 +1153,7 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
                                     float* d_theta, float* xdx, const regnn_rowsplit_t* split_t,
                                     float* split_workspace, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr_t && indices_t && etype_t && theta && X && Gd && dX && partials && d_theta,
+  REGNN_REQUIRE(indptr_t && theta && X && Gd && dX && partials && d_theta,
                 REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: null pointer");
   const int R = num_relations;
   REGNN_REQUIRE(R >= 1 && R <= 160, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,160]", R);
@@ -1221,7 +1221,7 @@ extern "C" int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, c
                                 double* partials, float* d_theta, float* d_norm,
                                 const regnn_rowsplit_t* split, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && indices && X && Y && Gd && dX, REGNN_ERR_INVALID_ARG, "spmm_bwd_w: null pointer");
+  REGNN_REQUIRE(indptr && X && Y && Gd && dX, REGNN_ERR_INVALID_ARG, "spmm_bwd_w: null pointer");
   const bool weighted = etype != nullptr;
   const int R = weighted ? num_relations : 1;
   REGNN_REQUIRE(!weighted || (theta && partials && d_theta), REGNN_ERR_INVALID_ARG, "spmm_bwd_w: null relation buffers");

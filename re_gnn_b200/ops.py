@@ -197,7 +197,7 @@ def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowma
     dpre_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
     d_er = torch.zeros((n, h), dtype=torch.float32, device=dev)
     partials = torch.empty(max(_lib.partial_blocks(re - rb) * r * h, 1), dtype=torch.float64, device=dev)
-    d_theta = torch.empty((r, h), dtype=torch.float32, device=dev) if r else None
+    d_theta = torch.zeros((r, h), dtype=torch.float32, device=dev) if r else None   # stays 0 when the graph has no edges
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
@@ -257,7 +257,7 @@ def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, row
     d_fd = torch.empty_like(fd) if (rb, re) == (0, n) else torch.zeros_like(fd)
     d_attn = torch.empty(h * d, dtype=torch.float32, device=dev)
     partials = torch.empty(_lib.partial_blocks(re - rb) * (r * h + h * d), dtype=torch.float64, device=dev)
-    d_theta = torch.empty((r, h), dtype=torch.float32, device=dev) if r else None
+    d_theta = torch.zeros((r, h), dtype=torch.float32, device=dev) if r else None   # stays 0 when the graph has no edges
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
     with torch.cuda.device(dev):
         _lib.call('regnn_gatv2_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
