@@ -38,6 +38,8 @@ def parse():
     ap.add_argument('--workload', default='mag_regcn', choices=['mag_regcn', 'mag_ns', 'mag_saint'])
     ap.add_argument('--feat', type=int, default=FEAT)
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
+    ap.add_argument('--partition', default='rows', choices=['rows', 'edges'],
+                    help='multi-GPU row blocks: equal rows (even all-gather) or equal in-edge counts')
     ap.add_argument('--no-others', action='store_true', help='skip the secondary HGB-shaped workloads')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -158,7 +160,7 @@ def workload_config(args, d):
     return {'workload': 'REGraphConv RE-layer fwd+bwd, full-batch, synthetic ogbn-mag-shaped graph '
                         '(BASELINE config 4), dst-row-partitioned over --gpus',
             'num_nodes': int(d['num_nodes']), 'num_edges': int(d['src'].size), 'num_relations': int(d['num_relations']),
-            'feat': args.feat, 'graph_scale': args.scale,
+            'feat': args.feat, 'graph_scale': args.scale, 'partition': args.partition,
             'l2': 'inputs larger than L2 (source matrix %.0f MB vs 126 MB L2); no flush needed'
                   % (d['num_nodes'] * args.feat * 4 / 1e6)}
 
@@ -324,7 +326,7 @@ def run_ours(args, d):
             nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5)
             RF.propagate(g, etv, x, theta, ALPHA, nrm).backward(gout)
     else:
-        bounds = partition.row_blocks(csr['indptr'], world)
+        bounds = partition.row_blocks(csr['indptr'], world, balance=args.partition)
         rb, re = bounds[rank], bounds[rank + 1]
         x = x_full[rb:re].clone().requires_grad_(True)
         gout = g_full[rb:re].clone()

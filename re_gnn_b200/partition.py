@@ -18,9 +18,15 @@ import torch.distributed as dist
 from . import ops
 
 
-def row_blocks(indptr, parts):
-    """Row boundaries [r_0=0, ..., r_P=N] with ~equal in-edge counts per block (prefix sums of indptr)."""
+def row_blocks(indptr, parts, balance='edges'):
+    """Row boundaries [r_0=0, ..., r_P=N].  ``balance='edges'``: ~equal in-edge counts per block (prefix sums of
+    indptr), uneven row counts.  ``balance='rows'``: ceil(N/P) rows per block -- compute is less balanced, but the
+    exchange becomes ONE even ``all_gather_into_tensor`` straight into the row-indexed buffer, which is what
+    matters when the step is exchange-bound."""
     n = indptr.numel() - 1
+    if balance == 'rows':
+        per = (n + parts - 1) // parts
+        return [min(n, p * per) for p in range(parts)] + [n]
     e = int(indptr[-1].item())
     targets = torch.arange(1, parts, device=indptr.device, dtype=torch.int64) * e // parts
     cuts = torch.searchsorted(indptr.to(torch.int64), targets)
@@ -30,9 +36,29 @@ def row_blocks(indptr, parts):
     return bounds
 
 
+def _uniform_rows(bounds):
+    parts = len(bounds) - 1
+    per = bounds[1] - bounds[0]
+    return per if per > 0 and all(bounds[p] == min(bounds[-1], p * per) for p in range(parts)) else 0
+
+
+def _alloc_full(n, f, bounds, like):
+    """[N, F] buffer indexed by global row id; over-allocated to P*ceil(N/P) rows for the even all-gather."""
+    per = _uniform_rows(bounds)
+    rows = max(n, per * (len(bounds) - 1)) if per else n
+    return torch.empty((rows, f), dtype=like.dtype, device=like.device)
+
+
 def _all_gather_rows(full, own, bounds, group):
-    """Gathers every rank's row block into ``full`` ([N, F], global row ids).  Blocks are uneven
-    (balanced by edges, not rows); ProcessGroupNCCL handles that with grouped broadcasts."""
+    """Gathers every rank's row block into ``full`` (global row ids).  Equal-size blocks: one
+    ``all_gather_into_tensor``.  Uneven blocks (balanced by edges): ProcessGroupNCCL's grouped broadcasts."""
+    per = _uniform_rows(bounds)
+    if per and dist.get_backend(group) == 'nccl' and full.shape[0] >= per * (len(bounds) - 1):
+        send = own.contiguous()
+        if send.shape[0] != per:      # last block: pad to the common size
+            send = torch.cat([send, send.new_zeros((per - send.shape[0], send.shape[1]))])
+        dist.all_gather_into_tensor(full[:per * (len(bounds) - 1)], send, group=group)
+        return full
     views = [full[bounds[p]:bounds[p + 1]] for p in range(len(bounds) - 1)]
     if dist.get_backend(group) == 'nccl':
         dist.all_gather(views, own.contiguous(), group=group)
@@ -53,7 +79,7 @@ class _PartitionedPropagate(torch.autograd.Function):
         csr = graph.csr()
         n = graph.number_of_nodes()
         rb, re = bounds[rank], bounds[rank + 1]
-        x_full = torch.empty((n, x_own.shape[1]), dtype=x_own.dtype, device=x_own.device)
+        x_full = _alloc_full(n, x_own.shape[1], bounds, x_own)
         _all_gather_rows(x_full, x_own, bounds, group)
         y_full = torch.empty_like(x_full)
         ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, alpha, norm, norm, x_full, rows=(rb, re), out=y_full,

@@ -145,9 +145,9 @@ def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=
 
 
 def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3, xdx=None):
-    x, y, g, dx = x.detach(), y.detach(), g.detach(), dx.detach()
-    n = norm.numel()
-    xd = xdx if xdx is not None else (x * dx).sum(1)
+    n = norm.numel()  # row-indexed buffers may carry padding rows past n (even all-gather layout)
+    x, y, g, dx = x.detach()[:n], y.detach()[:n], g.detach()[:n], dx.detach()[:n]
+    xd = xdx[:n] if xdx is not None else (x * dx).sum(1)
     d = ((y * g).sum(1) * bool(sides & 2) + xd * bool(sides & 1)) / norm.detach()
     if rows is not None:
         own = torch.zeros(n, dtype=torch.bool)

@@ -46,7 +46,7 @@ def _worker(rank, world, port, ret):
     theta0 = torch.as_tensor(rng.uniform(0.5, 1.5, (r, 1)) / 100.0)
     g = Graph(d['src'], d['dst'], n)
     etv = g.etype_views(torch.as_tensor(d['etype']), r)
-    bounds = partition.row_blocks(g.csr()['indptr'], world)
+    bounds = partition.row_blocks(g.csr()['indptr'], world, balance='edges' if port % 2 else 'rows')
     rb, re = bounds[rank], bounds[rank + 1]
     xo = x[rb:re].clone().requires_grad_(True)
     th = theta0.clone().requires_grad_(True)
@@ -77,6 +77,8 @@ def test_row_blocks_balance_edges():
     assert b[0] == 0 and b[-1] == 6 and all(x <= y for x, y in zip(b, b[1:]))
     b4 = partition.row_blocks(indptr, 4)
     assert len(b4) == 5 and b4[-1] == 6
+    assert partition.row_blocks(indptr, 4, balance='rows') == [0, 2, 4, 6, 6]
+    assert partition._uniform_rows([0, 2, 4, 6, 6]) == 2 and partition._uniform_rows(b) in (0, b[1])
 
 
 @pytest.mark.timeout(300)
