@@ -38,8 +38,9 @@ def parse():
     ap.add_argument('--workload', default='mag_regcn', choices=['mag_regcn', 'mag_ns', 'mag_saint'])
     ap.add_argument('--feat', type=int, default=FEAT)
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
-    ap.add_argument('--partition', default='rows', choices=['rows', 'edges'],
-                    help='multi-GPU row blocks: equal rows (even all-gather) or equal in-edge counts')
+    ap.add_argument('--partition', default='rows', choices=['cols', 'rows', 'edges'],
+                    help='multi-GPU scheme: cols = feature-sliced aggregation between all-to-alls; rows / edges = '
+                         'destination-row blocks (equal rows / equal in-edge counts) fed by all-gathers')
     ap.add_argument('--no-others', action='store_true', help='skip the secondary HGB-shaped workloads')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -326,7 +327,8 @@ def run_ours(args, d):
             nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5)
             RF.propagate(g, etv, x, theta, ALPHA, nrm).backward(gout)
     else:
-        bounds = partition.row_blocks(csr['indptr'], world, balance=args.partition)
+        bounds = partition.row_blocks(csr['indptr'], world, balance='edges' if args.partition == 'edges' else 'rows')
+        dist_propagate = partition.feature_sliced_propagate if args.partition == 'cols' else partition.partitioned_propagate
         rb, re = bounds[rank], bounds[rank + 1]
         x = x_full[rb:re].clone().requires_grad_(True)
         gout = g_full[rb:re].clone()
@@ -335,7 +337,7 @@ def run_ours(args, d):
         def step():
             x.grad = theta.grad = None
             nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5)
-            partition.partitioned_propagate(g, etv, x, theta, ALPHA, nrm, bounds, rank).backward(gout)
+            dist_propagate(g, etv, x, theta, ALPHA, nrm, bounds, rank).backward(gout)
             partition.allreduce_relation_grads([theta])
 
     sampler = ClockSampler(local)
@@ -367,7 +369,7 @@ def run_ours(args, d):
         if world == 1:
             out = RF.propagate(g, etv, x_e, theta, ALPHA, nrm)
         else:
-            out = partition.partitioned_propagate(g, etv, x_e, theta, ALPHA, nrm, bounds, rank)
+            out = dist_propagate(g, etv, x_e, theta, ALPHA, nrm, bounds, rank)
         out.backward(g_e)
         if world > 1:
             partition.allreduce_relation_grads([theta])
@@ -394,9 +396,11 @@ def run_ours(args, d):
     hbm, how = peaks()
     with torch.no_grad():
         nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5).detach()
-        xs = x_e.detach() if world == 1 else torch.randn(n, f, device=dev)
-        y = torch.empty(n, f, device=dev)
-        rows = None if world == 1 else (bounds[rank], bounds[rank + 1])
+        sliced = world > 1 and args.partition == 'cols'
+        fk = f // world if sliced else f      # feature-sliced: this rank's launch covers all rows x F/P columns
+        xs = x_e.detach() if world == 1 else torch.randn(n, fk, device=dev)
+        y = torch.empty(n, fk, device=dev)
+        rows = None if world == 1 or sliced else (bounds[rank], bounds[rank + 1])
 
         def k():
             ops.spmm(csr['indptr'], csr['indices'], etv[0], theta.detach(), ALPHA, nrm, nrm, xs, rows=rows, out=y,
@@ -404,13 +408,15 @@ def run_ours(args, d):
         tk = timed(k, 20, 5, sync) / 20
         rows_n = n if rows is None else rows[1] - rows[0]
         edges_n = e if rows is None else int(csr['indptr'][rows[1]].item() - csr['indptr'][rows[0]].item())
-    alg = algorithmic_bytes_spmm(rows_n, edges_n, f)
+    alg = algorithmic_bytes_spmm(rows_n, edges_n, fk)
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp) and world == 1 and args.scale == 1.0 and f == FEAT:
         with open(tp) as fh:
             traffic = json.load(fh).get('spmm_kernel_fwd_mag_f128_bytes')
-    roofline = {'bound': 'hbm', 'kernel': 'regnn::spmm_stream_kernel<1,4,false> (forward launch)', 'achieved': alg / tk / 1e9,
+    vw = 4 if fk >= 96 and fk % 4 == 0 else 2 if fk >= 34 and fk % 2 == 0 else 1
+    kname = 'regnn::spmm_stream_kernel<%d,%d,false> (forward launch)' % (max(1, -(-fk // (32 * vw))), vw)
+    roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': alg / tk / 1e9,
                 'peak': hbm, 'peak_source': how, 'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm, 'traffic': traffic,
                 'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3}
 

@@ -86,7 +86,7 @@ def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None,
         y = y * keep
     if out is not None:
         if rows is None:
-            out.copy_(y)
+            out[:y.shape[0]].copy_(y)   # `out` may carry padding rows
         else:
             out[rows[0]:rows[1]] = y[rows[0]:rows[1]]
         return out

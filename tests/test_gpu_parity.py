@@ -405,6 +405,80 @@ def test_mag_regcn_layer_and_train_step():
     assert losses[-1] < 0.7 * losses[0], losses
 
 
+# ---- feature-sliced (column slab) kernel paths on one GPU: P virtual ranks, each all rows x F/P columns ----
+@pytest.mark.parametrize('parts,f', [(2, 128), (4, 128), (8, 128), (4, 48)])
+def test_column_slab_kernels_equal_full_run(parts, f):
+    from re_gnn_b200 import ops
+    d = synth.hetero_graph('dblp', seed=9, scale=0.3)
+    g, et = _graph(d), torch.as_tensor(d['etype']).to(DEV)
+    n, r = d['num_nodes'], d['num_relations']
+    csr = g.csr()
+    etv = g.etype_views(et, r)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(n, f, device=DEV, generator=gen)
+    gout = torch.randn(n, f, device=DEV, generator=gen)
+    th = _theta(r, 1, 5).to(DEV, torch.float32)
+    _, nrm = ops.wdeg_norm_fwd(csr, etv[0], th, 100.0, -0.5, counts=etv[2])
+    y = ops.spmm(csr['indptr'], csr['indices'], etv[0], th, 100.0, nrm, nrm, x, split=csr.get('split'))
+    dx, dth, xdx = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, x, gout, want_xdx=True)
+    dn = ops.rowdot_norm_bwd(nrm, x, y, gout, dx, xdx=xdx)
+    fc = f // parts
+    pad = 3  # slabs carry padding rows past N, as the all-to-all layout does
+    dth_p = torch.zeros_like(dth, dtype=torch.float64)
+    dn_p = torch.zeros_like(dn, dtype=torch.float64)
+    for p in range(parts):
+        cols = slice(p * fc, (p + 1) * fc)
+        xs = torch.cat([x[:, cols], torch.full((pad, fc), float('nan'), device=DEV)]).contiguous()
+        gs = torch.cat([gout[:, cols], torch.full((pad, fc), float('nan'), device=DEV)]).contiguous()
+        ys, dxs = torch.empty_like(xs), torch.empty_like(xs)
+        ops.spmm(csr['indptr'], csr['indices'], etv[0], th, 100.0, nrm, nrm, xs, out=ys, split=csr.get('split'))
+        _, t, xd = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, xs, gs, out=dxs, want_xdx=True)
+        # per-column sums never mix columns: slabs reproduce the full run bit for bit
+        assert torch.equal(ys[:n], y[:, cols]) and torch.equal(dxs[:n], dx[:, cols])
+        dth_p += t.double()
+        dn_p += ops.rowdot_norm_bwd(nrm, xs, ys, gs, dxs, xdx=xd).double()
+    helpers.assert_close(dth_p.cpu(), dth.double().cpu(), RTOL if DEV != 'cpu' else 10 * RTOL,   # shim sums in fp32
+                         'd_theta (sum of column shares)')
+    helpers.assert_close(dn_p.cpu(), dn.double().cpu(), 10 * RTOL, 'd_norm (sum of column shares)', atol=1e-5)
+
+
+def test_feature_sliced_propagate_world1_nccl():
+    """Single-rank NCCL group: the all-to-all plumbing of partition.feature_sliced_propagate degenerates to copies and
+    the result must equal functional.propagate."""
+    import torch.distributed as dist
+    from re_gnn_b200 import functional as RF, partition
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', str(29400 + os.getpid() % 500))
+        if DEV == 'cpu':
+            dist.init_process_group('gloo', rank=0, world_size=1)
+        else:
+            dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device(DEV))
+    try:
+        d = synth.hetero_graph('acm', seed=4, scale=0.2)
+        g, et = _graph(d), torch.as_tensor(d['etype']).to(DEV)
+        n, r, f = d['num_nodes'], d['num_relations'], 64
+        etv = g.etype_views(et, r)
+        gen = torch.Generator(device=DEV).manual_seed(8)
+        x = torch.randn(n, f, device=DEV, generator=gen)
+        gout = torch.randn(n, f, device=DEV, generator=gen)
+        res = []
+        for fn in (None, partition.feature_sliced_propagate):
+            xs = x.clone().requires_grad_(True)
+            th = _theta(r, 1, 5).to(DEV, torch.float32).requires_grad_(True)
+            nrm = RF.weighted_degree_norm(g, etv, th, 100.0, -0.5)
+            if fn is None:
+                out = RF.propagate(g, etv, xs, th, 100.0, nrm)
+            else:
+                out = fn(g, etv, xs, th, 100.0, nrm, partition.row_blocks(g.csr()['indptr'], 1, balance='rows'), 0)
+            out.backward(gout)
+            res.append((out.detach(), xs.grad, th.grad))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        helpers.assert_close(res[1][2].cpu(), res[0][2].cpu(), RTOL, 'd_theta')
+    finally:
+        dist.destroy_process_group()
+
+
 # ---- row-range (partitioned) kernel paths on one GPU: P virtual ranks, all-gather emulated by sharing buffers ----
 @pytest.mark.parametrize('parts', [2, 5])
 def test_row_partitioned_kernels_equal_full_run(parts):

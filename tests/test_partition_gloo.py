@@ -25,7 +25,7 @@ def _single(d, x, gout, theta0):
     return out.detach(), xs.grad, th.grad
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, mode='rows'):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -46,12 +46,13 @@ def _worker(rank, world, port, ret):
     theta0 = torch.as_tensor(rng.uniform(0.5, 1.5, (r, 1)) / 100.0)
     g = Graph(d['src'], d['dst'], n)
     etv = g.etype_views(torch.as_tensor(d['etype']), r)
-    bounds = partition.row_blocks(g.csr()['indptr'], world, balance='edges' if port % 2 else 'rows')
+    bounds = partition.row_blocks(g.csr()['indptr'], world, balance='edges' if mode == 'edges' else 'rows')
     rb, re = bounds[rank], bounds[rank + 1]
     xo = x[rb:re].clone().requires_grad_(True)
     th = theta0.clone().requires_grad_(True)
     nrm = RF.weighted_degree_norm(g, etv, th, 100.0, -0.5)
-    out = partition.partitioned_propagate(g, etv, xo, th, 100.0, nrm, bounds, rank)
+    fn = partition.feature_sliced_propagate if mode == 'cols' else partition.partitioned_propagate
+    out = fn(g, etv, xo, th, 100.0, nrm, bounds, rank)
     out.backward(gout[rb:re])
     partition.allreduce_relation_grads([th])
     ref_out, ref_dx, ref_dth = _single(d, x, gout, theta0)
@@ -82,10 +83,12 @@ def test_row_blocks_balance_edges():
 
 
 @pytest.mark.timeout(300)
-def test_partitioned_layer_matches_single_process_world2():
+@pytest.mark.parametrize('mode', ['edges', 'rows', 'cols'])
+def test_partitioned_layer_matches_single_process_world2(mode):
+    """edges / rows: destination-row blocks + all-gather; cols: feature-sliced aggregation between all-to-alls."""
     world = 2
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + {'edges': 0, 'rows': 2000, 'cols': 4000}[mode]
     mgr = mp.get_context('spawn').Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, ret, mode), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
