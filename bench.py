@@ -404,7 +404,7 @@ def run_ours(args, d):
 
         def k():
             ops.spmm(csr['indptr'], csr['indices'], etv[0], theta.detach(), ALPHA, nrm, nrm, xs, rows=rows, out=y,
-                     split=csr.get('split'))
+                     split=csr.get('split'), order=ops.row_order(csr) if fk <= ops.NARROW_FEAT else None)
         tk = timed(k, 20, 5, sync) / 20
         rows_n = n if rows is None else rows[1] - rows[0]
         edges_n = e if rows is None else int(csr['indptr'][rows[1]].item() - csr['indptr'][rows[0]].item())
@@ -416,6 +416,8 @@ def run_ours(args, d):
             traffic = json.load(fh).get('spmm_kernel_fwd_mag_f128_bytes')
     vw = 4 if fk >= 96 and fk % 4 == 0 else 2 if fk >= 34 and fk % 2 == 0 else 1
     kname = 'regnn::spmm_stream_kernel<%d,%d,false> (forward launch)' % (max(1, -(-fk // (32 * vw))), vw)
+    if fk <= ops.NARROW_FEAT and fk % 4 == 0 and rows is None:
+        kname = 'regnn::spmm_rowgroup_kernel<false,%d> (forward launch)' % (16 if fk > 32 else 8 if fk > 16 else 4)
     roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': alg / tk / 1e9,
                 'peak': hbm, 'peak_source': how, 'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm, 'traffic': traffic,
                 'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3}

@@ -128,12 +128,17 @@ int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const i
  * The same entry point run on the transposed view (indptr_t, indices_t, etype_t) is the
  * backward pass w.r.t. X (DGL: gspmm on the reverse graph).
  * X: [*, F] with leading dimension ldx (floats); Y: rows [row_begin,row_end) written at Y[v*ldy].
+ * row_order (optional, NULL = none): the rows of [0, row_end) NOT listed in split->long_rows, by descending
+ * slot count (ties by ascending row id) -- [row_end - num_long] ids, built once per graph.  With it, a full
+ * range (row_begin == 0) and F <= 64 (F % 4 == 0, 16-byte aligned rows) the narrow-row kernel runs: several
+ * rows per warp, each summed by one lane group in slot order (results identical to the whole-warp kernel).
  */
 int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
                    const float* theta, float alpha, int num_relations, const float* norm_src,
                    const float* norm_dst, const float* X, int64_t ldx, float* Y, int64_t ldy,
                    int64_t row_begin, int64_t row_end, int feat, const regnn_rowsplit_t* split,
-                   float* split_workspace /* [split->num_frags * feat] floats, or NULL */, void* stream);
+                   float* split_workspace /* [split->num_frags * feat] floats, or NULL */,
+                   const int32_t* row_order, void* stream);
 
 /* Backward of regnn_spmm_fwd w.r.t. the relation weights and the norm vector (norm_src == norm_dst
  * == norm, the reference's case).  Given G = dL/dY, X, Y and dX (= the transposed regnn_spmm_fwd of G):
@@ -159,13 +164,16 @@ int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_
  * G[dst] row that the dX gather already holds in registers; X rows of the block are staged in shared
  * memory by TMA bulk copies.  d_norm is NOT produced here: see regnn_rowdot_norm_bwd.
  * partials: double [regnn_max_partial_blocks() * R]; d_theta is OVERWRITTEN;
- * split_workspace: split_t->num_frags * feat floats. */
+ * split_workspace: split_t->num_frags * feat floats.  With row_order_t (F <= 64, full range) the narrow-row
+ * kernel runs instead and keeps X[u] in registers (no shared-memory tile). */
 int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t, const uint8_t* etype_t,
                          const float* theta, float alpha, int num_relations, const float* norm,
                          int norm_sides, const float* X, int64_t ldx, const float* G, int64_t ldg,
                          float* dX, int64_t lddx, int64_t row_begin, int64_t row_end, int feat,
                          double* partials, float* d_theta, float* xdx /* optional [N]: <X[u],dX[u]> per row */,
-                         const regnn_rowsplit_t* split_t, float* split_workspace, void* stream);
+                         const regnn_rowsplit_t* split_t, float* split_workspace,
+                         const int32_t* row_order_t /* as regnn_spmm_fwd's row_order, for the transposed view */,
+                         void* stream);
 
 /* d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v] for rows [row_begin,row_end):
  * the gradient of regnn_spmm_fwd w.r.t. the norm vector (row-local, pure streaming).  If xdx (from

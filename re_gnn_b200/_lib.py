@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libregnn_b200.so')
+# REGNN_B200_LIB: development knob, points the binding at an A/B build of the same C ABI (scripts/build_variants.sh)
+LIB_PATH = os.environ.get('REGNN_B200_LIB') or os.path.join(_HERE, 'lib', 'libregnn_b200.so')
 
 _p = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -27,11 +28,11 @@ SIGNATURES = {
     'regnn_relation_counts': (_i32, [_p, _p, _i64, _i64, _i32, _p, _p]),
     'regnn_wdeg_norm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _f32, _f32, _i64, _i64, _p, _p, _p]),
     'regnn_wdeg_norm_bwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _f32, _f32, _i64, _i64, _p, _p, _p, _p, _p]),
-    'regnn_spmm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i32, _p, _p, _p]),
+    'regnn_spmm_fwd': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),
     'regnn_spmm_bwd_w': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
                                 _i64, _i64, _i32, _p, _p, _p, _p, _p]),
     'regnn_spmm_bwd_fused': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i64,
-                                    _i32, _p, _p, _p, _p, _p, _p]),
+                                    _i32, _p, _p, _p, _p, _p, _p, _p]),
     'regnn_rowdot_norm_bwd': (_i32, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p]),
     'regnn_random_walk': (_i32, [_p, _p, _i64, _i64, _i32, ctypes.c_uint64, _p, _p]),
     'regnn_sample_neighbors': (_i32, [_p, _p, _i64, _i32, ctypes.c_uint64, _p, _p]),

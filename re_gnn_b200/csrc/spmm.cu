@@ -243,6 +243,9 @@ struct StreamArgs {
   double* partials;      // [gridDim.x][R]
   int use_tma;           // rows are 16-byte aligned multiples of 16 bytes: stage the tile with cp.async.bulk
   float* xdx;            // optional [N]: <Xrow[u], dX[u]> per row (the source-side half of d_norm), or null
+  // spmm_rowgroup_kernel only
+  const int32_t* order;  // rows not covered by fragments, by descending slot count
+  int64_t n_order;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -493,6 +496,133 @@ spmm_stream_kernel(StreamArgs sa) {
     if (BINS && !tile_ready) {  // item without a single short-row slot: still consume the barrier phase
       mbar_wait(mybar, phase);
       phase ^= 1u;
+    }
+  }
+  if (BINS) reduce_bins(bins, scratch, a.R, sa.partials + (size_t)blockIdx.x * a.R);
+}
+
+// ---- narrow rows (F <= 64): lane-group SpMM over degree-sorted rows -----------------------------------
+// A 128-bit chunk per lane covers a row of F <= 64 floats with G = 4 / 8 / 16 lanes, so a warp works on
+// 32/G rows at once -- one gather instruction fetches 32/G source rows (the column slabs of the
+// feature-sliced multi-GPU scheme, hidden width 64 of the HGB models).  Rows come from `order` (rows not
+// covered by fragments, by descending slot count, built once per graph): neighbouring lane groups get
+// rows of (nearly) equal length, so the warp-uniform trip count wastes almost nothing, and each row is
+// summed by ONE lane group in slot order -- bit-identical to the whole-warp kernels, no cross-lane fold, no
+// row-boundary bookkeeping.  Fragments of long rows (all `threshold` slots long) are the first items.
+// BINS: as in spmm_stream_kernel, but the row-level operand Xrow[u] is one 128-bit register per lane.
+template <bool BINS, int G>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+spmm_rowgroup_kernel(StreamArgs sa) {
+  static_assert(G == 4 || G == 8 || G == 16, "lane groups of 4, 8 or 16 lanes");
+  constexpr int GPW = 32 / G;  // rows per warp
+  constexpr int U = 4;         // gathers in flight per lane
+  const SpmmArgs& a = sa.s;
+  __shared__ float w_s[256];
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % G, grp = lane / G;
+  // dynamic smem (BINS): [warps][R] double scratch | [warps][R][32] lane-local bins
+  double* scratch = reinterpret_cast<double*>(dsm);
+  float* bins = reinterpret_cast<float*>(scratch + kWarpsPerBlock * a.R);
+  float* mybins = bins + (size_t)warp * a.R * 32 + lane;
+  const bool weighted = a.etype != nullptr;
+  if (weighted)
+    for (int i = threadIdx.x; i < a.R; i += blockDim.x) w_s[i] = leaky(a.theta[i] * a.alpha, kRelationSlope);
+  if (BINS)
+    for (int r = 0; r < a.R; ++r) mybins[r * 32] = 0.f;
+  __syncthreads();
+
+  // lanes past the last column gather column 0 (same sectors as lane 0) and are masked at the stores
+  const bool col_ok = lg * 4 < a.F;
+  const char* xbytes = reinterpret_cast<const char*>(a.X + (col_ok ? lg : 0) * 4);
+  const uint32_t ldxb = (uint32_t)a.ldx * 4u;  // row pitch in bytes: one IMAD.WIDE per gather
+  const int64_t nitems = (int64_t)a.nfrag + sa.n_order;
+  const int64_t nwork = (nitems + GPW - 1) / GPW;
+  const int64_t stride = BINS ? (int64_t)gridDim.x * kWarpsPerBlock : nwork;  // plain: one item per warp
+
+  for (int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; wi < nwork; wi += stride) {
+    const int64_t vi = wi * GPW + grp;
+    int64_t v = -1;
+    int begin = 0, len = 0;
+    const bool is_frag = vi < a.nfrag;
+    if (vi < nitems) {
+      if (is_frag) {
+        v = a.frag_row[vi];
+        begin = a.frag_begin[vi];
+        len = min(a.threshold, a.indptr[v + 1] - begin);
+      } else {
+        v = sa.order[vi - a.nfrag];
+        begin = a.indptr[v];
+        len = a.indptr[v + 1] - begin;
+      }
+    }
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    const float nd = (v >= 0 && a.norm_dst != nullptr) ? a.norm_dst[v] : 1.f;
+    float4 trow = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BINS && v >= 0 && col_ok) trow = ldg4(sa.Xrow + (size_t)v * sa.ldr + lg * 4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur_rel = 0;
+    float racc = 0.f;
+    const int32_t* ip = a.indices + begin;
+    const uint8_t* ep = a.etype + begin;
+
+    int nidx[U], net[U];  // next round's column indices / edge types (-1 = no slot)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      nidx[u] = u < len ? __ldg(ip + u) : -1;
+      net[u] = (weighted && u < len) ? (int)__ldg(ep + u) : 0;
+    }
+    for (int t = 0; t < maxlen; t += U) {
+      int idx[U], et[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        idx[u] = nidx[u];
+        et[u] = net[u];
+      }
+      float4 x[U];
+      float ns[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = idx[u] >= 0;
+        x[u] = ok ? ldg4(reinterpret_cast<const float*>(xbytes + (uint64_t)(uint32_t)idx[u] * ldxb))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        ns[u] = ok ? (a.norm_src != nullptr ? __ldg(a.norm_src + idx[u]) : 1.f) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {  // indices of the next round: in flight behind this round's gathers
+        const int tn = t + U + u;
+        nidx[u] = tn < len ? __ldg(ip + tn) : -1;
+        net[u] = (weighted && tn < len) ? (int)__ldg(ep + tn) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float coef = (weighted ? w_s[et[u]] : 1.f) * ns[u];  // 0 for a missing slot
+        fma4(acc, coef, x[u]);
+        if (BINS) {
+          const float d = dot4(x[u], trow);
+          if (idx[u] >= 0 && et[u] != cur_rel) {  // lane-local bin, slot order, bank-conflict free
+            mybins[cur_rel * 32] += racc;
+            racc = 0.f;
+            cur_rel = et[u];
+          }
+          racc = fmaf(ns[u] * nd, d, racc);
+        }
+      }
+    }
+    if (BINS) {
+      mybins[cur_rel * 32] += racc;
+      if (sa.xdx != nullptr) {  // <X[u], dX[u]> while dX[u] is still in registers (long rows: long_row_xdx_kernel)
+        const float d = group_sum<G>(dot4(acc, trow)) * nd;
+        if (lg == 0 && v >= 0 && !is_frag) sa.xdx[v] = d;
+      }
+    }
+    if (v >= 0 && col_ok) {
+      if (is_frag) {
+        st4(a.partial + (size_t)vi * a.F + lg * 4, acc);
+      } else {
+        scale4(acc, nd);
+        st4(a.Y + (size_t)v * a.ldy + lg * 4, acc);
+      }
     }
   }
   if (BINS) reduce_bins(bins, scratch, a.R, sa.partials + (size_t)blockIdx.x * a.R);
@@ -1085,6 +1215,22 @@ static int common_align(std::initializer_list<const void*> ptrs, std::initialize
   REGNN_STREAM_CASE(1, 1, BINS_, CALL) REGNN_STREAM_CASE(2, 1, BINS_, CALL) REGNN_STREAM_CASE(3, 1, BINS_, CALL) \
   REGNN_STREAM_CASE(4, 1, BINS_, CALL) REGNN_STREAM_CASE(8, 1, BINS_, CALL)
 
+// Lane-group width of spmm_rowgroup_kernel for this call, or 0 when the whole-warp kernels must run: needs the
+// degree-sorted row order (which lists the rows of the FULL range), F <= 64 in whole 128-bit chunks, 16-byte rows.
+static int rowgroup_lanes(int F, const int32_t* order, int64_t row_begin, int align) {
+  if (order == nullptr || row_begin != 0 || F > 64 || F % 4 != 0 || align < 16) return 0;
+  return F > 32 ? 16 : (F > 16 ? 8 : 4);
+}
+#define REGNN_ROWGROUP_CASE(G_, BINS_, CALL) \
+  if (G == G_) {                             \
+    constexpr int GL = G_;                   \
+    constexpr bool BINS = BINS_;             \
+    CALL;                                    \
+    launched = true;                         \
+  }
+#define REGNN_ROWGROUP_DISPATCH(BINS_, CALL) \
+  REGNN_ROWGROUP_CASE(16, BINS_, CALL) REGNN_ROWGROUP_CASE(8, BINS_, CALL) REGNN_ROWGROUP_CASE(4, BINS_, CALL)
+
 template <typename K>
 static int resident_blocks(K kernel, size_t smem) {
   int dev = 0, sms = 148, per_sm = 1;
@@ -1116,7 +1262,7 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
                               const float* norm_src, const float* norm_dst, const float* X,
                               int64_t ldx, float* Y, int64_t ldy, int64_t row_begin,
                               int64_t row_end, int feat, const regnn_rowsplit_t* split,
-                              float* split_workspace, void* stream_) {
+                              float* split_workspace, const int32_t* row_order, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && X && Y,  /* per-edge arrays may be NULL when E == 0 */ REGNN_ERR_INVALID_ARG, "spmm_fwd: null pointer");
   REGNN_REQUIRE(etype == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd: etype without theta");
@@ -1134,10 +1280,20 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
                   row_begin, row_end, feat, nullptr, nullptr, 0, 0, 0x7fffffff, nullptr};
   int rc = fill_split(sa.s, split, split_workspace, "spmm_fwd");
   if (rc != REGNN_OK) return rc;
-  const int64_t nitems = sa.s.nfrag_pad + (rows + kRowsPerItem - 1) / kRowsPerItem;
-  const unsigned blocks = (unsigned)((nitems + kWarpsPerBlock - 1) / kWarpsPerBlock);
   bool launched = false;
-  REGNN_STREAM_DISPATCH(false, (spmm_stream_kernel<C, VW, BINS><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(sa)))
+  const int G = rowgroup_lanes(feat, row_order, row_begin, common_align({X, Y, split_workspace}, {ldx, ldy, (int64_t)feat}));
+  if (G != 0) {  // narrow rows over the degree-sorted row order
+    REGNN_REQUIRE(ldx < (1ll << 30), REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: leading dimension too large");
+    sa.order = row_order;
+    sa.n_order = rows - (sa.s.nfrag > 0 ? split->num_long : 0);
+    const int64_t nwork = (sa.s.nfrag + sa.n_order + 32 / G - 1) / (32 / G);
+    const unsigned blocks = (unsigned)((nwork + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    REGNN_ROWGROUP_DISPATCH(false, (spmm_rowgroup_kernel<BINS, GL><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(sa)))
+  } else {
+    const int64_t nitems = sa.s.nfrag_pad + (rows + kRowsPerItem - 1) / kRowsPerItem;
+    const unsigned blocks = (unsigned)((nitems + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    REGNN_STREAM_DISPATCH(false, (spmm_stream_kernel<C, VW, BINS><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(sa)))
+  }
   REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: no kernel for C=%d VW=%d", sh.C, sh.VW);
   if (sa.s.nfrag > 0)
     spmm_frag_finalize_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->frag_ptr, split->num_long,
@@ -1151,7 +1307,7 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
                                     int64_t ldx, const float* Gd, int64_t ldg, float* dX, int64_t lddx,
                                     int64_t row_begin, int64_t row_end, int feat, double* partials,
                                     float* d_theta, float* xdx, const regnn_rowsplit_t* split_t,
-                                    float* split_workspace, void* stream_) {
+                                    float* split_workspace, const int32_t* row_order_t, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr_t && theta && X && Gd && dX && partials && d_theta,
                 REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: null pointer");
@@ -1181,7 +1337,18 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
                       (size_t)kWarpsPerBlock * kRowsPerItemBins * Fp * sizeof(float);
   int nb = partial_blocks(rows / kRowsPerItemBins + sa.s.nfrag + 1);
   bool launched = false;
-  // persistent kernel: exactly one resident wave (148 SMs x blocks per SM), never more than the partial slots
+  const int G = rowgroup_lanes(feat, row_order_t, row_begin,
+                               common_align({X, Gd, dX, split_workspace}, {ldx, ldg, lddx, (int64_t)feat}));
+  // persistent kernels: exactly one resident wave (148 SMs x blocks per SM), never more than the partial slots
+  if (G != 0) {
+    REGNN_REQUIRE(ldg < (1ll << 30), REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_fused: leading dimension too large");
+    sa.order = row_order_t;
+    sa.n_order = rows - (sa.s.nfrag > 0 ? split_t->num_long : 0);
+    const size_t gsmem = (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float));
+    REGNN_ROWGROUP_DISPATCH(true, (rc = set_smem(spmm_rowgroup_kernel<BINS, GL>, gsmem),
+                                   nb = min(nb, resident_blocks(spmm_rowgroup_kernel<BINS, GL>, gsmem)),
+                                   spmm_rowgroup_kernel<BINS, GL><<<nb, kWarpsPerBlock * 32, gsmem, stream>>>(sa)))
+  } else
   REGNN_STREAM_DISPATCH(true, (rc = set_smem(spmm_stream_kernel<C, VW, BINS>, smem),
                                nb = min(nb, resident_blocks(spmm_stream_kernel<C, VW, BINS>, smem)),
                                spmm_stream_kernel<C, VW, BINS><<<nb, kWarpsPerBlock * 32, smem, stream>>>(sa)))

@@ -46,7 +46,7 @@ class _Propagate(torch.autograd.Function):
         ns = norm if sides & 1 else None
         nd = norm if sides & 2 else None
         y = ops.spmm(csr['indptr'], csr['indices'], etv[0] if weighted else None, theta, alpha, ns, nd, x,
-                     split=csr.get('split'))
+                     split=csr.get('split'), order=ops.row_order(csr) if x.shape[1] <= ops.NARROW_FEAT else None)
         ctx.graph, ctx.etv, ctx.alpha, ctx.weighted, ctx.has_norm = graph, etv, alpha, weighted, norm is not None
         ctx.sides = sides
         ctx.save_for_backward(x, y, theta if weighted else None, norm)
@@ -73,7 +73,8 @@ class _Propagate(torch.autograd.Function):
                 ns = norm if ctx.sides & 2 else None
                 nd = norm if ctx.sides & 1 else None
                 dx = ops.spmm(csr['indptr_t'], csr['indices_t'], ctx.etv[1] if ctx.weighted else None, theta,
-                              ctx.alpha, ns, nd, g, split=csr.get('split_t'))
+                              ctx.alpha, ns, nd, g, split=csr.get('split_t'),
+                              order=ops.row_order(csr, True) if g.shape[1] <= ops.NARROW_FEAT else None)
             if need_theta:
                 d_theta, _ = ops.spmm_bwd_w(csr, ctx.etv[0], theta, ctx.alpha, norm, x, y, g, dx, sides=ctx.sides,
                                             split=csr.get('split'))

@@ -69,9 +69,28 @@ def _split_args(split, feat, device):
     return ctypes.byref(split['struct']), ws, 1
 
 
-def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None, split=None):
+NARROW_FEAT = 64   # widths up to this run the lane-group kernel when the degree-sorted row order is supplied
+
+
+def row_order(csr, transposed=False):
+    """Rows of one CSR view that are not cut into fragments, by descending slot count (stable): the work list of
+    the narrow-row SpMM kernels (``row_order`` of regnn_spmm_fwd / regnn_spmm_bwd_fused).  Index bookkeeping with
+    torch ops on the device, built on first use and cached in the csr dict."""
+    key = 'order_t' if transposed else 'order'
+    if key not in csr:
+        indptr = csr['indptr_t' if transposed else 'indptr']
+        split = csr.get('split_t' if transposed else 'split')
+        deg = indptr[1:] - indptr[:-1]
+        order = torch.sort(deg, descending=True, stable=True).indices
+        # long rows (more slots than the split threshold) sort first: drop them
+        csr[key] = order[(split['struct'].num_long if split is not None else 0):].to(torch.int32).contiguous()
+    return csr[key]
+
+
+def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None, split=None, order=None):
     """Y[v] = norm_dst[v] * sum_s w[etype[s]] * norm_src[indices[s]] * X[indices[s]] over rows.
-    ``split``: the long-row decomposition of this CSR view (Graph.csr()['split' | 'split_t'])."""
+    ``split``: the long-row decomposition of this CSR view (Graph.csr()['split' | 'split_t']);
+    ``order``: ``row_order`` of the same view (used for widths <= NARROW_FEAT on the full row range)."""
     x = _f32(x)
     n = indptr.numel() - 1
     rb, re = _rows(rows, n)
@@ -85,7 +104,8 @@ def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None,
     with torch.cuda.device(x.device):
         _lib.call('regnn_spmm_fwd', _ptr(indptr), _ptr(indices), _ptr(etype) if theta is not None else None,
                   _ptr(theta), float(alpha), theta.numel() if theta is not None else 0, _ptr(norm_src),
-                  _ptr(norm_dst), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rb, re, f, sp, _ptr(ws), _stream())
+                  _ptr(norm_dst), _ptr(x), x.stride(0), _ptr(out), out.stride(0), rb, re, f, sp, _ptr(ws),
+                  _ptr(order) if (order is not None and f <= NARROW_FEAT and (rb, re) == (0, n)) else None, _stream())
         _lib.count_launches(1 + extra)
     return out
 
@@ -125,10 +145,12 @@ def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=
     d_theta = torch.empty(r, dtype=torch.float32, device=x.device)
     sp, ws, extra = _split_args(csr.get('split_t'), f, x.device)
     xdx = torch.zeros(n, dtype=torch.float32, device=x.device) if want_xdx else None
+    order = row_order(csr, True) if (f <= NARROW_FEAT and (rb, re) == (0, n)) else None
     with torch.cuda.device(x.device):
         _lib.call('regnn_spmm_bwd_fused', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(et_t), _ptr(theta),
                   float(alpha), r, _ptr(norm), int(sides), _ptr(x), x.stride(0), _ptr(g), g.stride(0), _ptr(out),
-                  out.stride(0), rb, re, f, _ptr(partials), _ptr(d_theta), _ptr(xdx), sp, _ptr(ws), _stream())
+                  out.stride(0), rb, re, f, _ptr(partials), _ptr(d_theta), _ptr(xdx), sp, _ptr(ws), _ptr(order),
+                  _stream())
         _lib.count_launches(2 + extra * (2 if want_xdx else 1))
     return out, d_theta, xdx
 

@@ -153,7 +153,7 @@ class _ColumnSlabPropagate(torch.autograd.Function):
         x_cols = _rows_to_columns(x_own, per, parts, group)
         y_cols = torch.empty_like(x_cols)
         ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, alpha, norm, norm, x_cols, out=y_cols,
-                 split=csr.get('split'))
+                 split=csr.get('split'), order=ops.row_order(csr) if x_cols.shape[1] <= ops.NARROW_FEAT else None)
         ctx.graph, ctx.etv, ctx.alpha, ctx.bounds, ctx.rank, ctx.group = graph, etv, alpha, bounds, rank, group
         ctx.save_for_backward(x_cols, y_cols, theta, norm)
         return _columns_to_rows(y_cols, per, parts, x_own.shape[0], group)

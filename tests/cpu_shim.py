@@ -69,7 +69,7 @@ def wdeg_norm_bwd(csr, et_csr, theta, alpha, exponent, deg, d_norm, rows=None, c
     return dw * alpha * _lgrad(th * alpha, SLOPE)
 
 
-def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None, split=None):
+def spmm(indptr, indices, etype, theta, alpha, norm_src, norm_dst, x, rows=None, out=None, split=None, order=None):
     x = x.detach()
     row, col = _rows_of(indptr), indices.long()
     coef = torch.ones(col.numel(), dtype=x.dtype)

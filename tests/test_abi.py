@@ -61,7 +61,7 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.regnn_csr_build(None, None, -1, 0, None, None, None, None, None, None, None, None, 0, None) == -1
     assert lib.regnn_etype_permute(None, None, None, 5, 300, None, None, None, None) == -2
     assert b'num_relations' in lib.regnn_last_error_string()
-    assert lib.regnn_spmm_fwd(None, None, None, None, 1.0, 0, None, None, None, 4, None, 4, 0, 0, 4, None, None, None) == -1
+    assert lib.regnn_spmm_fwd(None, None, None, None, 1.0, 0, None, None, None, 4, None, 4, 0, 0, 4, None, None, None, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -405,6 +405,50 @@ def test_mag_regcn_layer_and_train_step():
     assert losses[-1] < 0.7 * losses[0], losses
 
 
+# ---- narrow-row kernels (lane groups over degree-sorted rows) against the whole-warp kernels --------------------
+@pytest.mark.parametrize('f', [4, 8, 16, 20, 32, 48, 64])
+@pytest.mark.parametrize('weighted', [True, False])
+def test_narrow_row_kernels_equal_whole_warp_kernels(f, weighted):
+    from re_gnn_b200 import ops
+    rng = np.random.RandomState(f)
+    n, e, r = 3001, 40000, 5
+    src = rng.randint(0, n, size=e).astype(np.int64)
+    dst = rng.randint(0, n - 200, size=e).astype(np.int64)      # the last 200 rows have no in-edges
+    dst[:9000] = rng.randint(0, 3, size=9000)                   # hub rows: cut into fragments
+    g = Graph(src, dst, n).to(DEV)
+    et = torch.as_tensor(rng.randint(1, r + 1, size=e)).to(DEV)
+    csr = g.csr()
+    etv = g.etype_views(et, r)
+    gen = torch.Generator(device=DEV).manual_seed(f)
+    x = torch.randn(n, f, device=DEV, generator=gen)
+    gout = torch.randn(n, f, device=DEV, generator=gen)
+    th = _theta(r, 1, 5).to(DEV, torch.float32)
+    _, nrm = ops.wdeg_norm_fwd(csr, etv[0], th, 100.0, -0.5, counts=etv[2])
+    order = ops.row_order(csr)
+    if DEV != 'cpu':
+        deg = (csr['indptr'][1:] - csr['indptr'][:-1])
+        assert csr['split'] is not None and order.numel() == n - csr['split']['struct'].num_long
+        od = deg[order.long()]
+        assert bool((od[:-1] >= od[1:]).all()) and int(od.max()) <= csr['split']['struct'].threshold
+    args = (csr['indptr'], csr['indices'], etv[0] if weighted else None, th if weighted else None, 100.0, nrm, nrm, x)
+    wide = ops.spmm(*args, split=csr.get('split'))
+    narrow = ops.spmm(*args, split=csr.get('split'), order=order)
+    assert torch.equal(wide, narrow)
+    if weighted:
+        # fused backward: rows=(0, n) given explicitly still counts as the full range; a sub-range does not
+        dx_n, dth_n, xdx_n = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, x, gout, want_xdx=True)
+        dx_w = torch.empty_like(dx_n)
+        dth_w = torch.zeros_like(dth_n, dtype=torch.float64)
+        xdx_w = torch.zeros_like(xdx_n)
+        for rows in ((0, n // 2), (n // 2, n)):                   # sub-ranges run the whole-warp kernel
+            _, t, xd = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, x, gout, rows=rows, out=dx_w, want_xdx=True)
+            dth_w += t.double()
+            xdx_w += xd
+        assert torch.equal(dx_n, dx_w)
+        helpers.assert_close(dth_n.double().cpu(), dth_w.cpu(), RTOL, 'd_theta')
+        helpers.assert_close(xdx_n.cpu(), xdx_w.cpu(), 10 * RTOL, 'xdx', atol=1e-5)
+
+
 # ---- feature-sliced (column slab) kernel paths on one GPU: P virtual ranks, each all rows x F/P columns ----
 @pytest.mark.parametrize('parts,f', [(2, 128), (4, 128), (8, 128), (4, 48)])
 def test_column_slab_kernels_equal_full_run(parts, f):
@@ -431,9 +475,10 @@ def test_column_slab_kernels_equal_full_run(parts, f):
         xs = torch.cat([x[:, cols], torch.full((pad, fc), float('nan'), device=DEV)]).contiguous()
         gs = torch.cat([gout[:, cols], torch.full((pad, fc), float('nan'), device=DEV)]).contiguous()
         ys, dxs = torch.empty_like(xs), torch.empty_like(xs)
-        ops.spmm(csr['indptr'], csr['indices'], etv[0], th, 100.0, nrm, nrm, xs, out=ys, split=csr.get('split'))
+        ops.spmm(csr['indptr'], csr['indices'], etv[0], th, 100.0, nrm, nrm, xs, out=ys, split=csr.get('split'),
+                 order=ops.row_order(csr))   # narrow slabs: lane-group kernel over the degree-sorted rows
         _, t, xd = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, xs, gs, out=dxs, want_xdx=True)
-        # per-column sums never mix columns: slabs reproduce the full run bit for bit
+        # per-column sums never mix columns and every kernel adds a row's slots in slot order: bit for bit
         assert torch.equal(ys[:n], y[:, cols]) and torch.equal(dxs[:n], dx[:, cols])
         dth_p += t.double()
         dn_p += ops.rowdot_norm_bwd(nrm, xs, ys, gs, dxs, xdx=xd).double()
@@ -480,12 +525,12 @@ def test_feature_sliced_propagate_world1_nccl():
 
 
 # ---- row-range (partitioned) kernel paths on one GPU: P virtual ranks, all-gather emulated by sharing buffers ----
-@pytest.mark.parametrize('parts', [2, 5])
-def test_row_partitioned_kernels_equal_full_run(parts):
+@pytest.mark.parametrize('parts,f', [(2, 128), (5, 128), (3, 64)])
+def test_row_partitioned_kernels_equal_full_run(parts, f):
     from re_gnn_b200 import ops, partition
     d = synth.hetero_graph('dblp', seed=9, scale=0.3)
     g, et = _graph(d), torch.as_tensor(d['etype']).to(DEV)
-    n, r, f = d['num_nodes'], d['num_relations'], 64
+    n, r = d['num_nodes'], d['num_relations']
     csr = g.csr()
     etv = g.etype_views(et, r)
     gen = torch.Generator(device=DEV).manual_seed(3)
@@ -511,7 +556,12 @@ def test_row_partitioned_kernels_equal_full_run(parts):
         dn_p[rows[0]:rows[1]] = dnr[rows[0]:rows[1]]
         assert float(dnr[:rows[0]].abs().sum() + dnr[rows[1]:].abs().sum()) == 0.0
         dth_np += ops.wdeg_norm_bwd(csr, etv[0], th, 100.0, -0.5, deg, dnr, rows=rows, counts=etv[2]).double()
-    assert torch.equal(y_p, y) and torch.equal(dx_p, dx) and torch.equal(dn_p, dn)      # row-local: bit-identical
+    # row-local sums in slot order: bit-identical whatever the row range (and whichever kernel the width selects)
+    assert torch.equal(y_p, y) and torch.equal(dx_p, dx)
+    if f > 64:
+        assert torch.equal(dn_p, dn)
+    else:        # the narrow-row kernel reduces <X[u], dX[u]> over a lane group, the row-range path over a warp
+        helpers.assert_close(dn_p.cpu(), dn.cpu(), 10 * RTOL, 'd_norm', atol=1e-5)
     helpers.assert_close(dth_p.cpu(), dth.double().cpu(), RTOL, 'd_theta (sum of rank shares)')
     helpers.assert_close(dth_np.cpu(), dth_n.double().cpu(), 5 * RTOL, 'd_theta via norm (sum of rank shares)')
     # attention kernels with a row range
