@@ -38,9 +38,10 @@ def parse():
     ap.add_argument('--workload', default='mag_regcn', choices=['mag_regcn', 'mag_ns', 'mag_saint'])
     ap.add_argument('--feat', type=int, default=FEAT)
     ap.add_argument('--scale', type=float, default=1.0, help='shrink the graph (debug only; reported in config)')
-    ap.add_argument('--partition', default='rows', choices=['cols', 'rows', 'edges'],
-                    help='multi-GPU scheme: cols = feature-sliced aggregation between all-to-alls; rows / edges = '
-                         'destination-row blocks (equal rows / equal in-edge counts) fed by all-gathers')
+    ap.add_argument('--partition', default='auto', choices=['auto', 'peer', 'cols', 'rows', 'edges'],
+                    help='multi-GPU scheme: peer = feature-sliced aggregation, re-partition over peer memory inside our '
+                         'kernels; cols = the same between NCCL all-to-alls; rows / edges = destination-row blocks '
+                         '(equal rows / equal in-edge counts) fed by all-gathers; auto = peer, else cols (>= 4 ranks) / rows')
     ap.add_argument('--no-others', action='store_true', help='skip the secondary HGB-shaped workloads')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -158,8 +159,16 @@ def run_reference(args, d):
 
 
 def workload_config(args, d):
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    how = {'peer': 'feature-sliced over --gpus (column slabs; rows<->slabs re-partition over NVLink peer memory inside '
+                   'the kernels, outputs alias the exchange buffers)',
+           'cols': 'feature-sliced over --gpus (column slabs between NCCL all-to-alls)',
+           'rows': 'dst-row blocks (equal rows) over --gpus, NCCL all-gather of source rows',
+           'edges': 'dst-row blocks (equal in-edges) over --gpus, NCCL all-gather of source rows'}
+    if world == 1:
+        args.partition = 'none'
     return {'workload': 'REGraphConv RE-layer fwd+bwd, full-batch, synthetic ogbn-mag-shaped graph '
-                        '(BASELINE config 4), dst-row-partitioned over --gpus',
+                        '(BASELINE config 4), ' + how.get(args.partition, 'single GPU'),
             'num_nodes': int(d['num_nodes']), 'num_edges': int(d['src'].size), 'num_relations': int(d['num_relations']),
             'feat': args.feat, 'graph_scale': args.scale, 'partition': args.partition,
             'l2': 'inputs larger than L2 (source matrix %.0f MB vs 126 MB L2); no flush needed'
@@ -328,8 +337,33 @@ def run_ours(args, d):
             RF.propagate(g, etv, x, theta, ALPHA, nrm).backward(gout)
     else:
         bounds = partition.row_blocks(csr['indptr'], world, balance='edges' if args.partition == 'edges' else 'rows')
-        dist_propagate = partition.feature_sliced_propagate if args.partition == 'cols' else partition.partitioned_propagate
         rb, re = bounds[rank], bounds[rank + 1]
+        mode = args.partition
+        if mode in ('auto', 'peer'):
+            xch, why = None, ''
+            try:
+                if f % (4 * world) or f // world > ops.NARROW_FEAT:
+                    raise ValueError('F=%d does not split into 128-bit slabs of <= %d columns over %d ranks'
+                                     % (f, ops.NARROW_FEAT, world))
+                xch = partition.SlabExchange(f, bounds, rank, dev)
+            except Exception as ex:   # no peer mapping on this box / shape: every rank falls back together
+                why = '%s: %s' % (type(ex).__name__, ex)
+            flag = torch.tensor([int(xch is not None)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()):
+                mode = 'peer'
+            else:
+                if rank == 0:
+                    print('[bench] peer-memory exchange unavailable (%s); using collectives' % why, file=sys.stderr)
+                xch, mode = None, ('cols' if world >= 4 and f % world == 0 else 'rows')
+        args.partition = mode
+        if mode == 'peer':
+            def dist_propagate(g_, etv_, x_, th_, al_, nrm_, b_, r_):
+                return partition.feature_sliced_propagate(g_, etv_, x_, th_, al_, nrm_, b_, r_, exchange=xch, alias=True)
+        elif mode == 'cols':
+            dist_propagate = partition.feature_sliced_propagate
+        else:
+            dist_propagate = partition.partitioned_propagate
         x = x_full[rb:re].clone().requires_grad_(True)
         gout = g_full[rb:re].clone()
         del x_full, g_full
@@ -396,7 +430,7 @@ def run_ours(args, d):
     hbm, how = peaks()
     with torch.no_grad():
         nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5).detach()
-        sliced = world > 1 and args.partition == 'cols'
+        sliced = world > 1 and args.partition in ('cols', 'peer')
         fk = f // world if sliced else f      # feature-sliced: this rank's launch covers all rows x F/P columns
         xs = x_e.detach() if world == 1 else torch.randn(n, fk, device=dev)
         y = torch.empty(n, fk, device=dev)

@@ -175,6 +175,47 @@ int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t, cons
                          const int32_t* row_order_t /* as regnn_spmm_fwd's row_order, for the transposed view */,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Feature-sliced multi-GPU aggregation (no reference counterpart: the reference is single-device).
+ * Every rank propagates ALL rows for F/P of the columns (a "column slab" [P*rows_per_rank, F/P]); the dense
+ * layers around the aggregation are row-parallel (rank q owns rows [q*rows_per_rank, (q+1)*rows_per_rank)).
+ * The two re-partitions run over peer-mapped memory (NVLink), not through a collective library:
+ *   rows -> slabs: regnn_rows_to_slabs pushes this rank's row block, column slice q to rank q's slab;
+ *   slabs -> rows: the *_scatter variants of the two SpMM entry points store each finished row straight into
+ *                  its owner's row block (regnn_peer_rows_t) from the kernel epilogue -- compute and exchange
+ *                  are one kernel.
+ * The caller provides the peer-mapped buffers (e.g. CUDA VMM / IPC; the Python binding uses torch symmetric memory)
+ * and a cross-rank barrier after each call before the written buffers are read. */
+typedef struct regnn_peer_rows {
+  float* const* base;    /* device array [num_ranks]: row block [rows_per_rank, ld] of every rank (peer-mapped) */
+  int32_t num_ranks;
+  int64_t rows_per_rank; /* row v belongs to rank v / rows_per_rank                                             */
+  int64_t ld;            /* leading dimension of the row blocks (floats)                                        */
+  int64_t col_offset;    /* first column this rank's slab covers                                                */
+} regnn_peer_rows_t;
+
+/* X: [num_rows, feat] row block (ld ldx).  Slice q (columns [q*feat/P, (q+1)*feat/P)) is written to
+ * peer_slabs[q] + (row_offset + i) * (feat/P): per peer one contiguous range.  feat % (4*num_ranks) == 0. */
+int regnn_rows_to_slabs(const float* X, int64_t ldx, int64_t num_rows, int feat, int num_ranks, int64_t row_offset,
+                        float* const* peer_slabs /* device array [num_ranks] */, void* stream);
+
+/* regnn_spmm_fwd over the full row range [0, num_rows) of a column slab (feat <= 64, row_order required) whose
+ * result rows are stored to their owner ranks: peers->base[v / rows_per_rank][(v % rows_per_rank) * ld + col_offset]. */
+int regnn_spmm_fwd_scatter(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
+                           const float* theta, float alpha, int num_relations, const float* norm_src,
+                           const float* norm_dst, const float* X, int64_t ldx, int64_t num_rows, int feat,
+                           const regnn_rowsplit_t* split, float* split_workspace, const int32_t* row_order,
+                           const regnn_peer_rows_t* peers, void* stream);
+
+/* regnn_spmm_bwd_fused with the dX rows stored to their owner ranks; d_theta / xdx stay local (this rank's
+ * columns; the caller sums them across ranks). */
+int regnn_spmm_bwd_fused_scatter(const int32_t* indptr_t, const int32_t* indices_t, const uint8_t* etype_t,
+                                 const float* theta, float alpha, int num_relations, const float* norm,
+                                 int norm_sides, const float* X, int64_t ldx, const float* G, int64_t ldg,
+                                 int64_t num_rows, int feat, double* partials, float* d_theta, float* xdx,
+                                 const regnn_rowsplit_t* split_t, float* split_workspace,
+                                 const int32_t* row_order_t, const regnn_peer_rows_t* peers, void* stream);
+
 /* d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v] for rows [row_begin,row_end):
  * the gradient of regnn_spmm_fwd w.r.t. the norm vector (row-local, pure streaming).  If xdx (from
  * regnn_spmm_bwd_fused) is given, X and dX are not read. */

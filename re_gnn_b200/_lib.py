@@ -33,6 +33,10 @@ SIGNATURES = {
                                 _i64, _i64, _i32, _p, _p, _p, _p, _p]),
     'regnn_spmm_bwd_fused': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i64,
                                     _i32, _p, _p, _p, _p, _p, _p, _p]),
+    'regnn_rows_to_slabs': (_i32, [_p, _i64, _i64, _i32, _i32, _i64, _p, _p]),
+    'regnn_spmm_fwd_scatter': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
+    'regnn_spmm_bwd_fused_scatter': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i32,
+                                            _p, _p, _p, _p, _p, _p, _p, _p]),
     'regnn_rowdot_norm_bwd': (_i32, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p]),
     'regnn_random_walk': (_i32, [_p, _p, _i64, _i64, _i32, ctypes.c_uint64, _p, _p]),
     'regnn_sample_neighbors': (_i32, [_p, _p, _i64, _i32, ctypes.c_uint64, _p, _p]),
@@ -54,6 +58,12 @@ class RowSplit(ctypes.Structure):
     """Mirror of ``regnn_rowsplit_t`` (include/regnn_b200.h)."""
     _fields_ = [('long_rows', _p), ('frag_ptr', _p), ('frag_row', _p), ('frag_begin', _p),
                 ('num_long', ctypes.c_int32), ('num_frags', ctypes.c_int32), ('threshold', ctypes.c_int32)]
+
+
+class PeerRows(ctypes.Structure):
+    """Mirror of ``regnn_peer_rows_t`` (include/regnn_b200.h)."""
+    _fields_ = [('base', _p), ('num_ranks', ctypes.c_int32), ('rows_per_rank', ctypes.c_int64),
+                ('ld', ctypes.c_int64), ('col_offset', ctypes.c_int64)]
 
 
 _lib = None

@@ -36,6 +36,19 @@ struct SpmmArgs {
   float* partial;  // [nfrag][F] un-normalised fragment sums
 };
 
+// Row-block owners of the feature-sliced multi-GPU scheme (regnn_peer_rows_t): row v of a result belongs to rank
+// v / per and lives at base[v / per] + (v % per) * ld + col -- a peer-mapped (NVLink) address for remote ranks.
+struct PeerRows {
+  float* const* base;
+  uint32_t per;
+  int64_t ld, col;
+  __device__ __forceinline__ float* row(int64_t v) const {
+    const uint32_t q = (uint32_t)v / per;
+    return base[q] + (size_t)((uint32_t)v - q * per) * ld + col;
+  }
+};
+
+
 template <int VW> struct Vec;
 template <> struct Vec<4> {
   using T = float4;
@@ -189,6 +202,54 @@ __global__ void spmm_frag_finalize_kernel(const int32_t* __restrict__ long_rows,
   }
 }
 
+// Scatter variant of the above for the feature-sliced scheme: the row goes to its owner rank's row block, and
+// (xdx != null) <Xrow[v], dX[v]> is taken here because the finished row is no longer in local memory.
+__global__ void spmm_frag_finalize_peer_kernel(const int32_t* __restrict__ long_rows,
+                                               const int32_t* __restrict__ frag_ptr, int num_long,
+                                               const float* __restrict__ partial, const float* __restrict__ norm_dst,
+                                               PeerRows peers, int F, const float* __restrict__ Xrow, int64_t ldr,
+                                               float* __restrict__ xdx) {
+  __shared__ float red[4];
+  const int l = blockIdx.x;
+  if (l >= num_long) return;
+  const int64_t v = long_rows[l];
+  const int f0 = frag_ptr[l], f1 = frag_ptr[l + 1];
+  const float nd = norm_dst != nullptr ? norm_dst[v] : 1.f;
+  float* yrow = peers.row(v);
+  float p = 0.f;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float s = 0.f;
+    for (int f = f0; f < f1; ++f) s += partial[(size_t)f * F + c];
+    s *= nd;
+    yrow[c] = s;
+    if (xdx != nullptr) p = fmaf(Xrow[(size_t)v * ldr + c], s, p);
+  }
+  if (xdx != nullptr) {  // fixed-shape block reduction (4 warps)
+    p = group_sum<32>(p);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) xdx[v] = (red[0] + red[1]) + (red[2] + red[3]);
+  }
+}
+
+// Row block -> column slabs over peer memory (the input exchange of the feature-sliced scheme): this rank's
+// rows [0, rows) x all F columns are cut into P column slices; slice q lands in rank q's slab
+// [P*per, F/P] at row row_offset + i.  Per peer the destination is ONE contiguous range, written with
+// coalesced 128-bit stores (full NVLink packets); the strided side is the local read.
+__global__ void rows_to_slabs_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int Fc,
+                                     int64_t row_offset, float* const* __restrict__ peer_slabs) {
+  const int q = blockIdx.y;
+  const int L = Fc >> 2;  // 128-bit chunks per slab row
+  const int64_t total = rows * L;
+  float4* dst = reinterpret_cast<float4*>(peer_slabs[q]) + row_offset * L;
+  const float* src = X + (size_t)q * Fc;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / L;
+    const int c = (int)(e - i * L) << 2;
+    dst[e] = ldg4_stream(src + (size_t)i * ldx + c);
+  }
+}
+
 // ---- per-block reduction of lane-local relation bins ------------------------------------------
 // bins: [warps][R][32] floats (lane-local running sums), scratch: [warps][R] doubles.
 __device__ __forceinline__ void reduce_bins(const float* bins, double* scratch, int R,
@@ -246,6 +307,7 @@ struct StreamArgs {
   // spmm_rowgroup_kernel only
   const int32_t* order;  // rows not covered by fragments, by descending slot count
   int64_t n_order;
+  PeerRows peers;        // base != null: result rows go to the row blocks of their owner ranks (peer memory)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -621,7 +683,8 @@ spmm_rowgroup_kernel(StreamArgs sa) {
         st4(a.partial + (size_t)vi * a.F + lg * 4, acc);
       } else {
         scale4(acc, nd);
-        st4(a.Y + (size_t)v * a.ldy + lg * 4, acc);
+        float* yrow = sa.peers.base != nullptr ? sa.peers.row(v) : a.Y + (size_t)v * a.ldy;
+        st4(yrow + lg * 4, acc);  // 64..256 contiguous bytes per row: a full NVLink write packet when remote
       }
     }
   }
@@ -1257,13 +1320,28 @@ static int fill_split(SpmmArgs& a, const regnn_rowsplit_t* split, float* ws, con
   return REGNN_OK;
 }
 
-extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
-                              const float* theta, float alpha, int num_relations,
-                              const float* norm_src, const float* norm_dst, const float* X,
-                              int64_t ldx, float* Y, int64_t ldy, int64_t row_begin,
-                              int64_t row_end, int feat, const regnn_rowsplit_t* split,
-                              float* split_workspace, const int32_t* row_order, void* stream_) {
+// Validates a regnn_peer_rows_t and turns it into the device-side struct (base == null: no scatter).
+static int fill_peers(PeerRows* out, const regnn_peer_rows_t* peers, int feat, int64_t rows, const char* who) {
+  *out = PeerRows{nullptr, 1u, 0, 0};
+  if (peers == nullptr) return REGNN_OK;
+  REGNN_REQUIRE(peers->base != nullptr && peers->num_ranks >= 1 && peers->rows_per_rank >= 1 &&
+                    peers->rows_per_rank < (1ll << 31) && rows <= peers->rows_per_rank * peers->num_ranks &&
+                    peers->col_offset >= 0 && peers->col_offset % 4 == 0 && peers->ld % 4 == 0 &&
+                    peers->ld >= peers->col_offset + feat,
+                REGNN_ERR_INVALID_ARG, "%s: bad peer row-block table", who);
+  *out = PeerRows{peers->base, (uint32_t)peers->rows_per_rank, peers->ld, peers->col_offset};
+  return REGNN_OK;
+}
+
+static int spmm_fwd_impl(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
+                         const float* theta, float alpha, int num_relations,
+                         const float* norm_src, const float* norm_dst, const float* X,
+                         int64_t ldx, float* Y, int64_t ldy, int64_t row_begin,
+                         int64_t row_end, int feat, const regnn_rowsplit_t* split,
+                         float* split_workspace, const int32_t* row_order, const regnn_peer_rows_t* peers,
+                         void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (peers != nullptr) { Y = const_cast<float*>(X); ldy = feat; }  // Y is unused: keep the checks below simple
   REGNN_REQUIRE(indptr && X && Y,  /* per-edge arrays may be NULL when E == 0 */ REGNN_ERR_INVALID_ARG, "spmm_fwd: null pointer");
   REGNN_REQUIRE(etype == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd: etype without theta");
   REGNN_REQUIRE(etype == nullptr || (num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS),
@@ -1282,6 +1360,10 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
   if (rc != REGNN_OK) return rc;
   bool launched = false;
   const int G = rowgroup_lanes(feat, row_order, row_begin, common_align({X, Y, split_workspace}, {ldx, ldy, (int64_t)feat}));
+  rc = fill_peers(&sa.peers, peers, feat, rows, "spmm_fwd");
+  if (rc != REGNN_OK) return rc;
+  REGNN_REQUIRE(peers == nullptr || G != 0, REGNN_ERR_UNSUPPORTED_SHAPE,
+                "spmm_fwd: the peer scatter needs the narrow-row kernel (row_order, full range, F <= 64, F %% 4 == 0)");
   if (G != 0) {  // narrow rows over the degree-sorted row order
     REGNN_REQUIRE(ldx < (1ll << 30), REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: leading dimension too large");
     sa.order = row_order;
@@ -1295,20 +1377,64 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
     REGNN_STREAM_DISPATCH(false, (spmm_stream_kernel<C, VW, BINS><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(sa)))
   }
   REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: no kernel for C=%d VW=%d", sh.C, sh.VW);
-  if (sa.s.nfrag > 0)
+  if (sa.s.nfrag > 0 && peers != nullptr)
+    spmm_frag_finalize_peer_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->frag_ptr, split->num_long,
+                                                                        split_workspace, norm_dst, sa.peers, feat, nullptr, 0,
+                                                                        nullptr);
+  else if (sa.s.nfrag > 0)
     spmm_frag_finalize_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->frag_ptr, split->num_long,
                                                                    split_workspace, norm_dst, Y, ldy, feat, row_begin, row_end);
   return check_launch("regnn_spmm_fwd");
 }
 
-extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t,
-                                    const uint8_t* etype_t, const float* theta, float alpha,
-                                    int num_relations, const float* norm, int norm_sides, const float* X,
-                                    int64_t ldx, const float* Gd, int64_t ldg, float* dX, int64_t lddx,
-                                    int64_t row_begin, int64_t row_end, int feat, double* partials,
-                                    float* d_theta, float* xdx, const regnn_rowsplit_t* split_t,
-                                    float* split_workspace, const int32_t* row_order_t, void* stream_) {
+extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
+                              const float* theta, float alpha, int num_relations,
+                              const float* norm_src, const float* norm_dst, const float* X,
+                              int64_t ldx, float* Y, int64_t ldy, int64_t row_begin,
+                              int64_t row_end, int feat, const regnn_rowsplit_t* split,
+                              float* split_workspace, const int32_t* row_order, void* stream) {
+  return spmm_fwd_impl(indptr, indices, etype, theta, alpha, num_relations, norm_src, norm_dst, X, ldx, Y, ldy,
+                       row_begin, row_end, feat, split, split_workspace, row_order, nullptr, stream);
+}
+
+extern "C" int regnn_spmm_fwd_scatter(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
+                                      const float* theta, float alpha, int num_relations,
+                                      const float* norm_src, const float* norm_dst, const float* X,
+                                      int64_t ldx, int64_t num_rows, int feat, const regnn_rowsplit_t* split,
+                                      float* split_workspace, const int32_t* row_order,
+                                      const regnn_peer_rows_t* peers, void* stream) {
+  REGNN_REQUIRE(peers != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd_scatter: null peer table");
+  return spmm_fwd_impl(indptr, indices, etype, theta, alpha, num_relations, norm_src, norm_dst, X, ldx, nullptr, 0,
+                       0, num_rows, feat, split, split_workspace, row_order, peers, stream);
+}
+
+extern "C" int regnn_rows_to_slabs(const float* X, int64_t ldx, int64_t num_rows, int feat, int num_ranks,
+                                   int64_t row_offset, float* const* peer_slabs, void* stream) {
+  REGNN_REQUIRE(X && peer_slabs && num_ranks >= 1 && num_rows >= 0 && row_offset >= 0, REGNN_ERR_INVALID_ARG,
+                "rows_to_slabs: bad argument");
+  REGNN_REQUIRE(feat % (4 * num_ranks) == 0 && ldx % 4 == 0 && aligned_to(X, 16), REGNN_ERR_UNSUPPORTED_SHAPE,
+                "rows_to_slabs: F=%d must split into whole 128-bit chunks over %d ranks (16-byte aligned rows)", feat,
+                num_ranks);
+  if (num_rows == 0) return REGNN_OK;
+  const int Fc = feat / num_ranks;
+  const int64_t total = num_rows * (Fc / 4);
+  const int64_t want = (total + 255) / 256;
+  const unsigned bx = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  rows_to_slabs_kernel<<<dim3(bx, (unsigned)num_ranks), 256, 0, (cudaStream_t)stream>>>(X, ldx, num_rows, Fc, row_offset,
+                                                                                     peer_slabs);
+  return check_launch("regnn_rows_to_slabs");
+}
+
+static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t,
+                               const uint8_t* etype_t, const float* theta, float alpha,
+                               int num_relations, const float* norm, int norm_sides, const float* X,
+                               int64_t ldx, const float* Gd, int64_t ldg, float* dX, int64_t lddx,
+                               int64_t row_begin, int64_t row_end, int feat, double* partials,
+                               float* d_theta, float* xdx, const regnn_rowsplit_t* split_t,
+                               float* split_workspace, const int32_t* row_order_t, const regnn_peer_rows_t* peers,
+                               void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (peers != nullptr) { dX = const_cast<float*>(X); lddx = ldx; }  // dX is unused: keep the checks below simple
   REGNN_REQUIRE(indptr_t && theta && X && Gd && dX && partials && d_theta,
                 REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: null pointer");
   const int R = num_relations;
@@ -1339,6 +1465,10 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
   bool launched = false;
   const int G = rowgroup_lanes(feat, row_order_t, row_begin,
                                common_align({X, Gd, dX, split_workspace}, {ldx, ldg, lddx, (int64_t)feat}));
+  rc = fill_peers(&sa.peers, peers, feat, rows, "spmm_bwd_fused");
+  if (rc != REGNN_OK) return rc;
+  REGNN_REQUIRE(peers == nullptr || G != 0, REGNN_ERR_UNSUPPORTED_SHAPE,
+                "spmm_bwd_fused: the peer scatter needs the narrow-row kernel (row_order_t, full range, F <= 64, F %% 4 == 0)");
   // persistent kernels: exactly one resident wave (148 SMs x blocks per SM), never more than the partial slots
   if (G != 0) {
     REGNN_REQUIRE(ldg < (1ll << 30), REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_fused: leading dimension too large");
@@ -1348,21 +1478,51 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
     REGNN_ROWGROUP_DISPATCH(true, (rc = set_smem(spmm_rowgroup_kernel<BINS, GL>, gsmem),
                                    nb = min(nb, resident_blocks(spmm_rowgroup_kernel<BINS, GL>, gsmem)),
                                    spmm_rowgroup_kernel<BINS, GL><<<nb, kWarpsPerBlock * 32, gsmem, stream>>>(sa)))
-  } else
-  REGNN_STREAM_DISPATCH(true, (rc = set_smem(spmm_stream_kernel<C, VW, BINS>, smem),
-                               nb = min(nb, resident_blocks(spmm_stream_kernel<C, VW, BINS>, smem)),
-                               spmm_stream_kernel<C, VW, BINS><<<nb, kWarpsPerBlock * 32, smem, stream>>>(sa)))
+  } else {
+    REGNN_STREAM_DISPATCH(true, (rc = set_smem(spmm_stream_kernel<C, VW, BINS>, smem),
+                                 nb = min(nb, resident_blocks(spmm_stream_kernel<C, VW, BINS>, smem)),
+                                 spmm_stream_kernel<C, VW, BINS><<<nb, kWarpsPerBlock * 32, smem, stream>>>(sa)))
+  }
   if (rc != REGNN_OK) return rc;
   REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_fused: no kernel for C=%d VW=%d", sh.C, sh.VW);
-  if (sa.s.nfrag > 0)
+  if (sa.s.nfrag > 0 && peers != nullptr)
+    spmm_frag_finalize_peer_kernel<<<split_t->num_long, 128, 0, stream>>>(split_t->long_rows, split_t->frag_ptr,
+                                                                          split_t->num_long, split_workspace, sa.s.norm_dst,
+                                                                          sa.peers, feat, X, ldx, xdx);
+  else if (sa.s.nfrag > 0)
     spmm_frag_finalize_kernel<<<split_t->num_long, 128, 0, stream>>>(split_t->long_rows, split_t->frag_ptr,
                                                                      split_t->num_long, split_workspace, sa.s.norm_dst, dX,
                                                                      lddx, feat, row_begin, row_end);
-  if (sa.s.nfrag > 0 && xdx != nullptr)
+  if (sa.s.nfrag > 0 && xdx != nullptr && peers == nullptr)
     long_row_xdx_kernel<<<(split_t->num_long + 3) / 4, 128, 0, stream>>>(split_t->long_rows, split_t->num_long, X, ldx, dX,
                                                                          lddx, feat, row_begin, row_end, xdx);
   launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
   return check_launch("regnn_spmm_bwd_fused");
+}
+
+extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t,
+                                    const uint8_t* etype_t, const float* theta, float alpha,
+                                    int num_relations, const float* norm, int norm_sides, const float* X,
+                                    int64_t ldx, const float* Gd, int64_t ldg, float* dX, int64_t lddx,
+                                    int64_t row_begin, int64_t row_end, int feat, double* partials,
+                                    float* d_theta, float* xdx, const regnn_rowsplit_t* split_t,
+                                    float* split_workspace, const int32_t* row_order_t, void* stream) {
+  return spmm_bwd_fused_impl(indptr_t, indices_t, etype_t, theta, alpha, num_relations, norm, norm_sides, X, ldx, Gd, ldg,
+                             dX, lddx, row_begin, row_end, feat, partials, d_theta, xdx, split_t, split_workspace,
+                             row_order_t, nullptr, stream);
+}
+
+extern "C" int regnn_spmm_bwd_fused_scatter(const int32_t* indptr_t, const int32_t* indices_t,
+                                            const uint8_t* etype_t, const float* theta, float alpha,
+                                            int num_relations, const float* norm, int norm_sides, const float* X,
+                                            int64_t ldx, const float* Gd, int64_t ldg, int64_t num_rows, int feat,
+                                            double* partials, float* d_theta, float* xdx,
+                                            const regnn_rowsplit_t* split_t, float* split_workspace,
+                                            const int32_t* row_order_t, const regnn_peer_rows_t* peers, void* stream) {
+  REGNN_REQUIRE(peers != nullptr, REGNN_ERR_INVALID_ARG, "spmm_bwd_fused_scatter: null peer table");
+  return spmm_bwd_fused_impl(indptr_t, indices_t, etype_t, theta, alpha, num_relations, norm, norm_sides, X, ldx, Gd, ldg,
+                             nullptr, 0, 0, num_rows, feat, partials, d_theta, xdx, split_t, split_workspace, row_order_t,
+                             peers, stream);
 }
 
 extern "C" int regnn_rowdot_norm_bwd(const float* norm, int norm_sides, const float* X, int64_t ldx,

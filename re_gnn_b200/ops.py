@@ -173,6 +173,50 @@ def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3, xdx=None):
     return d_norm
 
 
+def rows_to_slabs(x_own, num_ranks, row_offset, peer_slab_ptrs):
+    """Pushes this rank's row block ``x_own`` [rows, F] into every rank's column slab (regnn_rows_to_slabs).
+    ``peer_slab_ptrs``: int64 device tensor [P] of peer-mapped slab base addresses."""
+    x_own = _f32(x_own)
+    with torch.cuda.device(x_own.device):
+        _lib.call('regnn_rows_to_slabs', _ptr(x_own), x_own.stride(0), x_own.shape[0], x_own.shape[1], int(num_ranks),
+                  int(row_offset), _ptr(peer_slab_ptrs), _stream())
+        _lib.count_launches(1)
+
+
+def spmm_scatter(csr, etype, theta, alpha, norm_src, norm_dst, x_cols, peers):
+    """regnn_spmm_fwd_scatter: forward SpMM of a column slab, result rows stored to their owner ranks (``peers``: a
+    ``_lib.PeerRows``)."""
+    x_cols = _f32(x_cols)
+    n = csr['indptr'].numel() - 1
+    f = x_cols.shape[1]
+    theta = _f32(theta).view(-1) if theta is not None else None
+    sp, ws, extra = _split_args(csr.get('split'), f, x_cols.device)
+    with torch.cuda.device(x_cols.device):
+        _lib.call('regnn_spmm_fwd_scatter', _ptr(csr['indptr']), _ptr(csr['indices']),
+                  _ptr(etype) if theta is not None else None, _ptr(theta), float(alpha),
+                  theta.numel() if theta is not None else 0, _ptr(norm_src), _ptr(norm_dst), _ptr(x_cols),
+                  x_cols.stride(0), n, f, sp, _ptr(ws), _ptr(row_order(csr)), ctypes.byref(peers), _stream())
+        _lib.count_launches(1 + extra)
+
+
+def spmm_bwd_fused_scatter(csr, et_t, theta, alpha, norm, x_cols, g_cols, peers, sides=3):
+    """regnn_spmm_bwd_fused_scatter -> d_theta[R] (this rank's columns); the dX rows go to their owner ranks."""
+    x_cols, g_cols = _f32(x_cols), _f32(g_cols)
+    theta = _f32(theta).view(-1)
+    n = csr['indptr_t'].numel() - 1
+    f, r = x_cols.shape[1], theta.numel()
+    partials = torch.empty(_lib.partial_blocks(n) * r, dtype=torch.float64, device=x_cols.device)
+    d_theta = torch.empty(r, dtype=torch.float32, device=x_cols.device)
+    sp, ws, extra = _split_args(csr.get('split_t'), f, x_cols.device)
+    with torch.cuda.device(x_cols.device):
+        _lib.call('regnn_spmm_bwd_fused_scatter', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(et_t), _ptr(theta),
+                  float(alpha), r, _ptr(norm), int(sides), _ptr(x_cols), x_cols.stride(0), _ptr(g_cols),
+                  g_cols.stride(0), n, f, _ptr(partials), _ptr(d_theta), None, sp, _ptr(ws),
+                  _ptr(row_order(csr, True)), ctypes.byref(peers), _stream())
+        _lib.count_launches(2 + extra)
+    return d_theta
+
+
 def _attn_split(split, h, d, device):
     """(byref(struct) | None, workspace | None, extra finalize launches flag) for the attention kernels."""
     if split is None:

@@ -19,7 +19,7 @@ fewer bytes over NVLink than the all-gathers above.
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _lib, ops
 
 
 def row_blocks(indptr, parts, balance='edges'):
@@ -135,6 +135,14 @@ def _columns_to_rows(slab, per, parts, rows_own, group):
     return recv.view(parts, per, fc).permute(1, 0, 2).reshape(per, parts * fc)[:rows_own]
 
 
+def _own_rows_norm_grad(norm, x_own, y_own, g_own, dx_own, rb, re):
+    """d_norm (length N, zero outside [rb, re)) from the owner's complete rows."""
+    d_norm = torch.zeros_like(norm)
+    if re > rb:
+        d_norm[rb:re] = ops.rowdot_norm_bwd(norm[rb:re].contiguous(), x_own, y_own, g_own, dx_own)
+    return d_norm
+
+
 class _ColumnSlabPropagate(torch.autograd.Function):
     """Same contract as ``_PartitionedPropagate`` (row block in, row block out), but the aggregation itself runs
     feature-sliced: every rank propagates ALL rows for F/P of the columns, so the SpMM and its backward need
@@ -155,32 +163,114 @@ class _ColumnSlabPropagate(torch.autograd.Function):
         ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, alpha, norm, norm, x_cols, out=y_cols,
                  split=csr.get('split'), order=ops.row_order(csr) if x_cols.shape[1] <= ops.NARROW_FEAT else None)
         ctx.graph, ctx.etv, ctx.alpha, ctx.bounds, ctx.rank, ctx.group = graph, etv, alpha, bounds, rank, group
-        ctx.save_for_backward(x_cols, y_cols, theta, norm)
-        return _columns_to_rows(y_cols, per, parts, x_own.shape[0], group)
+        y_own = _columns_to_rows(y_cols, per, parts, x_own.shape[0], group)
+        ctx.x_own, ctx.y_own = x_own.detach(), y_own
+        ctx.save_for_backward(x_cols, theta, norm)
+        return y_own
 
     @staticmethod
     def backward(ctx, g_own):
-        x_cols, y_cols, theta, norm = ctx.saved_tensors
+        x_cols, theta, norm = ctx.saved_tensors
         csr = ctx.graph.csr()
         bounds, rank = ctx.bounds, ctx.rank
         parts, per = len(bounds) - 1, _uniform_rows(bounds)
         rb, re = bounds[rank], bounds[rank + 1]
-        g_cols = _rows_to_columns(g_own.contiguous(), per, parts, ctx.group)
+        g_own = g_own.contiguous()
+        g_cols = _rows_to_columns(g_own, per, parts, ctx.group)
         dx_cols = torch.empty_like(x_cols)
-        _, d_theta, xdx = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x_cols, g_cols, out=dx_cols,
-                                             want_xdx=True)
-        # row dot products over this rank's columns only; the sum over ranks completes them
-        d_norm = ops.rowdot_norm_bwd(norm, x_cols, y_cols, g_cols, dx_cols, xdx=xdx)
-        dist.all_reduce(d_norm, op=dist.ReduceOp.SUM, group=ctx.group)
-        # keep the owned rows: the norm's own backward then yields a per-rank share of the relation gradient,
-        # like d_theta above (this rank's columns), and the caller all-reduces the parameter gradient once
-        own = torch.zeros_like(d_norm)
-        own[rb:re] = d_norm[rb:re]
+        _, d_theta, _ = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x_cols, g_cols, out=dx_cols)
         dx_own = _columns_to_rows(dx_cols, per, parts, re - rb, ctx.group)
-        return None, None, dx_own, d_theta.view_as(theta), None, own, None, None, None
+        # the row dot products of d_norm span all columns: the row owner has them all (x, y, dL/dY, dX row blocks),
+        # so this is a local pass; the norm's own backward then yields a per-rank share of the relation gradient,
+        # like d_theta above (this rank's columns), and the caller all-reduces the parameter gradient once
+        d_norm = _own_rows_norm_grad(norm, ctx.x_own, ctx.y_own, g_own, dx_own, rb, re)
+        return None, None, dx_own, d_theta.view_as(theta), None, d_norm, None, None, None
 
 
-def feature_sliced_propagate(graph, etv, x_own, theta, alpha, norm, bounds, rank, group=None):
+class SlabExchange:
+    """Peer-mapped (torch symmetric memory over NVLink) buffers of ONE feature-sliced aggregation call site: the
+    two column slabs (X and dL/dY, [P*per, F/P]) that peers push their row blocks into, and the two row blocks
+    (Y and dX, [per, F]) that the SpMM kernels of all ranks store finished rows into.  Create it once per layer;
+    a forward must be followed by its backward before the next forward (the buffers are reused every step)."""
+
+    def __init__(self, feat, bounds, rank, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.parts, self.per, self.rank, self.feat = len(bounds) - 1, _uniform_rows(bounds), rank, feat
+        if not self.per or feat % (4 * self.parts):
+            raise ValueError('SlabExchange needs equal row blocks and F divisible by 4 * ranks')
+        self.fc = feat // self.parts
+        self._handles = []
+
+        def alloc(rows, cols):
+            t = symm.empty((rows, cols), dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, group)
+            self._handles.append(h)
+            return t, torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=device)
+
+        self.x_cols, self.x_ptrs = alloc(self.parts * self.per, self.fc)
+        self.g_cols, self.g_ptrs = alloc(self.parts * self.per, self.fc)
+        self.y_rows, self.y_ptrs = alloc(self.per, feat)
+        self.dx_rows, self.dx_ptrs = alloc(self.per, feat)
+        self.x_cols.zero_()
+        self.g_cols.zero_()
+        self.peer_y = _lib.PeerRows(self.y_ptrs.data_ptr(), self.parts, self.per, feat, rank * self.fc)
+        self.peer_dx = _lib.PeerRows(self.dx_ptrs.data_ptr(), self.parts, self.per, feat, rank * self.fc)
+        self.barrier()
+
+    def barrier(self):
+        """Device-side barrier across the ranks on the current stream: everything the ranks wrote into each
+        other's buffers before it is visible after it."""
+        self._handles[0].barrier()
+
+
+class _PeerSlabPropagate(torch.autograd.Function):
+    """``_ColumnSlabPropagate`` with both re-partitions done by our own kernels over peer memory: row blocks are
+    pushed into the peers' column slabs (regnn_rows_to_slabs), and the SpMM kernels store every finished row
+    straight into its owner's row block from their epilogue (regnn_spmm_*_scatter) -- no collective library
+    call, no pack / unpack pass.  ``alias=True`` returns views of the exchange buffers (valid until the next
+    step) instead of copies."""
+
+    @staticmethod
+    def forward(ctx, graph, etv, x_own, theta, alpha, norm, bounds, rank, xch, alias):
+        csr = graph.csr()
+        rb, re = bounds[rank], bounds[rank + 1]
+        x_own = x_own.contiguous()
+        ops.rows_to_slabs(x_own, xch.parts, rank * xch.per, xch.x_ptrs)
+        xch.barrier()            # every rank's slice of X has landed in my slab
+        ops.spmm_scatter(csr, etv[0], theta, alpha, norm, norm, xch.x_cols, xch.peer_y)
+        xch.barrier()            # every rank's columns of my rows have landed in my row block
+        y_own = xch.y_rows[:re - rb]
+        if not alias:
+            y_own = y_own.clone()
+        ctx.graph, ctx.etv, ctx.alpha, ctx.bounds, ctx.rank, ctx.xch, ctx.alias = graph, etv, alpha, bounds, rank, xch, alias
+        ctx.x_own, ctx.y_own = x_own.detach(), y_own
+        ctx.save_for_backward(theta, norm)
+        return y_own
+
+    @staticmethod
+    def backward(ctx, g_own):
+        theta, norm = ctx.saved_tensors
+        csr, xch, rank = ctx.graph.csr(), ctx.xch, ctx.rank
+        rb, re = ctx.bounds[rank], ctx.bounds[rank + 1]
+        g_own = g_own.contiguous()
+        ops.rows_to_slabs(g_own, xch.parts, rank * xch.per, xch.g_ptrs)
+        xch.barrier()
+        d_theta = ops.spmm_bwd_fused_scatter(csr, ctx.etv[1], theta, ctx.alpha, norm, xch.x_cols, xch.g_cols, xch.peer_dx)
+        xch.barrier()
+        dx_own = xch.dx_rows[:re - rb]
+        if not ctx.alias:
+            dx_own = dx_own.clone()
+        d_norm = _own_rows_norm_grad(norm, ctx.x_own, ctx.y_own, g_own, dx_own, rb, re)
+        return None, None, dx_own, d_theta.view_as(theta), None, d_norm, None, None, None, None
+
+
+def feature_sliced_propagate(graph, etv, x_own, theta, alpha, norm, bounds, rank, group=None, exchange=None,
+                             alias=False):
+    """Row block in, row block out; the aggregation runs on column slabs.  ``exchange`` (a ``SlabExchange``):
+    re-partition over peer memory inside our own kernels; None: NCCL / gloo all-to-alls."""
+    if exchange is not None:
+        return _PeerSlabPropagate.apply(graph, etv, x_own, theta, alpha, norm, bounds, rank, exchange, alias)
     return _ColumnSlabPropagate.apply(graph, etv, x_own, theta, alpha, norm, bounds, rank, group)
 
 
