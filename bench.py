@@ -451,7 +451,7 @@ def run_ours(args, d):
     vw = 4 if fk >= 96 and fk % 4 == 0 else 2 if fk >= 34 and fk % 2 == 0 else 1
     kname = 'regnn::spmm_stream_kernel<%d,%d,false> (forward launch)' % (max(1, -(-fk // (32 * vw))), vw)
     if fk <= ops.NARROW_FEAT and fk % 4 == 0 and rows is None:
-        kname = 'regnn::spmm_rowgroup_kernel<false,%d> (forward launch)' % (16 if fk > 32 else 8 if fk > 16 else 4)
+        kname = 'regnn::spmm_rowgroup_kernel<false,%d> (forward launch)' % (32 if fk > 64 else 16 if fk > 32 else 8 if fk > 16 else 4)
     roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': alg / tk / 1e9,
                 'peak': hbm, 'peak_source': how, 'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm, 'traffic': traffic,
                 'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3}

@@ -563,21 +563,36 @@ spmm_stream_kernel(StreamArgs sa) {
   if (BINS) reduce_bins(bins, scratch, a.R, sa.partials + (size_t)blockIdx.x * a.R);
 }
 
-// ---- narrow rows (F <= 64): lane-group SpMM over degree-sorted rows -----------------------------------
-// A 128-bit chunk per lane covers a row of F <= 64 floats with G = 4 / 8 / 16 lanes, so a warp works on
+// ---- rows of F <= 128 floats: lane-group SpMM over degree-sorted rows -----------------------------------
+// A 128-bit chunk per lane covers a row of F floats with G = 4 / 8 / 16 / 32 lanes, so a warp works on
 // 32/G rows at once -- one gather instruction fetches 32/G source rows (the column slabs of the
-// feature-sliced multi-GPU scheme, hidden width 64 of the HGB models).  Rows come from `order` (rows not
+// feature-sliced multi-GPU scheme, hidden width 64 of the HGB models, the F = 128 headline workload).  Rows come from `order` (rows not
 // covered by fragments, by descending slot count, built once per graph): neighbouring lane groups get
 // rows of (nearly) equal length, so the warp-uniform trip count wastes almost nothing, and each row is
 // summed by ONE lane group in slot order -- bit-identical to the whole-warp kernels, no cross-lane fold, no
 // row-boundary bookkeeping.  Fragments of long rows (all `threshold` slots long) are the first items.
 // BINS: as in spmm_stream_kernel, but the row-level operand Xrow[u] is one 128-bit register per lane.
+// Occupancy beats loads per warp here as well (measured, MAG graph, F = 64 / 32 / 16 forward): 6 blocks/SM x 2
+// gathers 1.07 / 0.57 / 0.37 ms, 4 x 4: 1.21 / 0.63 / 0.38, 3 x 8: 1.53 / 0.79 / 0.47.  F = 128 (whole warp per
+// row): 8 x 2 2.05 ms, 6 x 2 2.10, 4 x 4 2.35 (the streaming kernel: 2.35); fused backward 4 x 4 2.73 (streaming 2.88).
+#ifndef REGNN_RG_BLOCKS
+#define REGNN_RG_BLOCKS (G == 32 ? 8 : 6)
+#endif
+#ifndef REGNN_RG_U
+#define REGNN_RG_U 2
+#endif
+#ifndef REGNN_RGB_BLOCKS
+#define REGNN_RGB_BLOCKS 4
+#endif
+#ifndef REGNN_RGB_U
+#define REGNN_RGB_U 4
+#endif
 template <bool BINS, int G>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, BINS ? REGNN_RGB_BLOCKS : REGNN_RG_BLOCKS)
 spmm_rowgroup_kernel(StreamArgs sa) {
-  static_assert(G == 4 || G == 8 || G == 16, "lane groups of 4, 8 or 16 lanes");
-  constexpr int GPW = 32 / G;  // rows per warp
-  constexpr int U = 4;         // gathers in flight per lane
+  static_assert(G == 4 || G == 8 || G == 16 || G == 32, "lane groups of 4, 8, 16 or 32 lanes");
+  constexpr int GPW = 32 / G;                          // rows per warp
+  constexpr int U = BINS ? REGNN_RGB_U : REGNN_RG_U;   // gathers in flight per lane
   const SpmmArgs& a = sa.s;
   __shared__ float w_s[256];
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -1280,9 +1295,12 @@ static int common_align(std::initializer_list<const void*> ptrs, std::initialize
 
 // Lane-group width of spmm_rowgroup_kernel for this call, or 0 when the whole-warp kernels must run: needs the
 // degree-sorted row order (which lists the rows of the FULL range), F <= 64 in whole 128-bit chunks, 16-byte rows.
+#ifndef REGNN_RG_MAXF
+#define REGNN_RG_MAXF 128  // one 128-bit chunk per lane: up to a whole warp per row
+#endif
 static int rowgroup_lanes(int F, const int32_t* order, int64_t row_begin, int align) {
-  if (order == nullptr || row_begin != 0 || F > 64 || F % 4 != 0 || align < 16) return 0;
-  return F > 32 ? 16 : (F > 16 ? 8 : 4);
+  if (order == nullptr || row_begin != 0 || F > REGNN_RG_MAXF || F % 4 != 0 || align < 16) return 0;
+  return F > 64 ? 32 : (F > 32 ? 16 : (F > 16 ? 8 : 4));
 }
 #define REGNN_ROWGROUP_CASE(G_, BINS_, CALL) \
   if (G == G_) {                             \
@@ -1291,8 +1309,9 @@ static int rowgroup_lanes(int F, const int32_t* order, int64_t row_begin, int al
     CALL;                                    \
     launched = true;                         \
   }
-#define REGNN_ROWGROUP_DISPATCH(BINS_, CALL) \
-  REGNN_ROWGROUP_CASE(16, BINS_, CALL) REGNN_ROWGROUP_CASE(8, BINS_, CALL) REGNN_ROWGROUP_CASE(4, BINS_, CALL)
+#define REGNN_ROWGROUP_DISPATCH(BINS_, CALL)                                                               \
+  REGNN_ROWGROUP_CASE(32, BINS_, CALL) REGNN_ROWGROUP_CASE(16, BINS_, CALL) REGNN_ROWGROUP_CASE(8, BINS_, CALL) \
+  REGNN_ROWGROUP_CASE(4, BINS_, CALL)
 
 template <typename K>
 static int resident_blocks(K kernel, size_t smem) {

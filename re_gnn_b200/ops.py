@@ -5,6 +5,7 @@ and the current CUDA stream, and raises on any error.  No arithmetic happens her
 CPU branch: tensors must live on a CUDA device.
 """
 import ctypes
+import os
 
 import torch
 
@@ -69,7 +70,8 @@ def _split_args(split, feat, device):
     return ctypes.byref(split['struct']), ws, 1
 
 
-NARROW_FEAT = 64   # widths up to this run the lane-group kernel when the degree-sorted row order is supplied
+# widths up to this run the lane-group kernel when the degree-sorted row order is supplied
+NARROW_FEAT = int(os.environ.get('REGNN_NARROW_FEAT', '128'))
 
 
 def row_order(csr, transposed=False):

@@ -16,6 +16,6 @@ $CMD > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches exit $?"
 $CMD > $OUT/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"spmm_stream_kernel" -s 4 -c 4 -o $OUT/${TAG}_spmm $CMD > $OUT/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"spmm_(stream|rowgroup)_kernel" -s 4 -c 4 -o $OUT/${TAG}_spmm $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la $OUT

@@ -406,7 +406,7 @@ def test_mag_regcn_layer_and_train_step():
 
 
 # ---- narrow-row kernels (lane groups over degree-sorted rows) against the whole-warp kernels --------------------
-@pytest.mark.parametrize('f', [4, 8, 16, 20, 32, 48, 64])
+@pytest.mark.parametrize('f', [4, 8, 16, 20, 32, 48, 64, 96, 128])
 @pytest.mark.parametrize('weighted', [True, False])
 def test_narrow_row_kernels_equal_whole_warp_kernels(f, weighted):
     from re_gnn_b200 import ops
