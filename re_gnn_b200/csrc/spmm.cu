@@ -588,12 +588,18 @@ spmm_stream_kernel(StreamArgs sa) {
 #ifndef REGNN_RGB_U
 #define REGNN_RGB_U 4
 #endif
+// Cooperative slot loads pay off where the kernel is issue-bound (fused backward: 2.73 -> 2.44 ms at F = 128,
+// 1.37 -> 1.22 at 64, 0.53 -> 0.50 at 16); the forward kernel is HBM-bound and slightly faster without (2.05 vs 2.14).
+#ifndef REGNN_RG_COOP
+#define REGNN_RG_COOP BINS
+#endif
 template <bool BINS, int G>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, BINS ? REGNN_RGB_BLOCKS : REGNN_RG_BLOCKS)
 spmm_rowgroup_kernel(StreamArgs sa) {
   static_assert(G == 4 || G == 8 || G == 16 || G == 32, "lane groups of 4, 8, 16 or 32 lanes");
   constexpr int GPW = 32 / G;                          // rows per warp
   constexpr int U = BINS ? REGNN_RGB_U : REGNN_RG_U;   // gathers in flight per lane
+  constexpr bool kCoop = REGNN_RG_COOP;
   const SpmmArgs& a = sa.s;
   __shared__ float w_s[256];
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -644,46 +650,100 @@ spmm_rowgroup_kernel(StreamArgs sa) {
     const int32_t* ip = a.indices + begin;
     const uint8_t* ep = a.etype + begin;
 
-    int nidx[U], net[U];  // next round's column indices / edge types (-1 = no slot)
+    if constexpr (kCoop) {
+      // Cooperative slot loads: lane lg of a group holds slot t0+lg of the group's row (column index, edge type,
+      // norm[src], coefficient) -- one coalesced load per G slots, broadcast inside the group by shuffles --
+      // instead of every lane loading every slot's scalars.  The next batch is in flight behind the gathers.
+      static_assert(G % U == 0, "a round must not straddle a slot batch");
+      const int gbase = lane & ~(G - 1);
+      auto load_batch = [&](int t0, int& bi, int& be, float& bn) {
+        const int t = t0 + lg;
+        bi = -1;
+        be = 0;
+        bn = 0.f;
+        if (t < len) {
+          bi = __ldg(ip + t);
+          be = weighted ? (int)__ldg(ep + t) : 0;
+          bn = a.norm_src != nullptr ? __ldg(a.norm_src + bi) : 1.f;
+        }
+      };
+      int nbi, nbe;
+      float nbn;
+      load_batch(0, nbi, nbe, nbn);
+      for (int t0 = 0; t0 < maxlen; t0 += G) {
+        const int bi = nbi, be = nbe;
+        const float bn = nbn;
+        const float bc = (weighted ? w_s[be] : 1.f) * bn;  // 0 for a missing slot
+        if (t0 + G < maxlen) load_batch(t0 + G, nbi, nbe, nbn);
+        const int cnt = min(G, maxlen - t0);
+        for (int j = 0; j < cnt; j += U) {
+          float4 x[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      nidx[u] = u < len ? __ldg(ip + u) : -1;
-      net[u] = (weighted && u < len) ? (int)__ldg(ep + u) : 0;
-    }
-    for (int t = 0; t < maxlen; t += U) {
-      int idx[U], et[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        idx[u] = nidx[u];
-        et[u] = net[u];
-      }
-      float4 x[U];
-      float ns[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = idx[u] >= 0;
-        x[u] = ok ? ldg4(reinterpret_cast<const float*>(xbytes + (uint64_t)(uint32_t)idx[u] * ldxb))
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        ns[u] = ok ? (a.norm_src != nullptr ? __ldg(a.norm_src + idx[u]) : 1.f) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {  // indices of the next round: in flight behind this round's gathers
-        const int tn = t + U + u;
-        nidx[u] = tn < len ? __ldg(ip + tn) : -1;
-        net[u] = (weighted && tn < len) ? (int)__ldg(ep + tn) : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float coef = (weighted ? w_s[et[u]] : 1.f) * ns[u];  // 0 for a missing slot
-        fma4(acc, coef, x[u]);
-        if (BINS) {
-          const float d = dot4(x[u], trow);
-          if (idx[u] >= 0 && et[u] != cur_rel) {  // lane-local bin, slot order, bank-conflict free
-            mybins[cur_rel * 32] += racc;
-            racc = 0.f;
-            cur_rel = et[u];
+          for (int u = 0; u < U; ++u) {
+            const int si = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+            x[u] = si >= 0 ? ldg4(reinterpret_cast<const float*>(xbytes + (uint64_t)(uint32_t)si * ldxb))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          racc = fmaf(ns[u] * nd, d, racc);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int from = gbase + j + u;
+            fma4(acc, __shfl_sync(0xffffffffu, bc, from), x[u]);
+            if (BINS) {
+              const int se = __shfl_sync(0xffffffffu, be, from);
+              const float sn = __shfl_sync(0xffffffffu, bn, from);
+              const float d = dot4(x[u], trow);
+              if (t0 + j + u < len && se != cur_rel) {  // lane-local bin, slot order, bank-conflict free
+                mybins[cur_rel * 32] += racc;
+                racc = 0.f;
+                cur_rel = se;
+              }
+              racc = fmaf(sn * nd, d, racc);
+            }
+          }
+        }
+      }
+    } else {
+      int nidx[U], net[U];  // next round's column indices / edge types (-1 = no slot)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        nidx[u] = u < len ? __ldg(ip + u) : -1;
+        net[u] = (weighted && u < len) ? (int)__ldg(ep + u) : 0;
+      }
+      for (int t = 0; t < maxlen; t += U) {
+        int idx[U], et[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          idx[u] = nidx[u];
+          et[u] = net[u];
+        }
+        float4 x[U];
+        float ns[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool ok = idx[u] >= 0;
+          x[u] = ok ? ldg4(reinterpret_cast<const float*>(xbytes + (uint64_t)(uint32_t)idx[u] * ldxb))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          ns[u] = ok ? (a.norm_src != nullptr ? __ldg(a.norm_src + idx[u]) : 1.f) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // indices of the next round: in flight behind this round's gathers
+          const int tn = t + U + u;
+          nidx[u] = tn < len ? __ldg(ip + tn) : -1;
+          net[u] = (weighted && tn < len) ? (int)__ldg(ep + tn) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float coef = (weighted ? w_s[et[u]] : 1.f) * ns[u];  // 0 for a missing slot
+          fma4(acc, coef, x[u]);
+          if (BINS) {
+            const float d = dot4(x[u], trow);
+            if (idx[u] >= 0 && et[u] != cur_rel) {  // lane-local bin, slot order, bank-conflict free
+              mybins[cur_rel * 32] += racc;
+              racc = 0.f;
+              cur_rel = et[u];
+            }
+            racc = fmaf(ns[u] * nd, d, racc);
+          }
         }
       }
     }

@@ -41,7 +41,8 @@ def t(name, fn, iters=20):
 print('N=%d E=%d F=%d' % (n, e, feat))
 t('wdeg_norm_fwd (counts)', lambda: ops.wdeg_norm_fwd(csr, etv[0], theta, 100.0, -0.5, counts=etv[2]))
 t('wdeg_norm_fwd (slots)', lambda: ops.wdeg_norm_fwd(csr, etv[0], theta, 100.0, -0.5))
-t('spmm fwd', lambda: ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, 100.0, norm, norm, x, split=csr.get('split')))
+t('spmm fwd (stream kernel)', lambda: ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, 100.0, norm, norm, x, split=csr.get('split')))
+t('spmm fwd (row-group kernel)', lambda: ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, 100.0, norm, norm, x, split=csr.get('split'), order=ops.row_order(csr)))
 t('spmm transposed (plain bwd_x)', lambda: ops.spmm(csr['indptr_t'], csr['indices_t'], etv[1], theta, 100.0, norm, norm, gout, split=csr.get('split_t')))
 t('spmm_bwd_fused (no xdx)', lambda: ops.spmm_bwd_fused(csr, etv[1], theta, 100.0, norm, x, gout))
 t('spmm_bwd_fused (+xdx)', lambda: ops.spmm_bwd_fused(csr, etv[1], theta, 100.0, norm, x, gout, want_xdx=True))
