@@ -70,3 +70,41 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libregnn_b200.so')
     with pytest.raises(RuntimeError, match='no CPU or eager fallback'):
         _lib.load()
+
+
+def test_struct_layouts_match_the_c_header(tmp_path):
+    """The header compiles as plain C and the ctypes mirrors of its structs have the C compiler's layout."""
+    import subprocess
+    from re_gnn_b200 import _lib
+    src = tmp_path / 'layout.c'
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "regnn_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(regnn_rowsplit_t), offsetof(regnn_rowsplit_t, frag_begin),
+         offsetof(regnn_rowsplit_t, num_long), offsetof(regnn_rowsplit_t, threshold), sizeof(regnn_peer_rows_t),
+         offsetof(regnn_peer_rows_t, num_ranks), offsetof(regnn_peer_rows_t, rows_per_rank),
+         offsetof(regnn_peer_rows_t, col_offset));
+  return 0;
+}
+''')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)],
+                   check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    rs, pr = _lib.RowSplit, _lib.PeerRows
+    want = [ctypes.sizeof(rs), rs.frag_begin.offset, rs.num_long.offset, rs.threshold.offset, ctypes.sizeof(pr),
+            pr.num_ranks.offset, pr.rows_per_rank.offset, pr.col_offset.offset]
+    assert got == want
+
+
+def test_scatter_entry_points_validate_arguments(lib):
+    """The peer-memory variants reject a missing peer table / a shape the narrow-row kernel cannot take before any launch."""
+    from re_gnn_b200 import _lib
+    assert lib.regnn_spmm_fwd_scatter(None, None, None, None, 1.0, 0, None, None, None, 4, 8, 4, None, None, None, None,
+                                      None) == -1
+    assert b'peer' in lib.regnn_last_error_string()
+    assert lib.regnn_rows_to_slabs(None, 4, 8, 4, 2, 0, None, None) == -1
+    peers = _lib.PeerRows(1, 2, 4, 6, 0)   # ld 6 is not a multiple of 4 floats
+    assert lib.regnn_spmm_bwd_fused_scatter(None, None, None, None, 1.0, 1, None, 3, None, 4, None, 4, 8, 4, None, None,
+                                            None, None, None, None, ctypes.byref(peers), None) == -1

@@ -142,3 +142,17 @@ def test_mirrored_models_match_reference_golden(name, cpu_ops):
     case = helpers.load_case(name)
     net, feats, out = helpers.run_model_case(our_model, Graph, case)
     helpers.check_model_case(case, net, feats, out, 1e-9, 1e-8)
+
+
+def test_row_order_lists_short_rows_by_descending_slot_count():
+    """ops.row_order: the work list of the narrow-row kernels (host-side index bookkeeping, device-independent)."""
+    import ctypes
+    from re_gnn_b200 import _lib, ops
+    indptr = torch.tensor([0, 3, 3, 10, 11, 11, 16, 19], dtype=torch.int32)     # slot counts 3 0 7 1 0 5 3
+    csr = {'indptr': indptr, 'indptr_t': indptr, 'split': None, 'split_t': None}
+    assert ops.row_order(csr).tolist() == [2, 5, 0, 6, 3, 1, 4]                 # stable: ties by ascending row id
+    assert ops.row_order(csr) is csr['order'] and ops.row_order(csr).dtype == torch.int32
+    # rows cut into fragments (more slots than the threshold) are not in the list
+    split = {'struct': _lib.RowSplit(None, None, None, None, 2, 4, 4)}          # two long rows at threshold 4
+    csr_t = {'indptr': indptr, 'indptr_t': indptr, 'split': None, 'split_t': split}
+    assert ops.row_order(csr_t, True).tolist() == [0, 6, 3, 1, 4]
