@@ -487,11 +487,16 @@ def test_column_slab_kernels_equal_full_run(parts, f):
     helpers.assert_close(dn_p.cpu(), dn.double().cpu(), 10 * RTOL, 'd_norm (sum of column shares)', atol=1e-5)
 
 
-def test_feature_sliced_propagate_world1_nccl():
-    """Single-rank NCCL group: the all-to-all plumbing of partition.feature_sliced_propagate degenerates to copies and
-    the result must equal functional.propagate."""
+@pytest.mark.parametrize('peer', [False, True])
+def test_feature_sliced_propagate_world1_nccl(peer):
+    """Single-rank NCCL group: the re-partition plumbing of partition.feature_sliced_propagate degenerates to copies and
+    the result must equal functional.propagate.  peer=True runs the peer-memory variant (regnn_rows_to_slabs and the
+    *_scatter SpMM epilogues through a SlabExchange whose only peer is this rank) -- the kernels the multi-GPU default
+    uses; scripts/check_multi_gpu.py is the same check across 2 / 8 real ranks."""
     import torch.distributed as dist
     from re_gnn_b200 import functional as RF, partition
+    if DEV == 'cpu' and peer:
+        pytest.skip('peer-mapped memory needs a GPU')
     if not dist.is_initialized():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', str(29400 + os.getpid() % 500))
@@ -507,19 +512,22 @@ def test_feature_sliced_propagate_world1_nccl():
         gen = torch.Generator(device=DEV).manual_seed(8)
         x = torch.randn(n, f, device=DEV, generator=gen)
         gout = torch.randn(n, f, device=DEV, generator=gen)
+        bounds = partition.row_blocks(g.csr()['indptr'], 1, balance='rows')
+        xch = partition.SlabExchange(f, bounds, 0, torch.device(DEV)) if peer else None
         res = []
-        for fn in (None, partition.feature_sliced_propagate):
+        for fn in (None, partition.feature_sliced_propagate, partition.feature_sliced_propagate):
             xs = x.clone().requires_grad_(True)
             th = _theta(r, 1, 5).to(DEV, torch.float32).requires_grad_(True)
             nrm = RF.weighted_degree_norm(g, etv, th, 100.0, -0.5)
             if fn is None:
                 out = RF.propagate(g, etv, xs, th, 100.0, nrm)
-            else:
-                out = fn(g, etv, xs, th, 100.0, nrm, partition.row_blocks(g.csr()['indptr'], 1, balance='rows'), 0)
+            else:   # twice: the exchange buffers are reused from step to step
+                out = fn(g, etv, xs, th, 100.0, nrm, bounds, 0, exchange=xch)
             out.backward(gout)
-            res.append((out.detach(), xs.grad, th.grad))
-        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
-        helpers.assert_close(res[1][2].cpu(), res[0][2].cpu(), RTOL, 'd_theta')
+            res.append((out.detach().clone(), xs.grad.clone(), th.grad.clone()))
+        for k in (1, 2):
+            assert torch.equal(res[0][0], res[k][0]) and torch.equal(res[0][1], res[k][1])
+            helpers.assert_close(res[k][2].cpu(), res[0][2].cpu(), RTOL, 'd_theta')
     finally:
         dist.destroy_process_group()
 
