@@ -16,6 +16,8 @@ Parity status: the reference ships no tests, golden vectors or fixtures, and its
     ``tests/test_oracle_golden.py`` checks every function below against them;
   * ``tests/test_oracle_dense.py`` checks it against an independent dense-adjacency formulation
     in float64 and against analytic known answers.
+  * the MAG-stack functions (``mag_*``) are pinned the same way through ``oracle/pyg_stub`` and
+    ``tests/golden/mag/*.npz`` (see the comment above them).
 The DGL primitive semantics themselves (u_mul_e/copy_u/u_add_v + sum, edge_softmax) remain
 "parity unpinned": no DGL binary is available to confirm them.
 
@@ -205,8 +207,12 @@ def regcn_model_forward(src, dst, etype, num_nodes, features_list, params, alpha
 
 
 # ------------------------------------------------------------------------------------------------
-# MAG stack (PyG API).  PyG / torch_scatter cannot be installed here, so this restatement of
-# mag/regnn_layers.py is "parity unpinned" (no reference run to compare with).
+# MAG stack (PyG API).  PyG / torch_scatter cannot be installed here; these restatements of mag/regnn_layers.py are
+# pinned to fixtures recorded from the reference's own, unmodified mag/regnn_layers.py + mag/utils.py run over
+# oracle/pyg_stub (tests/golden/make_golden_mag.py -> tests/golden/mag/*.npz, checked by tests/test_oracle_golden.py).
+# The PyG MessagePassing / torch_scatter primitive semantics themselves remain "parity unpinned" (no PyG binary).
+# mag/regnn_saint.py is a script (its classes cannot be imported without running it): saint_regcn_forward below
+# restates it by reading and stays "parity unpinned".
 def mag_regcn_forward(x_src, x_target, edge_index, edge_type, target_node_type, weight, bias, relation_weight,
                       scaling_factor, num_edge_types, self_loop_type=2, residual=False):
     """mag/regnn_layers.py:80-150 (``REGCNConv.forward``; ``aggr='mean'``, bias added in ``update``)."""
@@ -225,6 +231,69 @@ def mag_regcn_forward(x_src, x_target, edge_index, edge_type, target_node_type, 
     if residual:
         out = out + x_target @ weight                                             # weight_root aliases weight (:50)
     return out
+
+
+def _mag_self_loops(edge_index, edge_type, target_node_type, num_edge_types, self_loop_type, n_dst):
+    """mag/regnn_layers.py:90-96 / :237-243 / :365-371: self_loop_type 2 appends one loop per target whose type
+    is num_edge_types + node type; types 1 and 3 leave the edge list alone."""
+    src, dst = edge_index[0], edge_index[1]
+    if self_loop_type == 2:
+        loop = torch.arange(n_dst, dtype=src.dtype)
+        src, dst = torch.cat([src, loop]), torch.cat([dst, loop])
+        edge_type = torch.cat([edge_type, target_node_type + num_edge_types])
+    return src, dst, edge_type
+
+
+def _mag_softmax(logits, dst, n_dst):
+    """mag/utils.py:28-57: softmax over the in-edges of every target, stabilised with the GLOBAL maximum (all edges,
+    all heads) and with 1e-16 added to the denominator."""
+    out = (logits - logits.max()).exp()
+    den = torch.zeros((n_dst,) + tuple(out.shape[1:]), dtype=out.dtype).index_add(0, dst, out)
+    return out / (den[dst] + 1e-16)
+
+
+def _mag_attention_tail(out, x_dst, bias, heads, out_channels, concat, residual):
+    """mag/regnn_layers.py:275-284 / :413-422 (use_norm None)."""
+    out = out.reshape(-1, heads * out_channels) if concat else out.mean(dim=1)
+    out = out + bias
+    if residual:
+        out = out + x_dst.reshape(-1, heads * out_channels)
+    return out
+
+
+def mag_regat_forward(x_src, x_target, edge_index, edge_type, target_node_type, lin_weight, att_src, att_dst, bias,
+                      relation_weight, scaling_factor, num_edge_types, heads, out_channels, negative_slope=0.2,
+                      self_loop_type=2, residual=False, concat=True):
+    """mag/regnn_layers.py:221-296 (``REGATConv.forward``; ``lin_dst`` aliases ``lin_src``, :188; aggr='add')."""
+    h, c = heads, out_channels
+    xs = (x_src @ lin_weight.t()).view(-1, h, c)                                   # :226-234
+    xd = (x_target @ lin_weight.t()).view(-1, h, c)
+    src, dst, edge_type = _mag_self_loops(edge_index, edge_type, target_node_type, num_edge_types, self_loop_type,
+                                          xd.shape[0])
+    a_src = (xs * att_src).sum(-1)                                                 # :254-255
+    a_dst = (xd * att_dst).sum(-1)
+    w = F.leaky_relu(relation_weight * scaling_factor, RELATION_SLOPE)[edge_type]  # :258-261, [E,H]
+    logits = F.leaky_relu(w + a_src[src] + a_dst[dst], negative_slope)             # :263-267
+    ew = _mag_softmax(logits, dst, xd.shape[0])                                    # :269
+    out = torch.zeros_like(xd).index_add(0, dst, ew.unsqueeze(-1) * xs[src])       # :273, message :294-296
+    return _mag_attention_tail(out, xd, bias, h, c, concat, residual)
+
+
+def mag_regatv2_forward(x_src, x_target, edge_index, edge_type, target_node_type, lin_weight, att, bias,
+                        relation_weight, scaling_factor, num_edge_types, heads, out_channels, negative_slope=0.2,
+                        self_loop_type=2, residual=False, concat=True):
+    """mag/regnn_layers.py:354-433 (``REGATv2Conv.forward``): the relation term is added AFTER the attention
+    product and there is no outer LeakyReLU."""
+    h, c = heads, out_channels
+    xs = (x_src @ lin_weight.t()).view(-1, h, c)
+    xd = (x_target @ lin_weight.t()).view(-1, h, c)
+    src, dst, edge_type = _mag_self_loops(edge_index, edge_type, target_node_type, num_edge_types, self_loop_type,
+                                          xd.shape[0])
+    alpha = (F.leaky_relu(xs[src] + xd[dst], negative_slope) * att).sum(-1)        # :388-393
+    w = F.leaky_relu(relation_weight * scaling_factor, RELATION_SLOPE)[edge_type]  # :396-399
+    ew = _mag_softmax(w + alpha, dst, xd.shape[0])                                 # :401-403
+    out = torch.zeros_like(xd).index_add(0, dst, ew.unsqueeze(-1) * xs[src])
+    return _mag_attention_tail(out, xd, bias, h, c, concat, residual)
 
 
 def saint_regcn_forward(x, edge_index, edge_type, weight, bias, relation_weight, scaling_factor):

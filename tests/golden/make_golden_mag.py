@@ -1,0 +1,90 @@
+"""Golden fixtures for the MAG-stack layers, generated from the REFERENCE'S OWN ``mag/regnn_layers.py``.
+
+Run in the build container (needs /root/reference; the GPU box never runs this):
+
+    python tests/golden/make_golden_mag.py
+
+How: ``oracle/pyg_stub`` (a pure-PyTorch restatement of the PyG / torch-scatter primitives the file uses) is put on
+``sys.path``, then the reference's unmodified ``mag/regnn_layers.py`` (and the ``mag/utils.py`` it imports) run in
+float64 on small seeded bipartite blocks of the shape PyG's NeighborSampler hands to the layers (targets are the
+first ``n_dst`` sources).  Inputs, parameters, outputs and all gradients go to ``tests/golden/mag/<case>.npz``.
+"""
+import json
+import zlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('REGNN_REFERENCE', '/root/reference')
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'pyg_stub'))
+sys.path.insert(0, os.path.join(REF, 'mag'))
+torch.set_default_dtype(torch.float64)   # the reference builds its one-hot edge features with the default dtype
+
+import regnn_layers as RL  # noqa: E402  (the reference)
+
+NUM_NODE_TYPES, NUM_EDGE_TYPES, ALPHA = 3, 5, 100.0
+
+
+def block(seed, n_src=60, n_dst=25, e=300, empty_targets=True):
+    """Random bipartite multigraph: duplicate edges, two hub targets, (optionally) targets without in-edges."""
+    rng = np.random.RandomState(seed)
+    src = rng.randint(0, n_src, size=e)
+    lo = 5 if empty_targets else 0
+    dst = np.where(rng.rand(e) < 0.3, rng.randint(lo, lo + 2, size=e), rng.randint(lo, n_dst, size=e))
+    et = rng.randint(0, NUM_EDGE_TYPES, size=e)
+    tnt = rng.randint(0, NUM_NODE_TYPES, size=n_dst)
+    return (np.stack([src, dst]).astype(np.int64), et.astype(np.int64), tnt.astype(np.int64), n_src, n_dst)
+
+
+def save_case(name, kind, kw, blk, tuple_input=True):
+    edge_index, et, tnt, n_src, n_dst = blk
+    rng = np.random.RandomState(zlib.crc32(name.encode()) % (2 ** 31))
+    torch.manual_seed(11)
+    mod = getattr(RL, kind)(16, 8, NUM_NODE_TYPES, NUM_EDGE_TYPES, **kw)
+    with torch.no_grad():      # non-trivial relation embeddings (one negative entry) and bias
+        mod.relation_weight.copy_(torch.as_tensor(rng.uniform(0.5, 1.5, size=tuple(mod.relation_weight.shape)) / ALPHA))
+        mod.relation_weight.view(-1)[0] = -0.7 / ALPHA
+        mod.bias.copy_(torch.as_tensor(rng.randn(*mod.bias.shape) * 0.1))
+    x_src = torch.as_tensor(rng.randn(n_src, 16)).requires_grad_(True)
+    x_in = (x_src, x_src[:n_dst]) if tuple_input else x_src
+    out = mod(x_in, torch.as_tensor(edge_index), torch.as_tensor(et), torch.as_tensor(tnt))
+    gout = torch.as_tensor(np.random.RandomState(7).randn(*out.shape))
+    out.backward(gout)
+    blob = dict(edge_index=edge_index, edge_type=et, target_node_type=tnt, n_src=np.int64(n_src), n_dst=np.int64(n_dst),
+                x_src=x_src.detach().numpy(), gx_src=x_src.grad.numpy(), out=out.detach().numpy(), gout=gout.numpy(),
+                meta=np.array(json.dumps(dict(kind=kind, kw=kw, tuple_input=tuple_input, in_channels=16, out_channels=8,
+                                              num_node_types=NUM_NODE_TYPES, num_edge_types=NUM_EDGE_TYPES))))
+    for k, v in mod.state_dict().items():
+        blob['param::' + k] = v.detach().numpy()
+    for k, p in mod.named_parameters():
+        blob['grad::' + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    np.savez_compressed(os.path.join(HERE, 'mag', name + '.npz'), **blob)
+    print('%-30s out %s' % (name, tuple(out.shape)))
+
+
+def main():
+    b1, b2 = block(1), block(2, empty_targets=False)
+    square = block(3, n_src=40, n_dst=40, e=260)       # full-graph inference shape: targets == sources
+    for name, kw, blk in [
+        ('regcn_loop2', dict(self_loop_type=2), b1),
+        ('regcn_loop1_residual', dict(self_loop_type=1, residual=True), b1),     # targets without in-edges: mean of nothing
+        ('regcn_loop3', dict(self_loop_type=3), b2),
+        ('regcn_loop2_residual_square', dict(self_loop_type=2, residual=True), square),
+    ]:
+        save_case(name, 'REGCNConv', kw, blk)
+    for kind, tag in [('REGATConv', 'regat'), ('REGATv2Conv', 'regatv2')]:
+        for name, kw, blk, tup in [
+            (tag + '_h2_loop2', dict(heads=2, self_loop_type=2), b1, True),
+            (tag + '_h4_loop1_residual', dict(heads=4, self_loop_type=1, residual=True), b1, True),
+            (tag + '_h2_mean', dict(heads=2, self_loop_type=2, concat=False), b2, True),
+            (tag + '_h1_tensor_input', dict(heads=1, self_loop_type=2, negative_slope=0.05), square, False),
+        ]:
+            save_case(name, kind, kw, blk, tup)
+
+
+if __name__ == '__main__':
+    main()

@@ -98,3 +98,18 @@ def check_model_case(case, net, feats, out, rtol, grad_rtol=None):
     for k, p in net.named_parameters():
         got = p.grad if p.grad is not None else torch.zeros_like(p)
         assert_close(got.cpu(), case['grad::' + k], grad_rtol, 'd_' + k)
+
+
+MAG_GOLDEN = os.path.join(GOLDEN, 'mag')
+
+
+def mag_golden_cases(prefix=''):
+    """Fixtures recorded from the reference's own mag/regnn_layers.py over oracle/pyg_stub (make_golden_mag.py)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(MAG_GOLDEN, prefix + '*.npz')))
+
+
+def load_mag_case(name):
+    z = np.load(os.path.join(MAG_GOLDEN, name + '.npz'), allow_pickle=False)
+    case = {k: z[k] for k in z.files}
+    case['meta'] = json.loads(str(case['meta']))
+    return case

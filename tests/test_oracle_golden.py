@@ -91,3 +91,40 @@ def test_oracle_regcn_model_matches_reference_golden():
                                        torch.as_tensor(case['etype']), int(case['num_nodes']), feats, params,
                                        meta['args'][1], n_layers, F.elu)
         helpers.assert_close(out, case['out0'], 1e-12, name)
+
+
+# ---- MAG-stack layers: fixtures from the reference's own mag/regnn_layers.py over the PyG-semantics stub ----------
+@pytest.mark.parametrize('name', helpers.mag_golden_cases())
+def test_mag_oracle_matches_reference_layer_code(name):
+    c = helpers.load_mag_case(name)
+    m, kw = c['meta'], c['meta']['kw']
+    t = lambda k: torch.as_tensor(c[k])  # noqa: E731
+    p = {k[7:]: torch.as_tensor(v).clone().requires_grad_(True) for k, v in c.items() if k.startswith('param::')}
+    x = t('x_src').clone().requires_grad_(True)
+    n_dst = int(c['n_dst'])
+    common = (x, x[:n_dst], t('edge_index'), t('edge_type'), t('target_node_type'))
+    slt, res = kw.get('self_loop_type', 1), kw.get('residual', False)
+    if m['kind'] == 'REGCNConv':
+        out = O.mag_regcn_forward(*common, p['weight'], p['bias'], p['relation_weight'], 100.0, m['num_edge_types'], slt, res)
+    elif m['kind'] == 'REGATConv':
+        out = O.mag_regat_forward(*common, p['lin_src.weight'], p['att_src'], p['att_dst'], p['bias'], p['relation_weight'],
+                                  100.0, m['num_edge_types'], kw['heads'], m['out_channels'],
+                                  kw.get('negative_slope', 0.2), slt, res, kw.get('concat', True))
+    else:
+        out = O.mag_regatv2_forward(*common, p['lin_src.weight'], p['att'], p['bias'], p['relation_weight'], 100.0,
+                                    m['num_edge_types'], kw['heads'], m['out_channels'], kw.get('negative_slope', 0.2),
+                                    slt, res, kw.get('concat', True))
+    assert torch.allclose(out, t('out'), rtol=1e-11, atol=1e-12)
+    out.backward(t('gout'))
+    assert torch.allclose(x.grad, t('gx_src'), rtol=1e-10, atol=1e-12)
+    seen = set()
+    for k, v in c.items():
+        if not k.startswith('grad::'):
+            continue
+        key = k[6:]
+        if key in ('weight_root', 'lin_dst.weight') or key not in p:    # aliases of weight / lin_src.weight
+            continue
+        seen.add(key)
+        g = p[key].grad if p[key].grad is not None else torch.zeros_like(p[key])
+        assert torch.allclose(g, torch.as_tensor(v), rtol=1e-10, atol=1e-12), key
+    assert 'relation_weight' in seen and 'bias' in seen

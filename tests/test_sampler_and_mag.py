@@ -3,6 +3,8 @@ import numpy as np
 import pytest
 import torch
 
+import helpers
+
 from oracle import csr_oracle, regnn_oracle as O, sampler_oracle as S
 from re_gnn_b200 import synth
 
@@ -142,3 +144,25 @@ def test_saint_regcn_layer_matches_oracle(cpu_ops):
     assert torch.allclose(x.grad, xr.grad, rtol=1e-9, atol=1e-12)
     for k, v in conv.named_parameters():
         assert torch.allclose(v.grad, p[k].grad, rtol=1e-8, atol=1e-10), k
+
+
+@pytest.mark.parametrize('name', helpers.mag_golden_cases('regcn_'))
+def test_mag_regcn_layer_matches_reference_golden(cpu_ops, name):
+    """Our mag.REGCNConv (host logic over the operator shim) against fixtures recorded from the reference's own
+    mag/regnn_layers.py REGCNConv: same constructor, same state_dict keys, same outputs and gradients."""
+    from re_gnn_b200 import mag
+    c = helpers.load_mag_case(name)
+    m = c['meta']
+    conv = mag.REGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], **m['kw']).double()
+    state = {k[7:]: torch.as_tensor(v) for k, v in c.items() if k.startswith('param::')}
+    assert set(conv.state_dict()) == set(state)
+    conv.load_state_dict(state)
+    x = torch.as_tensor(c['x_src']).clone().requires_grad_(True)
+    n_dst = int(c['n_dst'])
+    out = conv((x, x[:n_dst]), torch.as_tensor(c['edge_index']), torch.as_tensor(c['edge_type']),
+               torch.as_tensor(c['target_node_type']))
+    assert torch.allclose(out, torch.as_tensor(c['out']), rtol=1e-10, atol=1e-12)
+    out.backward(torch.as_tensor(c['gout']))
+    assert torch.allclose(x.grad, torch.as_tensor(c['gx_src']), rtol=1e-9, atol=1e-12)
+    for k, p in conv.named_parameters():
+        assert torch.allclose(p.grad, torch.as_tensor(c['grad::' + k]), rtol=1e-9, atol=1e-11), k
