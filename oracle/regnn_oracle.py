@@ -211,8 +211,8 @@ def regcn_model_forward(src, dst, etype, num_nodes, features_list, params, alpha
 # pinned to fixtures recorded from the reference's own, unmodified mag/regnn_layers.py + mag/utils.py run over
 # oracle/pyg_stub (tests/golden/make_golden_mag.py -> tests/golden/mag/*.npz, checked by tests/test_oracle_golden.py).
 # The PyG MessagePassing / torch_scatter primitive semantics themselves remain "parity unpinned" (no PyG binary).
-# mag/regnn_saint.py is a script (its classes cannot be imported without running it): saint_regcn_forward below
-# restates it by reading and stays "parity unpinned".
+# mag/regnn_saint.py is a script (importing it parses arguments and loads the dataset): make_golden_mag.py lifts its
+# REGCNConv class out by source range, unmodified, and saint_regcn_forward below is pinned to that class' outputs too.
 def mag_regcn_forward(x_src, x_target, edge_index, edge_type, target_node_type, weight, bias, relation_weight,
                       scaling_factor, num_edge_types, self_loop_type=2, residual=False):
     """mag/regnn_layers.py:80-150 (``REGCNConv.forward``; ``aggr='mean'``, bias added in ``update``)."""

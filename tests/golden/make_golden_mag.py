@@ -66,7 +66,54 @@ def save_case(name, kind, kw, blk, tuple_input=True):
     print('%-30s out %s' % (name, tuple(out.shape)))
 
 
+def reference_saint_conv():
+    """mag/regnn_saint.py is a script (argument parsing and dataset loading at import), so its ``REGCNConv`` class is
+    lifted out by source range -- the class body is the reference's text, unmodified -- and executed in a namespace
+    holding exactly the names the script imports for it."""
+    import ast
+    import torch.nn.functional as F
+    from torch.nn import Parameter, init
+    from torch_geometric.nn import MessagePassing
+    from utils import softmax, weighted_degree          # the reference's mag/utils.py
+    path = os.path.join(REF, 'mag', 'regnn_saint.py')
+    text = open(path).read()
+    node = [n for n in ast.parse(text).body if isinstance(n, ast.ClassDef) and n.name == 'REGCNConv'][0]
+    ns = dict(torch=torch, F=F, Parameter=Parameter, init=init, MessagePassing=MessagePassing, softmax=softmax,
+              weighted_degree=weighted_degree)
+    exec(compile(ast.get_source_segment(text, node), path, 'exec'), ns)
+    return ns['REGCNConv']
+
+
+def save_saint_case(name, n, e, seed, tuple_input):
+    rng = np.random.RandomState(seed)
+    dst = np.where(rng.rand(e) < 0.3, rng.randint(0, 2, size=e), rng.randint(0, n - 6, size=e))   # hubs; 6 rows w/o in-edges
+    edge_index = np.stack([rng.randint(0, n, size=e), dst]).astype(np.int64)
+    et = rng.randint(0, NUM_EDGE_TYPES, size=e).astype(np.int64)
+    torch.manual_seed(5)
+    mod = reference_saint_conv()(16, 8, NUM_NODE_TYPES, NUM_EDGE_TYPES, ALPHA)
+    with torch.no_grad():   # positive relation weights: the layer divides by the weighted in-degree without a clamp
+        mod.relation_weight.copy_(torch.as_tensor(rng.uniform(0.3, 1.5, size=NUM_EDGE_TYPES) / ALPHA))
+        mod.bias.copy_(torch.as_tensor(rng.randn(8) * 0.1))
+    x = torch.as_tensor(rng.randn(n, 16)).requires_grad_(True)
+    out = mod((x, x) if tuple_input else x, torch.as_tensor(edge_index), torch.as_tensor(et))
+    gout = torch.as_tensor(np.random.RandomState(7).randn(*out.shape))
+    out.backward(gout)
+    blob = dict(edge_index=edge_index, edge_type=et, n_src=np.int64(n), n_dst=np.int64(n), x_src=x.detach().numpy(),
+                gx_src=x.grad.numpy(), out=out.detach().numpy(), gout=gout.numpy(),
+                meta=np.array(json.dumps(dict(kind='SaintREGCNConv', kw={}, tuple_input=tuple_input, in_channels=16,
+                                              out_channels=8, num_node_types=NUM_NODE_TYPES,
+                                              num_edge_types=NUM_EDGE_TYPES))))
+    for k, v in mod.state_dict().items():
+        blob['param::' + k] = v.detach().numpy()
+    for k, p in mod.named_parameters():
+        blob['grad::' + k] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, 'mag', name + '.npz'), **blob)
+    print('%-30s out %s' % (name, tuple(out.shape)))
+
+
 def main():
+    save_saint_case('saint_regcn_tensor_input', 50, 320, 21, False)
+    save_saint_case('saint_regcn_tuple_input', 36, 200, 22, True)
     b1, b2 = block(1), block(2, empty_targets=False)
     square = block(3, n_src=40, n_dst=40, e=260)       # full-graph inference shape: targets == sources
     for name, kw, blk in [

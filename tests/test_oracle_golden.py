@@ -102,9 +102,15 @@ def test_mag_oracle_matches_reference_layer_code(name):
     p = {k[7:]: torch.as_tensor(v).clone().requires_grad_(True) for k, v in c.items() if k.startswith('param::')}
     x = t('x_src').clone().requires_grad_(True)
     n_dst = int(c['n_dst'])
-    common = (x, x[:n_dst], t('edge_index'), t('edge_type'), t('target_node_type'))
     slt, res = kw.get('self_loop_type', 1), kw.get('residual', False)
-    if m['kind'] == 'REGCNConv':
+    if m['kind'] == 'SaintREGCNConv':   # class lifted from the mag/regnn_saint.py script
+        out = O.saint_regcn_forward(x, t('edge_index'), t('edge_type'), p['weight'], p['bias'], p['relation_weight'], 100.0)
+        common = None
+    else:
+        common = (x, x[:n_dst], t('edge_index'), t('edge_type'), t('target_node_type'))
+    if common is None:
+        pass
+    elif m['kind'] == 'REGCNConv':
         out = O.mag_regcn_forward(*common, p['weight'], p['bias'], p['relation_weight'], 100.0, m['num_edge_types'], slt, res)
     elif m['kind'] == 'REGATConv':
         out = O.mag_regat_forward(*common, p['lin_src.weight'], p['att_src'], p['att_dst'], p['bias'], p['relation_weight'],

@@ -166,3 +166,22 @@ def test_mag_regcn_layer_matches_reference_golden(cpu_ops, name):
     assert torch.allclose(x.grad, torch.as_tensor(c['gx_src']), rtol=1e-9, atol=1e-12)
     for k, p in conv.named_parameters():
         assert torch.allclose(p.grad, torch.as_tensor(c['grad::' + k]), rtol=1e-9, atol=1e-11), k
+
+
+@pytest.mark.parametrize('name', helpers.mag_golden_cases('saint_regcn_'))
+def test_saint_regcn_layer_matches_reference_golden(cpu_ops, name):
+    """Our mag.SaintREGCNConv against fixtures recorded from the REGCNConv class of the reference's mag/regnn_saint.py."""
+    from re_gnn_b200 import mag
+    c = helpers.load_mag_case(name)
+    m = c['meta']
+    conv = mag.SaintREGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], 100.0).double()
+    state = {k[7:]: torch.as_tensor(v) for k, v in c.items() if k.startswith('param::')}
+    assert set(conv.state_dict()) == set(state)
+    conv.load_state_dict(state)
+    x = torch.as_tensor(c['x_src']).clone().requires_grad_(True)
+    out = conv((x, x) if m['tuple_input'] else x, torch.as_tensor(c['edge_index']), torch.as_tensor(c['edge_type']))
+    assert torch.allclose(out, torch.as_tensor(c['out']), rtol=1e-10, atol=1e-12)
+    out.backward(torch.as_tensor(c['gout']))
+    assert torch.allclose(x.grad, torch.as_tensor(c['gx_src']), rtol=1e-9, atol=1e-12)
+    for k, p in conv.named_parameters():
+        assert torch.allclose(p.grad, torch.as_tensor(c['grad::' + k]), rtol=1e-8, atol=1e-10), k
