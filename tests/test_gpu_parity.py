@@ -686,3 +686,30 @@ def test_empty_and_tiny_graphs_all_layers(n, edges):
             want = p64[k].grad if p64[k].grad is not None else torch.zeros_like(p64[k])
             got = v.grad if v.grad is not None else torch.zeros_like(v)
             helpers.assert_close(got.cpu(), want, 2 * RTOL, kind + ' d_' + k, atol=1e-4 if k == 'edge_weight' else 1e-5)
+
+
+# ---- MAG-stack layers against fixtures recorded from the reference's own mag/*.py (tests/golden/mag) ----------------
+@pytest.mark.parametrize('name', helpers.mag_golden_cases('regcn_') + helpers.mag_golden_cases('saint_regcn_'))
+def test_mag_layers_match_reference_golden(name):
+    from re_gnn_b200 import mag
+    c = helpers.load_mag_case(name)
+    m = c['meta']
+    saint = m['kind'] == 'SaintREGCNConv'
+    if saint:
+        conv = mag.SaintREGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], 100.0)
+    else:
+        conv = mag.REGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], **m['kw'])
+    conv.load_state_dict({k[7:]: torch.as_tensor(v, dtype=torch.float32) for k, v in c.items() if k.startswith('param::')})
+    conv = conv.to(DEV)
+    x = torch.as_tensor(c['x_src'], dtype=torch.float32).to(DEV).requires_grad_(True)
+    ei, et = torch.as_tensor(c['edge_index']).to(DEV), torch.as_tensor(c['edge_type']).to(DEV)
+    n_dst = int(c['n_dst'])
+    if saint:
+        out = conv((x, x) if m['tuple_input'] else x, ei, et)
+    else:
+        out = conv((x, x[:n_dst]), ei, et, torch.as_tensor(c['target_node_type']).to(DEV))
+    out.backward(torch.as_tensor(c['gout'], dtype=torch.float32).to(DEV))
+    helpers.assert_close(out.detach().cpu(), c['out'], RTOL, name + ' out')
+    helpers.assert_close(x.grad.cpu(), c['gx_src'], 2 * RTOL, name + ' d_x')
+    for k, p in conv.named_parameters():
+        helpers.assert_close(p.grad.cpu(), c['grad::' + k], 5 * RTOL, name + ' d_' + k)
