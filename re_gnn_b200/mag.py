@@ -1,8 +1,8 @@
-"""MAG-stack (PyG-API) RE-GCN layer and model on the fused CUDA operators -- the sampled-minibatch path of
-BASELINE config 5 ("next" row f-1 of SURVEY.md section 8).
+"""MAG-stack (PyG-API) RE-GCN / RE-GAT / RE-GATv2 layers and model on the fused CUDA operators -- the
+sampled-minibatch path of BASELINE config 5 ("next" row f-1 of SURVEY.md section 8).
 
-Mirrors, for ``--model regcn``, the constructor arguments, parameter names and forward conventions of
-``REGCNConv`` (mag/regnn_layers.py:24-150) and ``REGNN`` (mag/regnn_ns.py:216-346): bipartite
+Mirrors the constructor arguments, parameter names and forward conventions of
+``REGCNConv`` / ``REGATConv`` / ``REGATv2Conv`` (mag/regnn_layers.py:24-433) and ``REGNN`` (mag/regnn_ns.py:216-346): bipartite
 ``(x_src, x_target)`` inputs with the targets first, ``edge_index`` [2,E] of local ids, 0-based ``edge_type``,
 ``self_loop_type == 2`` appending one typed self loop per target, ``aggr='mean'`` over the UN-normalised
 relation weights (the ``ew`` the reference computes is returned but never used for aggregation, :119-129).
@@ -74,29 +74,141 @@ class REGCNConv(nn.Module):
         return out
 
 
+class _MagAttentionBase(nn.Module):
+    """Shared part of the MAG-stack ``REGATConv`` / ``REGATv2Conv`` (mag/regnn_layers.py:153-296, :298-433): one
+    ``lin_src`` projection shared by both sides (``lin_dst`` aliases it, :188 / :333), relation embeddings
+    ``[R, heads]``, typed self loops for ``self_loop_type == 2``, concat or mean over heads, bias, residual, norm.
+
+    Softmax: the reference stabilises with the GLOBAL maximum of all logits and adds 1e-16 to every denominator
+    (mag/utils.py:28-57); the fused kernels use the row maximum and no epsilon.  The two differ by the per-row
+    factor 1 / (1 + 1e-16 * exp(M - L_v)) (M: global max, L_v: log-sum-exp of row v), which is below fp32
+    resolution unless a row's logits sit more than ~20 below the global maximum -- not reproduced here."""
+
+    def __init__(self, in_channels, out_channels, num_node_types, num_edge_types, heads=1, scaling_factor=100.,
+                 concat=True, negative_slope=0.2, dropout=0.0, residual=False, use_norm=None, self_loop_type=1,
+                 no_re=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.negative_slope, self.dropout = negative_slope, dropout
+        self.num_node_types, self.num_edge_types = num_node_types, num_edge_types
+        self.residual, self.use_norm, self.self_loop_type = residual, use_norm, self_loop_type
+        self.scaling_factor = scaling_factor
+        self.out_dim = heads * out_channels if concat else out_channels
+        self.lin_src = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.lin_dst = self.lin_src
+        self.bias = nn.Parameter(torch.empty(self.out_dim))
+        rw_dim = num_edge_types if self_loop_type in (1, 3) else num_edge_types + num_node_types
+        self.relation_weight = nn.Parameter(torch.empty(rw_dim, heads), requires_grad=not no_re)
+        self._make_attention_parameters()
+        if use_norm == 'bn':
+            self.norm = nn.BatchNorm1d(self.out_dim)
+        elif use_norm == 'ln':
+            self.norm = nn.LayerNorm(self.out_dim)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.lin_src.reset_parameters()
+        self._reset_attention_parameters()
+        nn.init.zeros_(self.bias)
+        nn.init.constant_(self.relation_weight, 1.0 / self.scaling_factor)
+        if self.use_norm in ('bn', 'ln'):
+            self.norm.reset_parameters()
+
+    build_block = REGCNConv.build_block
+
+    def forward(self, x, edge_index, edge_type, target_node_type, return_weights=False, block=None):
+        h, c = self.heads, self.out_channels
+        if isinstance(x, torch.Tensor):
+            xs = xd = self.lin_src(x).view(-1, h, c)
+        else:
+            xs = self.lin_src(x[0]).view(-1, h, c)
+            xd = self.lin_dst(x[1]).view(-1, h, c)
+        n_src, n_dst = xs.shape[0], xd.shape[0]
+        graph, etype1 = block if block is not None else self.build_block(edge_index, edge_type, target_node_type,
+                                                                         n_src, n_dst)
+        etv = graph.etype_views(etype1, self.relation_weight.shape[0])
+        out, attn = self._aggregate(graph, etv, xs, xd, n_src, return_weights)
+        out = out[:n_dst]
+        out = out.reshape(-1, h * c) if self.concat else out.mean(dim=1)
+        out = out + self.bias
+        if self.residual:
+            out = out + xd.reshape(-1, h * c)
+        if self.use_norm in ('bn', 'ln'):
+            out = self.norm(out)
+        return (out, attn) if return_weights else out
+
+    @staticmethod
+    def _pad_rows(t, n):
+        """Destination-side tensors are indexed by graph row id; rows past the targets have no in-edges."""
+        return t if t.shape[0] == n else torch.cat([t, t.new_zeros((n - t.shape[0],) + tuple(t.shape[1:]))])
+
+
+class REGATConv(_MagAttentionBase):
+    """mag/regnn_layers.py:153-296 on ``regnn_gat_fwd / _bwd_dst / _bwd_src``:
+    ``logit = LeakyReLU_slope(w[etype] + <x_src, att_src>[src] + <x_dst, att_dst>[dst])``."""
+
+    def _make_attention_parameters(self):
+        self.att_src = nn.Parameter(torch.empty(1, self.heads, self.out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, self.heads, self.out_channels))
+
+    def _reset_attention_parameters(self):
+        nn.init.xavier_uniform_(self.att_src)
+        nn.init.xavier_uniform_(self.att_dst)
+
+    def _aggregate(self, graph, etv, xs, xd, n_src, want_attn):
+        el = (xs * self.att_src).sum(-1)
+        er = self._pad_rows((xd * self.att_dst).sum(-1), n_src)
+        return RF.gat_aggregate(graph, etv, xs, el, er, self.relation_weight, self.scaling_factor, self.negative_slope,
+                                None, want_attn)
+
+
+class REGATv2Conv(_MagAttentionBase):
+    """mag/regnn_layers.py:298-433 on ``regnn_gatv2_fwd / _bwd_dst / _bwd_src``:
+    ``logit = <att, LeakyReLU_slope(x_src[src] + x_dst[dst])> + w[etype]`` (relation term outside the activation)."""
+
+    def _make_attention_parameters(self):
+        self.att = nn.Parameter(torch.empty(1, self.heads, self.out_channels))
+
+    def _reset_attention_parameters(self):
+        nn.init.xavier_uniform_(self.att)
+
+    def _aggregate(self, graph, etv, xs, xd, n_src, want_attn):
+        return RF.gatv2_aggregate(graph, etv, xs, self._pad_rows(xd, n_src), self.att, self.relation_weight,
+                                  self.scaling_factor, self.negative_slope, None, want_attn)
+
+
 class REGNN(nn.Module):
-    """mag/regnn_ns.py:216-346 with ``args.model == 'regcn'`` and per-type feature projections
-    (``args.feats_type != 2``); the module-level ``args`` the reference reads become constructor keywords."""
+    """mag/regnn_ns.py:216-346 with per-type feature projections (``args.feats_type != 2``); the module-level
+    ``args`` the reference reads (``args.model`` in {'regcn', 'regat', 'regatv2'}, ``args.self_loop_type``) become
+    constructor keywords."""
 
     def __init__(self, in_channels, hidden_channels, out_channels, heads, num_layers, scaling_factor, dropout,
-                 num_feature_dict, num_edge_types, residual, no_re, use_norm=None, self_loop_type=2):
+                 num_feature_dict, num_edge_types, residual, no_re, use_norm=None, self_loop_type=2, model='regcn'):
         super().__init__()
         self.in_channels, self.hidden_channels, self.out_channels = in_channels, hidden_channels, out_channels
         self.heads, self.num_layers, self.dropout = heads, num_layers, dropout
         self.residual, self.use_norm = residual, use_norm
         self.num_node_types, self.num_edge_types = len(num_feature_dict), num_edge_types
-        self.hidden_dim = hidden_channels
+        self.model = model
+        self.hidden_dim = hidden_channels if model == 'regcn' else hidden_channels * heads      # :236-239
         self.lins = nn.ModuleDict({str(k): nn.Linear(d, self.hidden_dim) for k, d in num_feature_dict.items()})
-        self.convs = nn.ModuleList([
-            REGCNConv(hidden_channels, hidden_channels, self.num_node_types, num_edge_types, scaling_factor,
-                      dropout=dropout, residual=residual, use_norm=use_norm, self_loop_type=self_loop_type, no_re=no_re)
-            for _ in range(num_layers)])
+        kw = dict(dropout=dropout, residual=residual, use_norm=use_norm, self_loop_type=self_loop_type, no_re=no_re)
+        if model == 'regcn':                                                                   # :254-273
+            convs = [REGCNConv(hidden_channels, hidden_channels, self.num_node_types, num_edge_types, scaling_factor, **kw)
+                     for _ in range(num_layers)]
+        elif model in ('regat', 'regatv2'):
+            cls = REGATConv if model == 'regat' else REGATv2Conv
+            convs = [cls(self.hidden_dim, hidden_channels, self.num_node_types, num_edge_types, heads, scaling_factor, **kw)
+                     for _ in range(num_layers)]
+        else:
+            raise NotImplementedError(model)
+        self.convs = nn.ModuleList(convs)
         self.out_lin = nn.Linear(self.hidden_dim, out_channels)
 
     def group_input(self, x_dict, node_type, local_node_idx, n_id=None):
         if n_id is not None:
             node_type, local_node_idx = node_type[n_id], local_node_idx[n_id]
-        h = torch.zeros((node_type.size(0), self.hidden_dim), device=node_type.device)
+        h = torch.zeros((node_type.size(0), self.hidden_dim), device=node_type.device, dtype=self.out_lin.weight.dtype)
         for key, x in x_dict.items():
             mask = node_type == key
             h[mask] = self.lins[str(key)](x[local_node_idx[mask]])

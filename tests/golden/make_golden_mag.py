@@ -111,7 +111,75 @@ def save_saint_case(name, n, e, seed, tuple_input):
     print('%-30s out %s' % (name, tuple(out.shape)))
 
 
+def reference_regnn_model(model):
+    """``REGNN`` of the mag/regnn_ns.py script, lifted out by source range (unmodified) and bound to the conv classes of
+    mag/regnn_layers.py and to an ``args`` namespace standing in for the script's command line."""
+    import ast
+    import types
+    import torch.nn.functional as F
+    from torch.nn import Linear, ModuleDict, ModuleList, Parameter, ParameterDict
+    path = os.path.join(REF, 'mag', 'regnn_ns.py')
+    text = open(path).read()
+    node = [n for n in ast.parse(text).body if isinstance(n, ast.ClassDef) and n.name == 'REGNN'][0]
+    ns = dict(torch=torch, F=F, Linear=Linear, ModuleDict=ModuleDict, ModuleList=ModuleList, Parameter=Parameter,
+              ParameterDict=ParameterDict, REGCNConv=RL.REGCNConv, REGATConv=RL.REGATConv, REGATv2Conv=RL.REGATv2Conv,
+              args=types.SimpleNamespace(model=model, feats_type=3, self_loop_type=2, no_re=False))
+    exec(compile(ast.get_source_segment(text, node), path, 'exec'), ns)
+    return ns['REGNN']
+
+
+def save_model_case(name, model, heads, residual):
+    """Two sampled blocks in PyG's ``adjs`` form (outermost first; targets are the first rows of the sources)."""
+    rng = np.random.RandomState(zlib.crc32(name.encode()) % (2 ** 31))
+    n_total, sizes = 90, [(70, 30), (30, 10)]           # n_id has 70 entries; layer 1: 70 -> 30, layer 2: 30 -> 10
+    feat_dims = {0: 12, 1: 7, 2: 9}
+    node_type = rng.randint(0, NUM_NODE_TYPES, size=n_total)
+    local_idx = np.zeros(n_total, dtype=np.int64)
+    for t in range(NUM_NODE_TYPES):
+        local_idx[node_type == t] = np.arange((node_type == t).sum())
+    x_dict = {t: rng.randn(int((node_type == t).sum()), d) for t, d in feat_dims.items()}
+    n_id = rng.permutation(n_total)[:sizes[0][0]]
+    e_total = 400
+    edge_type_all = rng.randint(0, NUM_EDGE_TYPES, size=e_total)
+    adjs, off = [], 0
+    for (n_src, n_dst), e in zip(sizes, (260, 140)):
+        ei = np.stack([rng.randint(0, n_src, size=e), rng.randint(0, n_dst, size=e)]).astype(np.int64)
+        adjs.append((ei, np.arange(off, off + e), (n_src, n_dst)))
+        off += e
+    torch.manual_seed(3)
+    net = reference_regnn_model(model)(16, 8, 5, heads, 2, ALPHA, 0.0, feat_dims, NUM_EDGE_TYPES, residual, False)
+    with torch.no_grad():
+        for conv in net.convs:
+            conv.relation_weight.copy_(torch.as_tensor(rng.uniform(0.5, 1.5, size=tuple(conv.relation_weight.shape)) / ALPHA))
+            conv.bias.copy_(torch.as_tensor(rng.randn(*conv.bias.shape) * 0.1))
+    net.eval()
+    xd = {t: torch.as_tensor(v) for t, v in x_dict.items()}
+    out = net(torch.as_tensor(n_id), xd, [(torch.as_tensor(a), torch.as_tensor(b), c) for a, b, c in adjs],
+              torch.as_tensor(edge_type_all), torch.as_tensor(node_type), torch.as_tensor(local_idx))
+    gout = torch.as_tensor(np.random.RandomState(7).randn(*out.shape))
+    out.backward(gout)
+    blob = dict(n_id=n_id, node_type=node_type, local_node_idx=local_idx, edge_type=edge_type_all, out=out.detach().numpy(),
+                gout=gout.numpy(),
+                meta=np.array(json.dumps(dict(kind='REGNN', model=model, heads=heads, residual=residual, in_channels=16,
+                                              hidden_channels=8, out_channels=5, num_layers=2,
+                                              feat_dims={str(k): v for k, v in feat_dims.items()},
+                                              num_edge_types=NUM_EDGE_TYPES, sizes=sizes))))
+    for t, v in x_dict.items():
+        blob['x::%d' % t] = v
+    for i, (ei, eid, _) in enumerate(adjs):
+        blob['adj%d::edge_index' % i], blob['adj%d::e_id' % i] = ei, eid
+    for k, v in net.state_dict().items():
+        blob['param::' + k] = v.detach().numpy()
+    for k, p in net.named_parameters():
+        blob['grad::' + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    np.savez_compressed(os.path.join(HERE, 'mag', name + '.npz'), **blob)
+    print('%-30s out %s' % (name, tuple(out.shape)))
+
+
 def main():
+    save_model_case('model_regnn_regcn', 'regcn', 1, True)
+    save_model_case('model_regnn_regat_h2', 'regat', 2, True)
+    save_model_case('model_regnn_regatv2_h2', 'regatv2', 2, False)
     save_saint_case('saint_regcn_tensor_input', 50, 320, 21, False)
     save_saint_case('saint_regcn_tuple_input', 36, 200, 22, True)
     b1, b2 = block(1), block(2, empty_targets=False)

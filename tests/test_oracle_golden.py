@@ -94,7 +94,7 @@ def test_oracle_regcn_model_matches_reference_golden():
 
 
 # ---- MAG-stack layers: fixtures from the reference's own mag/regnn_layers.py over the PyG-semantics stub ----------
-@pytest.mark.parametrize('name', helpers.mag_golden_cases())
+@pytest.mark.parametrize('name', [c for c in helpers.mag_golden_cases() if not c.startswith('model_')])
 def test_mag_oracle_matches_reference_layer_code(name):
     c = helpers.load_mag_case(name)
     m, kw = c['meta'], c['meta']['kw']
