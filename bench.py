@@ -5,7 +5,8 @@ Metric (BASELINE.json): GTEPS forward+backward per RE-layer (+ % of the HBM roof
 one forward + backward of one RE-layer (REGraphConv aggregation core: relation-weighted degree norm
 + fused norm*SpMM*norm, gradients w.r.t. the features and the relation embedding) over the whole
 synthetic ogbn-mag-shaped graph (BASELINE config 4; 1.94 M nodes, 23.05 M edges incl. self loops,
-F = 128 fp32).  With --gpus N the same graph is partitioned by destination-row blocks (strong scaling).
+F = 128 fp32).  With --gpus N the same step is sharded over N ranks (strong scaling): feature-sliced aggregation with
+the row<->slab exchange inside our kernels over NVLink peer memory by default (--partition).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mag_regcn]
 
