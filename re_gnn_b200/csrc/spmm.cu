@@ -4,7 +4,7 @@
 //
 // All of these are gather-bound (HBM / L2 bandwidth): one source row of 4F bytes per edge.
 // Three generations of the SpMM live here, newest last:
-//   spmm_kernel / spmm_bwd_w_kernel   one row per lane group in natural row order (kept for regnn_spmm_bwd_w);
+//   spmm_bwd_w_kernel                 one row per lane group in natural row order (regnn_spmm_bwd_w, F > 512);
 //   spmm_stream_kernel                a warp streams the concatenated slots of 32 rows (F > 128, row sub-ranges);
 //   spmm_rowgroup_kernel              lane groups over the degree-sorted row list (F <= 128, full range): the
 //                                     production kernels, forward at 96 % of the measured HBM bandwidth.
@@ -72,118 +72,10 @@ template <> struct Vec<1> {
 
 template <int C> struct Unroll { static constexpr int U = C <= 1 ? 8 : (C <= 2 ? 4 : (C <= 4 ? 2 : 1)); };
 
-// ---- forward / backward-w.r.t.-X -------------------------------------------------------------
-// Work items: fragments of long rows first (lowest block ids start first, so the heaviest rows never
-// form the tail), then one item per ordinary row.  A fragment writes its un-normalised partial sum to
-// `partial`; spmm_frag_finalize_kernel adds the fragments of a row in fragment order.
-template <int G, int C, int VW>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-spmm_kernel(SpmmArgs a) {
-  using V = Vec<VW>;
-  using T = typename V::T;
-  constexpr int U = Unroll<C>::U;
-  constexpr int GPW = 32 / G;
-  __shared__ float w_s[256];
-  if (a.etype != nullptr) {
-    for (int i = threadIdx.x; i < a.R; i += blockDim.x) w_s[i] = leaky(a.theta[i] * a.alpha, kRelationSlope);
-    __syncthreads();
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lg = lane % G, grp = lane / G;
-  const int64_t wi = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * GPW + grp;
-  const bool is_frag = wi < a.nfrag_pad;
-  bool row_ok = false;
-  int64_t v = 0;
-  int s0 = 0, len = 0;
-  if (is_frag) {
-    if (wi < a.nfrag) {
-      v = a.frag_row[wi];
-      if (v >= a.row_begin && v < a.row_end) {
-        s0 = a.frag_begin[wi];
-        len = min(a.threshold, a.indptr[v + 1] - s0);
-        row_ok = true;
-      }
-    }
-  } else {
-    v = a.row_begin + (wi - a.nfrag_pad);
-    if (v < a.row_end) {
-      s0 = a.indptr[v];
-      len = a.indptr[v + 1] - s0;
-      row_ok = len <= a.threshold;  // longer rows are covered by fragments
-      if (!row_ok) len = 0;
-    }
-  }
-  const int maxlen = (G == 32) ? len : warp_max_int(len);
-
-  T acc[C];
-  bool col_ok[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) {
-    acc[k] = V::zero();
-    col_ok[k] = (lg + k * G) * VW < a.F;
-  }
-  const float* xcol = a.X + (size_t)lg * VW;
-
-  // software prefetch: the column index / coefficient of the next batch is in flight while the
-  // current batch's rows are gathered
-  int nidx = 0;
-  float ncoef = 0.f;
-  if (lg < len) {
-    const int s = s0 + lg;
-    nidx = a.indices[s];
-    ncoef = a.etype != nullptr ? w_s[a.etype[s]] : 1.f;
-    if (a.norm_src != nullptr) ncoef *= __ldg(a.norm_src + nidx);
-  }
-  for (int base = 0; base < maxlen; base += G) {
-    const int idx = nidx;
-    const float coef = ncoef;
-    nidx = 0;
-    ncoef = 0.f;
-    if (base + G + lg < len) {
-      const int s = s0 + base + G + lg;
-      nidx = a.indices[s];
-      ncoef = a.etype != nullptr ? w_s[a.etype[s]] : 1.f;
-      if (a.norm_src != nullptr) ncoef *= __ldg(a.norm_src + nidx);
-    }
-    const int cnt = min(G, maxlen - base);
-    for (int j = 0; j < cnt; j += U) {
-      int sidx[U];
-      float sc[U];
-      T x[U][C];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int jj = min(j + u, G - 1);
-        sidx[u] = __shfl_sync(0xffffffffu, idx, jj, G);
-        sc[u] = __shfl_sync(0xffffffffu, coef, jj, G);
-        const bool valid = base + j + u < len && j + u < G;
-        if (!valid) sc[u] = 0.f;
-#pragma unroll
-        for (int k = 0; k < C; ++k)
-          x[u][k] = (valid && col_ok[k]) ? V::load(xcol + (size_t)sidx[u] * a.ldx + (size_t)k * G * VW)
-                                         : V::zero();
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int k = 0; k < C; ++k) V::fma(acc[k], sc[u], x[u][k]);
-    }
-  }
-  if (row_ok) {
-    if (is_frag) {
-      float* y = a.partial + (size_t)wi * a.F + (size_t)lg * VW;
-#pragma unroll
-      for (int k = 0; k < C; ++k)
-        if (col_ok[k]) V::store(y + (size_t)k * G * VW, acc[k]);
-    } else {
-      const float nd = a.norm_dst != nullptr ? a.norm_dst[v] : 1.f;
-      float* y = a.Y + (size_t)v * a.ldy + (size_t)lg * VW;
-#pragma unroll
-      for (int k = 0; k < C; ++k)
-        if (col_ok[k]) V::store(y + (size_t)k * G * VW, V::scaled(acc[k], nd));
-    }
-  }
-}
-
+// ---- long-row fragments ---------------------------------------------------------------------------
+// Work items of every SpMM kernel below: fragments of long rows first (lowest block ids start first, so the
+// heaviest rows never form the tail), then the ordinary rows.  A fragment writes its un-normalised partial sum
+// to `partial`; spmm_frag_finalize_kernel adds the fragments of a row in fragment order.
 // Y[v] = norm_dst[v] * sum over the fragments of long row v (fragment order => deterministic).
 __global__ void spmm_frag_finalize_kernel(const int32_t* __restrict__ long_rows,
                                           const int32_t* __restrict__ frag_ptr, int num_long,
