@@ -114,6 +114,12 @@ def algorithmic_bytes_spmm(n, e, f):
     return e * (4 * f + 4 + 1 + 4) + n * (4 * f + 4 + 4)
 
 
+def compulsory_bytes_spmm(n, e, f):
+    """SURVEY.md 8(d) companion figure: every source row read once, every output row written once, the edge
+    structure streamed once -- a lower bound on DRAM traffic that no kernel can beat (fraction <= 1 always)."""
+    return 2 * 4 * n * f + 5 * e + 12 * n
+
+
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_sample(d, feat, steps, warmup, max_edges=1_500_000):
     """Times the CPU restatement of the reference layer (oracle) forward+backward on a bounded sample:
@@ -234,7 +240,7 @@ def others(dev, steps, warmup):
             ts.append(t0.elapsed_time(t1) / 1e3)
         t = float(np.median(ts[warmup:]))
         res[name] = {'gteps_fwd_bwd': d['src'].size / t / 1e9, 'ms': t * 1e3, 'num_edges': int(d['src'].size),
-                     'l2': 'flushed between iterations'}
+                     'l2': 'flushed between iterations', 'l2_resident': True}   # whole working set < 126 MB L2: not an HBM statement
     return res
 
 
@@ -476,7 +482,11 @@ def run_ours(args, d):
         kname = 'regnn::spmm_rowgroup_kernel<false,%d> (forward launch)' % (32 if fk > 64 else 16 if fk > 32 else 8 if fk > 16 else 4)
     roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': alg / tk / 1e9,
                 'peak': hbm, 'peak_source': how, 'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm, 'traffic': traffic,
-                'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3}
+                'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3,
+                # SURVEY 8(d) companions: the compulsory-traffic bound and whether the gathered matrix fits in L2
+                'compulsory_bytes_per_launch': int(compulsory_bytes_spmm(rows_n, edges_n, fk)),
+                'frac_compulsory': compulsory_bytes_spmm(rows_n, edges_n, fk) / tk / 1e9 / hbm,
+                'l2_resident': bool(n * fk * 4 <= 126 * 2 ** 20)}
 
     line = {
         'metric': 'GTEPS fwd+bwd per RE-layer', 'value': value, 'unit': 'GTEPS', 'n_gpus': world,
