@@ -1,20 +1,22 @@
-"""Destination-row-block partitioning of the full-batch REGCN aggregation across ranks
-(BASELINE config 4: ogbn-mag-shaped graph over 2/4/8 B200).  The reference has no multi-GPU code
-(SURVEY.md 2.4); numerics must equal the single-device result.
+"""Multi-GPU execution of the full-batch REGCN aggregation (BASELINE config 4: ogbn-mag-shaped graph over 2/4/8
+B200).  The reference has no multi-GPU code; numerics must equal the single-device result (Y and dX
+are bit-identical in every scheme below: all kernels add a row's slots in slot order).
 
-Scheme (owner computes, no floating-point reduction across ranks except the tiny relation-gradient
-table):
-  * rank p owns the contiguous destination rows [r_p, r_{p+1}), balanced by in-edge count;
-  * every rank holds the whole CSR / transposed view (int32 structures: ~0.4 GB at MAG scale) and
-    computes the (cheap, E-byte) relation-weighted degree norm for all rows;
-  * forward:  NCCL all-gather of the owned source-feature rows -> full X; fused SpMM on owned rows;
-  * backward: NCCL all-gather of the owned dL/dY rows -> full G; transposed SpMM on owned SOURCE rows
-    gives the owned dX rows (no reduce-scatter, no atomics); the relation-gradient partials of the
-    owned rows are summed with one all-reduce of R floats.
+Common contract: rank p holds the row block [r_p, r_{p+1}) of X and dL/dY and gets back the same rows of Y and dX;
+every rank holds the whole CSR / transposed view (int32 structures, ~0.4 GB at MAG scale) and computes the cheap
+relation-degree norm for all rows; the caller sums the R-float relation gradient once (``allreduce_relation_grads``).
 
-``feature_sliced_propagate`` is the second scheme with the same row-block-in / row-block-out contract: the
-aggregation runs on column slabs (all rows, F/P columns per rank) between two all-to-alls, which moves P times
-fewer bytes over NVLink than the all-gathers above.
+1. ``partitioned_propagate`` -- destination-row blocks (owner computes):
+   forward:  NCCL all-gather of the owned source rows -> full X; fused SpMM on the owned rows;
+   backward: NCCL all-gather of the owned dL/dY rows -> full G; transposed SpMM on the owned SOURCE rows gives the
+   owned dX rows (no reduce-scatter, no atomics).  Exchange-bound: (P-1)/P of the [N,F] matrix per rank, twice.
+2. ``feature_sliced_propagate`` -- column slabs: every rank propagates ALL rows for F/P columns, so the SpMM and its
+   backward need no remote rows; a row<->slab re-partition (N*F/P floats per rank, P times less) sits on each side:
+   * ``exchange=None``: ``all_to_all_single`` (NCCL; gloo in the CPU tests) plus pack / unpack copies;
+   * ``exchange=SlabExchange(...)``: our own kernels over NVLink peer memory -- ``regnn_rows_to_slabs`` pushes row
+     blocks into the peers' slabs, the ``regnn_spmm_*_scatter`` epilogues store finished rows into their owners'
+     row blocks; torch symmetric memory supplies the mapped buffers and the device-side barrier.
+   The norm gradient's row dots span all columns, but the row owner has complete rows: ``d_norm`` is a local pass.
 """
 import torch
 import torch.distributed as dist
