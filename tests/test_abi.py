@@ -108,3 +108,10 @@ def test_scatter_entry_points_validate_arguments(lib):
     peers = _lib.PeerRows(1, 2, 4, 6, 0)   # ld 6 is not a multiple of 4 floats
     assert lib.regnn_spmm_bwd_fused_scatter(None, None, None, None, 1.0, 1, None, 3, None, 4, None, 4, 8, 4, None, None,
                                             None, None, None, None, ctypes.byref(peers), None) == -1
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md maps every exported symbol to the reference call site it replaces."""
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    missing = [s for s in declared_symbols() if s not in text]
+    assert not missing, missing
