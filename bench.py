@@ -147,12 +147,14 @@ def cpu_reference_sample(d, feat, steps, warmup, max_edges=1_500_000):
     t = float(np.median(times[warmup:]))
     return {'value': k_edges / t / 1e9, 'unit': 'GTEPS', 'cores': cores, 'kind': 'port',
             'sample': 'oracle/regnn_oracle.py REGraphConv fwd+bwd (PyTorch CPU, fp32) on the destination-row block '
-                      'holding the first %d in-edges of the same graph, median of %d runs after %d warm-ups, '
-                      '%.3f s per run' % (k_edges, steps, warmup, t)}, t
+                      'holding the first %d in-edges (%.1f %% of the edges) of the same graph, median of %d runs after %d '
+                      'warm-ups, %.3f s per run; GTEPS = sample edges / sample time, i.e. the whole graph is assumed to '
+                      'run at the sample\'s per-edge rate (the oracle\'s cost is linear in E: index_select + index_add_)'
+                      % (k_edges, 100.0 * k_edges / dst.size, steps, warmup, t)}, t
 
 
 def run_reference(args, d):
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)   # the driver's --steps / --warmup, as given
     cb, t = cpu_reference_sample(d, args.feat, steps, warmup)
     line = {
         'impl': 'reference', 'metric': 'GTEPS fwd+bwd per RE-layer', 'value': cb['value'], 'unit': 'GTEPS',
@@ -165,19 +167,21 @@ def run_reference(args, d):
     print(json.dumps(line))
 
 
+PARTITION_HOW = {
+    'none': 'single GPU',
+    'peer': 'feature-sliced over --gpus (column slabs; rows<->slabs re-partition over NVLink peer memory inside the kernels, '
+            'outputs alias the exchange buffers)',
+    'cols': 'feature-sliced over --gpus (column slabs between NCCL all-to-alls)',
+    'rows': 'dst-row blocks (equal rows) over --gpus, NCCL all-gather of source rows',
+    'edges': 'dst-row blocks (equal in-edges) over --gpus, NCCL all-gather of source rows'}
+
+
 def workload_config(args, d):
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    how = {'peer': 'feature-sliced over --gpus (column slabs; rows<->slabs re-partition over NVLink peer memory inside '
-                   'the kernels, outputs alias the exchange buffers)',
-           'cols': 'feature-sliced over --gpus (column slabs between NCCL all-to-alls)',
-           'rows': 'dst-row blocks (equal rows) over --gpus, NCCL all-gather of source rows',
-           'edges': 'dst-row blocks (equal in-edges) over --gpus, NCCL all-gather of source rows'}
-    if world == 1:
-        args.partition = 'none'
-    return {'workload': 'REGraphConv RE-layer fwd+bwd, full-batch, synthetic ogbn-mag-shaped graph '
-                        '(BASELINE config 4), ' + how.get(args.partition, 'single GPU'),
+    """The workload both arms measure (identical for ``--impl ours`` and ``--impl reference`` at every N: how the repo
+    arm shards the step over the GPUs is reported beside it, in the line's ``partition`` key)."""
+    return {'workload': 'REGraphConv RE-layer fwd+bwd, full-batch, synthetic ogbn-mag-shaped graph (BASELINE config 4)',
             'num_nodes': int(d['num_nodes']), 'num_edges': int(d['src'].size), 'num_relations': int(d['num_relations']),
-            'feat': args.feat, 'graph_scale': args.scale, 'partition': args.partition,
+            'feat': args.feat, 'graph_scale': args.scale,
             'l2': 'inputs larger than L2 (source matrix %.0f MB vs 126 MB L2); no flush needed'
                   % (d['num_nodes'] * args.feat * 4 / 1e6)}
 

@@ -46,7 +46,7 @@ extern "C" {
 #define REGNN_ERR_CUDA (-3)
 #define REGNN_ERR_WORKSPACE_TOO_SMALL (-4)
 
-#define REGNN_MAX_RELATIONS 255 /* uint8 edge types */
+#define REGNN_MAX_RELATIONS 200 /* uint8 edge types; the backward kernels keep 8 x R x 32 lane-local bins in shared memory */
 #define REGNN_MAX_HEADS 32
 
 /* Long-row decomposition of one CSR view (built once per graph by the host, see re_gnn_b200/graph.py):
@@ -130,8 +130,8 @@ int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_csr, const i
  * X: [*, F] with leading dimension ldx (floats); Y: rows [row_begin,row_end) written at Y[v*ldy].
  * row_order (optional, NULL = none): the rows of [0, row_end) NOT listed in split->long_rows, by descending
  * slot count (ties by ascending row id) -- [row_end - num_long] ids, built once per graph.  With it, a full
- * range (row_begin == 0) and F <= 64 (F % 4 == 0, 16-byte aligned rows) the narrow-row kernel runs: several
- * rows per warp, each summed by one lane group in slot order (results identical to the whole-warp kernel).
+ * range (row_begin == 0) and F <= 128 (F % 4 == 0, 16-byte aligned rows) the lane-group kernel runs: 32/G
+ * rows per warp (G = 4/8/16/32 lanes per row), each summed by one lane group in slot order (results identical to the whole-warp kernel).
  */
 int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
                    const float* theta, float alpha, int num_relations, const float* norm_src,
@@ -162,15 +162,22 @@ int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, const uint8_
  *   d_theta[r] = alpha*LeakyReLU'(alpha*theta[r]) * sum_{e: etype=r} ns(src)*nd(dst)*<X[src], G[dst]>
  * (ns/nd = norm on the sides selected by norm_sides, else 1): the per-edge dot <X[u], G[dst]> reuses the
  * G[dst] row that the dX gather already holds in registers; X rows of the block are staged in shared
- * memory by TMA bulk copies.  d_norm is NOT produced here: see regnn_rowdot_norm_bwd.
+ * memory by TMA bulk copies.
+ * d_norm (optional, lane-group kernel only: row_order_t, full range, F <= 128): the gradient w.r.t. the norm vector
+ *   d_norm[u] = ( [sides&2] <Y[u],G[u]> + [sides&1] <X[u],dX[u]> ) / norm[u]
+ * is produced in the same pass (Y = the forward result; the lane group that owns row u reads Y[u] and G[u] behind its
+ * gathers), replacing the separate regnn_rowdot_norm_bwd pass of round 1.  NULL: not produced (use xdx +
+ * regnn_rowdot_norm_bwd, the path of the whole-warp kernel and of the row-partitioned multi-GPU scheme).
  * partials: double [regnn_max_partial_blocks() * R]; d_theta is OVERWRITTEN;
- * split_workspace: split_t->num_frags * feat floats.  With row_order_t (F <= 64, full range) the narrow-row
+ * split_workspace: split_t->num_frags * feat floats.  With row_order_t (F <= 128, full range) the lane-group
  * kernel runs instead and keeps X[u] in registers (no shared-memory tile). */
 int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t, const uint8_t* etype_t,
                          const float* theta, float alpha, int num_relations, const float* norm,
                          int norm_sides, const float* X, int64_t ldx, const float* G, int64_t ldg,
                          float* dX, int64_t lddx, int64_t row_begin, int64_t row_end, int feat,
                          double* partials, float* d_theta, float* xdx /* optional [N]: <X[u],dX[u]> per row */,
+                         const float* Y /* forward result, needed for d_norm when sides & 2 */, int64_t ldy,
+                         float* d_norm /* optional [N] */,
                          const regnn_rowsplit_t* split_t, float* split_workspace,
                          const int32_t* row_order_t /* as regnn_spmm_fwd's row_order, for the transposed view */,
                          void* stream);
@@ -199,7 +206,7 @@ typedef struct regnn_peer_rows {
 int regnn_rows_to_slabs(const float* X, int64_t ldx, int64_t num_rows, int feat, int num_ranks, int64_t row_offset,
                         float* const* peer_slabs /* device array [num_ranks] */, void* stream);
 
-/* regnn_spmm_fwd over the full row range [0, num_rows) of a column slab (feat <= 64, row_order required) whose
+/* regnn_spmm_fwd over the full row range [0, num_rows) of a column slab (feat <= 128, feat % 4 == 0, row_order required) whose
  * result rows are stored to their owner ranks: peers->base[v / rows_per_rank][(v % rows_per_rank) * ld + col_offset]. */
 int regnn_spmm_fwd_scatter(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
                            const float* theta, float alpha, int num_relations, const float* norm_src,

@@ -74,7 +74,7 @@ void launch_colsum_finalize(const double* partials, int num_blocks, int stride, 
 
 extern "C" {
 
-int regnn_version(void) { return 100; }
+int regnn_version(void) { return 200; }  // 2xx: round-2 ABI (regnn_spmm_bwd_fused takes Y / d_norm)
 
 const char* regnn_status_string(int status) {
   switch (status) {

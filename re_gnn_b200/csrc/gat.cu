@@ -926,7 +926,7 @@ extern "C" int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, cons
   REGNN_REQUIRE(indptr && feat && el && er && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gat_fwd: null pointer");
   REGNN_REQUIRE((keep == nullptr && attn_out == nullptr) || eid != nullptr, REGNN_ERR_INVALID_ARG, "gat_fwd: keep/attn_out need eid");
   REGNN_REQUIRE(etype_csr == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "gat_fwd: etype without theta");
-  int rc = check_shape("gat_fwd", num_heads, head_dim, num_relations, etype_csr != nullptr, false);
+  int rc = check_shape("gat_fwd", num_heads, head_dim, num_relations, etype_csr != nullptr, true);  // as the backward: fail early
   if (rc != REGNN_OK) return rc;
   REGNN_REQUIRE(aligned16(feat) && aligned16(out), REGNN_ERR_INVALID_ARG, "gat_fwd: feat/out must be 16-byte aligned");
   const int64_t rows = row_end - row_begin;
@@ -992,7 +992,7 @@ extern "C" int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr_t && Gd && d_feat, REGNN_ERR_INVALID_ARG, "gat_bwd_src: null pointer");
   REGNN_REQUIRE(dpre_csr == nullptr || d_el != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_src: dpre_csr without d_el");
-  int rc = check_shape("gat_bwd_src", num_heads, head_dim, 0, false, false);
+  int rc = check_shape("gat_bwd_src", num_heads, head_dim, 0, false, true);
   if (rc != REGNN_OK) return rc;
   REGNN_REQUIRE(aligned16(Gd) && aligned16(d_feat), REGNN_ERR_INVALID_ARG, "gat_bwd_src: 16-byte alignment required");
   const int64_t rows = row_end - row_begin;

@@ -197,6 +197,13 @@ struct StreamArgs {
   double* partials;      // [gridDim.x][R]
   int use_tma;           // rows are 16-byte aligned multiples of 16 bytes: stage the tile with cp.async.bulk
   float* xdx;            // optional [N]: <Xrow[u], dX[u]> per row (the source-side half of d_norm), or null
+  // spmm_rowgroup_kernel<BINS> only: the norm gradient folded into the same pass (d_norm != null)
+  //   d_norm[u] = ( [dn_sides&2] <Yfwd[u], G[u]> + [dn_sides&1] <Xrow[u], dX[u]> ) / norm[u]
+  const float* Yfwd;     // forward result rows (leading dim ldyf)
+  int64_t ldyf;
+  const float* norm;     // the norm vector itself (divisor)
+  int dn_sides;
+  float* d_norm;
   // spmm_rowgroup_kernel only
   const int32_t* order;  // rows not covered by fragments, by descending slot count
   int64_t n_order;
@@ -536,6 +543,15 @@ spmm_rowgroup_kernel(StreamArgs sa) {
     const float nd = (v >= 0 && a.norm_dst != nullptr) ? a.norm_dst[v] : 1.f;
     float4 trow = make_float4(0.f, 0.f, 0.f, 0.f);
     if (BINS && v >= 0 && col_ok) trow = ldg4(sa.Xrow + (size_t)v * sa.ldr + lg * 4);
+    // norm gradient, destination-side half: <Y[u], G[u]> of the row this lane group owns.  Both rows are requested
+    // here, ahead of the gathers, and consumed after them (G[u] is also one of the gathered rows when u has a self
+    // loop, so it is usually an L1/L2 hit).  Fragments: long_row_dnorm_kernel.
+    float4 yrow = make_float4(0.f, 0.f, 0.f, 0.f), grow = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool want_ydg = BINS && sa.d_norm != nullptr && (sa.dn_sides & 2);
+    if (BINS && want_ydg && v >= 0 && col_ok && !is_frag) {
+      yrow = ldg4(sa.Yfwd + (size_t)v * sa.ldyf + lg * 4);
+      grow = ldg4(reinterpret_cast<const float*>(xbytes + (uint64_t)(uint32_t)v * ldxb));
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur_rel = 0;
     float racc = 0.f;
@@ -641,7 +657,12 @@ spmm_rowgroup_kernel(StreamArgs sa) {
     }
     if (BINS) {
       mybins[cur_rel * 32] += racc;
-      if (sa.xdx != nullptr) {  // <X[u], dX[u]> while dX[u] is still in registers (long rows: long_row_xdx_kernel)
+      if (sa.d_norm != nullptr) {  // the whole norm gradient of row u in this pass: no separate row-dot kernel
+        float p = (sa.dn_sides & 1) ? dot4(acc, trow) * nd : 0.f;   // <X[u], dX[u]> while dX[u] is in registers
+        if (want_ydg) p += dot4(yrow, grow);
+        p = group_sum<G>(p);
+        if (lg == 0 && v >= 0 && !is_frag) sa.d_norm[v] = p / sa.norm[v];
+      } else if (sa.xdx != nullptr) {  // <X[u], dX[u]> only (long rows: long_row_dnorm_kernel)
         const float d = group_sum<G>(dot4(acc, trow)) * nd;
         if (lg == 0 && v >= 0 && !is_frag) sa.xdx[v] = d;
       }
@@ -710,19 +731,30 @@ rowdot_norm_kernel(const float* __restrict__ norm, int sides, const float* __res
   }
 }
 
-// xdx[v] = <X[v], dX[v]> for the long rows (their dX is only complete after the fragment finalize)
-__global__ void long_row_xdx_kernel(const int32_t* __restrict__ long_rows, int num_long, const float* __restrict__ X,
-                                    int64_t ldx, const float* __restrict__ dX, int64_t lddx, int F, int64_t row_begin,
-                                    int64_t row_end, float* __restrict__ xdx) {
+// The long rows' share of the norm gradient (their dX is only complete after the fragment finalize):
+//   xdx[v] = <X[v], dX[v]>                                                         (xdx != null)
+//   d_norm[v] = ( [sides&2] <Y[v], G[v]> + [sides&1] <X[v], dX[v]> ) / norm[v]      (d_norm != null)
+__global__ void long_row_dnorm_kernel(const int32_t* __restrict__ long_rows, int num_long, const float* __restrict__ X,
+                                      int64_t ldx, const float* __restrict__ dX, int64_t lddx, int F, int64_t row_begin,
+                                      int64_t row_end, float* __restrict__ xdx, const float* __restrict__ Y, int64_t ldy,
+                                      const float* __restrict__ Gd, int64_t ldg, const float* __restrict__ norm, int sides,
+                                      float* __restrict__ d_norm) {
   const int lane = threadIdx.x & 31;
   const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (l >= num_long) return;
   const int64_t v = long_rows[l];
   if (v < row_begin || v >= row_end) return;
-  float p = 0.f;
-  for (int c = lane; c < F; c += 32) p = fmaf(__ldg(X + (size_t)v * ldx + c), dX[(size_t)v * lddx + c], p);
+  float p = 0.f, q = 0.f;
+  if (xdx != nullptr || (sides & 1))
+    for (int c = lane; c < F; c += 32) p = fmaf(__ldg(X + (size_t)v * ldx + c), dX[(size_t)v * lddx + c], p);
+  if (d_norm != nullptr && (sides & 2))
+    for (int c = lane; c < F; c += 32) q = fmaf(__ldg(Y + (size_t)v * ldy + c), __ldg(Gd + (size_t)v * ldg + c), q);
   p = group_sum<32>(p);
-  if (lane == 0) xdx[v] = p;
+  q = group_sum<32>(q);
+  if (lane == 0) {
+    if (xdx != nullptr) xdx[v] = p;
+    if (d_norm != nullptr) d_norm[v] = (((sides & 1) ? p : 0.f) + q) / norm[v];
+  }
 }
 
 struct SpmmBwdArgs {
@@ -1181,22 +1213,27 @@ extern "C" int regnn_wdeg_norm_bwd(const int32_t* indptr, const uint8_t* etype_c
   REGNN_REQUIRE((counts || (indptr && etype_csr)) && theta && deg && d_norm && partials && d_theta,
                 REGNN_ERR_INVALID_ARG, "wdeg_norm_bwd: null pointer");
   const int R = num_relations;
-  REGNN_REQUIRE(R >= 1 && R <= 200, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,200]", R);
+  REGNN_REQUIRE(R >= 1 && R <= REGNN_MAX_RELATIONS, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,%d]", R,
+                REGNN_MAX_RELATIONS);
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "wdeg_norm_bwd: negative row range");
   const int nb = partial_blocks(rows);
   const size_t smem = bins_smem_bytes(R);
-  int rc = set_smem(wdeg_norm_bwd_kernel, smem);
-  if (rc != REGNN_OK) return rc;
-  if (counts != nullptr)
+  // the opt-in to > 48 KB of dynamic shared memory (R >= 46) is per kernel: set it on the one that is launched
+  int rc = REGNN_OK;
+  if (counts != nullptr) {
+    if ((rc = set_smem(wdeg_norm_bwd_cnt_kernel, smem)) != REGNN_OK) return rc;
     wdeg_norm_bwd_cnt_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(counts, R, exponent, clamp_min, row_begin, row_end, deg,
                                                                          d_norm, partials);
-  else if (R <= 32)
+  } else if (R <= 32) {
+    if ((rc = set_smem(wdeg_norm_bwd_slot_kernel, smem)) != REGNN_OK) return rc;
     wdeg_norm_bwd_slot_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent, clamp_min, row_begin,
                                                                           row_end, deg, d_norm, partials);
-  else
+  } else {
+    if ((rc = set_smem(wdeg_norm_bwd_kernel, smem)) != REGNN_OK) return rc;
     wdeg_norm_bwd_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(indptr, etype_csr, R, exponent, clamp_min,
                                                                      row_begin, row_end, deg, d_norm, partials);
+  }
   launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
   return check_launch("regnn_wdeg_norm_bwd");
 }
@@ -1247,7 +1284,7 @@ static int common_align(std::initializer_list<const void*> ptrs, std::initialize
   REGNN_STREAM_CASE(4, 1, BINS_, CALL) REGNN_STREAM_CASE(8, 1, BINS_, CALL)
 
 // Lane-group width of spmm_rowgroup_kernel for this call, or 0 when the whole-warp kernels must run: needs the
-// degree-sorted row order (which lists the rows of the FULL range), F <= 64 in whole 128-bit chunks, 16-byte rows.
+// degree-sorted row order (which lists the rows of the FULL range), F <= 128 in whole 128-bit chunks, 16-byte rows.
 #ifndef REGNN_RG_MAXF
 #define REGNN_RG_MAXF 128  // one 128-bit chunk per lane: up to a whole warp per row
 #endif
@@ -1335,7 +1372,7 @@ static int spmm_fwd_impl(const int32_t* indptr, const int32_t* indices, const ui
   rc = fill_peers(&sa.peers, peers, feat, rows, "spmm_fwd");
   if (rc != REGNN_OK) return rc;
   REGNN_REQUIRE(peers == nullptr || G != 0, REGNN_ERR_UNSUPPORTED_SHAPE,
-                "spmm_fwd: the peer scatter needs the narrow-row kernel (row_order, full range, F <= 64, F %% 4 == 0)");
+                "spmm_fwd: the peer scatter needs the lane-group kernel (row_order, full range, F <= 128, F %% 4 == 0)");
   if (G != 0) {  // narrow rows over the degree-sorted row order
     REGNN_REQUIRE(ldx < (1ll << 30), REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: leading dimension too large");
     sa.order = row_order;
@@ -1402,7 +1439,8 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
                                int num_relations, const float* norm, int norm_sides, const float* X,
                                int64_t ldx, const float* Gd, int64_t ldg, float* dX, int64_t lddx,
                                int64_t row_begin, int64_t row_end, int feat, double* partials,
-                               float* d_theta, float* xdx, const regnn_rowsplit_t* split_t,
+                               float* d_theta, float* xdx, const float* Yfwd, int64_t ldyf, float* d_norm,
+                               const regnn_rowsplit_t* split_t,
                                float* split_workspace, const int32_t* row_order_t, const regnn_peer_rows_t* peers,
                                void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1410,7 +1448,8 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
   REGNN_REQUIRE(indptr_t && theta && X && Gd && dX && partials && d_theta,
                 REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: null pointer");
   const int R = num_relations;
-  REGNN_REQUIRE(R >= 1 && R <= 160, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,160]", R);
+  REGNN_REQUIRE(R >= 1 && R <= REGNN_MAX_RELATIONS, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,%d]", R,
+                REGNN_MAX_RELATIONS);  // the shared-memory budget (bins + tile) is checked by set_smem below
   REGNN_REQUIRE(feat >= 1 && ldx >= feat && ldg >= feat && lddx >= feat, REGNN_ERR_INVALID_ARG,
                 "spmm_bwd_fused: bad feature width / leading dimension");
   const int64_t rows = row_end - row_begin;
@@ -1431,6 +1470,13 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
   sa.use_tma = (feat % 4 == 0 && aligned_to(X, 16) && ldx % 4 == 0) ? 1 : 0;
   sa.xdx = xdx;
   const int Fp = (feat + 3) & ~3;
+  if (d_norm != nullptr) {  // folded norm gradient: lane-group kernel only (the caller falls back to regnn_rowdot_norm_bwd)
+    REGNN_REQUIRE(norm != nullptr && peers == nullptr && (!(sides & 2) || (Yfwd != nullptr && ldyf >= feat)),
+                  REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: d_norm needs norm, Y (destination side) and local dX rows");
+    REGNN_REQUIRE(!(sides & 2) || (aligned_to(Yfwd, 16) && ldyf % 4 == 0), REGNN_ERR_INVALID_ARG,
+                  "spmm_bwd_fused: Y rows must be 16-byte aligned");
+    sa.Yfwd = Yfwd; sa.ldyf = ldyf; sa.norm = norm; sa.dn_sides = sides; sa.d_norm = d_norm;
+  }
   const size_t smem = 64 + (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float)) +
                       (size_t)kWarpsPerBlock * kRowsPerItemBins * Fp * sizeof(float);
   int nb = partial_blocks(rows / kRowsPerItemBins + sa.s.nfrag + 1);
@@ -1440,7 +1486,10 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
   rc = fill_peers(&sa.peers, peers, feat, rows, "spmm_bwd_fused");
   if (rc != REGNN_OK) return rc;
   REGNN_REQUIRE(peers == nullptr || G != 0, REGNN_ERR_UNSUPPORTED_SHAPE,
-                "spmm_bwd_fused: the peer scatter needs the narrow-row kernel (row_order_t, full range, F <= 64, F %% 4 == 0)");
+                "spmm_bwd_fused: the peer scatter needs the lane-group kernel (row_order_t, full range, F <= 128, F %% 4 == 0)");
+  REGNN_REQUIRE(d_norm == nullptr || G != 0, REGNN_ERR_UNSUPPORTED_SHAPE,
+                "spmm_bwd_fused: the folded norm gradient needs the lane-group kernel (row_order_t, full range, F <= 128, "
+                "F %% 4 == 0); use regnn_rowdot_norm_bwd otherwise");
   // persistent kernels: exactly one resident wave (148 SMs x blocks per SM), never more than the partial slots
   if (G != 0) {
     REGNN_REQUIRE(ldg < (1ll << 30), REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_fused: leading dimension too large");
@@ -1465,9 +1514,10 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
     spmm_frag_finalize_kernel<<<split_t->num_long, 128, 0, stream>>>(split_t->long_rows, split_t->frag_ptr,
                                                                      split_t->num_long, split_workspace, sa.s.norm_dst, dX,
                                                                      lddx, feat, row_begin, row_end);
-  if (sa.s.nfrag > 0 && xdx != nullptr && peers == nullptr)
-    long_row_xdx_kernel<<<(split_t->num_long + 3) / 4, 128, 0, stream>>>(split_t->long_rows, split_t->num_long, X, ldx, dX,
-                                                                         lddx, feat, row_begin, row_end, xdx);
+  if (sa.s.nfrag > 0 && (xdx != nullptr || d_norm != nullptr) && peers == nullptr)
+    long_row_dnorm_kernel<<<(split_t->num_long + 3) / 4, 128, 0, stream>>>(split_t->long_rows, split_t->num_long, X, ldx, dX,
+                                                                           lddx, feat, row_begin, row_end, xdx, Yfwd, ldyf, Gd,
+                                                                           ldg, norm, sides, d_norm);
   launch_relation_grad_finalize(partials, nb, R, R, theta, alpha, d_theta, stream);
   return check_launch("regnn_spmm_bwd_fused");
 }
@@ -1477,11 +1527,12 @@ extern "C" int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indi
                                     int num_relations, const float* norm, int norm_sides, const float* X,
                                     int64_t ldx, const float* Gd, int64_t ldg, float* dX, int64_t lddx,
                                     int64_t row_begin, int64_t row_end, int feat, double* partials,
-                                    float* d_theta, float* xdx, const regnn_rowsplit_t* split_t,
+                                    float* d_theta, float* xdx, const float* Y, int64_t ldy, float* d_norm,
+                                    const regnn_rowsplit_t* split_t,
                                     float* split_workspace, const int32_t* row_order_t, void* stream) {
   return spmm_bwd_fused_impl(indptr_t, indices_t, etype_t, theta, alpha, num_relations, norm, norm_sides, X, ldx, Gd, ldg,
-                             dX, lddx, row_begin, row_end, feat, partials, d_theta, xdx, split_t, split_workspace,
-                             row_order_t, nullptr, stream);
+                             dX, lddx, row_begin, row_end, feat, partials, d_theta, xdx, Y, ldy, d_norm, split_t,
+                             split_workspace, row_order_t, nullptr, stream);
 }
 
 extern "C" int regnn_spmm_bwd_fused_scatter(const int32_t* indptr_t, const int32_t* indices_t,
@@ -1493,8 +1544,8 @@ extern "C" int regnn_spmm_bwd_fused_scatter(const int32_t* indptr_t, const int32
                                             const int32_t* row_order_t, const regnn_peer_rows_t* peers, void* stream) {
   REGNN_REQUIRE(peers != nullptr, REGNN_ERR_INVALID_ARG, "spmm_bwd_fused_scatter: null peer table");
   return spmm_bwd_fused_impl(indptr_t, indices_t, etype_t, theta, alpha, num_relations, norm, norm_sides, X, ldx, Gd, ldg,
-                             nullptr, 0, 0, num_rows, feat, partials, d_theta, xdx, split_t, split_workspace, row_order_t,
-                             peers, stream);
+                             nullptr, 0, 0, num_rows, feat, partials, d_theta, xdx, nullptr, 0, nullptr, split_t,
+                             split_workspace, row_order_t, peers, stream);
 }
 
 extern "C" int regnn_rowdot_norm_bwd(const float* norm, int norm_sides, const float* X, int64_t ldx,
@@ -1524,7 +1575,8 @@ extern "C" int regnn_spmm_bwd_w(const int32_t* indptr, const int32_t* indices, c
   const bool weighted = etype != nullptr;
   const int R = weighted ? num_relations : 1;
   REGNN_REQUIRE(!weighted || (theta && partials && d_theta), REGNN_ERR_INVALID_ARG, "spmm_bwd_w: null relation buffers");
-  REGNN_REQUIRE(R >= 1 && R <= 200, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,200]", R);
+  REGNN_REQUIRE(R >= 1 && R <= REGNN_MAX_RELATIONS, REGNN_ERR_UNSUPPORTED_SHAPE, "num_relations=%d outside [1,%d]", R,
+                REGNN_MAX_RELATIONS);
   REGNN_REQUIRE(feat >= 1 && ldx >= feat && ldy >= feat && ldg >= feat && lddx >= feat, REGNN_ERR_INVALID_ARG,
                 "spmm_bwd_w: bad feature width / leading dimension");
   const int64_t rows = row_end - row_begin;

@@ -61,11 +61,17 @@ class _Propagate(torch.autograd.Function):
         need_theta = ctx.weighted and ctx.needs_input_grad[3]
         need_norm = ctx.has_norm and ctx.needs_input_grad[5]
         dx = d_theta = d_norm = xdx = None
-        if need_theta and x.shape[1] <= ops.FUSED_BWD_MAX_FEAT and theta.numel() <= ops.FUSED_BWD_MAX_REL:
-            # one gather pass over the transposed view: dX, the relation gradient and <X,dX> together
-            dx, d_theta, xdx = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x, g, sides=ctx.sides,
-                                                  want_xdx=need_norm and bool(ctx.sides & 1))
+        if need_theta and ops.fused_bwd_fits(x.shape[1], theta.numel()):
+            # one gather pass over the transposed view: dX, the relation gradient and the norm gradient together
+            fold = need_norm and ops.fused_dnorm_fits(x.shape[1]) and x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0
+            dx, d_theta, extra = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x, g, sides=ctx.sides,
+                                                    want_xdx=need_norm and not fold and bool(ctx.sides & 1),
+                                                    y=y if fold else None, want_dnorm=fold)
             d_theta = d_theta.view_as(theta)
+            if fold:
+                d_norm = extra
+            else:
+                xdx = extra
         else:
             if need_x or need_norm or need_theta:
                 # transposed SpMM: dX[u] = ns(u) * sum_{e in Out(u)} w_e * nd(dst) * G[dst]
@@ -79,7 +85,7 @@ class _Propagate(torch.autograd.Function):
                 d_theta, _ = ops.spmm_bwd_w(csr, ctx.etv[0], theta, ctx.alpha, norm, x, y, g, dx, sides=ctx.sides,
                                             split=csr.get('split'))
                 d_theta = d_theta.view_as(theta)
-        if need_norm:
+        if need_norm and d_norm is None:
             d_norm = ops.rowdot_norm_bwd(norm, x, y, g, dx, sides=ctx.sides, xdx=xdx)
         return None, None, (dx if need_x else None), d_theta, None, (d_norm if need_norm else None), None
 

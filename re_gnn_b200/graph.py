@@ -164,11 +164,12 @@ class Graph:
 
     def etype_views(self, e_feat, num_relations):
         """uint8 0-based edge types in CSR-slot order and transposed-entry order for the reference's
-        1-based int64 ``e_feat`` (edge-id order).  Cached per tensor (data_ptr, version)."""
+        1-based int64 ``e_feat`` (edge-id order).  Cached per tensor (data_ptr, version); a cached entry holds a
+        reference to the tensor, so the key cannot be recycled by the allocator while the entry lives."""
         key = (e_feat.data_ptr(), e_feat._version, int(e_feat.numel()), int(num_relations))
         hit = self._etype_cache.get(key)
         if hit is not None:
-            return hit
+            return hit[:3]
         csr = self.csr()
         e = self.number_of_edges()
         if e_feat.numel() != e:
@@ -189,5 +190,7 @@ class Graph:
                           _ptr(counts), _stream())
         if len(self._etype_cache) > 8:
             self._etype_cache.clear()
-        self._etype_cache[key] = (et_csr, et_t, counts)
-        return self._etype_cache[key]
+        # the entry keeps ``e_feat`` alive: while it is cached its storage cannot be freed and handed to another
+        # tensor with the same address / version (which would be a silent stale hit)
+        self._etype_cache[key] = (et_csr, et_t, counts, e_feat)
+        return self._etype_cache[key][:3]

@@ -109,6 +109,22 @@ class REMixHopConv(_RelationEmbedded):
         return self.dropout(final)
 
 
+def _kernel_head_dim(d):
+    """Head width the attention kernels run at: the next power of two >= max(4, d) (they reduce over the D/4
+    lanes of a head with butterfly shuffles).  Other widths -- e.g. ``out_feats = num_classes`` -- are zero-padded
+    by the layer: zero columns add nothing to any logit and their outputs / gradients are sliced away."""
+    p = 4
+    while p < d:
+        p *= 2
+    if p > 128:
+        raise ValueError('head width %d is not supported (at most 128 per head)' % d)
+    return p
+
+
+def _pad_last(t, width):
+    return t if t.shape[-1] == width else torch.nn.functional.pad(t, (0, width - t.shape[-1]))
+
+
 def _keep_mask(drop, num_edges, num_heads, like):
     """Attention-dropout scale per (edge, head) in edge-id order, drawn like the reference does
     (``attn_drop`` applied to the [E,H,1] attention tensor)."""
@@ -155,7 +171,10 @@ class REGATConv(_RelationEmbedded):
         er = (f * self.attn_r).sum(dim=-1)
         etv = self._views(graph, edge_feats) if edge_feats is not None else None
         keep = _keep_mask(self.attn_drop, graph.number_of_edges(), self.num_heads, f)
-        rst, _ = RF.gat_aggregate(graph, etv, f, el, er, self.edge_weight, self.alpha, self.negative_slope, keep)
+        dk = _kernel_head_dim(self.out_feats)
+        rst, _ = RF.gat_aggregate(graph, etv, _pad_last(f, dk), el, er, self.edge_weight, self.alpha,
+                                  self.negative_slope, keep)
+        rst = rst[..., :self.out_feats]
         if self.res_fc is not None:
             rst = rst + self.res_fc(h).view(h.shape[0], -1, self.out_feats)
         if self.activation:
@@ -234,8 +253,10 @@ class REGATv2Conv(_RelationEmbedded):
             fd = fs if self.share_weights else self.fc_dst(h_src).view(-1, H, D)
         etv = self._views(graph, edge_feats) if edge_feats is not None else None
         keep = _keep_mask(self.attn_drop, graph.number_of_edges(), H, fs)
-        rst, att = RF.gatv2_aggregate(graph, etv, fs, fd, self.attn, self.edge_weight, self.alpha,
-                                      self.negative_slope, keep, get_attention)
+        dk = _kernel_head_dim(D)
+        rst, att = RF.gatv2_aggregate(graph, etv, _pad_last(fs, dk), _pad_last(fd, dk), _pad_last(self.attn, dk),
+                                      self.edge_weight, self.alpha, self.negative_slope, keep, get_attention)
+        rst = rst[..., :D]
         if self.res_fc is not None:
             rst = rst + self.res_fc(h_dst).view(h_dst.shape[0], -1, D)
         if self.activation:

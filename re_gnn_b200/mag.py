@@ -204,6 +204,12 @@ class REGNN(nn.Module):
             raise NotImplementedError(model)
         self.convs = nn.ModuleList(convs)
         self.out_lin = nn.Linear(self.hidden_dim, out_channels)
+        # model-level norm of the reference (mag/regnn_ns.py:274-277): registered and reset but never used in its
+        # forward -- kept so that a reference checkpoint with use_norm set loads strictly
+        if use_norm == 'bn':
+            self.norm = nn.BatchNorm1d(self.hidden_dim)
+        elif use_norm == 'ln':
+            self.norm = nn.LayerNorm(self.hidden_dim)
 
     def group_input(self, x_dict, node_type, local_node_idx, n_id=None):
         if n_id is not None:

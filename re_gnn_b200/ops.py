@@ -132,8 +132,12 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3,
     return d_theta, d_norm
 
 
-def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None, want_xdx=False):
-    """One gather pass over the transposed view -> (dX[N,F], d_theta[R], xdx[N] | None).  See regnn_spmm_bwd_fused."""
+def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None, want_xdx=False, y=None,
+                   want_dnorm=False):
+    """One gather pass over the transposed view -> (dX[N,F], d_theta[R], xdx[N] | d_norm[N] | None).
+    ``want_dnorm`` (needs ``y`` = the forward result when the destination side is scaled, and a shape the lane-group
+    kernel covers: ``fused_dnorm_fits``): the third result is the whole norm gradient, no row-dot pass needed;
+    ``want_xdx``: it is <X[u],dX[u]> only (input of ``rowdot_norm_bwd``).  See regnn_spmm_bwd_fused."""
     x, g = _f32(x), _f32(g)
     theta = _f32(theta).view(-1)
     n = csr['indptr_t'].numel() - 1
@@ -146,19 +150,39 @@ def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=
     partials = torch.empty(_lib.partial_blocks(re - rb) * r, dtype=torch.float64, device=x.device)
     d_theta = torch.empty(r, dtype=torch.float32, device=x.device)
     sp, ws, extra = _split_args(csr.get('split_t'), f, x.device)
-    xdx = torch.zeros(n, dtype=torch.float32, device=x.device) if want_xdx else None
     order = row_order(csr, True) if (f <= NARROW_FEAT and (rb, re) == (0, n)) else None
+    d_norm = xdx = None
+    if want_dnorm:
+        if order is None or norm is None:
+            raise RuntimeError('the folded norm gradient needs the lane-group kernel (F <= %d, full row range)' % NARROW_FEAT)
+        y = _f32(y)
+        d_norm = torch.empty(n, dtype=torch.float32, device=x.device)
+    elif want_xdx:
+        xdx = torch.zeros(n, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.call('regnn_spmm_bwd_fused', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(et_t), _ptr(theta),
                   float(alpha), r, _ptr(norm), int(sides), _ptr(x), x.stride(0), _ptr(g), g.stride(0), _ptr(out),
-                  out.stride(0), rb, re, f, _ptr(partials), _ptr(d_theta), _ptr(xdx), sp, _ptr(ws), _ptr(order),
-                  _stream())
-        _lib.count_launches(2 + extra * (2 if want_xdx else 1))
-    return out, d_theta, xdx
+                  out.stride(0), rb, re, f, _ptr(partials), _ptr(d_theta), _ptr(xdx), _ptr(y) if want_dnorm else None,
+                  y.stride(0) if (want_dnorm and y is not None) else 0, _ptr(d_norm), sp, _ptr(ws), _ptr(order), _stream())
+        _lib.count_launches(2 + extra * (2 if (want_xdx or want_dnorm) else 1))
+    return out, d_theta, (d_norm if want_dnorm else xdx)
 
 
-FUSED_BWD_MAX_FEAT = 512   # wider rows do not fit the shared-memory tile: two-pass backward instead
-FUSED_BWD_MAX_REL = 160    # relation bins of the fused kernel live in shared memory
+def fused_dnorm_fits(feat, rows_full=True):
+    """True when regnn_spmm_bwd_fused can also produce d_norm (lane-group kernel: F <= NARROW_FEAT, F % 4 == 0)."""
+    return rows_full and feat <= NARROW_FEAT and feat % 4 == 0
+
+
+SMEM_BUDGET = 227 * 1024   # dynamic shared memory one block can opt in to on sm_100a
+
+
+def fused_bwd_fits(feat, num_relations):
+    """True when regnn_spmm_bwd_fused has a kernel for this shape: the lane-local relation bins (1088 bytes per
+    relation) and -- for the whole-warp kernel, F > NARROW_FEAT -- the 8 x 8-row X tile must fit in shared memory.
+    Otherwise the caller takes the two-pass backward (transposed regnn_spmm_fwd + regnn_spmm_bwd_w)."""
+    bins = 1088 * int(num_relations)
+    tile = 0 if feat <= NARROW_FEAT and feat % 4 == 0 else 64 + 256 * ((int(feat) + 3) & ~3)
+    return feat <= 1024 and bins + tile <= SMEM_BUDGET
 
 
 def rowdot_norm_bwd(norm, x, y, g, dx, rows=None, sides=3, xdx=None):

@@ -118,7 +118,8 @@ def spmm_bwd_w(csr, et_csr, theta, alpha, norm, x, y, g, dx, rows=None, sides=3,
     return d_theta, d_norm
 
 
-def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None, want_xdx=False):
+def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=None, want_xdx=False, y=None,
+                   want_dnorm=False):
     ns = norm if (norm is not None and sides & 2) else None
     nd = norm if (norm is not None and sides & 1) else None
     dx = spmm(csr['indptr_t'], csr['indices_t'], et_t, theta, alpha, ns, nd, g, rows=rows, out=out)
@@ -141,6 +142,12 @@ def spmm_bwd_fused(csr, et_t, theta, alpha, norm, x, g, rows=None, sides=3, out=
             own = torch.zeros(xdx.numel(), dtype=torch.bool)
             own[rows[0]:rows[1]] = True
             xdx = torch.where(own, xdx, torch.zeros_like(xdx))
+    if want_dnorm:               # the folded norm gradient of the lane-group kernel
+        n = norm.numel()
+        d = (x[:n] * dx.detach()[:n]).sum(1) * bool(sides & 1)
+        if sides & 2:
+            d = d + (y.detach()[:n] * g[:n]).sum(1)
+        xdx = d / norm.detach()
     return dx, dw * alpha * _lgrad(th * alpha, SLOPE), xdx
 
 

@@ -67,6 +67,12 @@ def assert_close(actual, expected, rtol, name='', max_outlier_frac=0.0, atol=0.0
         if k > 0:
             ratio = torch.topk(ratio.reshape(-1), k + 1, largest=True).values[-1:]
     worst = ratio.max().item() if e.numel() else 0.0
+    # measured errors, printed for passes too (``pytest -rP`` shows them): the norm-wise relative error
+    # max|a-e| / max|e| and the largest purely elementwise relative error over elements with |e| >= 1e-3 * max|e|
+    big = e.abs() >= 1e-3 * scale if scale > 0 else torch.zeros_like(e, dtype=torch.bool)
+    elem = (err[big] / e.abs()[big]).max().item() if bool(big.any()) else 0.0
+    print('[parity] %-28s n=%-9d max|err|/max|ref| = %.2e   max elementwise rel (|ref| >= 1e-3 max) = %.2e   '
+          'bound use %.2f of rtol=%g' % (name, e.numel(), (err.max().item() / scale) if scale > 0 else 0.0, elem, worst, rtol))
     assert worst <= 1.0, '%s: max err %.3e (scale %.3e), %.2fx over rtol=%g' % (
         name, err.max().item(), scale, worst, rtol)
 

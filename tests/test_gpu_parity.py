@@ -447,6 +447,17 @@ def test_narrow_row_kernels_equal_whole_warp_kernels(f, weighted):
         assert torch.equal(dx_n, dx_w)
         helpers.assert_close(dth_n.double().cpu(), dth_w.cpu(), RTOL, 'd_theta')
         helpers.assert_close(xdx_n.cpu(), xdx_w.cpu(), 10 * RTOL, 'xdx', atol=1e-5)
+        # the norm gradient folded into the same pass (d_norm output of regnn_spmm_bwd_fused, hub rows through
+        # long_row_dnorm_kernel) against the separate row-dot pass, for every combination of scaled sides
+        if f % 4 == 0 and DEV != 'cpu':
+            for sides in (3, 1, 2):
+                ns, nd = (nrm if sides & 1 else None), (nrm if sides & 2 else None)
+                y_s = ops.spmm(csr['indptr'], csr['indices'], etv[0], th, 100.0, ns, nd, x, split=csr.get('split'), order=order)
+                dx_s, dth_s, xdx_s = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, x, gout, sides=sides, want_xdx=True)
+                dn_ref = ops.rowdot_norm_bwd(nrm, x, y_s, gout, dx_s, sides=sides, xdx=xdx_s)
+                dx_f, dth_f, dn_f = ops.spmm_bwd_fused(csr, etv[1], th, 100.0, nrm, x, gout, sides=sides, y=y_s, want_dnorm=True)
+                assert torch.equal(dx_f, dx_s) and torch.equal(dth_f, dth_s)
+                helpers.assert_close(dn_f.cpu(), dn_ref.cpu(), 10 * RTOL, 'folded d_norm sides=%d' % sides, atol=1e-5)
 
 
 # ---- feature-sliced (column slab) kernel paths on one GPU: P virtual ranks, each all rows x F/P columns ----
@@ -713,3 +724,166 @@ def test_mag_layers_match_reference_golden(name):
     helpers.assert_close(x.grad.cpu(), c['gx_src'], 2 * RTOL, name + ' d_x')
     for k, p in conv.named_parameters():
         helpers.assert_close(p.grad.cpu(), c['grad::' + k], 5 * RTOL, name + ' d_' + k)
+
+
+@pytest.mark.parametrize('name', helpers.mag_golden_cases('regat'))
+def test_mag_attention_layers_match_reference_golden_gpu(name):
+    """mag.REGATConv / mag.REGATv2Conv on the B200 (fused regnn_gat* / regnn_gatv2* kernels through the C ABI) against
+    the fixtures recorded from the reference's own mag/regnn_layers.py:153-433: outputs and every gradient."""
+    from re_gnn_b200 import mag
+    c = helpers.load_mag_case(name)
+    m = c['meta']
+    conv = getattr(mag, m['kind'])(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], **m['kw'])
+    conv.load_state_dict({k[7:]: torch.as_tensor(v, dtype=torch.float32) for k, v in c.items() if k.startswith('param::')})
+    conv = conv.to(DEV)
+    x = torch.as_tensor(c['x_src'], dtype=torch.float32).to(DEV).requires_grad_(True)
+    n_dst = int(c['n_dst'])
+    out = conv((x, x[:n_dst]) if m['tuple_input'] else x, torch.as_tensor(c['edge_index']).to(DEV),
+               torch.as_tensor(c['edge_type']).to(DEV), torch.as_tensor(c['target_node_type']).to(DEV))
+    out.backward(torch.as_tensor(c['gout'], dtype=torch.float32).to(DEV))
+    # an fp32 GEMM (lin_src) sits in front of the LeakyReLU kink of the logits: same allowance as the HGB module tests
+    helpers.assert_close(out.detach().cpu(), c['out'], RTOL, name + ' out')
+    helpers.assert_close(x.grad.cpu(), c['gx_src'], 1e-4, name + ' d_x', 1e-4)
+    for k, p in conv.named_parameters():
+        helpers.assert_close(p.grad.cpu(), c['grad::' + k], 1e-4, name + ' d_' + k, 1e-4)
+
+
+@pytest.mark.parametrize('name', helpers.mag_golden_cases('model_regnn_'))
+def test_mag_regnn_model_matches_reference_golden_gpu(name):
+    """mag.REGNN (regcn / regat / regatv2, two sampled blocks) on the B200 against the fixtures recorded from the REGNN
+    class of the reference's mag/regnn_ns.py:216-346."""
+    from re_gnn_b200 import mag
+    c = helpers.load_mag_case(name)
+    m = c['meta']
+    feat_dims = {int(k): v for k, v in m['feat_dims'].items()}
+    net = mag.REGNN(m['in_channels'], m['hidden_channels'], m['out_channels'], m['heads'], m['num_layers'], 100.0, 0.0,
+                    feat_dims, m['num_edge_types'], m['residual'], False, self_loop_type=2, model=m['model'])
+    net.load_state_dict({k[7:]: torch.as_tensor(v, dtype=torch.float32) for k, v in c.items() if k.startswith('param::')})
+    net = net.to(DEV).eval()
+    dev = lambda k: torch.as_tensor(c[k]).to(DEV)
+    x_dict = {t: torch.as_tensor(c['x::%d' % t], dtype=torch.float32).to(DEV) for t in feat_dims}
+    adjs = [(dev('adj%d::edge_index' % i), dev('adj%d::e_id' % i), tuple(m['sizes'][i])) for i in range(m['num_layers'])]
+    out = net(dev('n_id'), x_dict, adjs, dev('edge_type'), dev('node_type'), dev('local_node_idx'))
+    out.backward(torch.as_tensor(c['gout'], dtype=torch.float32).to(DEV))
+    helpers.assert_close(out.detach().cpu(), c['out'], 2 * RTOL, name + ' log-probabilities')
+    for k, p in net.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        # atol: some gradients of these fixtures are exactly 0 in float64 (pure rounding noise in fp32)
+        helpers.assert_close(got.cpu(), c['grad::' + k], 1e-4, name + ' d_' + k, 1e-4, atol=1e-6)
+
+
+# ---- relation tables beyond the HGB sizes (shared-memory bins > 48 KB from R = 46 on) -------------------------------
+@pytest.mark.parametrize('r', [46, 64, 200])
+def test_many_relations_norm_and_propagate_vs_oracle(r):
+    rng = np.random.RandomState(r)
+    n, e, f = 700, 9000, 32
+    src = rng.randint(0, n, size=e).astype(np.int64)
+    dst = rng.randint(0, n, size=e).astype(np.int64)
+    et = rng.randint(1, r + 1, size=e).astype(np.int64)
+    g = Graph(src, dst, n).to(DEV)
+    x64 = helpers.f32_exact(rng.randn(n, f)).requires_grad_(True)
+    th64 = _theta(r, 1, r).requires_grad_(True)
+    ref = O.regraphconv_forward(torch.as_tensor(src), torch.as_tensor(dst), torch.as_tensor(et), n, x64, th64, 100.0)
+    x = x64.detach().to(DEV, torch.float32).requires_grad_(True)
+    th = th64.detach().to(DEV, torch.float32).requires_grad_(True)
+    etv = g.etype_views(torch.as_tensor(et), r)
+    out = RF.propagate(g, etv, x, th, 100.0, RF.weighted_degree_norm(g, etv, th, 100.0, -0.5))
+    _compare(out, [x, th], ref, [x64, th64], torch.as_tensor(rng.randn(n, f)), ['x', 'theta'], 2 * RTOL)
+    # the slot-walking variants of the norm backward (no count table) take the same shared-memory opt-in
+    from re_gnn_b200 import ops
+    csr = g.csr()
+    deg, nrm = ops.wdeg_norm_fwd(csr, etv[0], th.detach(), 100.0, -0.5, counts=etv[2])
+    dn = torch.randn(n, device=DEV)
+    a = ops.wdeg_norm_bwd(csr, etv[0], th.detach(), 100.0, -0.5, deg, dn, counts=etv[2])
+    b = ops.wdeg_norm_bwd(csr, etv[0], th.detach(), 100.0, -0.5, deg, dn, counts=None)
+    helpers.assert_close(b.cpu(), a.cpu(), RTOL, 'd_theta via norm: slot walk vs count table', atol=1e-6)
+
+
+@pytest.mark.parametrize('kind,dim', [('REGATConv', 3), ('REGATConv', 12), ('REGATv2Conv', 5), ('REGATv2Conv', 24)])
+def test_attention_head_widths_padded_by_the_layer(kind, dim):
+    """Head widths that are not a power of two (out_feats = num_classes in the reference's commented-out output
+    layer, layer widths like 12 / 24) run zero-padded; outputs and gradients equal the oracle at the true width."""
+    d = synth.hetero_graph('imdb', seed=dim, scale=0.03)
+    g, et = _graph(d), torch.as_tensor(d['etype'])
+    n, r, heads = d['num_nodes'], d['num_relations'], 2
+    rng = np.random.RandomState(dim)
+    mod = getattr(re_gnn_b200, kind)(r, 100.0, 16, dim, heads, negative_slope=0.2)
+    mod.edge_weight.data.copy_(_theta(r, heads, dim))
+    p64 = {k: v.detach().double().requires_grad_(True) for k, v in mod.named_parameters()}
+    x64 = helpers.f32_exact(rng.randn(n, 16)).requires_grad_(True)
+    s64, d64 = torch.as_tensor(d['src']), torch.as_tensor(d['dst'])
+    if kind == 'REGATConv':
+        ref = O.regat_forward(s64, d64, et, n, x64, p64['attn_l'], p64['attn_r'], p64['edge_weight'], 100.0, 0.2,
+                              p64['fc.weight'])
+    else:
+        ref = O.regatv2_forward(s64, d64, et, n, x64, p64['attn'], p64['edge_weight'], 100.0, 0.2,
+                                (p64['fc_src.weight'], p64['fc_src.bias']), (p64['fc_dst.weight'], p64['fc_dst.bias']))
+    gout = helpers.f32_exact(rng.randn(*ref.shape))
+    ref.backward(gout)
+    mod = mod.to(DEV)
+    x = x64.detach().to(DEV, torch.float32).requires_grad_(True)
+    out = mod(g, x, et.to(DEV))
+    assert tuple(out.shape) == (n, heads, dim)
+    out.backward(gout.to(DEV, torch.float32))
+    helpers.assert_close(out.detach().cpu(), ref.detach(), RTOL, kind + ' out')
+    helpers.assert_close(x.grad.cpu(), x64.grad, 1e-4, kind + ' d_x', 1e-4)
+    for k, v in mod.named_parameters():
+        helpers.assert_close(v.grad.cpu(), p64[k].grad, 1e-4, kind + ' d_' + k, 1e-4)
+
+
+# ---- BASELINE config 4 at full size, floats held to the oracle ----------------------------------------------------
+@pytest.fixture(scope='module')
+def mag_full():
+    d = synth.hetero_graph('mag')
+    g = _graph(d)
+    et = torch.as_tensor(d['etype']).to(DEV)
+    return d, g, et
+
+
+@pytest.mark.parametrize('feat', [128, 64])
+def test_mag_full_graph_regcn_vs_oracle_on_row_block(mag_full, feat):
+    """RF.weighted_degree_norm + RF.propagate forward and backward on the FULL ogbn-mag-shaped graph (N = 1.94 M,
+    E = 23.05 M) against the float64 oracle.  The oracle cannot afford [E, F] float64 temporaries for all edges, so the
+    loss is restricted to a destination-row set B: dL/dY is non-zero only on B = (the rows holding the first ~1.2 M
+    in-edges) + (the 16 rows with the most in-edges: 10^4..10^5-slot hub rows that run through the long-row fragment
+    path).  Everything the oracle then needs with an F dimension involves only the edges into B; the relation-weighted
+    degree norm is evaluated on ALL edges (scalars per edge).  Compared: Y on B, dX on all rows (zero outside the
+    sources of B), d_theta (SpMM part + norm part), all from kernels that process the whole graph."""
+    d, g, et = mag_full
+    n, r = d['num_nodes'], d['num_relations']
+    src, dst, etype = (torch.as_tensor(d[k]) for k in ('src', 'dst', 'etype'))
+    indeg = torch.bincount(dst, minlength=n)
+    csum = torch.cumsum(indeg, 0)
+    k_rows = int(torch.searchsorted(csum, torch.tensor(1_200_000)).item()) + 1
+    hubs = torch.topk(indeg, 16).indices
+    assert int(indeg[hubs].min()) > 256, 'hub rows must exceed the fragment threshold'
+    in_b = torch.zeros(n, dtype=torch.bool)
+    in_b[:k_rows] = True
+    in_b[hubs] = True
+    esel = in_b[dst]
+    rng = np.random.RandomState(feat)
+    x32 = torch.as_tensor(rng.standard_normal((n, feat)).astype(np.float32))
+    g32 = torch.as_tensor(rng.standard_normal((n, feat)).astype(np.float32)) * in_b.unsqueeze(1)
+    th32 = _theta(r, 1, feat).to(torch.float32)
+
+    # ---- float64 oracle (oracle/regnn_oracle.py primitives; layer/REGraphConv.py:58-98)
+    th64 = th32.double().requires_grad_(True)
+    x64 = x32.double().requires_grad_(True)
+    ew_all = O.edge_relation(th64, 100.0, etype)                              # [E,1] scalars: affordable for all edges
+    nrm = O.weighted_degree_norm(ew_all, dst, n).unsqueeze(1)                 # norm of every node from ALL its in-edges
+    sb, db = src[esel], dst[esel]
+    msg = (x64 * nrm)[sb] * ew_all[esel]                                      # only the edges into B carry an F dimension
+    y_ref = O.segment_sum(msg, db, n) * nrm                                   # rows outside B: partial / zero, unused
+    (y_ref * g32.double()).sum().backward()
+
+    # ---- B200, whole graph
+    etv = g.etype_views(et, r)
+    x = x32.to(DEV).requires_grad_(True)
+    th = th32.to(DEV).requires_grad_(True)
+    y = RF.propagate(g, etv, x, th, 100.0, RF.weighted_degree_norm(g, etv, th, 100.0, -0.5))
+    y.backward(g32.to(DEV))
+    rows_b = torch.nonzero(in_b).view(-1)
+    helpers.assert_close(y.detach().cpu()[rows_b], y_ref.detach()[rows_b], RTOL, 'MAG F=%d Y[B]' % feat)
+    helpers.assert_close(y.detach().cpu()[hubs], y_ref.detach()[hubs], RTOL, 'MAG F=%d Y[hub rows]' % feat)
+    helpers.assert_close(x.grad.cpu(), x64.grad, 2 * RTOL, 'MAG F=%d dX' % feat)
+    helpers.assert_close(th.grad.cpu(), th64.grad, 2 * RTOL, 'MAG F=%d d_theta' % feat)
