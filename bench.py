@@ -45,6 +45,7 @@ def parse():
                          '(equal rows / equal in-edge counts) fed by all-gathers; auto = peer, else cols (>= 4 ranks) / rows')
     ap.add_argument('--no-others', action='store_true', help='skip the secondary HGB-shaped workloads')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='multi-GPU: run the step eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
 
@@ -248,6 +249,58 @@ def others(dev, steps, warmup):
     return res
 
 
+def attention_at_hbm_scale(dev, d, g, et, steps, warmup):
+    """Fused REGAT / REGATv2 on the ogbn-mag-shaped graph, H*D = 128 (gathered matrix 993 MB >> L2): the HBM-bound case
+    the north-star's '>= 70 % of HBM roofline for fused REGAT edge-softmax+aggregate' is about.  Per shape: GTEPS of
+    the layer's forward+backward through the module API (use_weight=False: no dense projection in front), and a
+    ``roofline`` object for the forward kernel launch timed alone, on SURVEY 8(d)'s gather-model bytes."""
+    import re_gnn_b200
+    from re_gnn_b200 import ops
+    hbm, how = peaks()
+    n, e, r = d['num_nodes'], d['src'].size, d['num_relations']
+    csr = g.csr()
+    etv = g.etype_views(et, r)
+    res = {}
+    gen = torch.Generator(device=dev).manual_seed(99)
+    for kind, heads, dim in (('regat', 8, 16), ('regat', 2, 64), ('regatv2', 8, 16), ('regatv2', 2, 64)):
+        hd = heads * dim
+        cls = re_gnn_b200.REGATConv if kind == 'regat' else re_gnn_b200.REGATv2Conv
+        kw = dict(negative_slope=0.01, use_weight=False)
+        mod = cls(r, ALPHA, hd, dim, heads, **kw).to(dev)
+        mod.edge_weight.data.copy_(theta_init(r, heads))
+        x = (torch.randn(n, hd, device=dev, generator=gen) * 0.5).requires_grad_(True)
+        gout = torch.randn(n, heads, dim, device=dev, generator=gen)
+
+        def layer():
+            x.grad = None
+            mod.zero_grad(set_to_none=True)
+            mod(g, x, et).backward(gout)
+        t = timed(layer, steps, warmup, torch.cuda.synchronize) / steps
+        with torch.no_grad():
+            f3 = x.detach().view(n, heads, dim)
+            th = mod.edge_weight.detach()
+            if kind == 'regat':
+                el, er = (f3 * mod.attn_l).sum(-1), (f3 * mod.attn_r).sum(-1)
+                fwd = lambda: ops.gat_fwd(csr, etv[0], th, ALPHA, f3, el, er, 0.01)
+                alg = e * (4 * hd + 4 * heads + 4 + 1) + n * (4 * hd + 4 * heads + 4 + 8 * heads)
+                kname = 'regnn::gat_fwd (fused logits + LeakyReLU + online edge-softmax + aggregation)'
+            else:
+                at = mod.attn.detach().reshape(-1)
+                fwd = lambda: ops.gatv2_fwd(csr, etv[0], th, ALPHA, f3, f3, at, 0.01)
+                alg = e * (4 * hd + 4 + 1) + n * (2 * 4 * hd + 8 * heads + 4) + 4 * hd
+                kname = 'regnn::gatv2_fwd (fused logits + online edge-softmax + aggregation)'
+            tk = timed(fwd, steps, warmup, torch.cuda.synchronize) / steps
+        res['mag_%s_h%dd%d' % (kind, heads, dim)] = {
+            'gteps_fwd_bwd': e / t / 1e9, 'ms': t * 1e3, 'fwd_kernel_ms': tk * 1e3, 'gteps_fwd': e / tk / 1e9,
+            'num_edges': int(e), 'l2': 'gathered matrix %.0f MB vs 126 MB L2; no flush needed' % (n * hd * 4 / 1e6),
+            'roofline': {'bound': 'hbm', 'kernel': kname, 'achieved': alg / tk / 1e9, 'peak': hbm, 'peak_source': how,
+                         'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm, 'traffic': None,
+                         'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3, 'l2_resident': False}}
+        del mod, x, gout
+        torch.cuda.empty_cache()
+    return res
+
+
 def epoch_times(dev, steps, warmup):
     """Epoch time in the reference's own definition (run_regnn.py:144-159): one training step (forward, cross-entropy
     on the training nodes, backward, Adam) plus one no-grad evaluation forward, full batch, for the three callers
@@ -339,6 +392,7 @@ def run_ours(args, d):
     g_full = torch.randn(n, f, device=dev, generator=gen)
 
     if world == 1:
+        args.partition = 'none'
         x = x_full.clone().requires_grad_(True)
         gout = g_full
 
@@ -377,20 +431,82 @@ def run_ours(args, d):
             dist_propagate = partition.partitioned_propagate
         x = x_full[rb:re].clone().requires_grad_(True)
         gout = g_full[rb:re].clone()
-        del x_full, g_full
 
         def step():
             x.grad = theta.grad = None
             nrm = RF.weighted_degree_norm(g, etv, theta, ALPHA, -0.5)
-            dist_propagate(g, etv, x, theta, ALPHA, nrm, bounds, rank).backward(gout)
-            partition.allreduce_relation_grads([theta])
+            out = dist_propagate(g, etv, x, theta, ALPHA, nrm, bounds, rank)
+            out.backward(gout)
+            partition.allreduce_relation_grads([theta], exchange=xch if mode == 'peer' else None)
+            return out
 
+        # ---- self-check before any timing: this rank's rows of Y and dX against a single-device run of the same step
+        # on this GPU (bit-equal: every kernel adds a row's slots in slot order), the relation gradient within 1e-6
+        xs = x_full.clone().requires_grad_(True)
+        th1 = theta.detach().clone().requires_grad_(True)
+        y1 = RF.propagate(g, etv, xs, th1, ALPHA, RF.weighted_degree_norm(g, etv, th1, ALPHA, -0.5))
+        y1.backward(g_full)
+        y_d = step().detach()
+        rel = float(((theta.grad - th1.grad).abs().max() / th1.grad.abs().max()).item())
+        flags = torch.tensor([int(torch.equal(y_d, y1.detach()[rb:re])), int(torch.equal(x.grad, xs.grad[rb:re])),
+                              int(rel <= 1e-6)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        relt = torch.tensor([rel], device=dev, dtype=torch.float64)
+        dist.all_reduce(relt, op=dist.ReduceOp.MAX)
+        parity_check = {'y_equal': bool(flags[0].item()), 'dx_equal': bool(flags[1].item()),
+                        'd_theta_max_rel_err': float(relt.item()), 'd_theta_ok': bool(flags[2].item()),
+                        'against': 'single-device run of the same step on every rank, rows [r_p, r_p+1) of Y and dX '
+                                   'compared bit for bit, relation gradient to 1e-6 (all ranks must agree: MIN / MAX)'}
+        del x_full, g_full, xs, y1, y_d
+
+    # launches per step, counted on one eager step (a replayed CUDA graph issues the same kernels without going
+    # through the Python wrappers that count them)
+    l0 = _lib.launch_count
+    step()
+    launches_per_step = _lib.launch_count - l0
+    # ---- multi-GPU: the whole step (4 device-side barriers, ~14 launches of 0.02-0.5 ms) replayed as ONE CUDA graph, so
+    # that host launch latency and Python overhead sit outside the measurement's critical path
+    timed_step, graphed = step, False
+    if world > 1 and args.partition == 'peer' and not args.no_graph:
+        ok = 1
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            sync()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                step()
+            sync()
+        except Exception as ex:   # report, do not hide: every rank must take the same path
+            ok = 0
+            if rank == 0:
+                print('[bench] CUDA-graph capture of the multi-GPU step failed (%s: %s); running it eagerly'
+                      % (type(ex).__name__, str(ex)[:200]), file=sys.stderr)
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            timed_step, graphed = cg.replay, True
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = _lib.launch_count
-    total = timed(step, args.steps, args.warmup, sync, barrier)
-    launches = (_lib.launch_count - l0) * args.steps // (args.steps + args.warmup)
+    total = timed(timed_step, args.steps, args.warmup, sync, barrier)
+    launches = launches_per_step * args.steps
     clocks = sampler.stop()
+    # ---- per-phase device timeline of a few extra (eager) steps: CUDA events around every ABI call, barrier and
+    # collective (re_gnn_b200._lib.Trace); max over ranks per phase
+    with _lib.Trace() as tr:
+        for _ in range(3):
+            step()
+    phases = tr.summary(3)
+    if world > 1:
+        keys = sorted(phases)
+        pv = torch.tensor([phases[k] for k in keys], device=dev, dtype=torch.float64)
+        dist.all_reduce(pv, op=dist.ReduceOp.MAX)
+        phases = {k: float(v) for k, v in zip(keys, pv.tolist())}
+    phases = {k: round(v, 4) for k, v in phases.items()}
     if world > 1:
         t = torch.tensor([total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -498,11 +614,21 @@ def run_ours(args, d):
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, d), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
         'roofline': roofline, 'graph_build_s': build_s,
+        'partition': {'mode': args.partition, 'how': PARTITION_HOW.get(args.partition, args.partition),
+                      'cuda_graph_replay': graphed},
+        'phases_ms': dict(phases, note='eager steps with CUDA events around every C-ABI call / barrier / collective, '
+                                       'max over ranks per phase; (gaps) = step time outside them (launch gaps, autograd, '
+                                       'torch glue); the timed region itself runs without these events'),
     }
+    if world > 1:
+        line['parity_check'] = parity_check
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'], _ = cpu_reference_sample(d, f, 3, 1)
     if world == 1 and not args.no_others:
+        del x_bufs, g_bufs, xs, y
+        torch.cuda.empty_cache()
         line['others'] = others(dev, 10, 3)
+        line['others'].update(attention_at_hbm_scale(dev, d, g, et, 5, 3))
         line['epoch_time'] = epoch_times(dev, 10, 3)
     print(json.dumps(line))
     if world > 1:

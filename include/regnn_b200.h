@@ -207,19 +207,25 @@ int regnn_rows_to_slabs(const float* X, int64_t ldx, int64_t num_rows, int feat,
                         float* const* peer_slabs /* device array [num_ranks] */, void* stream);
 
 /* regnn_spmm_fwd over the full row range [0, num_rows) of a column slab (feat <= 128, feat % 4 == 0, row_order required) whose
- * result rows are stored to their owner ranks: peers->base[v / rows_per_rank][(v % rows_per_rank) * ld + col_offset]. */
+ * result rows are stored to their owner ranks: peers->base[v / rows_per_rank][(v % rows_per_rank) * ld + col_offset].
+ * y_local (optional, leading dimension ldl): the result slab is ALSO kept locally -- the backward pass then folds the
+ * norm gradient of this rank's columns into its own kernel (regnn_spmm_bwd_fused_scatter's d_norm). */
 int regnn_spmm_fwd_scatter(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
                            const float* theta, float alpha, int num_relations, const float* norm_src,
                            const float* norm_dst, const float* X, int64_t ldx, int64_t num_rows, int feat,
                            const regnn_rowsplit_t* split, float* split_workspace, const int32_t* row_order,
-                           const regnn_peer_rows_t* peers, void* stream);
+                           const regnn_peer_rows_t* peers, float* y_local, int64_t ldl, void* stream);
 
-/* regnn_spmm_bwd_fused with the dX rows stored to their owner ranks; d_theta / xdx stay local (this rank's
- * columns; the caller sums them across ranks). */
+/* regnn_spmm_bwd_fused with the dX rows stored to their owner ranks; d_theta / xdx / d_norm stay local and cover this
+ * rank's columns only.  d_norm (optional, with Y = the local result slab of regnn_spmm_fwd_scatter): every row's norm
+ * gradient restricted to this rank's columns.  The norm's own backward is linear in d_norm, so each rank pushes its
+ * column share through regnn_wdeg_norm_bwd and the caller sums R floats across ranks -- no N-float exchange and no
+ * separate row-dot pass. */
 int regnn_spmm_bwd_fused_scatter(const int32_t* indptr_t, const int32_t* indices_t, const uint8_t* etype_t,
                                  const float* theta, float alpha, int num_relations, const float* norm,
                                  int norm_sides, const float* X, int64_t ldx, const float* G, int64_t ldg,
                                  int64_t num_rows, int feat, double* partials, float* d_theta, float* xdx,
+                                 const float* Y, int64_t ldy, float* d_norm,
                                  const regnn_rowsplit_t* split_t, float* split_workspace,
                                  const int32_t* row_order_t, const regnn_peer_rows_t* peers, void* stream);
 
@@ -247,7 +253,9 @@ int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, const int32_t* 
                   const float* feat, const float* el, const float* er, float negative_slope,
                   const float* keep, int num_heads, int head_dim, int64_t row_begin, int64_t row_end,
                   float* out, float* rowmax, float* rowsum, float* attn_out, const regnn_rowsplit_t* split,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */,
+    const int32_t* row_order /* as regnn_spmm_fwd's: degree-sorted rows that are not long, or NULL (natural order) */,
+    void* stream);
 
 /* Backward, destination-major pass.  G = dL/d out.  Produces, per CSR slot, a_csr = a*keep and
  * dpre_csr = dL/d(el[src]+er[dst]+w) (both [E,H], slot order), d_er [N,H] and d_theta [R,H].
@@ -259,17 +267,31 @@ int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32
                       const float* G, int num_heads, int head_dim, int64_t row_begin,
                       int64_t row_end, float* a_csr, float* dpre_csr, float* d_er, double* partials,
                       float* d_theta, const regnn_rowsplit_t* split,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, const int32_t* row_order, void* stream);
 
 /* Backward, source-major pass over the transposed view:
  *   d_feat[u,h,:] = sum_{j in Out(u)} a_csr[slot_t[j],h] * G[indices_t[j],h,:]
  *   d_el[u,h]     = sum_{j in Out(u)} dpre_csr[slot_t[j],h]          (dpre_csr may be NULL)
- * (DGL: gspmm on the reverse graph + u_add_v backward reduce). */
+ * (DGL: gspmm on the reverse graph + u_add_v backward reduce).  With attn_l / attn_r ([H,D]) and d_er ([N,H], from
+ * regnn_gat_bwd_dst) the gradient through the projection scores el = <feat, attn_l>, er = <feat, attn_r>
+ * (layer/REGATConv.py:68-69) is folded into the epilogue: d_feat[u,h,:] += d_el[u,h]*attn_l[h,:] + d_er[u,h]*attn_r[h,:]. */
 int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
                       const float* a_csr, const float* dpre_csr, const float* G, int num_heads,
                       int head_dim, int64_t row_begin, int64_t row_end, float* d_feat, float* d_el,
+                      const float* attn_l /* optional */, const float* attn_r, const float* d_er,
                       const regnn_rowsplit_t* split_t /* of the transposed view */,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, const int32_t* row_order_t, void* stream);
+
+/* Projection scores of REGAT (layer/REGATConv.py:68-69: `el = (feat * attn_l).sum(-1)`, `er = (feat * attn_r).sum(-1)`,
+ * two eager mul + sum pairs in the reference) in one streaming pass over feat [N,H,D]: el, er [N,H]. */
+int regnn_attn_scores_fwd(const float* feat, const float* attn_l, const float* attn_r, int64_t num_nodes, int num_heads,
+                          int head_dim, float* el, float* er, void* stream);
+
+/* Parameter gradients of the projection scores: d_attn_l[h,d] = sum_n d_el[n,h]*feat[n,h,d], d_attn_r likewise
+ * (deterministic: lane-local sums, per-block double partials, fixed-order finalize).
+ * partials: double [regnn_max_partial_blocks() * 2*H*D]. */
+int regnn_attn_scores_bwd(const float* feat, const float* d_el, const float* d_er, int64_t num_nodes, int num_heads,
+                          int head_dim, double* partials, float* d_attn_l, float* d_attn_r, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused REGATv2 layer core (layer/REGATv2Conv.py:133-152):

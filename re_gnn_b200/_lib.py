@@ -34,17 +34,20 @@ SIGNATURES = {
     'regnn_spmm_bwd_fused': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i64,
                                     _i32, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
     'regnn_rows_to_slabs': (_i32, [_p, _i64, _i64, _i32, _i32, _i64, _p, _p]),
-    'regnn_spmm_fwd_scatter': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
+    'regnn_spmm_fwd_scatter': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _i64,
+                                      _p]),
     'regnn_spmm_bwd_fused_scatter': (_i32, [_p, _p, _p, _p, _f32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i32,
-                                            _p, _p, _p, _p, _p, _p, _p, _p]),
+                                            _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
     'regnn_rowdot_norm_bwd': (_i32, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p]),
     'regnn_random_walk': (_i32, [_p, _p, _i64, _i64, _i32, ctypes.c_uint64, _p, _p]),
     'regnn_sample_neighbors': (_i32, [_p, _p, _i64, _i32, ctypes.c_uint64, _p, _p]),
     'regnn_gat_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
-                             _p, _p, _p, _p, _p, _p, _p]),
+                             _p, _p, _p, _p, _p, _p, _p, _p]),
     'regnn_gat_bwd_dst': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p,
-                                 _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
-    'regnn_gat_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
+                                 _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'regnn_gat_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'regnn_attn_scores_fwd': (_i32, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
+    'regnn_attn_scores_bwd': (_i32, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p]),
     'regnn_gatv2_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
                                _p, _p, _p, _p, _p, _p, _p]),
     'regnn_gatv2_bwd_dst': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p,
@@ -97,10 +100,90 @@ def count_launches(n):
     launch_count += n
 
 
+# ---- tracing: NVTX ranges around every ABI call, and an optional CUDA-event timeline -----------------------------
+# NVTX costs well under a microsecond per call when no profiler is attached; REGNN_NVTX=0 turns it off.
+_NVTX = os.environ.get('REGNN_NVTX', '1') != '0'
+_trace = None   # active Trace or None
+
+
+class Trace:
+    """Per-phase device timeline of a region: while active, every ABI call (and every ``phase(name)`` block, used by
+    partition.py around barriers / collectives) is bracketed by CUDA events on the current stream.
+    ``summary(steps)`` -> {name: milliseconds per step}, plus ``'(gaps)'`` = region time not covered by any phase
+    (launch gaps, allocator and autograd overhead, torch glue kernels).  Costs two event records per call: use it
+    on a few extra steps, never inside a timed region."""
+
+    def __init__(self):
+        self.events = []      # (name, start, end)
+        self.t0 = self.t1 = None
+
+    def __enter__(self):
+        global _trace
+        import torch
+        self.t0 = torch.cuda.Event(enable_timing=True)
+        self.t0.record()
+        _trace = self
+        return self
+
+    def __exit__(self, *exc):
+        global _trace
+        import torch
+        _trace = None
+        self.t1 = torch.cuda.Event(enable_timing=True)
+        self.t1.record()
+
+    def summary(self, steps=1):
+        import torch
+        torch.cuda.synchronize()
+        out, covered = {}, 0.0
+        for name, a, b in self.events:
+            ms = a.elapsed_time(b)
+            out[name] = out.get(name, 0.0) + ms / steps
+            covered += ms
+        total = self.t0.elapsed_time(self.t1)
+        out['(gaps)'] = max(0.0, total - covered) / steps
+        out['(total)'] = total / steps
+        return out
+
+
+class phase:
+    """``with _lib.phase('barrier'): ...`` -- NVTX range + (when a Trace is active) a timeline entry."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        global _NVTX
+        import torch
+        if _NVTX:
+            try:
+                torch.cuda.nvtx.range_push(self.name)
+                self.pushed = True
+            except Exception:   # no NVTX in this build / no CUDA runtime: switch the ranges off, keep going
+                _NVTX = False
+        if _trace is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        if _trace is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _trace.events.append((self.name, self.a, b))
+        if getattr(self, 'pushed', False):
+            torch.cuda.nvtx.range_pop()
+
+
 def call(name, *args):
     """Calls a status-returning entry point; raises RuntimeError with the library's message on failure."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _NVTX or _trace is not None:
+        with phase(name):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.regnn_last_error_string().decode() or lib.regnn_status_string(rc).decode()
         raise RuntimeError('%s failed (%d: %s): %s' % (name, rc, lib.regnn_status_string(rc).decode(), msg))

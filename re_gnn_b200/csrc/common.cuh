@@ -89,6 +89,18 @@ inline int set_smem(K kernel, size_t bytes) {
   return REGNN_OK;
 }
 
+// Grid of a persistent kernel: exactly one resident wave (SMs x blocks per SM), never more than the partial slots.
+template <typename K>
+inline int resident_blocks(K kernel, size_t smem) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const int want = sms * per_sm;
+  return want < kMaxPartialBlocks ? want : kMaxPartialBlocks;
+}
+
 inline int partial_blocks(int64_t rows) {
   int64_t b = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (b < 1) b = 1;

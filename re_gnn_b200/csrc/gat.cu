@@ -53,6 +53,14 @@ struct AttnArgs {
   float* p0;               // [nfrag][H*D]  partial rows (fwd: un-normalised acc; bwd: d_feat / d_fd / d_fs)
   float* p1;               // [nfrag][H]    fwd: fragment max      bwd: d_er / d_el partial
   float* p2;               // [nfrag][H]    fwd: fragment sum
+  // row-group REGAT kernels: rows of the view that are not cut into fragments, by descending slot count (null:
+  // natural order over [row_begin, row_end), rows longer than the threshold skipped)
+  const int32_t* order;
+  int64_t n_order;
+  // gat_bwd_src epilogue (optional): d_feat[u,h,:] += d_el[u,h]*attn_l[h,:] + d_er[u,h]*attn_r[h,:]
+  const float* attn_l;
+  const float* attn_r;
+  const float* d_er_in;
 };
 
 struct WorkItem {
@@ -144,318 +152,449 @@ __device__ __forceinline__ void split_item(int64_t wi, int HG, int64_t* ri, int*
 }
 
 // =================================================================================================
-// REGAT forward.  Logits of a batch of 32 edges are computed one edge per lane (heads of this group);
-// batch max / sum through warp shuffles; probabilities staged in shared memory; then the warp
-// aggregates the batch with kUA coalesced 128-bit loads in flight per lane.
-// Dynamic smem: w_s[R*H] | per warp: p_s[32][HP], sc_s[H], m_s[H]     (HP = H|1: conflict-free)
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
-gat_fwd_kernel(AttnArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  const int H = a.H, HD = H * a.D, HP = H | 1;
-  float* w_s = smem;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* p_s = smem + a.R * H + warp * (32 * HP + 2 * H);
-  float* sc_s = p_s + 32 * HP;
-  float* m_s = sc_s + H;
-  load_rel_table(w_s, a);
-  const int HG = num_groups(a);
-  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  int64_t ri;
-  int hg;
-  split_item(wi, HG, &ri, &hg);
-  const WorkItem it = decode_item(a, ri, a.nfrag);
-  if (!it.ok) return;
-  const Group g = make_group(a, hg, lane);
-  const int64_t v = it.v;
-  const int s0 = it.s0, len = it.len;
-  float4 acc = zero4();
-  float m_run = -INFINITY, s_run = 0.f;  // lane t (< nh) owns the running max / sum of head h_lo + t
-  const float* fcol = a.feat + g.col;
-  const bool need_eid = a.keep != nullptr || a.o3 != nullptr;
-  const int tl = g.hl - g.h_lo;
+// Row-group REGAT kernels (forward, destination-major backward, source-major backward).
+//
+// Mapping (as spmm_rowgroup_kernel): a 128-bit chunk per lane covers a slice of min(H*D, 128) floats of a row with
+// G = 4 / 8 / 16 / 32 lanes, so a warp works on 32/G rows at once and one gather instruction fetches 32/G source rows;
+// rows wider than 128 floats are cut into H*D/128 slices that are independent items (heads never mix).  Rows come
+// from the degree-sorted row list of the view, fragments of long rows first.
+// Every lane evaluates the logit of ITS OWN head for the edge at hand (one 4-byte load of el[src,h], served by the
+// same sector for all lanes of the group, + er[v,h] from a register + the relation table in shared memory), so the
+// edge softmax needs no cross-lane max / sum and no shared-memory staging: the lanes of a head carry identical
+// running (max, sum) pairs.  Online softmax per batch of U edges: one rescale exp per batch + one exp per edge.
+// Column indices / edge types are loaded cooperatively (lane l of a group loads slot t0+l) and broadcast by shuffles.
+struct RowItem {
+  int64_t v, fi;
+  int begin, len, hg;
+  bool frag;
+};
 
-  for (int base = 0; base < len; base += 32) {
-    const int cnt = min(32, len - base);
-    const bool valid = lane < cnt;
-    const int slot = s0 + base + lane;
-    int idx = 0, et = 0, e = 0;
-    if (valid) {
-      idx = a.indices[slot];
-      if (a.etype != nullptr) et = a.etype[slot];
-      if (need_eid) e = a.eid[slot];
+template <int G>
+__device__ __forceinline__ RowItem rg_item(const AttnArgs& a, int64_t wi, int grp) {
+  constexpr int GPW = 32 / G;
+  RowItem it{-1, 0, 0, 0, 0, false};
+  const int64_t nrows = a.order != nullptr ? a.n_order : (a.row_end - a.row_begin);
+  const int64_t nitems = (a.nfrag + nrows) * a.hg_count;
+  const int64_t vi = wi * GPW + grp;
+  if (vi >= nitems) return it;
+  int64_t ri = vi;
+  if (a.hg_count > 1) split_item(vi, a.hg_count, &ri, &it.hg);
+  if (ri < a.nfrag) {
+    it.frag = true;
+    it.fi = ri;
+    const int64_t v = a.frag_row[ri];
+    if (v >= a.row_begin && v < a.row_end) {
+      it.v = v;
+      it.begin = a.frag_begin[ri];
+      it.len = min(a.threshold, a.indptr[v + 1] - it.begin);
     }
-    for (int t = 0; t < g.nh; ++t) {
-      const int h = g.h_lo + t;
-      float x = -INFINITY;
-      if (valid) {
-        float pre = __ldg(a.el + (size_t)idx * H + h) + __ldg(a.er + (size_t)v * H + h);
-        if (a.etype != nullptr) pre += w_s[et * H + h];
-        x = leaky(pre, a.slope);
-        if (a.o3 != nullptr) a.o3[(size_t)e * H + h] = x;  // raw logit; normalised after the row
-      }
-      const float bm = warp_max(x);
-      const float m_old = __shfl_sync(0xffffffffu, m_run, t);
-      const float m_new = fmaxf(m_old, bm);
-      float p = valid ? expf(x - m_new) : 0.f;
-      const float bs = group_sum<32>(p);
-      const float sc = expf(m_old - m_new);  // first batch: exp(-inf) = 0
-      if (lane == t) {
-        m_run = m_new;
-        s_run = s_run * sc + bs;
-        sc_s[t] = sc;
-      }
-      if (valid && a.keep != nullptr) p *= __ldg(a.keep + (size_t)e * H + h);
-      p_s[lane * HP + t] = p;
+  } else {
+    const int64_t v = a.order != nullptr ? (int64_t)a.order[ri - a.nfrag] : a.row_begin + (ri - a.nfrag);
+    const int b = a.indptr[v];
+    const int l = a.indptr[v + 1] - b;
+    if (l <= a.threshold) {  // longer rows are covered by fragments
+      it.v = v;
+      it.begin = b;
+      it.len = l;
     }
-    __syncwarp();
-    scale4(acc, sc_s[tl]);
-    // full groups of kUA edges run without per-edge predicates; the tail group is predicated
-    auto body = [&](int j, auto full_tag) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      float4 x[kUA];
-      float p[kUA];
-#pragma unroll
-      for (int u = 0; u < kUA; ++u) {
-        const bool ok = FULL || j + u < cnt;
-        const int jj = ok ? j + u : j;
-        const int sidx = __shfl_sync(0xffffffffu, idx, jj);
-        const bool ld = ok && g.ok;
-        x[u] = ld ? ldg4(fcol + (size_t)sidx * HD) : zero4();
-        p[u] = ld ? p_s[jj * HP + tl] : 0.f;
+  }
+  return it;
+}
+__device__ __forceinline__ int64_t rg_num_work(const AttnArgs& a, int G) {
+  const int64_t nrows = a.order != nullptr ? a.n_order : (a.row_end - a.row_begin);
+  const int GPW = 32 / G;
+  return ((a.nfrag + nrows) * a.hg_count + GPW - 1) / GPW;
+}
+
+constexpr int kUG = 4;  // edges per online-softmax batch (= gathers in flight per lane)
+
+template <int G, bool EXTRA>   // EXTRA: attention dropout mask and / or attention output (both need edge ids)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (EXTRA || G < 32) ? 4 : 5)   // 48 registers spill for G < 32
+gat_fwd_rg_kernel(AttnArgs a) {
+  constexpr int U = kUG;
+  static_assert(G % U == 0, "a batch must not straddle a cooperative slot load");
+  extern __shared__ __align__(16) float smem[];
+  float* w_s = smem;
+  load_rel_table(w_s, a);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
+  const int H = a.H, HD = H * a.D;
+  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (wi >= rg_num_work(a, G)) return;  // warp-uniform
+  const RowItem it = rg_item<G>(a, wi, grp);
+  const int col = it.hg * 128 + lg * 4;
+  const bool col_ok = col < HD;
+  const int h = col_ok ? (col >> a.d_shift) : 0;
+  const bool act = it.v >= 0 && col_ok;
+  const bool leader = act && (col & (a.D - 1)) == 0;
+  const int len = it.v >= 0 ? it.len : 0;
+  const int maxlen = __reduce_max_sync(0xffffffffu, len);
+  const bool has_rel = a.etype != nullptr;
+  constexpr bool need_eid = EXTRA;
+  const float er_v = act ? __ldg(a.er + (size_t)it.v * H + h) : 0.f;
+  const float* fcol = a.feat + (col_ok ? col : 0);
+  const float* elh = a.el + h;
+  const int32_t* ip = a.indices + it.begin;
+  const uint8_t* ep = a.etype + it.begin;
+  const int32_t* eidp = a.eid + it.begin;
+  float4 acc = zero4();
+  float m = -INFINITY, s = 0.f;
+
+  for (int t0 = 0; t0 < maxlen; t0 += G) {
+    int bi = -1, be = 0, beid = 0;
+    {
+      const int t = t0 + lg;
+      if (t < len) {
+        bi = __ldg(ip + t);
+        if (has_rel) be = __ldg(ep + t);
+        if (need_eid) beid = __ldg(eidp + t);
       }
+    }
+    const int cnt = min(G, maxlen - t0);
+    for (int j = 0; j < cnt; j += U) {
+      float4 x[U];
+      float l[U];
+      int si[U], seid[EXTRA ? U : 1];
 #pragma unroll
-      for (int u = 0; u < kUA; ++u) fma4(acc, p[u], x[u]);
-    };
-    int j = 0;
-    for (; j + kUA <= cnt; j += kUA) body(j, std::true_type{});
-    if (j < cnt) body(j, std::false_type{});
-    __syncwarp();
+      for (int u = 0; u < U; ++u) {
+        si[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+        const bool ok = si[u] >= 0 && col_ok;
+        x[u] = ok ? ldg4(fcol + (size_t)si[u] * HD) : zero4();
+        l[u] = ok ? __ldg(elh + (size_t)si[u] * H) : 0.f;
+      }
+      float bm = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float pre = l[u] + er_v;
+        if (has_rel) pre += w_s[__shfl_sync(0xffffffffu, be, gbase + j + u) * H + h];
+        if (EXTRA) seid[u] = __shfl_sync(0xffffffffu, beid, gbase + j + u);
+        l[u] = si[u] >= 0 ? leaky(pre, a.slope) : -INFINITY;
+        bm = fmaxf(bm, l[u]);
+      }
+      if (bm > -INFINITY) {  // uniform within a lane group
+        const float m_new = fmaxf(m, bm);
+        const float sc = __expf(m - m_new);  // first batch: exp(-inf) = 0
+        m = m_new;
+        s *= sc;
+        scale4(acc, sc);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float p = __expf(l[u] - m_new);  // 0 for a missing slot
+          s += p;
+          if (EXTRA && si[u] >= 0 && act) {
+            const size_t o = (size_t)seid[u] * H + h;
+            if (a.o3 != nullptr && leader) a.o3[o] = l[u];  // raw logit; normalised after the row
+            if (a.keep != nullptr) p *= __ldg(a.keep + o);
+          }
+          fma4(acc, p, x[u]);
+        }
+      }
+    }
   }
 
   if (it.frag) {  // un-normalised partial + fragment statistics; attn_frag_finalize_kernel merges them
-    if (lane < g.nh) {
-      a.p1[(size_t)it.fi * H + g.h_lo + lane] = m_run;
-      a.p2[(size_t)it.fi * H + g.h_lo + lane] = s_run;
+    if (act) st4(a.p0 + (size_t)it.fi * HD + col, acc);
+    if (leader) {
+      a.p1[(size_t)it.fi * H + h] = m;
+      a.p2[(size_t)it.fi * H + h] = s;
     }
-    if (g.ok) st4(a.p0 + (size_t)it.fi * HD + g.col, acc);
     return;
   }
-  if (lane < g.nh) {
-    const float m = len > 0 ? m_run : 0.f;
-    a.o1[(size_t)v * H + g.h_lo + lane] = m;
-    a.o2[(size_t)v * H + g.h_lo + lane] = s_run;
-    sc_s[lane] = s_run > 0.f ? 1.f / s_run : 0.f;
-    m_s[lane] = m;
-  }
-  __syncwarp();
-  if (g.ok) {
-    scale4(acc, sc_s[tl]);
-    st4(a.o0 + (size_t)v * HD + g.col, acc);
-  }
-  if (a.o3 != nullptr) {  // get_attention: stored logits -> a*keep, edge-id order (heads of this group)
-    for (int i = lane; i < len * g.nh; i += 32) {
-      const int t = i % g.nh;
-      const size_t o = (size_t)a.eid[s0 + i / g.nh] * H + g.h_lo + t;
-      float av = expf(a.o3[o] - m_s[t]) * sc_s[t];
-      if (a.keep != nullptr) av *= a.keep[o];
-      a.o3[o] = av;
+  const float inv = s > 0.f ? 1.f / s : 0.f;
+  const float mm = len > 0 ? m : 0.f;
+  if (act) {
+    scale4(acc, inv);
+    st4(a.o0 + (size_t)it.v * HD + col, acc);
+    if (leader) {
+      a.o1[(size_t)it.v * H + h] = mm;
+      a.o2[(size_t)it.v * H + h] = s;
     }
+  }
+  if (EXTRA && a.o3 != nullptr) {  // get_attention: stored logits -> a*keep, edge-id order; the lanes of a head share its slots
+    __syncwarp();
+    const int lph = min(G, a.D >> 2);
+    if (act)
+      for (int t = lg & (lph - 1); t < len; t += lph) {
+        const size_t o = (size_t)eidp[t] * H + h;
+        float av = __expf(a.o3[o] - mm) * inv;
+        if (a.keep != nullptr) av *= a.keep[o];
+        a.o3[o] = av;
+      }
   }
 }
 
-// =================================================================================================
-// REGAT backward, destination-major.  Per edge: da = <feat[src,h,:], G[v,h,:]>, a recomputed from the
-// saved row max / sum, dl = a*keep*da - a*S with S = <out[v,h,:], G[v,h,:]>.
-// Two phases per batch of 32 slots, like the forward: (1) one edge per lane recomputes a, a*keep and the
-// LeakyReLU slope for the heads of this group (the el[src] gathers and exps are spread over 32 lanes instead
-// of serialising on the head-leader lanes); (2) the warp gathers the feat[src] slices, reduces the dots in the
-// D/4-lane head groups and the leader lanes finish dpre; (3) each lane writes the values of its edge.
-// Dynamic smem: w_s[R*H] | per warp: binsw[R*H] | per warp: pa_s, pt_s, pg_s, dp_s [32][HP]
-template <int LPH>   // lanes per head = min(32, D/4), a power of two
+// REGAT backward, destination-major.  Per edge: da = <feat[src,h,:], G[v,h,:]> (butterfly over the D/4 lanes of the
+// head), a recomputed from the saved row max / sum, dpre = (a*keep*da - a*S) * LeakyReLU'(pre), S = <out[v,h,:],
+// G[v,h,:]>.  Writes a*keep and dpre per (slot, head), d_er rows, and lane-group-local relation bins.
+// Dynamic smem: w_s[R*H] | per warp: bins[R*H][GPW]
+template <int G>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
-gat_bwd_dst_kernel(AttnArgs a) {
+gat_bwd_dst_rg_kernel(AttnArgs a) {
+  constexpr int GPW = 32 / G, U = kUG;
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, HD = H * a.D, HP = H | 1, RH = a.etype != nullptr ? a.R * H : 0;
+  const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
   float* w_s = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* binsw = smem + RH + warp * RH;
-  float* pa_s = smem + RH * (1 + kWarpsPerBlock) + warp * (4 * 32 * HP);
-  float* pt_s = pa_s + 32 * HP;
-  float* pg_s = pt_s + 32 * HP;
-  float* dp_s = pg_s + 32 * HP;
-  for (int i = lane; i < RH; i += 32) binsw[i] = 0.f;
+  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
+  float* bins = smem + RH + (size_t)warp * RH * GPW;
+  for (int i = lane; i < RH * GPW; i += 32) bins[i] = 0.f;
   load_rel_table(w_s, a);
-  const int HG = num_groups(a);
-  const int64_t items = (a.nfrag + (a.row_end - a.row_begin)) * HG;
+  const int lph = min(G, a.D >> 2);
+  const bool has_rel = a.etype != nullptr;
+  const int64_t nwork = rg_num_work(a, G);
 
-  for (int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; wi < items;
-       wi += (int64_t)gridDim.x * kWarpsPerBlock) {
-    int64_t ri;
-    int hg;
-    split_item(wi, HG, &ri, &hg);
-    const WorkItem it = decode_item(a, ri, a.nfrag);
-    if (!it.ok) continue;
-    const Group g = make_group(a, hg, lane);
-    const int64_t v = it.v;
-    const int s0 = it.s0, len = it.len;
-    const int tl = g.hl - g.h_lo;
-    const float* fcol = a.feat + g.col;
+  for (int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; wi < nwork; wi += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const RowItem it = rg_item<G>(a, wi, grp);
+    const int col = it.hg * 128 + lg * 4;
+    const bool col_ok = col < HD;
+    const int h = col_ok ? (col >> a.d_shift) : 0;
+    const bool act = it.v >= 0 && col_ok;
+    const bool leader = act && (col & (a.D - 1)) == 0;
+    const int len = it.v >= 0 ? it.len : 0;
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
     float4 gv = zero4();
-    float part = 0.f, der = 0.f;
-    if (g.ok) {
-      gv = ldg4(a.G + (size_t)v * HD + g.col);
-      part = dot4(ldg4(a.out + (size_t)v * HD + g.col), gv);
+    float part = 0.f, er_v = 0.f, m = 0.f, inv = 0.f, der = 0.f;
+    if (act) {
+      gv = ldg4(a.G + (size_t)it.v * HD + col);
+      part = dot4(ldg4(a.out + (size_t)it.v * HD + col), gv);
+      const size_t vh = (size_t)it.v * H + h;
+      er_v = __ldg(a.er + vh);
+      m = __ldg(a.rowmax + vh);
+      const float sm = __ldg(a.rowsum + vh);
+      inv = sm > 0.f ? 1.f / sm : 0.f;
     }
-    const float S = group_sum<LPH>(part);
-    for (int base = 0; base < len; base += 32) {
-      const int cnt = min(32, len - base);
-      const bool valid = lane < cnt;
-      const int slot = s0 + base + lane;
-      int idx = 0, et = 0, e = 0;
-      if (valid) {
-        idx = a.indices[slot];
-        if (a.etype != nullptr) et = a.etype[slot];
-        if (a.keep != nullptr) e = a.eid[slot];
-      }
-      for (int t = 0; t < g.nh; ++t) {  // phase 1: one edge per lane
-        const int h = g.h_lo + t;
-        float aa = 0.f, at = 0.f, gr = 0.f;
-        if (valid) {
-          const size_t vh = (size_t)v * H + h;
-          float pre = __ldg(a.el + (size_t)idx * H + h) + __ldg(a.er + vh);
-          if (a.etype != nullptr) pre += w_s[et * H + h];
-          const float sm = __ldg(a.rowsum + vh);
-          aa = expf(leaky(pre, a.slope) - __ldg(a.rowmax + vh)) * (sm > 0.f ? 1.f / sm : 0.f);
-          at = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)e * H + h) : aa;
-          gr = leaky_grad(pre, a.slope);
+    const float S = group_sum_rt(part, lph);
+    const float* fcol = a.feat + (col_ok ? col : 0);
+    const float* elh = a.el + h;
+    const int32_t* ip = a.indices + it.begin;
+    const uint8_t* ep = a.etype + it.begin;
+    const int32_t* eidp = a.eid + it.begin;
+
+    for (int t0 = 0; t0 < maxlen; t0 += G) {
+      int bi = -1, be = 0, beid = 0;
+      {
+        const int t = t0 + lg;
+        if (t < len) {
+          bi = __ldg(ip + t);
+          if (has_rel) be = __ldg(ep + t);
+          if (a.keep != nullptr) beid = __ldg(eidp + t);
         }
-        pa_s[lane * HP + t] = aa;
-        pt_s[lane * HP + t] = at;
-        pg_s[lane * HP + t] = gr;
       }
-      __syncwarp();
-      auto body = [&](int j, auto full_tag) {  // phase 2: gather + per-head dots
-        constexpr bool FULL = decltype(full_tag)::value;
-        float4 x[kUA];
-        float da[kUA];
+      const int cnt = min(G, maxlen - t0);
+      for (int j = 0; j < cnt; j += U) {
+        float4 x[U];
+        float e[U], da[U];
+        int si[U];
 #pragma unroll
-        for (int u = 0; u < kUA; ++u) {
-          const bool ok = FULL || j + u < cnt;
-          const int sidx = __shfl_sync(0xffffffffu, idx, ok ? j + u : j);
-          x[u] = (ok && g.ok) ? ldg4(fcol + (size_t)sidx * HD) : zero4();
+        for (int u = 0; u < U; ++u) {
+          si[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+          const bool ok = si[u] >= 0 && col_ok;
+          x[u] = ok ? ldg4(fcol + (size_t)si[u] * HD) : zero4();
+          e[u] = ok ? __ldg(elh + (size_t)si[u] * H) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < kUA; ++u) da[u] = group_sum<LPH>(dot4(x[u], gv));  // independent reductions: ILP
+        for (int u = 0; u < U; ++u) da[u] = group_sum_rt(dot4(x[u], gv), lph);  // U independent reductions
 #pragma unroll
-        for (int u = 0; u < kUA; ++u) {
-          if (FULL || j + u < cnt) {  // warp-uniform
-            const int set = __shfl_sync(0xffffffffu, et, j + u);
-            if (g.leader) {
-              const int o = (j + u) * HP + tl;
-              const float dp = (pt_s[o] * da[u] - pa_s[o] * S) * pg_s[o];
-              dp_s[o] = dp;
-              der += dp;
-              if (a.etype != nullptr) binsw[set * H + g.hl] += dp;
+        for (int u = 0; u < U; ++u) {
+          const int se = has_rel ? __shfl_sync(0xffffffffu, be, gbase + j + u) : 0;
+          const int seid = a.keep != nullptr ? __shfl_sync(0xffffffffu, beid, gbase + j + u) : 0;
+          if (si[u] >= 0 && act) {
+            float pre = e[u] + er_v;
+            if (has_rel) pre += w_s[se * H + h];
+            const float aa = __expf(leaky(pre, a.slope) - m) * inv;
+            const float at = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)seid * H + h) : aa;
+            const float dp = (at * da[u] - aa * S) * leaky_grad(pre, a.slope);
+            der += dp;
+            if (leader) {
+              const size_t sh = (size_t)(it.begin + t0 + j + u) * H + h;
+              a.o0[sh] = at;
+              a.o1[sh] = dp;
+              if (has_rel) bins[(se * H + h) * GPW + grp] += dp;  // one writer per (head, lane group): no conflicts
             }
           }
         }
-      };
-      {
-        int j = 0;
-        for (; j + kUA <= cnt; j += kUA) body(j, std::true_type{});
-        if (j < cnt) body(j, std::false_type{});
       }
-      __syncwarp();
-      if (valid) {  // phase 3: each lane writes the heads of its own edge
-        float* ao = a.o0 + (size_t)slot * H + g.h_lo;
-        float* po = a.o1 + (size_t)slot * H + g.h_lo;
-        for (int t = 0; t < g.nh; ++t) {
-          ao[t] = pt_s[lane * HP + t];
-          po[t] = dp_s[lane * HP + t];
-        }
-      }
-      __syncwarp();
     }
-    if (g.leader) {
-      if (it.frag) a.p1[(size_t)it.fi * H + g.hl] = der;
-      else a.o2[(size_t)v * H + g.hl] = der;
+    if (leader) {
+      if (it.frag) a.p1[(size_t)it.fi * H + h] = der;
+      else a.o2[(size_t)it.v * H + h] = der;
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < RH; i += blockDim.x) {
-    double s = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w) s += (double)smem[RH + w * RH + i];
-    a.partials[(size_t)blockIdx.x * a.partial_stride + i] = s;
+    double sum = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w)
+      for (int q = 0; q < GPW; ++q) sum += (double)smem[RH + ((size_t)w * RH + i) * GPW + q];
+    a.partials[(size_t)blockIdx.x * a.partial_stride + i] = sum;
   }
 }
 
-// =================================================================================================
-// Source-major aggregation with precomputed per-slot, per-head weights (REGAT backward w.r.t. feat,
-// and the el-gradient reduction):  d_feat[u] = sum_j a_csr[slot_t[j]] * G[indices_t[j]].
-// Dynamic smem per warp: p_s[32][HP]
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
-gat_bwd_src_kernel(AttnArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  const int H = a.H, HD = H * a.D, HP = H | 1;
+// Source-major aggregation with the stored per-slot, per-head weights:
+//   d_feat[u,h,:] = sum_j a_csr[slot_t[j],h] * G[indices_t[j],h,:]     d_el[u,h] = sum_j dpre_csr[slot_t[j],h]
+// and, when attn_l / attn_r / d_er are given, the projection-score gradient folded into the epilogue:
+//   d_feat[u,h,:] += d_el[u,h] * attn_l[h,:] + d_er[u,h] * attn_r[h,:]
+template <int G>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+gat_bwd_src_rg_kernel(AttnArgs a) {
+  constexpr int U = kUG;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* p_s = smem + warp * (32 * HP);
-  const int HG = num_groups(a);
+  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
+  const int H = a.H, HD = H * a.D;
   const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  int64_t ri;
-  int hg;
-  split_item(wi, HG, &ri, &hg);
-  const WorkItem it = decode_item(a, ri, a.nfrag);
-  if (!it.ok) return;
-  const Group g = make_group(a, hg, lane);
-  const int64_t u_row = it.v;
-  const int t0 = it.s0, len = it.len;
-  const int tl = g.hl - g.h_lo;
+  if (wi >= rg_num_work(a, G)) return;
+  const RowItem it = rg_item<G>(a, wi, grp);
+  const int col = it.hg * 128 + lg * 4;
+  const bool col_ok = col < HD;
+  const int h = col_ok ? (col >> a.d_shift) : 0;
+  const bool act = it.v >= 0 && col_ok;
+  const bool leader = act && (col & (a.D - 1)) == 0;
+  const int len = it.v >= 0 ? it.len : 0;
+  const int maxlen = __reduce_max_sync(0xffffffffu, len);
+  const float* gcol = a.G + (col_ok ? col : 0);
+  const float* ah = a.a_csr + h;
+  const float* dh = a.d_csr != nullptr ? a.d_csr + h : nullptr;
+  const int32_t* ip = a.indices + it.begin;
+  const int32_t* sp = a.eid + it.begin;
   float4 acc = zero4();
-  float del_run = 0.f;
-  const float* gcol = a.G + g.col;
-
-  for (int base = 0; base < len; base += 32) {
-    const int cnt = min(32, len - base);
-    const bool valid = lane < cnt;
-    int d = 0, slot = 0;
-    if (valid) {
-      d = a.indices[t0 + base + lane];
-      slot = a.eid[t0 + base + lane];
-    }
-    for (int t = 0; t < g.nh; ++t) {
-      const int h = g.h_lo + t;
-      p_s[lane * HP + t] = valid ? __ldg(a.a_csr + (size_t)slot * H + h) : 0.f;
-      if (a.d_csr != nullptr) {
-        const float tot = group_sum<32>(valid ? __ldg(a.d_csr + (size_t)slot * H + h) : 0.f);
-        if (lane == t) del_run += tot;
+  float del = 0.f;
+  for (int t0 = 0; t0 < maxlen; t0 += G) {
+    int bi = -1, bs = 0;
+    {
+      const int t = t0 + lg;
+      if (t < len) {
+        bi = __ldg(ip + t);
+        bs = __ldg(sp + t);
       }
     }
-    __syncwarp();
-    auto body = [&](int j, auto full_tag) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      float4 x[kUA];
-      float p[kUA];
+    const int cnt = min(G, maxlen - t0);
+    for (int j = 0; j < cnt; j += U) {
+      float4 x[U];
+      float pa[U], pd[U];
 #pragma unroll
-      for (int u = 0; u < kUA; ++u) {
-        const bool ok = FULL || j + u < cnt;
-        const int jj = ok ? j + u : j;
-        const int sd = __shfl_sync(0xffffffffu, d, jj);
-        const bool ld = ok && g.ok;
-        x[u] = ld ? ldg4(gcol + (size_t)sd * HD) : zero4();
-        p[u] = ld ? p_s[jj * HP + tl] : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int sd = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+        const int ss = __shfl_sync(0xffffffffu, bs, gbase + j + u);
+        const bool ok = sd >= 0 && col_ok;
+        x[u] = ok ? ldg4(gcol + (size_t)sd * HD) : zero4();
+        pa[u] = ok ? __ldg(ah + (size_t)ss * H) : 0.f;
+        pd[u] = (ok && dh != nullptr) ? __ldg(dh + (size_t)ss * H) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < kUA; ++u) fma4(acc, p[u], x[u]);
-    };
-    int j = 0;
-    for (; j + kUA <= cnt; j += kUA) body(j, std::true_type{});
-    if (j < cnt) body(j, std::false_type{});
-    __syncwarp();
+      for (int u = 0; u < U; ++u) {
+        fma4(acc, pa[u], x[u]);
+        del += pd[u];
+      }
+    }
   }
-  if (g.ok) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)u_row * HD) + g.col, acc);
-  if (a.d_csr != nullptr && lane < g.nh) {
-    if (it.frag) a.p1[(size_t)it.fi * H + g.h_lo + lane] = del_run;
-    else a.o1[(size_t)u_row * H + g.h_lo + lane] = del_run;
+  if (!act) return;
+  if (it.frag) {
+    st4(a.p0 + (size_t)it.fi * HD + col, acc);
+    if (dh != nullptr && leader) a.p1[(size_t)it.fi * H + h] = del;
+    return;
+  }
+  if (a.attn_l != nullptr) {
+    fma4(acc, del, ldg4(a.attn_l + col));
+    fma4(acc, __ldg(a.d_er_in + (size_t)it.v * H + h), ldg4(a.attn_r + col));
+  }
+  st4(a.o0 + (size_t)it.v * HD + col, acc);
+  if (dh != nullptr && leader) a.o1[(size_t)it.v * H + h] = del;
+}
+
+// The epilogue fold of gat_bwd_src_rg_kernel for the long rows (their sums are only complete after frag_rowsum_kernel)
+__global__ void gat_fold_long_rows_kernel(const int32_t* __restrict__ long_rows, int num_long, int H, int D,
+                                          const float* __restrict__ attn_l, const float* __restrict__ attn_r,
+                                          const float* __restrict__ d_el, const float* __restrict__ d_er,
+                                          float* __restrict__ d_feat, int64_t row_begin, int64_t row_end) {
+  const int l = blockIdx.x;
+  if (l >= num_long) return;
+  const int64_t v = long_rows[l];
+  if (v < row_begin || v >= row_end) return;
+  const int HD = H * D;
+  for (int c = threadIdx.x; c < HD; c += blockDim.x) {
+    const int h = c / D;
+    d_feat[(size_t)v * HD + c] += d_el[(size_t)v * H + h] * attn_l[c] + d_er[(size_t)v * H + h] * attn_r[c];
+  }
+}
+
+// Projection scores of REGAT (layer/REGATConv.py:68-69): el[n,h] = <feat[n,h,:], attn_l[h,:]>, er likewise -- one
+// streaming pass over feat instead of two eager mul + sum pairs.  Same lane-group mapping as above.
+template <int G>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+attn_scores_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ attn_l, const float* __restrict__ attn_r,
+                       int64_t n, int H, int D, int d_shift, int HG, float* __restrict__ el, float* __restrict__ er) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int lg = lane % G, grp = lane / G;
+  const int HD = H * D, lph = min(G, D >> 2);
+  const int64_t items = n * HG;
+  for (int64_t wi = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * GPW; wi < items;
+       wi += (int64_t)gridDim.x * kWarpsPerBlock * GPW) {
+    const int64_t vi = wi + grp;
+    const int64_t v = vi / HG;
+    const int col = (int)(vi % HG) * 128 + lg * 4;
+    const bool act = vi < items && col < HD;
+    float pl = 0.f, pr = 0.f;
+    if (act) {
+      const float4 f = ldg4(feat + (size_t)v * HD + col);
+      pl = dot4(f, ldg4(attn_l + col));
+      pr = dot4(f, ldg4(attn_r + col));
+    }
+    pl = group_sum_rt(pl, lph);
+    pr = group_sum_rt(pr, lph);
+    if (act && (col & (D - 1)) == 0) {
+      el[(size_t)v * H + (col >> d_shift)] = pl;
+      er[(size_t)v * H + (col >> d_shift)] = pr;
+    }
+  }
+}
+
+// d_attn_l[h,d] = sum_n d_el[n,h] * feat[n,h,d], d_attn_r likewise: lane-local float4 accumulators over a persistent
+// grid (warp w keeps slice w % HG for all its rows), per-block double partials [2*H*D], fixed-order finalize.
+// Dynamic smem: [warps][2][128] floats
+template <int G>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+attn_scores_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ d_el, const float* __restrict__ d_er,
+                       int64_t n, int H, int D, int d_shift, int HG, double* __restrict__ partials) {
+  constexpr int GPW = 32 / G;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % G, grp = lane / G;
+  const int HD = H * D;
+  const int64_t nW = (int64_t)gridDim.x * kWarpsPerBlock, usable = nW - nW % HG;
+  const int64_t wg = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const int hg = (int)(wg % HG);
+  const int col = hg * 128 + lg * 4;
+  const bool col_ok = col < HD;
+  const int h = col_ok ? (col >> d_shift) : 0;
+  float4 al = zero4(), ar = zero4();
+  if (wg < usable && col_ok)
+    for (int64_t v = (wg / HG) * GPW + grp; v < n; v += (usable / HG) * GPW) {
+      const float4 f = ldg4(feat + (size_t)v * HD + col);
+      fma4(al, __ldg(d_el + (size_t)v * H + h), f);
+      fma4(ar, __ldg(d_er + (size_t)v * H + h), f);
+    }
+  // fold the lane groups of the warp (same columns), then the warps of the block that own the same slice
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) {
+    al.x += __shfl_xor_sync(0xffffffffu, al.x, o); al.y += __shfl_xor_sync(0xffffffffu, al.y, o);
+    al.z += __shfl_xor_sync(0xffffffffu, al.z, o); al.w += __shfl_xor_sync(0xffffffffu, al.w, o);
+    ar.x += __shfl_xor_sync(0xffffffffu, ar.x, o); ar.y += __shfl_xor_sync(0xffffffffu, ar.y, o);
+    ar.z += __shfl_xor_sync(0xffffffffu, ar.z, o); ar.w += __shfl_xor_sync(0xffffffffu, ar.w, o);
+  }
+  float* mine = smem + (size_t)warp * 256;
+  if (lane < G) {
+    st4(mine + lg * 4, al);
+    st4(mine + 128 + lg * 4, ar);
+  }
+  __syncthreads();
+  double* outp = partials + (size_t)blockIdx.x * 2 * HD;
+  for (int i = threadIdx.x; i < 2 * HD; i += blockDim.x) {
+    const int c = i % HD, which = i / HD;
+    double sum = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w)  // warps of this block that own slice c/128, in warp order
+      if (((int64_t)blockIdx.x * kWarpsPerBlock + w) % HG == c / 128 && (c & 127) < G * 4)
+        sum += (double)smem[(size_t)w * 256 + which * 128 + (c & 127)];
+    outp[i] = sum;
   }
 }
 
@@ -897,6 +1036,33 @@ static int check_shape(const char* who, int H, int D, int R, bool has_rel, bool 
 
 static int head_groups(int H, int D) { return (H * D + 127) / 128; }
 
+// lanes per row slice of the row-group REGAT kernels: min(H*D, 128) floats in 128-bit chunks, rounded up to 4/8/16/32
+static int rg_lanes(int HD) { return HD > 64 ? 32 : (HD > 32 ? 16 : (HD > 16 ? 8 : 4)); }
+#define REGNN_DISPATCH_RG(KERNEL, GRID, SMEM)                                     \
+  do {                                                                            \
+    switch (rg_lanes(a.H * a.D)) {                                                \
+      case 4: REGNN_DISPATCH_C(KERNEL<4>, GRID, SMEM); break;                     \
+      case 8: REGNN_DISPATCH_C(KERNEL<8>, GRID, SMEM); break;                     \
+      case 16: REGNN_DISPATCH_C(KERNEL<16>, GRID, SMEM); break;                   \
+      default: REGNN_DISPATCH_C(KERNEL<32>, GRID, SMEM); break;                   \
+    }                                                                             \
+  } while (0)
+// work items (warps) of a row-group kernel over `rows` rows
+static int64_t rg_work(const AttnArgs& a, int64_t rows) {
+  const int gpw = 32 / rg_lanes(a.H * a.D);
+  const int64_t nrows = a.order != nullptr ? a.n_order : rows;
+  return ((a.nfrag + nrows) * a.hg_count + gpw - 1) / gpw;
+}
+// row_order lists the rows of the FULL range that are not long: only usable when the call covers [0, N)
+static void apply_order(AttnArgs& a, const int32_t* row_order, const regnn_rowsplit_t* split, int64_t rows) {
+  a.order = nullptr;
+  a.n_order = 0;
+  if (row_order != nullptr && a.row_begin == 0) {
+    a.order = row_order;
+    a.n_order = rows - (a.nfrag > 0 ? split->num_long : 0);
+  }
+}
+
 // kernels that reduce over the D/4 lanes of a head are compiled per lane count (fully unrolled butterflies)
 #define REGNN_DISPATCH_LPH(KERNEL, GRID, SMEM)                                          \
   do {                                                                                  \
@@ -921,7 +1087,7 @@ extern "C" int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, cons
                              float negative_slope, const float* keep, int num_heads, int head_dim,
                              int64_t row_begin, int64_t row_end, float* out, float* rowmax,
                              float* rowsum, float* attn_out, const regnn_rowsplit_t* split, float* split_workspace,
-    void* stream_) {
+                             const int32_t* row_order, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && feat && el && er && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gat_fwd: null pointer");
   REGNN_REQUIRE((keep == nullptr && attn_out == nullptr) || eid != nullptr, REGNN_ERR_INVALID_ARG, "gat_fwd: keep/attn_out need eid");
@@ -938,10 +1104,24 @@ extern "C" int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, cons
   a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end;
   a.o0 = out; a.o1 = rowmax; a.o2 = rowsum; a.o3 = attn_out;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_fwd: incomplete row split");
-  const int H = num_heads, HP = H | 1;
-  const size_t smem = sizeof(float) * ((size_t)a.R * H + (size_t)kWarpsPerBlock * (32 * HP + 2 * H));
-  const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  REGNN_DISPATCH_C(gat_fwd_kernel, grid, smem);
+  apply_order(a, row_order, split, rows);
+  const size_t smem = sizeof(float) * ((size_t)a.R * num_heads) + 16;
+  const unsigned grid = (unsigned)((rg_work(a, rows) + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  if (keep != nullptr || attn_out != nullptr) {
+    switch (rg_lanes(a.H * a.D)) {
+      case 4: REGNN_DISPATCH_C((gat_fwd_rg_kernel<4, true>), grid, smem); break;
+      case 8: REGNN_DISPATCH_C((gat_fwd_rg_kernel<8, true>), grid, smem); break;
+      case 16: REGNN_DISPATCH_C((gat_fwd_rg_kernel<16, true>), grid, smem); break;
+      default: REGNN_DISPATCH_C((gat_fwd_rg_kernel<32, true>), grid, smem); break;
+    }
+  } else {
+    switch (rg_lanes(a.H * a.D)) {
+      case 4: REGNN_DISPATCH_C((gat_fwd_rg_kernel<4, false>), grid, smem); break;
+      case 8: REGNN_DISPATCH_C((gat_fwd_rg_kernel<8, false>), grid, smem); break;
+      case 16: REGNN_DISPATCH_C((gat_fwd_rg_kernel<16, false>), grid, smem); break;
+      default: REGNN_DISPATCH_C((gat_fwd_rg_kernel<32, false>), grid, smem); break;
+    }
+  }
   if (a.nfrag > 0) {
     const unsigned fgrid = (unsigned)(((int64_t)split->num_long * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
     REGNN_DISPATCH_FINALIZE(fgrid);
@@ -957,7 +1137,7 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
                                  const float* Gd, int num_heads, int head_dim, int64_t row_begin,
                                  int64_t row_end, float* a_csr, float* dpre_csr, float* d_er,
                                  double* partials, float* d_theta, const regnn_rowsplit_t* split, float* split_workspace,
-    void* stream_) {
+                                 const int32_t* row_order, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && feat && el && er && out && rowmax && rowsum && Gd && d_er,
                 REGNN_ERR_INVALID_ARG, "gat_bwd_dst: null pointer");
@@ -975,10 +1155,17 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
   a.row_begin = row_begin; a.row_end = row_end; a.o0 = a_csr; a.o1 = dpre_csr; a.o2 = d_er;
   a.partials = partials; a.partial_stride = a.R * num_heads;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_dst: incomplete row split");
-  const int RH = a.R * num_heads;
-  const size_t smem = sizeof(float) * ((size_t)RH * (1 + kWarpsPerBlock) + (size_t)kWarpsPerBlock * 4 * 32 * (num_heads | 1)) + 16;
-  const int nb = partial_blocks((rows + a.nfrag) * head_groups(a.H, a.D));
-  REGNN_DISPATCH_LPH(gat_bwd_dst_kernel, nb, smem);
+  apply_order(a, row_order, split, rows);
+  const int RH = a.R * num_heads, gpw = 32 / rg_lanes(num_heads * head_dim);
+  const size_t smem = sizeof(float) * ((size_t)RH * (1 + kWarpsPerBlock * gpw)) + 16;
+  int nb = partial_blocks(rg_work(a, rows));
+  switch (rg_lanes(num_heads * head_dim)) {   // persistent: one resident wave
+    case 4: nb = min(nb, resident_blocks(gat_bwd_dst_rg_kernel<4>, smem)); break;
+    case 8: nb = min(nb, resident_blocks(gat_bwd_dst_rg_kernel<8>, smem)); break;
+    case 16: nb = min(nb, resident_blocks(gat_bwd_dst_rg_kernel<16>, smem)); break;
+    default: nb = min(nb, resident_blocks(gat_bwd_dst_rg_kernel<32>, smem)); break;
+  }
+  REGNN_DISPATCH_RG(gat_bwd_dst_rg_kernel, nb, smem);
   if (a.nfrag > 0) launch_rowsum(split, a.p1, num_heads, d_er, row_begin, row_end, stream);
   if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH, RH, theta, alpha, d_theta, stream);
   return check_launch("regnn_gat_bwd_dst");
@@ -987,11 +1174,14 @@ extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, 
 extern "C" int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices_t,
                                  const int32_t* slot_t, const float* a_csr, const float* dpre_csr,
                                  const float* Gd, int num_heads, int head_dim, int64_t row_begin,
-                                 int64_t row_end, float* d_feat, float* d_el, const regnn_rowsplit_t* split, float* split_workspace,
-    void* stream_) {
+                                 int64_t row_end, float* d_feat, float* d_el, const float* attn_l, const float* attn_r,
+                                 const float* d_er, const regnn_rowsplit_t* split, float* split_workspace,
+                                 const int32_t* row_order_t, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr_t && Gd && d_feat, REGNN_ERR_INVALID_ARG, "gat_bwd_src: null pointer");
+  REGNN_REQUIRE(indptr_t && Gd && d_feat && a_csr, REGNN_ERR_INVALID_ARG, "gat_bwd_src: null pointer");
   REGNN_REQUIRE(dpre_csr == nullptr || d_el != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_src: dpre_csr without d_el");
+  REGNN_REQUIRE(attn_l == nullptr || (attn_r && d_er && dpre_csr && aligned16(attn_l) && aligned16(attn_r)),
+                REGNN_ERR_INVALID_ARG, "gat_bwd_src: the score-gradient fold needs attn_l, attn_r (16-byte aligned), d_er and dpre_csr");
   int rc = check_shape("gat_bwd_src", num_heads, head_dim, 0, false, true);
   if (rc != REGNN_OK) return rc;
   REGNN_REQUIRE(aligned16(Gd) && aligned16(d_feat), REGNN_ERR_INVALID_ARG, "gat_bwd_src: 16-byte alignment required");
@@ -1001,16 +1191,80 @@ extern "C" int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices
   AttnArgs a{};
   a.indptr = indptr_t; a.indices = indices_t; a.eid = slot_t; a.a_csr = a_csr; a.d_csr = dpre_csr; a.G = Gd;
   a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end; a.o0 = d_feat; a.o1 = d_el;
+  a.attn_l = attn_l; a.attn_r = attn_r; a.d_er_in = d_er;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_src: incomplete row split");
-  const int HP = num_heads | 1;
-  const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * 32 * HP;
-  const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  REGNN_DISPATCH_C(gat_bwd_src_kernel, grid, smem);
+  apply_order(a, row_order_t, split, rows);
+  const unsigned grid = (unsigned)((rg_work(a, rows) + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  REGNN_DISPATCH_RG(gat_bwd_src_rg_kernel, grid, 0);
   if (a.nfrag > 0) {
     launch_rowsum(split, a.p0, num_heads * head_dim, d_feat, row_begin, row_end, stream);
     if (dpre_csr != nullptr) launch_rowsum(split, a.p1, num_heads, d_el, row_begin, row_end, stream);
+    if (attn_l != nullptr)
+      gat_fold_long_rows_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->num_long, num_heads, head_dim,
+                                                                     attn_l, attn_r, d_el, d_er, d_feat, row_begin, row_end);
   }
   return check_launch("regnn_gat_bwd_src");
+}
+
+extern "C" int regnn_attn_scores_fwd(const float* feat, const float* attn_l, const float* attn_r, int64_t num_nodes,
+                                     int num_heads, int head_dim, float* el, float* er, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  REGNN_REQUIRE(feat && attn_l && attn_r && el && er && num_nodes >= 0, REGNN_ERR_INVALID_ARG, "attn_scores_fwd: bad argument");
+  int rc = check_shape("attn_scores_fwd", num_heads, head_dim, 0, false, true);
+  if (rc != REGNN_OK) return rc;
+  REGNN_REQUIRE(aligned16(feat) && aligned16(attn_l) && aligned16(attn_r), REGNN_ERR_INVALID_ARG,
+                "attn_scores_fwd: 16-byte alignment required");
+  if (num_nodes == 0) return REGNN_OK;
+  AttnArgs a{};
+  a.H = num_heads; a.D = head_dim;
+  apply_split(a, nullptr, nullptr);
+  const int G = rg_lanes(num_heads * head_dim);
+  const int64_t work = (num_nodes * a.hg_count + 32 / G - 1) / (32 / G);
+  const int64_t want = (work + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+#define REGNN_SCORES_FWD(G_)                                                                                           \
+  attn_scores_fwd_kernel<G_><<<grid, kWarpsPerBlock * 32, 0, stream>>>(feat, attn_l, attn_r, num_nodes, num_heads, head_dim, \
+                                                                      a.d_shift, a.hg_count, el, er)
+  switch (G) {
+    case 4: REGNN_SCORES_FWD(4); break;
+    case 8: REGNN_SCORES_FWD(8); break;
+    case 16: REGNN_SCORES_FWD(16); break;
+    default: REGNN_SCORES_FWD(32); break;
+  }
+#undef REGNN_SCORES_FWD
+  return check_launch("regnn_attn_scores_fwd");
+}
+
+extern "C" int regnn_attn_scores_bwd(const float* feat, const float* d_el, const float* d_er, int64_t num_nodes,
+                                     int num_heads, int head_dim, double* partials, float* d_attn_l, float* d_attn_r,
+                                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  REGNN_REQUIRE(feat && d_el && d_er && partials && d_attn_l && d_attn_r && num_nodes >= 0, REGNN_ERR_INVALID_ARG,
+                "attn_scores_bwd: bad argument");
+  int rc = check_shape("attn_scores_bwd", num_heads, head_dim, 0, false, true);
+  if (rc != REGNN_OK) return rc;
+  REGNN_REQUIRE(aligned16(feat), REGNN_ERR_INVALID_ARG, "attn_scores_bwd: 16-byte alignment required");
+  AttnArgs a{};
+  a.H = num_heads; a.D = head_dim;
+  apply_split(a, nullptr, nullptr);
+  const int G = rg_lanes(num_heads * head_dim), HD = num_heads * head_dim;
+  const int64_t want = (num_nodes * a.hg_count / (32 / G) + kWarpsPerBlock) / kWarpsPerBlock + 1;
+  int nb = (int)(want < 148 * 4 ? want : 148 * 4);
+  if (nb * kWarpsPerBlock < a.hg_count) nb = (a.hg_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const size_t smem = sizeof(float) * kWarpsPerBlock * 256;
+#define REGNN_SCORES_BWD(G_)                                                                                      \
+  attn_scores_bwd_kernel<G_><<<nb, kWarpsPerBlock * 32, smem, stream>>>(feat, d_el, d_er, num_nodes, num_heads, head_dim, \
+                                                                       a.d_shift, a.hg_count, partials)
+  switch (G) {
+    case 4: REGNN_SCORES_BWD(4); break;
+    case 8: REGNN_SCORES_BWD(8); break;
+    case 16: REGNN_SCORES_BWD(16); break;
+    default: REGNN_SCORES_BWD(32); break;
+  }
+#undef REGNN_SCORES_BWD
+  launch_colsum_finalize(partials, nb, 2 * HD, 0, HD, d_attn_l, stream);
+  launch_colsum_finalize(partials, nb, 2 * HD, HD, HD, d_attn_r, stream);
+  return check_launch("regnn_attn_scores_bwd");
 }
 
 extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t* eid,

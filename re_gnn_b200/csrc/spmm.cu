@@ -95,13 +95,19 @@ __global__ void spmm_frag_finalize_kernel(const int32_t* __restrict__ long_rows,
   }
 }
 
-// Scatter variant of the above for the feature-sliced scheme: the row goes to its owner rank's row block, and
-// (xdx != null) <Xrow[v], dX[v]> is taken here because the finished row is no longer in local memory.
+// Scatter variant of the above for the feature-sliced scheme: the row goes to its owner rank's row block (and, when
+// Ylocal != null, also to the local slab), and the row dots of the norm gradient are taken here because the finished
+// row is no longer in local memory:  xdx[v] = <Xrow[v], dX[v]>  or, folded (d_norm != null),
+//   d_norm[v] = ( [sides&2] <Yfwd[v], Gd[v]> + [sides&1] <Xrow[v], dX[v]> ) / norm[v]   (this rank's columns only).
+struct FragPeerExtra {
+  float* Ylocal; int64_t ldl;                 // forward: local copy of the finished rows
+  const float* Xrow; int64_t ldr; float* xdx; // backward: <Xrow, dX>
+  const float* Yfwd; int64_t ldyf; const float* Gd; int64_t ldg; const float* norm; int sides; float* d_norm;
+};
 __global__ void spmm_frag_finalize_peer_kernel(const int32_t* __restrict__ long_rows,
                                                const int32_t* __restrict__ frag_ptr, int num_long,
                                                const float* __restrict__ partial, const float* __restrict__ norm_dst,
-                                               PeerRows peers, int F, const float* __restrict__ Xrow, int64_t ldr,
-                                               float* __restrict__ xdx) {
+                                               PeerRows peers, int F, FragPeerExtra ex) {
   __shared__ float red[4];
   const int l = blockIdx.x;
   if (l >= num_long) return;
@@ -109,19 +115,27 @@ __global__ void spmm_frag_finalize_peer_kernel(const int32_t* __restrict__ long_
   const int f0 = frag_ptr[l], f1 = frag_ptr[l + 1];
   const float nd = norm_dst != nullptr ? norm_dst[v] : 1.f;
   float* yrow = peers.row(v);
+  const bool want_x = ex.xdx != nullptr || (ex.d_norm != nullptr && (ex.sides & 1));
+  const bool want_y = ex.d_norm != nullptr && (ex.sides & 2);
   float p = 0.f;
   for (int c = threadIdx.x; c < F; c += blockDim.x) {
     float s = 0.f;
     for (int f = f0; f < f1; ++f) s += partial[(size_t)f * F + c];
     s *= nd;
     yrow[c] = s;
-    if (xdx != nullptr) p = fmaf(Xrow[(size_t)v * ldr + c], s, p);
+    if (ex.Ylocal != nullptr) ex.Ylocal[(size_t)v * ex.ldl + c] = s;
+    if (want_x) p = fmaf(ex.Xrow[(size_t)v * ex.ldr + c], s, p);
+    if (want_y) p = fmaf(ex.Yfwd[(size_t)v * ex.ldyf + c], ex.Gd[(size_t)v * ex.ldg + c], p);
   }
-  if (xdx != nullptr) {  // fixed-shape block reduction (4 warps)
+  if (want_x || want_y) {  // fixed-shape block reduction (4 warps)
     p = group_sum<32>(p);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
     __syncthreads();
-    if (threadIdx.x == 0) xdx[v] = (red[0] + red[1]) + (red[2] + red[3]);
+    if (threadIdx.x == 0) {
+      const float t = (red[0] + red[1]) + (red[2] + red[3]);
+      if (ex.d_norm != nullptr) ex.d_norm[v] = t / ex.norm[v];
+      else ex.xdx[v] = t;
+    }
   }
 }
 
@@ -208,6 +222,8 @@ struct StreamArgs {
   const int32_t* order;  // rows not covered by fragments, by descending slot count
   int64_t n_order;
   PeerRows peers;        // base != null: result rows go to the row blocks of their owner ranks (peer memory)
+  float* Ylocal;         // forward scatter: optional local copy of the result slab (leading dim ldl)
+  int64_t ldl;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -492,9 +508,10 @@ spmm_stream_kernel(StreamArgs sa) {
 #ifndef REGNN_RG_COOP
 #define REGNN_RG_COOP BINS
 #endif
-template <bool BINS, int G>
+template <bool BINS, int G, bool DNORM = false>   // DNORM (BINS only): the norm gradient is produced in the same pass
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, BINS ? REGNN_RGB_BLOCKS : REGNN_RG_BLOCKS)
 spmm_rowgroup_kernel(StreamArgs sa) {
+  static_assert(BINS || !DNORM, "the folded norm gradient belongs to the backward kernel");
   static_assert(G == 4 || G == 8 || G == 16 || G == 32, "lane groups of 4, 8, 16 or 32 lanes");
   constexpr int GPW = 32 / G;                          // rows per warp
   constexpr int U = BINS ? REGNN_RGB_U : REGNN_RG_U;   // gathers in flight per lane
@@ -547,10 +564,12 @@ spmm_rowgroup_kernel(StreamArgs sa) {
     // here, ahead of the gathers, and consumed after them (G[u] is also one of the gathered rows when u has a self
     // loop, so it is usually an L1/L2 hit).  Fragments: long_row_dnorm_kernel.
     float4 yrow = make_float4(0.f, 0.f, 0.f, 0.f), grow = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool want_ydg = BINS && sa.d_norm != nullptr && (sa.dn_sides & 2);
-    if (BINS && want_ydg && v >= 0 && col_ok && !is_frag) {
-      yrow = ldg4(sa.Yfwd + (size_t)v * sa.ldyf + lg * 4);
-      grow = ldg4(reinterpret_cast<const float*>(xbytes + (uint64_t)(uint32_t)v * ldxb));
+    const bool want_ydg = DNORM && (sa.dn_sides & 2);
+    if constexpr (DNORM) {
+      if (want_ydg && v >= 0 && col_ok && !is_frag) {
+        yrow = ldg4(sa.Yfwd + (size_t)v * sa.ldyf + lg * 4);
+        grow = ldg4(reinterpret_cast<const float*>(xbytes + (uint64_t)(uint32_t)v * ldxb));
+      }
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur_rel = 0;
@@ -657,7 +676,7 @@ spmm_rowgroup_kernel(StreamArgs sa) {
     }
     if (BINS) {
       mybins[cur_rel * 32] += racc;
-      if (sa.d_norm != nullptr) {  // the whole norm gradient of row u in this pass: no separate row-dot kernel
+      if constexpr (DNORM) {  // the whole norm gradient of row u in this pass: no separate row-dot kernel
         float p = (sa.dn_sides & 1) ? dot4(acc, trow) * nd : 0.f;   // <X[u], dX[u]> while dX[u] is in registers
         if (want_ydg) p += dot4(yrow, grow);
         p = group_sum<G>(p);
@@ -674,6 +693,7 @@ spmm_rowgroup_kernel(StreamArgs sa) {
         scale4(acc, nd);
         float* yrow = sa.peers.base != nullptr ? sa.peers.row(v) : a.Y + (size_t)v * a.ldy;
         st4(yrow + lg * 4, acc);  // 64..256 contiguous bytes per row: a full NVLink write packet when remote
+        if (!BINS && sa.peers.base != nullptr && sa.Ylocal != nullptr) st4(sa.Ylocal + (size_t)v * sa.ldl + lg * 4, acc);
       }
     }
   }
@@ -1303,15 +1323,6 @@ static int rowgroup_lanes(int F, const int32_t* order, int64_t row_begin, int al
   REGNN_ROWGROUP_CASE(32, BINS_, CALL) REGNN_ROWGROUP_CASE(16, BINS_, CALL) REGNN_ROWGROUP_CASE(8, BINS_, CALL) \
   REGNN_ROWGROUP_CASE(4, BINS_, CALL)
 
-template <typename K>
-static int resident_blocks(K kernel, size_t smem) {
-  int dev = 0, sms = 148, per_sm = 1;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, smem) != cudaSuccess || per_sm < 1)
-    per_sm = 1;
-  return min(sms * per_sm, kMaxPartialBlocks);
-}
 
 static int fill_split(SpmmArgs& a, const regnn_rowsplit_t* split, float* ws, const char* who) {
   a.frag_row = a.frag_begin = nullptr;
@@ -1348,9 +1359,11 @@ static int spmm_fwd_impl(const int32_t* indptr, const int32_t* indices, const ui
                          int64_t ldx, float* Y, int64_t ldy, int64_t row_begin,
                          int64_t row_end, int feat, const regnn_rowsplit_t* split,
                          float* split_workspace, const int32_t* row_order, const regnn_peer_rows_t* peers,
-                         void* stream_) {
+                         float* y_local, int64_t ldl, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (peers != nullptr) { Y = const_cast<float*>(X); ldy = feat; }  // Y is unused: keep the checks below simple
+  REGNN_REQUIRE(y_local == nullptr || (peers != nullptr && ldl >= feat && ldl % 4 == 0 && aligned_to(y_local, 16)),
+                REGNN_ERR_INVALID_ARG, "spmm_fwd: bad local result slab");
   REGNN_REQUIRE(indptr && X && Y,  /* per-edge arrays may be NULL when E == 0 */ REGNN_ERR_INVALID_ARG, "spmm_fwd: null pointer");
   REGNN_REQUIRE(etype == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd: etype without theta");
   REGNN_REQUIRE(etype == nullptr || (num_relations >= 1 && num_relations <= REGNN_MAX_RELATIONS),
@@ -1371,6 +1384,8 @@ static int spmm_fwd_impl(const int32_t* indptr, const int32_t* indices, const ui
   const int G = rowgroup_lanes(feat, row_order, row_begin, common_align({X, Y, split_workspace}, {ldx, ldy, (int64_t)feat}));
   rc = fill_peers(&sa.peers, peers, feat, rows, "spmm_fwd");
   if (rc != REGNN_OK) return rc;
+  sa.Ylocal = y_local;
+  sa.ldl = ldl;
   REGNN_REQUIRE(peers == nullptr || G != 0, REGNN_ERR_UNSUPPORTED_SHAPE,
                 "spmm_fwd: the peer scatter needs the lane-group kernel (row_order, full range, F <= 128, F %% 4 == 0)");
   if (G != 0) {  // narrow rows over the degree-sorted row order
@@ -1387,9 +1402,9 @@ static int spmm_fwd_impl(const int32_t* indptr, const int32_t* indices, const ui
   }
   REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_fwd: no kernel for C=%d VW=%d", sh.C, sh.VW);
   if (sa.s.nfrag > 0 && peers != nullptr)
-    spmm_frag_finalize_peer_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->frag_ptr, split->num_long,
-                                                                        split_workspace, norm_dst, sa.peers, feat, nullptr, 0,
-                                                                        nullptr);
+    spmm_frag_finalize_peer_kernel<<<split->num_long, 128, 0, stream>>>(
+        split->long_rows, split->frag_ptr, split->num_long, split_workspace, norm_dst, sa.peers, feat,
+        FragPeerExtra{y_local, ldl, nullptr, 0, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, nullptr});
   else if (sa.s.nfrag > 0)
     spmm_frag_finalize_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->frag_ptr, split->num_long,
                                                                    split_workspace, norm_dst, Y, ldy, feat, row_begin, row_end);
@@ -1403,7 +1418,7 @@ extern "C" int regnn_spmm_fwd(const int32_t* indptr, const int32_t* indices, con
                               int64_t row_end, int feat, const regnn_rowsplit_t* split,
                               float* split_workspace, const int32_t* row_order, void* stream) {
   return spmm_fwd_impl(indptr, indices, etype, theta, alpha, num_relations, norm_src, norm_dst, X, ldx, Y, ldy,
-                       row_begin, row_end, feat, split, split_workspace, row_order, nullptr, stream);
+                       row_begin, row_end, feat, split, split_workspace, row_order, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int regnn_spmm_fwd_scatter(const int32_t* indptr, const int32_t* indices, const uint8_t* etype,
@@ -1411,10 +1426,10 @@ extern "C" int regnn_spmm_fwd_scatter(const int32_t* indptr, const int32_t* indi
                                       const float* norm_src, const float* norm_dst, const float* X,
                                       int64_t ldx, int64_t num_rows, int feat, const regnn_rowsplit_t* split,
                                       float* split_workspace, const int32_t* row_order,
-                                      const regnn_peer_rows_t* peers, void* stream) {
+                                      const regnn_peer_rows_t* peers, float* y_local, int64_t ldl, void* stream) {
   REGNN_REQUIRE(peers != nullptr, REGNN_ERR_INVALID_ARG, "spmm_fwd_scatter: null peer table");
   return spmm_fwd_impl(indptr, indices, etype, theta, alpha, num_relations, norm_src, norm_dst, X, ldx, nullptr, 0,
-                       0, num_rows, feat, split, split_workspace, row_order, peers, stream);
+                       0, num_rows, feat, split, split_workspace, row_order, peers, y_local, ldl, stream);
 }
 
 extern "C" int regnn_rows_to_slabs(const float* X, int64_t ldx, int64_t num_rows, int feat, int num_ranks,
@@ -1471,8 +1486,8 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
   sa.xdx = xdx;
   const int Fp = (feat + 3) & ~3;
   if (d_norm != nullptr) {  // folded norm gradient: lane-group kernel only (the caller falls back to regnn_rowdot_norm_bwd)
-    REGNN_REQUIRE(norm != nullptr && peers == nullptr && (!(sides & 2) || (Yfwd != nullptr && ldyf >= feat)),
-                  REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: d_norm needs norm, Y (destination side) and local dX rows");
+    REGNN_REQUIRE(norm != nullptr && (!(sides & 2) || (Yfwd != nullptr && ldyf >= feat)),
+                  REGNN_ERR_INVALID_ARG, "spmm_bwd_fused: d_norm needs norm and (destination side scaled) Y");
     REGNN_REQUIRE(!(sides & 2) || (aligned_to(Yfwd, 16) && ldyf % 4 == 0), REGNN_ERR_INVALID_ARG,
                   "spmm_bwd_fused: Y rows must be 16-byte aligned");
     sa.Yfwd = Yfwd; sa.ldyf = ldyf; sa.norm = norm; sa.dn_sides = sides; sa.d_norm = d_norm;
@@ -1496,9 +1511,15 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
     sa.order = row_order_t;
     sa.n_order = rows - (sa.s.nfrag > 0 ? split_t->num_long : 0);
     const size_t gsmem = (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float));
-    REGNN_ROWGROUP_DISPATCH(true, (rc = set_smem(spmm_rowgroup_kernel<BINS, GL>, gsmem),
-                                   nb = min(nb, resident_blocks(spmm_rowgroup_kernel<BINS, GL>, gsmem)),
-                                   spmm_rowgroup_kernel<BINS, GL><<<nb, kWarpsPerBlock * 32, gsmem, stream>>>(sa)))
+    if (d_norm != nullptr) {
+      REGNN_ROWGROUP_DISPATCH(true, (rc = set_smem(spmm_rowgroup_kernel<BINS, GL, true>, gsmem),
+                                     nb = min(nb, resident_blocks(spmm_rowgroup_kernel<BINS, GL, true>, gsmem)),
+                                     spmm_rowgroup_kernel<BINS, GL, true><<<nb, kWarpsPerBlock * 32, gsmem, stream>>>(sa)))
+    } else {
+      REGNN_ROWGROUP_DISPATCH(true, (rc = set_smem(spmm_rowgroup_kernel<BINS, GL>, gsmem),
+                                     nb = min(nb, resident_blocks(spmm_rowgroup_kernel<BINS, GL>, gsmem)),
+                                     spmm_rowgroup_kernel<BINS, GL><<<nb, kWarpsPerBlock * 32, gsmem, stream>>>(sa)))
+    }
   } else {
     REGNN_STREAM_DISPATCH(true, (rc = set_smem(spmm_stream_kernel<C, VW, BINS>, smem),
                                  nb = min(nb, resident_blocks(spmm_stream_kernel<C, VW, BINS>, smem)),
@@ -1507,9 +1528,9 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
   if (rc != REGNN_OK) return rc;
   REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "spmm_bwd_fused: no kernel for C=%d VW=%d", sh.C, sh.VW);
   if (sa.s.nfrag > 0 && peers != nullptr)
-    spmm_frag_finalize_peer_kernel<<<split_t->num_long, 128, 0, stream>>>(split_t->long_rows, split_t->frag_ptr,
-                                                                          split_t->num_long, split_workspace, sa.s.norm_dst,
-                                                                          sa.peers, feat, X, ldx, xdx);
+    spmm_frag_finalize_peer_kernel<<<split_t->num_long, 128, 0, stream>>>(
+        split_t->long_rows, split_t->frag_ptr, split_t->num_long, split_workspace, sa.s.norm_dst, sa.peers, feat,
+        FragPeerExtra{nullptr, 0, X, ldx, xdx, Yfwd, ldyf, Gd, ldg, norm, sides, d_norm});
   else if (sa.s.nfrag > 0)
     spmm_frag_finalize_kernel<<<split_t->num_long, 128, 0, stream>>>(split_t->long_rows, split_t->frag_ptr,
                                                                      split_t->num_long, split_workspace, sa.s.norm_dst, dX,
@@ -1539,12 +1560,12 @@ extern "C" int regnn_spmm_bwd_fused_scatter(const int32_t* indptr_t, const int32
                                             const uint8_t* etype_t, const float* theta, float alpha,
                                             int num_relations, const float* norm, int norm_sides, const float* X,
                                             int64_t ldx, const float* Gd, int64_t ldg, int64_t num_rows, int feat,
-                                            double* partials, float* d_theta, float* xdx,
-                                            const regnn_rowsplit_t* split_t, float* split_workspace,
+                                            double* partials, float* d_theta, float* xdx, const float* Y, int64_t ldy,
+                                            float* d_norm, const regnn_rowsplit_t* split_t, float* split_workspace,
                                             const int32_t* row_order_t, const regnn_peer_rows_t* peers, void* stream) {
   REGNN_REQUIRE(peers != nullptr, REGNN_ERR_INVALID_ARG, "spmm_bwd_fused_scatter: null peer table");
   return spmm_bwd_fused_impl(indptr_t, indices_t, etype_t, theta, alpha, num_relations, norm, norm_sides, X, ldx, Gd, ldg,
-                             nullptr, 0, 0, num_rows, feat, partials, d_theta, xdx, nullptr, 0, nullptr, split_t,
+                             nullptr, 0, 0, num_rows, feat, partials, d_theta, xdx, Y, ldy, d_norm, split_t,
                              split_workspace, row_order_t, peers, stream);
 }
 

@@ -124,6 +124,44 @@ def gat_aggregate(graph, etv, feat, el, er, theta, alpha, slope, keep=None, want
     return _GatAggregate.apply(graph, etv, feat, el, er, theta, alpha, slope, keep, want_attn)
 
 
+class _GatLayer(torch.autograd.Function):
+    """The whole REGAT core of layer/REGATConv.py:68-92 as ONE autograd node: projection scores el / er (one streaming
+    kernel instead of two eager mul + sum pairs), fused logits + edge softmax + aggregation, and a backward whose
+    source-major pass adds the gradient through el / er in its epilogue (no [N,H,D] temporaries from autograd)."""
+
+    @staticmethod
+    def forward(ctx, graph, etv, feat, attn_l, attn_r, theta, alpha, slope, keep, want_attn):
+        csr = graph.csr()
+        et = etv[0] if etv is not None else None
+        feat = feat.contiguous()
+        el, er = ops.attn_scores_fwd(feat, attn_l, attn_r)
+        out, rowmax, rowsum, attn = ops.gat_fwd(csr, et, theta if et is not None else None, alpha, feat, el, er,
+                                                slope, keep, want_attn)
+        ctx.graph, ctx.et, ctx.alpha, ctx.slope = graph, et, alpha, slope
+        ctx.save_for_backward(feat, el, er, attn_l, attn_r, theta if et is not None else None, keep, out, rowmax, rowsum)
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+            return out, attn
+        return out, None
+
+    @staticmethod
+    def backward(ctx, g, _g_attn=None):
+        feat, el, er, attn_l, attn_r, theta, keep, out, rowmax, rowsum = ctx.saved_tensors
+        csr = ctx.graph.csr()
+        g = g.contiguous()
+        a_csr, dpre_csr, d_er, d_theta = ops.gat_bwd_dst(csr, ctx.et, theta, ctx.alpha, feat, el, er, ctx.slope,
+                                                         keep, out, rowmax, rowsum, g)
+        d_feat, d_el = ops.gat_bwd_src(csr, a_csr, dpre_csr, g, attn_l=attn_l, attn_r=attn_r, d_er=d_er)
+        d_al, d_ar = ops.attn_scores_bwd(feat, d_el, d_er)
+        return (None, None, d_feat, d_al.view_as(attn_l), d_ar.view_as(attn_r),
+                d_theta.view_as(theta) if d_theta is not None else None, None, None, None, None)
+
+
+def gat_layer(graph, etv, feat, attn_l, attn_r, theta, alpha, slope, keep=None, want_attn=False):
+    """feat [N,H,D] (source and destination side are the same nodes) -> (out [N,H,D], attention | None)."""
+    return _GatLayer.apply(graph, etv, feat, attn_l, attn_r, theta, alpha, slope, keep, want_attn)
+
+
 class _GatV2Aggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn):

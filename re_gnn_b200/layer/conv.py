@@ -167,13 +167,12 @@ class REGATConv(_RelationEmbedded):
     def forward(self, graph, feat, edge_feats=None):
         h = self.feat_drop(feat)
         f = self.fc(h).view(-1, self.num_heads, self.out_feats)
-        el = (f * self.attn_l).sum(dim=-1)
-        er = (f * self.attn_r).sum(dim=-1)
         etv = self._views(graph, edge_feats) if edge_feats is not None else None
         keep = _keep_mask(self.attn_drop, graph.number_of_edges(), self.num_heads, f)
         dk = _kernel_head_dim(self.out_feats)
-        rst, _ = RF.gat_aggregate(graph, etv, _pad_last(f, dk), el, er, self.edge_weight, self.alpha,
-                                  self.negative_slope, keep)
+        # el / er (:68-69), logits, edge softmax and aggregation (:71-92) are one autograd node on fused kernels
+        rst, _ = RF.gat_layer(graph, etv, _pad_last(f, dk), _pad_last(self.attn_l, dk), _pad_last(self.attn_r, dk),
+                              self.edge_weight, self.alpha, self.negative_slope, keep)
         rst = rst[..., :self.out_feats]
         if self.res_fc is not None:
             rst = rst + self.res_fc(h).view(h.shape[0], -1, self.out_feats)

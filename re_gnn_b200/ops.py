@@ -209,9 +209,9 @@ def rows_to_slabs(x_own, num_ranks, row_offset, peer_slab_ptrs):
         _lib.count_launches(1)
 
 
-def spmm_scatter(csr, etype, theta, alpha, norm_src, norm_dst, x_cols, peers):
+def spmm_scatter(csr, etype, theta, alpha, norm_src, norm_dst, x_cols, peers, y_local=None):
     """regnn_spmm_fwd_scatter: forward SpMM of a column slab, result rows stored to their owner ranks (``peers``: a
-    ``_lib.PeerRows``)."""
+    ``_lib.PeerRows``) and, with ``y_local`` ([rows >= N, F/P] fp32), also kept as a local slab."""
     x_cols = _f32(x_cols)
     n = csr['indptr'].numel() - 1
     f = x_cols.shape[1]
@@ -221,26 +221,30 @@ def spmm_scatter(csr, etype, theta, alpha, norm_src, norm_dst, x_cols, peers):
         _lib.call('regnn_spmm_fwd_scatter', _ptr(csr['indptr']), _ptr(csr['indices']),
                   _ptr(etype) if theta is not None else None, _ptr(theta), float(alpha),
                   theta.numel() if theta is not None else 0, _ptr(norm_src), _ptr(norm_dst), _ptr(x_cols),
-                  x_cols.stride(0), n, f, sp, _ptr(ws), _ptr(row_order(csr)), ctypes.byref(peers), _stream())
+                  x_cols.stride(0), n, f, sp, _ptr(ws), _ptr(row_order(csr)), ctypes.byref(peers), _ptr(y_local),
+                  y_local.stride(0) if y_local is not None else 0, _stream())
         _lib.count_launches(1 + extra)
 
 
-def spmm_bwd_fused_scatter(csr, et_t, theta, alpha, norm, x_cols, g_cols, peers, sides=3):
-    """regnn_spmm_bwd_fused_scatter -> d_theta[R] (this rank's columns); the dX rows go to their owner ranks."""
+def spmm_bwd_fused_scatter(csr, et_t, theta, alpha, norm, x_cols, g_cols, peers, sides=3, y_cols=None):
+    """regnn_spmm_bwd_fused_scatter -> (d_theta[R], d_norm[N] | None), both for this rank's columns only; the dX rows go
+    to their owner ranks.  ``y_cols`` (the local result slab of ``spmm_scatter``) switches the folded norm gradient on."""
     x_cols, g_cols = _f32(x_cols), _f32(g_cols)
     theta = _f32(theta).view(-1)
     n = csr['indptr_t'].numel() - 1
     f, r = x_cols.shape[1], theta.numel()
     partials = torch.empty(_lib.partial_blocks(n) * r, dtype=torch.float64, device=x_cols.device)
     d_theta = torch.empty(r, dtype=torch.float32, device=x_cols.device)
+    d_norm = torch.empty(n, dtype=torch.float32, device=x_cols.device) if (y_cols is not None and norm is not None) else None
     sp, ws, extra = _split_args(csr.get('split_t'), f, x_cols.device)
     with torch.cuda.device(x_cols.device):
         _lib.call('regnn_spmm_bwd_fused_scatter', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(et_t), _ptr(theta),
                   float(alpha), r, _ptr(norm), int(sides), _ptr(x_cols), x_cols.stride(0), _ptr(g_cols),
-                  g_cols.stride(0), n, f, _ptr(partials), _ptr(d_theta), None, sp, _ptr(ws),
-                  _ptr(row_order(csr, True)), ctypes.byref(peers), _stream())
+                  g_cols.stride(0), n, f, _ptr(partials), _ptr(d_theta), None,
+                  _ptr(y_cols) if d_norm is not None else None, y_cols.stride(0) if d_norm is not None else 0,
+                  _ptr(d_norm), sp, _ptr(ws), _ptr(row_order(csr, True)), ctypes.byref(peers), _stream())
         _lib.count_launches(2 + extra)
-    return d_theta
+    return d_theta, d_norm
 
 
 def _attn_split(split, h, d, device):
@@ -258,22 +262,27 @@ def _rel(theta, et_csr):
     return theta, et_csr, theta.shape[0]
 
 
+def _full(rb, re, n):
+    return (rb, re) == (0, n)
+
+
 def gat_fwd(csr, et_csr, theta, alpha, feat, el, er, slope, keep=None, want_attn=False, rows=None):
     feat, el, er, keep = _f32(feat), _f32(el), _f32(er), _f32(keep)
     n, h, d = feat.shape
     rb, re = _rows(rows, n)
     theta, et_csr, r = _rel(theta, et_csr)
     dev = feat.device
-    out = torch.empty_like(feat) if (rb, re) == (0, n) else torch.zeros_like(feat)
+    out = torch.empty_like(feat) if _full(rb, re, n) else torch.zeros_like(feat)
     rowmax = torch.zeros((n, h), dtype=torch.float32, device=dev)
     rowsum = torch.zeros((n, h), dtype=torch.float32, device=dev)
     e = csr['indices'].numel()
     attn = torch.zeros((max(e, 1), h), dtype=torch.float32, device=dev)[:e] if want_attn else None
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
+    order = row_order(csr) if _full(rb, re, n) else None
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep), h, d,
-                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(attn), sp, _ptr(ws), _stream())
+                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(attn), sp, _ptr(ws), _ptr(order), _stream())
         _lib.count_launches(1 + (sp is not None))
     return out, rowmax, rowsum, attn
 
@@ -291,28 +300,65 @@ def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowma
     partials = torch.empty(max(_lib.partial_blocks(re - rb) * r * h, 1), dtype=torch.float64, device=dev)
     d_theta = torch.zeros((r, h), dtype=torch.float32, device=dev) if r else None   # stays 0 when the graph has no edges
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
+    order = row_order(csr) if _full(rb, re, n) else None
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep),
                   _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dpre_csr),
-                  _ptr(d_er), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _stream())
+                  _ptr(d_er), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _ptr(order), _stream())
         _lib.count_launches((2 if r else 1) + (sp is not None))
     return a_csr, dpre_csr, d_er, d_theta
 
 
-def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None):
+def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None, attn_l=None, attn_r=None, d_er=None):
+    """-> (d_feat, d_el).  With ``attn_l`` / ``attn_r`` ([H*D] fp32) and ``d_er`` the gradient through the projection
+    scores is folded into the epilogue: d_feat += d_el (x) attn_l + d_er (x) attn_r."""
     g = _f32(g)
     n, h, d = g.shape
     rb, re = _rows(rows, n)
     dev = g.device
-    d_feat = torch.empty_like(g) if (rb, re) == (0, n) else torch.zeros_like(g)
+    d_feat = torch.empty_like(g) if _full(rb, re, n) else torch.zeros_like(g)
     d_el = torch.zeros((n, h), dtype=torch.float32, device=dev) if dpre_csr is not None else None
     sp, ws = _attn_split(csr.get('split_t'), h, d, dev)
+    order = row_order(csr, True) if _full(rb, re, n) else None
+    fold = attn_l is not None
+    if fold:
+        attn_l, attn_r, d_er = _f32(attn_l).view(-1), _f32(attn_r).view(-1), _f32(d_er)
     with torch.cuda.device(dev):
         _lib.call('regnn_gat_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
-                  _ptr(a_csr), _ptr(dpre_csr), _ptr(g), h, d, rb, re, _ptr(d_feat), _ptr(d_el), sp, _ptr(ws), _stream())
-        _lib.count_launches(1 + (2 if sp is not None else 0))
+                  _ptr(a_csr), _ptr(dpre_csr), _ptr(g), h, d, rb, re, _ptr(d_feat), _ptr(d_el),
+                  _ptr(attn_l) if fold else None, _ptr(attn_r) if fold else None, _ptr(d_er) if fold else None,
+                  sp, _ptr(ws), _ptr(order), _stream())
+        _lib.count_launches(1 + ((2 + fold) if sp is not None else 0))
     return d_feat, d_el
+
+
+def attn_scores_fwd(feat, attn_l, attn_r):
+    """el[n,h] = <feat[n,h,:], attn_l[h,:]>, er likewise (regnn_attn_scores_fwd)."""
+    feat = _f32(feat)
+    n, h, d = feat.shape
+    attn_l, attn_r = _f32(attn_l).view(-1), _f32(attn_r).view(-1)
+    el = torch.empty((n, h), dtype=torch.float32, device=feat.device)
+    er = torch.empty((n, h), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.call('regnn_attn_scores_fwd', _ptr(feat), _ptr(attn_l), _ptr(attn_r), n, h, d, _ptr(el), _ptr(er), _stream())
+        _lib.count_launches(1)
+    return el, er
+
+
+def attn_scores_bwd(feat, d_el, d_er):
+    """-> (d_attn_l[H*D], d_attn_r[H*D]) (regnn_attn_scores_bwd)."""
+    feat, d_el, d_er = _f32(feat), _f32(d_el), _f32(d_er)
+    n, h, d = feat.shape
+    dev = feat.device
+    partials = torch.empty(_lib.partial_blocks(n) * 2 * h * d, dtype=torch.float64, device=dev)
+    d_al = torch.empty(h * d, dtype=torch.float32, device=dev)
+    d_ar = torch.empty(h * d, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call('regnn_attn_scores_bwd', _ptr(feat), _ptr(d_el), _ptr(d_er), n, h, d, _ptr(partials), _ptr(d_al),
+                  _ptr(d_ar), _stream())
+        _lib.count_launches(3)
+    return d_al, d_ar
 
 
 def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_attn=False, rows=None):

@@ -150,7 +150,7 @@ class _ColumnSlabPropagate(torch.autograd.Function):
     feature-sliced: every rank propagates ALL rows for F/P of the columns, so the SpMM and its backward need
     no remote rows at all.  The row<->column re-partition is an all-to-all that moves (P-1)/P of ONE row block
     per rank (N*F/P floats) instead of the all-gather's (P-1) row blocks -- P times less NVLink traffic; the
-    only extra exchange is the all-reduce of the N-float norm gradient (its row dot products span all columns)."""
+    norm gradient's row dot products span all columns, but the row owner holds complete rows: a local pass."""
 
     @staticmethod
     def forward(ctx, graph, etv, x_own, theta, alpha, norm, bounds, rank, group):
@@ -191,9 +191,13 @@ class _ColumnSlabPropagate(torch.autograd.Function):
 
 class SlabExchange:
     """Peer-mapped (torch symmetric memory over NVLink) buffers of ONE feature-sliced aggregation call site: the
-    two column slabs (X and dL/dY, [P*per, F/P]) that peers push their row blocks into, and the two row blocks
-    (Y and dX, [per, F]) that the SpMM kernels of all ranks store finished rows into.  Create it once per layer;
-    a forward must be followed by its backward before the next forward (the buffers are reused every step)."""
+    two column slabs (X and dL/dY, [P*per, F/P]) that peers push their row blocks into, the two row blocks
+    (Y and dX, [per, F]) that the SpMM kernels of all ranks store finished rows into, and a [P, 256]-float table
+    every rank writes its share of the relation gradient into (``allreduce_relation_grads``).  ``y_cols`` is a plain
+    local slab: this rank's columns of Y, kept for the folded norm gradient of the backward kernel.  Create it once
+    per layer; a forward must be followed by its backward before the next forward (the buffers are reused)."""
+
+    GRAD_SLOTS = 256
 
     def __init__(self, feat, bounds, rank, device, group=None):
         import torch.distributed._symmetric_memory as symm
@@ -214,8 +218,11 @@ class SlabExchange:
         self.g_cols, self.g_ptrs = alloc(self.parts * self.per, self.fc)
         self.y_rows, self.y_ptrs = alloc(self.per, feat)
         self.dx_rows, self.dx_ptrs = alloc(self.per, feat)
+        self.grad_tab, self.grad_ptrs = alloc(self.parts, self.GRAD_SLOTS)
+        self.y_cols = torch.zeros((self.parts * self.per, self.fc), dtype=torch.float32, device=device)
         self.x_cols.zero_()
         self.g_cols.zero_()
+        self.grad_tab.zero_()
         self.peer_y = _lib.PeerRows(self.y_ptrs.data_ptr(), self.parts, self.per, feat, rank * self.fc)
         self.peer_dx = _lib.PeerRows(self.dx_ptrs.data_ptr(), self.parts, self.per, feat, rank * self.fc)
         self.barrier()
@@ -223,15 +230,32 @@ class SlabExchange:
     def barrier(self):
         """Device-side barrier across the ranks on the current stream: everything the ranks wrote into each
         other's buffers before it is visible after it."""
-        self._handles[0].barrier()
+        with _lib.phase('peer_barrier'):
+            self._handles[0].barrier()
+
+    def allreduce_small(self, flat):
+        """Deterministic sum of a small fp32 vector (<= GRAD_SLOTS) over the ranks: every rank pushes its share into
+        row ``rank`` of every peer's table (regnn_rows_to_slabs with a one-row block), a barrier, then each rank
+        reduces the P rows with one fixed-shape reduction -- the same order, hence the same bits, on every rank and
+        for every topology (no ring / tree of a collective library decides the association)."""
+        n = flat.numel()
+        if n > self.GRAD_SLOTS:
+            raise ValueError('at most %d floats' % self.GRAD_SLOTS)
+        if not hasattr(self, '_grad_row'):
+            self._grad_row = torch.zeros((1, self.GRAD_SLOTS * self.parts), dtype=torch.float32, device=flat.device)
+        self._grad_row.view(self.parts, self.GRAD_SLOTS)[:, :n] = flat.view(1, -1)     # the same share goes to every peer
+        ops.rows_to_slabs(self._grad_row, self.parts, self.rank, self.grad_ptrs)
+        self.barrier()
+        return self.grad_tab[:, :n].sum(dim=0)
 
 
 class _PeerSlabPropagate(torch.autograd.Function):
     """``_ColumnSlabPropagate`` with both re-partitions done by our own kernels over peer memory: row blocks are
     pushed into the peers' column slabs (regnn_rows_to_slabs), and the SpMM kernels store every finished row
     straight into its owner's row block from their epilogue (regnn_spmm_*_scatter) -- no collective library
-    call, no pack / unpack pass.  ``alias=True`` returns views of the exchange buffers (valid until the next
-    step) instead of copies."""
+    call, no pack / unpack pass.  The norm gradient is folded into the backward kernel per column slab (its
+    backward is linear, so the shares add up at the R-float level): no row-dot pass and no N-float exchange.
+    ``alias=True`` returns views of the exchange buffers (valid until the next step) instead of copies."""
 
     @staticmethod
     def forward(ctx, graph, etv, x_own, theta, alpha, norm, bounds, rank, xch, alias):
@@ -240,13 +264,13 @@ class _PeerSlabPropagate(torch.autograd.Function):
         x_own = x_own.contiguous()
         ops.rows_to_slabs(x_own, xch.parts, rank * xch.per, xch.x_ptrs)
         xch.barrier()            # every rank's slice of X has landed in my slab
-        ops.spmm_scatter(csr, etv[0], theta, alpha, norm, norm, xch.x_cols, xch.peer_y)
+        ops.spmm_scatter(csr, etv[0], theta, alpha, norm, norm, xch.x_cols, xch.peer_y,
+                         y_local=xch.y_cols if norm is not None else None)
         xch.barrier()            # every rank's columns of my rows have landed in my row block
         y_own = xch.y_rows[:re - rb]
         if not alias:
             y_own = y_own.clone()
         ctx.graph, ctx.etv, ctx.alpha, ctx.bounds, ctx.rank, ctx.xch, ctx.alias = graph, etv, alpha, bounds, rank, xch, alias
-        ctx.x_own, ctx.y_own = x_own.detach(), y_own
         ctx.save_for_backward(theta, norm)
         return y_own
 
@@ -258,12 +282,13 @@ class _PeerSlabPropagate(torch.autograd.Function):
         g_own = g_own.contiguous()
         ops.rows_to_slabs(g_own, xch.parts, rank * xch.per, xch.g_ptrs)
         xch.barrier()
-        d_theta = ops.spmm_bwd_fused_scatter(csr, ctx.etv[1], theta, ctx.alpha, norm, xch.x_cols, xch.g_cols, xch.peer_dx)
+        # d_norm: every row's norm gradient restricted to this rank's columns (all N rows, a share of the total)
+        d_theta, d_norm = ops.spmm_bwd_fused_scatter(csr, ctx.etv[1], theta, ctx.alpha, norm, xch.x_cols, xch.g_cols,
+                                                     xch.peer_dx, y_cols=xch.y_cols if norm is not None else None)
         xch.barrier()
         dx_own = xch.dx_rows[:re - rb]
         if not ctx.alias:
             dx_own = dx_own.clone()
-        d_norm = _own_rows_norm_grad(norm, ctx.x_own, ctx.y_own, g_own, dx_own, rb, re)
         return None, None, dx_own, d_theta.view_as(theta), None, d_norm, None, None, None, None
 
 
@@ -276,15 +301,26 @@ def feature_sliced_propagate(graph, etv, x_own, theta, alpha, norm, bounds, rank
     return _ColumnSlabPropagate.apply(graph, etv, x_own, theta, alpha, norm, bounds, rank, group)
 
 
-def allreduce_relation_grads(params, group=None):
-    """Sums the per-rank relation-embedding gradients (R x H floats each) -- the only cross-rank
-    floating-point reduction of the partitioned layer."""
+def allreduce_relation_grads(params, group=None, exchange=None):
+    """Sums the per-rank relation-embedding gradients (R x H floats each) -- the only cross-rank floating-point
+    reduction of the partitioned layer.  ``exchange`` (a ``SlabExchange``): all-gather over peer memory and a sum in
+    rank order (bit-identical on every rank and topology); otherwise all-gather with the collective library (NCCL /
+    gloo) followed by the same fixed-order sum."""
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if exchange is not None and flat.numel() <= exchange.GRAD_SLOTS:
+        total = exchange.allreduce_small(flat)
+    else:
+        with _lib.phase('allgather_relation_grads'):
+            world = dist.get_world_size(group)
+            parts = [torch.empty_like(flat) for _ in range(world)]
+            dist.all_gather(parts, flat, group=group)
+        total = parts[0].clone()
+        for q in range(1, world):
+            total = total + parts[q]
     off = 0
     for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
+        g.copy_(total[off:off + g.numel()].view_as(g))
         off += g.numel()

@@ -68,6 +68,10 @@ t('gat_fwd', lambda: ops.gat_fwd(csr, etv[0], theta, 100.0, feat, el, er, 0.2), 
 t('gat_bwd_dst', lambda: ops.gat_bwd_dst(csr, etv[0], theta, 100.0, feat, el, er, 0.2, None, out, rowmax, rowsum, gout),
   b_gat_bwd_dst)
 t('gat_bwd_src', lambda: ops.gat_bwd_src(csr, a_csr, dpre, gout), b_gat_bwd_src)
+t('gat_bwd_src (+score fold)', lambda: ops.gat_bwd_src(csr, a_csr, dpre, gout, attn_l=al, attn_r=ar, d_er=d_er), b_gat_bwd_src)
+d_el = ops.gat_bwd_src(csr, a_csr, dpre, gout)[1]
+t('attn_scores_fwd', lambda: ops.attn_scores_fwd(feat, al, ar), n * (4 * HD + 8 * H))
+t('attn_scores_bwd', lambda: ops.attn_scores_bwd(feat, d_el, d_er), n * (4 * HD + 8 * H))
 o2, m2, s2, _ = ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2)
 a2, dl2, _, _, _ = ops.gatv2_bwd_dst(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, gout)
 t('gatv2_fwd', lambda: ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2), b_v2_fwd)

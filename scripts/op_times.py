@@ -38,6 +38,9 @@ def t(name, fn, iters=20):
     print('%-34s %8.3f ms' % (name, a.elapsed_time(b) / iters))
 
 
+import subprocess  # noqa: E402
+print(subprocess.run(['nvidia-smi', '--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu', '--format=csv,noheader'],
+                     capture_output=True, text=True).stdout.strip())
 print('N=%d E=%d F=%d' % (n, e, feat))
 t('wdeg_norm_fwd (counts)', lambda: ops.wdeg_norm_fwd(csr, etv[0], theta, 100.0, -0.5, counts=etv[2]))
 t('wdeg_norm_fwd (slots)', lambda: ops.wdeg_norm_fwd(csr, etv[0], theta, 100.0, -0.5))
@@ -46,9 +49,12 @@ t('spmm fwd (row-group kernel)', lambda: ops.spmm(csr['indptr'], csr['indices'],
 t('spmm transposed (plain bwd_x)', lambda: ops.spmm(csr['indptr_t'], csr['indices_t'], etv[1], theta, 100.0, norm, norm, gout, split=csr.get('split_t')))
 t('spmm_bwd_fused (no xdx)', lambda: ops.spmm_bwd_fused(csr, etv[1], theta, 100.0, norm, x, gout))
 t('spmm_bwd_fused (+xdx)', lambda: ops.spmm_bwd_fused(csr, etv[1], theta, 100.0, norm, x, gout, want_xdx=True))
+t('spmm_bwd_fused (+folded d_norm)', lambda: ops.spmm_bwd_fused(csr, etv[1], theta, 100.0, norm, x, gout, y=y, want_dnorm=True))
 t('spmm_bwd_w (two-pass variant)', lambda: ops.spmm_bwd_w(csr, etv[0], theta, 100.0, norm, x, y, gout, dx, split=csr.get('split')))
 t('rowdot_norm_bwd (Y,G,X,dX)', lambda: ops.rowdot_norm_bwd(norm, x, y, gout, dx))
 t('rowdot_norm_bwd (xdx given)', lambda: ops.rowdot_norm_bwd(norm, x, y, gout, dx, xdx=xdx))
 t('wdeg_norm_bwd (counts)', lambda: ops.wdeg_norm_bwd(csr, etv[0], theta, 100.0, -0.5, deg, dn, counts=etv[2]))
 t('wdeg_norm_bwd (slots)', lambda: ops.wdeg_norm_bwd(csr, etv[0], theta, 100.0, -0.5, deg, dn))
 t('copy [N,F] (torch)', lambda: y.copy_(x))
+print(subprocess.run(['nvidia-smi', '--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu', '--format=csv,noheader'],
+                     capture_output=True, text=True).stdout.strip())

@@ -221,7 +221,7 @@ def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowma
     return at, dpre, d_er, d_theta
 
 
-def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None):
+def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None, attn_l=None, attn_r=None, d_er=None):
     g = g.detach()
     src = _rows_of(csr['indptr_t'])
     dstn, slot = csr['indices_t'].long(), csr['slot_t'].long()
@@ -229,7 +229,21 @@ def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None):
     d_el = None
     if dpre_csr is not None:
         d_el = torch.zeros((g.shape[0], g.shape[1]), dtype=g.dtype).index_add(0, src, dpre_csr[slot])
+    if attn_l is not None:      # epilogue fold: gradient through el = <feat, attn_l>, er = <feat, attn_r>
+        h, d = g.shape[1], g.shape[2]
+        d_feat = d_feat + d_el[:, :, None] * attn_l.detach().view(1, h, d) + d_er[:, :, None] * attn_r.detach().view(1, h, d)
     return d_feat, d_el
+
+
+def attn_scores_fwd(feat, attn_l, attn_r):
+    f = feat.detach()
+    h, d = f.shape[1], f.shape[2]
+    return (f * attn_l.detach().view(1, h, d)).sum(-1), (f * attn_r.detach().view(1, h, d)).sum(-1)
+
+
+def attn_scores_bwd(feat, d_el, d_er):
+    f = feat.detach()
+    return (d_el[:, :, None] * f).sum(0).reshape(-1), (d_er[:, :, None] * f).sum(0).reshape(-1)
 
 
 def _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope):
@@ -301,5 +315,5 @@ def install(monkeypatch):
     monkeypatch.setattr(G.Graph, 'csr', graph_csr)
     monkeypatch.setattr(G.Graph, 'etype_views', graph_etype_views)
     for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'spmm_bwd_fused', 'rowdot_norm_bwd', 'gat_fwd', 'gat_bwd_dst',
-                 'gat_bwd_src', 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src'):
+                 'gat_bwd_src', 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src', 'attn_scores_fwd', 'attn_scores_bwd'):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -102,12 +102,12 @@ def test_scatter_entry_points_validate_arguments(lib):
     """The peer-memory variants reject a missing peer table / a shape the narrow-row kernel cannot take before any launch."""
     from re_gnn_b200 import _lib
     assert lib.regnn_spmm_fwd_scatter(None, None, None, None, 1.0, 0, None, None, None, 4, 8, 4, None, None, None, None,
-                                      None) == -1
+                                      None, 0, None) == -1
     assert b'peer' in lib.regnn_last_error_string()
     assert lib.regnn_rows_to_slabs(None, 4, 8, 4, 2, 0, None, None) == -1
     peers = _lib.PeerRows(1, 2, 4, 6, 0)   # ld 6 is not a multiple of 4 floats
     assert lib.regnn_spmm_bwd_fused_scatter(None, None, None, None, 1.0, 1, None, 3, None, 4, None, 4, 8, 4, None, None,
-                                            None, None, None, None, ctypes.byref(peers), None) == -1
+                                            None, None, 0, None, None, None, None, ctypes.byref(peers), None) == -1
 
 
 def test_integration_doc_lists_every_entry_point():
