@@ -257,30 +257,39 @@ int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, const int32_t* 
     const int32_t* row_order /* as regnn_spmm_fwd's: degree-sorted rows that are not long, or NULL (natural order) */,
     void* stream);
 
-/* Backward, destination-major pass.  G = dL/d out.  Produces, per CSR slot, a_csr = a*keep and
- * dpre_csr = dL/d(el[src]+er[dst]+w) (both [E,H], slot order), d_er [N,H] and d_theta [R,H].
- * partials: double [regnn_max_partial_blocks() * R * H]. */
-int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
-                      const uint8_t* etype_csr, const float* theta, float alpha, int num_relations,
-                      const float* feat, const float* el, const float* er, float negative_slope,
-                      const float* keep, const float* out, const float* rowmax, const float* rowsum,
-                      const float* G, int num_heads, int head_dim, int64_t row_begin,
-                      int64_t row_end, float* a_csr, float* dpre_csr, float* d_er, double* partials,
-                      float* d_theta, const regnn_rowsplit_t* split,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, const int32_t* row_order, void* stream);
+/* Backward of regnn_gat_fwd as ONE gather pass (G = dL/d out).  The softmax backward of edge e = (u -> v) needs
+ * da_e = <feat[u,h,:], G[v,h,:]>, a_e (recomputed from the saved row max / sum) and S_v = <out[v,h,:], G[v,h,:]>; the
+ * source-major pass that produces d_feat[u] = sum_e a_e*keep_e*G[v] gathers G[v] anyway, so with the per-destination
+ * statistics packed per (node, head) everything per edge is computed there -- DGL's autograd runs gsddmm(dot) over
+ * feat[src] and a reverse-graph gspmm as two gather passes with [E,H] tensors in between.
+ *
+ * regnn_gat_bwd_stats: stats[v,h] = (er[v,h], rowmax[v,h], 1/rowsum[v,h], <out[v,h,:], G[v,h,:]>), float4 per (node, head). */
+int regnn_gat_bwd_stats(const float* out, const float* G, const float* er, const float* rowmax, const float* rowsum,
+                        int64_t num_nodes, int num_heads, int head_dim, float* stats /* [N,H,4] */, void* stream);
 
-/* Backward, source-major pass over the transposed view:
- *   d_feat[u,h,:] = sum_{j in Out(u)} a_csr[slot_t[j],h] * G[indices_t[j],h,:]
- *   d_el[u,h]     = sum_{j in Out(u)} dpre_csr[slot_t[j],h]          (dpre_csr may be NULL)
- * (DGL: gspmm on the reverse graph + u_add_v backward reduce).  With attn_l / attn_r ([H,D]) and d_er ([N,H], from
- * regnn_gat_bwd_dst) the gradient through the projection scores el = <feat, attn_l>, er = <feat, attn_r>
- * (layer/REGATConv.py:68-69) is folded into the epilogue: d_feat[u,h,:] += d_el[u,h]*attn_l[h,:] + d_er[u,h]*attn_r[h,:]. */
-int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
-                      const float* a_csr, const float* dpre_csr, const float* G, int num_heads,
-                      int head_dim, int64_t row_begin, int64_t row_end, float* d_feat, float* d_el,
-                      const float* attn_l /* optional */, const float* attn_r, const float* d_er,
-                      const regnn_rowsplit_t* split_t /* of the transposed view */,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, const int32_t* row_order_t, void* stream);
+/* regnn_gat_bwd_edges: source-major pass over the transposed view:
+ *   dpre_e  = (a_e*keep_e*da_e - a_e*S_v) * LeakyReLU'(pre_e)      -> dpre_csr[slot_t[j], h]  ([E,H], CSR slot order)
+ *   d_feat[u,h,:] = sum_{e in Out(u)} a_e*keep_e * G[v,h,:]  (+ d_el[u,h]*attn_l[h,:] when attn_l != NULL: the gradient
+ *                   through el = <feat, attn_l>, layer/REGATConv.py:68)
+ *   d_el[u,h]     = sum_{e in Out(u)} dpre_e
+ * etype_t: edge types per transposed entry; eid: CSR slot -> edge id (only read when keep != NULL). */
+int regnn_gat_bwd_edges(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
+                        const uint8_t* etype_t, const int32_t* eid, const float* theta, float alpha, int num_relations,
+                        const float* feat, const float* el, const float* stats, float negative_slope,
+                        const float* keep, const float* G, int num_heads, int head_dim, int64_t row_begin,
+                        int64_t row_end, float* d_feat, float* d_el, float* dpre_csr, const float* attn_l,
+                        const regnn_rowsplit_t* split_t /* of the transposed view */,
+                        float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */,
+                        const int32_t* row_order_t, void* stream);
+
+/* regnn_gat_bwd_reduce: the destination-side reductions of dpre_csr, both pure streaming passes over [E,H]:
+ *   d_er[v,h] = sum_{slots of row v} dpre_csr[slot,h]        d_theta[r,h] = alpha*LeakyReLU'(alpha*theta[r,h]) * sum_{etype=r} dpre
+ * (deterministic: slot order per row; lane-local bins -> per-block double partials -> fixed-order finalize).
+ * partials: double [regnn_max_partial_blocks() * R * H]; split_workspace: split->num_frags * H floats. */
+int regnn_gat_bwd_reduce(const int32_t* indptr, const uint8_t* etype_csr, const float* theta, float alpha,
+                         int num_relations, const float* dpre_csr, int num_heads, int64_t row_begin, int64_t row_end,
+                         float* d_er, double* partials, float* d_theta, const regnn_rowsplit_t* split,
+                         float* split_workspace, void* stream);
 
 /* Projection scores of REGAT (layer/REGATConv.py:68-69: `el = (feat * attn_l).sum(-1)`, `er = (feat * attn_r).sum(-1)`,
  * two eager mul + sum pairs in the reference) in one streaming pass over feat [N,H,D]: el, er [N,H]. */
@@ -288,10 +297,12 @@ int regnn_attn_scores_fwd(const float* feat, const float* attn_l, const float* a
                           int head_dim, float* el, float* er, void* stream);
 
 /* Parameter gradients of the projection scores: d_attn_l[h,d] = sum_n d_el[n,h]*feat[n,h,d], d_attn_r likewise
- * (deterministic: lane-local sums, per-block double partials, fixed-order finalize).
+ * (deterministic: lane-local sums, per-block double partials, fixed-order finalize).  d_feat != NULL: the same pass adds
+ * the destination-side score gradient to the feature gradient in place, d_feat[n,h,:] += d_er[n,h]*attn_r[h,:].
  * partials: double [regnn_max_partial_blocks() * 2*H*D]. */
 int regnn_attn_scores_bwd(const float* feat, const float* d_el, const float* d_er, int64_t num_nodes, int num_heads,
-                          int head_dim, double* partials, float* d_attn_l, float* d_attn_r, void* stream);
+                          int head_dim, double* partials, float* d_attn_l, float* d_attn_r, float* d_feat,
+                          const float* attn_r, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused REGATv2 layer core (layer/REGATv2Conv.py:133-152):

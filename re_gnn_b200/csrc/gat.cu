@@ -59,8 +59,7 @@ struct AttnArgs {
   int64_t n_order;
   // gat_bwd_src epilogue (optional): d_feat[u,h,:] += d_el[u,h]*attn_l[h,:] + d_er[u,h]*attn_r[h,:]
   const float* attn_l;
-  const float* attn_r;
-  const float* d_er_in;
+  const int32_t* a_csr_eid;  // gat_bwd_edges with a dropout mask: CSR slot -> edge id
 };
 
 struct WorkItem {
@@ -323,120 +322,53 @@ gat_fwd_rg_kernel(AttnArgs a) {
   }
 }
 
-// REGAT backward, destination-major.  Per edge: da = <feat[src,h,:], G[v,h,:]> (butterfly over the D/4 lanes of the
-// head), a recomputed from the saved row max / sum, dpre = (a*keep*da - a*S) * LeakyReLU'(pre), S = <out[v,h,:],
-// G[v,h,:]>.  Writes a*keep and dpre per (slot, head), d_er rows, and lane-group-local relation bins.
-// Dynamic smem: w_s[R*H] | per warp: bins[R*H][GPW]
+// =================================================================================================
+// REGAT backward as ONE gather pass.  The softmax backward of an edge e = (u -> v) needs
+//   da_e = <feat[u,h,:], G[v,h,:]>,   a_e = exp(l_e - m_v) / s_v,   S_v = sum_e' a_e' da_e' = <out[v,h,:], G[v,h,:]>
+// and the source-major pass that produces d_feat[u] = sum_e a_e G[v] gathers G[v] anyway while feat[u] is the row
+// the lane group owns: with the per-destination statistics (er, m, 1/s, S) packed as one float4 per (node, head) by
+// a streaming pre-pass, every per-edge quantity is available in that ONE pass -- the destination-major pass over
+// feat[src] of round 1 (a second 4HD-byte gather per edge) and the [E,H] attention tensor between the passes are gone.
+//   gat_bwd_stats_kernel    stats[v,h] = (er, rowmax, 1/rowsum, <out,G>)                      streaming, 2 N H D reads
+//   gat_bwd_edges_kernel    d_feat[u], d_el[u], dpre[slot,h]  (source-major, row groups)      the gather pass
+//   gat_bwd_der_kernel      d_er[v,h] = sum_{slots of v} dpre[slot,h]                         streaming over [E,H]
+//   gat_bwd_bins_kernel     relation bins of dpre (lane-local, per-block double partials)     streaming over [E,H]
 template <int G>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
-gat_bwd_dst_rg_kernel(AttnArgs a) {
-  constexpr int GPW = 32 / G, U = kUG;
-  extern __shared__ __align__(16) float smem[];
-  const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
-  float* w_s = smem;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
-  float* bins = smem + RH + (size_t)warp * RH * GPW;
-  for (int i = lane; i < RH * GPW; i += 32) bins[i] = 0.f;
-  load_rel_table(w_s, a);
-  const int lph = min(G, a.D >> 2);
-  const bool has_rel = a.etype != nullptr;
-  const int64_t nwork = rg_num_work(a, G);
-
-  for (int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; wi < nwork; wi += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const RowItem it = rg_item<G>(a, wi, grp);
-    const int col = it.hg * 128 + lg * 4;
-    const bool col_ok = col < HD;
-    const int h = col_ok ? (col >> a.d_shift) : 0;
-    const bool act = it.v >= 0 && col_ok;
-    const bool leader = act && (col & (a.D - 1)) == 0;
-    const int len = it.v >= 0 ? it.len : 0;
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    float4 gv = zero4();
-    float part = 0.f, er_v = 0.f, m = 0.f, inv = 0.f, der = 0.f;
-    if (act) {
-      gv = ldg4(a.G + (size_t)it.v * HD + col);
-      part = dot4(ldg4(a.out + (size_t)it.v * HD + col), gv);
-      const size_t vh = (size_t)it.v * H + h;
-      er_v = __ldg(a.er + vh);
-      m = __ldg(a.rowmax + vh);
-      const float sm = __ldg(a.rowsum + vh);
-      inv = sm > 0.f ? 1.f / sm : 0.f;
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gat_bwd_stats_kernel(const float* __restrict__ out, const float* __restrict__ Gd, const float* __restrict__ er,
+                     const float* __restrict__ rowmax, const float* __restrict__ rowsum, int64_t n, int H, int D,
+                     int d_shift, int HG, float4* __restrict__ stats) {
+  constexpr int GPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int lg = lane % G, grp = lane / G;
+  const int HD = H * D, lph = min(G, D >> 2);
+  const int64_t items = n * HG;
+  for (int64_t wi = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * GPW; wi < items;
+       wi += (int64_t)gridDim.x * kWarpsPerBlock * GPW) {
+    const int64_t vi = wi + grp;
+    const int64_t v = vi / HG;
+    const int col = (int)(vi % HG) * 128 + lg * 4;
+    const bool act = vi < items && col < HD;
+    float p = 0.f;
+    if (act) p = dot4(ldg4(out + (size_t)v * HD + col), ldg4(Gd + (size_t)v * HD + col));
+    p = group_sum_rt(p, lph);
+    if (act && (col & (D - 1)) == 0) {
+      const size_t vh = (size_t)v * H + (col >> d_shift);
+      const float sm = rowsum[vh];
+      stats[vh] = make_float4(er[vh], rowmax[vh], sm > 0.f ? 1.f / sm : 0.f, p);
     }
-    const float S = group_sum_rt(part, lph);
-    const float* fcol = a.feat + (col_ok ? col : 0);
-    const float* elh = a.el + h;
-    const int32_t* ip = a.indices + it.begin;
-    const uint8_t* ep = a.etype + it.begin;
-    const int32_t* eidp = a.eid + it.begin;
-
-    for (int t0 = 0; t0 < maxlen; t0 += G) {
-      int bi = -1, be = 0, beid = 0;
-      {
-        const int t = t0 + lg;
-        if (t < len) {
-          bi = __ldg(ip + t);
-          if (has_rel) be = __ldg(ep + t);
-          if (a.keep != nullptr) beid = __ldg(eidp + t);
-        }
-      }
-      const int cnt = min(G, maxlen - t0);
-      for (int j = 0; j < cnt; j += U) {
-        float4 x[U];
-        float e[U], da[U];
-        int si[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          si[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
-          const bool ok = si[u] >= 0 && col_ok;
-          x[u] = ok ? ldg4(fcol + (size_t)si[u] * HD) : zero4();
-          e[u] = ok ? __ldg(elh + (size_t)si[u] * H) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) da[u] = group_sum_rt(dot4(x[u], gv), lph);  // U independent reductions
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int se = has_rel ? __shfl_sync(0xffffffffu, be, gbase + j + u) : 0;
-          const int seid = a.keep != nullptr ? __shfl_sync(0xffffffffu, beid, gbase + j + u) : 0;
-          if (si[u] >= 0 && act) {
-            float pre = e[u] + er_v;
-            if (has_rel) pre += w_s[se * H + h];
-            const float aa = __expf(leaky(pre, a.slope) - m) * inv;
-            const float at = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)seid * H + h) : aa;
-            const float dp = (at * da[u] - aa * S) * leaky_grad(pre, a.slope);
-            der += dp;
-            if (leader) {
-              const size_t sh = (size_t)(it.begin + t0 + j + u) * H + h;
-              a.o0[sh] = at;
-              a.o1[sh] = dp;
-              if (has_rel) bins[(se * H + h) * GPW + grp] += dp;  // one writer per (head, lane group): no conflicts
-            }
-          }
-        }
-      }
-    }
-    if (leader) {
-      if (it.frag) a.p1[(size_t)it.fi * H + h] = der;
-      else a.o2[(size_t)it.v * H + h] = der;
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < RH; i += blockDim.x) {
-    double sum = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w)
-      for (int q = 0; q < GPW; ++q) sum += (double)smem[RH + ((size_t)w * RH + i) * GPW + q];
-    a.partials[(size_t)blockIdx.x * a.partial_stride + i] = sum;
   }
 }
 
-// Source-major aggregation with the stored per-slot, per-head weights:
-//   d_feat[u,h,:] = sum_j a_csr[slot_t[j],h] * G[indices_t[j],h,:]     d_el[u,h] = sum_j dpre_csr[slot_t[j],h]
-// and, when attn_l / attn_r / d_er are given, the projection-score gradient folded into the epilogue:
-//   d_feat[u,h,:] += d_el[u,h] * attn_l[h,:] + d_er[u,h] * attn_r[h,:]
-template <int G>
+// Source-major gather pass (transposed view; AttnArgs: indptr/indices/eid = indptr_t/indices_t/slot_t, etype = etype_t,
+// fd = stats as float4[N*H], G = dL/d out, a_csr = slot -> edge id when keep != null).
+template <int G, bool KEEP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
-gat_bwd_src_rg_kernel(AttnArgs a) {
-  constexpr int U = kUG;
+gat_bwd_edges_kernel(AttnArgs a) {
+  constexpr int U = 2;  // two rows of G and two statistics vectors in flight per lane
+  extern __shared__ __align__(16) float smem[];
+  float* w_s = smem;
+  load_rel_table(w_s, a);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
   const int H = a.H, HD = H * a.D;
@@ -450,69 +382,146 @@ gat_bwd_src_rg_kernel(AttnArgs a) {
   const bool leader = act && (col & (a.D - 1)) == 0;
   const int len = it.v >= 0 ? it.len : 0;
   const int maxlen = __reduce_max_sync(0xffffffffu, len);
+  const int lph = min(G, a.D >> 2);
+  const bool has_rel = a.etype != nullptr;
+  float4 fu = zero4();
+  float el_u = 0.f;
+  if (act) {
+    fu = ldg4(a.feat + (size_t)it.v * HD + col);
+    el_u = __ldg(a.el + (size_t)it.v * H + h);
+  }
   const float* gcol = a.G + (col_ok ? col : 0);
-  const float* ah = a.a_csr + h;
-  const float* dh = a.d_csr != nullptr ? a.d_csr + h : nullptr;
+  const float4* sth = reinterpret_cast<const float4*>(a.fd) + h;
   const int32_t* ip = a.indices + it.begin;
   const int32_t* sp = a.eid + it.begin;
+  const uint8_t* ep = a.etype + it.begin;
   float4 acc = zero4();
   float del = 0.f;
+
   for (int t0 = 0; t0 < maxlen; t0 += G) {
-    int bi = -1, bs = 0;
+    int bi = -1, bs = 0, be = 0;
     {
       const int t = t0 + lg;
       if (t < len) {
         bi = __ldg(ip + t);
         bs = __ldg(sp + t);
+        if (has_rel) be = __ldg(ep + t);
       }
     }
     const int cnt = min(G, maxlen - t0);
     for (int j = 0; j < cnt; j += U) {
-      float4 x[U];
-      float pa[U], pd[U];
+      float4 x[U], st[U];
+      int sd[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int sd = __shfl_sync(0xffffffffu, bi, gbase + j + u);
-        const int ss = __shfl_sync(0xffffffffu, bs, gbase + j + u);
-        const bool ok = sd >= 0 && col_ok;
-        x[u] = ok ? ldg4(gcol + (size_t)sd * HD) : zero4();
-        pa[u] = ok ? __ldg(ah + (size_t)ss * H) : 0.f;
-        pd[u] = (ok && dh != nullptr) ? __ldg(dh + (size_t)ss * H) : 0.f;
+        sd[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+        const bool ok = sd[u] >= 0 && col_ok;
+        x[u] = ok ? ldg4(gcol + (size_t)sd[u] * HD) : zero4();
+        st[u] = ok ? __ldg(sth + (size_t)sd[u] * H) : zero4();
       }
+      float da[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) da[u] = group_sum_rt(dot4(fu, x[u]), lph);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        fma4(acc, pa[u], x[u]);
-        del += pd[u];
+        const int ss = __shfl_sync(0xffffffffu, bs, gbase + j + u);
+        const int se = has_rel ? __shfl_sync(0xffffffffu, be, gbase + j + u) : 0;
+        if (sd[u] >= 0 && act) {
+          float pre = el_u + st[u].x;
+          if (has_rel) pre += w_s[se * H + h];
+          const float aa = __expf(leaky(pre, a.slope) - st[u].y) * st[u].z;
+          float at = aa;
+          if (KEEP) at *= __ldg(a.keep + (size_t)__ldg(a.a_csr_eid + ss) * H + h);
+          const float dp = (at * da[u] - aa * st[u].w) * leaky_grad(pre, a.slope);
+          fma4(acc, at, x[u]);
+          del += dp;
+          if (leader) a.o2[(size_t)ss * H + h] = dp;   // dpre per CSR slot: the destination-side reductions read it
+        }
       }
     }
   }
   if (!act) return;
   if (it.frag) {
     st4(a.p0 + (size_t)it.fi * HD + col, acc);
-    if (dh != nullptr && leader) a.p1[(size_t)it.fi * H + h] = del;
+    if (leader) a.p1[(size_t)it.fi * H + h] = del;
     return;
   }
-  if (a.attn_l != nullptr) {
-    fma4(acc, del, ldg4(a.attn_l + col));
-    fma4(acc, __ldg(a.d_er_in + (size_t)it.v * H + h), ldg4(a.attn_r + col));
-  }
+  if (a.attn_l != nullptr) fma4(acc, del, ldg4(a.attn_l + col));   // gradient through el = <feat, attn_l>
   st4(a.o0 + (size_t)it.v * HD + col, acc);
-  if (dh != nullptr && leader) a.o1[(size_t)it.v * H + h] = del;
+  if (leader) a.o1[(size_t)it.v * H + h] = del;
 }
 
-// The epilogue fold of gat_bwd_src_rg_kernel for the long rows (their sums are only complete after frag_rowsum_kernel)
+// d_feat[v,h,:] += d_el[v,h] * attn_l[h,:] for the long rows (their sums are only complete after frag_rowsum_kernel)
 __global__ void gat_fold_long_rows_kernel(const int32_t* __restrict__ long_rows, int num_long, int H, int D,
-                                          const float* __restrict__ attn_l, const float* __restrict__ attn_r,
-                                          const float* __restrict__ d_el, const float* __restrict__ d_er,
+                                          const float* __restrict__ attn_l, const float* __restrict__ d_el,
                                           float* __restrict__ d_feat, int64_t row_begin, int64_t row_end) {
   const int l = blockIdx.x;
   if (l >= num_long) return;
   const int64_t v = long_rows[l];
   if (v < row_begin || v >= row_end) return;
   const int HD = H * D;
-  for (int c = threadIdx.x; c < HD; c += blockDim.x) {
-    const int h = c / D;
-    d_feat[(size_t)v * HD + c] += d_el[(size_t)v * H + h] * attn_l[c] + d_er[(size_t)v * H + h] * attn_r[c];
+  for (int c = threadIdx.x; c < HD; c += blockDim.x)
+    d_feat[(size_t)v * HD + c] += d_el[(size_t)v * H + c / D] * attn_l[c];
+}
+
+// d_er[v,h] = sum over the CSR slots of row v of dpre[slot,h]: HP = next power of two >= H lanes per item (lane = head),
+// 32/HP items per warp (fragments of long rows first, then the rows), each lane adds its head in slot order
+// (deterministic), 4 loads in flight.  AttnArgs: indptr, d_csr = dpre, o2 = d_er, p1 = fragment partials.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gat_bwd_der_kernel(AttnArgs a, int HP) {
+  const int lane = threadIdx.x & 31;
+  const int H = a.H, hh = lane % HP, per = 32 / HP;
+  const int64_t vi = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * per + lane / HP;
+  const int64_t rows = a.row_end - a.row_begin;
+  if (vi >= a.nfrag + rows || hh >= H) return;
+  int s0, s1;
+  float* dst;
+  if (vi < a.nfrag) {
+    const int64_t v = a.frag_row[vi];
+    if (v < a.row_begin || v >= a.row_end) return;
+    s0 = a.frag_begin[vi];
+    s1 = s0 + min(a.threshold, a.indptr[v + 1] - s0);
+    dst = a.p1 + (size_t)vi * H + hh;
+  } else {
+    const int64_t v = a.row_begin + (vi - a.nfrag);
+    s0 = a.indptr[v];
+    s1 = a.indptr[v + 1];
+    if (s1 - s0 > a.threshold) return;  // covered by fragments
+    dst = a.o2 + (size_t)v * H + hh;
+  }
+  const float* p = a.d_csr + (size_t)s0 * H + hh;
+  float acc = 0.f;
+  int s = s0;
+  for (; s + 4 <= s1; s += 4, p += 4 * H) {
+    const float a0 = __ldg(p), a1 = __ldg(p + H), a2 = __ldg(p + 2 * H), a3 = __ldg(p + 3 * H);
+    acc = (((acc + a0) + a1) + a2) + a3;
+  }
+  for (; s < s1; ++s, p += H) acc += __ldg(p);
+  *dst = acc;
+}
+
+// Relation bins of dpre: pure streaming over [E,H] (+ the uint8 edge types), lane-local bins, per-block double partials.
+// Dynamic smem: [warps][R][32] floats
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gat_bwd_bins_kernel(const uint8_t* __restrict__ etype, const float* __restrict__ dpre, const int32_t* __restrict__ indptr,
+                    int64_t row_begin, int64_t row_end, int R, int H, int HP, double* __restrict__ partials) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s_begin = indptr[row_begin], s_end = indptr[row_end];
+  float* mybins = smem + (size_t)warp * R * 32 + lane;
+  for (int r = 0; r < R; ++r) mybins[r * 32] = 0.f;
+  const int hh = lane % HP, per = 32 / HP;
+  if (hh < H)
+    for (int64_t s = s_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * per + lane / HP; s < s_end;
+         s += (int64_t)gridDim.x * kWarpsPerBlock * per)
+      mybins[(int)etype[s] * 32] += __ldg(dpre + (size_t)s * H + hh);
+  __syncthreads();
+  for (int i = threadIdx.x; i < R * H; i += blockDim.x) {
+    const int r = i / H, h2 = i % H;
+    double sum = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w)
+      for (int q = h2; q < 32; q += HP) sum += (double)smem[((size_t)w * R + r) * 32 + q];
+    partials[(size_t)blockIdx.x * R * H + i] = sum;
   }
 }
 
@@ -550,11 +559,14 @@ attn_scores_fwd_kernel(const float* __restrict__ feat, const float* __restrict__
 
 // d_attn_l[h,d] = sum_n d_el[n,h] * feat[n,h,d], d_attn_r likewise: lane-local float4 accumulators over a persistent
 // grid (warp w keeps slice w % HG for all its rows), per-block double partials [2*H*D], fixed-order finalize.
+// d_feat != null: the same pass also finishes the feature gradient, d_feat[n,h,:] += d_er[n,h] * attn_r[h,:] (the
+// destination-side score gradient, only complete after gat_bwd_der_kernel).
 // Dynamic smem: [warps][2][128] floats
 template <int G>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 attn_scores_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ d_el, const float* __restrict__ d_er,
-                       int64_t n, int H, int D, int d_shift, int HG, double* __restrict__ partials) {
+                       int64_t n, int H, int D, int d_shift, int HG, double* __restrict__ partials,
+                       float* __restrict__ d_feat, const float* __restrict__ attn_r) {
   constexpr int GPW = 32 / G;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -567,12 +579,20 @@ attn_scores_bwd_kernel(const float* __restrict__ feat, const float* __restrict__
   const bool col_ok = col < HD;
   const int h = col_ok ? (col >> d_shift) : 0;
   float4 al = zero4(), ar = zero4();
-  if (wg < usable && col_ok)
+  if (wg < usable && col_ok) {
+    const float4 arv = d_feat != nullptr ? ldg4(attn_r + col) : zero4();
     for (int64_t v = (wg / HG) * GPW + grp; v < n; v += (usable / HG) * GPW) {
       const float4 f = ldg4(feat + (size_t)v * HD + col);
+      const float de = __ldg(d_er + (size_t)v * H + h);
       fma4(al, __ldg(d_el + (size_t)v * H + h), f);
-      fma4(ar, __ldg(d_er + (size_t)v * H + h), f);
+      fma4(ar, de, f);
+      if (d_feat != nullptr) {
+        float4 x = *reinterpret_cast<const float4*>(d_feat + (size_t)v * HD + col);
+        fma4(x, de, arv);
+        st4(d_feat + (size_t)v * HD + col, x);
+      }
     }
+  }
   // fold the lane groups of the warp (same columns), then the warps of the block that own the same slice
 #pragma unroll
   for (int o = G; o < 32; o <<= 1) {
@@ -1129,81 +1149,128 @@ extern "C" int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, cons
   return check_launch("regnn_gat_fwd");
 }
 
-extern "C" int regnn_gat_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
-                                 const uint8_t* etype_csr, const float* theta, float alpha,
-                                 int num_relations, const float* feat, const float* el,
-                                 const float* er, float negative_slope, const float* keep,
-                                 const float* out, const float* rowmax, const float* rowsum,
-                                 const float* Gd, int num_heads, int head_dim, int64_t row_begin,
-                                 int64_t row_end, float* a_csr, float* dpre_csr, float* d_er,
-                                 double* partials, float* d_theta, const regnn_rowsplit_t* split, float* split_workspace,
-                                 const int32_t* row_order, void* stream_) {
+extern "C" int regnn_gat_bwd_stats(const float* out, const float* Gd, const float* er, const float* rowmax,
+                                   const float* rowsum, int64_t num_nodes, int num_heads, int head_dim, float* stats,
+                                   void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && feat && el && er && out && rowmax && rowsum && Gd && d_er,
-                REGNN_ERR_INVALID_ARG, "gat_bwd_dst: null pointer");
-  REGNN_REQUIRE(keep == nullptr || eid != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_dst: keep needs eid");
-  REGNN_REQUIRE(etype_csr == nullptr || (theta && partials && d_theta), REGNN_ERR_INVALID_ARG, "gat_bwd_dst: null relation buffers");
-  int rc = check_shape("gat_bwd_dst", num_heads, head_dim, num_relations, etype_csr != nullptr, true);
+  REGNN_REQUIRE(out && Gd && er && rowmax && rowsum && stats && num_nodes >= 0, REGNN_ERR_INVALID_ARG,
+                "gat_bwd_stats: bad argument");
+  int rc = check_shape("gat_bwd_stats", num_heads, head_dim, 0, false, true);
   if (rc != REGNN_OK) return rc;
-  REGNN_REQUIRE(aligned16(feat) && aligned16(out) && aligned16(Gd), REGNN_ERR_INVALID_ARG, "gat_bwd_dst: 16-byte alignment required");
-  const int64_t rows = row_end - row_begin;
-  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gat_bwd_dst: negative row range");
+  REGNN_REQUIRE(aligned16(out) && aligned16(Gd) && aligned16(stats), REGNN_ERR_INVALID_ARG,
+                "gat_bwd_stats: 16-byte alignment required");
+  if (num_nodes == 0) return REGNN_OK;
   AttnArgs a{};
-  a.indptr = indptr; a.indices = indices; a.eid = eid; a.etype = etype_csr; a.theta = theta; a.alpha = alpha;
-  a.R = etype_csr ? num_relations : 0; a.feat = feat; a.el = el; a.er = er; a.slope = negative_slope; a.keep = keep;
-  a.out = out; a.rowmax = rowmax; a.rowsum = rowsum; a.G = Gd; a.H = num_heads; a.D = head_dim;
-  a.row_begin = row_begin; a.row_end = row_end; a.o0 = a_csr; a.o1 = dpre_csr; a.o2 = d_er;
-  a.partials = partials; a.partial_stride = a.R * num_heads;
-  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_dst: incomplete row split");
-  apply_order(a, row_order, split, rows);
-  const int RH = a.R * num_heads, gpw = 32 / rg_lanes(num_heads * head_dim);
-  const size_t smem = sizeof(float) * ((size_t)RH * (1 + kWarpsPerBlock * gpw)) + 16;
-  int nb = partial_blocks(rg_work(a, rows));
-  switch (rg_lanes(num_heads * head_dim)) {   // persistent: one resident wave
-    case 4: nb = min(nb, resident_blocks(gat_bwd_dst_rg_kernel<4>, smem)); break;
-    case 8: nb = min(nb, resident_blocks(gat_bwd_dst_rg_kernel<8>, smem)); break;
-    case 16: nb = min(nb, resident_blocks(gat_bwd_dst_rg_kernel<16>, smem)); break;
-    default: nb = min(nb, resident_blocks(gat_bwd_dst_rg_kernel<32>, smem)); break;
+  a.H = num_heads; a.D = head_dim;
+  apply_split(a, nullptr, nullptr);
+  const int G = rg_lanes(num_heads * head_dim);
+  const int64_t work = (num_nodes * a.hg_count + 32 / G - 1) / (32 / G);
+  const int64_t want = (work + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+#define REGNN_STATS(G_)                                                                                              \
+  gat_bwd_stats_kernel<G_><<<grid, kWarpsPerBlock * 32, 0, stream>>>(out, Gd, er, rowmax, rowsum, num_nodes, num_heads, \
+                                                                    head_dim, a.d_shift, a.hg_count,                \
+                                                                    reinterpret_cast<float4*>(stats))
+  switch (G) {
+    case 4: REGNN_STATS(4); break;
+    case 8: REGNN_STATS(8); break;
+    case 16: REGNN_STATS(16); break;
+    default: REGNN_STATS(32); break;
   }
-  REGNN_DISPATCH_RG(gat_bwd_dst_rg_kernel, nb, smem);
-  if (a.nfrag > 0) launch_rowsum(split, a.p1, num_heads, d_er, row_begin, row_end, stream);
-  if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH, RH, theta, alpha, d_theta, stream);
-  return check_launch("regnn_gat_bwd_dst");
+#undef REGNN_STATS
+  return check_launch("regnn_gat_bwd_stats");
 }
 
-extern "C" int regnn_gat_bwd_src(const int32_t* indptr_t, const int32_t* indices_t,
-                                 const int32_t* slot_t, const float* a_csr, const float* dpre_csr,
-                                 const float* Gd, int num_heads, int head_dim, int64_t row_begin,
-                                 int64_t row_end, float* d_feat, float* d_el, const float* attn_l, const float* attn_r,
-                                 const float* d_er, const regnn_rowsplit_t* split, float* split_workspace,
-                                 const int32_t* row_order_t, void* stream_) {
+extern "C" int regnn_gat_bwd_edges(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
+                                   const uint8_t* etype_t, const int32_t* eid, const float* theta, float alpha,
+                                   int num_relations, const float* feat, const float* el, const float* stats,
+                                   float negative_slope, const float* keep, const float* Gd, int num_heads,
+                                   int head_dim, int64_t row_begin, int64_t row_end, float* d_feat, float* d_el,
+                                   float* dpre_csr, const float* attn_l, const regnn_rowsplit_t* split_t,
+                                   float* split_workspace, const int32_t* row_order_t, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr_t && Gd && d_feat && a_csr, REGNN_ERR_INVALID_ARG, "gat_bwd_src: null pointer");
-  REGNN_REQUIRE(dpre_csr == nullptr || d_el != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_src: dpre_csr without d_el");
-  REGNN_REQUIRE(attn_l == nullptr || (attn_r && d_er && dpre_csr && aligned16(attn_l) && aligned16(attn_r)),
-                REGNN_ERR_INVALID_ARG, "gat_bwd_src: the score-gradient fold needs attn_l, attn_r (16-byte aligned), d_er and dpre_csr");
-  int rc = check_shape("gat_bwd_src", num_heads, head_dim, 0, false, true);
+  REGNN_REQUIRE(indptr_t && feat && el && stats && Gd && d_feat && d_el, /* per-edge arrays may be NULL when E == 0 */
+                REGNN_ERR_INVALID_ARG, "gat_bwd_edges: null pointer");
+  REGNN_REQUIRE(keep == nullptr || eid != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_edges: keep needs eid");
+  REGNN_REQUIRE(etype_t == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "gat_bwd_edges: etype without theta");
+  int rc = check_shape("gat_bwd_edges", num_heads, head_dim, num_relations, etype_t != nullptr, true);
   if (rc != REGNN_OK) return rc;
-  REGNN_REQUIRE(aligned16(Gd) && aligned16(d_feat), REGNN_ERR_INVALID_ARG, "gat_bwd_src: 16-byte alignment required");
+  REGNN_REQUIRE(aligned16(feat) && aligned16(Gd) && aligned16(d_feat) && aligned16(stats) && aligned16(attn_l),
+                REGNN_ERR_INVALID_ARG, "gat_bwd_edges: 16-byte alignment required");
   const int64_t rows = row_end - row_begin;
-  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gat_bwd_src: negative row range");
+  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gat_bwd_edges: negative row range");
   if (rows == 0) return REGNN_OK;
   AttnArgs a{};
-  a.indptr = indptr_t; a.indices = indices_t; a.eid = slot_t; a.a_csr = a_csr; a.d_csr = dpre_csr; a.G = Gd;
-  a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end; a.o0 = d_feat; a.o1 = d_el;
-  a.attn_l = attn_l; a.attn_r = attn_r; a.d_er_in = d_er;
-  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_src: incomplete row split");
-  apply_order(a, row_order_t, split, rows);
+  a.indptr = indptr_t; a.indices = indices_t; a.eid = slot_t; a.etype = etype_t; a.theta = theta; a.alpha = alpha;
+  a.R = etype_t ? num_relations : 0; a.feat = feat; a.el = el; a.fd = stats; a.slope = negative_slope; a.keep = keep;
+  a.a_csr_eid = eid; a.G = Gd; a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end;
+  a.o0 = d_feat; a.o1 = d_el; a.o2 = dpre_csr; a.attn_l = attn_l;
+  REGNN_REQUIRE(apply_split(a, split_t, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_edges: incomplete row split");
+  apply_order(a, row_order_t, split_t, rows);
+  const size_t smem = sizeof(float) * ((size_t)a.R * num_heads) + 16;
   const unsigned grid = (unsigned)((rg_work(a, rows) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  REGNN_DISPATCH_RG(gat_bwd_src_rg_kernel, grid, 0);
-  if (a.nfrag > 0) {
-    launch_rowsum(split, a.p0, num_heads * head_dim, d_feat, row_begin, row_end, stream);
-    if (dpre_csr != nullptr) launch_rowsum(split, a.p1, num_heads, d_el, row_begin, row_end, stream);
-    if (attn_l != nullptr)
-      gat_fold_long_rows_kernel<<<split->num_long, 128, 0, stream>>>(split->long_rows, split->num_long, num_heads, head_dim,
-                                                                     attn_l, attn_r, d_el, d_er, d_feat, row_begin, row_end);
+  if (keep != nullptr) {
+    switch (rg_lanes(a.H * a.D)) {
+      case 4: REGNN_DISPATCH_C((gat_bwd_edges_kernel<4, true>), grid, smem); break;
+      case 8: REGNN_DISPATCH_C((gat_bwd_edges_kernel<8, true>), grid, smem); break;
+      case 16: REGNN_DISPATCH_C((gat_bwd_edges_kernel<16, true>), grid, smem); break;
+      default: REGNN_DISPATCH_C((gat_bwd_edges_kernel<32, true>), grid, smem); break;
+    }
+  } else {
+    switch (rg_lanes(a.H * a.D)) {
+      case 4: REGNN_DISPATCH_C((gat_bwd_edges_kernel<4, false>), grid, smem); break;
+      case 8: REGNN_DISPATCH_C((gat_bwd_edges_kernel<8, false>), grid, smem); break;
+      case 16: REGNN_DISPATCH_C((gat_bwd_edges_kernel<16, false>), grid, smem); break;
+      default: REGNN_DISPATCH_C((gat_bwd_edges_kernel<32, false>), grid, smem); break;
+    }
   }
-  return check_launch("regnn_gat_bwd_src");
+  if (a.nfrag > 0) {
+    launch_rowsum(split_t, a.p0, num_heads * head_dim, d_feat, row_begin, row_end, stream);
+    launch_rowsum(split_t, a.p1, num_heads, d_el, row_begin, row_end, stream);
+    if (attn_l != nullptr)
+      gat_fold_long_rows_kernel<<<split_t->num_long, 128, 0, stream>>>(split_t->long_rows, split_t->num_long, num_heads,
+                                                                       head_dim, attn_l, d_el, d_feat, row_begin, row_end);
+  }
+  return check_launch("regnn_gat_bwd_edges");
+}
+
+extern "C" int regnn_gat_bwd_reduce(const int32_t* indptr, const uint8_t* etype_csr, const float* theta, float alpha,
+                                    int num_relations, const float* dpre_csr, int num_heads, int64_t row_begin,
+                                    int64_t row_end, float* d_er, double* partials, float* d_theta,
+                                    const regnn_rowsplit_t* split, float* split_workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  REGNN_REQUIRE(indptr && d_er, REGNN_ERR_INVALID_ARG, "gat_bwd_reduce: null pointer");
+  REGNN_REQUIRE(etype_csr == nullptr || (theta && partials && d_theta), REGNN_ERR_INVALID_ARG,
+                "gat_bwd_reduce: null relation buffers");
+  REGNN_REQUIRE(num_heads >= 1 && num_heads <= REGNN_MAX_HEADS, REGNN_ERR_UNSUPPORTED_SHAPE, "gat_bwd_reduce: num_heads=%d", num_heads);
+  const int R = etype_csr ? num_relations : 0;
+  REGNN_REQUIRE(etype_csr == nullptr || (R >= 1 && R <= REGNN_MAX_RELATIONS), REGNN_ERR_UNSUPPORTED_SHAPE,
+                "gat_bwd_reduce: num_relations=%d", R);
+  const int64_t rows = row_end - row_begin;
+  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gat_bwd_reduce: negative row range");
+  if (rows == 0) return REGNN_OK;
+  int HP = 1;
+  while (HP < num_heads) HP <<= 1;
+  AttnArgs a{};
+  a.indptr = indptr; a.H = num_heads; a.D = 4; a.row_begin = row_begin; a.row_end = row_end; a.d_csr = dpre_csr; a.o2 = d_er;
+  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gat_bwd_reduce: incomplete row split");
+  a.p1 = split_workspace;   // [nfrag][H] fragment partials
+  const int per = 32 / HP;
+  const int64_t items = a.nfrag + rows;
+  const unsigned grid = (unsigned)((items + (int64_t)per * kWarpsPerBlock - 1) / ((int64_t)per * kWarpsPerBlock));
+  gat_bwd_der_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, HP);
+  if (a.nfrag > 0) launch_rowsum(split, a.p1, num_heads, d_er, row_begin, row_end, stream);
+  if (etype_csr != nullptr) {
+    // the slot range of the row range (host-side values are not available without a sync: pass the pointers)
+    const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * R * 32;
+    int rc = set_smem(gat_bwd_bins_kernel, smem);
+    if (rc != REGNN_OK) return rc;
+    const int nb = min(partial_blocks(rows), 148 * 4);
+    gat_bwd_bins_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(etype_csr, dpre_csr, indptr, row_begin, row_end, R,
+                                                                  num_heads, HP, partials);
+    launch_relation_grad_finalize(partials, nb, R * num_heads, R * num_heads, theta, alpha, d_theta, stream);
+  }
+  return check_launch("regnn_gat_bwd_reduce");
 }
 
 extern "C" int regnn_attn_scores_fwd(const float* feat, const float* attn_l, const float* attn_r, int64_t num_nodes,
@@ -1237,24 +1304,26 @@ extern "C" int regnn_attn_scores_fwd(const float* feat, const float* attn_l, con
 
 extern "C" int regnn_attn_scores_bwd(const float* feat, const float* d_el, const float* d_er, int64_t num_nodes,
                                      int num_heads, int head_dim, double* partials, float* d_attn_l, float* d_attn_r,
-                                     void* stream_) {
+                                     float* d_feat, const float* attn_r, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(feat && d_el && d_er && partials && d_attn_l && d_attn_r && num_nodes >= 0, REGNN_ERR_INVALID_ARG,
                 "attn_scores_bwd: bad argument");
+  REGNN_REQUIRE(d_feat == nullptr || attn_r != nullptr, REGNN_ERR_INVALID_ARG, "attn_scores_bwd: d_feat without attn_r");
   int rc = check_shape("attn_scores_bwd", num_heads, head_dim, 0, false, true);
   if (rc != REGNN_OK) return rc;
-  REGNN_REQUIRE(aligned16(feat), REGNN_ERR_INVALID_ARG, "attn_scores_bwd: 16-byte alignment required");
+  REGNN_REQUIRE(aligned16(feat) && aligned16(d_feat) && aligned16(attn_r), REGNN_ERR_INVALID_ARG,
+                "attn_scores_bwd: 16-byte alignment required");
   AttnArgs a{};
   a.H = num_heads; a.D = head_dim;
   apply_split(a, nullptr, nullptr);
   const int G = rg_lanes(num_heads * head_dim), HD = num_heads * head_dim;
   const int64_t want = (num_nodes * a.hg_count / (32 / G) + kWarpsPerBlock) / kWarpsPerBlock + 1;
-  int nb = (int)(want < 148 * 4 ? want : 148 * 4);
+  int nb = (int)(want < 148 * 8 ? want : 148 * 8);
   if (nb * kWarpsPerBlock < a.hg_count) nb = (a.hg_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const size_t smem = sizeof(float) * kWarpsPerBlock * 256;
 #define REGNN_SCORES_BWD(G_)                                                                                      \
   attn_scores_bwd_kernel<G_><<<nb, kWarpsPerBlock * 32, smem, stream>>>(feat, d_el, d_er, num_nodes, num_heads, head_dim, \
-                                                                       a.d_shift, a.hg_count, partials)
+                                                                       a.d_shift, a.hg_count, partials, d_feat, attn_r)
   switch (G) {
     case 4: REGNN_SCORES_BWD(4); break;
     case 8: REGNN_SCORES_BWD(8); break;

@@ -95,6 +95,9 @@ def propagate(graph, etv, x, theta, alpha, norm, sides=3):
 
 
 class _GatAggregate(torch.autograd.Function):
+    """Fused logits + edge softmax + aggregation with el / er supplied by the caller (bipartite blocks of the MAG stack:
+    the scores come from different node sets)."""
+
     @staticmethod
     def forward(ctx, graph, etv, feat, el, er, theta, alpha, slope, keep, want_attn):
         csr = graph.csr()
@@ -102,6 +105,7 @@ class _GatAggregate(torch.autograd.Function):
         out, rowmax, rowsum, attn = ops.gat_fwd(csr, et, theta if et is not None else None, alpha, feat, el, er,
                                                 slope, keep, want_attn)
         ctx.graph, ctx.et, ctx.alpha, ctx.slope = graph, et, alpha, slope
+        ctx.et_t = etv[1] if etv is not None else None
         ctx.save_for_backward(feat, el, er, theta if et is not None else None, keep, out, rowmax, rowsum)
         if want_attn:
             ctx.mark_non_differentiable(attn)
@@ -112,10 +116,8 @@ class _GatAggregate(torch.autograd.Function):
     def backward(ctx, g, _g_attn=None):
         feat, el, er, theta, keep, out, rowmax, rowsum = ctx.saved_tensors
         csr = ctx.graph.csr()
-        g = g.contiguous()
-        a_csr, dpre_csr, d_er, d_theta = ops.gat_bwd_dst(csr, ctx.et, theta, ctx.alpha, feat, el, er, ctx.slope,
-                                                         keep, out, rowmax, rowsum, g)
-        d_feat, d_el = ops.gat_bwd_src(csr, a_csr, dpre_csr, g)
+        d_feat, d_el, d_er, d_theta, _, _ = ops.gat_bwd(csr, ctx.et, ctx.et_t, theta, ctx.alpha, feat, el, er, ctx.slope,
+                                                        keep, out, rowmax, rowsum, g.contiguous())
         return (None, None, d_feat, d_el, d_er, d_theta.view_as(theta) if d_theta is not None else None,
                 None, None, None, None)
 
@@ -126,8 +128,8 @@ def gat_aggregate(graph, etv, feat, el, er, theta, alpha, slope, keep=None, want
 
 class _GatLayer(torch.autograd.Function):
     """The whole REGAT core of layer/REGATConv.py:68-92 as ONE autograd node: projection scores el / er (one streaming
-    kernel instead of two eager mul + sum pairs), fused logits + edge softmax + aggregation, and a backward whose
-    source-major pass adds the gradient through el / er in its epilogue (no [N,H,D] temporaries from autograd)."""
+    kernel instead of two eager mul + sum pairs), fused logits + edge softmax + aggregation, and a one-gather-pass
+    backward with the gradients through el / er folded into its kernels (no [N,H,D] temporaries from autograd)."""
 
     @staticmethod
     def forward(ctx, graph, etv, feat, attn_l, attn_r, theta, alpha, slope, keep, want_attn):
@@ -138,6 +140,7 @@ class _GatLayer(torch.autograd.Function):
         out, rowmax, rowsum, attn = ops.gat_fwd(csr, et, theta if et is not None else None, alpha, feat, el, er,
                                                 slope, keep, want_attn)
         ctx.graph, ctx.et, ctx.alpha, ctx.slope = graph, et, alpha, slope
+        ctx.et_t = etv[1] if etv is not None else None
         ctx.save_for_backward(feat, el, er, attn_l, attn_r, theta if et is not None else None, keep, out, rowmax, rowsum)
         if want_attn:
             ctx.mark_non_differentiable(attn)
@@ -148,11 +151,9 @@ class _GatLayer(torch.autograd.Function):
     def backward(ctx, g, _g_attn=None):
         feat, el, er, attn_l, attn_r, theta, keep, out, rowmax, rowsum = ctx.saved_tensors
         csr = ctx.graph.csr()
-        g = g.contiguous()
-        a_csr, dpre_csr, d_er, d_theta = ops.gat_bwd_dst(csr, ctx.et, theta, ctx.alpha, feat, el, er, ctx.slope,
-                                                         keep, out, rowmax, rowsum, g)
-        d_feat, d_el = ops.gat_bwd_src(csr, a_csr, dpre_csr, g, attn_l=attn_l, attn_r=attn_r, d_er=d_er)
-        d_al, d_ar = ops.attn_scores_bwd(feat, d_el, d_er)
+        d_feat, _, _, d_theta, d_al, d_ar = ops.gat_bwd(csr, ctx.et, ctx.et_t, theta, ctx.alpha, feat, el, er, ctx.slope,
+                                                        keep, out, rowmax, rowsum, g.contiguous(), attn_l=attn_l,
+                                                        attn_r=attn_r)
         return (None, None, d_feat, d_al.view_as(attn_l), d_ar.view_as(attn_r),
                 d_theta.view_as(theta) if d_theta is not None else None, None, None, None, None)
 

@@ -287,50 +287,51 @@ def gat_fwd(csr, et_csr, theta, alpha, feat, el, er, slope, keep=None, want_attn
     return out, rowmax, rowsum, attn
 
 
-def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowmax, rowsum, g, rows=None):
-    feat, el, er, keep, g = _f32(feat), _f32(el), _f32(er), _f32(keep), _f32(g)
+def gat_bwd(csr, et_csr, et_t, theta, alpha, feat, el, er, slope, keep, out, rowmax, rowsum, g, attn_l=None,
+            attn_r=None, rows=None):
+    """Backward of ``gat_fwd`` as one gather pass (regnn_gat_bwd_stats -> regnn_gat_bwd_edges -> regnn_gat_bwd_reduce)
+    -> (d_feat, d_el, d_er, d_theta | None, d_attn_l | None, d_attn_r | None).
+    With ``attn_l`` / ``attn_r`` ([H*D], the projection-score vectors of layer/REGATConv.py:68-69, el = <feat, attn_l>,
+    er = <feat, attn_r>) the gradients through the scores are folded in: ``d_feat`` is the total feature gradient and
+    the two parameter gradients are returned (regnn_attn_scores_bwd)."""
+    feat, el, er, keep, g, out = _f32(feat), _f32(el), _f32(er), _f32(keep), _f32(g), _f32(out)
     n, h, d = feat.shape
     rb, re = _rows(rows, n)
     theta, et_csr, r = _rel(theta, et_csr)
     dev = feat.device
     e = csr['indices'].numel()
-    a_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]      # never a null pointer, even for E = 0
-    dpre_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
-    d_er = torch.zeros((n, h), dtype=torch.float32, device=dev)
-    partials = torch.empty(max(_lib.partial_blocks(re - rb) * r * h, 1), dtype=torch.float64, device=dev)
-    d_theta = torch.zeros((r, h), dtype=torch.float32, device=dev) if r else None   # stays 0 when the graph has no edges
-    sp, ws = _attn_split(csr.get('split'), h, d, dev)
-    order = row_order(csr) if _full(rb, re, n) else None
-    with torch.cuda.device(dev):
-        _lib.call('regnn_gat_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
-                  _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el), _ptr(er), float(slope), _ptr(keep),
-                  _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dpre_csr),
-                  _ptr(d_er), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _ptr(order), _stream())
-        _lib.count_launches((2 if r else 1) + (sp is not None))
-    return a_csr, dpre_csr, d_er, d_theta
-
-
-def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None, attn_l=None, attn_r=None, d_er=None):
-    """-> (d_feat, d_el).  With ``attn_l`` / ``attn_r`` ([H*D] fp32) and ``d_er`` the gradient through the projection
-    scores is folded into the epilogue: d_feat += d_el (x) attn_l + d_er (x) attn_r."""
-    g = _f32(g)
-    n, h, d = g.shape
-    rb, re = _rows(rows, n)
-    dev = g.device
-    d_feat = torch.empty_like(g) if _full(rb, re, n) else torch.zeros_like(g)
-    d_el = torch.zeros((n, h), dtype=torch.float32, device=dev) if dpre_csr is not None else None
-    sp, ws = _attn_split(csr.get('split_t'), h, d, dev)
-    order = row_order(csr, True) if _full(rb, re, n) else None
+    full = _full(rb, re, n)
     fold = attn_l is not None
     if fold:
-        attn_l, attn_r, d_er = _f32(attn_l).view(-1), _f32(attn_r).view(-1), _f32(d_er)
+        attn_l, attn_r = _f32(attn_l).view(-1), _f32(attn_r).view(-1)
+    stats = torch.empty((n, h, 4), dtype=torch.float32, device=dev)
+    dpre_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
+    d_feat = torch.empty_like(g) if full else torch.zeros_like(g)
+    d_el = torch.zeros((n, h), dtype=torch.float32, device=dev)
+    d_er = torch.zeros((n, h), dtype=torch.float32, device=dev)
+    partials = torch.empty(max(_lib.partial_blocks(n) * max(r * h, 2 * h * d if fold else 0), 1), dtype=torch.float64,
+                           device=dev)
+    d_theta = torch.zeros((r, h), dtype=torch.float32, device=dev) if r else None   # stays 0 when the graph has no edges
+    sp_t, ws_t = _attn_split(csr.get('split_t'), h, d, dev)
+    sp, ws = _attn_split(csr.get('split'), h, 0, dev)
     with torch.cuda.device(dev):
-        _lib.call('regnn_gat_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
-                  _ptr(a_csr), _ptr(dpre_csr), _ptr(g), h, d, rb, re, _ptr(d_feat), _ptr(d_el),
-                  _ptr(attn_l) if fold else None, _ptr(attn_r) if fold else None, _ptr(d_er) if fold else None,
-                  sp, _ptr(ws), _ptr(order), _stream())
-        _lib.count_launches(1 + ((2 + fold) if sp is not None else 0))
-    return d_feat, d_el
+        _lib.call('regnn_gat_bwd_stats', _ptr(out), _ptr(g), _ptr(er), _ptr(rowmax), _ptr(rowsum), n, h, d, _ptr(stats),
+                  _stream())
+        _lib.call('regnn_gat_bwd_edges', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
+                  _ptr(et_t) if r else None, _ptr(csr['eid']), _ptr(theta), float(alpha), r, _ptr(feat), _ptr(el),
+                  _ptr(stats), float(slope), _ptr(keep), _ptr(g), h, d, rb, re, _ptr(d_feat), _ptr(d_el), _ptr(dpre_csr),
+                  _ptr(attn_l) if fold else None, sp_t, _ptr(ws_t), _ptr(row_order(csr, True)) if full else None, _stream())
+        _lib.call('regnn_gat_bwd_reduce', _ptr(csr['indptr']), _ptr(et_csr) if r else None, _ptr(theta), float(alpha), r,
+                  _ptr(dpre_csr), h, rb, re, _ptr(d_er), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _stream())
+        _lib.count_launches(3 + (2 if r else 0) + (3 if sp_t is not None else 0) + (sp is not None))
+        d_al = d_ar = None
+        if fold:
+            d_al = torch.empty(h * d, dtype=torch.float32, device=dev)
+            d_ar = torch.empty(h * d, dtype=torch.float32, device=dev)
+            _lib.call('regnn_attn_scores_bwd', _ptr(feat), _ptr(d_el), _ptr(d_er), n, h, d, _ptr(partials), _ptr(d_al),
+                      _ptr(d_ar), _ptr(d_feat), _ptr(attn_r), _stream())
+            _lib.count_launches(3)
+    return d_feat, d_el, d_er, d_theta, d_al, d_ar
 
 
 def attn_scores_fwd(feat, attn_l, attn_r):
@@ -344,21 +345,6 @@ def attn_scores_fwd(feat, attn_l, attn_r):
         _lib.call('regnn_attn_scores_fwd', _ptr(feat), _ptr(attn_l), _ptr(attn_r), n, h, d, _ptr(el), _ptr(er), _stream())
         _lib.count_launches(1)
     return el, er
-
-
-def attn_scores_bwd(feat, d_el, d_er):
-    """-> (d_attn_l[H*D], d_attn_r[H*D]) (regnn_attn_scores_bwd)."""
-    feat, d_el, d_er = _f32(feat), _f32(d_el), _f32(d_er)
-    n, h, d = feat.shape
-    dev = feat.device
-    partials = torch.empty(_lib.partial_blocks(n) * 2 * h * d, dtype=torch.float64, device=dev)
-    d_al = torch.empty(h * d, dtype=torch.float32, device=dev)
-    d_ar = torch.empty(h * d, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.call('regnn_attn_scores_bwd', _ptr(feat), _ptr(d_el), _ptr(d_er), n, h, d, _ptr(partials), _ptr(d_al),
-                  _ptr(d_ar), _stream())
-        _lib.count_launches(3)
-    return d_al, d_ar
 
 
 def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_attn=False, rows=None):

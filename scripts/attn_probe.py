@@ -63,15 +63,20 @@ b_gat_bwd_dst = e * (4 * HD + 4 * H + 5) + n * (4 * HD + 12 * H) + 2 * 4 * e * H
 b_gat_bwd_src = e * (4 * HD + 4 * H + 4 + 4) + n * (4 * HD + 4 * H) + 4 * e * H
 b_v2_fwd = e * (4 * HD + 4 + 1) + n * (2 * 4 * HD + 8 * H + 4) + 4 * HD
 out, rowmax, rowsum, _ = ops.gat_fwd(csr, etv[0], theta, 100.0, feat, el, er, 0.2)
-a_csr, dpre, d_er, d_th = ops.gat_bwd_dst(csr, etv[0], theta, 100.0, feat, el, er, 0.2, None, out, rowmax, rowsum, gout)
 t('gat_fwd', lambda: ops.gat_fwd(csr, etv[0], theta, 100.0, feat, el, er, 0.2), b_gat_fwd)
-t('gat_bwd_dst', lambda: ops.gat_bwd_dst(csr, etv[0], theta, 100.0, feat, el, er, 0.2, None, out, rowmax, rowsum, gout),
-  b_gat_bwd_dst)
-t('gat_bwd_src', lambda: ops.gat_bwd_src(csr, a_csr, dpre, gout), b_gat_bwd_src)
-t('gat_bwd_src (+score fold)', lambda: ops.gat_bwd_src(csr, a_csr, dpre, gout, attn_l=al, attn_r=ar, d_er=d_er), b_gat_bwd_src)
-d_el = ops.gat_bwd_src(csr, a_csr, dpre, gout)[1]
+# one-gather-pass backward: stats (2 N HD reads) + edges (E x (4HD + 16H + 9 + 4H write)) + reduce (2 x 4EH reads)
+b_gat_bwd = n * (2 * 4 * HD + 16 * H) + e * (4 * HD + 16 * H + 9 + 4 * H) + n * 2 * 4 * HD + 2 * 4 * e * H
+t('gat_bwd (stats+edges+reduce)', lambda: ops.gat_bwd(csr, etv[0], etv[1], theta, 100.0, feat, el, er, 0.2, None, out,
+                                                       rowmax, rowsum, gout), b_gat_bwd)
+t('gat_bwd (+score gradients)', lambda: ops.gat_bwd(csr, etv[0], etv[1], theta, 100.0, feat, el, er, 0.2, None, out,
+                                                     rowmax, rowsum, gout, attn_l=al, attn_r=ar), b_gat_bwd + n * 3 * 4 * HD)
 t('attn_scores_fwd', lambda: ops.attn_scores_fwd(feat, al, ar), n * (4 * HD + 8 * H))
-t('attn_scores_bwd', lambda: ops.attn_scores_bwd(feat, d_el, d_er), n * (4 * HD + 8 * H))
+if not once:
+    from re_gnn_b200 import _lib
+    with _lib.Trace() as tr:
+        for _ in range(5):
+            ops.gat_bwd(csr, etv[0], etv[1], theta, 100.0, feat, el, er, 0.2, None, out, rowmax, rowsum, gout, attn_l=al, attn_r=ar)
+    print('  per ABI call (ms):', {k: round(v, 3) for k, v in tr.summary(5).items()})
 o2, m2, s2, _ = ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2)
 a2, dl2, _, _, _ = ops.gatv2_bwd_dst(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, gout)
 t('gatv2_fwd', lambda: ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2), b_v2_fwd)

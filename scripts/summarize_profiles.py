@@ -29,6 +29,9 @@ METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.
            'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
            'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
            'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+           'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+           'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+           'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
            'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
 
 
@@ -61,10 +64,16 @@ def launches(tag):
 
 
 def full(tag, rep):
+    """From gpurun_out/<tag>_<rep>.ncu-rep, or from gpurun_out/<tag>_<rep>_raw.csv when the report was exported with
+    `ncu -i ... --page raw --csv` on the GPU box (gpurun_out is capped at 64 MiB, a source-level report is larger)."""
     src = os.path.join(OUT, '%s_%s.ncu-rep' % (tag, rep))
-    if not os.path.exists(src):
+    pre = os.path.join(OUT, '%s_%s_raw.csv' % (tag, rep))
+    if os.path.exists(src):
+        raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    elif os.path.exists(pre):
+        raw = open(pre).read()
+    else:
         return
-    raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(os.path.join(PROF, '%s_%s_metrics.md' % (tag, rep)), 'w') as f:

@@ -202,37 +202,33 @@ def gat_fwd(csr, et_csr, theta, alpha, feat, el, er, slope, keep=None, want_attn
     return out, mx, sm, (_to_edge_order(at, csr) if want_attn else None)
 
 
-def gat_bwd_dst(csr, et_csr, theta, alpha, feat, el, er, slope, keep, out, rowmax, rowsum, g, rows=None):
+def gat_bwd(csr, et_csr, et_t, theta, alpha, feat, el, er, slope, keep, out, rowmax, rowsum, g, attn_l=None,
+            attn_r=None, rows=None):
     feat, g, out = feat.detach(), g.detach(), out.detach()
     row, col = csr['row'].long(), csr['indices'].long()
     pre, l = _gat_logits(csr, et_csr, theta, alpha, el, er, slope)
-    a = torch.exp(l - rowmax[row]) / rowsum[row]
+    sm = rowsum[row]
+    a = torch.exp(l - rowmax[row]) * torch.where(sm > 0, 1.0 / sm, torch.zeros_like(sm))
     kc = _keep_csr(keep, csr)
     at = a if kc is None else a * kc
     da = (feat[col] * g[row]).sum(-1)
     S = (out * g).sum(-1)
     dpre = (at * da - a * S[row]) * _lgrad(pre, slope)
     d_er = torch.zeros_like(rowmax).index_add(0, row, dpre)
+    d_el = torch.zeros_like(rowmax).index_add(0, col, dpre)
+    d_feat = torch.zeros_like(g).index_add(0, col, at[:, :, None] * g[row])
     d_theta = None
     if theta is not None and et_csr is not None:
         th = theta.detach()
         dw = torch.zeros_like(th).index_add(0, et_csr.long(), dpre)
         d_theta = dw * alpha * _lgrad(th * alpha, SLOPE)
-    return at, dpre, d_er, d_theta
-
-
-def gat_bwd_src(csr, a_csr, dpre_csr, g, rows=None, attn_l=None, attn_r=None, d_er=None):
-    g = g.detach()
-    src = _rows_of(csr['indptr_t'])
-    dstn, slot = csr['indices_t'].long(), csr['slot_t'].long()
-    d_feat = torch.zeros_like(g).index_add(0, src, a_csr[slot][:, :, None] * g[dstn])
-    d_el = None
-    if dpre_csr is not None:
-        d_el = torch.zeros((g.shape[0], g.shape[1]), dtype=g.dtype).index_add(0, src, dpre_csr[slot])
-    if attn_l is not None:      # epilogue fold: gradient through el = <feat, attn_l>, er = <feat, attn_r>
+    d_al = d_ar = None
+    if attn_l is not None:      # gradients through el = <feat, attn_l>, er = <feat, attn_r>
         h, d = g.shape[1], g.shape[2]
         d_feat = d_feat + d_el[:, :, None] * attn_l.detach().view(1, h, d) + d_er[:, :, None] * attn_r.detach().view(1, h, d)
-    return d_feat, d_el
+        d_al = (d_el[:, :, None] * feat).sum(0).reshape(-1)
+        d_ar = (d_er[:, :, None] * feat).sum(0).reshape(-1)
+    return d_feat, d_el, d_er, d_theta, d_al, d_ar
 
 
 def attn_scores_fwd(feat, attn_l, attn_r):
@@ -241,9 +237,6 @@ def attn_scores_fwd(feat, attn_l, attn_r):
     return (f * attn_l.detach().view(1, h, d)).sum(-1), (f * attn_r.detach().view(1, h, d)).sum(-1)
 
 
-def attn_scores_bwd(feat, d_el, d_er):
-    f = feat.detach()
-    return (d_el[:, :, None] * f).sum(0).reshape(-1), (d_er[:, :, None] * f).sum(0).reshape(-1)
 
 
 def _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope):
@@ -314,6 +307,6 @@ def install(monkeypatch):
     monkeypatch.setattr(sampling.SaintRandomWalkSampler, 'walks', saint_walks)
     monkeypatch.setattr(G.Graph, 'csr', graph_csr)
     monkeypatch.setattr(G.Graph, 'etype_views', graph_etype_views)
-    for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'spmm_bwd_fused', 'rowdot_norm_bwd', 'gat_fwd', 'gat_bwd_dst',
-                 'gat_bwd_src', 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src', 'attn_scores_fwd', 'attn_scores_bwd'):
+    for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'spmm_bwd_fused', 'rowdot_norm_bwd', 'gat_fwd', 'gat_bwd',
+                 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src', 'attn_scores_fwd'):
         monkeypatch.setattr(ops, name, globals()[name])
