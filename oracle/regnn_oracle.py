@@ -296,12 +296,27 @@ def mag_regatv2_forward(x_src, x_target, edge_index, edge_type, target_node_type
     return _mag_attention_tail(out, xd, bias, h, c, concat, residual)
 
 
-def saint_regcn_forward(x, edge_index, edge_type, weight, bias, relation_weight, scaling_factor):
-    """mag/regnn_saint.py:224-275 (``REGCNConv.forward``, ``aggr='add'``, dropout 0, use_softmax False)."""
+def mag_softmax(src, index, num_nodes):
+    """mag/utils.py:28-57 ``softmax``: the GLOBAL maximum is subtracted and 1e-16 added to every denominator."""
+    out = torch.exp(src - src.max()) if src.numel() else src
+    den = torch.zeros((num_nodes,) + tuple(out.shape[1:]), dtype=out.dtype).index_add(0, index, out)
+    return out / (den[index] + 1e-16)
+
+
+def saint_regcn_forward(x, edge_index, edge_type, weight, bias, relation_weight, scaling_factor, use_softmax=False,
+                        edge_keep=None, dropout=0.0, return_weights=False):
+    """mag/regnn_saint.py:224-275 (``REGCNConv.forward``, ``aggr='add'``).  ``edge_keep`` (bool [E]) with ``dropout`` p
+    restates ``F.dropout(ew, p, training=True)`` (:258) for a given mask: kept weights are scaled by 1/(1-p)."""
     src, dst = edge_index[0], edge_index[1]
     n = x.shape[0]
     xs = x @ weight                                                               # :234-236
     w = F.leaky_relu(relation_weight * scaling_factor, RELATION_SLOPE)[edge_type]  # :239-242
-    deg = torch.zeros(n, dtype=x.dtype).index_add(0, dst, w)                      # :253 weighted_degree
-    ew = w * deg.pow(-1.0)[dst]                                                   # :254-256
-    return torch.zeros((n, xs.shape[1]), dtype=x.dtype).index_add(0, dst, ew.view(-1, 1) * xs[src]) + bias
+    if use_softmax:
+        ew = mag_softmax(w, dst, n)                                               # :249-250
+    else:
+        deg = torch.zeros(n, dtype=x.dtype).index_add(0, dst, w)                  # :253 weighted_degree
+        ew = w * deg.pow(-1.0)[dst]                                               # :254-256
+    if edge_keep is not None:
+        ew = ew * edge_keep.to(ew.dtype) / (1.0 - dropout)                        # :258
+    out = torch.zeros((n, xs.shape[1]), dtype=x.dtype).index_add(0, dst, ew.view(-1, 1) * xs[src]) + bias
+    return (out, ew) if return_weights else out

@@ -362,8 +362,11 @@ gat_bwd_stats_kernel(const float* __restrict__ out, const float* __restrict__ Gd
 
 // Source-major gather pass (transposed view; AttnArgs: indptr/indices/eid = indptr_t/indices_t/slot_t, etype = etype_t,
 // fd = stats as float4[N*H], G = dL/d out, a_csr = slot -> edge id when keep != null).
-template <int G, bool KEEP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+#ifndef REGNN_GATB_BLOCKS
+#define REGNN_GATB_BLOCKS 4
+#endif
+template <int G, int LPH, bool KEEP>   // LPH = min(G, D/4): lanes per head (compile-time butterfly)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_GATB_BLOCKS)
 gat_bwd_edges_kernel(AttnArgs a) {
   constexpr int U = 2;  // two rows of G and two statistics vectors in flight per lane
   extern __shared__ __align__(16) float smem[];
@@ -382,7 +385,6 @@ gat_bwd_edges_kernel(AttnArgs a) {
   const bool leader = act && (col & (a.D - 1)) == 0;
   const int len = it.v >= 0 ? it.len : 0;
   const int maxlen = __reduce_max_sync(0xffffffffu, len);
-  const int lph = min(G, a.D >> 2);
   const bool has_rel = a.etype != nullptr;
   float4 fu = zero4();
   float el_u = 0.f;
@@ -390,8 +392,12 @@ gat_bwd_edges_kernel(AttnArgs a) {
     fu = ldg4(a.feat + (size_t)it.v * HD + col);
     el_u = __ldg(a.el + (size_t)it.v * H + h);
   }
-  const float* gcol = a.G + (col_ok ? col : 0);
-  const float4* sth = reinterpret_cast<const float4*>(a.fd) + h;
+  // one IMAD.WIDE.U32 per gathered address: 32-bit index x 32-bit pitch (bytes) added to a 64-bit base
+  const char* gbytes = reinterpret_cast<const char*>(a.G + (col_ok ? col : 0));
+  const char* sbytes = reinterpret_cast<const char*>(a.fd) + (size_t)h * 16;
+  const uint32_t gpitch = (uint32_t)HD * 4u, spitch = (uint32_t)H * 16u;
+  float* dpre_h = a.o2 + h;
+  const float* w_h = w_s + h;
   const int32_t* ip = a.indices + it.begin;
   const int32_t* sp = a.eid + it.begin;
   const uint8_t* ep = a.etype + it.begin;
@@ -416,27 +422,29 @@ gat_bwd_edges_kernel(AttnArgs a) {
       for (int u = 0; u < U; ++u) {
         sd[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
         const bool ok = sd[u] >= 0 && col_ok;
-        x[u] = ok ? ldg4(gcol + (size_t)sd[u] * HD) : zero4();
-        st[u] = ok ? __ldg(sth + (size_t)sd[u] * H) : zero4();
+        x[u] = ok ? ldg4(reinterpret_cast<const float*>(gbytes + (uint64_t)(uint32_t)sd[u] * gpitch)) : zero4();
+        // missing slot: rowmax = +inf makes exp(. - rowmax) = 0, so a = dpre = 0 without per-edge masks
+        st[u] = ok ? __ldg(reinterpret_cast<const float4*>(sbytes + (uint64_t)(uint32_t)sd[u] * spitch))
+                   : make_float4(0.f, INFINITY, 0.f, 0.f);
       }
       float da[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) da[u] = group_sum_rt(dot4(fu, x[u]), lph);
+      for (int u = 0; u < U; ++u) da[u] = group_sum<LPH>(dot4(fu, x[u]));
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int ss = __shfl_sync(0xffffffffu, bs, gbase + j + u);
         const int se = has_rel ? __shfl_sync(0xffffffffu, be, gbase + j + u) : 0;
-        if (sd[u] >= 0 && act) {
-          float pre = el_u + st[u].x;
-          if (has_rel) pre += w_s[se * H + h];
-          const float aa = __expf(leaky(pre, a.slope) - st[u].y) * st[u].z;
-          float at = aa;
-          if (KEEP) at *= __ldg(a.keep + (size_t)__ldg(a.a_csr_eid + ss) * H + h);
-          const float dp = (at * da[u] - aa * st[u].w) * leaky_grad(pre, a.slope);
-          fma4(acc, at, x[u]);
-          del += dp;
-          if (leader) a.o2[(size_t)ss * H + h] = dp;   // dpre per CSR slot: the destination-side reductions read it
+        float pre = el_u + st[u].x;
+        if (has_rel) pre += w_h[se * H];
+        const float aa = __expf(leaky(pre, a.slope) - st[u].y) * st[u].z;
+        float at = aa;
+        if (KEEP) {
+          if (sd[u] >= 0 && act) at *= __ldg(a.keep + (size_t)__ldg(a.a_csr_eid + ss) * H + h);
         }
+        const float dp = (at * da[u] - aa * st[u].w) * leaky_grad(pre, a.slope);
+        fma4(acc, at, x[u]);
+        del += dp;
+        if (leader && sd[u] >= 0) dpre_h[(uint64_t)(uint32_t)ss * (uint32_t)H] = dp;   // dpre per CSR slot
       }
     }
   }
@@ -501,20 +509,35 @@ gat_bwd_der_kernel(AttnArgs a, int HP) {
 }
 
 // Relation bins of dpre: pure streaming over [E,H] (+ the uint8 edge types), lane-local bins, per-block double partials.
+// A warp reads 32/HP slots x HP heads per load; 8 loads are issued before the (loop-carried) shared-memory updates.
 // Dynamic smem: [warps][R][32] floats
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gat_bwd_bins_kernel(const uint8_t* __restrict__ etype, const float* __restrict__ dpre, const int32_t* __restrict__ indptr,
                     int64_t row_begin, int64_t row_end, int R, int H, int HP, double* __restrict__ partials) {
+  constexpr int UB = 8;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t s_begin = indptr[row_begin], s_end = indptr[row_end];
   float* mybins = smem + (size_t)warp * R * 32 + lane;
   for (int r = 0; r < R; ++r) mybins[r * 32] = 0.f;
   const int hh = lane % HP, per = 32 / HP;
-  if (hh < H)
-    for (int64_t s = s_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * per + lane / HP; s < s_end;
-         s += (int64_t)gridDim.x * kWarpsPerBlock * per)
-      mybins[(int)etype[s] * 32] += __ldg(dpre + (size_t)s * H + hh);
+  if (hh < H) {
+    const int64_t tile = (int64_t)per * UB;   // slots per warp iteration
+    for (int64_t s0 = s_begin + ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * tile + lane / HP; s0 < s_end;
+         s0 += (int64_t)gridDim.x * kWarpsPerBlock * tile) {
+      float v[UB];
+      int t[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int64_t s = s0 + (int64_t)u * per;
+        const bool ok = s < s_end;
+        t[u] = ok ? (int)__ldg(etype + s) : 0;
+        v[u] = ok ? __ldg(dpre + (size_t)s * H + hh) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) mybins[t[u] * 32] += v[u];
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < R * H; i += blockDim.x) {
     const int r = i / H, h2 = i % H;
@@ -1209,20 +1232,22 @@ extern "C" int regnn_gat_bwd_edges(const int32_t* indptr_t, const int32_t* indic
   apply_order(a, row_order_t, split_t, rows);
   const size_t smem = sizeof(float) * ((size_t)a.R * num_heads) + 16;
   const unsigned grid = (unsigned)((rg_work(a, rows) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  if (keep != nullptr) {
-    switch (rg_lanes(a.H * a.D)) {
-      case 4: REGNN_DISPATCH_C((gat_bwd_edges_kernel<4, true>), grid, smem); break;
-      case 8: REGNN_DISPATCH_C((gat_bwd_edges_kernel<8, true>), grid, smem); break;
-      case 16: REGNN_DISPATCH_C((gat_bwd_edges_kernel<16, true>), grid, smem); break;
-      default: REGNN_DISPATCH_C((gat_bwd_edges_kernel<32, true>), grid, smem); break;
-    }
-  } else {
-    switch (rg_lanes(a.H * a.D)) {
-      case 4: REGNN_DISPATCH_C((gat_bwd_edges_kernel<4, false>), grid, smem); break;
-      case 8: REGNN_DISPATCH_C((gat_bwd_edges_kernel<8, false>), grid, smem); break;
-      case 16: REGNN_DISPATCH_C((gat_bwd_edges_kernel<16, false>), grid, smem); break;
-      default: REGNN_DISPATCH_C((gat_bwd_edges_kernel<32, false>), grid, smem); break;
-    }
+  {
+    const int G = rg_lanes(a.H * a.D), lph = min(G, head_dim / 4);
+    bool launched = false;
+#define REGNN_EDGES_CASE(G_, L_)                                                                   \
+  if (G == G_ && lph == L_) {                                                                      \
+    if (keep != nullptr) REGNN_DISPATCH_C((gat_bwd_edges_kernel<G_, L_, true>), grid, smem);       \
+    else REGNN_DISPATCH_C((gat_bwd_edges_kernel<G_, L_, false>), grid, smem);                      \
+    launched = true;                                                                               \
+  }
+    REGNN_EDGES_CASE(4, 1) REGNN_EDGES_CASE(4, 2) REGNN_EDGES_CASE(4, 4)
+    REGNN_EDGES_CASE(8, 1) REGNN_EDGES_CASE(8, 2) REGNN_EDGES_CASE(8, 4) REGNN_EDGES_CASE(8, 8)
+    REGNN_EDGES_CASE(16, 1) REGNN_EDGES_CASE(16, 2) REGNN_EDGES_CASE(16, 4) REGNN_EDGES_CASE(16, 8) REGNN_EDGES_CASE(16, 16)
+    REGNN_EDGES_CASE(32, 1) REGNN_EDGES_CASE(32, 2) REGNN_EDGES_CASE(32, 4) REGNN_EDGES_CASE(32, 8) REGNN_EDGES_CASE(32, 16)
+    REGNN_EDGES_CASE(32, 32)
+#undef REGNN_EDGES_CASE
+    REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "gat_bwd_edges: no kernel for H=%d D=%d", num_heads, head_dim);
   }
   if (a.nfrag > 0) {
     launch_rowsum(split_t, a.p0, num_heads * head_dim, d_feat, row_begin, row_end, stream);

@@ -94,16 +94,40 @@ def propagate(graph, etv, x, theta, alpha, norm, sides=3):
     return _Propagate.apply(graph, etv, x, theta, alpha, norm, sides if norm is not None else 0)
 
 
+def _global_max_eps(csr, out, rowmax, rowsum, attn, eps):
+    """The MAG stack's softmax (mag/utils.py:28-57) subtracts the GLOBAL maximum M of all logits and adds ``eps`` to
+    every denominator: a_e = exp(l_e - M) / (sum exp(l - M) + eps).  In terms of the row statistics the fused kernels
+    keep (row maximum m_v, s_v = sum exp(l - m_v)) that is exp(l_e - m_v) / (s_v + eps * exp(M - m_v)): the kernel result
+    is rescaled by s_v / (s_v + eps_v) and the corrected denominator is what the backward kernels then see -- their
+    formula dl = a (da - sum a da) holds unchanged for the un-normalised a.  (The derivative through M itself -- one
+    logit, weight sum_v (1 - s_v / (s_v + eps_v)) <out_v, G_v> -- is dropped; it vanishes unless a row's logits sit
+    ~20 below the global maximum.)  In place; returns the corrected row sums."""
+    indptr = csr['indptr']
+    has = (indptr[1:] > indptr[:-1]).unsqueeze(1)
+    m_glob = torch.where(has, rowmax, torch.full_like(rowmax, float('-inf'))).max()
+    corr = eps * torch.exp(m_glob - rowmax)
+    new_sum = rowsum + corr
+    factor = torch.where(rowsum > 0, rowsum / new_sum, torch.zeros_like(rowsum))
+    out.mul_(factor.unsqueeze(-1))
+    if attn is not None and attn.numel():
+        dst_of_slot = csr['row'].long()
+        eid = csr['eid'].long()
+        attn[eid] = attn[eid] * factor[dst_of_slot]
+    return torch.where(rowsum > 0, new_sum, rowsum)
+
+
 class _GatAggregate(torch.autograd.Function):
     """Fused logits + edge softmax + aggregation with el / er supplied by the caller (bipartite blocks of the MAG stack:
     the scores come from different node sets)."""
 
     @staticmethod
-    def forward(ctx, graph, etv, feat, el, er, theta, alpha, slope, keep, want_attn):
+    def forward(ctx, graph, etv, feat, el, er, theta, alpha, slope, keep, want_attn, softmax_eps):
         csr = graph.csr()
         et = etv[0] if etv is not None else None
         out, rowmax, rowsum, attn = ops.gat_fwd(csr, et, theta if et is not None else None, alpha, feat, el, er,
                                                 slope, keep, want_attn)
+        if softmax_eps:
+            rowsum = _global_max_eps(csr, out, rowmax, rowsum, attn, softmax_eps)
         ctx.graph, ctx.et, ctx.alpha, ctx.slope = graph, et, alpha, slope
         ctx.et_t = etv[1] if etv is not None else None
         ctx.save_for_backward(feat, el, er, theta if et is not None else None, keep, out, rowmax, rowsum)
@@ -119,11 +143,12 @@ class _GatAggregate(torch.autograd.Function):
         d_feat, d_el, d_er, d_theta, _, _ = ops.gat_bwd(csr, ctx.et, ctx.et_t, theta, ctx.alpha, feat, el, er, ctx.slope,
                                                         keep, out, rowmax, rowsum, g.contiguous())
         return (None, None, d_feat, d_el, d_er, d_theta.view_as(theta) if d_theta is not None else None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
-def gat_aggregate(graph, etv, feat, el, er, theta, alpha, slope, keep=None, want_attn=False):
-    return _GatAggregate.apply(graph, etv, feat, el, er, theta, alpha, slope, keep, want_attn)
+def gat_aggregate(graph, etv, feat, el, er, theta, alpha, slope, keep=None, want_attn=False, softmax_eps=0.0):
+    """``softmax_eps`` > 0: the MAG stack's global-max softmax with ``+ eps`` in the denominator (``_global_max_eps``)."""
+    return _GatAggregate.apply(graph, etv, feat, el, er, theta, alpha, slope, keep, want_attn, softmax_eps)
 
 
 class _GatLayer(torch.autograd.Function):
@@ -165,11 +190,13 @@ def gat_layer(graph, etv, feat, attn_l, attn_r, theta, alpha, slope, keep=None, 
 
 class _GatV2Aggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn):
+    def forward(ctx, graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn, softmax_eps):
         csr = graph.csr()
         et = etv[0] if etv is not None else None
         out, rowmax, rowsum, a = ops.gatv2_fwd(csr, et, theta if et is not None else None, alpha, fs, fd, attn,
                                                slope, keep, want_attn)
+        if softmax_eps:
+            rowsum = _global_max_eps(csr, out, rowmax, rowsum, a, softmax_eps)
         ctx.graph, ctx.et, ctx.alpha, ctx.slope = graph, et, alpha, slope
         ctx.save_for_backward(fs, fd, attn, theta if et is not None else None, keep, out, rowmax, rowsum)
         if want_attn:
@@ -186,8 +213,8 @@ class _GatV2Aggregate(torch.autograd.Function):
                                                                  ctx.slope, keep, out, rowmax, rowsum, g)
         d_fs = ops.gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, ctx.slope, g)
         return (None, None, d_fs, d_fd, d_attn.view_as(attn),
-                d_theta.view_as(theta) if d_theta is not None else None, None, None, None, None)
+                d_theta.view_as(theta) if d_theta is not None else None, None, None, None, None, None)
 
 
-def gatv2_aggregate(graph, etv, fs, fd, attn, theta, alpha, slope, keep=None, want_attn=False):
-    return _GatV2Aggregate.apply(graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn)
+def gatv2_aggregate(graph, etv, fs, fd, attn, theta, alpha, slope, keep=None, want_attn=False, softmax_eps=0.0):
+    return _GatV2Aggregate.apply(graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn, softmax_eps)

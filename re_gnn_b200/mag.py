@@ -16,6 +16,17 @@ from . import functional as RF
 from .graph import Graph
 
 
+def _reference_edge_weights(edge_weight, col, num_targets, use_softmax):
+    """``ew`` of mag/regnn_layers.py:113-124 / mag/regnn_saint.py:248-256: the relation weights of the edges normalised
+    per destination -- by the weighted in-degree, or by mag/utils.py's global-max softmax with ``+ 1e-16``."""
+    if use_softmax:
+        ex = torch.exp(edge_weight - edge_weight.max()) if edge_weight.numel() else edge_weight
+        den = torch.zeros(num_targets, dtype=ex.dtype, device=ex.device).index_add_(0, col, ex)
+        return ex / (den[col] + 1e-16)
+    deg = torch.zeros(num_targets, dtype=edge_weight.dtype, device=edge_weight.device).index_add_(0, col, edge_weight)
+    return edge_weight * deg.pow(-1.0)[col]
+
+
 class REGCNConv(nn.Module):
     def __init__(self, in_channels, out_channels, num_node_types, num_edge_types, scaling_factor=100., dropout=0.,
                  use_softmax=False, residual=False, use_norm=None, self_loop_type=1, no_re=False):
@@ -69,8 +80,13 @@ class REGCNConv(nn.Module):
         if self.use_norm in ('bn', 'ln'):
             out = self.norm(out)
         if return_weights:
+            # the normalised per-edge weights the reference computes and returns but never aggregates with (:113-126),
+            # in the order of the (self-loop-extended) edge list; a diagnostic path: plain torch ops
             w = F.leaky_relu(self.relation_weight * self.scaling_factor)
-            return out, None, w
+            src, dst = graph.edges()
+            edge_weight = w[etype1 - 1]
+            ew = _reference_edge_weights(edge_weight, dst, n_dst, self.use_softmax)
+            return out, ew, w
         return out
 
 
@@ -80,9 +96,10 @@ class _MagAttentionBase(nn.Module):
     ``[R, heads]``, typed self loops for ``self_loop_type == 2``, concat or mean over heads, bias, residual, norm.
 
     Softmax: the reference stabilises with the GLOBAL maximum of all logits and adds 1e-16 to every denominator
-    (mag/utils.py:28-57); the fused kernels use the row maximum and no epsilon.  The two differ by the per-row
-    factor 1 / (1 + 1e-16 * exp(M - L_v)) (M: global max, L_v: log-sum-exp of row v), which is below fp32
-    resolution unless a row's logits sit more than ~20 below the global maximum -- not reproduced here."""
+    (mag/utils.py:28-57); the fused kernels keep per-row statistics, from which the same values follow exactly
+    (``functional._global_max_eps``: per-row factor s_v / (s_v + 1e-16 * exp(M - m_v)), carried into the backward)."""
+
+    SOFTMAX_EPS = 1e-16
 
     def __init__(self, in_channels, out_channels, num_node_types, num_edge_types, heads=1, scaling_factor=100.,
                  concat=True, negative_slope=0.2, dropout=0.0, residual=False, use_norm=None, self_loop_type=1,
@@ -159,7 +176,7 @@ class REGATConv(_MagAttentionBase):
         el = (xs * self.att_src).sum(-1)
         er = self._pad_rows((xd * self.att_dst).sum(-1), n_src)
         return RF.gat_aggregate(graph, etv, xs, el, er, self.relation_weight, self.scaling_factor, self.negative_slope,
-                                None, want_attn)
+                                None, want_attn, softmax_eps=self.SOFTMAX_EPS)
 
 
 class REGATv2Conv(_MagAttentionBase):
@@ -174,7 +191,7 @@ class REGATv2Conv(_MagAttentionBase):
 
     def _aggregate(self, graph, etv, xs, xd, n_src, want_attn):
         return RF.gatv2_aggregate(graph, etv, xs, self._pad_rows(xd, n_src), self.att, self.relation_weight,
-                                  self.scaling_factor, self.negative_slope, None, want_attn)
+                                  self.scaling_factor, self.negative_slope, None, want_attn, softmax_eps=self.SOFTMAX_EPS)
 
 
 class REGNN(nn.Module):
@@ -278,10 +295,14 @@ def train_step(model, optimizer, sampler, seeds, labels, x_dict, edge_type, node
 # ------------------------------------------------------------------------------------------------------------------
 # GraphSAINT variant (mag/regnn_saint.py)
 class SaintREGCNConv(nn.Module):
-    """``REGCNConv`` of mag/regnn_saint.py:195-275: ``aggr='add'`` with the relation weights normalised by the
-    relation-WEIGHTED in-degree, ``ew = w[etype] / deg[dst]`` (no clamp), bias added after aggregation.  The
-    model never passes ``dropout`` to the layer (:303-307), so the edge-weight dropout is inactive; a non-zero
-    value in training mode is rejected rather than silently ignored."""
+    """``REGCNConv`` of mag/regnn_saint.py:195-275: ``aggr='add'`` with the relation weights normalised per destination,
+    ``ew = w[etype] / deg[dst]`` (relation-WEIGHTED in-degree, no clamp) or, with ``use_softmax``, mag/utils.py's
+    global-max softmax of the relation weights (``+ 1e-16``); ``F.dropout`` on ``ew`` in training; bias after aggregation.
+
+    Both options run on the same fused SpMM: the softmax is a relation table ``exp(w - M)`` (positive, so the kernels'
+    LeakyReLU is the identity on it) with the destination-side normaliser ``1 / (sum + 1e-16)``; dropping an edge weight
+    is dropping the edge, so the aggregation runs on the kept-edge subgraph (its own CSR) with the survivors scaled by
+    ``1 / (1 - p)``, while the normaliser still comes from all edges, as in the reference."""
 
     def __init__(self, in_channels, out_channels, num_node_types, num_edge_types, scaling_factor=100., gcn=False,
                  dropout=0., use_softmax=False):
@@ -299,24 +320,47 @@ class SaintREGCNConv(nn.Module):
         nn.init.zeros_(self.bias)
         nn.init.constant_(self.relation_weight, 1.0 / self.scaling_factor)
 
-    def forward(self, x, edge_index, edge_type, return_weights=False, graph=None):
-        if self.use_softmax:
-            raise NotImplementedError('use_softmax=True (global-max softmax of mag/utils.py:28-57) is not built')
-        if self.training and self.dropout > 0:
-            raise NotImplementedError('edge-weight dropout is not built (the reference model leaves it at 0)')
+    def forward(self, x, edge_index, edge_type, return_weights=False, graph=None, edge_keep=None):
+        """``edge_keep`` (optional bool [E]): the dropout mask to use instead of drawing one (tests)."""
         x_src, x_target = x if isinstance(x, tuple) else (x, x)
         n_src, n_dst = x_src.shape[0], x_target.shape[0]
         if graph is None:
             graph = Graph(edge_index[0], edge_index[1], n_src)
-        etv = graph.etype_views(edge_type + 1, self.num_edge_types)
-        theta = self.relation_weight.view(-1, 1)
-        inv_deg = RF.weighted_degree_norm(graph, etv, theta, self.scaling_factor, -1.0, clamp_min=0.0)
+        r = self.num_edge_types
+        etv = graph.etype_views(edge_type + 1, r)
+        theta, alpha = self.relation_weight.view(-1, 1), self.scaling_factor
+        if self.use_softmax:
+            w = F.leaky_relu(theta * alpha)                                   # [R,1]: differentiable, R floats
+            present = torch.zeros(r, dtype=torch.bool, device=w.device).index_fill_(0, edge_type, True).view(-1, 1)
+            m_glob = torch.where(present, w, torch.full_like(w, float('-inf'))).max()
+            theta = torch.where(present, torch.exp(w - m_glob), torch.zeros_like(w))   # table exp(w - M) >= 0
+            alpha = 1.0
+            deg = RF.weighted_degree_norm(graph, etv, theta, alpha, 1.0, clamp_min=0.0)   # exponent 1: the sum itself
+            inv = 1.0 / (deg + 1e-16)
+        else:
+            inv = RF.weighted_degree_norm(graph, etv, theta, alpha, -1.0, clamp_min=0.0)
+        g_agg, etv_agg, scale = graph, etv, 1.0
+        if edge_keep is not None or (self.training and self.dropout > 0):
+            if edge_keep is None:
+                edge_keep = torch.rand(edge_type.numel(), device=edge_type.device) >= self.dropout
+            scale = 1.0 / (1.0 - self.dropout)
+            src, dst = graph.edges()
+            g_agg = Graph(src[edge_keep], dst[edge_keep], n_src)
+            etv_agg = g_agg.etype_views((edge_type + 1)[edge_keep], r)
+            inv = inv * scale
         if self.in_channels < self.out_channels:
             # aggregation is linear, so A(xW) = (Ax)W: gather the narrower rows (e.g. 128 instead of 349 classes)
-            out = RF.propagate(graph, etv, x_src, theta, self.scaling_factor, inv_deg, sides=2)[:n_dst] @ self.weight
+            out = RF.propagate(g_agg, etv_agg, x_src, theta, alpha, inv, sides=2)[:n_dst] @ self.weight
         else:
-            out = RF.propagate(graph, etv, x_src @ self.weight, theta, self.scaling_factor, inv_deg, sides=2)[:n_dst]
-        return out + self.bias
+            out = RF.propagate(g_agg, etv_agg, x_src @ self.weight, theta, alpha, inv, sides=2)[:n_dst]
+        out = out + self.bias
+        if return_weights:
+            wr = F.leaky_relu(self.relation_weight * self.scaling_factor)
+            ew = _reference_edge_weights(wr[edge_type], graph.edges()[1], n_src, self.use_softmax)
+            if edge_keep is not None:
+                ew = ew * edge_keep.to(ew.dtype) * scale
+            return out, ew
+        return out
 
 
 class SaintREGCN(nn.Module):

@@ -48,7 +48,7 @@ def main():
                 out = partition.feature_sliced_propagate(g, etv, xo, th, 100.0, nrm, bounds, rank, exchange=xch,
                                                          alias=(rep == 1))
             out.backward(gout[rb:re])
-            partition.allreduce_relation_grads([th])
+            partition.allreduce_relation_grads([th], exchange=xch)
             e_out = bool(torch.equal(out.detach(), ref[0][rb:re]))
             e_dx = bool(torch.equal(xo.grad, ref[1][rb:re]))
             rel = float((th.grad - ref[2]).abs().max() / ref[2].abs().max())

@@ -51,13 +51,19 @@ def save_case(name, kind, kw, blk, tuple_input=True):
         mod.bias.copy_(torch.as_tensor(rng.randn(*mod.bias.shape) * 0.1))
     x_src = torch.as_tensor(rng.randn(n_src, 16)).requires_grad_(True)
     x_in = (x_src, x_src[:n_dst]) if tuple_input else x_src
-    out = mod(x_in, torch.as_tensor(edge_index), torch.as_tensor(et), torch.as_tensor(tnt))
+    ew = None
+    if kind == 'REGCNConv':   # also record the normalised edge weights the layer returns on request (:119-126, :137-138)
+        out, ew, _ = mod(x_in, torch.as_tensor(edge_index), torch.as_tensor(et), torch.as_tensor(tnt), return_weights=True)
+    else:
+        out = mod(x_in, torch.as_tensor(edge_index), torch.as_tensor(et), torch.as_tensor(tnt))
     gout = torch.as_tensor(np.random.RandomState(7).randn(*out.shape))
     out.backward(gout)
     blob = dict(edge_index=edge_index, edge_type=et, target_node_type=tnt, n_src=np.int64(n_src), n_dst=np.int64(n_dst),
                 x_src=x_src.detach().numpy(), gx_src=x_src.grad.numpy(), out=out.detach().numpy(), gout=gout.numpy(),
                 meta=np.array(json.dumps(dict(kind=kind, kw=kw, tuple_input=tuple_input, in_channels=16, out_channels=8,
                                               num_node_types=NUM_NODE_TYPES, num_edge_types=NUM_EDGE_TYPES))))
+    if ew is not None:
+        blob['ew'] = ew.detach().numpy()
     for k, v in mod.state_dict().items():
         blob['param::' + k] = v.detach().numpy()
     for k, p in mod.named_parameters():
@@ -84,23 +90,28 @@ def reference_saint_conv():
     return ns['REGCNConv']
 
 
-def save_saint_case(name, n, e, seed, tuple_input):
+def save_saint_case(name, n, e, seed, tuple_input, kw=None, train=False):
+    """``kw``: extra constructor keywords (``use_softmax``, ``dropout``); ``train``: run in training mode, so that
+    ``F.dropout`` acts on the edge weights -- the mask it drew is recovered from the returned ``ew`` (weights are
+    positive, a dropped edge returns exactly 0)."""
+    kw = kw or {}
     rng = np.random.RandomState(seed)
     dst = np.where(rng.rand(e) < 0.3, rng.randint(0, 2, size=e), rng.randint(0, n - 6, size=e))   # hubs; 6 rows w/o in-edges
     edge_index = np.stack([rng.randint(0, n, size=e), dst]).astype(np.int64)
     et = rng.randint(0, NUM_EDGE_TYPES, size=e).astype(np.int64)
     torch.manual_seed(5)
-    mod = reference_saint_conv()(16, 8, NUM_NODE_TYPES, NUM_EDGE_TYPES, ALPHA)
+    mod = reference_saint_conv()(16, 8, NUM_NODE_TYPES, NUM_EDGE_TYPES, ALPHA, **kw)
+    mod.train(train)
     with torch.no_grad():   # positive relation weights: the layer divides by the weighted in-degree without a clamp
         mod.relation_weight.copy_(torch.as_tensor(rng.uniform(0.3, 1.5, size=NUM_EDGE_TYPES) / ALPHA))
         mod.bias.copy_(torch.as_tensor(rng.randn(8) * 0.1))
     x = torch.as_tensor(rng.randn(n, 16)).requires_grad_(True)
-    out = mod((x, x) if tuple_input else x, torch.as_tensor(edge_index), torch.as_tensor(et))
+    out, ew = mod((x, x) if tuple_input else x, torch.as_tensor(edge_index), torch.as_tensor(et), return_weights=True)
     gout = torch.as_tensor(np.random.RandomState(7).randn(*out.shape))
     out.backward(gout)
     blob = dict(edge_index=edge_index, edge_type=et, n_src=np.int64(n), n_dst=np.int64(n), x_src=x.detach().numpy(),
-                gx_src=x.grad.numpy(), out=out.detach().numpy(), gout=gout.numpy(),
-                meta=np.array(json.dumps(dict(kind='SaintREGCNConv', kw={}, tuple_input=tuple_input, in_channels=16,
+                gx_src=x.grad.numpy(), out=out.detach().numpy(), gout=gout.numpy(), ew=ew.detach().numpy(),
+                meta=np.array(json.dumps(dict(kind='SaintREGCNConv', kw=kw, train=train, tuple_input=tuple_input, in_channels=16,
                                               out_channels=8, num_node_types=NUM_NODE_TYPES,
                                               num_edge_types=NUM_EDGE_TYPES))))
     for k, v in mod.state_dict().items():
@@ -182,6 +193,9 @@ def main():
     save_model_case('model_regnn_regatv2_h2', 'regatv2', 2, False)
     save_saint_case('saint_regcn_tensor_input', 50, 320, 21, False)
     save_saint_case('saint_regcn_tuple_input', 36, 200, 22, True)
+    save_saint_case('saint_regcn_softmax', 50, 320, 23, False, dict(use_softmax=True))
+    save_saint_case('saint_regcn_dropout', 50, 320, 24, False, dict(dropout=0.4), train=True)
+    save_saint_case('saint_regcn_softmax_dropout', 44, 260, 25, True, dict(use_softmax=True, dropout=0.25), train=True)
     b1, b2 = block(1), block(2, empty_targets=False)
     square = block(3, n_src=40, n_dst=40, e=260)       # full-graph inference shape: targets == sources
     for name, kw, blk in [

@@ -707,7 +707,9 @@ def test_mag_layers_match_reference_golden(name):
     m = c['meta']
     saint = m['kind'] == 'SaintREGCNConv'
     if saint:
-        conv = mag.SaintREGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], 100.0)
+        conv = mag.SaintREGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], 100.0,
+                                  **m['kw'])
+        conv.train(bool(m.get('train')))
     else:
         conv = mag.REGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], **m['kw'])
     conv.load_state_dict({k[7:]: torch.as_tensor(v, dtype=torch.float32) for k, v in c.items() if k.startswith('param::')})
@@ -715,8 +717,9 @@ def test_mag_layers_match_reference_golden(name):
     x = torch.as_tensor(c['x_src'], dtype=torch.float32).to(DEV).requires_grad_(True)
     ei, et = torch.as_tensor(c['edge_index']).to(DEV), torch.as_tensor(c['edge_type']).to(DEV)
     n_dst = int(c['n_dst'])
-    if saint:
-        out = conv((x, x) if m['tuple_input'] else x, ei, et)
+    if saint:   # use_softmax / edge-weight dropout fixtures: the reference's dropout mask is recovered from its returned weights
+        keep = (torch.as_tensor(c['ew']) != 0).to(DEV) if m.get('train') else None
+        out = conv((x, x) if m['tuple_input'] else x, ei, et, edge_keep=keep)
     else:
         out = conv((x, x[:n_dst]), ei, et, torch.as_tensor(c['target_node_type']).to(DEV))
     out.backward(torch.as_tensor(c['gout'], dtype=torch.float32).to(DEV))

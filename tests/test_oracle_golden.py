@@ -104,7 +104,10 @@ def test_mag_oracle_matches_reference_layer_code(name):
     n_dst = int(c['n_dst'])
     slt, res = kw.get('self_loop_type', 1), kw.get('residual', False)
     if m['kind'] == 'SaintREGCNConv':   # class lifted from the mag/regnn_saint.py script
-        out = O.saint_regcn_forward(x, t('edge_index'), t('edge_type'), p['weight'], p['bias'], p['relation_weight'], 100.0)
+        keep = (t('ew') != 0) if m.get('train') else None     # the mask F.dropout drew, recovered from the returned weights
+        out, ew = O.saint_regcn_forward(x, t('edge_index'), t('edge_type'), p['weight'], p['bias'], p['relation_weight'],
+                                        100.0, kw.get('use_softmax', False), keep, kw.get('dropout', 0.0), True)
+        assert torch.allclose(ew, t('ew'), rtol=1e-11, atol=1e-14)
         common = None
     else:
         common = (x, x[:n_dst], t('edge_index'), t('edge_type'), t('target_node_type'))

@@ -159,8 +159,11 @@ def test_mag_regcn_layer_matches_reference_golden(cpu_ops, name):
     conv.load_state_dict(state)
     x = torch.as_tensor(c['x_src']).clone().requires_grad_(True)
     n_dst = int(c['n_dst'])
-    out = conv((x, x[:n_dst]), torch.as_tensor(c['edge_index']), torch.as_tensor(c['edge_type']),
-               torch.as_tensor(c['target_node_type']))
+    out, ew, _ = conv((x, x[:n_dst]), torch.as_tensor(c['edge_index']), torch.as_tensor(c['edge_type']),
+                      torch.as_tensor(c['target_node_type']), return_weights=True)
+    # the normalised edge weights the reference returns on request (mag/regnn_layers.py:119-126); rows the reference
+    # divides by a zero degree are inf / nan on both sides
+    assert torch.allclose(ew, torch.as_tensor(c['ew']), rtol=1e-10, atol=1e-14, equal_nan=True)
     assert torch.allclose(out, torch.as_tensor(c['out']), rtol=1e-10, atol=1e-12)
     out.backward(torch.as_tensor(c['gout']))
     assert torch.allclose(x.grad, torch.as_tensor(c['gx_src']), rtol=1e-9, atol=1e-12)
@@ -174,12 +177,19 @@ def test_saint_regcn_layer_matches_reference_golden(cpu_ops, name):
     from re_gnn_b200 import mag
     c = helpers.load_mag_case(name)
     m = c['meta']
-    conv = mag.SaintREGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], 100.0).double()
+    conv = mag.SaintREGCNConv(m['in_channels'], m['out_channels'], m['num_node_types'], m['num_edge_types'], 100.0,
+                              **m['kw']).double()
     state = {k[7:]: torch.as_tensor(v) for k, v in c.items() if k.startswith('param::')}
     assert set(conv.state_dict()) == set(state)
     conv.load_state_dict(state)
+    conv.train(bool(m.get('train')))
+    # use_softmax / edge-weight dropout (mag/regnn_saint.py:248-258): the mask the reference drew is recovered from the
+    # weights it returned (a dropped edge returns exactly 0)
+    keep = (torch.as_tensor(c['ew']) != 0) if m.get('train') else None
     x = torch.as_tensor(c['x_src']).clone().requires_grad_(True)
-    out = conv((x, x) if m['tuple_input'] else x, torch.as_tensor(c['edge_index']), torch.as_tensor(c['edge_type']))
+    out, ew = conv((x, x) if m['tuple_input'] else x, torch.as_tensor(c['edge_index']), torch.as_tensor(c['edge_type']),
+                   return_weights=True, edge_keep=keep)
+    assert torch.allclose(ew, torch.as_tensor(c['ew']), rtol=1e-10, atol=1e-14)
     assert torch.allclose(out, torch.as_tensor(c['out']), rtol=1e-10, atol=1e-12)
     out.backward(torch.as_tensor(c['gout']))
     assert torch.allclose(x.grad, torch.as_tensor(c['gx_src']), rtol=1e-9, atol=1e-12)
