@@ -246,6 +246,39 @@ def others(dev, steps, warmup):
         t = float(np.median(ts[warmup:]))
         res[name] = {'gteps_fwd_bwd': d['src'].size / t / 1e9, 'ms': t * 1e3, 'num_edges': int(d['src'].size),
                      'l2': 'flushed between iterations', 'l2_resident': True}   # whole working set < 126 MB L2: not an HBM statement
+        # the same forward + backward replayed as ONE CUDA graph: these layers are a dozen launches of a few microseconds
+        # each, so the eager number above is host time (Python, autograd, allocator), this one is device time
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    x.grad = None
+                    mod.zero_grad(set_to_none=True)
+                    mod(g, x, et).backward(gout)
+            torch.cuda.current_stream().wait_stream(side)
+            cg = torch.cuda.CUDAGraph()
+            x.grad = None
+            mod.zero_grad(set_to_none=True)
+            with torch.cuda.graph(cg):
+                mod(g, x, et).backward(gout)
+            tg = []
+            for i in range(warmup + steps):
+                flush.zero_()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                cg.replay()
+                t1.record()
+                torch.cuda.synchronize()
+                tg.append(t0.elapsed_time(t1) / 1e3)
+            tgm = float(np.median(tg[warmup:]))
+            res[name]['ms_cuda_graph'] = tgm * 1e3
+            res[name]['gteps_fwd_bwd_cuda_graph'] = d['src'].size / tgm / 1e9
+            del cg
+        except Exception as exc:   # report, do not hide
+            res[name]['ms_cuda_graph'] = None
+            res[name]['cuda_graph_error'] = str(exc)[:200]
+            torch.cuda.synchronize()
     return res
 
 
@@ -361,6 +394,29 @@ def epoch_times(dev, steps, warmup):
     return res
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated
+    (first touch places them): with N ranks on one host the H2D streams of the e2e arm otherwise cross the socket
+    interconnect and contend.  Best effort: returns the node id or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = '/sys/bus/pci/devices/%s/numa_node' % bus.lower()[-12:]
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(args, d):
     import torch.distributed as dist
     import re_gnn_b200  # noqa: F401  (fails loudly if the CUDA library is missing)
@@ -372,6 +428,7 @@ def run_ours(args, d):
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -550,7 +607,7 @@ def run_ours(args, d):
             out = dist_propagate(g, etv, x_e, theta, ALPHA, nrm, bounds, rank)
         out.backward(g_e)
         if world > 1:
-            partition.allreduce_relation_grads([theta])
+            partition.allreduce_relation_grads([theta], exchange=xch if args.partition == 'peer' else None)
         res_h.copy_(torch.cat([theta.grad.view(-1), out.detach().sum().view(1)]), non_blocking=True)
         freed[slot].record(cur)
         state['i'] = i + 1
@@ -563,7 +620,7 @@ def run_ours(args, d):
     e2e_steps = max(3, args.steps // 2)
     e2e = {'value': e / (e2e_total / e2e_steps) / 1e9, 'unit': 'GTEPS',
            'h2d_bytes_per_step': int(x_h.numel() * 4 + g_h.numel() * 4), 'd2h_bytes_per_step': int(res_h.numel() * 4),
-           'ms_per_step': e2e_total / e2e_steps * 1e3,
+           'ms_per_step': e2e_total / e2e_steps * 1e3, 'numa_node_rank0': numa_node,
            'note': 'per rank, every step: pinned-host X and dL/dY rows copied in (double-buffered on a copy stream, so '
                    'step i+1 streams in behind the kernels of step i; K+1 input copies for K timed steps), relation '
                    'gradient + output checksum copied out'}

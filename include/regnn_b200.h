@@ -316,7 +316,8 @@ int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t
                     const float* keep, int num_heads, int head_dim, int64_t row_begin,
                     int64_t row_end, float* out, float* rowmax, float* rowsum, float* attn_out,
                     const regnn_rowsplit_t* split,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */,
+    const int32_t* row_order /* as regnn_gat_fwd */, void* stream);
 
 /* Backward, destination-major pass: a_csr = a*keep, dl_csr = dL/dl (both [E,H] slot order),
  * d_fd [N,H,D], d_attn [H,D], d_theta [R,H].

@@ -50,7 +50,7 @@ SIGNATURES = {
     'regnn_attn_scores_fwd': (_i32, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
     'regnn_attn_scores_bwd': (_i32, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     'regnn_gatv2_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
-                               _p, _p, _p, _p, _p, _p, _p]),
+                               _p, _p, _p, _p, _p, _p, _p, _p]),
     'regnn_gatv2_bwd_dst': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p,
                                    _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'regnn_gatv2_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64, _p, _p, _p, _p]),

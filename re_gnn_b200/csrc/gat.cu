@@ -362,13 +362,20 @@ gat_bwd_stats_kernel(const float* __restrict__ out, const float* __restrict__ Gd
 
 // Source-major gather pass (transposed view; AttnArgs: indptr/indices/eid = indptr_t/indices_t/slot_t, etype = etype_t,
 // fd = stats as float4[N*H], G = dL/d out, a_csr = slot -> edge id when keep != null).
+// The gather pass is latency-bound at HBM scale (short rows, two gathers + two statistics loads per round): resident
+// warps win -- MAG graph, H8 D16: 4 blocks/SM 4.00 ms, 5: 3.66, 6 (40 registers, 24 bytes of spill): 3.49; L2-resident
+// ACM H8 D64: 0.226 / 0.244 / 0.250 ms.
 #ifndef REGNN_GATB_BLOCKS
-#define REGNN_GATB_BLOCKS 4
+#define REGNN_GATB_BLOCKS 6
+#endif
+#ifndef REGNN_GATB_U
+#define REGNN_GATB_U 2
 #endif
 template <int G, int LPH, bool KEEP>   // LPH = min(G, D/4): lanes per head (compile-time butterfly)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_GATB_BLOCKS)
 gat_bwd_edges_kernel(AttnArgs a) {
-  constexpr int U = 2;  // two rows of G and two statistics vectors in flight per lane
+  constexpr int U = REGNN_GATB_U;  // rows of G (and statistics vectors) in flight per lane
+  static_assert(G % U == 0, "a round must not straddle a slot batch");
   extern __shared__ __align__(16) float smem[];
   float* w_s = smem;
   load_rel_table(w_s, a);
@@ -642,122 +649,122 @@ attn_scores_bwd_kernel(const float* __restrict__ feat, const float* __restrict__
 }
 
 // =================================================================================================
-// REGATv2 forward: the gathered fs[src] slice feeds both the logit (sum_d attn*LeakyReLU(fs+fd),
-// reduced by xor-shuffles over the D/4 lanes of a head) and the aggregation; online softmax per
-// group of kUA edges.  Nothing [E,H,D]-sized is ever written.
-// Dynamic smem: w_s[R*H] | per warp: m_s[H], inv_s[H]
-template <int LPH>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
-gatv2_fwd_kernel(AttnArgs a) {
+// REGATv2 forward, row-group mapping (as gat_fwd_rg_kernel): the gathered fs[src] slice feeds both the logit
+// (sum_d attn*LeakyReLU(fs+fd), reduced by a compile-time butterfly over the LPH = min(G, D/4) lanes of a head) and the
+// aggregation; online softmax per batch of U edges.  Nothing [E,H,D]-sized is ever written.
+// Dynamic smem: w_s[R*H]
+template <int G, int LPH, bool EXTRA>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+gatv2_fwd_rg_kernel(AttnArgs a) {
+  constexpr int U = kUG;
+  static_assert(G % U == 0, "a batch must not straddle a cooperative slot load");
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
   float* w_s = smem;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* m_s = smem + RH + warp * 2 * H;
-  float* inv_s = m_s + H;
   load_rel_table(w_s, a);
-  const int HG = num_groups(a);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
+  const int H = a.H, HD = H * a.D;
   const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  int64_t ri;
-  int hg;
-  split_item(wi, HG, &ri, &hg);
-  const WorkItem it = decode_item(a, ri, a.nfrag);
-  if (!it.ok) return;
-  const Group g = make_group(a, hg, lane);
-  const int64_t v = it.v;
-  const int s0 = it.s0, len = it.len;
-  float4 acc = zero4(), fdv = zero4(), at = zero4();
+  if (wi >= rg_num_work(a, G)) return;  // warp-uniform
+  const RowItem it = rg_item<G>(a, wi, grp);
+  const int col = it.hg * 128 + lg * 4;
+  const bool col_ok = col < HD;
+  const int h = col_ok ? (col >> a.d_shift) : 0;
+  const bool act = it.v >= 0 && col_ok;
+  const bool leader = act && (col & (a.D - 1)) == 0;
+  const int len = it.v >= 0 ? it.len : 0;
+  const int maxlen = __reduce_max_sync(0xffffffffu, len);
+  const bool has_rel = a.etype != nullptr;
+  float4 fdv = zero4(), at = zero4();
+  if (act) fdv = ldg4(a.fd + (size_t)it.v * HD + col);
+  if (col_ok) at = ldg4(a.el + col);
+  const char* fbytes = reinterpret_cast<const char*>(a.feat + (col_ok ? col : 0));
+  const uint32_t fpitch = (uint32_t)HD * 4u;
+  const float* w_h = w_s + h;
+  const int32_t* ip = a.indices + it.begin;
+  const uint8_t* ep = a.etype + it.begin;
+  const int32_t* eidp = a.eid + it.begin;
+  float4 acc = zero4();
   float m = -INFINITY, s = 0.f;
-  if (g.ok) {
-    fdv = ldg4(a.fd + (size_t)v * HD + g.col);
-    at = ldg4(a.el + g.col);
-  }
-  const float* fcol = a.feat + g.col;
-  const bool need_eid = a.keep != nullptr || a.o3 != nullptr;
 
-  for (int base = 0; base < len; base += 32) {
-    const int cnt = min(32, len - base);
-    const int slot = s0 + base + lane;
-    int idx = 0, et = 0, e = 0;
-    if (lane < cnt) {
-      idx = a.indices[slot];
-      if (a.etype != nullptr) et = a.etype[slot];
-      if (need_eid) e = a.eid[slot];
+  for (int t0 = 0; t0 < maxlen; t0 += G) {
+    int bi = -1, be = 0, beid = 0;
+    {
+      const int t = t0 + lg;
+      if (t < len) {
+        bi = __ldg(ip + t);
+        if (has_rel) be = __ldg(ep + t);
+        if (EXTRA) beid = __ldg(eidp + t);
+      }
     }
-    auto body = [&](int j, auto full_tag) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      float4 x[kUA];
-      float l[kUA];
+    const int cnt = min(G, maxlen - t0);
+    for (int j = 0; j < cnt; j += U) {
+      float4 x[U];
+      float l[U];
+      int si[U], seid[EXTRA ? U : 1];
 #pragma unroll
-      for (int u = 0; u < kUA; ++u) {
-        const bool ok = FULL || j + u < cnt;
-        const int sidx = __shfl_sync(0xffffffffu, idx, ok ? j + u : j);
-        x[u] = (ok && g.ok) ? ldg4(fcol + (size_t)sidx * HD) : zero4();
+      for (int u = 0; u < U; ++u) {
+        si[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+        x[u] = (si[u] >= 0 && col_ok) ? ldg4(reinterpret_cast<const float*>(fbytes + (uint64_t)(uint32_t)si[u] * fpitch))
+                                      : zero4();
       }
       float bm = -INFINITY;
 #pragma unroll
-      for (int u = 0; u < kUA; ++u) {  // kUA independent head reductions
-        const bool ok = FULL || j + u < cnt;
-        l[u] = group_sum<LPH>(dot4(at, leaky4(add4(x[u], fdv), a.slope)));
-        if (a.etype != nullptr) l[u] += w_s[__shfl_sync(0xffffffffu, et, ok ? j + u : j) * H + g.hl];
-        if (!ok) l[u] = -INFINITY;
+      for (int u = 0; u < U; ++u) {   // U independent head reductions
+        float lu = group_sum<LPH>(dot4(at, leaky4(add4(x[u], fdv), a.slope)));
+        if (has_rel) lu += w_h[__shfl_sync(0xffffffffu, be, gbase + j + u) * H];
+        if (EXTRA) seid[u] = __shfl_sync(0xffffffffu, beid, gbase + j + u);
+        l[u] = si[u] >= 0 ? lu : -INFINITY;
         bm = fmaxf(bm, l[u]);
       }
-      const float m_new = fmaxf(m, bm);
-      const float sc = expf(m - m_new);
-      m = m_new;
-      s *= sc;
-      scale4(acc, sc);
+      if (bm > -INFINITY) {  // uniform within a lane group
+        const float m_new = fmaxf(m, bm);
+        const float sc = __expf(m - m_new);
+        m = m_new;
+        s *= sc;
+        scale4(acc, sc);
 #pragma unroll
-      for (int u = 0; u < kUA; ++u) {
-        if (FULL || j + u < cnt) {  // warp-uniform
-          int se = 0;
-          if (need_eid) se = __shfl_sync(0xffffffffu, e, j + u);
-          if (g.ok) {
-            if (a.o3 != nullptr && g.leader) a.o3[(size_t)se * H + g.hl] = l[u];
-            float p = expf(l[u] - m_new);
-            s += p;
-            if (a.keep != nullptr) p *= __ldg(a.keep + (size_t)se * H + g.hl);
-            fma4(acc, p, x[u]);
+        for (int u = 0; u < U; ++u) {
+          float p = __expf(l[u] - m_new);  // 0 for a missing slot
+          s += p;
+          if (EXTRA && si[u] >= 0 && act) {
+            const size_t o = (size_t)seid[u] * H + h;
+            if (a.o3 != nullptr && leader) a.o3[o] = l[u];
+            if (a.keep != nullptr) p *= __ldg(a.keep + o);
           }
+          fma4(acc, p, x[u]);
         }
       }
-    };
-    int j = 0;
-    for (; j + kUA <= cnt; j += kUA) body(j, std::true_type{});
-    if (j < cnt) body(j, std::false_type{});
+    }
   }
+
   if (it.frag) {
-    if (g.ok) {
-      st4(a.p0 + (size_t)it.fi * HD + g.col, acc);
-      if (g.leader) {
-        a.p1[(size_t)it.fi * H + g.hl] = m;
-        a.p2[(size_t)it.fi * H + g.hl] = s;
-      }
+    if (act) st4(a.p0 + (size_t)it.fi * HD + col, acc);
+    if (leader) {
+      a.p1[(size_t)it.fi * H + h] = m;
+      a.p2[(size_t)it.fi * H + h] = s;
     }
     return;
   }
-  if (g.ok) {
-    const float inv = s > 0.f ? 1.f / s : 0.f;
-    const float mm = len > 0 ? m : 0.f;
+  const float inv = s > 0.f ? 1.f / s : 0.f;
+  const float mm = len > 0 ? m : 0.f;
+  if (act) {
     scale4(acc, inv);
-    st4(a.o0 + (size_t)v * HD + g.col, acc);
-    if (g.leader) {
-      a.o1[(size_t)v * H + g.hl] = mm;
-      a.o2[(size_t)v * H + g.hl] = s;
-      m_s[g.hl] = mm;
-      inv_s[g.hl] = inv;
+    st4(a.o0 + (size_t)it.v * HD + col, acc);
+    if (leader) {
+      a.o1[(size_t)it.v * H + h] = mm;
+      a.o2[(size_t)it.v * H + h] = s;
     }
   }
-  if (a.o3 != nullptr) {
+  if (EXTRA && a.o3 != nullptr) {
     __syncwarp();
-    for (int i = lane; i < len * g.nh; i += 32) {
-      const int h = g.h_lo + i % g.nh;
-      const size_t o = (size_t)a.eid[s0 + i / g.nh] * H + h;
-      float av = expf(a.o3[o] - m_s[h]) * inv_s[h];
-      if (a.keep != nullptr) av *= a.keep[o];
-      a.o3[o] = av;
-    }
+    if (act)
+      for (int t = lg & (LPH - 1); t < len; t += LPH) {
+        const size_t o = (size_t)eidp[t] * H + h;
+        float av = __expf(a.o3[o] - mm) * inv;
+        if (a.keep != nullptr) av *= a.keep[o];
+        a.o3[o] = av;
+      }
   }
 }
 
@@ -1367,7 +1374,7 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
                                const float* attn, float negative_slope, const float* keep,
                                int num_heads, int head_dim, int64_t row_begin, int64_t row_end,
                                float* out, float* rowmax, float* rowsum, float* attn_out,
-                               const regnn_rowsplit_t* split, float* split_workspace,
+                               const regnn_rowsplit_t* split, float* split_workspace, const int32_t* row_order,
     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && fs && fd && attn && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gatv2_fwd: null pointer");
@@ -1385,9 +1392,27 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
   a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end;
   a.o0 = out; a.o1 = rowmax; a.o2 = rowsum; a.o3 = attn_out;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_fwd: incomplete row split");
-  const size_t smem = sizeof(float) * ((size_t)a.R * num_heads + (size_t)kWarpsPerBlock * 2 * num_heads) + 16;
-  const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  REGNN_DISPATCH_LPH(gatv2_fwd_kernel, grid, smem);
+  apply_order(a, row_order, split, rows);
+  const size_t smem = sizeof(float) * ((size_t)a.R * num_heads) + 16;
+  const unsigned grid = (unsigned)((rg_work(a, rows) + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  {
+    const int G = rg_lanes(a.H * a.D), lph = min(G, head_dim / 4);
+    const bool extra = keep != nullptr || attn_out != nullptr;
+    bool launched = false;
+#define REGNN_V2F_CASE(G_, L_)                                                                   \
+  if (G == G_ && lph == L_) {                                                                    \
+    if (extra) REGNN_DISPATCH_C((gatv2_fwd_rg_kernel<G_, L_, true>), grid, smem);                \
+    else REGNN_DISPATCH_C((gatv2_fwd_rg_kernel<G_, L_, false>), grid, smem);                     \
+    launched = true;                                                                             \
+  }
+    REGNN_V2F_CASE(4, 1) REGNN_V2F_CASE(4, 2) REGNN_V2F_CASE(4, 4)
+    REGNN_V2F_CASE(8, 1) REGNN_V2F_CASE(8, 2) REGNN_V2F_CASE(8, 4) REGNN_V2F_CASE(8, 8)
+    REGNN_V2F_CASE(16, 1) REGNN_V2F_CASE(16, 2) REGNN_V2F_CASE(16, 4) REGNN_V2F_CASE(16, 8) REGNN_V2F_CASE(16, 16)
+    REGNN_V2F_CASE(32, 1) REGNN_V2F_CASE(32, 2) REGNN_V2F_CASE(32, 4) REGNN_V2F_CASE(32, 8) REGNN_V2F_CASE(32, 16)
+    REGNN_V2F_CASE(32, 32)
+#undef REGNN_V2F_CASE
+    REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "gatv2_fwd: no kernel for H=%d D=%d", num_heads, head_dim);
+  }
   if (a.nfrag > 0) {
     const unsigned fgrid = (unsigned)(((int64_t)split->num_long * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
     REGNN_DISPATCH_FINALIZE(fgrid);

@@ -503,6 +503,10 @@ spmm_stream_kernel(StreamArgs sa) {
 #ifndef REGNN_RGB_U
 #define REGNN_RGB_U 4
 #endif
+// Tried and dropped (round 2, measured on the MAG graph): the fused backward with 16 / 8 / 4 lanes x TWO 128-bit chunks
+// per lane (twice the rows in flight per warp): 2.41 vs 2.43 ms at F = 128, 1.31 vs 1.19 at F = 64, 0.86 vs 0.72 at
+// F = 32 -- no gain where it is equal, slower on narrow rows; 5 / 6 resident blocks per SM by capping registers at
+// 48 / 40 (2.52 / 2.56 ms) and 3 blocks x 71 registers (2.91): 4 x 4 gathers stays.
 // Cooperative slot loads pay off where the kernel is issue-bound (fused backward: 2.73 -> 2.44 ms at F = 128,
 // 1.37 -> 1.22 at 64, 0.53 -> 0.50 at 16); the forward kernel is HBM-bound and slightly faster without (2.05 vs 2.14).
 #ifndef REGNN_RG_COOP
@@ -697,177 +701,6 @@ spmm_rowgroup_kernel(StreamArgs sa) {
     }
   }
   if (BINS) reduce_bins(bins, scratch, a.R, sa.partials + (size_t)blockIdx.x * a.R);
-}
-
-// ---- fused backward, two 128-bit chunks per lane ---------------------------------------------------------
-// The fused backward is latency-bound, not bandwidth-bound (ncu, r2b: 32 resident warps/SM at 64 registers, 43 % issue
-// utilisation, 58 % of DRAM peak; a quarter of the stall samples sit in the per-row prologue chain order -> indptr ->
-// slots -> gathers).  Covering a row with HALF as many lanes, two chunks each, puts twice as many rows in flight per
-// warp at the same bytes in flight per lane, and the shuffles / bin bookkeeping / loop control of an edge are paid
-// once for two rows' worth of lanes.  F = 128: 16 lanes x 2 chunks, 2 rows per warp; F = 64: 8 x 2, 4 rows; F = 32: 4 x 2.
-#ifndef REGNN_RGB2_BLOCKS
-#define REGNN_RGB2_BLOCKS 4
-#endif
-#ifndef REGNN_RGB2_U
-#define REGNN_RGB2_U 2
-#endif
-template <int G, bool DNORM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_RGB2_BLOCKS)
-spmm_rowgroup2_kernel(StreamArgs sa) {
-  static_assert(G == 4 || G == 8 || G == 16, "lane groups of 4, 8 or 16 lanes, two chunks per lane");
-  constexpr int GPW = 32 / G, U = REGNN_RGB2_U, C = 2;
-  static_assert(G % U == 0, "a round must not straddle a slot batch");
-  const SpmmArgs& a = sa.s;
-  __shared__ float w_s[256];
-  extern __shared__ __align__(16) unsigned char dsm[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
-  double* scratch = reinterpret_cast<double*>(dsm);
-  float* bins = reinterpret_cast<float*>(scratch + kWarpsPerBlock * a.R);
-  float* mybins = bins + (size_t)warp * a.R * 32 + lane;
-  const bool weighted = a.etype != nullptr;
-  if (weighted)
-    for (int i = threadIdx.x; i < a.R; i += blockDim.x) w_s[i] = leaky(a.theta[i] * a.alpha, kRelationSlope);
-  for (int r = 0; r < a.R; ++r) mybins[r * 32] = 0.f;
-  __syncthreads();
-
-  bool ok[C];
-  int colk[C];
-  const char* xb[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) {
-    colk[k] = (k * G + lg) * 4;
-    ok[k] = colk[k] < a.F;
-    xb[k] = reinterpret_cast<const char*>(a.X + (ok[k] ? colk[k] : 0));
-  }
-  const uint32_t ldxb = (uint32_t)a.ldx * 4u;
-  const int64_t nitems = (int64_t)a.nfrag + sa.n_order;
-  const int64_t nwork = (nitems + GPW - 1) / GPW;
-  const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
-
-  for (int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp; wi < nwork; wi += stride) {
-    const int64_t vi = wi * GPW + grp;
-    int64_t v = -1;
-    int begin = 0, len = 0;
-    const bool is_frag = vi < a.nfrag;
-    if (vi < nitems) {
-      if (is_frag) {
-        v = a.frag_row[vi];
-        begin = a.frag_begin[vi];
-        len = min(a.threshold, a.indptr[v + 1] - begin);
-      } else {
-        v = sa.order[vi - a.nfrag];
-        begin = a.indptr[v];
-        len = a.indptr[v + 1] - begin;
-      }
-    }
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    const float nd = (v >= 0 && a.norm_dst != nullptr) ? a.norm_dst[v] : 1.f;
-    float4 trow[C], acc[C];
-    // norm gradient, destination-side half <Y[u], G[u]>: the two rows are requested into L2 here, ahead of the gathers
-    // (no registers held), and read after them at L2 latency; G[u] is also one of the gathered rows when u has a self loop
-    const bool want_ydg = DNORM && (sa.dn_sides & 2) && v >= 0 && !is_frag;
-#pragma unroll
-    for (int k = 0; k < C; ++k) {
-      acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      trow[k] = (v >= 0 && ok[k]) ? ldg4(sa.Xrow + (size_t)v * sa.ldr + colk[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (DNORM) {
-        if (want_ydg && ok[k]) {
-          prefetch_l2(sa.Yfwd + (size_t)v * sa.ldyf + colk[k]);
-          prefetch_l2(xb[k] + (uint64_t)(uint32_t)v * ldxb);
-        }
-      }
-    }
-    int cur_rel = 0;
-    float racc = 0.f;
-    const int32_t* ip = a.indices + begin;
-    const uint8_t* ep = a.etype + begin;
-    auto load_batch = [&](int t0, int& bi, int& be, float& bn) {
-      const int t = t0 + lg;
-      bi = -1;
-      be = 0;
-      bn = 0.f;
-      if (t < len) {
-        bi = __ldg(ip + t);
-        be = weighted ? (int)__ldg(ep + t) : 0;
-        bn = a.norm_src != nullptr ? __ldg(a.norm_src + bi) : 1.f;
-      }
-    };
-    int nbi, nbe;
-    float nbn;
-    load_batch(0, nbi, nbe, nbn);
-    for (int t0 = 0; t0 < maxlen; t0 += G) {
-      const int bi = nbi, be = nbe;
-      const float bn = nbn;
-      const float bc = (weighted ? w_s[be] : 1.f) * bn;  // 0 for a missing slot
-      if (t0 + G < maxlen) load_batch(t0 + G, nbi, nbe, nbn);
-      const int cnt = min(G, maxlen - t0);
-      for (int j = 0; j < cnt; j += U) {
-        float4 x[U][C];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int si = __shfl_sync(0xffffffffu, bi, gbase + j + u);
-#pragma unroll
-          for (int k = 0; k < C; ++k)
-            x[u][k] = si >= 0 ? ldg4(reinterpret_cast<const float*>(xb[k] + (uint64_t)(uint32_t)si * ldxb))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int from = gbase + j + u;
-          const float c = __shfl_sync(0xffffffffu, bc, from);
-          const int se = __shfl_sync(0xffffffffu, be, from);
-          const float sn = __shfl_sync(0xffffffffu, bn, from);
-          float d = 0.f;
-#pragma unroll
-          for (int k = 0; k < C; ++k) {
-            fma4(acc[k], c, x[u][k]);
-            d += dot4(x[u][k], trow[k]);
-          }
-          if (t0 + j + u < len && se != cur_rel) {  // lane-local bin, slot order, bank-conflict free
-            mybins[cur_rel * 32] += racc;
-            racc = 0.f;
-            cur_rel = se;
-          }
-          racc = fmaf(sn * nd, d, racc);
-        }
-      }
-    }
-    mybins[cur_rel * 32] += racc;
-    if constexpr (DNORM) {
-      float p = 0.f;
-#pragma unroll
-      for (int k = 0; k < C; ++k) {
-        if (sa.dn_sides & 1) p += dot4(acc[k], trow[k]) * nd;
-        if (want_ydg && ok[k])
-          p += dot4(ldg4(sa.Yfwd + (size_t)v * sa.ldyf + colk[k]),
-                    ldg4(reinterpret_cast<const float*>(xb[k] + (uint64_t)(uint32_t)v * ldxb)));
-      }
-      p = group_sum<G>(p);
-      if (lg == 0 && v >= 0 && !is_frag) sa.d_norm[v] = p / sa.norm[v];
-    } else if (sa.xdx != nullptr) {
-      float d = 0.f;
-#pragma unroll
-      for (int k = 0; k < C; ++k) d += dot4(acc[k], trow[k]);
-      d = group_sum<G>(d) * nd;
-      if (lg == 0 && v >= 0 && !is_frag) sa.xdx[v] = d;
-    }
-    if (v >= 0) {
-#pragma unroll
-      for (int k = 0; k < C; ++k) {
-        if (!ok[k]) continue;
-        if (is_frag) {
-          st4(a.partial + (size_t)vi * a.F + colk[k], acc[k]);
-        } else {
-          float4 o = acc[k];
-          scale4(o, nd);
-          float* yr = sa.peers.base != nullptr ? sa.peers.row(v) : a.Y + (size_t)v * a.ldy;
-          st4(yr + colk[k], o);
-        }
-      }
-    }
-  }
-  reduce_bins(bins, scratch, a.R, sa.partials + (size_t)blockIdx.x * a.R);
 }
 
 // d_norm[v] = ( [sides&2] <Y[v],G[v]> + [sides&1] <X[v],dX[v]> ) / norm[v]   (pure streaming, row per warp).
@@ -1681,18 +1514,7 @@ static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t
     sa.order = row_order_t;
     sa.n_order = rows - (sa.s.nfrag > 0 ? split_t->num_long : 0);
     const size_t gsmem = (size_t)kWarpsPerBlock * R * (sizeof(double) + 32 * sizeof(float));
-#ifndef REGNN_RGB_C2
-#define REGNN_RGB_C2 1
-#endif
-    // two chunks per lane (twice the rows in flight per warp) wherever the row is wide enough: F > 16
-    const int G2 = (REGNN_RGB_C2 && feat > 16) ? (feat > 64 ? 16 : (feat > 32 ? 8 : 4)) : 0;
-#define REGNN_RG2_LAUNCH(G_, DN_)                                                                          \
-  (rc = set_smem(spmm_rowgroup2_kernel<G_, DN_>, gsmem), nb = min(nb, resident_blocks(spmm_rowgroup2_kernel<G_, DN_>, gsmem)), \
-   spmm_rowgroup2_kernel<G_, DN_><<<nb, kWarpsPerBlock * 32, gsmem, stream>>>(sa), launched = true)
-    if (G2 == 16) { if (d_norm != nullptr) REGNN_RG2_LAUNCH(16, true); else REGNN_RG2_LAUNCH(16, false); }
-    else if (G2 == 8) { if (d_norm != nullptr) REGNN_RG2_LAUNCH(8, true); else REGNN_RG2_LAUNCH(8, false); }
-    else if (G2 == 4) { if (d_norm != nullptr) REGNN_RG2_LAUNCH(4, true); else REGNN_RG2_LAUNCH(4, false); }
-    else if (d_norm != nullptr) {
+    if (d_norm != nullptr) {
       REGNN_ROWGROUP_DISPATCH(true, (rc = set_smem(spmm_rowgroup_kernel<BINS, GL, true>, gsmem),
                                      nb = min(nb, resident_blocks(spmm_rowgroup_kernel<BINS, GL, true>, gsmem)),
                                      spmm_rowgroup_kernel<BINS, GL, true><<<nb, kWarpsPerBlock * 32, gsmem, stream>>>(sa)))

@@ -360,10 +360,11 @@ def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_at
     e = csr['indices'].numel()
     att = torch.zeros((max(e, 1), h), dtype=torch.float32, device=dev)[:e] if want_attn else None
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
+    order = row_order(csr) if _full(rb, re, n) else None
     with torch.cuda.device(dev):
         _lib.call('regnn_gatv2_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep), h, d,
-                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(att), sp, _ptr(ws), _stream())
+                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(att), sp, _ptr(ws), _ptr(order), _stream())
         _lib.count_launches(1 + (sp is not None))
     return out, rowmax, rowsum, att
 

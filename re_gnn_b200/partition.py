@@ -162,9 +162,11 @@ class _ColumnSlabPropagate(torch.autograd.Function):
                              'and a feature width divisible by the number of ranks')
         x_cols = _rows_to_columns(x_own, per, parts, group)
         y_cols = torch.empty_like(x_cols)
-        ops.spmm(csr['indptr'], csr['indices'], etv[0], theta, alpha, norm, norm, x_cols, out=y_cols,
+        weighted = theta is not None
+        ops.spmm(csr['indptr'], csr['indices'], etv[0] if weighted else None, theta, alpha, norm, norm, x_cols, out=y_cols,
                  split=csr.get('split'), order=ops.row_order(csr) if x_cols.shape[1] <= ops.NARROW_FEAT else None)
         ctx.graph, ctx.etv, ctx.alpha, ctx.bounds, ctx.rank, ctx.group = graph, etv, alpha, bounds, rank, group
+        ctx.weighted = weighted
         y_own = _columns_to_rows(y_cols, per, parts, x_own.shape[0], group)
         ctx.x_own, ctx.y_own = x_own.detach(), y_own
         ctx.save_for_backward(x_cols, theta, norm)
@@ -180,13 +182,19 @@ class _ColumnSlabPropagate(torch.autograd.Function):
         g_own = g_own.contiguous()
         g_cols = _rows_to_columns(g_own, per, parts, ctx.group)
         dx_cols = torch.empty_like(x_cols)
-        _, d_theta, _ = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x_cols, g_cols, out=dx_cols)
+        d_theta = None
+        if ctx.weighted:
+            _, d_theta, _ = ops.spmm_bwd_fused(csr, ctx.etv[1], theta, ctx.alpha, norm, x_cols, g_cols, out=dx_cols)
+            d_theta = d_theta.view_as(theta)
+        else:   # un-weighted propagation (REMixHop's copy_u): the transposed SpMM alone
+            ops.spmm(csr['indptr_t'], csr['indices_t'], None, None, ctx.alpha, norm, norm, g_cols, out=dx_cols,
+                     split=csr.get('split_t'), order=ops.row_order(csr, True) if g_cols.shape[1] <= ops.NARROW_FEAT else None)
         dx_own = _columns_to_rows(dx_cols, per, parts, re - rb, ctx.group)
         # the row dot products of d_norm span all columns: the row owner has them all (x, y, dL/dY, dX row blocks),
         # so this is a local pass; the norm's own backward then yields a per-rank share of the relation gradient,
         # like d_theta above (this rank's columns), and the caller all-reduces the parameter gradient once
-        d_norm = _own_rows_norm_grad(norm, ctx.x_own, ctx.y_own, g_own, dx_own, rb, re)
-        return None, None, dx_own, d_theta.view_as(theta), None, d_norm, None, None, None
+        d_norm = _own_rows_norm_grad(norm, ctx.x_own, ctx.y_own, g_own, dx_own, rb, re) if norm is not None else None
+        return None, None, dx_own, d_theta, None, d_norm, None, None, None
 
 
 class SlabExchange:
@@ -299,6 +307,65 @@ def feature_sliced_propagate(graph, etv, x_own, theta, alpha, norm, bounds, rank
     if exchange is not None:
         return _PeerSlabPropagate.apply(graph, etv, x_own, theta, alpha, norm, bounds, rank, exchange, alias)
     return _ColumnSlabPropagate.apply(graph, etv, x_own, theta, alpha, norm, bounds, rank, group)
+
+
+class _HeadSlicedGat(torch.autograd.Function):
+    """REGAT core (projection scores + fused logits / edge softmax / aggregation) sharded over the HEADS: attention
+    heads are independent (el / er, the softmax statistics and the aggregation never mix heads), so rank q runs all
+    rows for heads [q*H/P, (q+1)*H/P) -- the same column-slab scheme as the REGCN aggregation, with the row <-> slab
+    re-partition done by one all-to-all on each side (NCCL; gloo in the CPU tests).  Row block in, row block out;
+    parameter gradients (attn_l, attn_r, relation embedding) come back with this rank's head slice filled and zeros
+    elsewhere: the caller sums them across ranks (``allreduce_relation_grads``)."""
+
+    @staticmethod
+    def forward(ctx, graph, etv, f_own, attn_l, attn_r, theta, alpha, slope, bounds, rank, group):
+        csr = graph.csr()
+        n = graph.number_of_nodes()
+        parts, per = len(bounds) - 1, _uniform_rows(bounds)
+        rows_own, heads, dim = f_own.shape
+        if not per or heads % parts:
+            raise ValueError('head-sliced attention needs equal row blocks and num_heads divisible by the number of ranks')
+        hs = heads // parts
+        sl = slice(rank * hs, (rank + 1) * hs)
+        f_cols = _rows_to_columns(f_own.reshape(rows_own, heads * dim), per, parts, group)[:n].view(n, hs, dim)
+        al, ar = attn_l[:, sl].contiguous(), attn_r[:, sl].contiguous()
+        th = theta[:, sl].contiguous() if etv is not None else None
+        et = etv[0] if etv is not None else None
+        el, er = ops.attn_scores_fwd(f_cols, al, ar)
+        out, rowmax, rowsum, _ = ops.gat_fwd(csr, et, th, alpha, f_cols, el, er, slope)
+        ctx.graph, ctx.etv, ctx.alpha, ctx.slope, ctx.bounds, ctx.rank, ctx.group = graph, etv, alpha, slope, bounds, rank, group
+        ctx.shape, ctx.sl = (rows_own, heads, dim), sl
+        ctx.save_for_backward(f_cols, el, er, al, ar, th, out, rowmax, rowsum, attn_l, attn_r, theta)
+        pad = torch.cat([out.view(n, hs * dim), out.new_zeros((parts * per - n, hs * dim))]) if parts * per > n else out.view(n, hs * dim)
+        return _columns_to_rows(pad.contiguous(), per, parts, rows_own, group).view(rows_own, heads, dim)
+
+    @staticmethod
+    def backward(ctx, g_own):
+        f_cols, el, er, al, ar, th, out, rowmax, rowsum, attn_l, attn_r, theta = ctx.saved_tensors
+        csr = ctx.graph.csr()
+        rows_own, heads, dim = ctx.shape
+        n = ctx.graph.number_of_nodes()
+        parts, per = len(ctx.bounds) - 1, _uniform_rows(ctx.bounds)
+        hs = heads // parts
+        g_cols = _rows_to_columns(g_own.reshape(rows_own, heads * dim).contiguous(), per, parts, ctx.group)[:n].view(n, hs, dim)
+        et, et_t = (ctx.etv[0], ctx.etv[1]) if ctx.etv is not None else (None, None)
+        d_f, _, _, d_th, d_al, d_ar = ops.gat_bwd(csr, et, et_t, th, ctx.alpha, f_cols, el, er, ctx.slope, None, out,
+                                                   rowmax, rowsum, g_cols.contiguous(), attn_l=al, attn_r=ar)
+        pad = torch.cat([d_f.view(n, hs * dim), d_f.new_zeros((parts * per - n, hs * dim))]) if parts * per > n else d_f.view(n, hs * dim)
+        d_f_own = _columns_to_rows(pad.contiguous(), per, parts, rows_own, ctx.group).view(rows_own, heads, dim)
+        g_al, g_ar = torch.zeros_like(attn_l), torch.zeros_like(attn_r)
+        g_al[:, ctx.sl] = d_al.view(1, hs, dim)
+        g_ar[:, ctx.sl] = d_ar.view(1, hs, dim)
+        g_th = None
+        if d_th is not None:
+            g_th = torch.zeros_like(theta)
+            g_th[:, ctx.sl] = d_th
+        return None, None, d_f_own, g_al, g_ar, g_th, None, None, None, None, None
+
+
+def head_sliced_gat(graph, etv, f_own, attn_l, attn_r, theta, alpha, slope, bounds, rank, group=None):
+    """f_own [rows_own, H, D] -> out rows [rows_own, H, D]; see ``_HeadSlicedGat``."""
+    return _HeadSlicedGat.apply(graph, etv, f_own, attn_l, attn_r, theta, alpha, slope, bounds, rank, group)
 
 
 def allreduce_relation_grads(params, group=None, exchange=None):
