@@ -625,6 +625,15 @@ def run_ours(args, d):
                    'step i+1 streams in behind the kernels of step i; K+1 input copies for K timed steps), relation '
                    'gradient + output checksum copied out'}
 
+    # ---- BASELINE config 5 beside the headline, at the same N: neighbour-sampled minibatch training, data-parallel (weak
+    # scaling).  Every rank takes part; the numbers ride in the line's `others` so the driver's per-N runs record them.
+    ns = None
+    if not args.no_others:
+        try:
+            ns = ns_measure(d, dev, world, rank, 10, 3, sync, barrier)
+        except Exception as ex:   # report, do not hide (all ranks fail or succeed together: same code, same shapes)
+            ns = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -679,12 +688,17 @@ def run_ours(args, d):
     }
     if world > 1:
         line['parity_check'] = parity_check
+    if ns is not None:
+        line.setdefault('others', {})['mag_ns_data_parallel'] = dict(
+            ns, n_gpus=world, scaling='weak',
+            workload='BASELINE config 5: RE-GCN (MAG stack) neighbour-sampled minibatch training, 512 seeds per rank, '
+                     'fan-out [25, 20], hidden 512, gradient all-reduce per step')
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'], _ = cpu_reference_sample(d, f, 3, 1)
     if world == 1 and not args.no_others:
         del x_bufs, g_bufs, xs, y
         torch.cuda.empty_cache()
-        line['others'] = others(dev, 10, 3)
+        line.setdefault('others', {}).update(others(dev, 10, 3))
         line['others'].update(attention_at_hbm_scale(dev, d, g, et, 5, 3))
         line['epoch_time'] = epoch_times(dev, 10, 3)
     print(json.dumps(line))
@@ -693,20 +707,14 @@ def run_ours(args, d):
         dist.destroy_process_group()
 
 
-def run_ns(args, d):
-    """BASELINE config 5: neighbour-sampled minibatch training of the MAG-stack RE-GCN (batch 512 seeds per rank,
-    fan-out [25, 20], 2 layers, hidden 512, 349 classes; mag/regnn_ns.py:41-51,200-208), data-parallel with one
-    gradient all-reduce per step.  Weak scaling: every rank draws its own batches.  value = sampled edges / s."""
+def ns_measure(d, dev, world, rank, steps, warmup, sync, barrier):
+    """Neighbour-sampled minibatch training of the MAG-stack RE-GCN, data-parallel (BASELINE config 5): batch 512 seeds per
+    rank, fan-out [25, 20], 2 layers, hidden 512, 349 classes (mag/regnn_ns.py:41-51,200-208), one gradient all-reduce
+    per step; weak scaling (every rank draws its own batches).  Collective: every rank must call it.  Returns the
+    timing dict (identical on all ranks)."""
     import torch.distributed as dist
     from re_gnn_b200 import Graph, _lib, mag
     from re_gnn_b200.sampling import NeighborSampler
-    world, rank, local = (int(os.environ.get(k, '0' if k != 'WORLD_SIZE' else '1')) for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    sync = torch.cuda.synchronize
-    barrier = (lambda: dist.barrier()) if world > 1 else None
     n, net, sizes = d['num_nodes'], d['num_etype'], d['type_sizes']
     nnt = len(sizes)
     g = Graph(d['src'][:-n], d['dst'][:-n], n).to(dev)        # MAG stack: no stored self loops (self_loop_type 2 adds them)
@@ -738,15 +746,12 @@ def run_ns(args, d):
         state['i'] += 1
         state['edges'] += ne
 
-    sampler_clk = ClockSampler(local)
-    sampler_clk.start()
     l0 = _lib.launch_count
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     state['edges'] = 0
-    total = timed(step, args.steps, 0, sync, barrier)
-    clocks = sampler_clk.stop()
-    launches = (_lib.launch_count - l0) * args.steps // (args.steps + args.warmup)
+    total = timed(step, steps, 0, sync, barrier)
+    launches = (_lib.launch_count - l0) * steps // (steps + warmup)
     edges = torch.tensor([float(state['edges']), total], device=dev, dtype=torch.float64)
     if world > 1:
         tmax = edges[1:].clone()
@@ -756,21 +761,39 @@ def run_ns(args, d):
         total, all_edges = float(tmax.item()), float(esum.item())
     else:
         all_edges = float(state['edges'])
+    return {'gteps_sampled': all_edges / total / 1e9, 'ms_per_step': total / steps * 1e3,
+            'steps_per_s_all_ranks': steps / total * world, 'sampled_edges_per_step': all_edges / steps,
+            'params': sum(p.numel() for p in model.parameters()), 'launches': int(launches), 'batch_size_per_rank': batch_size}
+
+
+def run_ns(args, d):
+    """``--workload mag_ns``: the line of BASELINE config 5 on its own (see ``ns_measure``).  value = sampled edges / s."""
+    import torch.distributed as dist
+    world, rank, local = (int(os.environ.get(k, '0' if k != 'WORLD_SIZE' else '1')) for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    sync = torch.cuda.synchronize
+    barrier = (lambda: dist.barrier()) if world > 1 else None
+    sampler_clk = ClockSampler(local)
+    sampler_clk.start()
+    m = ns_measure(d, dev, world, rank, args.steps, args.warmup, sync, barrier)
+    clocks = sampler_clk.stop()
     if rank == 0:
-        val = all_edges / total / 1e9
-        n_params = sum(p.numel() for p in model.parameters())
-        line = {'metric': 'GTEPS (sampled edges) per neighbour-sampled train step, data-parallel', 'value': val,
+        line = {'metric': 'GTEPS (sampled edges) per neighbour-sampled train step, data-parallel', 'value': m['gteps_sampled'],
                 'unit': 'GTEPS', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': total / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'ms_per_step': m['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': 'RE-GCN (MAG stack) neighbour-sampled minibatch training, BASELINE config 5',
-                           'batch_size_per_rank': batch_size, 'fanout': [25, 20], 'hidden': 512, 'classes': 349,
-                           'params': n_params, 'sampled_edges_per_step': all_edges / args.steps,
+                           'batch_size_per_rank': m['batch_size_per_rank'], 'fanout': [25, 20], 'hidden': 512, 'classes': 349,
+                           'params': m['params'], 'sampled_edges_per_step': m['sampled_edges_per_step'],
                            'l2': 'every step touches a new random batch; feature tables (993 MB) exceed L2'},
                 'clocks': clocks,
-                'e2e': {'value': val, 'unit': 'GTEPS', 'h2d_bytes_per_step': batch_size * 8, 'd2h_bytes_per_step': 4,
+                'e2e': {'value': m['gteps_sampled'], 'unit': 'GTEPS', 'h2d_bytes_per_step': m['batch_size_per_rank'] * 8,
+                        'd2h_bytes_per_step': 4,
                         'note': 'the timed step already starts from pinned-host seed ids and ends with the loss on the host'},
-                'gpu_launches': int(launches), 'steps_per_s': args.steps / total * world}
+                'gpu_launches': m['launches'], 'steps_per_s': m['steps_per_s_all_ranks']}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

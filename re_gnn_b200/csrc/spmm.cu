@@ -143,9 +143,12 @@ __global__ void spmm_frag_finalize_peer_kernel(const int32_t* __restrict__ long_
 // rows [0, rows) x all F columns are cut into P column slices; slice q lands in rank q's slab
 // [P*per, F/P] at row row_offset + i.  Per peer the destination is ONE contiguous range, written with
 // coalesced 128-bit stores (full NVLink packets); the strided side is the local read.
+// Peers are visited in a rank-rotated order (rank r starts with peer r, then r+1, ...): blocks are scheduled y-major, so
+// without the rotation every rank would write to peer 0 first, then peer 1, ... -- P senders on one receiver's NVLink
+// ingress while the other links idle (measured at 8 GPUs: 0.35 ms per 109 MB push, 311 GB/s per rank).
 __global__ void rows_to_slabs_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int Fc,
-                                     int64_t row_offset, float* const* __restrict__ peer_slabs) {
-  const int q = blockIdx.y;
+                                     int64_t row_offset, float* const* __restrict__ peer_slabs, int first_peer) {
+  const int q = (int)((blockIdx.y + (unsigned)first_peer) % gridDim.y);
   const int L = Fc >> 2;  // 128-bit chunks per slab row
   const int64_t total = rows * L;
   float4* dst = reinterpret_cast<float4*>(peer_slabs[q]) + row_offset * L;
@@ -1447,8 +1450,11 @@ extern "C" int regnn_rows_to_slabs(const float* X, int64_t ldx, int64_t num_rows
   const int64_t total = num_rows * (Fc / 4);
   const int64_t want = (total + 255) / 256;
   const unsigned bx = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  // this rank's index = row_offset / rows-per-rank; any rotation that differs per rank spreads the traffic, so the row
+  // offset itself (taken modulo the rank count of a block-sized stride) is enough when num_rows > 0
+  const int first_peer = (int)((row_offset / (num_rows > 0 ? num_rows : 1)) % num_ranks);
   rows_to_slabs_kernel<<<dim3(bx, (unsigned)num_ranks), 256, 0, (cudaStream_t)stream>>>(X, ldx, num_rows, Fc, row_offset,
-                                                                                     peer_slabs);
+                                                                                     peer_slabs, first_peer);
   return check_launch("regnn_rows_to_slabs");
 }
 
