@@ -230,9 +230,9 @@ def others(dev, steps, warmup):
         mod = ctor(d['num_relations']).to(dev)
         mod.edge_weight.data.copy_(theta_init(d['num_relations'], mod.edge_weight.shape[1]))
         x = torch.randn(d['num_nodes'], fin, device=dev, requires_grad=True)
-        out = mod(g, x, et)
-        gout = torch.randn_like(out)
-        ts = []
+        with torch.no_grad():
+            gout = torch.randn_like(mod(g, x, et))   # no autograd graph kept alive (its AccumulateGrad node would pin x's
+        ts = []                                      # gradient accumulation to this stream and break the capture below)
         for i in range(warmup + steps):
             x.grad = None
             mod.zero_grad(set_to_none=True)
@@ -373,7 +373,13 @@ def epoch_times(dev, steps, warmup):
 
         t = timed(epoch, steps, warmup, torch.cuda.synchronize) / steps
         res[name] = {'epoch_ms': t * 1e3, 'num_edges': int(d['src'].size), 'num_nodes': int(d['num_nodes']),
-                     'definition': 'train step + no-grad eval forward (run_regnn.py:144-159)'}
+                     'definition': 'train step + no-grad eval forward (run_regnn.py:144-159); dense projections in true '
+                                   'fp32 (TF32 off), as the parity runs'}
+        # the same epoch with PyTorch's TF32 tensor-core GEMMs for the dense projections (what a user who does not need
+        # 1e-5 parity would run; our kernels are unaffected: they have no GEMM)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        res[name]['epoch_ms_tf32_projections'] = timed(epoch, steps, warmup, torch.cuda.synchronize) / steps * 1e3
+        torch.backends.cuda.matmul.allow_tf32 = False
         # the same epoch captured once into a CUDA graph and replayed: these graphs are launch-bound
         try:
             side = torch.cuda.Stream()

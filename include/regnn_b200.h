@@ -48,6 +48,7 @@ extern "C" {
 
 #define REGNN_MAX_RELATIONS 200 /* uint8 edge types; the backward kernels keep 8 x R x 32 lane-local bins in shared memory */
 #define REGNN_MAX_HEADS 32
+#define REGNN_MAX_NODE_TYPES 16 /* regnn_grouped_linear_*: node types per launch */
 
 /* Long-row decomposition of one CSR view (built once per graph by the host, see re_gnn_b200/graph.py):
  * rows with more than `threshold` slots are cut into fragments of `threshold` consecutive slots so that
@@ -358,6 +359,30 @@ int regnn_sample_neighbors(const int32_t* indptr, const int64_t* targets, int64_
  * walks[i*(walk_length+1) + s] is the node after s steps.  Counter-based, bit-exact with the oracle. */
 int regnn_random_walk(const int32_t* indptr_t, const int32_t* indices_t, int64_t num_nodes, int64_t num_roots,
                       int walk_length, uint64_t key, int64_t* walks, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grouped per-node-type input projection (model/REGCN.py:36-39, model/REGAT.py:56-58, model/REMixHop.py:89-92:
+ * `fc_list[t](features_list[t])` per type + torch.cat; mag/regnn_ns.py:300-326 `group_input`: per type a boolean mask,
+ * an index_select of the type's feature table, a Linear and a masked scatter):
+ *   out[i,:] = W[type(i)] * x_{type(i)}[row(i),:] + b[type(i)]          for all node types in ONE launch.
+ * Rows are visited in type-sorted order: seg_ptr[t] .. seg_ptr[t+1] are the sorted positions of type t (device array,
+ * [T+1] int32), perm maps a sorted position to its row of `out` (NULL: rows already type-contiguous), local_idx maps a row
+ * of `out` to the row of its type's table (NULL: position inside the segment).  x / ldx / k / w / b are HOST arrays of
+ * length num_types (device pointers, leading dimensions, input widths; b or b[t] may be NULL); W[t] is nn.Linear's
+ * [n_out, k[t]] row-major.  fp32 in and out; the products run on the tensor pipe as 3 x TF32 (split operands, fp32
+ * accumulate), which keeps fp32 GEMM accuracy. */
+int regnn_grouped_linear_fwd(int num_types, const float* const* x, const int64_t* ldx, const int* k,
+                             const float* const* w, const float* const* b, int n_out, int64_t num_rows,
+                             const int32_t* seg_ptr, const int64_t* perm, const int64_t* local_idx, float* out,
+                             int64_t ldo, void* stream);
+
+/* Weight / bias gradients of the above: dw_partials[t] is [splits, n_out, k[t]], db_partials[t] (optional) is
+ * [splits, n_out]; split s holds the sum over the s-th part of the type's rows (row order, deterministic) -- the caller
+ * adds the `splits` partials in order.  dout: dL/d out [num_rows, n_out] (leading dimension ldo). */
+int regnn_grouped_linear_bwd(int num_types, const float* const* x, const int64_t* ldx, const int* k, int n_out,
+                             int64_t num_rows, const int32_t* seg_ptr, const int64_t* perm, const int64_t* local_idx,
+                             const float* dout, int64_t ldo, int splits, float* const* dw_partials,
+                             float* const* db_partials, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libregnn_b200.so')
-SOURCES = ['api.cu', 'csr_build.cu', 'spmm.cu', 'gat.cu', 'sample.cu']
+SOURCES = ['api.cu', 'csr_build.cu', 'spmm.cu', 'gat.cu', 'sample.cu', 'grouped_linear.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC']
 

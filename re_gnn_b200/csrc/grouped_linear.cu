@@ -33,16 +33,13 @@ struct GroupedArgs {
   int splits;
 };
 
-constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;   // block tile; 4 warps as 2 x 2, each 32 x 32 (2 x 4 mma tiles)
+constexpr int BM = 64, BN = 64, BK = 32, PAD = 4;   // block tile; 4 warps as 2 x 2, each 32 x 32 (2 x 4 mma tiles)
+constexpr int LDT = BK + PAD;                          // shared-memory row pitch (words): fragment loads conflict-free
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
 }
 // D(16x8) += A(16x8, row) * B(8x8, col), TF32 operands, fp32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -51,9 +48,20 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// One BK-deep step of the 64 x 64 block tile: As[m][k], Bs[n][k] (both k-contiguous, row pitch BK + PAD).
-__device__ __forceinline__ void tile_step(const float (*As)[BK + PAD], const float (*Bs)[BK + PAD], int wm, int wn, int lane,
-                                          float (&acc)[2][4][4]) {
+// Operand tiles live in shared memory already split into their two TF32 terms (hi = tf32(x), lo = tf32(x - hi)): the
+// split costs 3 instructions per element and is done ONCE by the thread that stages the element, not by every warp
+// that multiplies with it.
+struct Tiles {
+  uint32_t ah[BM][LDT], al[BM][LDT], bh[BN][LDT], bl[BN][LDT];
+};
+__device__ __forceinline__ void put(uint32_t (*hi)[LDT], uint32_t (*lo)[LDT], int r, int c, float x) {
+  const uint32_t h = to_tf32(x);
+  hi[r][c] = h;
+  lo[r][c] = to_tf32(x - __uint_as_float(h));
+}
+
+// One BK-deep step of the 64 x 64 block tile (A[m][k], B[n][k], both k-contiguous).
+__device__ __forceinline__ void tile_step(const Tiles& s, int wm, int wn, int lane, float (&acc)[2][4][4]) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int kk = 0; kk < BK; kk += 8) {
@@ -61,16 +69,16 @@ __device__ __forceinline__ void tile_step(const float (*As)[BK + PAD], const flo
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int r = wm * 32 + i * 16 + g;
-      split_tf32(As[r][kk + t], ah[i][0], al[i][0]);
-      split_tf32(As[r + 8][kk + t], ah[i][1], al[i][1]);
-      split_tf32(As[r][kk + t + 4], ah[i][2], al[i][2]);
-      split_tf32(As[r + 8][kk + t + 4], ah[i][3], al[i][3]);
+      ah[i][0] = s.ah[r][kk + t];         al[i][0] = s.al[r][kk + t];
+      ah[i][1] = s.ah[r + 8][kk + t];     al[i][1] = s.al[r + 8][kk + t];
+      ah[i][2] = s.ah[r][kk + t + 4];     al[i][2] = s.al[r][kk + t + 4];
+      ah[i][3] = s.ah[r + 8][kk + t + 4]; al[i][3] = s.al[r + 8][kk + t + 4];
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = wn * 32 + j * 8 + g;
-      split_tf32(Bs[c][kk + t], bh[j][0], bl[j][0]);
-      split_tf32(Bs[c][kk + t + 4], bh[j][1], bl[j][1]);
+      bh[j][0] = s.bh[c][kk + t];     bl[j][0] = s.bl[c][kk + t];
+      bh[j][1] = s.bh[c][kk + t + 4]; bl[j][1] = s.bl[c][kk + t + 4];
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -81,6 +89,19 @@ __device__ __forceinline__ void tile_step(const float (*As)[BK + PAD], const flo
         mma_tf32(acc[i][j], ah[i], bh[j]);
       }
   }
+}
+
+constexpr int kFlush = 4;   // k-tiles (of BK) collected in the MMA accumulator before a round-to-nearest flush
+__device__ __forceinline__ void flush_acc(float (&acc)[2][4][4], float (&tot)[2][4][4]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        tot[i][j][q] += acc[i][j][q];
+        acc[i][j][q] = 0.f;
+      }
 }
 
 // Type and row range of forward tile `tile` (tiles are numbered type by type); false when past the last tile.
@@ -100,10 +121,22 @@ __device__ __forceinline__ bool locate_tile(const GroupedArgs& a, int tile, int*
   return false;
 }
 
+// 4 consecutive floats of a row (k .. k+3) with the tail / alignment handled: a 128-bit load when the row allows it
+__device__ __forceinline__ float4 load4(const float* row, int k, int K, bool vec) {
+  if (vec && k + 3 < K) return ldg4(row + k);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < K) v.x = __ldg(row + k);
+  if (k + 1 < K) v.y = __ldg(row + k + 1);
+  if (k + 2 < K) v.z = __ldg(row + k + 2);
+  if (k + 3 < K) v.w = __ldg(row + k + 3);
+  return v;
+}
+
+constexpr int kLd = (BM * BK / 4) / 128;   // float4 loads per thread and operand tile (= 4)
+
 __global__ void __launch_bounds__(128)
 grouped_linear_fwd_kernel(GroupedArgs a) {
-  __shared__ __align__(16) float As[BM][BK + PAD];
-  __shared__ __align__(16) float Bs[BN][BK + PAD];
+  __shared__ __align__(16) Tiles sm;
   __shared__ int64_t src_row[BM], dst_row[BM];
   int type, row0, row1;
   if (!locate_tile(a, blockIdx.x, &type, &row0, &row1)) return;
@@ -114,6 +147,8 @@ grouped_linear_fwd_kernel(GroupedArgs a) {
   const float* X = a.x[type];
   const float* W = a.w[type];
   const int64_t ldx = a.ldx[type];
+  const bool vec_x = (ldx & 3) == 0 && ((uintptr_t)X & 15) == 0;
+  const bool vec_w = (K & 3) == 0 && ((uintptr_t)W & 15) == 0;
   if (tid < BM) {
     const int p = row0 + tid;
     int64_t o = -1, s = 0;
@@ -125,22 +160,43 @@ grouped_linear_fwd_kernel(GroupedArgs a) {
     src_row[tid] = s;
   }
   __syncthreads();
-  float acc[2][4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    // A tile: 64 gathered rows x BK; B tile: 64 weight rows x BK -- 8 scalars per thread each, coalesced along k
+  // The tensor pipe adds into its fp32 accumulator with truncation: over thousands of k steps that bias shows (measured:
+  // 2.5e-5 of max|out| at K = 4231).  The MMA accumulator therefore only collects kFlush k-tiles (128 values of k) and is
+  // then added, round-to-nearest, into a second set of registers.
+  float acc[2][4][4] = {}, tot[2][4][4] = {};
+  float4 pa[kLd], pb[kLd];
+  auto fetch = [&](int k0) {   // global -> registers: 8 threads read the 128 contiguous bytes of one row
 #pragma unroll
-    for (int i = 0; i < (BM * BK) / 128; ++i) {
-      const int e = tid + i * 128;
-      const int r = e / BK, c = e % BK;
-      const int k = k0 + c;
-      As[r][c] = (dst_row[r] >= 0 && k < K) ? __ldg(X + src_row[r] * ldx + k) : 0.f;
-      const int n = n0 + r;
-      Bs[r][c] = (n < a.n_out && k < K) ? __ldg(W + (size_t)n * K + k) : 0.f;
+    for (int i = 0; i < kLd; ++i) {
+      const int e = tid + i * 128, r = e >> 3, k = k0 + (e & 7) * 4;
+      pa[i] = dst_row[r] >= 0 ? load4(X + src_row[r] * ldx, k, K, vec_x) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pb[i] = n0 + r < a.n_out ? load4(W + (size_t)(n0 + r) * K, k, K, vec_w) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  auto stage = [&]() {         // registers -> shared memory, split into the two TF32 terms
+#pragma unroll
+    for (int i = 0; i < kLd; ++i) {
+      const int e = tid + i * 128, r = e >> 3, c = (e & 7) * 4;
+      put(sm.ah, sm.al, r, c, pa[i].x); put(sm.ah, sm.al, r, c + 1, pa[i].y);
+      put(sm.ah, sm.al, r, c + 2, pa[i].z); put(sm.ah, sm.al, r, c + 3, pa[i].w);
+      put(sm.bh, sm.bl, r, c, pb[i].x); put(sm.bh, sm.bl, r, c + 1, pb[i].y);
+      put(sm.bh, sm.bl, r, c + 2, pb[i].z); put(sm.bh, sm.bl, r, c + 3, pb[i].w);
+    }
+  };
+  fetch(0);
+  int since_flush = 0;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    stage();
     __syncthreads();
-    tile_step(As, Bs, wm, wn, lane, acc);
+    if (k0 + BK < K) fetch(k0 + BK);   // the next tile's loads fly behind this tile's MMAs
+    tile_step(sm, wm, wn, lane, acc);
     __syncthreads();
+    if (++since_flush == kFlush) {
+      flush_acc(acc, tot);
+      since_flush = 0;
+    }
   }
+  flush_acc(acc, tot);
   const int g = lane >> 2, t = lane & 3;
   const float* bias = a.b[type];
 #pragma unroll
@@ -153,19 +209,19 @@ grouped_linear_fwd_kernel(GroupedArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int n = n0 + wn * 32 + j * 8 + 2 * t;
-        if (n < a.n_out) a.out[o * a.ldo + n] = acc[i][j][half * 2] + (bias != nullptr ? bias[n] : 0.f);
-        if (n + 1 < a.n_out) a.out[o * a.ldo + n + 1] = acc[i][j][half * 2 + 1] + (bias != nullptr ? bias[n + 1] : 0.f);
+        if (n < a.n_out) a.out[o * a.ldo + n] = tot[i][j][half * 2] + (bias != nullptr ? bias[n] : 0.f);
+        if (n + 1 < a.n_out) a.out[o * a.ldo + n + 1] = tot[i][j][half * 2 + 1] + (bias != nullptr ? bias[n + 1] : 0.f);
       }
     }
 }
 
 // d W_t[n,k] = sum_{rows of type t} dout[row,n] * x_t[src(row),k]   (and d b_t[n] = sum dout[row,n]):
 // block (x: k tile, y: n tile, z: type * splits + split) reduces the rows of its split of the type's segment in order
-// (deterministic), 16 rows per step, and writes ONE partial tile; the caller adds the `splits` partials in split order.
+// (deterministic), BK rows per step, and writes ONE partial tile; the caller adds the `splits` partials in split order.
+// The operand tiles are the TRANSPOSES of row chunks: A[n][row] = dout[row][n], B[k][row] = x[row][k].
 __global__ void __launch_bounds__(128)
 grouped_linear_bwd_w_kernel(GroupedArgs a) {
-  __shared__ __align__(16) float As[BM][BK + PAD];   // dout^T: [n][row]
-  __shared__ __align__(16) float Bs[BN][BK + PAD];   // x^T:    [k][row]
+  __shared__ __align__(16) Tiles sm;
   const int type = blockIdx.z / a.splits, split = blockIdx.z % a.splits;
   const int K = a.k[type];
   const int k0 = blockIdx.x * BN, n0 = blockIdx.y * BM;
@@ -177,32 +233,53 @@ grouped_linear_bwd_w_kernel(GroupedArgs a) {
   const int r_begin = s0 + split * per, r_end = min(s1, r_begin + per);
   const float* X = a.x[type];
   const int64_t ldx = a.ldx[type];
-  float acc[2][4][4] = {};
+  const bool vec_x = (ldx & 3) == 0 && ((uintptr_t)X & 15) == 0;
+  const bool vec_d = (a.ldo & 3) == 0 && ((uintptr_t)a.out & 15) == 0;
+  float acc[2][4][4] = {}, tot[2][4][4] = {};
   float bsum = 0.f;   // thread n < 64 of the k-tile-0 blocks: column sum of dout
-  for (int r0 = r_begin; r0 < r_end; r0 += BK) {
+  float4 pa[kLd], pb[kLd];
+  auto fetch = [&](int r0) {   // 16 threads read the 64 contiguous n (resp. k) values of one row of the chunk
 #pragma unroll
-    for (int i = 0; i < (BM * BK) / 128; ++i) {
-      const int e = tid + i * 128;
-      const int c = e / BM, m = e % BM;          // row r0 + c of the segment, element m of the 64-wide n / k tile
+    for (int i = 0; i < kLd; ++i) {
+      const int e = tid + i * 128, c = e >> 4, m = (e & 15) * 4;
       const int p = r0 + c;
-      float dv = 0.f, xv = 0.f;
+      pa[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p < r_end) {
         const int64_t o = a.perm != nullptr ? a.perm[p] : p;
         const int64_t s = a.local_idx != nullptr ? a.local_idx[o] : p - s0;
-        if (n0 + m < a.n_out) dv = __ldg(a.out + o * a.ldo + n0 + m);
-        if (k0 + m < K) xv = __ldg(X + s * ldx + k0 + m);
+        pa[i] = load4(a.out + o * a.ldo, n0 + m, a.n_out, vec_d);
+        pb[i] = load4(X + s * ldx, k0 + m, K, vec_x);
       }
-      As[m][c] = dv;
-      Bs[m][c] = xv;
     }
-    __syncthreads();
-    if (blockIdx.x == 0 && tid < BM) {
+  };
+  auto stage = [&]() {
 #pragma unroll
-      for (int c = 0; c < BK; ++c) bsum += As[tid][c];
+    for (int i = 0; i < kLd; ++i) {
+      const int e = tid + i * 128, c = e >> 4, m = (e & 15) * 4;
+      put(sm.ah, sm.al, m, c, pa[i].x); put(sm.ah, sm.al, m + 1, c, pa[i].y);
+      put(sm.ah, sm.al, m + 2, c, pa[i].z); put(sm.ah, sm.al, m + 3, c, pa[i].w);
+      put(sm.bh, sm.bl, m, c, pb[i].x); put(sm.bh, sm.bl, m + 1, c, pb[i].y);
+      put(sm.bh, sm.bl, m + 2, c, pb[i].z); put(sm.bh, sm.bl, m + 3, c, pb[i].w);
     }
-    tile_step(As, Bs, wm, wn, lane, acc);
+  };
+  fetch(r_begin);
+  int since_flush = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += BK) {
+    stage();
     __syncthreads();
+    if (r0 + BK < r_end) fetch(r0 + BK);
+    if (blockIdx.x == 0 && tid < BM) {   // d b: column sums of dout, rows in order (hi + lo restores the fp32 value to ~2^-22)
+#pragma unroll 8
+      for (int c = 0; c < BK; ++c) bsum += __uint_as_float(sm.ah[tid][c]) + __uint_as_float(sm.al[tid][c]);
+    }
+    tile_step(sm, wm, wn, lane, acc);
+    __syncthreads();
+    if (++since_flush == kFlush) {
+      flush_acc(acc, tot);
+      since_flush = 0;
+    }
   }
+  flush_acc(acc, tot);
   const int g = lane >> 2, t = lane & 3;
   float* dw = a.dw[type] + (size_t)split * a.n_out * K;
 #pragma unroll
@@ -214,8 +291,8 @@ grouped_linear_bwd_w_kernel(GroupedArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = k0 + wn * 32 + j * 8 + 2 * t;
-        if (k < K) dw[(size_t)n * K + k] = acc[i][j][half * 2];
-        if (k + 1 < K) dw[(size_t)n * K + k + 1] = acc[i][j][half * 2 + 1];
+        if (k < K) dw[(size_t)n * K + k] = tot[i][j][half * 2];
+        if (k + 1 < K) dw[(size_t)n * K + k + 1] = tot[i][j][half * 2 + 1];
       }
     }
   if (blockIdx.x == 0 && tid < BM && a.db[type] != nullptr && n0 + tid < a.n_out)

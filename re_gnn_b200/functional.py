@@ -218,3 +218,57 @@ class _GatV2Aggregate(torch.autograd.Function):
 
 def gatv2_aggregate(graph, etv, fs, fd, attn, theta, alpha, slope, keep=None, want_attn=False, softmax_eps=0.0):
     return _GatV2Aggregate.apply(graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn, softmax_eps)
+
+
+class _GroupedLinear(torch.autograd.Function):
+    """All per-node-type input projections in one launch (model/REGCN.py:36-39 ``fc_list`` + cat,
+    mag/regnn_ns.py:300-326 ``group_input``).  Differentiable w.r.t. the weights and biases; the feature tables are
+    inputs of the model (no gradient)."""
+
+    @staticmethod
+    def forward(ctx, seg_ptr, perm, local_idx, num_rows, num_types, *tensors):
+        tables = tensors[:num_types]
+        weights = tensors[num_types:2 * num_types]
+        biases = tensors[2 * num_types:3 * num_types]
+        if any(x.requires_grad for x in tables):
+            raise NotImplementedError('grouped_linear: gradients w.r.t. the feature tables are not built '
+                                      '(the reference feeds fixed input features here)')
+        out = ops.grouped_linear_fwd(tables, weights, biases, seg_ptr, perm, local_idx, num_rows)
+        ctx.meta = (seg_ptr, perm, local_idx, num_types, weights[0].shape[0], [b is not None for b in biases])
+        ctx.save_for_backward(*tables)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        seg_ptr, perm, local_idx, num_types, n_out, has_bias = ctx.meta
+        dws, dbs = ops.grouped_linear_bwd(ctx.saved_tensors, n_out, seg_ptr, perm, local_idx, dout.contiguous(), any(has_bias))
+        dbs = [d if h else None for d, h in zip(dbs, has_bias)] if dbs is not None else [None] * num_types
+        return (None, None, None, None, None) + (None,) * num_types + tuple(dws) + tuple(dbs)
+
+
+_SEG_PTR_CACHE = {}
+
+
+def grouped_linear(tables, weights, biases, node_type=None, local_idx=None):
+    """``tables[t]``: [n_t, K_t] features of node type t; ``weights[t]`` / ``biases[t]``: its nn.Linear parameters.
+    ``node_type`` / ``local_idx`` ([M] int64): the type of output row i and its row in that type's table
+    (mag/regnn_ns.py:300-326).  Both None: the output is the concatenation of all tables' projections in type order
+    (model/REGCN.py:36-39).  -> [M, n_out].  No host synchronisation either way."""
+    t = len(tables)
+    dev = tables[0].device
+    if node_type is None:
+        sizes = tuple(int(x.shape[0]) for x in tables)
+        key = (sizes, str(dev))
+        if key not in _SEG_PTR_CACHE:    # one host -> device copy per distinct shape (keeps the call graph-capturable)
+            _SEG_PTR_CACHE[key] = torch.tensor((0,) + sizes, dtype=torch.int64).cumsum(0).to(device=dev, dtype=torch.int32)
+        seg_ptr = _SEG_PTR_CACHE[key]
+        perm, num_rows = None, sum(sizes)
+    else:
+        perm = torch.sort(node_type, stable=True).indices
+        counts = torch.bincount(node_type, minlength=t)[:t]
+        seg_ptr = torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(torch.int32)
+        num_rows = int(node_type.numel())
+        local_idx = local_idx.to(torch.int64).contiguous()
+    bs = [b if b is not None else None for b in biases]
+    # autograd.Function cannot take None tensors positionally in *args for differentiable slots: pass them through as is
+    return _GroupedLinear.apply(seg_ptr, perm, local_idx, num_rows, t, *tables, *weights, *bs)

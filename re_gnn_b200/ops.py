@@ -406,3 +406,58 @@ def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
                   rb, re, _ptr(d_fs), sp, _ptr(ws), _stream())
         _lib.count_launches(1 + (sp is not None))
     return d_fs
+
+
+# ---- grouped per-node-type input projection ---------------------------------------------------------------------
+GROUPED_BWD_SPLITS = 8
+
+
+def _host_ptrs(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def _grouped_common(tables):
+    t = len(tables)
+    ldx = (ctypes.c_int64 * t)(*[x.stride(0) for x in tables])
+    k = (ctypes.c_int * t)(*[x.shape[1] for x in tables])
+    return ldx, k
+
+
+def grouped_linear_fwd(tables, weights, biases, seg_ptr, perm, local_idx, num_rows):
+    """out[i] = W[t(i)] x_{t(i)}[row(i)] + b[t(i)] for all node types in one launch (regnn_grouped_linear_fwd).
+    ``tables`` / ``weights`` / ``biases``: per-type lists ([n_t, K_t] fp32; nn.Linear [n_out, K_t]; [n_out] or None);
+    ``seg_ptr`` int32 [T+1] on the device; ``perm`` / ``local_idx`` int64 device tensors or None."""
+    tables = [_f32(x) for x in tables]
+    weights = [_f32(w) for w in weights]
+    biases = [_f32(b) if b is not None else None for b in biases]
+    n_out = weights[0].shape[0]
+    dev = tables[0].device
+    out = torch.empty((num_rows, n_out), dtype=torch.float32, device=dev)
+    ldx, k = _grouped_common(tables)
+    with torch.cuda.device(dev):
+        _lib.call('regnn_grouped_linear_fwd', len(tables), _host_ptrs(tables), ldx, k, _host_ptrs(weights),
+                  _host_ptrs(biases), n_out, int(num_rows), _ptr(seg_ptr), _ptr(perm), _ptr(local_idx), _ptr(out),
+                  out.stride(0), _stream())
+        _lib.count_launches(1)
+    return out
+
+
+def grouped_linear_bwd(tables, n_out, seg_ptr, perm, local_idx, dout, want_bias):
+    """-> (per-type weight gradients [n_out, K_t], per-type bias gradients [n_out] | None): regnn_grouped_linear_bwd
+    writes ``GROUPED_BWD_SPLITS`` deterministic partials per type, added here in split order."""
+    tables = [_f32(x) for x in tables]
+    dout = _f32(dout)
+    dev = dout.device
+    s = GROUPED_BWD_SPLITS
+    dwp = [torch.empty((s, n_out, x.shape[1]), dtype=torch.float32, device=dev) for x in tables]
+    dbp = [torch.empty((s, n_out), dtype=torch.float32, device=dev) for _ in tables] if want_bias else None
+    ldx, k = _grouped_common(tables)
+    with torch.cuda.device(dev):
+        _lib.call('regnn_grouped_linear_bwd', len(tables), _host_ptrs(tables), ldx, k, n_out, dout.shape[0], _ptr(seg_ptr),
+                  _ptr(perm), _ptr(local_idx), _ptr(dout), dout.stride(0), s, _host_ptrs(dwp),
+                  _host_ptrs(dbp) if want_bias else None, _stream())
+        _lib.count_launches(1)
+    return [p.sum(dim=0) for p in dwp], ([p.sum(dim=0) for p in dbp] if want_bias else None)

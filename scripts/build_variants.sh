@@ -16,7 +16,7 @@ wait
 for spec in "$@"; do
   tag="${spec%%:*}"
   objs=""
-  for o in api csr_build spmm gat sample; do
+  for o in api csr_build spmm gat sample grouped_linear; do
     if [ $o = $SRC ]; then objs="$objs build/var/${SRC}_$tag.o"; else objs="$objs build/obj/$o.o"; fi
   done
   nvcc -shared -o variants/libregnn_$tag.so $objs -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -cudart static

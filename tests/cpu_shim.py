@@ -290,6 +290,41 @@ def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
     return torch.zeros_like(fs).index_add(0, src, msg)
 
 
+def _grouped_rows(tables, seg_ptr, perm, local_idx, num_rows):
+    """(type of every output row, row of its table) from the sorted-segment description of the C ABI."""
+    seg = seg_ptr.long()
+    pos_type = torch.repeat_interleave(torch.arange(len(tables)), seg[1:] - seg[:-1])
+    rows = perm.long() if perm is not None else torch.arange(num_rows)
+    typ = torch.empty(num_rows, dtype=torch.long)
+    typ[rows] = pos_type
+    if local_idx is not None:
+        src = local_idx.long()
+    else:
+        src = torch.empty(num_rows, dtype=torch.long)
+        src[rows] = torch.arange(num_rows) - seg[pos_type]
+    return typ, src
+
+
+def grouped_linear_fwd(tables, weights, biases, seg_ptr, perm, local_idx, num_rows):
+    typ, src = _grouped_rows(tables, seg_ptr, perm, local_idx, num_rows)
+    out = torch.zeros((num_rows, weights[0].shape[0]), dtype=tables[0].dtype)
+    for t, (x, w, b) in enumerate(zip(tables, weights, biases)):
+        m = typ == t
+        y = x.detach()[src[m]] @ w.detach().t()
+        out[m] = y + b.detach() if b is not None else y
+    return out
+
+
+def grouped_linear_bwd(tables, n_out, seg_ptr, perm, local_idx, dout, want_bias):
+    typ, src = _grouped_rows(tables, seg_ptr, perm, local_idx, dout.shape[0])
+    dws, dbs = [], []
+    for t, x in enumerate(tables):
+        m = typ == t
+        dws.append(dout[m].t() @ x.detach()[src[m]])
+        dbs.append(dout[m].sum(0))
+    return dws, (dbs if want_bias else None)
+
+
 def sampler_sample_slots(self, targets, fanout, key):
     from oracle import sampler_oracle
     return torch.as_tensor(sampler_oracle.sample_slots(self.graph.csr()['indptr'].numpy(), targets.numpy(), fanout, key))
@@ -308,5 +343,5 @@ def install(monkeypatch):
     monkeypatch.setattr(G.Graph, 'csr', graph_csr)
     monkeypatch.setattr(G.Graph, 'etype_views', graph_etype_views)
     for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'spmm_bwd_fused', 'rowdot_norm_bwd', 'gat_fwd', 'gat_bwd',
-                 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src', 'attn_scores_fwd'):
+                 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src', 'attn_scores_fwd', 'grouped_linear_fwd', 'grouped_linear_bwd'):
         monkeypatch.setattr(ops, name, globals()[name])

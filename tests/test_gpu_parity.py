@@ -946,3 +946,42 @@ def test_mag_full_graph_regat_properties(mag_full, heads, dim):
         # the kernel's running max is the same maximum; its sum is taken relative to it
         assert torch.allclose(rowmax[v].double(), m, rtol=0, atol=1e-6)
         assert torch.allclose(rowsum[v].double(), ssum, rtol=2e-5, atol=0)
+
+
+# ---- grouped per-node-type input projection (one launch for all types, 3 x TF32 products) -------------------------
+@pytest.mark.parametrize('mode,dims,n_out', [('contiguous', (334, 4231, 50, 20), 64), ('sampled', (128, 128, 128, 128), 512),
+                                             ('sampled', (12, 7, 9), 8), ('contiguous', (5,), 3)])
+def test_grouped_linear_vs_float64(mode, dims, n_out):
+    """RF.grouped_linear against a float64 evaluation of the reference's per-type loop (model/REGCN.py:36-39 for
+    type-contiguous rows, mag/regnn_ns.py:300-326 for sampled batches with a type and a table row per output row):
+    outputs, weight and bias gradients.  The products run as 3 x TF32 on the tensor pipe: fp32 GEMM accuracy."""
+    rng = np.random.RandomState(len(dims) * 100 + n_out)
+    t = len(dims)
+    sizes = [int(rng.randint(40, 900)) for _ in dims]
+    tables64 = [helpers.f32_exact(rng.randn(s, k)) for s, k in zip(sizes, dims)]
+    w64 = [helpers.f32_exact(rng.randn(n_out, k) / np.sqrt(k)).requires_grad_(True) for k in dims]
+    b64 = [helpers.f32_exact(rng.randn(n_out) * 0.1).requires_grad_(True) for _ in dims]
+    if mode == 'contiguous':
+        node_type = local_idx = None
+        ref = torch.cat([x @ w.t() + b for x, w, b in zip(tables64, w64, b64)])
+    else:
+        m = 3000
+        node_type = torch.as_tensor(rng.randint(0, t, size=m))
+        node_type[:5] = t - 1                                   # make sure the last type is present
+        local_idx = torch.as_tensor(np.array([rng.randint(0, sizes[int(tt)]) for tt in node_type]))
+        ref = torch.zeros(m, n_out, dtype=torch.float64)
+        for tt in range(t):
+            mask = node_type == tt
+            ref[mask] = tables64[tt][local_idx[mask]] @ w64[tt].t() + b64[tt]
+    gout = helpers.f32_exact(rng.randn(*ref.shape))
+    ref.backward(gout)
+    tables = [x.to(DEV, torch.float32) for x in tables64]
+    w = [p.detach().to(DEV, torch.float32).requires_grad_(True) for p in w64]
+    b = [p.detach().to(DEV, torch.float32).requires_grad_(True) for p in b64]
+    out = RF.grouped_linear(tables, w, b, node_type.to(DEV) if node_type is not None else None,
+                            local_idx.to(DEV) if local_idx is not None else None)
+    out.backward(gout.to(DEV, torch.float32))
+    helpers.assert_close(out.detach().cpu(), ref.detach(), RTOL, 'grouped_linear out')
+    for tt in range(t):
+        helpers.assert_close(w[tt].grad.cpu(), w64[tt].grad, 2 * RTOL, 'grouped_linear d_W[%d]' % tt)
+        helpers.assert_close(b[tt].grad.cpu(), b64[tt].grad, 2 * RTOL, 'grouped_linear d_b[%d]' % tt)
