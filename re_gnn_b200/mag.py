@@ -16,9 +16,22 @@ from . import functional as RF
 from .graph import Graph
 
 
+import os as _os
+
+# REGNN_GROUPED_INPUT=0: the reference's per-type loop (mask / gather / Linear / scatter) instead of the grouped launch
+USE_GROUPED_INPUT = _os.environ.get('REGNN_GROUPED_INPUT', '1') != '0'
+
+
 def _grouped_input(lins, x_dict, node_type, local_node_idx):
     """Per-type input projection of a batch of nodes: types must be the keys 0 .. T-1 of ``x_dict`` (as in ogbn-mag's
     ``group_hetero_graph`` numbering)."""
+    if not USE_GROUPED_INPUT or not node_type.is_cuda:
+        width = next(iter(lins.values())).out_features
+        h = torch.zeros((node_type.size(0), width), device=node_type.device, dtype=next(iter(lins.values())).weight.dtype)
+        for key, x in x_dict.items():
+            mask = node_type == key
+            h[mask] = lins[str(key)](x[local_node_idx[mask]])
+        return h
     keys = sorted(x_dict.keys())
     if keys != list(range(len(keys))):
         raise ValueError('node types must be numbered 0 .. T-1')
