@@ -320,8 +320,11 @@ int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t
     float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */,
     const int32_t* row_order /* as regnn_gat_fwd */, void* stream);
 
-/* Backward, destination-major pass: a_csr = a*keep, dl_csr = dL/dl (both [E,H] slot order),
- * d_fd [N,H,D], d_attn [H,D], d_theta [R,H].
+/* Backward, destination-major pass: a_csr = a*keep, dl_csr = dL/dl (both [E,H] slot order), d_fd [N,H,D], d_attn [H,D],
+ * d_theta [R,H], and qmask: per (slot, 128-float slice of the H*D row) a 128-bit sign mask of q = fs[src]+fd[dst]
+ * (uint32 [E, ceil(H*D/128), 4]; bit l of word c = component c of the l-th 128-bit chunk of the slice is > 0) -- the
+ * derivative LeakyReLU'(q) is one bit per feature, so the source-major pass reads 16 bytes per edge instead of
+ * gathering the 4HD-byte row fd[dst] again.
  * partials: double [regnn_max_partial_blocks() * (R*H + H*D)]. */
 int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
                         const uint8_t* etype_csr, const float* theta, float alpha,
@@ -329,19 +332,19 @@ int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices, const int
                         float negative_slope, const float* keep, const float* out,
                         const float* rowmax, const float* rowsum, const float* G, int num_heads,
                         int head_dim, int64_t row_begin, int64_t row_end, float* a_csr,
-                        float* dl_csr, float* d_fd, float* d_attn, double* partials, float* d_theta,
+                        float* dl_csr, uint32_t* qmask, float* d_fd, float* d_attn, double* partials, float* d_theta,
                         const regnn_rowsplit_t* split,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, const int32_t* row_order, void* stream);
 
 /* Backward, source-major pass:
  *   d_fs[u,h,d] = sum_{j in Out(u)} ( a_csr[s,h]*G[v,h,d]
  *                                   + dl_csr[s,h]*attn[h,d]*LeakyReLU'(fs[u,h,d]+fd[v,h,d]) ),
- *   s = slot_t[j], v = indices_t[j]. */
+ *   s = slot_t[j], v = indices_t[j]; the derivative comes from qmask (1 where the bit is set, else negative_slope). */
 int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
-                        const float* a_csr, const float* dl_csr, const float* fs, const float* fd,
-                        const float* attn, float negative_slope, const float* G, int num_heads,
-                        int head_dim, int64_t row_begin, int64_t row_end, float* d_fs, const regnn_rowsplit_t* split_t /* of the transposed view */,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
+                        const float* a_csr, const float* dl_csr, const uint32_t* qmask, const float* attn,
+                        float negative_slope, const float* G, int num_heads, int head_dim, int64_t row_begin,
+                        int64_t row_end, float* d_fs, const regnn_rowsplit_t* split_t /* of the transposed view */,
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, const int32_t* row_order_t, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Neighbour sampling for the sampled-minibatch path (replaces torch_sparse's CPU `sample_adj` behind

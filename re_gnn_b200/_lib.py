@@ -54,8 +54,8 @@ SIGNATURES = {
     'regnn_gatv2_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
                                _p, _p, _p, _p, _p, _p, _p, _p]),
     'regnn_gatv2_bwd_dst': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p,
-                                   _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    'regnn_gatv2_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64, _p, _p, _p, _p]),
+                                   _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'regnn_gatv2_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
 }
 
 

@@ -769,189 +769,244 @@ gatv2_fwd_rg_kernel(AttnArgs a) {
 }
 
 // =================================================================================================
-// REGATv2 backward, destination-major: a_csr, dl_csr, d_fd rows, per-block partials of d_attn and
-// of the relation-gradient table.
-// Dynamic smem: w_s[R*H] | per warp: binsw[R*H] | per warp: dat_s[128]
-template <int LPH>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
-gatv2_bwd_dst_kernel(AttnArgs a) {
+// REGATv2 backward.  Two gather passes are inherent (d_fd is a destination-side, d_fs a source-side reduction of an
+// [E,H,D]-sized quantity), but the source-major pass no longer gathers fd[dst] to rebuild LeakyReLU'(fs[u]+fd[v]):
+// that derivative is one BIT per feature (q > 0 ? 1 : slope), so the destination-major pass, which has q in registers,
+// stores a 128-bit sign mask per (slot, 128-float slice) -- four warp ballots -- and the source-major pass reads 16
+// bytes instead of gathering a 4HD-byte row: 616 instead of 1100 bytes per edge at H*D = 128.
+//
+// Destination-major (row groups over the degree-sorted rows, persistent grid; a warp keeps ONE 128-float slice for all
+// its rows so that its d_attn share accumulates in registers): recomputes logits and a, dl = a*keep*da - a*S, writes
+// a*keep and dl per (slot, head) and the sign mask, accumulates d_fd rows, d_attn and lane-group-local relation bins.
+// Dynamic smem: w_s[R*H] | per warp: bins[R*H][GPW] | per warp: dat[128]
+#ifndef REGNN_V2D_BLOCKS
+#define REGNN_V2D_BLOCKS 4
+#endif
+template <int G, int LPH>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_V2D_BLOCKS)
+gatv2_bwd_dst_rg_kernel(AttnArgs a, uint32_t* __restrict__ qmask) {
+  constexpr int GPW = 32 / G, U = 2;
   extern __shared__ __align__(16) float smem[];
   const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
-  const int RHp = (RH + 3) & ~3;  // keeps dat_all 16-byte aligned
+  const int RHp = (RH * GPW + 3) & ~3;  // keeps dat_all 16-byte aligned
   float* w_s = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* binsw = smem + RHp + warp * RHp;
-  float* dat_all = smem + RHp * (1 + kWarpsPerBlock);
-  for (int i = lane; i < RH; i += 32) binsw[i] = 0.f;
+  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
+  float* bins = smem + ((RH + 3) & ~3) + (size_t)warp * RHp;
+  float* dat_all = smem + ((RH + 3) & ~3) + (size_t)kWarpsPerBlock * RHp;
+  for (int i = lane; i < RH * GPW; i += 32) bins[i] = 0.f;
   load_rel_table(w_s, a);
-  const int HG = num_groups(a);
-  // every warp keeps ONE head group for all its items (its d_attn slice accumulates in registers): warp wg owns
-  // group wg % HG and walks the row items wg / HG, + usable / HG, ...; the last (nW % HG) warps stay idle
+  const int HG = a.hg_count;
+  const bool has_rel = a.etype != nullptr;
   const int64_t nW = (int64_t)gridDim.x * kWarpsPerBlock, usable = nW - nW % HG;
   const int64_t wg = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  const Group g = make_group(a, (int)(wg % HG), lane);
-  const int64_t row_items = a.nfrag + (a.row_end - a.row_begin);
-  const float* fcol = a.feat + g.col;
-  const float4 at = g.ok ? ldg4(a.el + g.col) : zero4();
+  const int hg = (int)(wg % HG);
+  const int col = hg * 128 + lg * 4;
+  const bool col_ok = col < HD;
+  const int h = col_ok ? (col >> a.d_shift) : 0;
+  const bool head_leader = col_ok && (col & (a.D - 1)) == 0;
+  const int64_t nrows = a.order != nullptr ? a.n_order : (a.row_end - a.row_begin);
+  const int64_t nitems = a.nfrag + nrows;
+  const float4 at = col_ok ? ldg4(a.el + col) : zero4();
+  const char* fbytes = reinterpret_cast<const char*>(a.feat + (col_ok ? col : 0));
+  const uint32_t fpitch = (uint32_t)HD * 4u;
+  const float* w_h = w_s + h;
   float4 dat = zero4();
 
-  for (int64_t ri = wg / HG; wg < usable && ri < row_items; ri += usable / HG) {
-    const WorkItem it = decode_item(a, ri, a.nfrag);
-    if (!it.ok) continue;
-    const int64_t v = it.v;
-    const int s0 = it.s0, len = it.len;
+  for (int64_t rgi = wg / HG; wg < usable && rgi * GPW < nitems; rgi += usable / HG) {
+    // ---- the item of this lane group: a fragment of a long row or a row of the work list
+    const int64_t ri = rgi * GPW + grp;
+    int64_t v = -1, fi = 0;
+    int begin = 0, len = 0;
+    bool frag = false;
+    if (ri < nitems) {
+      if (ri < a.nfrag) {
+        frag = true;
+        fi = ri;
+        const int64_t r = a.frag_row[ri];
+        if (r >= a.row_begin && r < a.row_end) {
+          v = r;
+          begin = a.frag_begin[ri];
+          len = min(a.threshold, a.indptr[r + 1] - begin);
+        }
+      } else {
+        const int64_t r = a.order != nullptr ? (int64_t)a.order[ri - a.nfrag] : a.row_begin + (ri - a.nfrag);
+        const int b = a.indptr[r], l = a.indptr[r + 1] - b;
+        if (l <= a.threshold) {
+          v = r;
+          begin = b;
+          len = l;
+        }
+      }
+    }
+    const bool act = v >= 0 && col_ok;
+    const int maxlen = __reduce_max_sync(0xffffffffu, v >= 0 ? len : 0);
+    if (v < 0) len = 0;
     float4 gv = zero4(), fdv = zero4(), dfd = zero4();
     float part = 0.f, m = 0.f, inv = 0.f;
-    if (g.ok) {
-      gv = ldg4(a.G + (size_t)v * HD + g.col);
-      fdv = ldg4(a.fd + (size_t)v * HD + g.col);
-      part = dot4(ldg4(a.out + (size_t)v * HD + g.col), gv);
-      const size_t vh = (size_t)v * H + g.hl;
-      m = a.rowmax[vh];
-      const float sm = a.rowsum[vh];
+    if (act) {
+      gv = ldg4(a.G + (size_t)v * HD + col);
+      fdv = ldg4(a.fd + (size_t)v * HD + col);
+      part = dot4(ldg4(a.out + (size_t)v * HD + col), gv);
+      const size_t vh = (size_t)v * H + h;
+      m = __ldg(a.rowmax + vh);
+      const float sm = __ldg(a.rowsum + vh);
       inv = sm > 0.f ? 1.f / sm : 0.f;
     }
     const float S = group_sum<LPH>(part);
-    for (int base = 0; base < len; base += 32) {
-      const int cnt = min(32, len - base);
-      const int slot = s0 + base + lane;
-      int idx = 0, et = 0, e = 0;
-      if (lane < cnt) {
-        idx = a.indices[slot];
-        if (a.etype != nullptr) et = a.etype[slot];
-        if (a.keep != nullptr) e = a.eid[slot];
+    const int32_t* ip = a.indices + begin;
+    const uint8_t* ep = a.etype + begin;
+    const int32_t* eidp = a.eid + begin;
+
+    for (int t0 = 0; t0 < maxlen; t0 += G) {
+      int bi = -1, be = 0, beid = 0;
+      {
+        const int t = t0 + lg;
+        if (t < len) {
+          bi = __ldg(ip + t);
+          if (has_rel) be = __ldg(ep + t);
+          if (a.keep != nullptr) beid = __ldg(eidp + t);
+        }
       }
-      for (int j = 0; j < cnt; j += kUA) {
-        float4 x[kUA];
-        float l[kUA], da[kUA];
+      const int cnt = min(G, maxlen - t0);
+      for (int j = 0; j < cnt; j += U) {
+        float4 x[U];
+        int si[U];
 #pragma unroll
-        for (int u = 0; u < kUA; ++u) {
-          const int sidx = __shfl_sync(0xffffffffu, idx, min(j + u, cnt - 1));
-          x[u] = (j + u < cnt && g.ok) ? ldg4(fcol + (size_t)sidx * HD) : zero4();
+        for (int u = 0; u < U; ++u) {
+          si[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+          x[u] = (si[u] >= 0 && col_ok) ? ldg4(reinterpret_cast<const float*>(fbytes + (uint64_t)(uint32_t)si[u] * fpitch))
+                                        : zero4();
         }
 #pragma unroll
-        for (int u = 0; u < kUA; ++u) {
-          l[u] = group_sum<LPH>(dot4(at, leaky4(add4(x[u], fdv), a.slope)));
-          da[u] = group_sum<LPH>(dot4(x[u], gv));
-        }
-#pragma unroll
-        for (int u = 0; u < kUA; ++u) {
-          if (j + u < cnt) {  // warp-uniform
-            const int set = __shfl_sync(0xffffffffu, et, j + u);
-            const int se = __shfl_sync(0xffffffffu, e, j + u);
-            if (g.ok) {
-              const int h = g.hl;
-              float lu = l[u];
-              if (a.etype != nullptr) lu += w_s[set * H + h];
-              const float aa = expf(lu - m) * inv;
-              const float att = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)se * H + h) : aa;
-              const float dl = att * da[u] - aa * S;
-              if (g.leader) {
-                const size_t sh = (size_t)(s0 + base + j + u) * H + h;
-                a.o0[sh] = att;
-                a.o1[sh] = dl;
-                if (a.etype != nullptr) binsw[set * H + h] += dl;
-              }
-              const float4 q = add4(x[u], fdv);
-              dfd.x = fmaf(dl * at.x, leaky_grad(q.x, a.slope), dfd.x);
-              dfd.y = fmaf(dl * at.y, leaky_grad(q.y, a.slope), dfd.y);
-              dfd.z = fmaf(dl * at.z, leaky_grad(q.z, a.slope), dfd.z);
-              dfd.w = fmaf(dl * at.w, leaky_grad(q.w, a.slope), dfd.w);
-              fma4(dat, dl, leaky4(q, a.slope));
+        for (int u = 0; u < U; ++u) {
+          const float4 q = add4(x[u], fdv);
+          const float4 lr = leaky4(q, a.slope);
+          const float l = group_sum<LPH>(dot4(at, lr));
+          const float da = group_sum<LPH>(dot4(x[u], gv));
+          const int se = has_rel ? __shfl_sync(0xffffffffu, be, gbase + j + u) : 0;
+          const int seid = a.keep != nullptr ? __shfl_sync(0xffffffffu, beid, gbase + j + u) : 0;
+          // sign mask of q for the source-major pass: bit (lane) of word c = (q.c > 0)
+          const uint32_t b0 = __ballot_sync(0xffffffffu, q.x > 0.f), b1 = __ballot_sync(0xffffffffu, q.y > 0.f);
+          const uint32_t b2 = __ballot_sync(0xffffffffu, q.z > 0.f), b3 = __ballot_sync(0xffffffffu, q.w > 0.f);
+          if (si[u] >= 0 && act) {
+            const int slot = begin + t0 + j + u;
+            float lu = l;
+            if (has_rel) lu += w_h[se * H];
+            const float aa = __expf(lu - m) * inv;
+            const float att = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)seid * H + h) : aa;
+            const float dl = att * da - aa * S;
+            if (head_leader) {
+              const size_t sh = (size_t)slot * H + h;
+              a.o0[sh] = att;
+              a.o1[sh] = dl;
+              if (has_rel) bins[(se * H + h) * GPW + grp] += dl;
             }
+            if (lg < 4) {
+              const uint32_t wsel = lg == 0 ? b0 : (lg == 1 ? b1 : (lg == 2 ? b2 : b3));
+              qmask[((size_t)slot * HG + hg) * 4 + lg] = G == 32 ? wsel : ((wsel >> gbase) & ((1u << G) - 1u));
+            }
+            dfd.x = fmaf(dl * at.x, leaky_grad(q.x, a.slope), dfd.x);
+            dfd.y = fmaf(dl * at.y, leaky_grad(q.y, a.slope), dfd.y);
+            dfd.z = fmaf(dl * at.z, leaky_grad(q.z, a.slope), dfd.z);
+            dfd.w = fmaf(dl * at.w, leaky_grad(q.w, a.slope), dfd.w);
+            fma4(dat, dl, lr);
           }
         }
       }
     }
-    if (g.ok) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o2 + (size_t)v * HD) + g.col, dfd);
+    if (act) st4((frag ? a.p0 + (size_t)fi * HD : a.o2 + (size_t)v * HD) + col, dfd);
   }
-  st4(dat_all + (size_t)warp * 128 + lane * 4, dat);
+  // fold the lane groups of the warp (same columns), then the warps of the block that own the same slice
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) {
+    dat.x += __shfl_xor_sync(0xffffffffu, dat.x, o); dat.y += __shfl_xor_sync(0xffffffffu, dat.y, o);
+    dat.z += __shfl_xor_sync(0xffffffffu, dat.z, o); dat.w += __shfl_xor_sync(0xffffffffu, dat.w, o);
+  }
+  if (lane < G) st4(dat_all + (size_t)warp * 128 + lg * 4, dat);
   __syncthreads();
   double* outp = a.partials + (size_t)blockIdx.x * a.partial_stride;
   for (int i = threadIdx.x; i < RH; i += blockDim.x) {
     double sum = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w) sum += (double)smem[RHp + w * RHp + i];
+    for (int w = 0; w < kWarpsPerBlock; ++w)
+      for (int q = 0; q < GPW; ++q) sum += (double)smem[((RH + 3) & ~3) + (size_t)w * RHp + (size_t)i * GPW + q];
     outp[i] = sum;
   }
   for (int i = threadIdx.x; i < HD; i += blockDim.x) {
     double sum = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w)  // warps of this block that own head group i/128, in warp order
-      if (((int64_t)blockIdx.x * kWarpsPerBlock + w) % HG == i / 128) sum += (double)dat_all[w * 128 + (i & 127)];
+    for (int w = 0; w < kWarpsPerBlock; ++w)  // warps of this block that own slice i/128, in warp order
+      if (((int64_t)blockIdx.x * kWarpsPerBlock + w) % HG == i / 128 && (i & 127) < G * 4)
+        sum += (double)dat_all[w * 128 + (i & 127)];
     outp[RH + i] = sum;
   }
 }
 
-// =================================================================================================
-// REGATv2 backward, source-major: d_fs[u] = sum_j a_csr*G[dst] + dl_csr*attn*LeakyReLU'(fs[u]+fd[dst]).
-// Dynamic smem per warp: p_s[32][HP], q_s[32][HP]
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
-gatv2_bwd_src_kernel(AttnArgs a) {
-  constexpr int U = kUA / 2;  // two gathered rows per edge
-  extern __shared__ __align__(16) float smem[];
-  const int H = a.H, HD = H * a.D, HP = H | 1;
+// Source-major pass: d_fs[u,h,:] = sum_j ( a_csr[s,h]*G[v,h,:] + dl_csr[s,h]*attn[h,:]*(bit ? 1 : slope) ),
+// s = slot_t[j], v = indices_t[j], bit = the stored sign of fs[u]+fd[v] (qmask).  One row gather per edge.
+#ifndef REGNN_V2S_BLOCKS
+#define REGNN_V2S_BLOCKS 5
+#endif
+template <int G>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_V2S_BLOCKS)
+gatv2_bwd_src_rg_kernel(AttnArgs a, const uint32_t* __restrict__ qmask) {
+  constexpr int U = 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* p_s = smem + warp * (64 * HP);
-  float* q_s = p_s + 32 * HP;
-  const int HG = num_groups(a);
+  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
+  const int H = a.H, HD = H * a.D, HG = a.hg_count;
   const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  int64_t ri;
-  int hg;
-  split_item(wi, HG, &ri, &hg);
-  const WorkItem it = decode_item(a, ri, a.nfrag);
-  if (!it.ok) return;
-  const Group g = make_group(a, hg, lane);
-  const int64_t u_row = it.v;
-  const int t0 = it.s0, len = it.len;
-  const int tl = g.hl - g.h_lo;
-  float4 acc = zero4(), fsu = zero4(), at = zero4();
-  if (g.ok) {
-    fsu = ldg4(a.feat + (size_t)u_row * HD + g.col);
-    at = ldg4(a.el + g.col);
-  }
-  const float* gcol = a.G + g.col;
-  const float* dcol = a.fd + g.col;
-
-  for (int base = 0; base < len; base += 32) {
-    const int cnt = min(32, len - base);
-    const bool valid = lane < cnt;
-    int d = 0, slot = 0;
-    if (valid) {
-      d = a.indices[t0 + base + lane];
-      slot = a.eid[t0 + base + lane];
+  if (wi >= rg_num_work(a, G)) return;
+  const RowItem it = rg_item<G>(a, wi, grp);
+  const int col = it.hg * 128 + lg * 4;
+  const bool col_ok = col < HD;
+  const int h = col_ok ? (col >> a.d_shift) : 0;
+  const bool act = it.v >= 0 && col_ok;
+  const int len = it.v >= 0 ? it.len : 0;
+  const int maxlen = __reduce_max_sync(0xffffffffu, len);
+  const char* gbytes = reinterpret_cast<const char*>(a.G + (col_ok ? col : 0));
+  const uint32_t gpitch = (uint32_t)HD * 4u;
+  const float* ah = a.a_csr + h;
+  const float* dh = a.d_csr + h;
+  const uint4* mk = reinterpret_cast<const uint4*>(qmask) + it.hg;
+  const float4 at = col_ok ? ldg4(a.el + col) : zero4();
+  const float4 ats = make_float4(at.x * a.slope, at.y * a.slope, at.z * a.slope, at.w * a.slope);
+  const int32_t* ip = a.indices + it.begin;
+  const int32_t* sp = a.eid + it.begin;
+  float4 acc = zero4();
+  for (int t0 = 0; t0 < maxlen; t0 += G) {
+    int bi = -1, bs = 0;
+    {
+      const int t = t0 + lg;
+      if (t < len) {
+        bi = __ldg(ip + t);
+        bs = __ldg(sp + t);
+      }
     }
-    for (int t = 0; t < g.nh; ++t) {
-      const int h = g.h_lo + t;
-      p_s[lane * HP + t] = valid ? __ldg(a.a_csr + (size_t)slot * H + h) : 0.f;
-      q_s[lane * HP + t] = valid ? __ldg(a.d_csr + (size_t)slot * H + h) : 0.f;
-    }
-    __syncwarp();
+    const int cnt = min(G, maxlen - t0);
     for (int j = 0; j < cnt; j += U) {
-      float4 xg[U], xd[U];
-      float p[U], q[U];
+      float4 x[U];
+      float pa[U], pd[U];
+      uint4 mb[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const bool ok = j + u < cnt;
-        const int jj = ok ? j + u : j;
-        const int sd = __shfl_sync(0xffffffffu, d, jj);
-        const bool ld = ok && g.ok;
-        xg[u] = ld ? ldg4(gcol + (size_t)sd * HD) : zero4();
-        xd[u] = ld ? ldg4(dcol + (size_t)sd * HD) : zero4();
-        p[u] = ld ? p_s[jj * HP + tl] : 0.f;
-        q[u] = ld ? q_s[jj * HP + tl] : 0.f;
+        const int sd = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+        const int ss = __shfl_sync(0xffffffffu, bs, gbase + j + u);
+        const bool ok = sd >= 0 && col_ok;
+        x[u] = ok ? ldg4(reinterpret_cast<const float*>(gbytes + (uint64_t)(uint32_t)sd * gpitch)) : zero4();
+        pa[u] = ok ? __ldg(ah + (uint64_t)(uint32_t)ss * (uint32_t)H) : 0.f;
+        pd[u] = ok ? __ldg(dh + (uint64_t)(uint32_t)ss * (uint32_t)H) : 0.f;
+        mb[u] = ok ? __ldg(mk + (uint64_t)(uint32_t)ss * (uint32_t)HG) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        fma4(acc, p[u], xg[u]);
-        const float4 z = add4(fsu, xd[u]);
-        acc.x = fmaf(q[u] * at.x, leaky_grad(z.x, a.slope), acc.x);
-        acc.y = fmaf(q[u] * at.y, leaky_grad(z.y, a.slope), acc.y);
-        acc.z = fmaf(q[u] * at.z, leaky_grad(z.z, a.slope), acc.z);
-        acc.w = fmaf(q[u] * at.w, leaky_grad(z.w, a.slope), acc.w);
+        fma4(acc, pa[u], x[u]);
+        acc.x = fmaf(pd[u], ((mb[u].x >> lg) & 1u) ? at.x : ats.x, acc.x);
+        acc.y = fmaf(pd[u], ((mb[u].y >> lg) & 1u) ? at.y : ats.y, acc.y);
+        acc.z = fmaf(pd[u], ((mb[u].z >> lg) & 1u) ? at.z : ats.z, acc.z);
+        acc.w = fmaf(pd[u], ((mb[u].w >> lg) & 1u) ? at.w : ats.w, acc.w);
       }
     }
-    __syncwarp();
   }
-  if (g.ok) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)u_row * HD) + g.col, acc);
+  if (act) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)it.v * HD) + col, acc);
 }
 
 // =================================================================================================
@@ -1426,9 +1481,9 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
                                    const float* attn, float negative_slope, const float* keep,
                                    const float* out, const float* rowmax, const float* rowsum,
                                    const float* Gd, int num_heads, int head_dim, int64_t row_begin,
-                                   int64_t row_end, float* a_csr, float* dl_csr, float* d_fd,
-                                   float* d_attn, double* partials, float* d_theta, const regnn_rowsplit_t* split, float* split_workspace,
-    void* stream_) {
+                                   int64_t row_end, float* a_csr, float* dl_csr, uint32_t* qmask, float* d_fd,
+                                   float* d_attn, double* partials, float* d_theta, const regnn_rowsplit_t* split,
+                                   float* split_workspace, const int32_t* row_order, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && fs && fd && attn && out && rowmax && rowsum && Gd && d_fd && d_attn && partials,
                 REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: null pointer");
@@ -1436,7 +1491,8 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
   REGNN_REQUIRE(etype_csr == nullptr || (theta && d_theta), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: null relation buffers");
   int rc = check_shape("gatv2_bwd_dst", num_heads, head_dim, num_relations, etype_csr != nullptr, true);
   if (rc != REGNN_OK) return rc;
-  REGNN_REQUIRE(aligned16(fs) && aligned16(fd) && aligned16(attn) && aligned16(out) && aligned16(Gd) && aligned16(d_fd),
+  REGNN_REQUIRE(aligned16(fs) && aligned16(fd) && aligned16(attn) && aligned16(out) && aligned16(Gd) && aligned16(d_fd) &&
+                    aligned16(qmask),
                 REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: 16-byte alignment required");
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: negative row range");
@@ -1447,10 +1503,29 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
   a.row_begin = row_begin; a.row_end = row_end; a.o0 = a_csr; a.o1 = dl_csr; a.o2 = d_fd;
   const int RH = a.R * num_heads, HD = num_heads * head_dim;
   a.partials = partials; a.partial_stride = RH + HD;
-  const size_t smem = sizeof(float) * ((size_t)((RH + 3) & ~3) * (1 + kWarpsPerBlock) + (size_t)kWarpsPerBlock * 128) + 16;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: incomplete row split");
-  const int nb = partial_blocks((rows + a.nfrag) * head_groups(a.H, a.D));
-  REGNN_DISPATCH_LPH(gatv2_bwd_dst_kernel, nb, smem);
+  apply_order(a, row_order, split, rows);
+  const int G = rg_lanes(HD), gpw = 32 / G, lph = min(G, head_dim / 4);
+  const size_t smem = sizeof(float) * ((size_t)((RH + 3) & ~3) + (size_t)kWarpsPerBlock * ((RH * gpw + 3) & ~3) +
+                                       (size_t)kWarpsPerBlock * 128) + 16;
+  int nb = partial_blocks(rg_work(a, rows));
+  if (nb * kWarpsPerBlock < a.hg_count) nb = (a.hg_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  bool launched = false;
+#define REGNN_V2D_CASE(G_, L_)                                                                          \
+  if (G == G_ && lph == L_) {                                                                           \
+    rc = set_smem(gatv2_bwd_dst_rg_kernel<G_, L_>, smem);                                               \
+    if (rc != REGNN_OK) return rc;                                                                      \
+    nb = max(min(nb, resident_blocks(gatv2_bwd_dst_rg_kernel<G_, L_>, smem)), (a.hg_count + kWarpsPerBlock - 1) / kWarpsPerBlock); \
+    gatv2_bwd_dst_rg_kernel<G_, L_><<<nb, kWarpsPerBlock * 32, smem, stream>>>(a, qmask);              \
+    launched = true;                                                                                    \
+  }
+  REGNN_V2D_CASE(4, 1) REGNN_V2D_CASE(4, 2) REGNN_V2D_CASE(4, 4)
+  REGNN_V2D_CASE(8, 1) REGNN_V2D_CASE(8, 2) REGNN_V2D_CASE(8, 4) REGNN_V2D_CASE(8, 8)
+  REGNN_V2D_CASE(16, 1) REGNN_V2D_CASE(16, 2) REGNN_V2D_CASE(16, 4) REGNN_V2D_CASE(16, 8) REGNN_V2D_CASE(16, 16)
+  REGNN_V2D_CASE(32, 1) REGNN_V2D_CASE(32, 2) REGNN_V2D_CASE(32, 4) REGNN_V2D_CASE(32, 8) REGNN_V2D_CASE(32, 16)
+  REGNN_V2D_CASE(32, 32)
+#undef REGNN_V2D_CASE
+  REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "gatv2_bwd_dst: no kernel for H=%d D=%d", num_heads, head_dim);
   if (a.nfrag > 0) launch_rowsum(split, a.p0, HD, d_fd, row_begin, row_end, stream);
   if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH + HD, RH, theta, alpha, d_theta, stream);
   launch_colsum_finalize(partials, nb, RH + HD, RH, HD, d_attn, stream);
@@ -1459,30 +1534,33 @@ extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices
 
 extern "C" int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indices_t,
                                    const int32_t* slot_t, const float* a_csr, const float* dl_csr,
-                                   const float* fs, const float* fd, const float* attn,
-                                   float negative_slope, const float* Gd, int num_heads,
-                                   int head_dim, int64_t row_begin, int64_t row_end, float* d_fs,
-                                   const regnn_rowsplit_t* split, float* split_workspace,
-    void* stream_) {
+                                   const uint32_t* qmask, const float* attn, float negative_slope, const float* Gd,
+                                   int num_heads, int head_dim, int64_t row_begin, int64_t row_end, float* d_fs,
+                                   const regnn_rowsplit_t* split, float* split_workspace, const int32_t* row_order_t,
+                                   void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr_t && fs && fd && attn && Gd && d_fs,
+  REGNN_REQUIRE(indptr_t && attn && Gd && d_fs, /* per-edge arrays may be NULL when E == 0 */
                 REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: null pointer");
-  int rc = check_shape("gatv2_bwd_src", num_heads, head_dim, 0, false, false);
+  int rc = check_shape("gatv2_bwd_src", num_heads, head_dim, 0, false, true);
   if (rc != REGNN_OK) return rc;
-  REGNN_REQUIRE(aligned16(fs) && aligned16(fd) && aligned16(attn) && aligned16(Gd) && aligned16(d_fs),
+  REGNN_REQUIRE(aligned16(attn) && aligned16(Gd) && aligned16(d_fs) && aligned16(qmask),
                 REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: 16-byte alignment required");
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: negative row range");
   if (rows == 0) return REGNN_OK;
   AttnArgs a{};
   a.indptr = indptr_t; a.indices = indices_t; a.eid = slot_t; a.a_csr = a_csr; a.d_csr = dl_csr;
-  a.feat = fs; a.fd = fd; a.el = attn; a.slope = negative_slope; a.G = Gd;
+  a.el = attn; a.slope = negative_slope; a.G = Gd;
   a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end; a.o0 = d_fs;
-  const int HP = num_heads | 1;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: incomplete row split");
-  const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * 64 * HP;
-  const unsigned grid = (unsigned)(((rows + a.nfrag) * head_groups(a.H, a.D) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  REGNN_DISPATCH_C(gatv2_bwd_src_kernel, grid, smem);
+  apply_order(a, row_order_t, split, rows);
+  const unsigned grid = (unsigned)((rg_work(a, rows) + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  switch (rg_lanes(num_heads * head_dim)) {
+    case 4: gatv2_bwd_src_rg_kernel<4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
+    case 8: gatv2_bwd_src_rg_kernel<8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
+    case 16: gatv2_bwd_src_rg_kernel<16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
+    default: gatv2_bwd_src_rg_kernel<32><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
+  }
   if (a.nfrag > 0) launch_rowsum(split, a.p0, num_heads * head_dim, d_fs, row_begin, row_end, stream);
   return check_launch("regnn_gatv2_bwd_src");
 }

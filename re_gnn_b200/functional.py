@@ -209,9 +209,9 @@ class _GatV2Aggregate(torch.autograd.Function):
         fs, fd, attn, theta, keep, out, rowmax, rowsum = ctx.saved_tensors
         csr = ctx.graph.csr()
         g = g.contiguous()
-        a_csr, dl_csr, d_fd, d_attn, d_theta = ops.gatv2_bwd_dst(csr, ctx.et, theta, ctx.alpha, fs, fd, attn,
-                                                                 ctx.slope, keep, out, rowmax, rowsum, g)
-        d_fs = ops.gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, ctx.slope, g)
+        a_csr, dl_csr, qmask, d_fd, d_attn, d_theta = ops.gatv2_bwd_dst(csr, ctx.et, theta, ctx.alpha, fs, fd, attn,
+                                                                        ctx.slope, keep, out, rowmax, rowsum, g)
+        d_fs = ops.gatv2_bwd_src(csr, a_csr, dl_csr, qmask, attn, ctx.slope, g)
         return (None, None, d_fs, d_fd, d_attn.view_as(attn),
                 d_theta.view_as(theta) if d_theta is not None else None, None, None, None, None, None)
 

@@ -370,6 +370,7 @@ def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_at
 
 
 def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, rowmax, rowsum, g, rows=None):
+    """-> (a_csr, dl_csr, qmask, d_fd, d_attn, d_theta): see regnn_gatv2_bwd_dst."""
     fs, fd, keep, g = _f32(fs), _f32(fd), _f32(keep), _f32(g)
     attn = _f32(attn).view(-1)
     n, h, d = fd.shape
@@ -379,31 +380,34 @@ def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, row
     e = csr['indices'].numel()
     a_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
     dl_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
-    d_fd = torch.empty_like(fd) if (rb, re) == (0, n) else torch.zeros_like(fd)
+    qmask = torch.empty((max(e, 1), (h * d + 127) // 128, 4), dtype=torch.int32, device=dev)
+    d_fd = torch.empty_like(fd) if _full(rb, re, n) else torch.zeros_like(fd)
     d_attn = torch.empty(h * d, dtype=torch.float32, device=dev)
     partials = torch.empty(_lib.partial_blocks(re - rb) * (r * h + h * d), dtype=torch.float64, device=dev)
     d_theta = torch.zeros((r, h), dtype=torch.float32, device=dev) if r else None   # stays 0 when the graph has no edges
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
+    order = row_order(csr) if _full(rb, re, n) else None
     with torch.cuda.device(dev):
         _lib.call('regnn_gatv2_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep),
-                  _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dl_csr),
-                  _ptr(d_fd), _ptr(d_attn), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _stream())
+                  _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dl_csr), _ptr(qmask),
+                  _ptr(d_fd), _ptr(d_attn), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _ptr(order), _stream())
         _lib.count_launches((3 if r else 2) + (sp is not None))
-    return a_csr, dl_csr, d_fd, d_attn, d_theta
+    return a_csr, dl_csr, qmask, d_fd, d_attn, d_theta
 
 
-def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
-    fs, fd, g = _f32(fs), _f32(fd), _f32(g)
+def gatv2_bwd_src(csr, a_csr, dl_csr, qmask, attn, slope, g, rows=None):
+    g = _f32(g)
     attn = _f32(attn).view(-1)
-    n, h, d = fs.shape
+    n, h, d = g.shape
     rb, re = _rows(rows, n)
-    d_fs = torch.empty_like(fs) if (rb, re) == (0, n) else torch.zeros_like(fs)
-    sp, ws = _attn_split(csr.get('split_t'), h, d, fs.device)
-    with torch.cuda.device(fs.device):
+    d_fs = torch.empty_like(g) if _full(rb, re, n) else torch.zeros_like(g)
+    sp, ws = _attn_split(csr.get('split_t'), h, d, g.device)
+    order = row_order(csr, True) if _full(rb, re, n) else None
+    with torch.cuda.device(g.device):
         _lib.call('regnn_gatv2_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
-                  _ptr(a_csr), _ptr(dl_csr), _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(g), h, d,
-                  rb, re, _ptr(d_fs), sp, _ptr(ws), _stream())
+                  _ptr(a_csr), _ptr(dl_csr), _ptr(qmask), _ptr(attn), float(slope), _ptr(g), h, d,
+                  rb, re, _ptr(d_fs), sp, _ptr(ws), _ptr(order), _stream())
         _lib.count_launches(1 + (sp is not None))
     return d_fs
 

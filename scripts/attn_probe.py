@@ -78,8 +78,8 @@ if not once:
             ops.gat_bwd(csr, etv[0], etv[1], theta, 100.0, feat, el, er, 0.2, None, out, rowmax, rowsum, gout, attn_l=al, attn_r=ar)
     print('  per ABI call (ms):', {k: round(v, 3) for k, v in tr.summary(5).items()})
 o2, m2, s2, _ = ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2)
-a2, dl2, _, _, _ = ops.gatv2_bwd_dst(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, gout)
+a2, dl2, qm2, _, _, _ = ops.gatv2_bwd_dst(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, gout)
 t('gatv2_fwd', lambda: ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2), b_v2_fwd)
 t('gatv2_bwd_dst', lambda: ops.gatv2_bwd_dst(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, gout))
-t('gatv2_bwd_src', lambda: ops.gatv2_bwd_src(csr, a2, dl2, feat, fd, attn, 0.2, gout))
+t('gatv2_bwd_src', lambda: ops.gatv2_bwd_src(csr, a2, dl2, qm2, attn, 0.2, gout))
 t('el/er (eager torch, 2 x mul+sum)', lambda: ((feat * al).sum(-1), (feat * ar).sum(-1)))

@@ -278,16 +278,17 @@ def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, row
     if theta is not None and et_csr is not None:
         th = theta.detach()
         d_theta = torch.zeros_like(th).index_add(0, et_csr.long(), dl) * alpha * _lgrad(th * alpha, SLOPE)
-    return at, dl, d_fd, d_attn, d_theta
+    return at, dl, (q > 0), d_fd, d_attn, d_theta      # the sign mask as a bool [E,H,D] tensor in slot order
 
 
-def gatv2_bwd_src(csr, a_csr, dl_csr, fs, fd, attn, slope, g, rows=None):
-    fs, fd, g = fs.detach(), fd.detach(), g.detach()
+def gatv2_bwd_src(csr, a_csr, dl_csr, qmask, attn, slope, g, rows=None):
+    g = g.detach()
     src = _rows_of(csr['indptr_t'])
     dstn, slot = csr['indices_t'].long(), csr['slot_t'].long()
-    av = attn.detach().view(1, fs.shape[1], fs.shape[2])
-    msg = a_csr[slot][:, :, None] * g[dstn] + dl_csr[slot][:, :, None] * av * _lgrad(fs[src] + fd[dstn], slope)
-    return torch.zeros_like(fs).index_add(0, src, msg)
+    av = attn.detach().view(1, g.shape[1], g.shape[2])
+    deriv = torch.where(qmask[slot], torch.ones((), dtype=g.dtype), torch.full((), slope, dtype=g.dtype))
+    msg = a_csr[slot][:, :, None] * g[dstn] + dl_csr[slot][:, :, None] * av * deriv
+    return torch.zeros_like(g).index_add(0, src, msg)
 
 
 def _grouped_rows(tables, seg_ptr, perm, local_idx, num_rows):
