@@ -294,6 +294,11 @@ def attention_at_hbm_scale(dev, d, g, et, steps, warmup):
     csr = g.csr()
     etv = g.etype_views(et, r)
     res = {}
+    traffic = {}
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            traffic = json.load(fh)
     gen = torch.Generator(device=dev).manual_seed(99)
     for kind, heads, dim in (('regat', 8, 16), ('regat', 2, 64), ('regatv2', 8, 16), ('regatv2', 2, 64)):
         hd = heads * dim
@@ -327,7 +332,8 @@ def attention_at_hbm_scale(dev, d, g, et, steps, warmup):
             'gteps_fwd_bwd': e / t / 1e9, 'ms': t * 1e3, 'fwd_kernel_ms': tk * 1e3, 'gteps_fwd': e / tk / 1e9,
             'num_edges': int(e), 'l2': 'gathered matrix %.0f MB vs 126 MB L2; no flush needed' % (n * hd * 4 / 1e6),
             'roofline': {'bound': 'hbm', 'kernel': kname, 'achieved': alg / tk / 1e9, 'peak': hbm, 'peak_source': how,
-                         'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm, 'traffic': None,
+                         'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm,
+                         'traffic': traffic.get('gat_fwd_mag_h8d16_bytes') if (kind, heads, dim) == ('regat', 8, 16) else None,
                          'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3, 'l2_resident': False}}
         del mod, x, gout
         torch.cuda.empty_cache()

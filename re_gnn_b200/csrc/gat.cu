@@ -93,8 +93,6 @@ __device__ __forceinline__ WorkItem decode_item(const AttnArgs& a, int64_t wi, i
   return w;
 }
 
-constexpr int kUA = 4;  // source rows gathered per lane before any math; kept small so that 5 blocks (40 warps) fit
-                         // per SM: with short rows it is resident warps, not loads per warp, that hide the latency chain
 
 __device__ __forceinline__ void load_rel_table(float* w_s, const AttnArgs& a) {
   if (a.etype != nullptr) {
@@ -364,7 +362,9 @@ gat_bwd_stats_kernel(const float* __restrict__ out, const float* __restrict__ Gd
 // fd = stats as float4[N*H], G = dL/d out, a_csr = slot -> edge id when keep != null).
 // The gather pass is latency-bound at HBM scale (short rows, two gathers + two statistics loads per round): resident
 // warps win -- MAG graph, H8 D16: 4 blocks/SM 4.00 ms, 5: 3.66, 6 (40 registers, 24 bytes of spill): 3.49; L2-resident
-// ACM H8 D64: 0.226 / 0.244 / 0.250 ms.
+// ACM H8 D64: 0.226 / 0.244 / 0.250 ms.  Tried and dropped: staging the per-destination statistics of a whole slot batch in
+// shared memory (every lane fetches the nh heads of its slot, broadcast LDS.128 later) so that 4 rows of G fit in flight:
+// 5.5 ms instead of 3.5 -- the extra serial load / store / __syncwarp phase costs more than the halved round trips save.
 #ifndef REGNN_GATB_BLOCKS
 #define REGNN_GATB_BLOCKS 6
 #endif
@@ -889,6 +889,10 @@ gatv2_bwd_dst_rg_kernel(AttnArgs a, uint32_t* __restrict__ qmask) {
           // sign mask of q for the source-major pass: bit (lane) of word c = (q.c > 0)
           const uint32_t b0 = __ballot_sync(0xffffffffu, q.x > 0.f), b1 = __ballot_sync(0xffffffffu, q.y > 0.f);
           const uint32_t b2 = __ballot_sync(0xffffffffu, q.z > 0.f), b3 = __ballot_sync(0xffffffffu, q.w > 0.f);
+          if (si[u] >= 0 && v >= 0 && lg < 4) {   // all four words, also from lanes past the last column (H*D < 16)
+            const uint32_t wsel = lg == 0 ? b0 : (lg == 1 ? b1 : (lg == 2 ? b2 : b3));
+            qmask[((size_t)(begin + t0 + j + u) * HG + hg) * 4 + lg] = G == 32 ? wsel : ((wsel >> gbase) & ((1u << G) - 1u));
+          }
           if (si[u] >= 0 && act) {
             const int slot = begin + t0 + j + u;
             float lu = l;
@@ -901,10 +905,6 @@ gatv2_bwd_dst_rg_kernel(AttnArgs a, uint32_t* __restrict__ qmask) {
               a.o0[sh] = att;
               a.o1[sh] = dl;
               if (has_rel) bins[(se * H + h) * GPW + grp] += dl;
-            }
-            if (lg < 4) {
-              const uint32_t wsel = lg == 0 ? b0 : (lg == 1 ? b1 : (lg == 2 ? b2 : b3));
-              qmask[((size_t)slot * HG + hg) * 4 + lg] = G == 32 ? wsel : ((wsel >> gbase) & ((1u << G) - 1u));
             }
             dfd.x = fmaf(dl * at.x, leaky_grad(q.x, a.slope), dfd.x);
             dfd.y = fmaf(dl * at.y, leaky_grad(q.y, a.slope), dfd.y);
