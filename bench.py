@@ -324,9 +324,12 @@ def attention_at_hbm_scale(dev, d, g, et, steps, warmup):
                 kname = 'regnn::gat_fwd (fused logits + LeakyReLU + online edge-softmax + aggregation)'
             else:
                 at = mod.attn.detach().reshape(-1)
-                fwd = lambda: ops.gatv2_fwd(csr, etv[0], th, ALPHA, f3, f3, at, 0.01)
-                alg = e * (4 * hd + 4 + 1) + n * (2 * 4 * hd + 8 * heads + 4) + 4 * hd
-                kname = 'regnn::gatv2_fwd (fused logits + online edge-softmax + aggregation)'
+                # the training forward: also stores the logits and LeakyReLU' sign masks the backward reads
+                fwd = lambda: ops.gatv2_fwd(csr, etv[0], th, ALPHA, f3, f3, at, 0.01, save=True)
+                alg = (e * (4 * hd + 4 + 1 + 4 * heads + 16 * ((hd + 127) // 128)) + n * (2 * 4 * hd + 8 * heads + 4)
+                       + 4 * hd)
+                kname = ('regnn::gatv2_fwd (fused logits + online edge-softmax + aggregation; training variant that '
+                         'stores per-slot logits and sign masks)')
             tk = timed(fwd, steps, warmup, torch.cuda.synchronize) / steps
         res['mag_%s_h%dd%d' % (kind, heads, dim)] = {
             'gteps_fwd_bwd': e / t / 1e9, 'ms': t * 1e3, 'fwd_kernel_ms': tk * 1e3, 'gteps_fwd': e / tk / 1e9,

@@ -316,35 +316,43 @@ int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t
                     const float* fs, const float* fd, const float* attn, float negative_slope,
                     const float* keep, int num_heads, int head_dim, int64_t row_begin,
                     int64_t row_end, float* out, float* rowmax, float* rowsum, float* attn_out,
+                    float* logit_csr /* [E,H] CSR-slot order, or NULL (inference) */,
+                    uint32_t* qmask /* [E, ceil(H*D/128), 4], or NULL; see below */,
                     const regnn_rowsplit_t* split,
     float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */,
     const int32_t* row_order /* as regnn_gat_fwd */, void* stream);
 
-/* Backward, destination-major pass: a_csr = a*keep, dl_csr = dL/dl (both [E,H] slot order), d_fd [N,H,D], d_attn [H,D],
- * d_theta [R,H], and qmask: per (slot, 128-float slice of the H*D row) a 128-bit sign mask of q = fs[src]+fd[dst]
- * (uint32 [E, ceil(H*D/128), 4]; bit l of word c = component c of the l-th 128-bit chunk of the slice is > 0) -- the
- * derivative LeakyReLU'(q) is one bit per feature, so the source-major pass reads 16 bytes per edge instead of
- * gathering the 4HD-byte row fd[dst] again.
- * partials: double [regnn_max_partial_blocks() * (R*H + H*D)]. */
-int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
-                        const uint8_t* etype_csr, const float* theta, float alpha,
-                        int num_relations, const float* fs, const float* fd, const float* attn,
-                        float negative_slope, const float* keep, const float* out,
-                        const float* rowmax, const float* rowsum, const float* G, int num_heads,
-                        int head_dim, int64_t row_begin, int64_t row_end, float* a_csr,
-                        float* dl_csr, uint32_t* qmask, float* d_fd, float* d_attn, double* partials, float* d_theta,
-                        const regnn_rowsplit_t* split,
-    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, const int32_t* row_order, void* stream);
-
-/* Backward, source-major pass:
- *   d_fs[u,h,d] = sum_{j in Out(u)} ( a_csr[s,h]*G[v,h,d]
- *                                   + dl_csr[s,h]*attn[h,d]*LeakyReLU'(fs[u,h,d]+fd[v,h,d]) ),
- *   s = slot_t[j], v = indices_t[j]; the derivative comes from qmask (1 where the bit is set, else negative_slope). */
-int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
-                        const float* a_csr, const float* dl_csr, const uint32_t* qmask, const float* attn,
-                        float negative_slope, const float* G, int num_heads, int head_dim, int64_t row_begin,
-                        int64_t row_end, float* d_fs, const regnn_rowsplit_t* split_t /* of the transposed view */,
+/* Backward of regnn_gatv2_fwd: ONE gather pass (source-major) + one streaming pass (destination-major).  The forward
+ * saved, per CSR slot, the raw logit l[e,h] (logit_csr) and the sign of every component of q = fs[src]+fd[dst] as a
+ * 128-bit mask per 128-float slice of the H*D row (qmask: uint32 [E, ceil(H*D/128), 4]; bit l of word c = component c of
+ * the l-th 128-bit chunk of the slice is > 0) -- LeakyReLU'(q) is one bit per feature.  With the per-destination
+ * statistics stats[v,h] = (., rowmax, 1/rowsum, <out[v,h,:], G[v,h,:]>) of regnn_gat_bwd_stats every per-edge quantity
+ *   a = exp(l - rowmax)/rowsum,  dl = a*keep*<fs[u],G[v]> - a*<out[v],G[v]>
+ * is local to the pass that gathers G[v] for d_fs[u]:
+ *   regnn_gatv2_bwd_edges  d_fs[u,h,:] = sum_{Out(u)} ( a*keep*G[v,h,:] + dl*attn[h,:]*LeakyReLU'(q) ),  dl_csr[slot,h],
+ *                          d_attn_src[h,:] = sum_u fs[u,h,:] (.) sum_{Out(u)} dl*LeakyReLU'(q)
+ *   regnn_gatv2_bwd_dst    d_fd[v,h,:] = attn[h,:] (.) T[v],  T[v] = sum_{In(v)} dl*LeakyReLU'(q)   (no gather: dl_csr and
+ *                          qmask are read in slot order),  d_attn_dst = sum_v fd[v] (.) T[v],  d_theta [R,H]
+ * and d_attn = d_attn_src + d_attn_dst (the caller adds the two [H*D] vectors).
+ * Both calls must cover rows whose slots the forward call covered.  Deterministic: lane-local sums, per-block partials,
+ * fixed-order finalize.
+ * block_partials: float [regnn_gatv2_bwd_edges_blocks(...) * H*D];  partials (edges): double [592 * H*D];
+ * partials (dst): double [max(regnn_max_partial_blocks() * H*D, 592 * R*H)]. */
+int64_t regnn_gatv2_bwd_edges_blocks(int64_t num_rows, int num_frags /* of split_t */, int num_long /* of split_t */,
+                                     int num_heads, int head_dim, int ordered /* row_order_t given and row_begin == 0 */);
+int regnn_gatv2_bwd_edges(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
+                          const int32_t* eid /* CSR slot -> edge id; only read with keep */, const float* fs,
+                          const float* stats, const float* logit_csr, const uint32_t* qmask, const float* attn,
+                          float negative_slope, const float* keep, const float* G, int num_heads, int head_dim,
+                          int64_t row_begin, int64_t row_end, float* d_fs, float* dl_csr, float* d_attn_src,
+                          float* block_partials, double* partials, const regnn_rowsplit_t* split_t /* transposed view */,
     float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, const int32_t* row_order_t, void* stream);
+int regnn_gatv2_bwd_dst(const int32_t* indptr, const uint8_t* etype_csr, const float* theta, float alpha,
+                        int num_relations, const float* fd, const float* dl_csr, const uint32_t* qmask,
+                        const float* attn, float negative_slope, int num_heads, int head_dim, int64_t row_begin,
+                        int64_t row_end, float* d_fd, float* d_attn_dst, double* partials, float* d_theta,
+                        const regnn_rowsplit_t* split,
+    float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Neighbour sampling for the sampled-minibatch path (replaces torch_sparse's CPU `sample_adj` behind

@@ -52,10 +52,12 @@ SIGNATURES = {
     'regnn_grouped_linear_fwd': (_i32, [_i32, _p, _p, _p, _p, _p, _i32, _i64, _p, _p, _p, _p, _i64, _p]),
     'regnn_grouped_linear_bwd': (_i32, [_i32, _p, _p, _p, _i32, _i64, _p, _p, _p, _p, _i64, _i32, _p, _p, _p]),
     'regnn_gatv2_fwd': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64,
-                               _p, _p, _p, _p, _p, _p, _p, _p]),
-    'regnn_gatv2_bwd_dst': (_i32, [_p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p,
-                                   _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    'regnn_gatv2_bwd_src': (_i32, [_p, _p, _p, _p, _p, _p, _p, _f32, _p, _i32, _i32, _i64, _i64, _p, _p, _p, _p, _p]),
+                               _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'regnn_gatv2_bwd_edges_blocks': (_i64, [_i64, _i32, _i32, _i32, _i32, _i32]),
+    'regnn_gatv2_bwd_edges': (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _p, _i32, _i32, _i64, _i64,
+                                     _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'regnn_gatv2_bwd_dst': (_i32, [_p, _p, _p, _f32, _i32, _p, _p, _p, _p, _f32, _i32, _i32, _i64, _i64,
+                                   _p, _p, _p, _p, _p, _p, _p]),
 }
 
 

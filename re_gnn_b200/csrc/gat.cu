@@ -203,6 +203,12 @@ __device__ __forceinline__ int64_t rg_num_work(const AttnArgs& a, int G) {
   return ((a.nfrag + nrows) * a.hg_count + GPW - 1) / GPW;
 }
 
+#ifndef REGNN_FWD_PF
+#define REGNN_FWD_PF 0
+#endif
+#ifndef REGNN_PF_BYTES
+#define REGNN_PF_BYTES 128
+#endif
 constexpr int kUG = 4;  // edges per online-softmax batch (= gathers in flight per lane)
 
 template <int G, bool EXTRA>   // EXTRA: attention dropout mask and / or attention output (both need edge ids)
@@ -245,6 +251,14 @@ gat_fwd_rg_kernel(AttnArgs a) {
         bi = __ldg(ip + t);
         if (has_rel) be = __ldg(ep + t);
         if (need_eid) beid = __ldg(eidp + t);
+#if REGNN_FWD_PF
+        {
+          const char* fr = reinterpret_cast<const char*>(a.feat + it.hg * 128) + (uint64_t)(uint32_t)bi * ((uint32_t)HD * 4u);
+          const int nl = (min(128, HD - it.hg * 128) * 4 + REGNN_PF_BYTES - 1) / REGNN_PF_BYTES;
+          for (int k = 0; k < nl; ++k) prefetch_l2(fr + k * REGNN_PF_BYTES);
+          prefetch_l2(a.el + (uint64_t)(uint32_t)bi * (uint32_t)H);
+        }
+#endif
       }
     }
     const int cnt = min(G, maxlen - t0);
@@ -368,6 +382,12 @@ gat_bwd_stats_kernel(const float* __restrict__ out, const float* __restrict__ Gd
 #ifndef REGNN_GATB_BLOCKS
 #define REGNN_GATB_BLOCKS 6
 #endif
+#ifndef REGNN_GATB_PF
+#define REGNN_GATB_PF 0
+#endif
+#ifndef REGNN_PF_BYTES
+#define REGNN_PF_BYTES 128
+#endif
 #ifndef REGNN_GATB_U
 #define REGNN_GATB_U 2
 #endif
@@ -410,6 +430,12 @@ gat_bwd_edges_kernel(AttnArgs a) {
   const uint8_t* ep = a.etype + it.begin;
   float4 acc = zero4();
   float del = 0.f;
+#if REGNN_GATB_PF
+  // the G row slice and the statistics this lane's own slot will need, into L2 while the first rounds run
+  const char* pf_g = reinterpret_cast<const char*>(a.G + it.hg * 128);
+  const int pf_lines = (min(128, HD - it.hg * 128) * 4 + REGNN_PF_BYTES - 1) / REGNN_PF_BYTES;
+  const char* pf_s = reinterpret_cast<const char*>(a.fd) + (size_t)((it.hg * 128) >> a.d_shift) * 16;
+#endif
 
   for (int t0 = 0; t0 < maxlen; t0 += G) {
     int bi = -1, bs = 0, be = 0;
@@ -419,6 +445,11 @@ gat_bwd_edges_kernel(AttnArgs a) {
         bi = __ldg(ip + t);
         bs = __ldg(sp + t);
         if (has_rel) be = __ldg(ep + t);
+#if REGNN_GATB_PF
+        const char* gr = pf_g + (uint64_t)(uint32_t)bi * gpitch;
+        for (int k = 0; k < pf_lines; ++k) prefetch_l2(gr + k * REGNN_PF_BYTES);
+        prefetch_l2(pf_s + (uint64_t)(uint32_t)bi * spitch);
+#endif
       }
     }
     const int cnt = min(G, maxlen - t0);
@@ -515,12 +546,13 @@ gat_bwd_der_kernel(AttnArgs a, int HP) {
   *dst = acc;
 }
 
-// Relation bins of dpre: pure streaming over [E,H] (+ the uint8 edge types), lane-local bins, per-block double partials.
+// Relation bins of dpre (rows of `pitch` floats, the first H used): pure streaming over [E,H] (+ the uint8 edge types), lane-local bins, per-block double partials.
 // A warp reads 32/HP slots x HP heads per load; 8 loads are issued before the (loop-carried) shared-memory updates.
 // Dynamic smem: [warps][R][32] floats
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-gat_bwd_bins_kernel(const uint8_t* __restrict__ etype, const float* __restrict__ dpre, const int32_t* __restrict__ indptr,
-                    int64_t row_begin, int64_t row_end, int R, int H, int HP, double* __restrict__ partials) {
+gat_bwd_bins_kernel(const uint8_t* __restrict__ etype, const float* __restrict__ dpre, int pitch,
+                    const int32_t* __restrict__ indptr, int64_t row_begin, int64_t row_end, int R, int H, int HP,
+                    double* __restrict__ partials) {
   constexpr int UB = 8;
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -539,7 +571,7 @@ gat_bwd_bins_kernel(const uint8_t* __restrict__ etype, const float* __restrict__
         const int64_t s = s0 + (int64_t)u * per;
         const bool ok = s < s_end;
         t[u] = ok ? (int)__ldg(etype + s) : 0;
-        v[u] = ok ? __ldg(dpre + (size_t)s * H + hh) : 0.f;
+        v[u] = ok ? __ldg(dpre + (size_t)s * pitch + hh) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < UB; ++u) mybins[t[u] * 32] += v[u];
@@ -653,9 +685,13 @@ attn_scores_bwd_kernel(const float* __restrict__ feat, const float* __restrict__
 // (sum_d attn*LeakyReLU(fs+fd), reduced by a compile-time butterfly over the LPH = min(G, D/4) lanes of a head) and the
 // aggregation; online softmax per batch of U edges.  Nothing [E,H,D]-sized is ever written.
 // Dynamic smem: w_s[R*H]
+// Training (lcsr / qmask != null): the raw logit of every (CSR slot, head) and the sign of every component of
+// q = fs[u] + fd[v] (LeakyReLU' is ONE BIT per feature: four warp ballots -> a 128-bit mask per (slot, 128-float slice))
+// are stored for the backward, 4H + 16*ceil(HD/128) bytes per edge -- the only place where fs[u] and fd[v] meet without
+// an extra gather is this pass.
 template <int G, int LPH, bool EXTRA>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
-gatv2_fwd_rg_kernel(AttnArgs a) {
+gatv2_fwd_rg_kernel(AttnArgs a, float* __restrict__ lcsr, uint32_t* __restrict__ qmask) {
   constexpr int U = kUG;
   static_assert(G % U == 0, "a batch must not straddle a cooperative slot load");
   extern __shared__ __align__(16) float smem[];
@@ -684,6 +720,8 @@ gatv2_fwd_rg_kernel(AttnArgs a) {
   const int32_t* ip = a.indices + it.begin;
   const uint8_t* ep = a.etype + it.begin;
   const int32_t* eidp = a.eid + it.begin;
+  uint4* mrow = reinterpret_cast<uint4*>(qmask) + (size_t)it.begin * a.hg_count + it.hg;   // only used when saving
+  float* lrow = lcsr + (size_t)it.begin * H + h;
   float4 acc = zero4();
   float m = -INFINITY, s = 0.f;
 
@@ -695,6 +733,13 @@ gatv2_fwd_rg_kernel(AttnArgs a) {
         bi = __ldg(ip + t);
         if (has_rel) be = __ldg(ep + t);
         if (EXTRA) beid = __ldg(eidp + t);
+#if REGNN_FWD_PF
+        {
+          const char* fr = reinterpret_cast<const char*>(a.feat + it.hg * 128) + (uint64_t)(uint32_t)bi * fpitch;
+          const int nl = (min(128, HD - it.hg * 128) * 4 + REGNN_PF_BYTES - 1) / REGNN_PF_BYTES;
+          for (int k = 0; k < nl; ++k) prefetch_l2(fr + k * REGNN_PF_BYTES);
+        }
+#endif
       }
     }
     const int cnt = min(G, maxlen - t0);
@@ -711,11 +756,24 @@ gatv2_fwd_rg_kernel(AttnArgs a) {
       float bm = -INFINITY;
 #pragma unroll
       for (int u = 0; u < U; ++u) {   // U independent head reductions
-        float lu = group_sum<LPH>(dot4(at, leaky4(add4(x[u], fdv), a.slope)));
+        const float4 q = add4(x[u], fdv);
+        float lu = group_sum<LPH>(dot4(at, leaky4(q, a.slope)));
         if (has_rel) lu += w_h[__shfl_sync(0xffffffffu, be, gbase + j + u) * H];
         if (EXTRA) seid[u] = __shfl_sync(0xffffffffu, beid, gbase + j + u);
         l[u] = si[u] >= 0 ? lu : -INFINITY;
         bm = fmaxf(bm, l[u]);
+        if (qmask != nullptr) {   // warp-uniform
+          uint4 b;
+          b.x = __ballot_sync(0xffffffffu, q.x > 0.f); b.y = __ballot_sync(0xffffffffu, q.y > 0.f);
+          b.z = __ballot_sync(0xffffffffu, q.z > 0.f); b.w = __ballot_sync(0xffffffffu, q.w > 0.f);
+          if (G < 32) {
+            constexpr uint32_t gm = G < 32 ? (1u << G) - 1u : 0xffffffffu;
+            b.x = (b.x >> gbase) & gm; b.y = (b.y >> gbase) & gm; b.z = (b.z >> gbase) & gm; b.w = (b.w >> gbase) & gm;
+          }
+          const uint32_t t = (uint32_t)(t0 + j + u);
+          if (si[u] >= 0 && lg == 0) mrow[t * (uint32_t)a.hg_count] = b;   // one 16-byte store per (slot, slice)
+          if (si[u] >= 0 && leader) lrow[t * (uint32_t)H] = lu;
+        }
       }
       if (bm > -INFINITY) {  // uniform within a lane group
         const float m_new = fmaxf(m, bm);
@@ -769,52 +827,223 @@ gatv2_fwd_rg_kernel(AttnArgs a) {
 }
 
 // =================================================================================================
-// REGATv2 backward.  Two gather passes are inherent (d_fd is a destination-side, d_fs a source-side reduction of an
-// [E,H,D]-sized quantity), but the source-major pass no longer gathers fd[dst] to rebuild LeakyReLU'(fs[u]+fd[v]):
-// that derivative is one BIT per feature (q > 0 ? 1 : slope), so the destination-major pass, which has q in registers,
-// stores a 128-bit sign mask per (slot, 128-float slice) -- four warp ballots -- and the source-major pass reads 16
-// bytes instead of gathering a 4HD-byte row: 616 instead of 1100 bytes per edge at H*D = 128.
-//
-// Destination-major (row groups over the degree-sorted rows, persistent grid; a warp keeps ONE 128-float slice for all
-// its rows so that its d_attn share accumulates in registers): recomputes logits and a, dl = a*keep*da - a*S, writes
-// a*keep and dl per (slot, head) and the sign mask, accumulates d_fd rows, d_attn and lane-group-local relation bins.
-// Dynamic smem: w_s[R*H] | per warp: bins[R*H][GPW] | per warp: dat[128]
-#ifndef REGNN_V2D_BLOCKS
-#define REGNN_V2D_BLOCKS 4
+// REGATv2 backward as ONE gather pass + one streaming pass.  For an edge e = (u -> v), head h:
+//   a_e = exp(l_e - m_v) / s_v,  da_e = <fs[u], G[v]>,  dl_e = a_e keep_e da_e - a_e S_v,  S_v = <out[v], G[v]>
+//   d_fs[u] = sum_{Out(u)} a_e keep_e G[v] + attn (.) T_src[u],    T_src[u] = sum_{Out(u)} dl_e phi_e
+//   d_fd[v] = attn (.) T_dst[v],                                    T_dst[v] = sum_{In(v)}  dl_e phi_e
+//   d_attn  = sum_e dl_e LeakyReLU(fs[u]+fd[v]) = sum_u fs[u] (.) T_src[u] + sum_v fd[v] (.) T_dst[v]
+// with phi_e = LeakyReLU'(fs[u]+fd[v]) in {1, slope}^D, one bit per feature.  The forward stored l_e per (slot, head)
+// and the bits of phi_e per (slot, 128-float slice); with the per-destination statistics (m, 1/s, S) of
+// gat_bwd_stats_kernel every quantity of the source-major pass is local to the lane that owns fs[u] -- the
+// destination-major GATHER pass of round 1 / the first half of round 2 (one more 4HD-byte row per edge) is gone:
+//   gatv2_bwd_edges_kernel      source-major, gathers G[v]: d_fs rows, dl per slot, block partials of fs (.) T_src
+//   gatv2_bwd_dst_stream_kernel destination-major, NO gather: streams dl + sign masks in slot order -> d_fd, fd (.) T_dst
+//   gat_bwd_bins_kernel         relation bins of dl (streaming)
+// Measured on the MAG graph (H8 D16) and dropped: L2 prefetch of everything a slot will need (G row, statistics, logit,
+// mask) issued with the cooperative index load: no change; one record per slot (logits and masks adjacent, dl written in
+// place over the logit): 6.1 ms instead of 5.0 (the in-place store orders the loads of the next round behind it).
+#define REGNN_V2_STAGE_CHUNKS 592   // first-stage blocks of the d_attn column sum (4 per SM)
+#ifndef REGNN_V2D_UD
+#define REGNN_V2D_UD 4   // slots in flight per lane in the streaming pass
 #endif
-template <int G, int LPH>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_V2D_BLOCKS)
-gatv2_bwd_dst_rg_kernel(AttnArgs a, uint32_t* __restrict__ qmask) {
-  constexpr int GPW = 32 / G, U = 2;
-  extern __shared__ __align__(16) float smem[];
-  const int H = a.H, HD = H * a.D, RH = a.etype != nullptr ? a.R * H : 0;
-  const int RHp = (RH * GPW + 3) & ~3;  // keeps dat_all 16-byte aligned
-  float* w_s = smem;
+#ifndef REGNN_V2E_BLOCKS
+#define REGNN_V2E_BLOCKS 5
+#endif
+// sum_e dl_e * phi_e with phi in {1, slope}:  slope * sum_e dl_e + (1 - slope) * sum_{e: bit set} dl_e -- one predicated add
+// per component and edge (lanebit = 1 << lane-in-group).
+struct PhiAcc {
+  float4 p;   // sum over the edges whose bit is set
+  float d;    // sum over all edges
+};
+__device__ __forceinline__ void phi_add(PhiAcc& t, float dl, uint4 mb, uint32_t lanebit) {
+  t.d += dl;
+  if (mb.x & lanebit) t.p.x += dl;
+  if (mb.y & lanebit) t.p.y += dl;
+  if (mb.z & lanebit) t.p.z += dl;
+  if (mb.w & lanebit) t.p.w += dl;
+}
+__device__ __forceinline__ float4 phi_total(const PhiAcc& t, float slope) {
+  const float b = slope * t.d, k = 1.f - slope;
+  return make_float4(fmaf(k, t.p.x, b), fmaf(k, t.p.y, b), fmaf(k, t.p.z, b), fmaf(k, t.p.w, b));
+}
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+
+// AttnArgs: indptr/indices/eid = indptr_t/indices_t/slot_t, feat = fs, fd = stats (float4[N*H]), el = attn, a_csr = the
+// stored logits, a_csr_eid = slot -> edge id (keep only), o0 = d_fs, o2 = dl per slot.  dat_part: [gridDim.x][H*D].
+template <int G, int LPH, bool KEEP>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_V2E_BLOCKS)
+gatv2_bwd_edges_kernel(AttnArgs a, const uint32_t* __restrict__ qmask, float* __restrict__ dat_part) {
+  constexpr int U = 2;
+  static_assert(G % U == 0, "a round must not straddle a slot batch");
+  __shared__ __align__(16) float dat_s[kWarpsPerBlock * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
-  float* bins = smem + ((RH + 3) & ~3) + (size_t)warp * RHp;
-  float* dat_all = smem + ((RH + 3) & ~3) + (size_t)kWarpsPerBlock * RHp;
-  for (int i = lane; i < RH * GPW; i += 32) bins[i] = 0.f;
-  load_rel_table(w_s, a);
-  const int HG = a.hg_count;
-  const bool has_rel = a.etype != nullptr;
+  const int H = a.H, HD = H * a.D, HG = a.hg_count;
+  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  RowItem it{-1, 0, 0, 0, 0, false};
+  if (wi < rg_num_work(a, G)) it = rg_item<G>(a, wi, grp);
+  const int col = it.hg * 128 + lg * 4;
+  const bool col_ok = col < HD;
+  const int h = col_ok ? (col >> a.d_shift) : 0;
+  const bool act = it.v >= 0 && col_ok;
+  const bool leader = act && (col & (a.D - 1)) == 0;
+  const int len = it.v >= 0 ? it.len : 0;
+  const int maxlen = __reduce_max_sync(0xffffffffu, len);
+  const float4 fu = act ? ldg4(a.feat + (size_t)it.v * HD + col) : zero4();
+  const char* gbytes = reinterpret_cast<const char*>(a.G + (col_ok ? col : 0));
+  const char* sbytes = reinterpret_cast<const char*>(a.fd) + (size_t)h * 16;
+  const uint32_t gpitch = (uint32_t)HD * 4u, spitch = (uint32_t)H * 16u;
+  const float* lh = a.a_csr + h;
+  float* dlh = a.o2 + h;
+  const uint4* mk = reinterpret_cast<const uint4*>(qmask) + it.hg;
+  const int32_t* ip = a.indices + it.begin;
+  const int32_t* sp = a.eid + it.begin;
+  float4 acc = zero4();
+  PhiAcc ta{zero4(), 0.f};
+  const uint32_t lanebit = 1u << lg;
+
+  for (int t0 = 0; t0 < maxlen; t0 += G) {
+    int bi = -1, bs = 0;
+    {
+      const int t = t0 + lg;
+      if (t < len) {
+        bi = __ldg(ip + t);
+        bs = __ldg(sp + t);
+      }
+    }
+    const int cnt = min(G, maxlen - t0);
+    for (int j = 0; j < cnt; j += U) {
+      float4 x[U], st[U];
+      uint4 mb[U];
+      float lv[U];
+      int sd[U], ss[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        sd[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
+        ss[u] = __shfl_sync(0xffffffffu, bs, gbase + j + u);
+        const bool ok = sd[u] >= 0 && col_ok;
+        x[u] = ok ? ldg4(reinterpret_cast<const float*>(gbytes + (uint64_t)(uint32_t)sd[u] * gpitch)) : zero4();
+        // missing slot: rowmax = +inf makes exp(. - rowmax) = 0, so a = dl = 0 without per-edge masks
+        st[u] = ok ? __ldg(reinterpret_cast<const float4*>(sbytes + (uint64_t)(uint32_t)sd[u] * spitch))
+                   : make_float4(0.f, INFINITY, 0.f, 0.f);
+        lv[u] = ok ? __ldg(lh + (uint64_t)(uint32_t)ss[u] * (uint32_t)H) : 0.f;
+        mb[u] = ok ? __ldg(mk + (uint64_t)(uint32_t)ss[u] * (uint32_t)HG) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      float da[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) da[u] = group_sum<LPH>(dot4(fu, x[u]));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float aa = __expf(lv[u] - st[u].y) * st[u].z;
+        float at = aa;
+        if (KEEP) {
+          if (sd[u] >= 0 && act) at *= __ldg(a.keep + (size_t)__ldg(a.a_csr_eid + ss[u]) * H + h);
+        }
+        const float dl = at * da[u] - aa * st[u].w;
+        fma4(acc, at, x[u]);
+        phi_add(ta, dl, mb[u], lanebit);
+        if (leader && sd[u] >= 0) dlh[(uint64_t)(uint32_t)ss[u] * (uint32_t)H] = dl;
+      }
+    }
+  }
+  float4 c = zero4();
+  const float4 T = phi_total(ta, a.slope);
+  if (act) {
+    const float4 at4 = ldg4(a.el + col);
+    acc.x = fmaf(at4.x, T.x, acc.x); acc.y = fmaf(at4.y, T.y, acc.y);
+    acc.z = fmaf(at4.z, T.z, acc.z); acc.w = fmaf(at4.w, T.w, acc.w);
+    st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)it.v * HD) + col, acc);
+    c = mul4(fu, T);
+  }
+  // d_attn share of this block: fold the lane groups of the warp (same columns, different rows), then the warps that
+  // own the same 128-float slice, in warp order
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) {
+    c.x += __shfl_xor_sync(0xffffffffu, c.x, o); c.y += __shfl_xor_sync(0xffffffffu, c.y, o);
+    c.z += __shfl_xor_sync(0xffffffffu, c.z, o); c.w += __shfl_xor_sync(0xffffffffu, c.w, o);
+  }
+  if (lane < G) st4(dat_s + warp * 128 + lg * 4, c);
+  __syncthreads();
+  float* outp = dat_part + (size_t)blockIdx.x * HD;
+  for (int i = threadIdx.x; i < HD; i += blockDim.x) {
+    float sum = 0.f;
+    if ((i & 127) < G * 4)
+      for (int w = 0; w < kWarpsPerBlock; ++w)
+        if (HG == 1 || (int)(((int64_t)blockIdx.x * kWarpsPerBlock + w) % HG) == i / 128) sum += dat_s[w * 128 + (i & 127)];
+    outp[i] = sum;
+  }
+}
+
+// First stage of the column sum of the [nb][W] float block partials above: block c sums rows [c*per, (c+1)*per) in row
+// order into doubles (threads over columns; W < 256: 256/W row phases, folded in phase order).  out: [gridDim.x][W].
+__global__ void __launch_bounds__(256)
+colsum_stage_kernel(const float* __restrict__ part, int64_t nb, int W, int64_t per, double* __restrict__ out) {
+  __shared__ double fold[256];
+  const int nr = W < 256 ? 256 / W : 1;
+  const int64_t b0 = (int64_t)blockIdx.x * per, b1 = min(nb, b0 + per);
+  for (int c0 = 0; c0 < W; c0 += 256) {
+    const int t = threadIdx.x;
+    const int c = c0 + (nr > 1 ? t % W : t), r0 = nr > 1 ? t / W : 0;
+    const bool on = c < W && r0 < nr;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (on) {
+      int64_t b = b0 + r0;
+      const int64_t step = nr;
+      for (; b + 3 * step < b1; b += 4 * step) {
+        const float v0 = __ldg(part + (size_t)b * W + c), v1 = __ldg(part + (size_t)(b + step) * W + c);
+        const float v2 = __ldg(part + (size_t)(b + 2 * step) * W + c), v3 = __ldg(part + (size_t)(b + 3 * step) * W + c);
+        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+      }
+      for (; b < b1; b += step) s0 += __ldg(part + (size_t)b * W + c);
+    }
+    const double s = (s0 + s1) + (s2 + s3);
+    if (nr > 1) {
+      fold[t] = on ? s : 0.0;
+      __syncthreads();
+      if (t < W) {
+        double tot = 0.0;
+        for (int r = 0; r < nr; ++r) tot += fold[r * W + t];
+        out[(size_t)blockIdx.x * W + t] = tot;
+      }
+      __syncthreads();
+    } else if (on) {
+      out[(size_t)blockIdx.x * W + c] = s;
+    }
+  }
+}
+
+// Destination-major streaming pass (no gather): T_dst[v] = sum over the CSR slots of v of dl[slot,h] * phi[slot] from
+// the per-slot dl and sign masks (consecutive slots = consecutive addresses, every lane of a group reads the same 16-byte
+// mask and its head's dl), d_fd[v] = attn (.) T_dst[v], and the lane-local d_attn share fd[v] (.) T_dst[v] of a
+// persistent grid (a warp keeps ONE 128-float slice for all its rows).  Fragments of long rows first (partial rows to
+// p0; the d_attn share is linear in T, so fragments contribute directly).
+// AttnArgs: indptr (CSR), fd, el = attn, d_csr = dl, o2 = d_fd, partials [gridDim.x][H*D].
+#ifndef REGNN_V2DS_BLOCKS
+#define REGNN_V2DS_BLOCKS 5
+#endif
+template <int G>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_V2DS_BLOCKS)
+gatv2_bwd_dst_stream_kernel(AttnArgs a, const uint32_t* __restrict__ qmask) {
+  constexpr int GPW = 32 / G, UD = REGNN_V2D_UD;
+  __shared__ __align__(16) float dat_s[kWarpsPerBlock * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % G, grp = lane / G;
+  const int H = a.H, HD = H * a.D, HG = a.hg_count;
   const int64_t nW = (int64_t)gridDim.x * kWarpsPerBlock, usable = nW - nW % HG;
   const int64_t wg = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   const int hg = (int)(wg % HG);
   const int col = hg * 128 + lg * 4;
   const bool col_ok = col < HD;
   const int h = col_ok ? (col >> a.d_shift) : 0;
-  const bool head_leader = col_ok && (col & (a.D - 1)) == 0;
-  const int64_t nrows = a.order != nullptr ? a.n_order : (a.row_end - a.row_begin);
+  const int64_t nrows = a.row_end - a.row_begin;
   const int64_t nitems = a.nfrag + nrows;
   const float4 at = col_ok ? ldg4(a.el + col) : zero4();
-  const char* fbytes = reinterpret_cast<const char*>(a.feat + (col_ok ? col : 0));
-  const uint32_t fpitch = (uint32_t)HD * 4u;
-  const float* w_h = w_s + h;
+  const uint4* mk = reinterpret_cast<const uint4*>(qmask) + hg;
+  const float* dh = a.d_csr + h;
   float4 dat = zero4();
 
+  const uint32_t lanebit = 1u << lg;
   for (int64_t rgi = wg / HG; wg < usable && rgi * GPW < nitems; rgi += usable / HG) {
-    // ---- the item of this lane group: a fragment of a long row or a row of the work list
     const int64_t ri = rgi * GPW + grp;
     int64_t v = -1, fi = 0;
     int begin = 0, len = 0;
@@ -830,7 +1059,7 @@ gatv2_bwd_dst_rg_kernel(AttnArgs a, uint32_t* __restrict__ qmask) {
           len = min(a.threshold, a.indptr[r + 1] - begin);
         }
       } else {
-        const int64_t r = a.order != nullptr ? (int64_t)a.order[ri - a.nfrag] : a.row_begin + (ri - a.nfrag);
+        const int64_t r = a.row_begin + (ri - a.nfrag);
         const int b = a.indptr[r], l = a.indptr[r + 1] - b;
         if (l <= a.threshold) {
           v = r;
@@ -839,174 +1068,43 @@ gatv2_bwd_dst_rg_kernel(AttnArgs a, uint32_t* __restrict__ qmask) {
         }
       }
     }
-    const bool act = v >= 0 && col_ok;
-    const int maxlen = __reduce_max_sync(0xffffffffu, v >= 0 ? len : 0);
-    if (v < 0) len = 0;
-    float4 gv = zero4(), fdv = zero4(), dfd = zero4();
-    float part = 0.f, m = 0.f, inv = 0.f;
-    if (act) {
-      gv = ldg4(a.G + (size_t)v * HD + col);
-      fdv = ldg4(a.fd + (size_t)v * HD + col);
-      part = dot4(ldg4(a.out + (size_t)v * HD + col), gv);
-      const size_t vh = (size_t)v * H + h;
-      m = __ldg(a.rowmax + vh);
-      const float sm = __ldg(a.rowsum + vh);
-      inv = sm > 0.f ? 1.f / sm : 0.f;
-    }
-    const float S = group_sum<LPH>(part);
-    const int32_t* ip = a.indices + begin;
-    const uint8_t* ep = a.etype + begin;
-    const int32_t* eidp = a.eid + begin;
-
-    for (int t0 = 0; t0 < maxlen; t0 += G) {
-      int bi = -1, be = 0, beid = 0;
-      {
-        const int t = t0 + lg;
-        if (t < len) {
-          bi = __ldg(ip + t);
-          if (has_rel) be = __ldg(ep + t);
-          if (a.keep != nullptr) beid = __ldg(eidp + t);
-        }
-      }
-      const int cnt = min(G, maxlen - t0);
-      for (int j = 0; j < cnt; j += U) {
-        float4 x[U];
-        int si[U];
+    if (v < 0 || !col_ok) continue;   // no warp-level primitives below
+    const float4 fdv = ldg4(a.fd + (size_t)v * HD + col);
+    PhiAcc ta{zero4(), 0.f};
+    const float* dp = dh + (size_t)begin * H;
+    const uint4* mp = mk + (size_t)begin * HG;
+    for (int t = 0; t < len; t += UD) {
+      float dl[UD];
+      uint4 mb[UD];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          si[u] = __shfl_sync(0xffffffffu, bi, gbase + j + u);
-          x[u] = (si[u] >= 0 && col_ok) ? ldg4(reinterpret_cast<const float*>(fbytes + (uint64_t)(uint32_t)si[u] * fpitch))
-                                        : zero4();
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float4 q = add4(x[u], fdv);
-          const float4 lr = leaky4(q, a.slope);
-          const float l = group_sum<LPH>(dot4(at, lr));
-          const float da = group_sum<LPH>(dot4(x[u], gv));
-          const int se = has_rel ? __shfl_sync(0xffffffffu, be, gbase + j + u) : 0;
-          const int seid = a.keep != nullptr ? __shfl_sync(0xffffffffu, beid, gbase + j + u) : 0;
-          // sign mask of q for the source-major pass: bit (lane) of word c = (q.c > 0)
-          const uint32_t b0 = __ballot_sync(0xffffffffu, q.x > 0.f), b1 = __ballot_sync(0xffffffffu, q.y > 0.f);
-          const uint32_t b2 = __ballot_sync(0xffffffffu, q.z > 0.f), b3 = __ballot_sync(0xffffffffu, q.w > 0.f);
-          if (si[u] >= 0 && v >= 0 && lg < 4) {   // all four words, also from lanes past the last column (H*D < 16)
-            const uint32_t wsel = lg == 0 ? b0 : (lg == 1 ? b1 : (lg == 2 ? b2 : b3));
-            qmask[((size_t)(begin + t0 + j + u) * HG + hg) * 4 + lg] = G == 32 ? wsel : ((wsel >> gbase) & ((1u << G) - 1u));
-          }
-          if (si[u] >= 0 && act) {
-            const int slot = begin + t0 + j + u;
-            float lu = l;
-            if (has_rel) lu += w_h[se * H];
-            const float aa = __expf(lu - m) * inv;
-            const float att = a.keep != nullptr ? aa * __ldg(a.keep + (size_t)seid * H + h) : aa;
-            const float dl = att * da - aa * S;
-            if (head_leader) {
-              const size_t sh = (size_t)slot * H + h;
-              a.o0[sh] = att;
-              a.o1[sh] = dl;
-              if (has_rel) bins[(se * H + h) * GPW + grp] += dl;
-            }
-            dfd.x = fmaf(dl * at.x, leaky_grad(q.x, a.slope), dfd.x);
-            dfd.y = fmaf(dl * at.y, leaky_grad(q.y, a.slope), dfd.y);
-            dfd.z = fmaf(dl * at.z, leaky_grad(q.z, a.slope), dfd.z);
-            dfd.w = fmaf(dl * at.w, leaky_grad(q.w, a.slope), dfd.w);
-            fma4(dat, dl, lr);
-          }
-        }
+      for (int u = 0; u < UD; ++u) {
+        const bool ok = t + u < len;
+        dl[u] = ok ? __ldg(dp + (uint32_t)(t + u) * (uint32_t)H) : 0.f;
+        mb[u] = ok ? __ldg(mp + (uint32_t)(t + u) * (uint32_t)HG) : make_uint4(0u, 0u, 0u, 0u);
       }
+#pragma unroll
+      for (int u = 0; u < UD; ++u) phi_add(ta, dl[u], mb[u], lanebit);
     }
-    if (act) st4((frag ? a.p0 + (size_t)fi * HD : a.o2 + (size_t)v * HD) + col, dfd);
+    const float4 T = phi_total(ta, a.slope);
+    st4((frag ? a.p0 + (size_t)fi * HD : a.o2 + (size_t)v * HD) + col, mul4(at, T));
+    dat.x = fmaf(fdv.x, T.x, dat.x); dat.y = fmaf(fdv.y, T.y, dat.y);
+    dat.z = fmaf(fdv.z, T.z, dat.z); dat.w = fmaf(fdv.w, T.w, dat.w);
   }
-  // fold the lane groups of the warp (same columns), then the warps of the block that own the same slice
 #pragma unroll
   for (int o = G; o < 32; o <<= 1) {
     dat.x += __shfl_xor_sync(0xffffffffu, dat.x, o); dat.y += __shfl_xor_sync(0xffffffffu, dat.y, o);
     dat.z += __shfl_xor_sync(0xffffffffu, dat.z, o); dat.w += __shfl_xor_sync(0xffffffffu, dat.w, o);
   }
-  if (lane < G) st4(dat_all + (size_t)warp * 128 + lg * 4, dat);
+  if (lane < G) st4(dat_s + warp * 128 + lg * 4, dat);
   __syncthreads();
-  double* outp = a.partials + (size_t)blockIdx.x * a.partial_stride;
-  for (int i = threadIdx.x; i < RH; i += blockDim.x) {
-    double sum = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w)
-      for (int q = 0; q < GPW; ++q) sum += (double)smem[((RH + 3) & ~3) + (size_t)w * RHp + (size_t)i * GPW + q];
-    outp[i] = sum;
-  }
+  double* outp = a.partials + (size_t)blockIdx.x * HD;
   for (int i = threadIdx.x; i < HD; i += blockDim.x) {
     double sum = 0.0;
-    for (int w = 0; w < kWarpsPerBlock; ++w)  // warps of this block that own slice i/128, in warp order
-      if (((int64_t)blockIdx.x * kWarpsPerBlock + w) % HG == i / 128 && (i & 127) < G * 4)
-        sum += (double)dat_all[w * 128 + (i & 127)];
-    outp[RH + i] = sum;
+    if ((i & 127) < G * 4)
+      for (int w = 0; w < kWarpsPerBlock; ++w)  // warps of this block that own slice i/128, in warp order
+        if (((int64_t)blockIdx.x * kWarpsPerBlock + w) % HG == i / 128) sum += (double)dat_s[w * 128 + (i & 127)];
+    outp[i] = sum;
   }
-}
-
-// Source-major pass: d_fs[u,h,:] = sum_j ( a_csr[s,h]*G[v,h,:] + dl_csr[s,h]*attn[h,:]*(bit ? 1 : slope) ),
-// s = slot_t[j], v = indices_t[j], bit = the stored sign of fs[u]+fd[v] (qmask).  One row gather per edge.
-#ifndef REGNN_V2S_BLOCKS
-#define REGNN_V2S_BLOCKS 5
-#endif
-template <int G>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_V2S_BLOCKS)
-gatv2_bwd_src_rg_kernel(AttnArgs a, const uint32_t* __restrict__ qmask) {
-  constexpr int U = 2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lg = lane % G, grp = lane / G, gbase = lane & ~(G - 1);
-  const int H = a.H, HD = H * a.D, HG = a.hg_count;
-  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (wi >= rg_num_work(a, G)) return;
-  const RowItem it = rg_item<G>(a, wi, grp);
-  const int col = it.hg * 128 + lg * 4;
-  const bool col_ok = col < HD;
-  const int h = col_ok ? (col >> a.d_shift) : 0;
-  const bool act = it.v >= 0 && col_ok;
-  const int len = it.v >= 0 ? it.len : 0;
-  const int maxlen = __reduce_max_sync(0xffffffffu, len);
-  const char* gbytes = reinterpret_cast<const char*>(a.G + (col_ok ? col : 0));
-  const uint32_t gpitch = (uint32_t)HD * 4u;
-  const float* ah = a.a_csr + h;
-  const float* dh = a.d_csr + h;
-  const uint4* mk = reinterpret_cast<const uint4*>(qmask) + it.hg;
-  const float4 at = col_ok ? ldg4(a.el + col) : zero4();
-  const float4 ats = make_float4(at.x * a.slope, at.y * a.slope, at.z * a.slope, at.w * a.slope);
-  const int32_t* ip = a.indices + it.begin;
-  const int32_t* sp = a.eid + it.begin;
-  float4 acc = zero4();
-  for (int t0 = 0; t0 < maxlen; t0 += G) {
-    int bi = -1, bs = 0;
-    {
-      const int t = t0 + lg;
-      if (t < len) {
-        bi = __ldg(ip + t);
-        bs = __ldg(sp + t);
-      }
-    }
-    const int cnt = min(G, maxlen - t0);
-    for (int j = 0; j < cnt; j += U) {
-      float4 x[U];
-      float pa[U], pd[U];
-      uint4 mb[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int sd = __shfl_sync(0xffffffffu, bi, gbase + j + u);
-        const int ss = __shfl_sync(0xffffffffu, bs, gbase + j + u);
-        const bool ok = sd >= 0 && col_ok;
-        x[u] = ok ? ldg4(reinterpret_cast<const float*>(gbytes + (uint64_t)(uint32_t)sd * gpitch)) : zero4();
-        pa[u] = ok ? __ldg(ah + (uint64_t)(uint32_t)ss * (uint32_t)H) : 0.f;
-        pd[u] = ok ? __ldg(dh + (uint64_t)(uint32_t)ss * (uint32_t)H) : 0.f;
-        mb[u] = ok ? __ldg(mk + (uint64_t)(uint32_t)ss * (uint32_t)HG) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        fma4(acc, pa[u], x[u]);
-        acc.x = fmaf(pd[u], ((mb[u].x >> lg) & 1u) ? at.x : ats.x, acc.x);
-        acc.y = fmaf(pd[u], ((mb[u].y >> lg) & 1u) ? at.y : ats.y, acc.y);
-        acc.z = fmaf(pd[u], ((mb[u].z >> lg) & 1u) ? at.z : ats.z, acc.z);
-        acc.w = fmaf(pd[u], ((mb[u].w >> lg) & 1u) ? at.w : ats.w, acc.w);
-      }
-    }
-  }
-  if (act) st4((it.frag ? a.p0 + (size_t)it.fi * HD : a.o0 + (size_t)it.v * HD) + col, acc);
 }
 
 // =================================================================================================
@@ -1353,8 +1451,8 @@ extern "C" int regnn_gat_bwd_reduce(const int32_t* indptr, const uint8_t* etype_
     int rc = set_smem(gat_bwd_bins_kernel, smem);
     if (rc != REGNN_OK) return rc;
     const int nb = min(partial_blocks(rows), 148 * 4);
-    gat_bwd_bins_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(etype_csr, dpre_csr, indptr, row_begin, row_end, R,
-                                                                  num_heads, HP, partials);
+    gat_bwd_bins_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(etype_csr, dpre_csr, num_heads, indptr, row_begin, row_end,
+                                                                  R, num_heads, HP, partials);
     launch_relation_grad_finalize(partials, nb, R * num_heads, R * num_heads, theta, alpha, d_theta, stream);
   }
   return check_launch("regnn_gat_bwd_reduce");
@@ -1428,16 +1526,18 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
                                int num_relations, const float* fs, const float* fd,
                                const float* attn, float negative_slope, const float* keep,
                                int num_heads, int head_dim, int64_t row_begin, int64_t row_end,
-                               float* out, float* rowmax, float* rowsum, float* attn_out,
-                               const regnn_rowsplit_t* split, float* split_workspace, const int32_t* row_order,
-    void* stream_) {
+                               float* out, float* rowmax, float* rowsum, float* attn_out, float* logit_csr,
+                               uint32_t* qmask, const regnn_rowsplit_t* split, float* split_workspace,
+                               const int32_t* row_order, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   REGNN_REQUIRE(indptr && fs && fd && attn && out && rowmax && rowsum, REGNN_ERR_INVALID_ARG, "gatv2_fwd: null pointer");
   REGNN_REQUIRE((keep == nullptr && attn_out == nullptr) || eid != nullptr, REGNN_ERR_INVALID_ARG, "gatv2_fwd: keep/attn_out need eid");
   REGNN_REQUIRE(etype_csr == nullptr || theta != nullptr, REGNN_ERR_INVALID_ARG, "gatv2_fwd: etype without theta");
   int rc = check_shape("gatv2_fwd", num_heads, head_dim, num_relations, etype_csr != nullptr, true);
   if (rc != REGNN_OK) return rc;
-  REGNN_REQUIRE(aligned16(fs) && aligned16(fd) && aligned16(attn) && aligned16(out), REGNN_ERR_INVALID_ARG, "gatv2_fwd: 16-byte alignment required");
+  REGNN_REQUIRE((logit_csr == nullptr) == (qmask == nullptr), REGNN_ERR_INVALID_ARG, "gatv2_fwd: logit_csr and qmask go together");
+  REGNN_REQUIRE(aligned16(fs) && aligned16(fd) && aligned16(attn) && aligned16(out) && aligned16(qmask), REGNN_ERR_INVALID_ARG,
+                "gatv2_fwd: 16-byte alignment required");
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gatv2_fwd: negative row range");
   if (rows == 0) return REGNN_OK;
@@ -1456,9 +1556,11 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
     bool launched = false;
 #define REGNN_V2F_CASE(G_, L_)                                                                   \
   if (G == G_ && lph == L_) {                                                                    \
-    if (extra) REGNN_DISPATCH_C((gatv2_fwd_rg_kernel<G_, L_, true>), grid, smem);                \
-    else REGNN_DISPATCH_C((gatv2_fwd_rg_kernel<G_, L_, false>), grid, smem);                     \
-    launched = true;                                                                             \
+    rc = set_smem(extra ? gatv2_fwd_rg_kernel<G_, L_, true> : gatv2_fwd_rg_kernel<G_, L_, false>, smem);             \
+    if (rc != REGNN_OK) return rc;                                                                                   \
+    if (extra) gatv2_fwd_rg_kernel<G_, L_, true><<<grid, kWarpsPerBlock * 32, smem, stream>>>(a, logit_csr, qmask);  \
+    else gatv2_fwd_rg_kernel<G_, L_, false><<<grid, kWarpsPerBlock * 32, smem, stream>>>(a, logit_csr, qmask);       \
+    launched = true;                                                                                                 \
   }
     REGNN_V2F_CASE(4, 1) REGNN_V2F_CASE(4, 2) REGNN_V2F_CASE(4, 4)
     REGNN_V2F_CASE(8, 1) REGNN_V2F_CASE(8, 2) REGNN_V2F_CASE(8, 4) REGNN_V2F_CASE(8, 8)
@@ -1475,92 +1577,113 @@ extern "C" int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, co
   return check_launch("regnn_gatv2_fwd");
 }
 
-extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
-                                   const uint8_t* etype_csr, const float* theta, float alpha,
-                                   int num_relations, const float* fs, const float* fd,
-                                   const float* attn, float negative_slope, const float* keep,
-                                   const float* out, const float* rowmax, const float* rowsum,
-                                   const float* Gd, int num_heads, int head_dim, int64_t row_begin,
-                                   int64_t row_end, float* a_csr, float* dl_csr, uint32_t* qmask, float* d_fd,
-                                   float* d_attn, double* partials, float* d_theta, const regnn_rowsplit_t* split,
-                                   float* split_workspace, const int32_t* row_order, void* stream_) {
+extern "C" int64_t regnn_gatv2_bwd_edges_blocks(int64_t num_rows, int num_frags, int num_long, int num_heads,
+                                                int head_dim, int ordered) {
+  if (num_rows < 0 || num_heads < 1 || head_dim < 4) return 0;
+  const int HD = num_heads * head_dim, gpw = 32 / rg_lanes(HD);
+  const int64_t nrows = ordered ? num_rows - num_long : num_rows;
+  const int64_t work = ((num_frags + nrows) * head_groups(num_heads, head_dim) + gpw - 1) / gpw;
+  return (work + kWarpsPerBlock - 1) / kWarpsPerBlock;
+}
+
+extern "C" int regnn_gatv2_bwd_edges(const int32_t* indptr_t, const int32_t* indices_t, const int32_t* slot_t,
+                                     const int32_t* eid, const float* fs, const float* stats, const float* logit_csr,
+                                     const uint32_t* qmask, const float* attn, float negative_slope, const float* keep,
+                                     const float* Gd, int num_heads, int head_dim, int64_t row_begin, int64_t row_end,
+                                     float* d_fs, float* dl_csr, float* d_attn_src, float* block_partials,
+                                     double* partials, const regnn_rowsplit_t* split_t, float* split_workspace,
+                                     const int32_t* row_order_t, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr && fs && fd && attn && out && rowmax && rowsum && Gd && d_fd && d_attn && partials,
-                REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: null pointer");
-  REGNN_REQUIRE(keep == nullptr || eid != nullptr, REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: keep needs eid");
+  REGNN_REQUIRE(indptr_t && fs && stats && attn && Gd && d_fs && d_attn_src && block_partials && partials,
+                REGNN_ERR_INVALID_ARG, "gatv2_bwd_edges: null pointer");  /* per-edge arrays may be NULL when E == 0 */
+  REGNN_REQUIRE(keep == nullptr || eid != nullptr, REGNN_ERR_INVALID_ARG, "gatv2_bwd_edges: keep needs eid");
+  int rc = check_shape("gatv2_bwd_edges", num_heads, head_dim, 0, false, true);
+  if (rc != REGNN_OK) return rc;
+  REGNN_REQUIRE(aligned16(fs) && aligned16(stats) && aligned16(attn) && aligned16(Gd) && aligned16(d_fs) && aligned16(qmask),
+                REGNN_ERR_INVALID_ARG, "gatv2_bwd_edges: 16-byte alignment required");
+  const int64_t rows = row_end - row_begin;
+  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gatv2_bwd_edges: negative row range");
+  const int HD = num_heads * head_dim;
+  if (rows == 0) {
+    cudaMemsetAsync(d_attn_src, 0, sizeof(float) * HD, stream);
+    return check_launch("regnn_gatv2_bwd_edges");
+  }
+  AttnArgs a{};
+  a.indptr = indptr_t; a.indices = indices_t; a.eid = slot_t; a.a_csr_eid = eid; a.feat = fs; a.fd = stats;
+  a.a_csr = logit_csr; a.el = attn; a.slope = negative_slope; a.keep = keep; a.G = Gd; a.H = num_heads; a.D = head_dim;
+  a.row_begin = row_begin; a.row_end = row_end; a.o0 = d_fs; a.o2 = dl_csr;
+  REGNN_REQUIRE(apply_split(a, split_t, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_edges: incomplete row split");
+  apply_order(a, row_order_t, split_t, rows);
+  const int64_t nb = (rg_work(a, rows) + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  {
+    const int G = rg_lanes(HD), lph = min(G, head_dim / 4);
+    bool launched = false;
+#define REGNN_V2E_CASE(G_, L_)                                                                                          \
+  if (G == G_ && lph == L_) {                                                                                           \
+    if (keep != nullptr)                                                                                                \
+      gatv2_bwd_edges_kernel<G_, L_, true><<<(unsigned)nb, kWarpsPerBlock * 32, 0, stream>>>(a, qmask, block_partials); \
+    else                                                                                                                \
+      gatv2_bwd_edges_kernel<G_, L_, false><<<(unsigned)nb, kWarpsPerBlock * 32, 0, stream>>>(a, qmask, block_partials);\
+    launched = true;                                                                                                    \
+  }
+    REGNN_V2E_CASE(4, 1) REGNN_V2E_CASE(4, 2) REGNN_V2E_CASE(4, 4)
+    REGNN_V2E_CASE(8, 1) REGNN_V2E_CASE(8, 2) REGNN_V2E_CASE(8, 4) REGNN_V2E_CASE(8, 8)
+    REGNN_V2E_CASE(16, 1) REGNN_V2E_CASE(16, 2) REGNN_V2E_CASE(16, 4) REGNN_V2E_CASE(16, 8) REGNN_V2E_CASE(16, 16)
+    REGNN_V2E_CASE(32, 1) REGNN_V2E_CASE(32, 2) REGNN_V2E_CASE(32, 4) REGNN_V2E_CASE(32, 8) REGNN_V2E_CASE(32, 16)
+    REGNN_V2E_CASE(32, 32)
+#undef REGNN_V2E_CASE
+    REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "gatv2_bwd_edges: no kernel for H=%d D=%d", num_heads, head_dim);
+  }
+  if (a.nfrag > 0) launch_rowsum(split_t, a.p0, HD, d_fs, row_begin, row_end, stream);
+  // d_attn share of the source side: [nb][HD] float block partials -> [chunks][HD] doubles -> [HD]
+  const int chunks = (int)(nb < REGNN_V2_STAGE_CHUNKS ? nb : REGNN_V2_STAGE_CHUNKS);
+  const int64_t per = (nb + chunks - 1) / chunks;
+  colsum_stage_kernel<<<chunks, 256, 0, stream>>>(block_partials, nb, HD, per, partials);
+  launch_colsum_finalize(partials, chunks, HD, 0, HD, d_attn_src, stream);
+  return check_launch("regnn_gatv2_bwd_edges");
+}
+
+extern "C" int regnn_gatv2_bwd_dst(const int32_t* indptr, const uint8_t* etype_csr, const float* theta, float alpha,
+                                   int num_relations, const float* fd, const float* dl_csr, const uint32_t* qmask,
+                                   const float* attn, float negative_slope, int num_heads, int head_dim,
+                                   int64_t row_begin, int64_t row_end, float* d_fd, float* d_attn_dst, double* partials,
+                                   float* d_theta, const regnn_rowsplit_t* split, float* split_workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  REGNN_REQUIRE(indptr && fd && attn && d_fd && d_attn_dst && partials, REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: null pointer");
   REGNN_REQUIRE(etype_csr == nullptr || (theta && d_theta), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: null relation buffers");
   int rc = check_shape("gatv2_bwd_dst", num_heads, head_dim, num_relations, etype_csr != nullptr, true);
   if (rc != REGNN_OK) return rc;
-  REGNN_REQUIRE(aligned16(fs) && aligned16(fd) && aligned16(attn) && aligned16(out) && aligned16(Gd) && aligned16(d_fd) &&
-                    aligned16(qmask),
-                REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: 16-byte alignment required");
+  REGNN_REQUIRE(aligned16(fd) && aligned16(attn) && aligned16(d_fd) && aligned16(qmask), REGNN_ERR_INVALID_ARG,
+                "gatv2_bwd_dst: 16-byte alignment required");
   const int64_t rows = row_end - row_begin;
   REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: negative row range");
   AttnArgs a{};
-  a.indptr = indptr; a.indices = indices; a.eid = eid; a.etype = etype_csr; a.theta = theta; a.alpha = alpha;
-  a.R = etype_csr ? num_relations : 0; a.feat = fs; a.fd = fd; a.el = attn; a.slope = negative_slope; a.keep = keep;
-  a.out = out; a.rowmax = rowmax; a.rowsum = rowsum; a.G = Gd; a.H = num_heads; a.D = head_dim;
-  a.row_begin = row_begin; a.row_end = row_end; a.o0 = a_csr; a.o1 = dl_csr; a.o2 = d_fd;
-  const int RH = a.R * num_heads, HD = num_heads * head_dim;
-  a.partials = partials; a.partial_stride = RH + HD;
+  a.indptr = indptr; a.fd = fd; a.el = attn; a.d_csr = dl_csr; a.slope = negative_slope; a.H = num_heads; a.D = head_dim;
+  a.row_begin = row_begin; a.row_end = row_end; a.o2 = d_fd; a.partials = partials;
+  const int R = etype_csr ? num_relations : 0, HD = num_heads * head_dim;
   REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_dst: incomplete row split");
-  apply_order(a, row_order, split, rows);
-  const int G = rg_lanes(HD), gpw = 32 / G, lph = min(G, head_dim / 4);
-  const size_t smem = sizeof(float) * ((size_t)((RH + 3) & ~3) + (size_t)kWarpsPerBlock * ((RH * gpw + 3) & ~3) +
-                                       (size_t)kWarpsPerBlock * 128) + 16;
-  int nb = partial_blocks(rg_work(a, rows));
+  const int G = rg_lanes(HD), gpw = 32 / G;
+  const int64_t work = ((a.nfrag + rows) * a.hg_count + gpw - 1) / gpw;
+  int nb = partial_blocks(work);
   if (nb * kWarpsPerBlock < a.hg_count) nb = (a.hg_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  bool launched = false;
-#define REGNN_V2D_CASE(G_, L_)                                                                          \
-  if (G == G_ && lph == L_) {                                                                           \
-    rc = set_smem(gatv2_bwd_dst_rg_kernel<G_, L_>, smem);                                               \
-    if (rc != REGNN_OK) return rc;                                                                      \
-    nb = max(min(nb, resident_blocks(gatv2_bwd_dst_rg_kernel<G_, L_>, smem)), (a.hg_count + kWarpsPerBlock - 1) / kWarpsPerBlock); \
-    gatv2_bwd_dst_rg_kernel<G_, L_><<<nb, kWarpsPerBlock * 32, smem, stream>>>(a, qmask);              \
-    launched = true;                                                                                    \
+  switch (G) {
+    case 4: gatv2_bwd_dst_stream_kernel<4><<<nb, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
+    case 8: gatv2_bwd_dst_stream_kernel<8><<<nb, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
+    case 16: gatv2_bwd_dst_stream_kernel<16><<<nb, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
+    default: gatv2_bwd_dst_stream_kernel<32><<<nb, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
   }
-  REGNN_V2D_CASE(4, 1) REGNN_V2D_CASE(4, 2) REGNN_V2D_CASE(4, 4)
-  REGNN_V2D_CASE(8, 1) REGNN_V2D_CASE(8, 2) REGNN_V2D_CASE(8, 4) REGNN_V2D_CASE(8, 8)
-  REGNN_V2D_CASE(16, 1) REGNN_V2D_CASE(16, 2) REGNN_V2D_CASE(16, 4) REGNN_V2D_CASE(16, 8) REGNN_V2D_CASE(16, 16)
-  REGNN_V2D_CASE(32, 1) REGNN_V2D_CASE(32, 2) REGNN_V2D_CASE(32, 4) REGNN_V2D_CASE(32, 8) REGNN_V2D_CASE(32, 16)
-  REGNN_V2D_CASE(32, 32)
-#undef REGNN_V2D_CASE
-  REGNN_REQUIRE(launched, REGNN_ERR_UNSUPPORTED_SHAPE, "gatv2_bwd_dst: no kernel for H=%d D=%d", num_heads, head_dim);
   if (a.nfrag > 0) launch_rowsum(split, a.p0, HD, d_fd, row_begin, row_end, stream);
-  if (etype_csr != nullptr) launch_relation_grad_finalize(partials, nb, RH + HD, RH, theta, alpha, d_theta, stream);
-  launch_colsum_finalize(partials, nb, RH + HD, RH, HD, d_attn, stream);
-  return check_launch("regnn_gatv2_bwd_dst");
-}
-
-extern "C" int regnn_gatv2_bwd_src(const int32_t* indptr_t, const int32_t* indices_t,
-                                   const int32_t* slot_t, const float* a_csr, const float* dl_csr,
-                                   const uint32_t* qmask, const float* attn, float negative_slope, const float* Gd,
-                                   int num_heads, int head_dim, int64_t row_begin, int64_t row_end, float* d_fs,
-                                   const regnn_rowsplit_t* split, float* split_workspace, const int32_t* row_order_t,
-                                   void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(indptr_t && attn && Gd && d_fs, /* per-edge arrays may be NULL when E == 0 */
-                REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: null pointer");
-  int rc = check_shape("gatv2_bwd_src", num_heads, head_dim, 0, false, true);
-  if (rc != REGNN_OK) return rc;
-  REGNN_REQUIRE(aligned16(attn) && aligned16(Gd) && aligned16(d_fs) && aligned16(qmask),
-                REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: 16-byte alignment required");
-  const int64_t rows = row_end - row_begin;
-  REGNN_REQUIRE(rows >= 0, REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: negative row range");
-  if (rows == 0) return REGNN_OK;
-  AttnArgs a{};
-  a.indptr = indptr_t; a.indices = indices_t; a.eid = slot_t; a.a_csr = a_csr; a.d_csr = dl_csr;
-  a.el = attn; a.slope = negative_slope; a.G = Gd;
-  a.H = num_heads; a.D = head_dim; a.row_begin = row_begin; a.row_end = row_end; a.o0 = d_fs;
-  REGNN_REQUIRE(apply_split(a, split, split_workspace), REGNN_ERR_INVALID_ARG, "gatv2_bwd_src: incomplete row split");
-  apply_order(a, row_order_t, split, rows);
-  const unsigned grid = (unsigned)((rg_work(a, rows) + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  switch (rg_lanes(num_heads * head_dim)) {
-    case 4: gatv2_bwd_src_rg_kernel<4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
-    case 8: gatv2_bwd_src_rg_kernel<8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
-    case 16: gatv2_bwd_src_rg_kernel<16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
-    default: gatv2_bwd_src_rg_kernel<32><<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, qmask); break;
+  launch_colsum_finalize(partials, nb, HD, 0, HD, d_attn_dst, stream);
+  if (etype_csr != nullptr && rows > 0) {   // relation bins of dl: streaming (the partials buffer is free again)
+    int HP = 1;
+    while (HP < num_heads) HP <<= 1;
+    const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * R * 32;
+    rc = set_smem(gat_bwd_bins_kernel, smem);
+    if (rc != REGNN_OK) return rc;
+    const int nbb = min(partial_blocks(rows), 148 * 4);
+    gat_bwd_bins_kernel<<<nbb, kWarpsPerBlock * 32, smem, stream>>>(etype_csr, dl_csr, num_heads, indptr, row_begin, row_end, R,
+                                                                   num_heads, HP, partials);
+    launch_relation_grad_finalize(partials, nbb, R * num_heads, R * num_heads, theta, alpha, d_theta, stream);
   }
-  if (a.nfrag > 0) launch_rowsum(split, a.p0, num_heads * head_dim, d_fs, row_begin, row_end, stream);
-  return check_launch("regnn_gatv2_bwd_src");
+  return check_launch("regnn_gatv2_bwd_dst");
 }

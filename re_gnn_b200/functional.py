@@ -193,12 +193,14 @@ class _GatV2Aggregate(torch.autograd.Function):
     def forward(ctx, graph, etv, fs, fd, attn, theta, alpha, slope, keep, want_attn, softmax_eps):
         csr = graph.csr()
         et = etv[0] if etv is not None else None
-        out, rowmax, rowsum, a = ops.gatv2_fwd(csr, et, theta if et is not None else None, alpha, fs, fd, attn,
-                                               slope, keep, want_attn)
+        train = any(ctx.needs_input_grad)
+        out, rowmax, rowsum, a, saved = ops.gatv2_fwd(csr, et, theta if et is not None else None, alpha, fs, fd, attn,
+                                                      slope, keep, want_attn, save=train)
         if softmax_eps:
             rowsum = _global_max_eps(csr, out, rowmax, rowsum, a, softmax_eps)
         ctx.graph, ctx.et, ctx.alpha, ctx.slope = graph, et, alpha, slope
-        ctx.save_for_backward(fs, fd, attn, theta if et is not None else None, keep, out, rowmax, rowsum)
+        ctx.save_for_backward(fs, fd, attn, theta if et is not None else None, keep, out, rowmax, rowsum,
+                              *(saved if train else ()))
         if want_attn:
             ctx.mark_non_differentiable(a)
             return out, a
@@ -206,12 +208,10 @@ class _GatV2Aggregate(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _g_attn=None):
-        fs, fd, attn, theta, keep, out, rowmax, rowsum = ctx.saved_tensors
+        fs, fd, attn, theta, keep, out, rowmax, rowsum, logit_csr, qmask = ctx.saved_tensors
         csr = ctx.graph.csr()
-        g = g.contiguous()
-        a_csr, dl_csr, qmask, d_fd, d_attn, d_theta = ops.gatv2_bwd_dst(csr, ctx.et, theta, ctx.alpha, fs, fd, attn,
-                                                                        ctx.slope, keep, out, rowmax, rowsum, g)
-        d_fs = ops.gatv2_bwd_src(csr, a_csr, dl_csr, qmask, attn, ctx.slope, g)
+        d_fs, d_fd, d_attn, d_theta = ops.gatv2_bwd(csr, ctx.et, theta, ctx.alpha, fs, fd, attn, ctx.slope, keep, out,
+                                                    rowmax, rowsum, (logit_csr, qmask), g.contiguous())
         return (None, None, d_fs, d_fd, d_attn.view_as(attn),
                 d_theta.view_as(theta) if d_theta is not None else None, None, None, None, None, None)
 

@@ -347,7 +347,10 @@ def attn_scores_fwd(feat, attn_l, attn_r):
     return el, er
 
 
-def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_attn=False, rows=None):
+def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_attn=False, rows=None, save=False):
+    """-> (out, rowmax, rowsum, attention | None, saved | None).  ``save``: also store what the backward needs, the raw
+    logit of every (CSR slot, head) and the 128-bit sign mask of fs[src]+fd[dst] per (slot, 128-float slice):
+    ``saved = (logit_csr [E,H], qmask [E, ceil(H*D/128), 4] int32)``."""
     fs, fd, keep = _f32(fs), _f32(fd), _f32(keep)
     attn = _f32(attn).view(-1)
     n, h, d = fd.shape
@@ -359,57 +362,65 @@ def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_at
     rowsum = torch.zeros((n, h), dtype=torch.float32, device=dev)
     e = csr['indices'].numel()
     att = torch.zeros((max(e, 1), h), dtype=torch.float32, device=dev)[:e] if want_attn else None
+    saved = None
+    if save:
+        saved = (torch.empty((max(e, 1), h), dtype=torch.float32, device=dev),    # max(E, 1): never a NULL pointer
+                 torch.empty((max(e, 1), (h * d + 127) // 128, 4), dtype=torch.int32, device=dev))
     sp, ws = _attn_split(csr.get('split'), h, d, dev)
     order = row_order(csr) if _full(rb, re, n) else None
     with torch.cuda.device(dev):
         _lib.call('regnn_gatv2_fwd', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
                   _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep), h, d,
-                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(att), sp, _ptr(ws), _ptr(order), _stream())
+                  rb, re, _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(att), _ptr(saved[0]) if save else None,
+                  _ptr(saved[1]) if save else None, sp, _ptr(ws), _ptr(order), _stream())
         _lib.count_launches(1 + (sp is not None))
-    return out, rowmax, rowsum, att
+    return out, rowmax, rowsum, att, saved
 
 
-def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, rowmax, rowsum, g, rows=None):
-    """-> (a_csr, dl_csr, qmask, d_fd, d_attn, d_theta): see regnn_gatv2_bwd_dst."""
-    fs, fd, keep, g = _f32(fs), _f32(fd), _f32(keep), _f32(g)
+V2_STAGE_CHUNKS = 592   # REGNN_V2_STAGE_CHUNKS (csrc/gat.cu)
+
+
+def gatv2_bwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, rowmax, rowsum, saved, g, rows=None):
+    """Backward of ``gatv2_fwd(..., save=True)``: regnn_gat_bwd_stats -> regnn_gatv2_bwd_edges (the one gather pass) ->
+    regnn_gatv2_bwd_dst (streaming) -> (d_fs, d_fd, d_attn [H*D], d_theta | None)."""
+    fs, fd, keep, g, out = _f32(fs), _f32(fd), _f32(keep), _f32(g), _f32(out)
     attn = _f32(attn).view(-1)
+    logit_csr, qmask = saved
     n, h, d = fd.shape
     rb, re = _rows(rows, n)
     theta, et_csr, r = _rel(theta, et_csr)
     dev = fs.device
     e = csr['indices'].numel()
-    a_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
-    dl_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)[:e]
-    qmask = torch.empty((max(e, 1), (h * d + 127) // 128, 4), dtype=torch.int32, device=dev)
-    d_fd = torch.empty_like(fd) if _full(rb, re, n) else torch.zeros_like(fd)
-    d_attn = torch.empty(h * d, dtype=torch.float32, device=dev)
-    partials = torch.empty(_lib.partial_blocks(re - rb) * (r * h + h * d), dtype=torch.float64, device=dev)
+    full = _full(rb, re, n)
+    stats = torch.empty((n, h, 4), dtype=torch.float32, device=dev)
+    dl_csr = torch.empty((max(e, 1), h), dtype=torch.float32, device=dev)
+    d_fs = torch.empty_like(g) if full else torch.zeros_like(g)
+    d_fd = torch.empty_like(fd) if full else torch.zeros_like(fd)
+    d_attn_src = torch.empty(h * d, dtype=torch.float32, device=dev)
+    d_attn_dst = torch.empty(h * d, dtype=torch.float32, device=dev)
     d_theta = torch.zeros((r, h), dtype=torch.float32, device=dev) if r else None   # stays 0 when the graph has no edges
-    sp, ws = _attn_split(csr.get('split'), h, d, dev)
-    order = row_order(csr) if _full(rb, re, n) else None
+    split_t, split = csr.get('split_t'), csr.get('split')
+    sp_t, ws_t = _attn_split(split_t, h, d, dev)
+    sp, ws = _attn_split(split, h, d, dev)
+    order_t = row_order(csr, True) if full else None
+    nblocks = _lib.load().regnn_gatv2_bwd_edges_blocks(re - rb, split_t['struct'].num_frags if split_t else 0,
+                                                       split_t['struct'].num_long if split_t else 0, h, d,
+                                                       int(order_t is not None))
+    block_partials = torch.empty(max(nblocks, 1) * h * d, dtype=torch.float32, device=dev)
+    partials = torch.empty(max(_lib.partial_blocks() * h * d, V2_STAGE_CHUNKS * max(r * h, h * d)), dtype=torch.float64,
+                           device=dev)
     with torch.cuda.device(dev):
-        _lib.call('regnn_gatv2_bwd_dst', _ptr(csr['indptr']), _ptr(csr['indices']), _ptr(csr['eid']), _ptr(et_csr),
-                  _ptr(theta), float(alpha), r, _ptr(fs), _ptr(fd), _ptr(attn), float(slope), _ptr(keep),
-                  _ptr(out), _ptr(rowmax), _ptr(rowsum), _ptr(g), h, d, rb, re, _ptr(a_csr), _ptr(dl_csr), _ptr(qmask),
-                  _ptr(d_fd), _ptr(d_attn), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _ptr(order), _stream())
-        _lib.count_launches((3 if r else 2) + (sp is not None))
-    return a_csr, dl_csr, qmask, d_fd, d_attn, d_theta
-
-
-def gatv2_bwd_src(csr, a_csr, dl_csr, qmask, attn, slope, g, rows=None):
-    g = _f32(g)
-    attn = _f32(attn).view(-1)
-    n, h, d = g.shape
-    rb, re = _rows(rows, n)
-    d_fs = torch.empty_like(g) if _full(rb, re, n) else torch.zeros_like(g)
-    sp, ws = _attn_split(csr.get('split_t'), h, d, g.device)
-    order = row_order(csr, True) if _full(rb, re, n) else None
-    with torch.cuda.device(g.device):
-        _lib.call('regnn_gatv2_bwd_src', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
-                  _ptr(a_csr), _ptr(dl_csr), _ptr(qmask), _ptr(attn), float(slope), _ptr(g), h, d,
-                  rb, re, _ptr(d_fs), sp, _ptr(ws), _ptr(order), _stream())
-        _lib.count_launches(1 + (sp is not None))
-    return d_fs
+        _lib.call('regnn_gat_bwd_stats', _ptr(out), _ptr(g), _ptr(rowmax), _ptr(rowmax), _ptr(rowsum), n, h, d,
+                  _ptr(stats), _stream())
+        _lib.call('regnn_gatv2_bwd_edges', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
+                  _ptr(csr['eid']), _ptr(fs), _ptr(stats), _ptr(logit_csr), _ptr(qmask), _ptr(attn), float(slope),
+                  _ptr(keep), _ptr(g), h, d, rb, re, _ptr(d_fs), _ptr(dl_csr), _ptr(d_attn_src), _ptr(block_partials),
+                  _ptr(partials), sp_t, _ptr(ws_t), _ptr(order_t), _stream())
+        _lib.call('regnn_gatv2_bwd_dst', _ptr(csr['indptr']), _ptr(et_csr) if r else None, _ptr(theta), float(alpha), r,
+                  _ptr(fd), _ptr(dl_csr), _ptr(qmask), _ptr(attn), float(slope), h, d, rb, re, _ptr(d_fd),
+                  _ptr(d_attn_dst), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _stream())
+        _lib.count_launches(6 + (2 if r else 0) + (sp_t is not None) + (sp is not None))
+    return d_fs, d_fd, d_attn_src + d_attn_dst, d_theta
 
 
 # ---- grouped per-node-type input projection ---------------------------------------------------------------------

@@ -77,9 +77,19 @@ if not once:
         for _ in range(5):
             ops.gat_bwd(csr, etv[0], etv[1], theta, 100.0, feat, el, er, 0.2, None, out, rowmax, rowsum, gout, attn_l=al, attn_r=ar)
     print('  per ABI call (ms):', {k: round(v, 3) for k, v in tr.summary(5).items()})
-o2, m2, s2, _ = ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2)
-a2, dl2, qm2, _, _, _ = ops.gatv2_bwd_dst(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, gout)
-t('gatv2_fwd', lambda: ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2), b_v2_fwd)
-t('gatv2_bwd_dst', lambda: ops.gatv2_bwd_dst(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, gout))
-t('gatv2_bwd_src', lambda: ops.gatv2_bwd_src(csr, a2, dl2, qm2, attn, 0.2, gout))
+o2, m2, s2, _, sv2 = ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, save=True)
+t('gatv2_fwd (inference)', lambda: ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2), b_v2_fwd)
+t('gatv2_fwd (training: + logits, sign masks)', lambda: ops.gatv2_fwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, save=True),
+  b_v2_fwd + e * (4 * H + 16 * ((HD + 127) // 128)))
+# stats (2 N HD reads) + edges (E x (4HD + 16H + 4H + 16 HG + 8 + 4H write)) + dst stream (E x (4H + 16 HG) + 2 N HD) + bins
+b_v2_bwd = (n * (2 * 4 * HD + 16 * H) + e * (4 * HD + 24 * H + 16 * ((HD + 127) // 128) + 8) + n * 4 * HD * 2
+            + e * (4 * H + 16 * ((HD + 127) // 128)) + n * 2 * 4 * HD + e * (4 * H + 1))
+t('gatv2_bwd (stats+edges+dst)', lambda: ops.gatv2_bwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, sv2, gout),
+  b_v2_bwd)
+if not once:
+    from re_gnn_b200 import _lib
+    with _lib.Trace() as tr:
+        for _ in range(5):
+            ops.gatv2_bwd(csr, etv[0], theta, 100.0, feat, fd, attn, 0.2, None, o2, m2, s2, sv2, gout)
+    print('  per ABI call (ms):', {k: round(v, 3) for k, v in tr.summary(5).items()})
 t('el/er (eager torch, 2 x mul+sum)', lambda: ((feat * al).sum(-1), (feat * ar).sum(-1)))

@@ -1,0 +1,16 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 --maxfail=30 -p no:cacheprovider -k "gat or attention or layer_golden or model_golden or tiny or mag_regnn or regatv2 or v2" > $OUT/r2t_pytest.log 2>&1
+echo "pytest exit $?"; tail -4 $OUT/r2t_pytest.log | cut -c1-300
+for v in base nopf pf32 gatpf fwdpf allpf5 ds4 ds8 nomask nologit; do
+  lib=variants/libregnn_$v.so; [ $v = base ] && lib=re_gnn_b200/lib/libregnn_b200.so
+  echo "== $v"; REGNN_B200_LIB=$lib timeout 300 python scripts/attn_probe.py mag 8 16 2>&1 | grep -E "gat_fwd|gatv2|per ABI"
+done | tee $OUT/r2t_probes.log
+for v in base gatpf fwdpf; do
+  lib=variants/libregnn_$v.so; [ $v = base ] && lib=re_gnn_b200/lib/libregnn_b200.so
+  echo "== $v h2d64 / acm"
+  REGNN_B200_LIB=$lib timeout 300 python scripts/attn_probe.py mag 2 64 2>&1 | grep -E "gat_fwd|gatv2|per ABI"
+  REGNN_B200_LIB=$lib timeout 300 python scripts/attn_probe.py acm 8 64 2>&1 | grep -E "gat_fwd|gatv2|per ABI"
+done | tee -a $OUT/r2t_probes.log

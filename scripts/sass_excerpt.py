@@ -21,8 +21,8 @@ KERNELS = [   # (label, substring of the mangled name)
     ('gat_fwd_rg_kernel<32,false> (REGAT forward)', 'gat_fwd_rg_kernelILi32ELb0'),
     ('gat_bwd_edges_kernel<32,4,false> (REGAT backward gather pass, D = 16)', 'gat_bwd_edges_kernelILi32ELi4ELb0'),
     ('gatv2_fwd_rg_kernel<32,4,false> (REGATv2 forward, D = 16)', 'gatv2_fwd_rg_kernelILi32ELi4ELb0'),
-    ('gatv2_bwd_dst_rg_kernel<32,4> (REGATv2 backward, destination-major)', 'gatv2_bwd_dst_rg_kernelILi32ELi4'),
-    ('gatv2_bwd_src_rg_kernel<32> (REGATv2 backward, source-major, sign mask)', 'gatv2_bwd_src_rg_kernelILi32'),
+    ('gatv2_bwd_edges_kernel<32,4,false> (REGATv2 backward, the one gather pass)', 'gatv2_bwd_edges_kernelILi32ELi4ELb0'),
+    ('gatv2_bwd_dst_stream_kernel<32> (REGATv2 backward, destination-major streaming pass)', 'gatv2_bwd_dst_stream_kernelILi32'),
     ('grouped_linear_fwd_kernel (3 x TF32 mma.sync)', 'grouped_linear_fwd_kernel'),
     ('rows_to_slabs_kernel (peer-memory push)', 'rows_to_slabs_kernel'),
 ]

@@ -249,46 +249,42 @@ def _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope):
     return q, lr, l
 
 
-def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_attn=False, rows=None):
+def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_attn=False, rows=None, save=False):
     n = fd.shape[0]
     row, col = csr['row'].long(), csr['indices'].long()
-    _, _, l = _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope)
+    q, _, l = _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope)
     a, mx, sm = _softmax_rows(l, row, n)
     kc = _keep_csr(keep, csr)
     at = a if kc is None else a * kc
     out = torch.zeros_like(fd.detach()).index_add(0, row, at[:, :, None] * fs.detach()[col])
-    return out, mx, sm, (_to_edge_order(at, csr) if want_attn else None)
+    saved = (l, q > 0) if save else None    # the sign mask as a bool [E,H,D] tensor in slot order
+    return out, mx, sm, (_to_edge_order(at, csr) if want_attn else None), saved
 
 
-def gatv2_bwd_dst(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, rowmax, rowsum, g, rows=None):
-    g, out = g.detach(), out.detach()
+def gatv2_bwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, rowmax, rowsum, saved, g, rows=None):
+    """The formulas of the kernels (stored logits + sign bits; d_attn as the two node-side sums)."""
+    g, out, fs, fd = g.detach(), out.detach(), fs.detach(), fd.detach()
+    l, pos = saved
     row, col = csr['row'].long(), csr['indices'].long()
-    q, lr, l = _v2_logits(csr, et_csr, theta, alpha, fs, fd, attn, slope)
     a = torch.exp(l - rowmax[row]) / rowsum[row]
     kc = _keep_csr(keep, csr)
     at = a if kc is None else a * kc
-    da = (fs.detach()[col] * g[row]).sum(-1)
+    da = (fs[col] * g[row]).sum(-1)
     S = (out * g).sum(-1)
     dl = at * da - a * S[row]
     av = attn.detach().view(1, fs.shape[1], fs.shape[2])
-    dq = dl[:, :, None] * av * _lgrad(q, slope)
-    d_fd = torch.zeros_like(fd.detach()).index_add(0, row, dq)
-    d_attn = (dl[:, :, None] * lr).sum(0).reshape(-1)
+    phi = torch.where(pos, torch.ones((), dtype=g.dtype), torch.full((), slope, dtype=g.dtype))
+    t = dl[:, :, None] * phi
+    t_dst = torch.zeros_like(fd).index_add(0, row, t)
+    t_src = torch.zeros_like(fs).index_add(0, col, t)
+    d_fd = av * t_dst
+    d_fs = torch.zeros_like(fs).index_add(0, col, at[:, :, None] * g[row]) + av * t_src
+    d_attn = ((fs * t_src).sum(0) + (fd * t_dst).sum(0)).reshape(-1)
     d_theta = None
     if theta is not None and et_csr is not None:
         th = theta.detach()
         d_theta = torch.zeros_like(th).index_add(0, et_csr.long(), dl) * alpha * _lgrad(th * alpha, SLOPE)
-    return at, dl, (q > 0), d_fd, d_attn, d_theta      # the sign mask as a bool [E,H,D] tensor in slot order
-
-
-def gatv2_bwd_src(csr, a_csr, dl_csr, qmask, attn, slope, g, rows=None):
-    g = g.detach()
-    src = _rows_of(csr['indptr_t'])
-    dstn, slot = csr['indices_t'].long(), csr['slot_t'].long()
-    av = attn.detach().view(1, g.shape[1], g.shape[2])
-    deriv = torch.where(qmask[slot], torch.ones((), dtype=g.dtype), torch.full((), slope, dtype=g.dtype))
-    msg = a_csr[slot][:, :, None] * g[dstn] + dl_csr[slot][:, :, None] * av * deriv
-    return torch.zeros_like(g).index_add(0, src, msg)
+    return d_fs, d_fd, d_attn, d_theta
 
 
 def _grouped_rows(tables, seg_ptr, perm, local_idx, num_rows):
@@ -344,5 +340,5 @@ def install(monkeypatch):
     monkeypatch.setattr(G.Graph, 'csr', graph_csr)
     monkeypatch.setattr(G.Graph, 'etype_views', graph_etype_views)
     for name in ('wdeg_norm_fwd', 'wdeg_norm_bwd', 'spmm', 'spmm_bwd_w', 'spmm_bwd_fused', 'rowdot_norm_bwd', 'gat_fwd', 'gat_bwd',
-                 'gatv2_fwd', 'gatv2_bwd_dst', 'gatv2_bwd_src', 'attn_scores_fwd', 'grouped_linear_fwd', 'grouped_linear_bwd'):
+                 'gatv2_fwd', 'gatv2_bwd', 'attn_scores_fwd', 'grouped_linear_fwd', 'grouped_linear_bwd'):
         monkeypatch.setattr(ops, name, globals()[name])

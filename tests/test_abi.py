@@ -27,7 +27,7 @@ def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for s in ('regnn_csr_build', 'regnn_etype_permute', 'regnn_wdeg_norm_fwd', 'regnn_wdeg_norm_bwd',
               'regnn_spmm_fwd', 'regnn_spmm_bwd_w', 'regnn_gat_fwd', 'regnn_gat_bwd_stats', 'regnn_gat_bwd_edges', 'regnn_gat_bwd_reduce',
-              'regnn_gatv2_fwd', 'regnn_gatv2_bwd_dst', 'regnn_gatv2_bwd_src'):
+              'regnn_gatv2_fwd', 'regnn_gatv2_bwd_edges_blocks', 'regnn_gatv2_bwd_edges', 'regnn_gatv2_bwd_dst'):
         assert s in syms
 
 
