@@ -264,7 +264,8 @@ int regnn_gat_fwd(const int32_t* indptr, const int32_t* indices, const int32_t* 
  * statistics packed per (node, head) everything per edge is computed there -- DGL's autograd runs gsddmm(dot) over
  * feat[src] and a reverse-graph gspmm as two gather passes with [E,H] tensors in between.
  *
- * regnn_gat_bwd_stats: stats[v,h] = (er[v,h], rowmax[v,h], 1/rowsum[v,h], <out[v,h,:], G[v,h,:]>), float4 per (node, head). */
+ * regnn_gat_bwd_stats: stats[v,h] = (er[v,h], rowmax[v,h], 1/rowsum[v,h], <out[v,h,:], G[v,h,:]>), float4 per (node, head).
+ * er == NULL (REGATv2, no destination score): stats.x = 0. */
 int regnn_gat_bwd_stats(const float* out, const float* G, const float* er, const float* rowmax, const float* rowsum,
                         int64_t num_nodes, int num_heads, int head_dim, float* stats /* [N,H,4] */, void* stream);
 
@@ -326,7 +327,8 @@ int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t
  * saved, per CSR slot, the raw logit l[e,h] (logit_csr) and the sign of every component of q = fs[src]+fd[dst] as a
  * 128-bit mask per 128-float slice of the H*D row (qmask: uint32 [E, ceil(H*D/128), 4]; bit l of word c = component c of
  * the l-th 128-bit chunk of the slice is > 0) -- LeakyReLU'(q) is one bit per feature.  With the per-destination
- * statistics stats[v,h] = (., rowmax, 1/rowsum, <out[v,h,:], G[v,h,:]>) of regnn_gat_bwd_stats every per-edge quantity
+ * statistics stats[v,h] = (0, rowmax, 1/rowsum, <out[v,h,:], G[v,h,:]>) of regnn_gat_bwd_stats (er == NULL) every
+ * per-edge quantity
  *   a = exp(l - rowmax)/rowsum,  dl = a*keep*<fs[u],G[v]> - a*<out[v],G[v]>
  * is local to the pass that gathers G[v] for d_fs[u]:
  *   regnn_gatv2_bwd_edges  d_fs[u,h,:] = sum_{Out(u)} ( a*keep*G[v,h,:] + dl*attn[h,:]*LeakyReLU'(q) ),  dl_csr[slot,h],
@@ -334,8 +336,8 @@ int regnn_gatv2_fwd(const int32_t* indptr, const int32_t* indices, const int32_t
  *   regnn_gatv2_bwd_dst    d_fd[v,h,:] = attn[h,:] (.) T[v],  T[v] = sum_{In(v)} dl*LeakyReLU'(q)   (no gather: dl_csr and
  *                          qmask are read in slot order),  d_attn_dst = sum_v fd[v] (.) T[v],  d_theta [R,H]
  * and d_attn = d_attn_src + d_attn_dst (the caller adds the two [H*D] vectors).
- * Both calls must cover rows whose slots the forward call covered.  Deterministic: lane-local sums, per-block partials,
- * fixed-order finalize.
+ * Both calls must cover rows whose slots the forward call covered; E * max(H, ceil(H*D/128)) < 2^32 (32-bit slot
+ * offsets in the forward).  Deterministic: lane-local sums, per-block partials, fixed-order finalize.
  * block_partials: float [regnn_gatv2_bwd_edges_blocks(...) * H*D];  partials (edges): double [592 * H*D];
  * partials (dst): double [max(regnn_max_partial_blocks() * H*D, 592 * R*H)]. */
 int64_t regnn_gatv2_bwd_edges_blocks(int64_t num_rows, int num_frags /* of split_t */, int num_long /* of split_t */,

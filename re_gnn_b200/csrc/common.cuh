@@ -40,6 +40,14 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {
 }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 // Request a line into L2 without holding a register for it: the value is loaded later, at L2 latency.
+// exp(x) as one FMUL + MUFU.EX2 (ex2.approx.ftz: 2^-22 relative error like __expf, results below 2^-126 flush to 0;
+// __expf without -ftz spends three more instructions per call on the subnormal range).  exp(-inf) = 0.
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ float dot4(float4 a, float4 b) {

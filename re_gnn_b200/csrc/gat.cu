@@ -284,13 +284,13 @@ gat_fwd_rg_kernel(AttnArgs a) {
       }
       if (bm > -INFINITY) {  // uniform within a lane group
         const float m_new = fmaxf(m, bm);
-        const float sc = __expf(m - m_new);  // first batch: exp(-inf) = 0
+        const float sc = fast_exp(m - m_new);  // first batch: exp(-inf) = 0
         m = m_new;
         s *= sc;
         scale4(acc, sc);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          float p = __expf(l[u] - m_new);  // 0 for a missing slot
+          float p = fast_exp(l[u] - m_new);  // 0 for a missing slot
           s += p;
           if (EXTRA && si[u] >= 0 && act) {
             const size_t o = (size_t)seid[u] * H + h;
@@ -367,7 +367,7 @@ gat_bwd_stats_kernel(const float* __restrict__ out, const float* __restrict__ Gd
     if (act && (col & (D - 1)) == 0) {
       const size_t vh = (size_t)v * H + (col >> d_shift);
       const float sm = rowsum[vh];
-      stats[vh] = make_float4(er[vh], rowmax[vh], sm > 0.f ? 1.f / sm : 0.f, p);
+      stats[vh] = make_float4(er != nullptr ? er[vh] : 0.f, rowmax[vh], sm > 0.f ? 1.f / sm : 0.f, p);
     }
   }
 }
@@ -689,8 +689,11 @@ attn_scores_bwd_kernel(const float* __restrict__ feat, const float* __restrict__
 // q = fs[u] + fd[v] (LeakyReLU' is ONE BIT per feature: four warp ballots -> a 128-bit mask per (slot, 128-float slice))
 // are stored for the backward, 4H + 16*ceil(HD/128) bytes per edge -- the only place where fs[u] and fd[v] meet without
 // an extra gather is this pass.
+#ifndef REGNN_V2F_BLOCKS
+#define REGNN_V2F_BLOCKS 4
+#endif
 template <int G, int LPH, bool EXTRA>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, REGNN_V2F_BLOCKS)
 gatv2_fwd_rg_kernel(AttnArgs a, float* __restrict__ lcsr, uint32_t* __restrict__ qmask) {
   constexpr int U = kUG;
   static_assert(G % U == 0, "a batch must not straddle a cooperative slot load");
@@ -720,8 +723,9 @@ gatv2_fwd_rg_kernel(AttnArgs a, float* __restrict__ lcsr, uint32_t* __restrict__
   const int32_t* ip = a.indices + it.begin;
   const uint8_t* ep = a.etype + it.begin;
   const int32_t* eidp = a.eid + it.begin;
-  uint4* mrow = reinterpret_cast<uint4*>(qmask) + (size_t)it.begin * a.hg_count + it.hg;   // only used when saving
-  float* lrow = lcsr + (size_t)it.begin * H + h;
+  // saved outputs: 32-bit element offsets from the kernel-parameter bases (E * max(H, HG) < 2^32, checked by the caller)
+  const uint32_t moff = (uint32_t)it.begin * (uint32_t)a.hg_count + (uint32_t)it.hg;
+  const uint32_t loff = (uint32_t)it.begin * (uint32_t)H + (uint32_t)h;
   float4 acc = zero4();
   float m = -INFINITY, s = 0.f;
 
@@ -771,19 +775,19 @@ gatv2_fwd_rg_kernel(AttnArgs a, float* __restrict__ lcsr, uint32_t* __restrict__
             b.x = (b.x >> gbase) & gm; b.y = (b.y >> gbase) & gm; b.z = (b.z >> gbase) & gm; b.w = (b.w >> gbase) & gm;
           }
           const uint32_t t = (uint32_t)(t0 + j + u);
-          if (si[u] >= 0 && lg == 0) mrow[t * (uint32_t)a.hg_count] = b;   // one 16-byte store per (slot, slice)
-          if (si[u] >= 0 && leader) lrow[t * (uint32_t)H] = lu;
+          if (si[u] >= 0 && lg == 0) reinterpret_cast<uint4*>(qmask)[moff + t * (uint32_t)a.hg_count] = b;   // 16 bytes per (slot, slice)
+          if (si[u] >= 0 && leader) lcsr[loff + t * (uint32_t)H] = lu;
         }
       }
       if (bm > -INFINITY) {  // uniform within a lane group
         const float m_new = fmaxf(m, bm);
-        const float sc = __expf(m - m_new);
+        const float sc = fast_exp(m - m_new);
         m = m_new;
         s *= sc;
         scale4(acc, sc);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          float p = __expf(l[u] - m_new);  // 0 for a missing slot
+          float p = fast_exp(l[u] - m_new);  // 0 for a missing slot
           s += p;
           if (EXTRA && si[u] >= 0 && act) {
             const size_t o = (size_t)seid[u] * H + h;
@@ -839,9 +843,12 @@ gatv2_fwd_rg_kernel(AttnArgs a, float* __restrict__ lcsr, uint32_t* __restrict__
 //   gatv2_bwd_edges_kernel      source-major, gathers G[v]: d_fs rows, dl per slot, block partials of fs (.) T_src
 //   gatv2_bwd_dst_stream_kernel destination-major, NO gather: streams dl + sign masks in slot order -> d_fd, fd (.) T_dst
 //   gat_bwd_bins_kernel         relation bins of dl (streaming)
-// Measured on the MAG graph (H8 D16) and dropped: L2 prefetch of everything a slot will need (G row, statistics, logit,
-// mask) issued with the cooperative index load: no change; one record per slot (logits and masks adjacent, dl written in
-// place over the logit): 6.1 ms instead of 5.0 (the in-place store orders the loads of the next round behind it).
+// Measured on the MAG graph (H8 D16, 5.0 - 5.3 ms, 22 GB of DRAM traffic at 4.3 TB/s) and dropped: L2 prefetch of
+// everything a slot will need (G row, statistics, logit, mask) issued with the cooperative index load: no change; one
+// record per slot (logits and masks adjacent, dl written in place over the logit): 6.1 ms (the in-place store orders the
+// loads of the next round behind it); statistics packed to (rowmax + log rowsum, S) float2, half the bytes: 5.8 ms, and
+// ex2.approx instead of __expf: +0.4 ms -- ptxas then issues the loads of the second edge of a round after the math of
+// the first (one edge in flight instead of two); 4 or 6 blocks per SM instead of 5: 6.1 / 5.5 ms.
 #define REGNN_V2_STAGE_CHUNKS 592   // first-stage blocks of the d_attn column sum (4 per SM)
 #ifndef REGNN_V2D_UD
 #define REGNN_V2D_UD 4   // slots in flight per lane in the streaming pass
@@ -913,7 +920,8 @@ gatv2_bwd_edges_kernel(AttnArgs a, const uint32_t* __restrict__ qmask, float* __
     }
     const int cnt = min(G, maxlen - t0);
     for (int j = 0; j < cnt; j += U) {
-      float4 x[U], st[U];
+      float4 x[U];
+      float4 st[U];
       uint4 mb[U];
       float lv[U];
       int sd[U], ss[U];
@@ -1037,7 +1045,6 @@ gatv2_bwd_dst_stream_kernel(AttnArgs a, const uint32_t* __restrict__ qmask) {
   const int h = col_ok ? (col >> a.d_shift) : 0;
   const int64_t nrows = a.row_end - a.row_begin;
   const int64_t nitems = a.nfrag + nrows;
-  const float4 at = col_ok ? ldg4(a.el + col) : zero4();
   const uint4* mk = reinterpret_cast<const uint4*>(qmask) + hg;
   const float* dh = a.d_csr + h;
   float4 dat = zero4();
@@ -1069,24 +1076,39 @@ gatv2_bwd_dst_stream_kernel(AttnArgs a, const uint32_t* __restrict__ qmask) {
       }
     }
     if (v < 0 || !col_ok) continue;   // no warp-level primitives below
-    const float4 fdv = ldg4(a.fd + (size_t)v * HD + col);
+    prefetch_l2(a.fd + (size_t)v * HD + col);   // read after the slots (registers for loads in flight instead)
     PhiAcc ta{zero4(), 0.f};
+    // running pointers, 32-bit strides: the loop body is the two loads + 9 arithmetic instructions per slot
     const float* dp = dh + (size_t)begin * H;
     const uint4* mp = mk + (size_t)begin * HG;
-    for (int t = 0; t < len; t += UD) {
+    const uint32_t dstep = (uint32_t)H, mstep = (uint32_t)HG;
+    int left = len;
+    for (; left >= UD; left -= UD, dp += UD * dstep, mp += UD * mstep) {   // full batches: no predicates
       float dl[UD];
       uint4 mb[UD];
 #pragma unroll
       for (int u = 0; u < UD; ++u) {
-        const bool ok = t + u < len;
-        dl[u] = ok ? __ldg(dp + (uint32_t)(t + u) * (uint32_t)H) : 0.f;
-        mb[u] = ok ? __ldg(mp + (uint32_t)(t + u) * (uint32_t)HG) : make_uint4(0u, 0u, 0u, 0u);
+        dl[u] = __ldg(dp + u * dstep);
+        mb[u] = __ldg(mp + u * mstep);
       }
 #pragma unroll
       for (int u = 0; u < UD; ++u) phi_add(ta, dl[u], mb[u], lanebit);
     }
+    if (left > 0) {
+      float dl[UD - 1];
+      uint4 mb[UD - 1];
+#pragma unroll
+      for (int u = 0; u < UD - 1; ++u) {
+        const bool ok = u < left;
+        dl[u] = ok ? __ldg(dp + u * dstep) : 0.f;
+        mb[u] = ok ? __ldg(mp + u * mstep) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < UD - 1; ++u) phi_add(ta, dl[u], mb[u], lanebit);
+    }
     const float4 T = phi_total(ta, a.slope);
-    st4((frag ? a.p0 + (size_t)fi * HD : a.o2 + (size_t)v * HD) + col, mul4(at, T));
+    const float4 fdv = ldg4(a.fd + (size_t)v * HD + col);
+    st4((frag ? a.p0 + (size_t)fi * HD : a.o2 + (size_t)v * HD) + col, mul4(ldg4(a.el + col), T));
     dat.x = fmaf(fdv.x, T.x, dat.x); dat.y = fmaf(fdv.y, T.y, dat.y);
     dat.z = fmaf(fdv.z, T.z, dat.z); dat.w = fmaf(fdv.w, T.w, dat.w);
   }
@@ -1336,7 +1358,7 @@ extern "C" int regnn_gat_bwd_stats(const float* out, const float* Gd, const floa
                                    const float* rowsum, int64_t num_nodes, int num_heads, int head_dim, float* stats,
                                    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  REGNN_REQUIRE(out && Gd && er && rowmax && rowsum && stats && num_nodes >= 0, REGNN_ERR_INVALID_ARG,
+  REGNN_REQUIRE(out && Gd && rowmax && rowsum && stats && num_nodes >= 0, REGNN_ERR_INVALID_ARG,   /* er == NULL (REGATv2): stats.x = 0 */
                 "gat_bwd_stats: bad argument");
   int rc = check_shape("gat_bwd_stats", num_heads, head_dim, 0, false, true);
   if (rc != REGNN_OK) return rc;

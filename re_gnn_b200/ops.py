@@ -363,6 +363,9 @@ def gatv2_fwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep=None, want_at
     e = csr['indices'].numel()
     att = torch.zeros((max(e, 1), h), dtype=torch.float32, device=dev)[:e] if want_attn else None
     saved = None
+    if save and e * max(h, (h * d + 127) // 128) >= 2 ** 32:
+        raise ValueError('gatv2_fwd(save=True): E * max(H, ceil(H*D/128)) = %d exceeds the 32-bit slot offsets of the kernel'
+                         % (e * max(h, (h * d + 127) // 128)))
     if save:
         saved = (torch.empty((max(e, 1), h), dtype=torch.float32, device=dev),    # max(E, 1): never a NULL pointer
                  torch.empty((max(e, 1), (h * d + 127) // 128, 4), dtype=torch.int32, device=dev))
@@ -410,8 +413,8 @@ def gatv2_bwd(csr, et_csr, theta, alpha, fs, fd, attn, slope, keep, out, rowmax,
     partials = torch.empty(max(_lib.partial_blocks() * h * d, V2_STAGE_CHUNKS * max(r * h, h * d)), dtype=torch.float64,
                            device=dev)
     with torch.cuda.device(dev):
-        _lib.call('regnn_gat_bwd_stats', _ptr(out), _ptr(g), _ptr(rowmax), _ptr(rowmax), _ptr(rowsum), n, h, d,
-                  _ptr(stats), _stream())
+        _lib.call('regnn_gat_bwd_stats', _ptr(out), _ptr(g), None, _ptr(rowmax), _ptr(rowsum), n, h, d, _ptr(stats),
+                  _stream())
         _lib.call('regnn_gatv2_bwd_edges', _ptr(csr['indptr_t']), _ptr(csr['indices_t']), _ptr(csr['slot_t']),
                   _ptr(csr['eid']), _ptr(fs), _ptr(stats), _ptr(logit_csr), _ptr(qmask), _ptr(attn), float(slope),
                   _ptr(keep), _ptr(g), h, d, rb, re, _ptr(d_fs), _ptr(dl_csr), _ptr(d_attn_src), _ptr(block_partials),
