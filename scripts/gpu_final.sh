@@ -22,7 +22,7 @@ echo "ncu launches exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"spmm_rowgroup_kernel" -s 6 -c 2 -o /tmp/${TAG}_spmm $CMD > $OUT/${TAG}_ncu_spmm.log 2>&1
 ncu -i /tmp/${TAG}_spmm.ncu-rep --page raw --csv > $OUT/${TAG}_spmm_raw.csv 2>/dev/null
 python scripts/attn_probe.py mag 8 16 1 once > $OUT/${TAG}_attn_plain.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gat_fwd_rg_kernel|gat_bwd_edges_kernel|gatv2_fwd_rg_kernel|gatv2_bwd_dst_rg_kernel|gatv2_bwd_src_rg_kernel" -c 6 -o /tmp/${TAG}_gat python scripts/attn_probe.py mag 8 16 1 once > $OUT/${TAG}_ncu_gat.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gat_fwd_rg_kernel|gat_bwd_edges_kernel|gatv2_fwd_rg_kernel|gatv2_bwd_edges_kernel|gatv2_bwd_dst_stream_kernel" -c 16 -o /tmp/${TAG}_gat python scripts/attn_probe.py mag 8 16 1 once > $OUT/${TAG}_ncu_gat.log 2>&1
 echo "ncu gat exit $?"
 ncu -i /tmp/${TAG}_gat.ncu-rep --page raw --csv > $OUT/${TAG}_gat_raw.csv 2>/dev/null
 timeout 300 python scripts/attn_probe.py mag 8 16 > $OUT/${TAG}_attn_mag_8_16.log 2>&1; cat $OUT/${TAG}_attn_mag_8_16.log
