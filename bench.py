@@ -336,7 +336,8 @@ def attention_at_hbm_scale(dev, d, g, et, steps, warmup):
             'num_edges': int(e), 'l2': 'gathered matrix %.0f MB vs 126 MB L2; no flush needed' % (n * hd * 4 / 1e6),
             'roofline': {'bound': 'hbm', 'kernel': kname, 'achieved': alg / tk / 1e9, 'peak': hbm, 'peak_source': how,
                          'unit': 'GB/s', 'frac': alg / tk / 1e9 / hbm,
-                         'traffic': traffic.get('gat_fwd_mag_h8d16_bytes') if (kind, heads, dim) == ('regat', 8, 16) else None,
+                         'traffic': traffic.get({'regat': 'gat_fwd_mag_h8d16_bytes', 'regatv2': 'gatv2_fwd_mag_h8d16_bytes'}[kind])
+                         if (heads, dim) == (8, 16) else None,
                          'algorithmic_bytes_per_launch': int(alg), 'launch_ms': tk * 1e3, 'l2_resident': False}}
         del mod, x, gout
         torch.cuda.empty_cache()
