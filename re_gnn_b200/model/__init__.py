@@ -1,12 +1,12 @@
-"""The three callers of the hot path, mirrored so that epoch time can be measured (and golden
+"""The callers of the hot path, mirrored so that epoch time can be measured (and golden
 parity checked) where the reference checkout is absent.  Same constructor arguments, sub-module /
-parameter names and forward conventions as model/REGCN.py:6-46, model/REGAT.py:6-66 and
-model/REMixHop.py:19-101; the reference's own files also run unmodified on ``re_gnn_b200.layer``
-(tests/test_layers_host.py)."""
+parameter names and forward conventions as model/REGCN.py:6-46, model/REGAT.py:6-66,
+model/REMixHop.py:19-101 and model/REGIN.py:35-84; the reference's own files also run unmodified on
+``re_gnn_b200.layer`` (tests/test_layers_host.py)."""
 import torch
 from torch import nn
 
-from ..layer import REGraphConv, RESAGEConv, REGATConv, REGATv2Conv, REMixHopConv
+from ..layer import REGraphConv, RESAGEConv, REGATConv, REGATv2Conv, REMixHopConv, REGINConv
 
 
 class _TypedInput(nn.Module):
@@ -97,3 +97,46 @@ class REMixHop(_TypedInput):
         for l in range(1, self.num_layers):
             h = self.layers[l](self.g, self.dropout(h), e_feat)
         return self.fc_layers(h), h
+
+
+class _GinMLP(nn.Module):
+    """model/REGIN.py:9-32: declared as a two-layer MLP, but only dropout + ``linears[1]`` (input_dim -> output_dim) run;
+    ``linears[0]`` exists for state_dict compatibility."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, activation, dropout=0.):
+        super().__init__()
+        self.linears = nn.ModuleList([nn.Linear(input_dim, hidden_dim, bias=False),
+                                      nn.Linear(input_dim, output_dim, bias=False)])
+        self.dropout = nn.Dropout(dropout)
+        self.activation = activation
+
+    def reset_parameters(self):
+        for lin in self.linears:
+            lin.reset_parameters()
+
+    def forward(self, x):
+        return self.linears[1](self.dropout(x))
+
+
+class REGIN(_TypedInput):
+    def __init__(self, g, num_etypes, R, input_dim, hidden_dim, output_dim, n_layers, activation, dropout,
+                 feats_dim_list):
+        super().__init__()
+        self.g, self.num_layers = g, n_layers
+        self._make_fc_list(feats_dim_list, input_dim)
+        self.layers = nn.ModuleList()
+        for layer in range(n_layers):
+            in_c = input_dim if layer == 0 else hidden_dim
+            out_c = output_dim if layer == n_layers - 1 else hidden_dim
+            if layer != n_layers - 1:
+                self.layers.append(REGINConv(num_etypes, R, _GinMLP(in_c, hidden_dim, out_c, activation, dropout),
+                                             activation=activation))
+            else:   # the last layer aggregates only; the classifier is out_mlp
+                self.layers.append(REGINConv(num_etypes, R, None, activation=None))
+        self.out_mlp = _GinMLP(hidden_dim, hidden_dim, output_dim, activation, dropout)
+
+    def forward(self, features_list, e_feat):
+        h = self.layers[0](self.g, self._project(features_list), e_feat)
+        for l in range(1, self.num_layers):
+            h = self.layers[l](self.g, h, e_feat)
+        return self.out_mlp(h), h

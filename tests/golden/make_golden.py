@@ -29,6 +29,7 @@ from layer import REGraphConv, REGATConv, REGATv2Conv, REMixHopConv, RESAGEConv,
 from model.REGCN import REGCN  # noqa: E402
 from model.REGAT import REGAT  # noqa: E402
 from model.REMixHop import REMixHop  # noqa: E402
+from model.REGIN import REGIN  # noqa: E402
 
 ACT = {'elu': F.elu, 'relu': F.relu, None: None}
 ALPHA = 100.0
@@ -65,7 +66,12 @@ def perturb_relations(module, rng):
             p.data.copy_(v)
 
 
+ONLY = set(sys.argv[1:])   # `python tests/golden/make_golden.py <case> ...` rewrites only the named fixtures
+
+
 def save_case(name, module, graph_arrays, inputs, run, meta):
+    if ONLY and name not in ONLY:
+        return
     src, dst, et, n = graph_arrays
     g = make_graph(src, dst, n)
     module = module.double()
@@ -208,6 +214,14 @@ def main():
         m = ctor()
         perturb_relations(m, rng)
         save_case(name, m, G1, feats(), model_run, meta)
+
+    # the fourth caller (model/REGIN.py), added later with its own generator state so that it can be produced alone
+    # (`python tests/golden/make_golden.py model_regin`) without touching the fixtures above
+    torch.manual_seed(321)
+    rng = np.random.RandomState(321)
+    m = REGIN(g0, R, ALPHA, 16, 16, 4, 2, F.elu, 0.0, dims)
+    perturb_relations(m, rng)
+    save_case('model_regin', m, G1, feats(), model_run, dict(kind='REGIN', args=[R, ALPHA, 16, 16, 4, 2, 'elu', 0.0, dims]))
 
 
 if __name__ == '__main__':

@@ -84,6 +84,8 @@ def build_model(model_pkg, meta, g):
         return model_pkg.REGCN(g, *args)
     if meta['kind'] == 'REGAT':
         return model_pkg.REGAT(g, *args, use_gatv2=meta.get('use_gatv2', False))
+    if meta['kind'] == 'REGIN':
+        return model_pkg.REGIN(g, *args)
     return model_pkg.REMixHop(g, *args, activation=ACT[meta.get('activation')])
 
 

@@ -100,7 +100,7 @@ def test_product_path_has_no_cpu_fallback():
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'model')), reason='reference checkout not present')
 @pytest.mark.parametrize('name', MODEL_CASES)
 def test_reference_models_run_unmodified_on_our_layers(name, cpu_ops, monkeypatch):
-    """model/REGCN.py, REGAT.py, REMixHop.py imported from the reference, with OUR package registered
+    """model/REGCN.py, REGAT.py, REMixHop.py, REGIN.py imported from the reference, with OUR package registered
     as ``layer`` (and a name-only ``dgl`` for REMixHop.py's unused imports), must reproduce the
     reference-over-DGL-stub goldens."""
     import torch.nn.functional as F
@@ -120,6 +120,8 @@ def test_reference_models_run_unmodified_on_our_layers(name, cpu_ops, monkeypatc
         net = importlib.import_module('model.REGCN').REGCN(g, *args)
     elif meta['kind'] == 'REGAT':
         net = importlib.import_module('model.REGAT').REGAT(g, *args, use_gatv2=meta.get('use_gatv2', False))
+    elif meta['kind'] == 'REGIN':
+        net = importlib.import_module('model.REGIN').REGIN(g, *args)
     else:
         net = importlib.import_module('model.REMixHop').REMixHop(g, *args, activation=F.elu)
     net = helpers.load_params(net, case)
