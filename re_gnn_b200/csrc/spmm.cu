@@ -510,6 +510,10 @@ spmm_stream_kernel(StreamArgs sa) {
 // per lane (twice the rows in flight per warp): 2.41 vs 2.43 ms at F = 128, 1.31 vs 1.19 at F = 64, 0.86 vs 0.72 at
 // F = 32 -- no gain where it is equal, slower on narrow rows; 5 / 6 resident blocks per SM by capping registers at
 // 48 / 40 (2.52 / 2.56 ms) and 3 blocks x 71 registers (2.91): 4 x 4 gathers stays.
+// Also dropped (measured, r3a): decoding the item header ahead of time in the persistent backward (row id two iterations
+// ahead, row pointers one ahead, the next row's slot arrays prefetched into L2 at the end of the current row; no spills
+// at 64 registers): 2.95 vs 2.70 ms at F = 128 with the folded norm gradient, 1.54 vs 1.36 at F = 64, 0.74 vs 0.61 at
+// F = 16 -- the extra loads ahead of every row's gathers cost more than the shorter per-row chain saves.
 // Cooperative slot loads pay off where the kernel is issue-bound (fused backward: 2.73 -> 2.44 ms at F = 128,
 // 1.37 -> 1.22 at 64, 0.53 -> 0.50 at 16); the forward kernel is HBM-bound and slightly faster without (2.05 vs 2.14).
 #ifndef REGNN_RG_COOP
