@@ -948,6 +948,119 @@ def test_mag_full_graph_regat_properties(mag_full, heads, dim):
         assert torch.allclose(rowsum[v].double(), ssum, rtol=2e-5, atol=0)
 
 
+def _attention_float64_full(kind, csr, et_csr, f, fd, vec_a, vec_b, th, gout, slope, chunk=1 << 20):
+    """float64 evaluation of a fused attention core (forward + all gradients) on the device, chunked over the CSR slots
+    so that nothing [E,H,D]-sized in float64 exists for more than `chunk` edges: plain PyTorch, formulas of
+    layer/REGATConv.py:68-92 (kind 'gat': f, attn_l = vec_a, attn_r = vec_b) and layer/REGATv2Conv.py:133-152 (kind 'v2':
+    fs = f, fd, attn = vec_a) with the edge-softmax backward written out.  The pre-activations are formed in float32 as
+    the kernels form them (fs + fd; el + er + w), so both sides sit on the same side of every LeakyReLU kink."""
+    n, h, dd = f.shape
+    dev = f.device
+    row, col, etc = csr['row'].long(), csr['indices'].long(), et_csr.long()
+    e = row.numel()
+    t100 = th * 100.0
+    w32 = torch.where(t100 > 0, t100, t100 * 0.01)
+    f64, g64 = f.double(), gout.double()
+    a64 = vec_a.double().view(1, h, dd)
+    if kind == 'gat':
+        from re_gnn_b200 import ops
+        b64 = vec_b.double().view(1, h, dd)
+        # the float32 projection scores exactly as the layer forms them (another summation order would move a few of the
+        # 1.8e8 pre-activations across the LeakyReLU kink and flip their derivative)
+        el32, er32 = ops.attn_scores_fwd(f, vec_a, vec_b)
+    else:
+        fd64 = fd.double()
+    logit = torch.empty(e, h, dtype=torch.float64, device=dev)
+    for s0 in range(0, e, chunk):
+        sl = slice(s0, min(e, s0 + chunk))
+        if kind == 'gat':
+            pre = (el32[col[sl]] + er32[row[sl]] + w32[etc[sl]]).double()
+            logit[sl] = torch.where(pre > 0, pre, pre * slope)
+        else:
+            q = (f[col[sl]] + fd[row[sl]]).double()
+            logit[sl] = (torch.where(q > 0, q, q * slope) * a64).sum(-1) + w32[etc[sl]].double()
+    m = torch.full((n, h), float('-inf'), dtype=torch.float64, device=dev).scatter_reduce(
+        0, row[:, None].expand(e, h), logit, 'amax', include_self=True)
+    p = torch.exp(logit - m[row])
+    ssum = torch.zeros(n, h, dtype=torch.float64, device=dev).index_add_(0, row, p)
+    a = p / ssum[row]
+    del p, logit
+    out = torch.zeros(n, h, dd, dtype=torch.float64, device=dev)
+    for s0 in range(0, e, chunk):
+        sl = slice(s0, min(e, s0 + chunk))
+        out.index_add_(0, row[sl], a[sl, :, None] * f64[col[sl]])
+    S = (out * g64).sum(-1)
+    d_f = torch.zeros_like(out)
+    d_fd = torch.zeros_like(out)
+    d_va = torch.zeros(h, dd, dtype=torch.float64, device=dev)
+    d_vb = torch.zeros(h, dd, dtype=torch.float64, device=dev)
+    d_el = torch.zeros(n, h, dtype=torch.float64, device=dev)
+    d_er = torch.zeros(n, h, dtype=torch.float64, device=dev)
+    bins = torch.zeros(th.shape[0], h, dtype=torch.float64, device=dev)
+    for s0 in range(0, e, chunk):
+        sl = slice(s0, min(e, s0 + chunk))
+        r_, c_ = row[sl], col[sl]
+        grow = g64[r_]
+        dl = a[sl] * ((f64[c_] * grow).sum(-1) - S[r_])
+        d_f.index_add_(0, c_, a[sl, :, None] * grow)
+        if kind == 'gat':
+            pre = (el32[c_] + er32[r_] + w32[etc[sl]]).double()
+            dpre = dl * torch.where(pre > 0, 1.0, slope)
+            d_el.index_add_(0, c_, dpre)
+            d_er.index_add_(0, r_, dpre)
+            bins.index_add_(0, etc[sl], dpre)
+        else:
+            q = (f[c_] + fd[r_]).double()
+            t = dl[:, :, None] * torch.where(q > 0, 1.0, slope)
+            d_f.index_add_(0, c_, t * a64)
+            d_fd.index_add_(0, r_, t * a64)
+            d_va += (dl[:, :, None] * torch.where(q > 0, q, q * slope)).sum(0)
+            bins.index_add_(0, etc[sl], dl)
+    if kind == 'gat':
+        d_f += d_el[:, :, None] * a64 + d_er[:, :, None] * b64
+        d_va = (d_el[:, :, None] * f64).sum(0)
+        d_vb = (d_er[:, :, None] * f64).sum(0)
+    d_th = bins * 100.0 * torch.where(t100 > 0, 1.0, 0.01).double()
+    return out, d_f, d_fd, d_va, d_vb, d_th
+
+
+@pytest.mark.parametrize('kind,heads,dim', [('gat', 8, 16), ('v2', 8, 16), ('v2', 2, 64)])
+def test_mag_full_graph_attention_vs_float64(mag_full, kind, heads, dim):
+    """BASELINE config 4's graph at FULL size (N = 1.94 M, E = 23.05 M, hub rows of 10^4..10^5 in-edges through the
+    long-row fragment path on both CSR views), H*D = 128: output and EVERY gradient of the fused REGAT core
+    (RF.gat_layer) and of the fused REGATv2 core (RF.gatv2_aggregate: forward that saves logits + sign masks, one-gather
+    backward, streaming destination pass) against a float64 evaluation of the same formulas in plain PyTorch on the
+    device (chunked over the edges)."""
+    d, g, et = mag_full
+    n, r = d['num_nodes'], d['num_relations']
+    csr = g.csr()
+    etv = g.etype_views(et, r)
+    gen = torch.Generator(device=DEV).manual_seed(heads * 100 + dim)
+    f = (torch.randn(n, heads, dim, device=DEV, generator=gen) * 0.5).requires_grad_(True)
+    fd = (torch.randn(n, heads, dim, device=DEV, generator=gen) * 0.5).requires_grad_(True)
+    va = (torch.randn(1, heads, dim, device=DEV, generator=gen) * 0.3).requires_grad_(True)
+    vb = (torch.randn(1, heads, dim, device=DEV, generator=gen) * 0.3).requires_grad_(True)
+    th = _theta(r, heads, 5).to(DEV, torch.float32).requires_grad_(True)
+    gout = torch.randn(n, heads, dim, device=DEV, generator=gen)
+    if kind == 'gat':
+        out, _ = RF.gat_layer(g, etv, f, va, vb, th, 100.0, 0.2)
+    else:
+        out, _ = RF.gatv2_aggregate(g, etv, f, fd, va, th, 100.0, 0.2)
+    out.backward(gout)
+    with torch.no_grad():
+        ref = _attention_float64_full(kind, csr, etv[0], f.detach(), fd.detach(), va.detach(), vb.detach(), th.detach(),
+                                      gout, 0.2)
+    tag = 'MAG full %s h%dd%d ' % (kind, heads, dim)
+    helpers.assert_close(out.detach().cpu(), ref[0].cpu(), 2 * RTOL, tag + 'out')
+    helpers.assert_close(f.grad.cpu(), ref[1].cpu(), 2 * RTOL, tag + ('d_feat' if kind == 'gat' else 'd_fs'))
+    if kind == 'v2':
+        helpers.assert_close(fd.grad.cpu(), ref[2].cpu(), 2 * RTOL, tag + 'd_fd')
+    helpers.assert_close(va.grad.view(heads, dim).cpu(), ref[3].cpu(), 5 * RTOL, tag + ('d_attn_l' if kind == 'gat' else 'd_attn'))
+    if kind == 'gat':
+        helpers.assert_close(vb.grad.view(heads, dim).cpu(), ref[4].cpu(), 5 * RTOL, tag + 'd_attn_r')
+    helpers.assert_close(th.grad.cpu(), ref[5].cpu(), 5 * RTOL, tag + 'd_theta')
+
+
 # ---- grouped per-node-type input projection (one launch for all types, 3 x TF32 products) -------------------------
 @pytest.mark.parametrize('mode,dims,n_out', [('contiguous', (334, 4231, 50, 20), 64), ('sampled', (128, 128, 128, 128), 512),
                                              ('sampled', (12, 7, 9), 8), ('contiguous', (5,), 3)])
