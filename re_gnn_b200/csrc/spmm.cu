@@ -510,6 +510,9 @@ spmm_stream_kernel(StreamArgs sa) {
 // per lane (twice the rows in flight per warp): 2.41 vs 2.43 ms at F = 128, 1.31 vs 1.19 at F = 64, 0.86 vs 0.72 at
 // F = 32 -- no gain where it is equal, slower on narrow rows; 5 / 6 resident blocks per SM by capping registers at
 // 48 / 40 (2.52 / 2.56 ms) and 3 blocks x 71 registers (2.91): 4 x 4 gathers stays.
+// Two gathers per lane with more resident blocks (r3e, folded norm gradient, F = 128 / 64 / 16): 4 x 2 2.99 / 1.55 / 0.64 ms,
+// 5 x 2 (48 registers) 3.14 / 1.46 / 0.64, 6 x 2 (40) 2.94 / 1.61 / 0.71, 8 x 2 (32, 40 B spilled) 2.96 / 1.61 / 0.78 against
+// 4 x 4: 2.63 / 1.36 / 0.62.
 // Also dropped (measured, r3a): decoding the item header ahead of time in the persistent backward (row id two iterations
 // ahead, row pointers one ahead, the next row's slot arrays prefetched into L2 at the end of the current row; no spills
 // at 64 registers): 2.95 vs 2.70 ms at F = 128 with the folded norm gradient, 1.54 vs 1.36 at F = 64, 0.74 vs 0.61 at
