@@ -191,7 +191,7 @@ int regnn_spmm_bwd_fused(const int32_t* indptr_t, const int32_t* indices_t, cons
  *   rows -> slabs: regnn_rows_to_slabs pushes this rank's row block, column slice q to rank q's slab;
  *   slabs -> rows: the *_scatter variants of the two SpMM entry points store each finished row straight into
  *                  its owner's row block (regnn_peer_rows_t) from the kernel epilogue -- compute and exchange
- *                  are one kernel.
+ *                  are one kernel; regnn_slabs_to_rows is the stand-alone push for the attention kernels.
  * The caller provides the peer-mapped buffers (e.g. CUDA VMM / IPC; the Python binding uses torch symmetric memory)
  * and a cross-rank barrier after each call before the written buffers are read. */
 typedef struct regnn_peer_rows {
@@ -206,6 +206,12 @@ typedef struct regnn_peer_rows {
  * peer_slabs[q] + (row_offset + i) * (feat/P): per peer one contiguous range.  feat % (4*num_ranks) == 0. */
 int regnn_rows_to_slabs(const float* X, int64_t ldx, int64_t num_rows, int feat, int num_ranks, int64_t row_offset,
                         float* const* peer_slabs /* device array [num_ranks] */, void* stream);
+
+/* The reverse re-partition for kernels without a scatter epilogue (the fused attention kernels, one head slice per
+ * rank): S [num_rows, feat] is this rank's column slab (ld lds); row v is stored to
+ * peers->base[v / rows_per_rank][(v % rows_per_rank) * ld + col_offset .. + feat). */
+int regnn_slabs_to_rows(const float* S, int64_t lds, int64_t num_rows, int feat, const regnn_peer_rows_t* peers,
+                        void* stream);
 
 /* regnn_spmm_fwd over the full row range [0, num_rows) of a column slab (feat <= 128, feat % 4 == 0, row_order required) whose
  * result rows are stored to their owner ranks: peers->base[v / rows_per_rank][(v % rows_per_rank) * ld + col_offset].

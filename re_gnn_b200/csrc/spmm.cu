@@ -160,6 +160,27 @@ __global__ void rows_to_slabs_kernel(const float* __restrict__ X, int64_t ldx, i
   }
 }
 
+// Column slab -> row blocks over peer memory, for the kernels that have no scatter epilogue of their own (the fused
+// attention kernels: one head slice per rank): rows [q*per, (q+1)*per) of this rank's slab S [N, Fc] go to rank q's row
+// block at column col_offset.  The local read is contiguous, every destination row gets one Fc*4-byte store burst
+// (64..512 bytes); peers in rank-rotated order as above.
+__global__ void slabs_to_rows_kernel(const float* __restrict__ S, int64_t lds, int64_t rows, int Fc, PeerRows peers,
+                                     int first_peer) {
+  const int q = (int)((blockIdx.y + (unsigned)first_peer) % gridDim.y);
+  const int L = Fc >> 2;
+  const int64_t r0 = (int64_t)q * peers.per;
+  const int64_t cnt = min(rows, r0 + (int64_t)peers.per) - r0;
+  if (cnt <= 0) return;
+  const int64_t total = cnt * L;
+  float* dst = peers.base[q] + peers.col;
+  const float* src = S + (size_t)r0 * lds;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / L;
+    const int c = (int)(e - i * L) << 2;
+    st4(dst + (size_t)i * peers.ld + c, ldg4_stream(src + (size_t)i * lds + c));
+  }
+}
+
 // ---- per-block reduction of lane-local relation bins ------------------------------------------
 // bins: [warps][R][32] floats (lane-local running sums), scratch: [warps][R] doubles.
 __device__ __forceinline__ void reduce_bins(const float* bins, double* scratch, int R,
@@ -1463,6 +1484,23 @@ extern "C" int regnn_rows_to_slabs(const float* X, int64_t ldx, int64_t num_rows
   rows_to_slabs_kernel<<<dim3(bx, (unsigned)num_ranks), 256, 0, (cudaStream_t)stream>>>(X, ldx, num_rows, Fc, row_offset,
                                                                                      peer_slabs, first_peer);
   return check_launch("regnn_rows_to_slabs");
+}
+
+extern "C" int regnn_slabs_to_rows(const float* S, int64_t lds, int64_t num_rows, int feat,
+                                   const regnn_peer_rows_t* peers, void* stream) {
+  REGNN_REQUIRE(S && peers && num_rows >= 0 && feat >= 4 && feat % 4 == 0 && lds % 4 == 0 && aligned_to(S, 16),
+                REGNN_ERR_INVALID_ARG, "slabs_to_rows: bad argument (16-byte aligned rows of whole 128-bit chunks)");
+  PeerRows pr;
+  int rc = fill_peers(&pr, peers, feat, num_rows, "slabs_to_rows");
+  if (rc != REGNN_OK) return rc;
+  if (num_rows == 0) return REGNN_OK;
+  const int64_t total = (int64_t)pr.per * (feat / 4);
+  const int64_t want = (total + 255) / 256;
+  const unsigned bx = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  const int first_peer = (int)((peers->col_offset / feat) % peers->num_ranks);   // this rank's index: rotated peer order
+  slabs_to_rows_kernel<<<dim3(bx, (unsigned)peers->num_ranks), 256, 0, (cudaStream_t)stream>>>(S, lds, num_rows, feat, pr,
+                                                                                              first_peer);
+  return check_launch("regnn_slabs_to_rows");
 }
 
 static int spmm_bwd_fused_impl(const int32_t* indptr_t, const int32_t* indices_t,

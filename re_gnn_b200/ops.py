@@ -209,19 +209,31 @@ def rows_to_slabs(x_own, num_ranks, row_offset, peer_slab_ptrs):
         _lib.count_launches(1)
 
 
-def spmm_scatter(csr, etype, theta, alpha, norm_src, norm_dst, x_cols, peers, y_local=None):
+def slabs_to_rows(slab, num_rows, peers):
+    """Pushes rows [0, num_rows) of this rank's column slab ``slab`` [>= num_rows, F/P] to their owner ranks' row blocks
+    (regnn_slabs_to_rows; ``peers``: a ``_lib.PeerRows``)."""
+    slab = _f32(slab)
+    with torch.cuda.device(slab.device):
+        _lib.call('regnn_slabs_to_rows', _ptr(slab), slab.stride(0), int(num_rows), slab.shape[1], ctypes.byref(peers),
+                  _stream())
+        _lib.count_launches(1)
+
+
+def spmm_scatter(csr, etype, theta, alpha, norm_src, norm_dst, x_cols, peers, y_local=None, transposed=False):
     """regnn_spmm_fwd_scatter: forward SpMM of a column slab, result rows stored to their owner ranks (``peers``: a
-    ``_lib.PeerRows``) and, with ``y_local`` ([rows >= N, F/P] fp32), also kept as a local slab."""
+    ``_lib.PeerRows``) and, with ``y_local`` ([rows >= N, F/P] fp32), also kept as a local slab.  ``transposed``: over
+    the transposed view (the backward of the un-weighted propagation; ``etype`` is then the transposed-order array)."""
     x_cols = _f32(x_cols)
-    n = csr['indptr'].numel() - 1
+    sfx = '_t' if transposed else ''
+    n = csr['indptr' + sfx].numel() - 1
     f = x_cols.shape[1]
     theta = _f32(theta).view(-1) if theta is not None else None
-    sp, ws, extra = _split_args(csr.get('split'), f, x_cols.device)
+    sp, ws, extra = _split_args(csr.get('split' + sfx), f, x_cols.device)
     with torch.cuda.device(x_cols.device):
-        _lib.call('regnn_spmm_fwd_scatter', _ptr(csr['indptr']), _ptr(csr['indices']),
+        _lib.call('regnn_spmm_fwd_scatter', _ptr(csr['indptr' + sfx]), _ptr(csr['indices' + sfx]),
                   _ptr(etype) if theta is not None else None, _ptr(theta), float(alpha),
                   theta.numel() if theta is not None else 0, _ptr(norm_src), _ptr(norm_dst), _ptr(x_cols),
-                  x_cols.stride(0), n, f, sp, _ptr(ws), _ptr(row_order(csr)), ctypes.byref(peers), _ptr(y_local),
+                  x_cols.stride(0), n, f, sp, _ptr(ws), _ptr(row_order(csr, transposed)), ctypes.byref(peers), _ptr(y_local),
                   y_local.stride(0) if y_local is not None else 0, _stream())
         _lib.count_launches(1 + extra)
 

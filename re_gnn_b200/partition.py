@@ -272,13 +272,17 @@ class _PeerSlabPropagate(torch.autograd.Function):
         x_own = x_own.contiguous()
         ops.rows_to_slabs(x_own, xch.parts, rank * xch.per, xch.x_ptrs)
         xch.barrier()            # every rank's slice of X has landed in my slab
-        ops.spmm_scatter(csr, etv[0], theta, alpha, norm, norm, xch.x_cols, xch.peer_y,
-                         y_local=xch.y_cols if norm is not None else None)
+        weighted = theta is not None
+        ops.spmm_scatter(csr, etv[0] if weighted else None, theta, alpha, norm, norm, xch.x_cols, xch.peer_y,
+                         y_local=xch.y_cols if (norm is not None and weighted) else None)
         xch.barrier()            # every rank's columns of my rows have landed in my row block
         y_own = xch.y_rows[:re - rb]
-        if not alias:
+        if not alias or not weighted:
             y_own = y_own.clone()
         ctx.graph, ctx.etv, ctx.alpha, ctx.bounds, ctx.rank, ctx.xch, ctx.alias = graph, etv, alpha, bounds, rank, xch, alias
+        ctx.weighted = weighted
+        if not weighted:   # REMixHop's copy_u propagation: no fused backward to fold the norm gradient into
+            ctx.x_own, ctx.y_own = x_own.detach(), y_own
         ctx.save_for_backward(theta, norm)
         return y_own
 
@@ -290,6 +294,12 @@ class _PeerSlabPropagate(torch.autograd.Function):
         g_own = g_own.contiguous()
         ops.rows_to_slabs(g_own, xch.parts, rank * xch.per, xch.g_ptrs)
         xch.barrier()
+        if not ctx.weighted:   # the transposed SpMM alone, rows scattered to their owners; the owner's row dots are local
+            ops.spmm_scatter(csr, None, None, ctx.alpha, norm, norm, xch.g_cols, xch.peer_dx, transposed=True)
+            xch.barrier()
+            dx_own = xch.dx_rows[:re - rb].clone()
+            d_norm = _own_rows_norm_grad(norm, ctx.x_own, ctx.y_own, g_own, dx_own, rb, re) if norm is not None else None
+            return None, None, dx_own, None, None, d_norm, None, None, None, None
         # d_norm: every row's norm gradient restricted to this rank's columns (all N rows, a share of the total)
         d_theta, d_norm = ops.spmm_bwd_fused_scatter(csr, ctx.etv[1], theta, ctx.alpha, norm, xch.x_cols, xch.g_cols,
                                                      xch.peer_dx, y_cols=xch.y_cols if norm is not None else None)
@@ -363,8 +373,72 @@ class _HeadSlicedGat(torch.autograd.Function):
         return None, None, d_f_own, g_al, g_ar, g_th, None, None, None, None, None
 
 
-def head_sliced_gat(graph, etv, f_own, attn_l, attn_r, theta, alpha, slope, bounds, rank, group=None):
-    """f_own [rows_own, H, D] -> out rows [rows_own, H, D]; see ``_HeadSlicedGat``."""
+class _PeerHeadSlicedGat(torch.autograd.Function):
+    """``_HeadSlicedGat`` with the four re-partitions done by our own kernels over peer memory (a ``SlabExchange`` of
+    width H*D): row blocks are pushed into the peers' head slabs (regnn_rows_to_slabs), the finished head slab is pushed
+    back to the row owners (regnn_slabs_to_rows) -- no collective library call, no pack / unpack pass.  The head slab of
+    the features stays in the exchange buffer for the backward pass."""
+
+    @staticmethod
+    def forward(ctx, graph, etv, f_own, attn_l, attn_r, theta, alpha, slope, bounds, rank, xch):
+        csr = graph.csr()
+        n = graph.number_of_nodes()
+        parts = xch.parts
+        rows_own, heads, dim = f_own.shape
+        if heads % parts or xch.feat != heads * dim:
+            raise ValueError('peer head-sliced attention needs num_heads divisible by the number of ranks and a '
+                             'SlabExchange of width num_heads * head_dim')
+        hs = heads // parts
+        sl = slice(rank * hs, (rank + 1) * hs)
+        ops.rows_to_slabs(f_own.reshape(rows_own, heads * dim).contiguous(), parts, rank * xch.per, xch.x_ptrs)
+        xch.barrier()            # every rank's rows of my heads have landed in my slab
+        f_cols = xch.x_cols[:n].view(n, hs, dim)
+        al, ar = attn_l[:, sl].contiguous(), attn_r[:, sl].contiguous()
+        th = theta[:, sl].contiguous() if etv is not None else None
+        et = etv[0] if etv is not None else None
+        el, er = ops.attn_scores_fwd(f_cols, al, ar)
+        out, rowmax, rowsum, _ = ops.gat_fwd(csr, et, th, alpha, f_cols, el, er, slope)
+        ops.slabs_to_rows(out.view(n, hs * dim), n, xch.peer_y)
+        xch.barrier()            # every rank's heads of my rows have landed in my row block
+        ctx.graph, ctx.etv, ctx.alpha, ctx.slope, ctx.rank, ctx.xch = graph, etv, alpha, slope, rank, xch
+        ctx.shape, ctx.sl = (rows_own, heads, dim), sl
+        ctx.save_for_backward(el, er, al, ar, th, out, rowmax, rowsum, attn_l, attn_r, theta)
+        return xch.y_rows[:rows_own].clone().view(rows_own, heads, dim)
+
+    @staticmethod
+    def backward(ctx, g_own):
+        el, er, al, ar, th, out, rowmax, rowsum, attn_l, attn_r, theta = ctx.saved_tensors
+        xch, rank = ctx.xch, ctx.rank
+        csr = ctx.graph.csr()
+        rows_own, heads, dim = ctx.shape
+        n = ctx.graph.number_of_nodes()
+        parts = xch.parts
+        hs = heads // parts
+        ops.rows_to_slabs(g_own.reshape(rows_own, heads * dim).contiguous(), parts, rank * xch.per, xch.g_ptrs)
+        xch.barrier()
+        f_cols = xch.x_cols[:n].view(n, hs, dim)
+        g_cols = xch.g_cols[:n].view(n, hs, dim)
+        et, et_t = (ctx.etv[0], ctx.etv[1]) if ctx.etv is not None else (None, None)
+        d_f, _, _, d_th, d_al, d_ar = ops.gat_bwd(csr, et, et_t, th, ctx.alpha, f_cols, el, er, ctx.slope, None, out,
+                                                   rowmax, rowsum, g_cols, attn_l=al, attn_r=ar)
+        ops.slabs_to_rows(d_f.view(n, hs * dim), n, xch.peer_dx)
+        xch.barrier()
+        d_f_own = xch.dx_rows[:rows_own].clone().view(rows_own, heads, dim)
+        g_al, g_ar = torch.zeros_like(attn_l), torch.zeros_like(attn_r)
+        g_al[:, ctx.sl] = d_al.view(1, hs, dim)
+        g_ar[:, ctx.sl] = d_ar.view(1, hs, dim)
+        g_th = None
+        if d_th is not None:
+            g_th = torch.zeros_like(theta)
+            g_th[:, ctx.sl] = d_th
+        return None, None, d_f_own, g_al, g_ar, g_th, None, None, None, None, None
+
+
+def head_sliced_gat(graph, etv, f_own, attn_l, attn_r, theta, alpha, slope, bounds, rank, group=None, exchange=None):
+    """f_own [rows_own, H, D] -> out rows [rows_own, H, D]; see ``_HeadSlicedGat``.  ``exchange`` (a ``SlabExchange`` of
+    width H*D): the re-partitions run over peer memory inside our own kernels instead of NCCL / gloo all-to-alls."""
+    if exchange is not None:
+        return _PeerHeadSlicedGat.apply(graph, etv, f_own, attn_l, attn_r, theta, alpha, slope, bounds, rank, exchange)
     return _HeadSlicedGat.apply(graph, etv, f_own, attn_l, attn_r, theta, alpha, slope, bounds, rank, group)
 
 

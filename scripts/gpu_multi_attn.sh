@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+N=${1:-2}
+TAG=${2:-r3f}
+OUT=gpurun_out
+mkdir -p $OUT
+RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 600 $RUN --master-port 29521 scripts/check_multi_gpu_attn.py 1.0 8 16 10 > $OUT/${TAG}_attn_$N.log 2> $OUT/${TAG}_attn_$N.err
+echo "exit $?"; grep -E "^\{|MULTI_GPU_ATTN" $OUT/${TAG}_attn_$N.log | cut -c1-1500; grep -v "OMP_NUM\|\*\*\*" $OUT/${TAG}_attn_$N.err | tail -12
