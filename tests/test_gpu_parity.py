@@ -543,6 +543,68 @@ def test_feature_sliced_propagate_world1_nccl(peer):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('peer', [False, True])
+def test_sharded_attention_and_mixhop_world1_nccl(peer):
+    """Single-rank NCCL group: partition.head_sliced_gat (REGAT core, heads = column slabs) and the un-weighted
+    (REMixHop) column-slab propagation must equal functional.gat_layer / functional.propagate bit for bit.  peer=True
+    runs the peer-memory variants (regnn_rows_to_slabs in, regnn_slabs_to_rows / the SpMM scatter epilogue out) through
+    a SlabExchange whose only peer is this rank; scripts/check_multi_gpu_attn.py is the same check across real ranks."""
+    import torch.distributed as dist
+    from re_gnn_b200 import functional as RF, partition
+    if DEV == 'cpu' and peer:
+        pytest.skip('peer-mapped memory needs a GPU')
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', str(29400 + os.getpid() % 500))
+        if DEV == 'cpu':
+            dist.init_process_group('gloo', rank=0, world_size=1)
+        else:
+            dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device(DEV))
+    try:
+        d = synth.hetero_graph('acm', seed=6, scale=0.2)
+        g, et = _graph(d), torch.as_tensor(d['etype']).to(DEV)
+        n, r, heads, dim = d['num_nodes'], d['num_relations'], 4, 16
+        etv = g.etype_views(et, r)
+        gen = torch.Generator(device=DEV).manual_seed(9)
+        f = torch.randn(n, heads, dim, device=DEV, generator=gen) * 0.5
+        gout = torch.randn(n, heads, dim, device=DEV, generator=gen)
+        al0 = torch.randn(1, heads, dim, device=DEV, generator=gen) * 0.3
+        ar0 = torch.randn(1, heads, dim, device=DEV, generator=gen) * 0.3
+        th0 = _theta(r, heads, 6).to(DEV, torch.float32)
+        bounds = partition.row_blocks(g.csr()['indptr'], 1, balance='rows')
+        xch = partition.SlabExchange(heads * dim, bounds, 0, torch.device(DEV)) if peer else None
+        res = []
+        for sharded in (False, True, True):   # twice: the exchange buffers are reused from step to step
+            leaves = [t.clone().requires_grad_(True) for t in (f, al0, ar0, th0)]
+            if sharded:
+                out = partition.head_sliced_gat(g, etv, *leaves, 100.0, 0.2, bounds, 0, exchange=xch)
+            else:
+                out, _ = RF.gat_layer(g, etv, *leaves, 100.0, 0.2)
+            out.backward(gout)
+            res.append([out.detach().clone()] + [t.grad.clone() for t in leaves])
+        for k in (1, 2):
+            assert torch.equal(res[0][0], res[k][0]) and torch.equal(res[0][1], res[k][1])
+            for i, name in ((2, 'd_attn_l'), (3, 'd_attn_r'), (4, 'd_theta')):
+                helpers.assert_close(res[k][i].cpu(), res[0][i].cpu(), RTOL, 'head-sliced ' + name)
+        x, gx = f.view(n, heads * dim), gout.view(n, heads * dim)
+        res = []
+        for sharded in (False, True, True):
+            xs = x.clone().requires_grad_(True)
+            th = _theta(r, 1, 7).to(DEV, torch.float32).requires_grad_(True)
+            nrm = RF.weighted_degree_norm(g, etv, th, 100.0, -0.5)
+            if sharded:
+                out = partition.feature_sliced_propagate(g, etv, xs, None, 100.0, nrm, bounds, 0, exchange=xch)
+            else:
+                out = RF.propagate(g, etv, xs, None, 100.0, nrm)
+            out.backward(gx)
+            res.append((out.detach().clone(), xs.grad.clone(), th.grad.clone()))
+        for k in (1, 2):
+            assert torch.equal(res[0][0], res[k][0]) and torch.equal(res[0][1], res[k][1])
+            helpers.assert_close(res[k][2].cpu(), res[0][2].cpu(), RTOL, 'un-weighted slabs d_theta')
+    finally:
+        dist.destroy_process_group()
+
+
 # ---- row-range (partitioned) kernel paths on one GPU: P virtual ranks, all-gather emulated by sharing buffers ----
 @pytest.mark.parametrize('parts,f', [(2, 128), (5, 128), (3, 64)])
 def test_row_partitioned_kernels_equal_full_run(parts, f):
