@@ -464,6 +464,7 @@ def run_ours(args, d):
     x_full = torch.randn(n, f, device=dev, generator=gen)
     g_full = torch.randn(n, f, device=dev, generator=gen)
 
+    xch = None
     if world == 1:
         args.partition = 'none'
         x = x_full.clone().requires_grad_(True)
@@ -650,6 +651,14 @@ def run_ours(args, d):
         except Exception as ex:   # report, do not hide (all ranks fail or succeed together: same code, same shapes)
             ns = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
 
+    # ---- the fused REGAT core on the same graph, sharded over the heads (N > 1, peer exchange, F = H*D = 128)
+    regat_sharded = None
+    if world > 1 and not args.no_others and args.partition == 'peer' and xch is not None and f == 128 and 8 % world == 0:
+        try:
+            regat_sharded = regat_sharded_measure(g, etv, dev, world, rank, bounds, xch, n, r, e, sync, barrier)
+        except Exception as ex:
+            regat_sharded = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -709,6 +718,8 @@ def run_ours(args, d):
             ns, n_gpus=world, scaling='weak',
             workload='BASELINE config 5: RE-GCN (MAG stack) neighbour-sampled minibatch training, 512 seeds per rank, '
                      'fan-out [25, 20], hidden 512, gradient all-reduce per step')
+    if regat_sharded is not None:
+        line.setdefault('others', {})['mag_regat_h8d16_head_sliced'] = regat_sharded
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'], _ = cpu_reference_sample(d, f, 3, 1)
     if world == 1 and not args.no_others:
@@ -721,6 +732,58 @@ def run_ours(args, d):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def regat_sharded_measure(g, etv, dev, world, rank, bounds, xch, n, r, e, sync, barrier, heads=8, dim=16, steps=10):
+    """The fused REGAT core (projection scores + logits + edge softmax + aggregation, forward + backward) on the same graph,
+    sharded over the attention heads across the ranks (partition.head_sliced_gat over peer memory: heads are independent
+    column slabs) next to the single-device layer on this rank: bit-equality of the rank's rows of the output and of the
+    feature gradient, parameter gradients to 5e-5, then both timed.  Collective: every rank calls it."""
+    import torch.distributed as dist
+    from re_gnn_b200 import functional as RF, partition
+    gen = torch.Generator(device=dev).manual_seed(4242)
+    f = torch.randn(n, heads, dim, device=dev, generator=gen) * 0.5
+    gout = torch.randn(n, heads, dim, device=dev, generator=gen)
+    al0 = torch.randn(1, heads, dim, device=dev, generator=gen) * 0.3
+    ar0 = torch.randn(1, heads, dim, device=dev, generator=gen) * 0.3
+    th0 = theta_init(r, heads).to(dev)
+    rb, re = bounds[rank], bounds[rank + 1]
+
+    def single():
+        leaves = [t.clone().requires_grad_(True) for t in (f, al0, ar0, th0)]
+        out, _ = RF.gat_layer(g, etv, *leaves, ALPHA, 0.2)
+        out.backward(gout)
+        return out.detach(), [t.grad for t in leaves]
+
+    def sharded():
+        mine = [f[rb:re].clone().requires_grad_(True)] + [t.clone().requires_grad_(True) for t in (al0, ar0, th0)]
+        out = partition.head_sliced_gat(g, etv, mine[0], mine[1], mine[2], mine[3], ALPHA, 0.2, bounds, rank, exchange=xch)
+        out.backward(gout[rb:re])
+        partition.allreduce_relation_grads(mine[1:])
+        return out.detach(), [t.grad for t in mine]
+
+    ref_out, ref_g = single()
+    out, grads = sharded()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))  # noqa: E731
+    prel = max(rel(grads[i], ref_g[i]) for i in (1, 2, 3))
+    chk = torch.tensor([int(torch.equal(out, ref_out[rb:re])), int(torch.equal(grads[0], ref_g[0][rb:re])), int(prel < 5e-5)],
+                       device=dev)
+    dist.all_reduce(chk, op=dist.ReduceOp.MIN)
+    pmax = torch.tensor([prel], device=dev, dtype=torch.float64)
+    dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+    del ref_out, ref_g, out, grads
+    t = torch.tensor([timed(single, steps, 3, sync, barrier), timed(sharded, steps, 3, sync, barrier)], device=dev,
+                     dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t1, tp = float(t[0].item()) / steps, float(t[1].item()) / steps
+    return {'gteps_fwd_bwd': e / tp / 1e9, 'ms': tp * 1e3, 'single_gpu_ms_same_boxes': t1 * 1e3, 'speedup_vs_one_gpu': t1 / tp,
+            'n_gpus': world, 'heads': heads, 'head_dim': dim, 'scaling': 'strong',
+            'how': 'heads sharded over the ranks (H/P heads x all rows per rank), row<->head-slab re-partition by '
+                   'regnn_rows_to_slabs / regnn_slabs_to_rows over NVLink peer memory, gradient all-gather of the '
+                   'attention vectors and the relation embedding included',
+            'parity_check': {'y_equal': bool(chk[0].item()), 'd_feat_equal': bool(chk[1].item()),
+                             'param_grad_max_rel_err': float(pmax.item()), 'param_grads_ok': bool(chk[2].item()),
+                             'against': 'the single-device RF.gat_layer on every rank, its rows compared bit for bit'}}
 
 
 def ns_measure(d, dev, world, rank, steps, warmup, sync, barrier):

@@ -1,14 +1,14 @@
-// Fused REGAT / REGATv2 kernels: edge logits + LeakyReLU + per-destination online softmax +
-// weighted aggregation in ONE pass over the in-edges of each destination row, and the two-pass
-// deterministic backward (destination-major, then source-major over the transposed view).
-// Reference call sites: layer/REGATConv.py:71-92, layer/REGATv2Conv.py:133-152 (DGL: gsddmm(add),
-// 4-kernel edge_softmax, broadcast gspmm; autograd: gspmm on the reverse graph + gsddmm(dot)).
+// Fused REGAT / REGATv2 kernels: edge logits + LeakyReLU + per-destination online softmax + weighted aggregation in
+// ONE pass over the in-edges of each destination row, and a deterministic backward that gathers every edge's row ONCE
+// (source-major over the transposed view, per-destination statistics from a streaming pre-pass) followed by streaming
+// reductions over per-slot scalars.
+// Reference call sites: layer/REGATConv.py:71-92, layer/REGATv2Conv.py:133-152 (DGL: gsddmm(add), 4-kernel
+// edge_softmax, broadcast gspmm; autograd: gspmm on the reverse graph + gsddmm(dot)).
 //
-// Mapping: one warp per destination row.  A row of H*D floats is split into 128-bit slices; lane l
-// owns slices l, l+32, ... (C per lane), so every gathered source row is read with fully coalesced
-// LDG.128.  Slice k of lane l belongs to head (4*(l+32k))/D.  Per-head dot products are reduced
-// with xor-shuffles inside the aligned group of D/4 lanes that covers a head.  Gather-bound: one
-// H*D*4-byte source row per edge (two in the GATv2 source-major backward pass).
+// Mapping (all hot kernels): a row of H*D floats is cut into slices of min(H*D, 128) floats; G = 4 / 8 / 16 / 32 lanes
+// own one (row, slice) item with a 128-bit chunk each, so a warp works on 32/G rows and every gathered row is read with
+// coalesced LDG.128; heads never straddle a slice, per-head dot products are compile-time butterflies over the D/4 lanes
+// of a head.  Rows come from the degree-sorted row list, long rows are cut into fragments (merged by finalize kernels).
 #include <type_traits>
 
 #include "common.cuh"
