@@ -29,22 +29,18 @@ struct AttnArgs {
   const float* er;         // GAT: er [N,H]
   float slope;
   const float* keep;       // [E,H] edge-id order or null
-  const float* out;
-  const float* rowmax;
-  const float* rowsum;
   const float* G;
   int H, D;
   int d_shift;             // log2(D) when D is a power of two (the common case), else -1: avoids integer divisions
   int hg_count;            // ceil(H*D / 128)
   int64_t row_begin, row_end;
-  float* o0;               // fwd: out      bwd_dst: a_csr     bwd_src: d_feat / d_fs
-  float* o1;               // fwd: rowmax   bwd_dst: dpre/dl   bwd_src: d_el
-  float* o2;               // fwd: rowsum   bwd_dst: d_er / d_fd
+  float* o0;               // fwd: out      gather pass: d_feat / d_fs
+  float* o1;               // fwd: rowmax   gather pass: d_el
+  float* o2;               // fwd: rowsum   gather pass: dpre / dl per slot    streaming passes: d_er / d_fd
   float* o3;               // fwd: attn_out
   double* partials;
-  int partial_stride;
-  const float* a_csr;      // bwd_src inputs
-  const float* d_csr;
+  const float* a_csr;      // REGATv2 backward: the saved logits (gather pass)
+  const float* d_csr;      // per-slot dpre / dl (streaming passes)
   // long-row fragments (regnn_rowsplit_t): items [0, nfrag) are fragments (padded to nfrag_pad in the
   // grid-mapped kernels); their partial results go to p0/p1/p2 and are merged by the finalize kernels
   const int32_t* frag_row;
@@ -61,38 +57,6 @@ struct AttnArgs {
   const float* attn_l;
   const int32_t* a_csr_eid;  // gat_bwd_edges with a dropout mask: CSR slot -> edge id
 };
-
-struct WorkItem {
-  int64_t v, fi;
-  int s0, len;
-  bool ok, frag, first;
-};
-
-// Item wi of a kernel whose first `nfrag_items` items are long-row fragments and the rest ordinary rows.
-__device__ __forceinline__ WorkItem decode_item(const AttnArgs& a, int64_t wi, int64_t nfrag_items) {
-  WorkItem w{0, wi, 0, 0, false, false, true};
-  if (wi < nfrag_items) {
-    w.frag = true;
-    if (wi < a.nfrag) {
-      w.v = a.frag_row[wi];
-      if (w.v >= a.row_begin && w.v < a.row_end) {
-        w.s0 = a.frag_begin[wi];
-        w.len = min(a.threshold, a.indptr[w.v + 1] - w.s0);
-        w.first = w.s0 == a.indptr[w.v];
-        w.ok = true;
-      }
-    }
-  } else {
-    w.v = a.row_begin + (wi - nfrag_items);
-    if (w.v < a.row_end) {
-      w.s0 = a.indptr[w.v];
-      w.len = a.indptr[w.v + 1] - w.s0;
-      w.ok = w.len <= a.threshold;  // longer rows are covered by fragments
-    }
-  }
-  return w;
-}
-
 
 __device__ __forceinline__ void load_rel_table(float* w_s, const AttnArgs& a) {
   if (a.etype != nullptr) {
@@ -1263,15 +1227,6 @@ static int head_groups(int H, int D) { return (H * D + 127) / 128; }
 
 // lanes per row slice of the row-group REGAT kernels: min(H*D, 128) floats in 128-bit chunks, rounded up to 4/8/16/32
 static int rg_lanes(int HD) { return HD > 64 ? 32 : (HD > 32 ? 16 : (HD > 16 ? 8 : 4)); }
-#define REGNN_DISPATCH_RG(KERNEL, GRID, SMEM)                                     \
-  do {                                                                            \
-    switch (rg_lanes(a.H * a.D)) {                                                \
-      case 4: REGNN_DISPATCH_C(KERNEL<4>, GRID, SMEM); break;                     \
-      case 8: REGNN_DISPATCH_C(KERNEL<8>, GRID, SMEM); break;                     \
-      case 16: REGNN_DISPATCH_C(KERNEL<16>, GRID, SMEM); break;                   \
-      default: REGNN_DISPATCH_C(KERNEL<32>, GRID, SMEM); break;                   \
-    }                                                                             \
-  } while (0)
 // work items (warps) of a row-group kernel over `rows` rows
 static int64_t rg_work(const AttnArgs& a, int64_t rows) {
   const int gpw = 32 / rg_lanes(a.H * a.D);
@@ -1287,20 +1242,6 @@ static void apply_order(AttnArgs& a, const int32_t* row_order, const regnn_rowsp
     a.n_order = rows - (a.nfrag > 0 ? split->num_long : 0);
   }
 }
-
-// kernels that reduce over the D/4 lanes of a head are compiled per lane count (fully unrolled butterflies)
-#define REGNN_DISPATCH_LPH(KERNEL, GRID, SMEM)                                          \
-  do {                                                                                  \
-    const int lph_ = a.D / 4 >= 32 ? 32 : a.D / 4;                                      \
-    switch (lph_) {                                                                     \
-      case 1: REGNN_DISPATCH_C(KERNEL<1>, GRID, SMEM); break;                           \
-      case 2: REGNN_DISPATCH_C(KERNEL<2>, GRID, SMEM); break;                           \
-      case 4: REGNN_DISPATCH_C(KERNEL<4>, GRID, SMEM); break;                           \
-      case 8: REGNN_DISPATCH_C(KERNEL<8>, GRID, SMEM); break;                           \
-      case 16: REGNN_DISPATCH_C(KERNEL<16>, GRID, SMEM); break;                         \
-      default: REGNN_DISPATCH_C(KERNEL<32>, GRID, SMEM); break;                         \
-    }                                                                                   \
-  } while (0)
 
 }  // namespace regnn
 
