@@ -510,6 +510,67 @@ gat_bwd_der_kernel(AttnArgs a, int HP) {
   *dst = acc;
 }
 
+// The two reductions above and below in ONE streaming pass over dpre (used when the layer has relation embeddings):
+// row sums d_er[v,h] as gat_bwd_der_kernel, and the relation bins of the same values, lane-local in shared memory
+// (lane = (item-in-warp, head): conflict-free), per-block double partials.  Persistent grid-stride loop over the items.
+// AttnArgs as gat_bwd_der_kernel + etype (CSR order), R, partials [gridDim.x][R*H].  Dynamic smem: [warps][R][32] floats
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gat_bwd_der_bins_kernel(AttnArgs a, int HP) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int H = a.H, R = a.R, hh = lane % HP, per = 32 / HP;
+  float* mybins = smem + (size_t)warp * R * 32 + lane;
+  for (int r = 0; r < R; ++r) mybins[r * 32] = 0.f;
+  const int64_t rows = a.row_end - a.row_begin;
+  const int64_t nitems = a.nfrag + rows;
+  for (int64_t it = (int64_t)blockIdx.x * kWarpsPerBlock + warp; it * per < nitems; it += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t vi = it * per + lane / HP;
+    if (vi >= nitems || hh >= H) continue;
+    int s0, s1;
+    float* dst;
+    if (vi < a.nfrag) {
+      const int64_t v = a.frag_row[vi];
+      if (v < a.row_begin || v >= a.row_end) continue;
+      s0 = a.frag_begin[vi];
+      s1 = s0 + min(a.threshold, a.indptr[v + 1] - s0);
+      dst = a.p1 + (size_t)vi * H + hh;
+    } else {
+      const int64_t v = a.row_begin + (vi - a.nfrag);
+      s0 = a.indptr[v];
+      s1 = a.indptr[v + 1];
+      if (s1 - s0 > a.threshold) continue;  // covered by fragments
+      dst = a.o2 + (size_t)v * H + hh;
+    }
+    const float* p = a.d_csr + (size_t)s0 * H + hh;
+    const uint8_t* tp = a.etype + s0;
+    float acc = 0.f;
+    int s = s0;
+    for (; s + 4 <= s1; s += 4, p += 4 * H, tp += 4) {
+      const float a0 = __ldg(p), a1 = __ldg(p + H), a2 = __ldg(p + 2 * H), a3 = __ldg(p + 3 * H);
+      const int t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
+      acc = (((acc + a0) + a1) + a2) + a3;
+      mybins[t0 * 32] += a0;
+      mybins[t1 * 32] += a1;
+      mybins[t2 * 32] += a2;
+      mybins[t3 * 32] += a3;
+    }
+    for (; s < s1; ++s, p += H, ++tp) {
+      const float a0 = __ldg(p);
+      acc += a0;
+      mybins[(int)__ldg(tp) * 32] += a0;
+    }
+    *dst = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R * H; i += blockDim.x) {
+    const int r = i / H, h2 = i % H;
+    double sum = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w)
+      for (int q = h2; q < 32; q += HP) sum += (double)smem[((size_t)w * R + r) * 32 + q];
+    a.partials[(size_t)blockIdx.x * R * H + i] = sum;
+  }
+}
+
 // Relation bins of dpre (rows of `pitch` floats, the first H used): pure streaming over [E,H] (+ the uint8 edge types), lane-local bins, per-block double partials.
 // A warp reads 32/HP slots x HP heads per load; 8 loads are issued before the (loop-carried) shared-memory updates.
 // Dynamic smem: [warps][R][32] floats
@@ -1406,6 +1467,22 @@ extern "C" int regnn_gat_bwd_reduce(const int32_t* indptr, const uint8_t* etype_
   const int per = 32 / HP;
   const int64_t items = a.nfrag + rows;
   const unsigned grid = (unsigned)((items + (int64_t)per * kWarpsPerBlock - 1) / ((int64_t)per * kWarpsPerBlock));
+#ifndef REGNN_GAT_REDUCE_FUSED
+#define REGNN_GAT_REDUCE_FUSED 1
+#endif
+  // d_er and the relation bins in one pass over dpre: 0.39 instead of 0.51 ms on the MAG graph (H8); on L2-resident
+  // graphs the two specialised kernels are a few microseconds faster (ACM H8 D64: 49 vs 58 us)
+  if (REGNN_GAT_REDUCE_FUSED && etype_csr != nullptr && rows >= 65536) {
+    const size_t smem = sizeof(float) * (size_t)kWarpsPerBlock * R * 32;
+    int rc = set_smem(gat_bwd_der_bins_kernel, smem);
+    if (rc != REGNN_OK) return rc;
+    a.etype = etype_csr; a.R = R; a.partials = partials;
+    const int nb = (int)min((int64_t)grid, (int64_t)148 * 16);
+    gat_bwd_der_bins_kernel<<<nb, kWarpsPerBlock * 32, smem, stream>>>(a, HP);
+    if (a.nfrag > 0) launch_rowsum(split, a.p1, num_heads, d_er, row_begin, row_end, stream);
+    launch_relation_grad_finalize(partials, nb, R * num_heads, R * num_heads, theta, alpha, d_theta, stream);
+    return check_launch("regnn_gat_bwd_reduce");
+  }
   gat_bwd_der_kernel<<<grid, kWarpsPerBlock * 32, 0, stream>>>(a, HP);
   if (a.nfrag > 0) launch_rowsum(split, a.p1, num_heads, d_er, row_begin, row_end, stream);
   if (etype_csr != nullptr) {

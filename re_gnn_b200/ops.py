@@ -335,7 +335,7 @@ def gat_bwd(csr, et_csr, et_t, theta, alpha, feat, el, er, slope, keep, out, row
                   _ptr(attn_l) if fold else None, sp_t, _ptr(ws_t), _ptr(row_order(csr, True)) if full else None, _stream())
         _lib.call('regnn_gat_bwd_reduce', _ptr(csr['indptr']), _ptr(et_csr) if r else None, _ptr(theta), float(alpha), r,
                   _ptr(dpre_csr), h, rb, re, _ptr(d_er), _ptr(partials), _ptr(d_theta), sp, _ptr(ws), _stream())
-        _lib.count_launches(3 + (2 if r else 0) + (3 if sp_t is not None else 0) + (sp is not None))
+        _lib.count_launches(3 + ((1 if re - rb >= 65536 else 2) if r else 0) + (3 if sp_t is not None else 0) + (sp is not None))
         d_al = d_ar = None
         if fold:
             d_al = torch.empty(h * d, dtype=torch.float32, device=dev)
