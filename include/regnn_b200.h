@@ -290,7 +290,8 @@ int regnn_gat_bwd_edges(const int32_t* indptr_t, const int32_t* indices_t, const
                         float* split_workspace /* num_frags * (H*D + 2*H) floats, or NULL */,
                         const int32_t* row_order_t, void* stream);
 
-/* regnn_gat_bwd_reduce: the destination-side reductions of dpre_csr, both pure streaming passes over [E,H]:
+/* regnn_gat_bwd_reduce: the destination-side reductions of dpre_csr, pure streaming over [E,H] (one fused pass when the
+ * row range is large, two specialised kernels on L2-resident graphs):
  *   d_er[v,h] = sum_{slots of row v} dpre_csr[slot,h]        d_theta[r,h] = alpha*LeakyReLU'(alpha*theta[r,h]) * sum_{etype=r} dpre
  * (deterministic: slot order per row; lane-local bins -> per-block double partials -> fixed-order finalize).
  * partials: double [regnn_max_partial_blocks() * R * H]; split_workspace: split->num_frags * H floats. */
