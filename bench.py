@@ -699,6 +699,29 @@ def run_ours(args, d):
                 'frac_compulsory': compulsory_bytes_spmm(rows_n, edges_n, fk) / tk / 1e9 / hbm,
                 'l2_resident': bool(n * fk * 4 <= 126 * 2 ** 20)}
 
+    # ---- the same for the kernel that is dominant BY TIME: the fused backward pass (gather + relation bins + folded
+    # norm gradient), timed alone; algorithmic bytes per DESIGN.md section 4: E*(4F+13) + N*(3*4F+8)
+    roofline_bwd = None
+    if world == 1:
+        try:
+            with torch.no_grad():
+                k()                                                       # y = the forward result of xs
+                gk = torch.randn(n, f, device=dev)
+                dxk = torch.empty(n, f, device=dev)
+
+                def kb():
+                    ops.spmm_bwd_fused(csr, etv[1], theta.detach(), ALPHA, nrm, xs, gk, out=dxk, y=y, want_dnorm=True)
+                tb = timed(kb, 20, 5, sync) / 20
+                del gk, dxk
+            alg_b = e * (4 * f + 13) + n * (3 * 4 * f + 8)
+            roofline_bwd = {'bound': 'hbm', 'kernel': 'regnn::spmm_rowgroup_kernel<true,32,true> (fused backward launch: dX, '
+                                                      'relation bins, folded norm gradient; + its finalize kernels)',
+                            'achieved': alg_b / tb / 1e9, 'peak': hbm, 'peak_source': how, 'unit': 'GB/s',
+                            'frac': alg_b / tb / 1e9 / hbm, 'traffic': None, 'algorithmic_bytes_per_launch': int(alg_b),
+                            'launch_ms': tb * 1e3}
+        except Exception as ex:   # never lose the line over the companion measurement
+            roofline_bwd = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
+
     line = {
         'metric': 'GTEPS fwd+bwd per RE-layer', 'value': value, 'unit': 'GTEPS', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
@@ -711,6 +734,8 @@ def run_ours(args, d):
                                        'max over ranks per phase; (gaps) = step time outside them (launch gaps, autograd, '
                                        'torch glue); the timed region itself runs without these events'),
     }
+    if roofline_bwd is not None:
+        line['roofline_backward'] = roofline_bwd
     if world > 1:
         line['parity_check'] = parity_check
     if ns is not None:
